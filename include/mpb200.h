@@ -1,0 +1,133 @@
+/* mpb200.h -- C ABI of libmpb200.so: the B200 (sm_100a) kernels behind the Gbase volumetric forward path.
+ *
+ * The reference (johndpope/MegaPortrait-hack, model.py) has no native code and no FFI: every operator on its hot
+ * path is a PyTorch ATen call.  The entry points below are therefore what a ctypes binding of that path binds
+ * (INTEGRATION.md shows the stub); each one names the reference call site (model.py:line) it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - every call is asynchronous and stream-ordered on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation, no default-stream use, no allocation except the per-process TMA-descriptor encoder lookup;
+ *   - return value 0 = success; non-zero = error, text available from mp_last_error() (thread-local);
+ *     never throws, never exits;
+ *   - "NCDHW" = the reference's contiguous fp32 layout; "CL" = channels-last [N, D, H, W, C] (2-D tensors use D=1);
+ *   - "split" = a pair of bf16 planes (hi, lo) with x ~= hi + lo (16 mantissa bits): the operand format of the
+ *     3-pass bf16 tensor-core convolution.
+ */
+#ifndef MPB200_H
+#define MPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPB200_ABI_VERSION 1
+
+/* activation codes shared by several entry points */
+enum { MP_ACT_NONE = 0, MP_ACT_RELU = 1, MP_ACT_RELU_TANH = 2, MP_ACT_SIGMOID = 3 };
+
+int mp_abi_version(void);
+const char* mp_last_error(void);
+/* 1 if the current device is sm_100 (tcgen05/TMA kernels usable), 0 otherwise, <0 on error. */
+int mp_device_supported(void);
+
+/* ---------------------------------------------------------------- layout ------------------------------------ */
+/* NCDHW fp32 -> CL.  Any of out_f32 / (out_hi,out_lo) may be NULL.  S = D*H*W.  (boundary of every module) */
+int mp_nchw_to_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, int N, int C, int64_t S, void* stream);
+/* CL -> NCDHW fp32; source is in_f32 if non-NULL else the split pair. */
+int mp_cl_to_nchw(const float* in_f32, const void* in_hi, const void* in_lo, float* out, int N, int C, int64_t S,
+                  void* stream);
+/* fp32 -> split planes, elementwise (n elements). */
+int mp_split(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream);
+
+/* AvgPool2d(2,2) / AvgPool3d(2,2) on CL fp32 (model.py:231, 576-580).  pool_d = 1 for 2-D. */
+int mp_avgpool2_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, int N, int D, int H, int W, int C,
+                   int pool_d, void* stream);
+/* nn.Upsample(scale 2, 'trilinear'|'bilinear', align_corners=True) on CL (model.py:585-589, 733-743).
+ * up_d = 1 keeps D (2-D bilinear).  Source: in_f32 if non-NULL else split.  Either output may be NULL. */
+int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out_f32, void* out_hi,
+                            void* out_lo, int N, int D, int H, int W, int C, int up_d, void* stream);
+/* nn.Upsample(scale_factor=(sd,sh,sw)) nearest on CL fp32 (model.py:427-433). */
+int mp_upsample_nearest_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, int N, int D, int H, int W,
+                           int C, int sd, int sh, int sw, void* stream);
+
+/* ---------------------------------------------------------------- normalisation ----------------------------- */
+/* Accumulate per-(sample, group) sum and sum-of-squares of a CL fp32 tensor into stats[N][G][2] (double, must be
+ * zeroed by the caller; mp_conv can accumulate the same statistics in its epilogue).  (F.group_norm, model.py:116) */
+int mp_gn_stats(const float* x, double* stats, int N, int64_t S, int C, int G, void* stream);
+/* stats -> per-(sample, channel) scale/shift ab[N][C][2] such that GN(x)*g2+b2 == x*a + b.
+ * gamma/beta (GroupNorm affine) and gamma2/beta2 (AdaptiveGroupNorm's second affine, model.py:314-316) may be NULL. */
+int mp_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* gamma2,
+                   const float* beta2, float* ab, int N, int64_t S, int C, int G, float eps, void* stream);
+/* out = act(x * a[n,c] + b[n,c] + residual) on CL.  ab may be NULL (identity); residual is res_f32, else the split
+ * pair, else none.  Outputs: out_f32 and/or split, either may be NULL.  x may alias out_f32. */
+int mp_affine_act_cl(const float* x, const float* ab, const float* res_f32, const void* res_hi, const void* res_lo,
+                     float* out_f32, void* out_hi, void* out_lo, int N, int64_t S, int C, int act, void* stream);
+
+/* ---------------------------------------------------------------- convolution ------------------------------- */
+typedef struct mp_conv_desc {
+  /* input activation, split CL [N, D, H, W, Cin] */
+  const void* in_hi;
+  const void* in_lo;
+  /* packed weights, split, K-major: [Cout_pad][taps*Cin], tap index = (kd*KH + kh)*KW + kw, cin fastest */
+  const void* w_hi;
+  const void* w_lo;
+  const float* bias;      /* [Cout] or NULL */
+  /* optional residual added before the activation, CL [N, D, H, W, Cout] */
+  const float* res_f32;
+  const void* res_hi;
+  const void* res_lo;
+  /* outputs, CL [N, D, H, W, Cout]; any may be NULL */
+  float* out_f32;
+  void* out_hi;
+  void* out_lo;
+  double* stats;          /* [N][gn_groups][2] accumulated over the written values, or NULL */
+  int N, D, H, W, Cin, Cout;
+  int KD, KH, KW;         /* odd, "same" padding, stride 1 (nn.Conv2d/3d(k, padding=k//2), model.py:95-107,374-375) */
+  int Cout_pad;           /* rows in the packed weight matrix (>= Cout, multiple of 16) */
+  int gn_groups;
+  int act;                /* MP_ACT_* applied after bias + residual */
+} mp_conv_desc;
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores fed by TMA (3-pass split-bf16, fp32 accumulate in TMEM).
+ * Requires Cin % 16 == 0 and a 128-position output tile that is a box of the (D,H,W) grid. */
+int mp_conv_tc(const mp_conv_desc* desc, void* stream);
+/* Same contract on CUDA cores (fp32 FMA): odd shapes (Cin=3 stem, Cout=3 heads, the FlowField tower) and the
+ * on-device cross-check of mp_conv_tc. */
+int mp_conv_simt(const mp_conv_desc* desc, void* stream);
+/* 1 if mp_conv_tc accepts the shape. */
+int mp_conv_tc_supported(const mp_conv_desc* desc);
+
+/* ---------------------------------------------------------------- warping ----------------------------------- */
+/* F.grid_sample(v, grid, 'bilinear', 'border', align_corners=True) for 5-D input (model.py:1062).
+ * v [N,C,D,H,W], grid [N,Do,Ho,Wo,3] (x,y,z in [-1,1]), out [N,C,Do,Ho,Wo], all fp32 NCDHW. */
+int mp_grid_sample3d(const float* v, const float* grid, float* out, int N, int C, int D, int H, int W, int Do,
+                     int Ho, int Wo, void* stream);
+/* apply_warping_field(v, warp_field) (model.py:1028-1065) in the reference layout: v [N,C,D,H,W],
+ * warp_field [N,3,Df,Hf,Wf] -> out [N,C,D,H,W]; the flow resample, identity grid, the reference's
+ * re-normalisation and the trilinear border gather run in one kernel. */
+int mp_apply_warping_field(const float* v, const float* warp_field, float* out, int N, int C, int D, int H, int W,
+                           int Df, int Hf, int Wf, void* stream);
+/* WarpGenerator tail (model.py:965-973): 64^3 field = affine_grid(theta[N,3,4], align_corners=False) +
+ * trilinear(em 16^3 -> 64^3, align_corners=False).  em is CL [N,E,E,E,3]; out is NCDHW [N,3,G,G,G]. */
+int mp_warp_field(const float* em_cl, const float* theta, float* out, int N, int E, int G, void* stream);
+/* Fused pipeline warp on CL volumes: grid built on the fly from em (CL [N,E,E,E,3]) + theta[N,3,4] exactly as
+ * mp_warp_field + mp_apply_warping_field would, then the trilinear gather of v (CL fp32 [Nv,D,H,W,C], Nv = 1 or N:
+ * one source volume may serve the whole driver batch).  sum_d = 0: out is CL [N,D,H,W,C];
+ * sum_d = 1: torch.sum(dim=2) is fused (model.py:1171) and out is CL [N,1,H,W,C].  Outputs fp32 and/or split. */
+int mp_warp_fused_cl(const float* v, const float* em_cl, const float* theta, float* out_f32, void* out_hi,
+                     void* out_lo, int N, int Nv, int C, int D, int H, int W, int E, int G, int sum_d, void* stream);
+
+/* ---------------------------------------------------------------- image pyramid ----------------------------- */
+/* AntiAliasInterpolation2d (model.py:683-691): zero-pad, depthwise ks x ks filter, nearest subsample by `step`.
+ * x [N,C,H,W] fp32 NCHW, kernel [ks*ks] (same for every channel), out [N,C,H/step,W/step]. */
+int mp_blur_subsample(const float* x, const float* kernel, float* out, int N, int C, int H, int W, int ks, int step,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPB200_H */

@@ -1,0 +1,61 @@
+// Shared helpers for libmpb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mpb200.h"
+
+int mp_set_error(const char* fmt, ...);
+
+#define MP_REQUIRE(cond, ...)                  \
+  do {                                         \
+    if (!(cond)) return mp_set_error(__VA_ARGS__); \
+  } while (0)
+
+#define MP_LAUNCH_CHECK(name)                                                          \
+  do {                                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess) return mp_set_error("%s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline cudaStream_t mp_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+typedef __nv_bfloat16 bf16;
+
+// x ~= hi + lo with 16 mantissa bits in total (both round-to-nearest-even).
+__device__ __forceinline__ void mp_split2(float x, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ float mp_join(bf16 hi, bf16 lo) { return __bfloat162float(hi) + __bfloat162float(lo); }
+
+__device__ __forceinline__ float mp_apply_act(float v, int act) {
+  switch (act) {
+    case MP_ACT_RELU: return fmaxf(v, 0.f);
+    case MP_ACT_RELU_TANH: return tanhf(fmaxf(v, 0.f));
+    case MP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// 4 consecutive channels <-> 8-byte bf16x4 vectors
+struct __align__(8) bf16x4 {
+  bf16 v[4];
+};
+
+__device__ __forceinline__ void mp_store_split4(bf16* hi, bf16* lo, int64_t idx, float4 v) {
+  bf16x4 h, l;
+  mp_split2(v.x, h.v[0], l.v[0]);
+  mp_split2(v.y, h.v[1], l.v[1]);
+  mp_split2(v.z, h.v[2], l.v[2]);
+  mp_split2(v.w, h.v[3], l.v[3]);
+  *reinterpret_cast<bf16x4*>(hi + idx) = h;
+  *reinterpret_cast<bf16x4*>(lo + idx) = l;
+}
+__device__ __forceinline__ float4 mp_load_split4(const bf16* hi, const bf16* lo, int64_t idx) {
+  bf16x4 h = *reinterpret_cast<const bf16x4*>(hi + idx);
+  bf16x4 l = *reinterpret_cast<const bf16x4*>(lo + idx);
+  return make_float4(mp_join(h.v[0], l.v[0]), mp_join(h.v[1], l.v[1]), mp_join(h.v[2], l.v[2]),
+                     mp_join(h.v[3], l.v[3]));
+}

@@ -1,0 +1,319 @@
+// Layout conversion, pooling and resampling kernels on channels-last (CL) tensors.  All are HBM-bound:
+// one read + one write per element, float4 / bf16x4 vector accesses along the channel axis.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors / misc
+static thread_local char g_err[512] = "";
+
+int mp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+extern "C" const char* mp_last_error(void) { return g_err; }
+extern "C" int mp_abi_version(void) { return MPB200_ABI_VERSION; }
+extern "C" int mp_device_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+  return major == 10 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ NCDHW <-> CL
+// in [N][C][S] -> out [N][S][C]; 32x32 tile through shared memory, coalesced on both sides.
+__global__ void k_nchw_to_cl(const float* __restrict__ in, float* __restrict__ out_f32, bf16* __restrict__ out_hi,
+                             bf16* __restrict__ out_lo, int C, int64_t S) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* src = in + (int64_t)n * C * S;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j;
+    int64_t s = s0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && s < S) ? src[(int64_t)c * S + s] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t s = s0 + j;
+    int c = c0 + threadIdx.x;
+    if (s < S && c < C) {
+      float v = tile[threadIdx.x][j];
+      int64_t o = ((int64_t)n * S + s) * C + c;
+      if (out_f32) out_f32[o] = v;
+      if (out_hi) {
+        bf16 h, l;
+        mp_split2(v, h, l);
+        out_hi[o] = h;
+        out_lo[o] = l;
+      }
+    }
+  }
+}
+
+extern "C" int mp_nchw_to_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, int N, int C, int64_t S,
+                             void* stream) {
+  MP_REQUIRE(in && (out_f32 || (out_hi && out_lo)), "mp_nchw_to_cl: null pointer");
+  MP_REQUIRE(N > 0 && C > 0 && S > 0 && N <= 65535, "mp_nchw_to_cl: bad dims");
+  dim3 grid((unsigned)((S + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  k_nchw_to_cl<<<grid, block, 0, mp_stream(stream)>>>(in, out_f32, (bf16*)out_hi, (bf16*)out_lo, C, S);
+  MP_LAUNCH_CHECK("mp_nchw_to_cl");
+  return 0;
+}
+
+__global__ void k_cl_to_nchw(const float* __restrict__ in_f32, const bf16* __restrict__ in_hi,
+                             const bf16* __restrict__ in_lo, float* __restrict__ out, int C, int64_t S) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t s = s0 + j;
+    int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (s < S && c < C) {
+      int64_t o = ((int64_t)n * S + s) * C + c;
+      v = in_f32 ? in_f32[o] : mp_join(in_hi[o], in_lo[o]);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  float* dst = out + (int64_t)n * C * S;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j;
+    int64_t s = s0 + threadIdx.x;
+    if (c < C && s < S) dst[(int64_t)c * S + s] = tile[threadIdx.x][j];
+  }
+}
+
+extern "C" int mp_cl_to_nchw(const float* in_f32, const void* in_hi, const void* in_lo, float* out, int N, int C,
+                             int64_t S, void* stream) {
+  MP_REQUIRE(out && (in_f32 || (in_hi && in_lo)), "mp_cl_to_nchw: null pointer");
+  MP_REQUIRE(N > 0 && C > 0 && S > 0 && N <= 65535, "mp_cl_to_nchw: bad dims");
+  dim3 grid((unsigned)((S + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  k_cl_to_nchw<<<grid, block, 0, mp_stream(stream)>>>(in_f32, (const bf16*)in_hi, (const bf16*)in_lo, out, C, S);
+  MP_LAUNCH_CHECK("mp_cl_to_nchw");
+  return 0;
+}
+
+__global__ void k_split(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(in + i);
+    mp_store_split4(hi, lo, i, v);
+  } else {
+    for (; i < n; ++i) mp_split2(in[i], hi[i], lo[i]);
+  }
+}
+
+extern "C" int mp_split(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream) {
+  MP_REQUIRE(in && out_hi && out_lo && n > 0, "mp_split: bad args");
+  int64_t q = (n + 3) / 4;
+  k_split<<<(unsigned)((q + 255) / 256), 256, 0, mp_stream(stream)>>>(in, (bf16*)out_hi, (bf16*)out_lo, n);
+  MP_LAUNCH_CHECK("mp_split");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ AvgPool(2)
+// One thread = one output position x 4 channels.
+__global__ void k_avgpool2_cl(const float* __restrict__ in, float* __restrict__ out_f32, bf16* __restrict__ out_hi,
+                              bf16* __restrict__ out_lo, int N, int D, int H, int W, int C, int pd) {
+  const int C4 = C >> 2;
+  const int Do = D / pd, Ho = H >> 1, Wo = W >> 1;
+  int64_t total = (int64_t)N * Do * Ho * Wo * C4;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int c4 = (int)(t % C4);
+  int64_t p = t / C4;
+  int wo = (int)(p % Wo); p /= Wo;
+  int ho = (int)(p % Ho); p /= Ho;
+  int d_o = (int)(p % Do);
+  int n = (int)(p / Do);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int dd = 0; dd < pd; ++dd)
+    for (int hh = 0; hh < 2; ++hh)
+      for (int ww = 0; ww < 2; ++ww) {
+        int64_t idx = ((((int64_t)n * D + (d_o * pd + dd)) * H + (ho * 2 + hh)) * W + (wo * 2 + ww)) * C + c4 * 4;
+        float4 v = *reinterpret_cast<const float4*>(in + idx);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+  const float inv = 1.f / (4.f * pd);
+  acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+  int64_t o = t * 4;
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = acc;
+  if (out_hi) mp_store_split4(out_hi, out_lo, o, acc);
+}
+
+extern "C" int mp_avgpool2_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, int N, int D, int H,
+                              int W, int C, int pool_d, void* stream) {
+  MP_REQUIRE(in && (out_f32 || (out_hi && out_lo)), "mp_avgpool2_cl: null pointer");
+  MP_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0 && (pool_d == 1 || (pool_d == 2 && D % 2 == 0)),
+             "mp_avgpool2_cl: bad dims C=%d D=%d H=%d W=%d pool_d=%d", C, D, H, W, pool_d);
+  int64_t total = (int64_t)N * (D / pool_d) * (H / 2) * (W / 2) * (C / 4);
+  k_avgpool2_cl<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(in, out_f32, (bf16*)out_hi,
+                                                                                (bf16*)out_lo, N, D, H, W, C, pool_d);
+  MP_LAUNCH_CHECK("mp_avgpool2_cl");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ linear x2, ac=True
+// ATen's align_corners=True rule (UpSample.h area_pixel_compute_scale / compute_source_index):
+//   scale = (in-1)/(out-1) (float), src = scale * dst, i0 = (int)src, l1 = src - i0, i1 = i0 + (i0 < in-1).
+__device__ __forceinline__ void lin_src(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+  if (out_size <= 1 || in_size == out_size) {
+    i0 = i1 = dst;
+    l1 = 0.f;
+    if (in_size != out_size) i0 = i1 = 0;
+    return;
+  }
+  float scale = (float)(in_size - 1) / (float)(out_size - 1);
+  float src = scale * (float)dst;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+template <bool SPLIT_IN>
+__global__ void k_upsample2x_linear_cl(const float* __restrict__ in_f32, const bf16* __restrict__ in_hi,
+                                       const bf16* __restrict__ in_lo, float* __restrict__ out_f32,
+                                       bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int N, int D, int H,
+                                       int W, int C, int ud) {
+  const int C4 = C >> 2;
+  const int Do = D * ud, Ho = H * 2, Wo = W * 2;
+  int64_t total = (int64_t)N * Do * Ho * Wo * C4;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int c4 = (int)(t % C4);
+  int64_t p = t / C4;
+  int wo = (int)(p % Wo); p /= Wo;
+  int ho = (int)(p % Ho); p /= Ho;
+  int d_o = (int)(p % Do);
+  int n = (int)(p / Do);
+  int d0, d1, h0, h1, w0, w1;
+  float ld, lh, lw;
+  lin_src(d_o, D, Do, d0, d1, ld);
+  lin_src(ho, H, Ho, h0, h1, lh);
+  lin_src(wo, W, Wo, w0, w1, lw);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    if (a == 1 && ud == 1) break;
+    float wd = (ud == 1) ? 1.f : (a ? ld : 1.f - ld);
+    int dz = a ? d1 : d0;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      float wh = b ? lh : 1.f - lh;
+      int hy = b ? h1 : h0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float ww = c ? lw : 1.f - lw;
+        int wx = c ? w1 : w0;
+        int64_t idx = ((((int64_t)n * D + dz) * H + hy) * W + wx) * C + c4 * 4;
+        float4 v;
+        if (SPLIT_IN) v = mp_load_split4(in_hi, in_lo, idx);
+        else v = *reinterpret_cast<const float4*>(in_f32 + idx);
+        // ATen accumulates w_d*w_h*w_w * v (UpSampleKernel.cpp / upsample_trilinear3d)
+        float wgt = wd * wh * ww;
+        acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+      }
+    }
+  }
+  int64_t o = t * 4;
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = acc;
+  if (out_hi) mp_store_split4(out_hi, out_lo, o, acc);
+}
+
+extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out_f32,
+                                       void* out_hi, void* out_lo, int N, int D, int H, int W, int C, int up_d,
+                                       void* stream) {
+  MP_REQUIRE((in_f32 || (in_hi && in_lo)) && (out_f32 || (out_hi && out_lo)), "mp_upsample2x_linear_cl: null pointer");
+  MP_REQUIRE(C % 4 == 0 && (up_d == 1 || up_d == 2), "mp_upsample2x_linear_cl: bad dims");
+  int64_t total = (int64_t)N * D * up_d * H * 2 * W * 2 * (C / 4);
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (in_f32)
+    k_upsample2x_linear_cl<false><<<grid, 256, 0, mp_stream(stream)>>>(in_f32, nullptr, nullptr, out_f32,
+                                                                       (bf16*)out_hi, (bf16*)out_lo, N, D, H, W, C, up_d);
+  else
+    k_upsample2x_linear_cl<true><<<grid, 256, 0, mp_stream(stream)>>>(nullptr, (const bf16*)in_hi, (const bf16*)in_lo,
+                                                                      out_f32, (bf16*)out_hi, (bf16*)out_lo, N, D, H, W,
+                                                                      C, up_d);
+  MP_LAUNCH_CHECK("mp_upsample2x_linear_cl");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ nearest
+__global__ void k_upsample_nearest_cl(const float* __restrict__ in, float* __restrict__ out_f32,
+                                      bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int N, int D, int H, int W,
+                                      int C, int sd, int sh, int sw) {
+  const int C4 = C >> 2;
+  const int Do = D * sd, Ho = H * sh, Wo = W * sw;
+  int64_t total = (int64_t)N * Do * Ho * Wo * C4;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int c4 = (int)(t % C4);
+  int64_t p = t / C4;
+  int wo = (int)(p % Wo); p /= Wo;
+  int ho = (int)(p % Ho); p /= Ho;
+  int d_o = (int)(p % Do);
+  int n = (int)(p / Do);
+  int64_t idx = ((((int64_t)n * D + d_o / sd) * H + ho / sh) * W + wo / sw) * C + c4 * 4;
+  float4 v = *reinterpret_cast<const float4*>(in + idx);
+  int64_t o = t * 4;
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
+  if (out_hi) mp_store_split4(out_hi, out_lo, o, v);
+}
+
+extern "C" int mp_upsample_nearest_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, int N, int D,
+                                      int H, int W, int C, int sd, int sh, int sw, void* stream) {
+  MP_REQUIRE(in && (out_f32 || (out_hi && out_lo)), "mp_upsample_nearest_cl: null pointer");
+  MP_REQUIRE(C % 4 == 0 && sd >= 1 && sh >= 1 && sw >= 1, "mp_upsample_nearest_cl: bad dims");
+  int64_t total = (int64_t)N * D * sd * H * sh * W * sw * (C / 4);
+  k_upsample_nearest_cl<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(
+      in, out_f32, (bf16*)out_hi, (bf16*)out_lo, N, D, H, W, C, sd, sh, sw);
+  MP_LAUNCH_CHECK("mp_upsample_nearest_cl");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ image pyramid
+__global__ void k_blur_subsample(const float* __restrict__ x, const float* __restrict__ kern, float* __restrict__ out,
+                                 int NC, int H, int W, int ks, int step) {
+  const int Ho = H / step, Wo = W / step;
+  int64_t total = (int64_t)NC * Ho * Wo;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int wo = (int)(t % Wo);
+  int ho = (int)((t / Wo) % Ho);
+  int nc = (int)(t / ((int64_t)Wo * Ho));
+  const int ka = ks / 2;
+  const float* src = x + (int64_t)nc * H * W;
+  float acc = 0.f;
+  for (int i = 0; i < ks; ++i) {
+    int y = ho * step + i - ka;
+    if (y < 0 || y >= H) continue;
+    for (int j = 0; j < ks; ++j) {
+      int xx = wo * step + j - ka;
+      if (xx < 0 || xx >= W) continue;
+      acc += src[(int64_t)y * W + xx] * kern[i * ks + j];
+    }
+  }
+  out[t] = acc;
+}
+
+extern "C" int mp_blur_subsample(const float* x, const float* kernel, float* out, int N, int C, int H, int W, int ks,
+                                 int step, void* stream) {
+  MP_REQUIRE(x && kernel && out, "mp_blur_subsample: null pointer");
+  MP_REQUIRE(ks % 2 == 1 && step >= 1 && H % step == 0 && W % step == 0, "mp_blur_subsample: bad dims");
+  int64_t total = (int64_t)N * C * (H / step) * (W / step);
+  k_blur_subsample<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(x, kernel, out, N * C, H, W, ks,
+                                                                                   step);
+  MP_LAUNCH_CHECK("mp_blur_subsample");
+  return 0;
+}

@@ -1,0 +1,341 @@
+// Trilinear warping kernels (memory-bound gathers, no tensor cores).
+//
+//   mp_grid_sample3d        F.grid_sample(5-D, bilinear, border, align_corners=True)           model.py:1062
+//   mp_apply_warping_field  apply_warping_field(v, warp_field) in the reference NCDHW layout    model.py:1028-1065
+//   mp_warp_field           compute_rt_warp + F.interpolate(w_em, 64^3) + add                   model.py:965-973
+//   mp_warp_fused_cl        the pipeline's fused form on channels-last volumes (+ optional sum over D, :1171)
+//
+// Coordinate arithmetic follows ATen (GridSampler.h:27-36,58-60; UpSample.h area_pixel_compute_source_index;
+// RangeFactories linspace) operation by operation so that results agree with the CPU oracle to ~1e-6.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------ shared math
+struct Taps {
+  int off[8];    // element offsets inside one (sample, channel) volume, or -1 when skipped
+  float w[8];
+};
+
+// pix coordinates are already clamped to [0, size-1] (padding_mode='border')
+__device__ __forceinline__ void make_taps(float ix, float iy, float iz, int D, int H, int W, Taps& t) {
+  float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  float tx = ix - fx, ty = iy - fy, tz = iz - fz;   // weight of the +1 corner
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+    int x = x0 + dx, y = y0 + dy, z = z0 + dz;
+    float w = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+    bool ok = x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D;   // within_bounds_3d
+    t.off[k] = ok ? (z * H + y) * W + x : -1;
+    t.w[k] = ok ? w : 0.f;
+  }
+}
+
+__device__ __forceinline__ float unnormalize_clip(float g, int size) {
+  float p = ((g + 1.f) / 2.f) * (float)(size - 1);            // grid_sampler_unnormalize, align_corners=True
+  return fminf((float)(size - 1), fmaxf(p, 0.f));            // clip_coordinates
+}
+
+// torch.linspace(-1, 1, steps)[i] (RangeFactories: symmetric evaluation around the midpoint)
+__device__ __forceinline__ float linspace_m1_1(int i, int steps) {
+  if (steps == 1) return -1.f;
+  float step = 2.f / (float)(steps - 1);
+  return (i < steps / 2) ? (-1.f + step * (float)i) : (1.f - step * (float)(steps - i - 1));
+}
+
+// align_corners=True source index (UpSample.h)
+__device__ __forceinline__ void src_ac_true(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+  float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  float src = scale * (float)dst;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+// align_corners=False source index (UpSample.h: scale*(dst+0.5)-0.5 clamped at 0)
+__device__ __forceinline__ void src_ac_false(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+  float scale = (float)in_size / (float)out_size;
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+// ------------------------------------------------------------------------------------------------ NCDHW gather
+// One thread = one output voxel (x fastest => coalesced grid reads and output writes) x a chunk of channels.
+constexpr int GS_CCHUNK = 8;
+
+__device__ __forceinline__ void gather_channels(const float* __restrict__ v, float* __restrict__ out, const Taps& t,
+                                                int c0, int c1, int64_t in_cs, int64_t out_cs) {
+  for (int c = c0; c < c1; ++c) {
+    const float* p = v + (int64_t)c * in_cs;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (t.off[k] >= 0) acc = fmaf(__ldg(p + t.off[k]), t.w[k], acc);
+    out[(int64_t)c * out_cs] = acc;
+  }
+}
+
+__global__ void k_grid_sample3d(const float* __restrict__ v, const float* __restrict__ grid, float* __restrict__ out,
+                                int C, int D, int H, int W, int64_t So) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= So) return;
+  const int n = blockIdx.z;
+  const float* g = grid + ((int64_t)n * So + s) * 3;
+  float ix = unnormalize_clip(g[0], W), iy = unnormalize_clip(g[1], H), iz = unnormalize_clip(g[2], D);
+  Taps t;
+  make_taps(ix, iy, iz, D, H, W, t);
+  int c0 = blockIdx.y * GS_CCHUNK, c1 = min(C, c0 + GS_CCHUNK);
+  int64_t in_cs = (int64_t)D * H * W;
+  gather_channels(v + (int64_t)n * C * in_cs, out + (int64_t)n * C * So + s, t, c0, c1, in_cs, So);
+}
+
+extern "C" int mp_grid_sample3d(const float* v, const float* grid, float* out, int N, int C, int D, int H, int W,
+                                int Do, int Ho, int Wo, void* stream) {
+  MP_REQUIRE(v && grid && out, "mp_grid_sample3d: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && C > 0 && D > 0 && H > 0 && W > 0 && Do > 0 && Ho > 0 && Wo > 0,
+             "mp_grid_sample3d: bad dims");
+  int64_t So = (int64_t)Do * Ho * Wo;
+  dim3 g((unsigned)((So + 127) / 128), (C + GS_CCHUNK - 1) / GS_CCHUNK, N);
+  k_grid_sample3d<<<g, 128, 0, mp_stream(stream)>>>(v, grid, out, C, D, H, W, So);
+  MP_LAUNCH_CHECK("mp_grid_sample3d");
+  return 0;
+}
+
+// flow value of channel k at output voxel (d,h,w): trilinear align_corners=True resample of wf [3,Df,Hf,Wf]
+__device__ __forceinline__ float resample_flow(const float* __restrict__ wf, int Df, int Hf, int Wf, int d0, int d1,
+                                               float ld, int h0, int h1, float lh, int w0, int w1, float lw) {
+  auto at = [&](int z, int y, int x) { return __ldg(wf + ((int64_t)z * Hf + y) * Wf + x); };
+  float a = (1.f - lh) * ((1.f - lw) * at(d0, h0, w0) + lw * at(d0, h0, w1)) +
+            lh * ((1.f - lw) * at(d0, h1, w0) + lw * at(d0, h1, w1));
+  float b = (1.f - lh) * ((1.f - lw) * at(d1, h0, w0) + lw * at(d1, h0, w1)) +
+            lh * ((1.f - lw) * at(d1, h1, w0) + lw * at(d1, h1, w1));
+  return (1.f - ld) * a + ld * b;
+}
+
+__global__ void k_apply_warping_field(const float* __restrict__ v, const float* __restrict__ wf,
+                                      float* __restrict__ out, int C, int D, int H, int W, int Df, int Hf, int Wf) {
+  const int64_t S = (int64_t)D * H * W;
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int n = blockIdx.z;
+  int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+  int d0, d1, h0, h1, w0, w1;
+  float ld, lh, lw;
+  src_ac_true(d, Df, D, d0, d1, ld);
+  src_ac_true(h, Hf, H, h0, h1, lh);
+  src_ac_true(w, Wf, W, w0, w1, lw);
+  const int64_t fs = (int64_t)Df * Hf * Wf;
+  const float* f = wf + (int64_t)n * 3 * fs;
+  float fx = resample_flow(f, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+  float fy = resample_flow(f + fs, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+  float fz = resample_flow(f + 2 * fs, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+  // grid + flow, then the reference's "2*g/(size-1) - 1" (model.py:1052-1058), then ATen's un-normalisation
+  float gx = 2.0f * (linspace_m1_1(w, W) + fx) / (float)(W - 1) - 1.0f;
+  float gy = 2.0f * (linspace_m1_1(h, H) + fy) / (float)(H - 1) - 1.0f;
+  float gz = 2.0f * (linspace_m1_1(d, D) + fz) / (float)(D - 1) - 1.0f;
+  Taps t;
+  make_taps(unnormalize_clip(gx, W), unnormalize_clip(gy, H), unnormalize_clip(gz, D), D, H, W, t);
+  int c0 = blockIdx.y * GS_CCHUNK, c1 = min(C, c0 + GS_CCHUNK);
+  gather_channels(v + (int64_t)n * C * S, out + (int64_t)n * C * S + s, t, c0, c1, S, S);
+}
+
+extern "C" int mp_apply_warping_field(const float* v, const float* warp_field, float* out, int N, int C, int D, int H,
+                                      int W, int Df, int Hf, int Wf, void* stream) {
+  MP_REQUIRE(v && warp_field && out, "mp_apply_warping_field: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && C > 0 && D > 1 && H > 1 && W > 1 && Df > 0 && Hf > 0 && Wf > 0,
+             "mp_apply_warping_field: bad dims");
+  int64_t S = (int64_t)D * H * W;
+  dim3 g((unsigned)((S + 127) / 128), (C + GS_CCHUNK - 1) / GS_CCHUNK, N);
+  k_apply_warping_field<<<g, 128, 0, mp_stream(stream)>>>(v, warp_field, out, C, D, H, W, Df, Hf, Wf);
+  MP_LAUNCH_CHECK("mp_apply_warping_field");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ 64^3 field
+// value of channel k of the G^3 warp field at (z,y,x): affine_grid(align_corners=False) + trilinear(em, ac=False)
+__device__ __forceinline__ void field_at(const float* __restrict__ em, const float* __restrict__ th, int E, int G,
+                                         int z, int y, int x, float f[3]) {
+  // affine_grid base coordinate: linspace(-1,1,G) * (G-1)/G  ==  (2i+1)/G - 1
+  float cx = linspace_m1_1(x, G) * (float)(G - 1) / (float)G;
+  float cy = linspace_m1_1(y, G) * (float)(G - 1) / (float)G;
+  float cz = linspace_m1_1(z, G) * (float)(G - 1) / (float)G;
+  int z0, z1, y0, y1, x0, x1;
+  float lz, ly, lx;
+  src_ac_false(z, E, G, z0, z1, lz);
+  src_ac_false(y, E, G, y0, y1, ly);
+  src_ac_false(x, E, G, x0, x1, lx);
+  auto at = [&](int zz, int yy, int xx, int k) { return __ldg(em + (((int64_t)zz * E + yy) * E + xx) * 3 + k); };
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float a = (1.f - ly) * ((1.f - lx) * at(z0, y0, x0, k) + lx * at(z0, y0, x1, k)) +
+              ly * ((1.f - lx) * at(z0, y1, x0, k) + lx * at(z0, y1, x1, k));
+    float b = (1.f - ly) * ((1.f - lx) * at(z1, y0, x0, k) + lx * at(z1, y0, x1, k)) +
+              ly * ((1.f - lx) * at(z1, y1, x0, k) + lx * at(z1, y1, x1, k));
+    float emv = (1.f - lz) * a + lz * b;
+    float rt = th[k * 4 + 0] * cx + th[k * 4 + 1] * cy + th[k * 4 + 2] * cz + th[k * 4 + 3];
+    f[k] = rt + emv;
+  }
+}
+
+__global__ void k_warp_field(const float* __restrict__ em, const float* __restrict__ theta, float* __restrict__ out,
+                             int E, int G) {
+  const int64_t S = (int64_t)G * G * G;
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int n = blockIdx.y;
+  int x = (int)(s % G), y = (int)((s / G) % G), z = (int)(s / ((int64_t)G * G));
+  float f[3];
+  field_at(em + (int64_t)n * E * E * E * 3, theta + n * 12, E, G, z, y, x, f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[((int64_t)n * 3 + k) * S + s] = f[k];
+}
+
+extern "C" int mp_warp_field(const float* em_cl, const float* theta, float* out, int N, int E, int G, void* stream) {
+  MP_REQUIRE(em_cl && theta && out, "mp_warp_field: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && E > 0 && G > 0, "mp_warp_field: bad dims");
+  int64_t S = (int64_t)G * G * G;
+  dim3 g((unsigned)((S + 255) / 256), N);
+  k_warp_field<<<g, 256, 0, mp_stream(stream)>>>(em_cl, theta, out, E, G);
+  MP_LAUNCH_CHECK("mp_warp_field");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ fused CL warp
+// Block = one (sample, h, 64-wide w segment); D is walked in slabs of WF_DSLAB depth slices.  Phase 1: one thread per
+// voxel of the slab builds the sampling taps (closed form of the whole flow -> grid chain)
+// into shared memory.  Phase 2: threads re-map to (voxel, 4-channel vector) and gather with 16-byte loads that are
+// contiguous across the lanes of a warp (channels-last), then either store or accumulate the depth sum in registers.
+constexpr int WF_WSEG = 64;
+constexpr int WF_DSLAB = 4;
+constexpr int WF_THREADS = WF_WSEG * WF_DSLAB;   // 256
+constexpr int WF_MAXACC = 8;                     // ceil(WSEG * C/4 / THREADS) for C <= 128
+
+template <bool SUM_D>
+__global__ void __launch_bounds__(WF_THREADS)
+k_warp_fused_cl(const float* __restrict__ v, const float* __restrict__ em, const float* __restrict__ theta,
+                float* __restrict__ out_f32, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int Nv, int C,
+                int D, int H, int W, int E, int G) {
+  __shared__ int s_off[WF_THREADS][8];
+  __shared__ float s_w[WF_THREADS][8];
+  const int n = blockIdx.z, h = blockIdx.y, wbase = blockIdx.x * WF_WSEG;
+  const int C4 = C >> 2;
+  const int items = WF_WSEG * C4;                 // (voxel-in-row, channel vector) work items per depth slice
+  const float* vn = v + (Nv == 1 ? 0 : (int64_t)n * D * H * W * C);
+  const float* emn = em + (int64_t)n * E * E * E * 3;
+  const float* th = theta + n * 12;
+  float4 acc[WF_MAXACC];
+#pragma unroll
+  for (int i = 0; i < WF_MAXACC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int dbase = 0; dbase < D; dbase += WF_DSLAB) {
+    // ---- phase 1: taps for voxel (d, h, w)
+    {
+      int dl = threadIdx.x / WF_WSEG, wl = threadIdx.x % WF_WSEG;
+      int d = dbase + dl, w = wbase + wl;
+      Taps t;
+      if (d < D && w < W) {
+        // flow: G^3 field resampled to (D,H,W) with align_corners=True (model.py:1036)
+        int z0, z1, y0, y1, x0, x1;
+        float lz, ly, lx;
+        src_ac_true(d, G, D, z0, z1, lz);
+        src_ac_true(h, G, H, y0, y1, ly);
+        src_ac_true(w, G, W, x0, x1, lx);
+        float F[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          float wz = a ? lz : 1.f - lz;
+          if (wz == 0.f) continue;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            float wy = b ? ly : 1.f - ly;
+            if (wy == 0.f) continue;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float wx = c ? lx : 1.f - lx;
+              if (wx == 0.f) continue;
+              float f[3];
+              field_at(emn, th, E, G, a ? z1 : z0, b ? y1 : y0, c ? x1 : x0, f);
+              float wgt = wz * wy * wx;
+              F[0] += wgt * f[0]; F[1] += wgt * f[1]; F[2] += wgt * f[2];
+            }
+          }
+        }
+        float gx = 2.0f * (linspace_m1_1(w, W) + F[0]) / (float)(W - 1) - 1.0f;
+        float gy = 2.0f * (linspace_m1_1(h, H) + F[1]) / (float)(H - 1) - 1.0f;
+        float gz = 2.0f * (linspace_m1_1(d, D) + F[2]) / (float)(D - 1) - 1.0f;
+        make_taps(unnormalize_clip(gx, W), unnormalize_clip(gy, H), unnormalize_clip(gz, D), D, H, W, t);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t.off[k] = -1; t.w[k] = 0.f; }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s_off[threadIdx.x][k] = t.off[k]; s_w[threadIdx.x][k] = t.w[k]; }
+    }
+    __syncthreads();
+    // ---- phase 2: gather
+    for (int dl = 0; dl < WF_DSLAB && dbase + dl < D; ++dl) {
+      int d = dbase + dl;
+#pragma unroll
+      for (int i = 0; i < WF_MAXACC; ++i) {
+        int it = threadIdx.x + i * WF_THREADS;
+        if (it >= items) break;
+        int wl = it / C4, c4 = it % C4;
+        if (wbase + wl >= W) continue;
+        const int* po = s_off[dl * WF_WSEG + wl];
+        const float* pw = s_w[dl * WF_WSEG + wl];
+        float4 r = SUM_D ? acc[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          int off = po[k];
+          if (off >= 0) {
+            float4 q = __ldg(reinterpret_cast<const float4*>(vn + (int64_t)off * C + c4 * 4));
+            float wk = pw[k];
+            r.x = fmaf(q.x, wk, r.x); r.y = fmaf(q.y, wk, r.y); r.z = fmaf(q.z, wk, r.z); r.w = fmaf(q.w, wk, r.w);
+          }
+        }
+        if (SUM_D) {
+          acc[i] = r;
+        } else {
+          int64_t o = ((((int64_t)n * D + d) * H + h) * W + (wbase + wl)) * C + c4 * 4;
+          if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = r;
+          if (out_hi) mp_store_split4(out_hi, out_lo, o, r);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (SUM_D) {
+#pragma unroll
+    for (int i = 0; i < WF_MAXACC; ++i) {
+      int it = threadIdx.x + i * WF_THREADS;
+      if (it >= items) break;
+      int wl = it / C4, c4 = it % C4;
+      if (wbase + wl >= W) continue;
+      int64_t o = (((int64_t)n * H + h) * W + (wbase + wl)) * C + c4 * 4;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = acc[i];
+      if (out_hi) mp_store_split4(out_hi, out_lo, o, acc[i]);
+    }
+  }
+}
+
+extern "C" int mp_warp_fused_cl(const float* v, const float* em_cl, const float* theta, float* out_f32, void* out_hi,
+                                void* out_lo, int N, int Nv, int C, int D, int H, int W, int E, int G, int sum_d,
+                                void* stream) {
+  MP_REQUIRE(v && em_cl && theta && (out_f32 || (out_hi && out_lo)), "mp_warp_fused_cl: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && (Nv == 1 || Nv == N), "mp_warp_fused_cl: bad batch N=%d Nv=%d", N, Nv);
+  MP_REQUIRE(C % 4 == 0 && WF_WSEG * (C / 4) <= WF_MAXACC * WF_THREADS, "mp_warp_fused_cl: unsupported C=%d", C);
+  MP_REQUIRE(D > 1 && H > 1 && W > 1 && H <= 65535 && E > 0 && G > 0, "mp_warp_fused_cl: bad dims");
+  dim3 g((W + WF_WSEG - 1) / WF_WSEG, H, N);
+  if (sum_d)
+    k_warp_fused_cl<true><<<g, WF_THREADS, 0, mp_stream(stream)>>>(v, em_cl, theta, out_f32, (bf16*)out_hi,
+                                                                   (bf16*)out_lo, Nv, C, D, H, W, E, G);
+  else
+    k_warp_fused_cl<false><<<g, WF_THREADS, 0, mp_stream(stream)>>>(v, em_cl, theta, out_f32, (bf16*)out_hi,
+                                                                    (bf16*)out_lo, Nv, C, D, H, W, E, G);
+  MP_LAUNCH_CHECK("mp_warp_fused_cl");
+  return 0;
+}

@@ -1,0 +1,113 @@
+"""ctypes binding of libmpb200.so (the C ABI declared in include/mpb200.h).
+
+The library is built in-tree by `build()` (nvcc, sm_100a) and loaded lazily.  There is no fallback: if the shared
+object is missing or a call fails, a RuntimeError is raised -- the product path never routes around the CUDA code.
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libmpb200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ into libmpb200.so for sm_100a (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + sources()
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
+    return LIB_PATH
+
+
+class ConvDesc(Structure):
+    """mirror of `mp_conv_desc` (include/mpb200.h)"""
+    _fields_ = [
+        ("in_hi", c_void_p), ("in_lo", c_void_p), ("w_hi", c_void_p), ("w_lo", c_void_p), ("bias", c_void_p),
+        ("res_f32", c_void_p), ("res_hi", c_void_p), ("res_lo", c_void_p),
+        ("out_f32", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p), ("stats", c_void_p),
+        ("N", c_int), ("D", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
+        ("KD", c_int), ("KH", c_int), ("KW", c_int), ("Cout_pad", c_int), ("gn_groups", c_int), ("act", c_int),
+    ]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    "mp_abi_version": (c_int, []),
+    "mp_last_error": (c_char_p, []),
+    "mp_device_supported": (c_int, []),
+    "mp_nchw_to_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int64, _P]),
+    "mp_cl_to_nchw": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int64, _P]),
+    "mp_split": (c_int, [_P, _P, _P, c_int64, _P]),
+    "mp_avgpool2_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_upsample2x_linear_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_upsample_nearest_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_gn_stats": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P]),
+    "mp_gn_finalize": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_float, _P]),
+    "mp_affine_act_cl": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P]),
+    "mp_conv_tc": (c_int, [POINTER(ConvDesc), _P]),
+    "mp_conv_simt": (c_int, [POINTER(ConvDesc), _P]),
+    "mp_conv_tc_supported": (c_int, [POINTER(ConvDesc)]),
+    "mp_grid_sample3d": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_apply_warping_field": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_warp_field": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "mp_warp_fused_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, _P]),
+    "mp_blur_subsample": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+}
+
+EXPORTS = tuple(_SIGNATURES.keys())
+_lib = None
+
+
+def load():
+    """Load libmpb200.so; raises RuntimeError (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA extension is mandatory; there is no CPU or ATen fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mp_abi_version() != 1:
+        raise RuntimeError("libmpb200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().mp_last_error()
+        raise RuntimeError(f"libmpb200 {what} failed: {msg.decode() if msg else status}")

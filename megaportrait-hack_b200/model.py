@@ -1,0 +1,698 @@
+"""Drop-in replacements for the hot-path classes of the reference's `model.py` (johndpope/MegaPortrait-hack).
+
+Same class names, constructor arguments, `forward()` signatures, attribute names and `state_dict()` keys as the
+reference (model.py:54-1180), so `train.py` / `inference.py` / `PairwiseTransferLoss` call them unchanged; the
+arithmetic runs in the sm_100a kernels of libmpb200 (include/mpb200.h).  There is NO CPU path and NO ATen fallback
+for the hot-path operators: CPU tensors, train-mode BatchNorm and autograd raise.
+
+Two calling levels:
+  * module level -- every class takes / returns the reference's NCHW / NCDHW fp32 tensors;
+  * fused level  -- `Gbase.forward`, `Gbase.encode_source`, `Gbase.drive` chain the stages on channels-last
+    split-bf16 activations without leaving the internal layout.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .emtn import COMPRESS_DIM, FEATURE_SIZE, FEATURE_SIZE_AVG_POOL, CustomResNet50, Emtn, SixDRepNet_Detector  # noqa: F401
+from .ops import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, Act
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")   # model.py:51 (kept for callers that read it)
+
+
+# ----------------------------------------------------------------------------------------------------- guards
+def _require_inference(mod: nn.Module, *tensors) -> None:
+    for t in tensors:
+        if torch.is_tensor(t) and not t.is_cuda:
+            raise RuntimeError(f"{type(mod).__name__}: input is on {t.device}; the B200 path has no CPU fallback "
+                               "(move the module and its inputs to a CUDA device)")
+    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise NotImplementedError(f"{type(mod).__name__}: backward is not implemented (SURVEY.md 8f-2); "
+                                  "call under torch.no_grad()")
+
+
+def _sig(mod: nn.Module):
+    """Cheap change-detector for cached packed weights."""
+    s = 0
+    dev = None
+    for t in list(mod.parameters()) + list(mod.buffers()):
+        s += t._version + (t.data_ptr() & 0xFFFF)
+        dev = t.device
+    return (s, str(dev), mod.training)
+
+
+class _Packed:
+    """Mixin: lazily (re)built kernel-format weights, keyed on parameter versions."""
+
+    def _plan(self):
+        sig = _sig(self)
+        cache = self.__dict__.get("_mp_plan")
+        if cache is None or cache[0] != sig:
+            with torch.no_grad():
+                cache = (sig, self._build_plan())
+            self.__dict__["_mp_plan"] = cache
+        return cache[1]
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+def _as_f32_cuda(x: torch.Tensor) -> torch.Tensor:
+    return x.detach().to(torch.float32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------- layers
+class Conv2d_WS(nn.Conv2d):
+    """model.py:54-69: weight-standardised conv."""
+
+    def forward(self, x):
+        _require_inference(self, x)
+        pw = ops.pack_conv(ops.standardize_weight(self.weight), self.bias, x.device)
+        a = ops.from_nchw(_as_f32_cuda(x))
+        out, _ = ops.conv(a, pw)
+        return ops.to_nchw(out, 4)
+
+
+class Conv3D_WS(nn.Conv3d):
+    """model.py:71-86."""
+
+    def forward(self, x):
+        _require_inference(self, x)
+        pw = ops.pack_conv(ops.standardize_weight(self.weight), self.bias, x.device)
+        a = ops.from_nchw(_as_f32_cuda(x))
+        out, _ = ops.conv(a, pw)
+        return ops.to_nchw(out, 5)
+
+
+class ResBlock_Custom(nn.Module, _Packed):
+    """model.py:88-130: conv_res(x) + conv(relu(gn(conv_ws(relu(gn(x)))))), GN(32) non-affine."""
+
+    def __init__(self, dimension, in_channels, out_channels):
+        super().__init__()
+        self.dimension = dimension
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        if dimension == 2:
+            self.conv_res = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+            self.conv_ws = Conv2d_WS(in_channels=in_channels, out_channels=out_channels, kernel_size=3, padding=1)
+            self.conv = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        elif dimension == 3:
+            self.conv_res = nn.Conv3d(in_channels, out_channels, 3, padding=1)
+            self.conv_ws = Conv3D_WS(in_channels=in_channels, out_channels=out_channels, kernel_size=3, padding=1)
+            self.conv = nn.Conv3d(out_channels, out_channels, 3, padding=1)
+
+    def _build_plan(self):
+        dev = self.conv.weight.device
+        return {"res": ops.pack_conv(self.conv_res.weight, self.conv_res.bias, dev),
+                "ws": ops.pack_conv(ops.standardize_weight(self.conv_ws.weight), self.conv_ws.bias, dev),
+                "conv": ops.pack_conv(self.conv.weight, self.conv.bias, dev)}
+
+    def _forward_cl(self, x: Act, x_stats: Optional[torch.Tensor]) -> Act:
+        """x needs f32 + split; returns f32 (the sum out1 + out2)."""
+        P = self._plan()
+        out2, _ = ops.conv(x, P["res"], f32=True)
+        h = ops.group_norm_act(x, 32, x_stats, act=ACT_RELU, split=True)
+        h, st = ops.conv(h, P["ws"], f32=True, stats_groups=32)
+        h = ops.group_norm_act(h, 32, st, act=ACT_RELU, split=True)
+        out, _ = ops.conv(h, P["conv"], res=out2, f32=True)
+        return out
+
+    def forward(self, x):
+        _require_inference(self, x)
+        a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
+        out = self._forward_cl(a, None)
+        y = ops.to_nchw(out, x.dim())
+        assert y.shape[1] == self.out_channels, f"Expected {self.out_channels} channels, got {y.shape[1]}"
+        assert y.shape[2] == x.shape[2] and y.shape[3] == x.shape[3], \
+            f"Expected spatial dimensions {(x.shape[2], x.shape[3])}, got {(y.shape[2], y.shape[3])}"
+        return y
+
+
+class AdaptiveGroupNorm(nn.Module):
+    """model.py:304-316: GroupNorm(32, C) (affine) followed by a second learned per-channel affine."""
+
+    def __init__(self, num_channels, num_groups=32):
+        super().__init__()
+        self.num_channels = num_channels
+        self.num_groups = num_groups
+        self.weight = nn.Parameter(torch.ones(1, num_channels, 1, 1, 1))
+        self.bias = nn.Parameter(torch.zeros(1, num_channels, 1, 1, 1))
+        self.group_norm = nn.GroupNorm(num_groups, num_channels)
+
+    def _affine(self):
+        return (_f32c(self.group_norm.weight), _f32c(self.group_norm.bias), _f32c(self.weight).view(-1),
+                _f32c(self.bias).view(-1))
+
+    def forward(self, x):
+        _require_inference(self, x)
+        a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=False)
+        g, b, g2, b2 = self._affine()
+        out = ops.group_norm_act(a, self.num_groups, None, g, b, g2, b2, act=ACT_NONE, f32=True, split=False)
+        return ops.to_nchw(out, x.dim())
+
+
+class ResBlock3D_Adaptive(nn.Module, _Packed):
+    """model.py:369-408."""
+
+    def __init__(self, in_channels, out_channels, upsample=False, scale_factors=(1, 1, 1)):
+        super().__init__()
+        self.upsample = upsample
+        self.scale_factors = scale_factors
+        self.conv1 = nn.Conv3d(in_channels, out_channels, 3, padding=1)
+        self.conv2 = nn.Conv3d(out_channels, out_channels, 3, padding=1)
+        self.norm1 = AdaptiveGroupNorm(out_channels)
+        self.norm2 = AdaptiveGroupNorm(out_channels)
+        if in_channels != out_channels:
+            self.residual_conv = nn.Conv3d(in_channels, out_channels, 1)
+        else:
+            self.residual_conv = nn.Identity()
+
+    def _build_plan(self):
+        dev = self.conv1.weight.device
+        P = {"c1": ops.pack_conv(self.conv1.weight, self.conv1.bias, dev),
+             "c2": ops.pack_conv(self.conv2.weight, self.conv2.bias, dev),
+             "n1": self.norm1._affine(), "n2": self.norm2._affine(), "rc": None}
+        if isinstance(self.residual_conv, nn.Conv3d):
+            P["rc"] = ops.pack_conv(self.residual_conv.weight, self.residual_conv.bias, dev)
+        return P
+
+    def _forward_cl(self, x: Act, f32: bool = True, split: bool = True) -> Act:
+        """x: split (+ f32 when the residual is the identity and full precision is wanted)."""
+        if self.upsample:
+            raise NotImplementedError("ResBlock3D_Adaptive(upsample=True) is never used by the reference hot path")
+        P = self._plan()
+        G = self.norm1.num_groups
+        h, st = ops.conv(x, P["c1"], f32=True, stats_groups=G)
+        h = ops.group_norm_act(h, G, st, *P["n1"], act=ACT_RELU, split=True)
+        h, st = ops.conv(h, P["c2"], f32=True, stats_groups=G)
+        res = x if P["rc"] is None else ops.conv(x, P["rc"], f32=True)[0]
+        return ops.group_norm_act(h, G, st, *P["n2"], res=res, act=ACT_RELU, f32=f32, split=split)
+
+    def forward(self, x):
+        _require_inference(self, x)
+        a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
+        return ops.to_nchw(self._forward_cl(a, f32=True, split=False), 5)
+
+
+class FlowField(nn.Module, _Packed):
+    """model.py:415-471: 512-vector -> (B,3,16,16,16) flow in [0,1)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1x1 = nn.Conv2d(512, 2048, kernel_size=1)
+        self.reshape_layer = lambda x: x.view(-1, 512, 4, *x.shape[2:])
+        self.resblock1 = ResBlock3D_Adaptive(in_channels=512, out_channels=256)
+        self.upsample1 = nn.Upsample(scale_factor=(2, 2, 2))
+        self.resblock2 = ResBlock3D_Adaptive(in_channels=256, out_channels=128)
+        self.upsample2 = nn.Upsample(scale_factor=(2, 2, 2))
+        self.resblock3 = ResBlock3D_Adaptive(in_channels=128, out_channels=64)
+        self.upsample3 = nn.Upsample(scale_factor=(1, 2, 2))
+        self.resblock4 = ResBlock3D_Adaptive(in_channels=64, out_channels=32)
+        self.upsample4 = nn.Upsample(scale_factor=(1, 2, 2))
+        self.conv3x3x3 = nn.Conv3d(32, 3, kernel_size=3, padding=1)
+        self.gn = nn.GroupNorm(1, 3)
+        self.tanh = nn.Tanh()
+
+    def _build_plan(self):
+        dev = self.conv1x1.weight.device
+        # output channel c*4+d of the 1x1 conv becomes (c, d) of the (512,4,1,1) volume (model.py:424): permute the
+        # rows to d*512+c so the GEMM result is already the channels-last [B, 4, 1, 1, 512] volume.
+        w = self.conv1x1.weight.detach().view(512, 4, 512, 1, 1).permute(1, 0, 2, 3, 4).reshape(2048, 512, 1, 1)
+        b = self.conv1x1.bias.detach().view(512, 4).t().reshape(2048)
+        return {"c0": ops.pack_conv(w, b, dev),
+                "c5": ops.pack_conv(self.conv3x3x3.weight, self.conv3x3x3.bias, dev),
+                "gn": (_f32c(self.gn.weight), _f32c(self.gn.bias))}
+
+    def _forward_cl(self, s: torch.Tensor) -> torch.Tensor:
+        """s [B,512] fp32 -> em channels-last [B,16,16,16,3] fp32."""
+        P = self._plan()
+        B = s.shape[0]
+        a = Act((B, 1, 1, 1, 512), f32=s.contiguous().view(B, 1, 1, 1, 512))
+        h, _ = ops.conv(a, P["c0"], f32=True)
+        x = Act((B, 4, 1, 1, 512), f32=h.f32.view(B, 4, 1, 1, 512))
+        ops.ensure_split(x)
+        for blk, sc in ((self.resblock1, (2, 2, 2)), (self.resblock2, (2, 2, 2)), (self.resblock3, (1, 2, 2)),
+                        (self.resblock4, (1, 2, 2))):
+            y = blk._forward_cl(x, f32=True, split=False)
+            x = ops.upsample_nearest(y, sc, f32=False, split=True)
+        h, st = ops.conv(x, P["c5"], f32=True, stats_groups=1)
+        out = ops.group_norm_act(h, 1, st, *P["gn"], act=ACT_RELU_TANH, f32=True, split=False)
+        return out.f32
+
+    def forward(self, zs, adaptive_gamma, adaptive_beta):
+        _require_inference(self, zs)
+        em = self._forward_cl(_as_f32_cuda(zs).reshape(zs.shape[0], 512))
+        x = em.permute(0, 4, 1, 2, 3).contiguous()
+        assert x.shape[1] == 3, f"Expected 3 channels after conv3x3x3, got {x.shape[1]}"
+        return x
+
+
+class ResBlock3D(nn.Module, _Packed):
+    """model.py:500-528."""
+
+    def __init__(self, in_channels, out_channels, upsample=False, scale_factors=(1, 1, 1)):
+        super().__init__()
+        self.upsample = upsample
+        self.scale_factors = scale_factors
+        self.conv1 = nn.Conv3d(in_channels, out_channels, kernel_size=3, padding=1)
+        self.gn1 = nn.GroupNorm(num_groups=32, num_channels=out_channels)
+        self.conv2 = nn.Conv3d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.gn2 = nn.GroupNorm(num_groups=32, num_channels=out_channels)
+        self.shortcut = nn.Conv3d(in_channels, out_channels, kernel_size=1) if in_channels != out_channels \
+            else nn.Identity()
+
+    def _build_plan(self):
+        dev = self.conv1.weight.device
+        P = {"c1": ops.pack_conv(self.conv1.weight, self.conv1.bias, dev),
+             "c2": ops.pack_conv(self.conv2.weight, self.conv2.bias, dev),
+             "g1": (_f32c(self.gn1.weight), _f32c(self.gn1.bias)),
+             "g2": (_f32c(self.gn2.weight), _f32c(self.gn2.bias)), "sc": None}
+        if isinstance(self.shortcut, nn.Conv3d):
+            P["sc"] = ops.pack_conv(self.shortcut.weight, self.shortcut.bias, dev)
+        return P
+
+    def _forward_cl(self, x: Act, f32: bool = True, split: bool = False) -> Act:
+        if self.upsample:
+            raise NotImplementedError("ResBlock3D(upsample=True) is never used by the reference hot path")
+        P = self._plan()
+        idt = x if P["sc"] is None else ops.conv(x, P["sc"], f32=True)[0]
+        h, st = ops.conv(x, P["c1"], f32=True, stats_groups=32)
+        h = ops.group_norm_act(h, 32, st, *P["g1"], act=ACT_RELU, split=True)
+        h, st = ops.conv(h, P["c2"], f32=True, stats_groups=32)
+        return ops.group_norm_act(h, 32, st, *P["g2"], res=idt, act=ACT_RELU, f32=f32, split=split)
+
+    def forward(self, x):
+        _require_inference(self, x)
+        a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
+        return ops.to_nchw(self._forward_cl(a, f32=True, split=False), 5)
+
+
+class G3d(nn.Module):
+    """model.py:571-597."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.downsampling = nn.Sequential(
+            ResBlock3D(in_channels, 96), nn.AvgPool3d(kernel_size=2, stride=2),
+            ResBlock3D(96, 192), nn.AvgPool3d(kernel_size=2, stride=2),
+            ResBlock3D(192, 384), nn.AvgPool3d(kernel_size=2, stride=2),
+            ResBlock3D(384, 768))
+        self.upsampling = nn.Sequential(
+            ResBlock3D(768, 384), nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True),
+            ResBlock3D(384, 192), nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True),
+            ResBlock3D(192, 96), nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True))
+        self.final_conv = nn.Conv3d(96, 96, kernel_size=3, padding=1)
+
+    def _final_pack(self):
+        sig = (self.final_conv.weight._version, self.final_conv.bias._version, str(self.final_conv.weight.device),
+               self.final_conv.weight.data_ptr())
+        c = self.__dict__.get("_mp_final")
+        if c is None or c[0] != sig:
+            c = (sig, ops.pack_conv(self.final_conv.weight, self.final_conv.bias))
+            self.__dict__["_mp_final"] = c
+        return c[1]
+
+    def _forward_cl(self, x: Act) -> Act:
+        """x: f32 + split, channels-last [N,16,64,64,96] -> f32 channels-last."""
+        for i in (0, 2, 4, 6):
+            y = self.downsampling[i]._forward_cl(x, f32=True, split=(i == 6))
+            x = ops.avgpool2(y, 2, f32=False, split=True) if i < 6 else y
+        for i in (0, 2, 4):
+            y = self.upsampling[i]._forward_cl(x, f32=True, split=False)
+            x = ops.upsample2x_linear(y, 2, f32=False, split=True)
+        out, _ = ops.conv(x, self._final_pack(), f32=True)
+        return out
+
+    def forward(self, x):
+        _require_inference(self, x)
+        a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
+        return ops.to_nchw(self._forward_cl(a), 5)
+
+
+class ResBlock2D(nn.Module, _Packed):
+    """model.py:600-640 (BatchNorm2d: eval-mode running statistics are folded into the conv weights)."""
+
+    def __init__(self, in_channels, out_channels, downsample=False):
+        super().__init__()
+        self.downsample = downsample
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.bn1 = nn.BatchNorm2d(out_channels)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.bn2 = nn.BatchNorm2d(out_channels)
+        if self.downsample:
+            self.downsample_conv = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=2)
+            self.downsample_bn = nn.BatchNorm2d(out_channels)
+        if in_channels != out_channels:
+            self.shortcut = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1),
+                                          nn.BatchNorm2d(out_channels))
+        else:
+            self.shortcut = nn.Identity()
+
+    @staticmethod
+    def _bn(bn: nn.BatchNorm2d) -> dict:
+        return {"weight": bn.weight.detach(), "bias": bn.bias.detach(), "running_mean": bn.running_mean,
+                "running_var": bn.running_var}
+
+    def _build_plan(self):
+        if self.training:
+            raise NotImplementedError("ResBlock2D: train-mode BatchNorm (batch statistics) is not implemented "
+                                      "(SURVEY.md 8f-2); call .eval()")
+        if self.downsample:
+            raise NotImplementedError("ResBlock2D(downsample=True) is never used by the reference hot path")
+        dev = self.conv1.weight.device
+        w1, b1 = ops.fold_bn(self.conv1.weight.detach(), self.conv1.bias.detach(), self._bn(self.bn1), self.bn1.eps)
+        w2, b2 = ops.fold_bn(self.conv2.weight.detach(), self.conv2.bias.detach(), self._bn(self.bn2), self.bn2.eps)
+        P = {"c1": ops.pack_conv(w1, b1, dev), "c2": ops.pack_conv(w2, b2, dev), "sc": None}
+        if isinstance(self.shortcut, nn.Sequential):
+            ws, bs = ops.fold_bn(self.shortcut[0].weight.detach(), self.shortcut[0].bias.detach(),
+                                 self._bn(self.shortcut[1]), self.shortcut[1].eps)
+            P["sc"] = ops.pack_conv(ws, bs, dev)
+        return P
+
+    def _forward_cl(self, x: Act, f32: bool = False, split: bool = True, stats_groups: int = 0):
+        """x: split.  Returns (Act, stats or None)."""
+        P = self._plan()
+        idt = x if P["sc"] is None else ops.conv(x, P["sc"], f32=True)[0]
+        t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, split=True)
+        return ops.conv(t, P["c2"], res=idt, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
+
+    def forward(self, x):
+        _require_inference(self, x)
+        a = ops.from_nchw(_as_f32_cuda(x), f32=False, split=True)
+        out, _ = self._forward_cl(a, f32=True, split=False)
+        return ops.to_nchw(out, 4)
+
+
+class G2d(nn.Module, _Packed):
+    """model.py:715-763."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.reshape = nn.Conv2d(96, 1536, kernel_size=1)
+        self.conv1x1 = nn.Conv2d(1536, 512, kernel_size=1)
+        self.res_blocks = nn.Sequential(*[ResBlock2D(512, 512) for _ in range(8)])
+        self.upsample1 = nn.Sequential(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                                       ResBlock2D(512, 256))
+        self.upsample2 = nn.Sequential(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                                       ResBlock2D(256, 128))
+        self.upsample3 = nn.Sequential(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                                       ResBlock2D(128, 64))
+        self.final_conv = nn.Sequential(nn.GroupNorm(num_groups=32, num_channels=64), nn.ReLU(inplace=True),
+                                        nn.Conv2d(64, 3, kernel_size=3, padding=1), nn.Sigmoid())
+
+    def _sig_extra(self):
+        return None
+
+    def _build_plan(self):
+        dev = self.reshape.weight.device
+        # reshape (96->1536) and conv1x1 (1536->512) have no non-linearity between them (model.py:756-757):
+        # fold them into one 96->512 1x1 conv in float64.
+        w1 = self.reshape.weight.detach().double().view(1536, 96)
+        b1 = self.reshape.bias.detach().double()
+        w2 = self.conv1x1.weight.detach().double().view(512, 1536)
+        b2 = self.conv1x1.bias.detach().double()
+        w = (w2 @ w1).view(512, 96, 1, 1)
+        b = w2 @ b1 + b2
+        return {"in": ops.pack_conv(w, b, dev),
+                "gn": (_f32c(self.final_conv[0].weight), _f32c(self.final_conv[0].bias)),
+                "out": ops.pack_conv(self.final_conv[2].weight, self.final_conv[2].bias, dev)}
+
+    def _forward_cl(self, x: Act) -> torch.Tensor:
+        """x: split channels-last [N,1,64,64,96] -> RGB NCHW fp32 [N,3,512,512]."""
+        P = self._plan()
+        h, _ = ops.conv(x, P["in"], f32=False, split=True)
+        for blk in self.res_blocks:
+            h, _ = blk._forward_cl(h)
+        st = None
+        for i, up in enumerate((self.upsample1, self.upsample2, self.upsample3)):
+            u = ops.upsample2x_linear(h, 1, f32=False, split=True)
+            last = i == 2
+            h, st = up[1]._forward_cl(u, f32=last, split=not last, stats_groups=32 if last else 0)
+        g = ops.group_norm_act(h, 32, st, *P["gn"], act=ACT_RELU, split=True)
+        rgb, _ = ops.conv(g, P["out"], act=ACT_SIGMOID, f32=True)
+        return ops.to_nchw(rgb, 4)
+
+    def forward(self, x):
+        _require_inference(self, x)
+        a = ops.from_nchw(_as_f32_cuda(x), f32=False, split=True)
+        return self._forward_cl(a)
+
+
+# ----------------------------------------------------------------------------------------------------- Eapp
+class Eapp(nn.Module, _Packed):
+    """model.py:206-299 (including the double assignment of `resblock3D_96_2`, model.py:218,225)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 64, 7, stride=1, padding=3)
+        self.resblock_128 = ResBlock_Custom(dimension=2, in_channels=64, out_channels=128)
+        self.resblock_256 = ResBlock_Custom(dimension=2, in_channels=128, out_channels=256)
+        self.resblock_512 = ResBlock_Custom(dimension=2, in_channels=256, out_channels=512)
+        self.resblock3D_96 = ResBlock3D_Adaptive(in_channels=96, out_channels=96)
+        self.resblock3D_96_2 = ResBlock3D_Adaptive(in_channels=96, out_channels=96)
+        self.resblock3D_96_1 = ResBlock3D_Adaptive(in_channels=96, out_channels=96)
+        self.resblock3D_96_1_2 = ResBlock3D_Adaptive(in_channels=96, out_channels=96)
+        self.resblock3D_96_2 = ResBlock3D_Adaptive(in_channels=96, out_channels=96)
+        self.resblock3D_96_2_2 = ResBlock3D_Adaptive(in_channels=96, out_channels=96)
+        self.conv_1 = nn.Conv2d(in_channels=512, out_channels=1536, kernel_size=1, stride=1, padding=0)
+        self.avgpool = nn.AvgPool2d(kernel_size=2, stride=2, padding=0)
+        self.custom_resnet50 = CustomResNet50()
+        self.fc = torch.nn.Linear(2048, COMPRESS_DIM)
+        self.tf32_descriptor = True   # cuDNN TF32 for the (non hot-path) ResNet-50 descriptor branch
+
+    def _build_plan(self):
+        dev = self.conv.weight.device
+        return {"stem": ops.pack_conv(self.conv.weight, self.conv.bias, dev),
+                "c1": ops.pack_conv(self.conv_1.weight, self.conv_1.bias, dev)}
+
+    def _volume_cl(self, x: torch.Tensor) -> Act:
+        """x NCHW fp32 [B,3,512,512] -> vs channels-last [B,16,64,64,96] (f32 + split)."""
+        P = self._plan()
+        a = ops.from_nchw(x, f32=False, split=True)
+        out, st = ops.conv(a, P["stem"], f32=True, split=True, stats_groups=32)
+        for blk in (self.resblock_128, self.resblock_256, self.resblock_512):
+            y = blk._forward_cl(out, st)
+            out = ops.avgpool2(y, 1, f32=True, split=True)
+            st = None
+        h = ops.group_norm_act(out, 32, None, act=ACT_RELU, split=True)
+        h, _ = ops.conv(h, P["c1"], f32=True)
+        B, _, Hh, Ww, _ = h.shape
+        # view(B, 96, 16, H, W) (model.py:271): channel c*16+d -> (c, d); go through NCHW to re-tile as NDHWC
+        vol = ops.to_nchw(h, 4).view(B, 96, 16, Hh, Ww)
+        vs = ops.from_nchw(vol, f32=True, split=True)
+        for blk in (self.resblock3D_96, self.resblock3D_96_2, self.resblock3D_96_1, self.resblock3D_96_1_2,
+                    self.resblock3D_96_2, self.resblock3D_96_2_2):
+            vs = blk._forward_cl(vs, f32=True, split=True)
+        return vs
+
+    def _descriptor(self, x: torch.Tensor) -> torch.Tensor:
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=bool(self.tf32_descriptor)):
+            es = self.custom_resnet50(x)
+        return self.fc(torch.flatten(es, start_dim=1))
+
+    def forward(self, x):
+        _require_inference(self, x)
+        x = _as_f32_cuda(x)
+        vs = ops.to_nchw(self._volume_cl(x), 5)
+        return vs, self._descriptor(x)
+
+
+# ----------------------------------------------------------------------------------------------------- warps
+def compute_rotation_matrix(rotation):
+    """model.py:811-856: degrees -> R = Rx(a) @ (Ry(b) @ Rz(c))."""
+    r = rotation * (torch.pi / 180.0)
+    ca, sa = torch.cos(r[:, 0]), torch.sin(r[:, 0])
+    cb, sb = torch.cos(r[:, 1]), torch.sin(r[:, 1])
+    cg, sg = torch.cos(r[:, 2]), torch.sin(r[:, 2])
+    z, o = torch.zeros_like(ca), torch.ones_like(ca)
+    Rx = torch.stack((torch.stack((o, z, z), 1), torch.stack((z, ca, -sa), 1), torch.stack((z, sa, ca), 1)), 1)
+    Ry = torch.stack((torch.stack((cb, z, sb), 1), torch.stack((z, o, z), 1), torch.stack((-sb, z, cb), 1)), 1)
+    Rz = torch.stack((torch.stack((cg, -sg, z), 1), torch.stack((sg, cg, z), 1), torch.stack((z, z, o), 1)), 1)
+    return torch.matmul(Rx, torch.matmul(Ry, Rz))
+
+
+def _affine_3x4(rotation, translation, invert: bool) -> torch.Tensor:
+    """First three rows of [R|t] or of its inverse (model.py:790-803) as a contiguous [B,3,4] fp32 tensor."""
+    B = rotation.shape[0]
+    A = torch.eye(4, device=rotation.device, dtype=torch.float32).repeat(B, 1, 1)
+    A[:, :3, :3] = compute_rotation_matrix(rotation.float())
+    A[:, :3, 3] = translation.float()
+    if invert:
+        A = torch.inverse(A)
+    return A[:, :3].contiguous()
+
+
+def compute_rt_warp(rotation, translation, invert=False, grid_size=64):
+    """model.py:777-809 -> (B, 3, G, G, G)."""
+    _require_inference(nn.Identity(), rotation, translation)
+    theta = _affine_3x4(rotation, translation, invert)
+    em0 = torch.zeros((rotation.shape[0], 1, 1, 1, 3), device=rotation.device, dtype=torch.float32)
+    return ops.warp_field(em0, theta, grid_size)
+
+
+class _WarpGenerator(nn.Module):
+    _invert = False
+
+    def __init__(self, num_channels):
+        super().__init__()
+        self.flowfield = FlowField()
+        self.num_channels = COMPRESS_DIM
+        # the reference's `nn.Parameter(...).to(device)` registers these only on CPU builds (model.py:934-935);
+        # here they are always registered so they follow .to()/state_dict() on every device.
+        self.adaptive_matrix_gamma = nn.Parameter(torch.randn(self.num_channels, self.num_channels))
+        self.adaptive_matrix_beta = nn.Parameter(torch.randn(self.num_channels, self.num_channels))
+
+    def _em_theta(self, R, t, z, e) -> Tuple[torch.Tensor, torch.Tensor]:
+        assert R.shape == (z.shape[0], 3), f"Expected R shape (batch_size, 3), got {R.shape}"
+        assert t.shape == (z.shape[0], 3), f"Expected t shape (batch_size, 3), got {t.shape}"
+        assert z.shape == e.shape, f"Expected z and es to have the same shape, got {z.shape} and {e.shape}"
+        s = torch.matmul((z + e).float(), self.adaptive_matrix_gamma.detach().float())
+        em = self.flowfield._forward_cl(s)
+        return em, _affine_3x4(R, t, self._invert)
+
+    def _forward(self, R, t, z, e):
+        _require_inference(self, R, t, z, e)
+        em, theta = self._em_theta(R, t, z, e)
+        return ops.warp_field(em, theta, 64)
+
+
+class WarpGeneratorS2C(_WarpGenerator):
+    """model.py:927-975."""
+    _invert = True
+
+    def forward(self, Rs, ts, zs, es):
+        return self._forward(Rs, ts, zs, es)
+
+
+class WarpGeneratorC2D(_WarpGenerator):
+    """model.py:978-1024."""
+    _invert = False
+
+    def forward(self, Rd, td, zd, es):
+        return self._forward(Rd, td, zd, es)
+
+
+def apply_warping_field(v, warp_field):
+    """model.py:1028-1065."""
+    _require_inference(nn.Identity(), v, warp_field)
+    return ops.apply_warping_field_ncdhw(_as_f32_cuda(v), _as_f32_cuda(warp_field))
+
+
+# ----------------------------------------------------------------------------------------------------- pyramid
+class AntiAliasInterpolation2d(nn.Module):
+    """model.py:646-691."""
+
+    def __init__(self, channels, scale):
+        super().__init__()
+        sigma = (1 / scale - 1) / 2
+        kernel_size = 2 * round(sigma * 4) + 1
+        self.ka = kernel_size // 2
+        self.kb = self.ka - 1 if kernel_size % 2 == 0 else self.ka
+        ax = torch.arange(kernel_size, dtype=torch.float32)
+        mean = (kernel_size - 1) / 2
+        g = torch.exp(-(ax - mean) ** 2 / (2 * sigma ** 2))
+        kernel = g[:, None] * g[None, :]
+        kernel = kernel / torch.sum(kernel)
+        kernel = kernel.view(1, 1, kernel_size, kernel_size).repeat(channels, 1, 1, 1)
+        self.register_buffer('weight', kernel)
+        self.groups = channels
+        self.scale = scale
+
+    def forward(self, input):
+        if self.scale == 1.0:
+            return input
+        _require_inference(self, input)
+        step = int(round(1.0 / self.scale))
+        return ops.blur_subsample(_as_f32_cuda(input), self.weight[0, 0].contiguous(), step)
+
+
+class ImagePyramide(torch.nn.Module):
+    """model.py:1070-1085."""
+
+    def __init__(self, scales, num_channels):
+        super().__init__()
+        downs = {}
+        for scale in scales:
+            downs[str(scale).replace('.', '-')] = AntiAliasInterpolation2d(num_channels, scale)
+        self.downs = nn.ModuleDict(downs)
+
+    def forward(self, x):
+        out_dict = {}
+        for scale, down_module in self.downs.items():
+            out_dict['prediction_' + str(scale).replace('-', '.')] = down_module(x)
+        return out_dict
+
+
+# ----------------------------------------------------------------------------------------------------- Gbase
+class Gbase(nn.Module):
+    """model.py:1127-1180.  `forward(xs, xd) -> (xhat_base, pyramids)`.
+
+    Extra (non-reference) entry points for "1 source x N drivers" (BASELINE configs 2-3): `encode_source(xs)` runs the
+    source-only half once, `drive(src, xd)` the per-driver half; `forward` is exactly `drive(encode_source(xs), xd)`.
+    """
+
+    def __init__(self):
+        super().__init__()
+        self.appearanceEncoder = Eapp()
+        self.motionEncoder = Emtn()
+        self.warp_generator_s2c = WarpGeneratorS2C(num_channels=512)
+        self.warp_generator_c2d = WarpGeneratorC2D(num_channels=512)
+        self.G3d = G3d(in_channels=96)
+        self.G2d = G2d(in_channels=96)
+        self.image_pyramid = ImagePyramide(scales=[0.5, 0.25], num_channels=3)
+        self.tf32_motion = True   # cuDNN TF32 for Emtn (not a hot-path row this round)
+
+    def _emtn(self, x):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=bool(self.tf32_motion)):
+            return self.motionEncoder(x)
+
+    @torch.no_grad()
+    def encode_source(self, xs, keep_stages: bool = False) -> Dict[str, object]:
+        """Source-only half (model.py:1141-1160): Eapp, Emtn(xs), S2C warp, G3d.  Returns the cached state."""
+        _require_inference(self, xs)
+        if self.training:
+            raise NotImplementedError("Gbase: train mode is not implemented on the B200 path (SURVEY.md 8f-2)")
+        xs = _as_f32_cuda(xs)
+        vs = self.appearanceEncoder._volume_cl(xs)
+        es = self.appearanceEncoder._descriptor(xs)
+        Rs, ts, zs = self._emtn(xs)
+        em, theta = self.warp_generator_s2c._em_theta(Rs, ts, zs, es)
+        vc = ops.warp_fused(vs, em, theta, sum_d=False, f32=True, split=True)
+        assert vc.shape[1:] == (16, 64, 64, 96), f"Expected vc shape (_, 96, 16, 64, 64), got {vc.shape}"
+        vc2d = self.G3d._forward_cl(vc)
+        src = {"vc2d": vc2d, "es": es}
+        if keep_stages:
+            src.update(vs=vs, Rs=Rs, ts=ts, zs=zs, em_s2c=em, theta_s2c=theta, vc=vc)
+        return src
+
+    @torch.no_grad()
+    def drive(self, src: Dict[str, object], xd, keep_stages: bool = False):
+        """Per-driver half (model.py:1145, 1163-1180).  `src["vc2d"]` may hold 1 sample (shared source) or len(xd)."""
+        _require_inference(self, xd)
+        xd = _as_f32_cuda(xd)
+        n = xd.shape[0]
+        es = src["es"]
+        if es.shape[0] != n:
+            assert es.shape[0] == 1, f"source batch {es.shape[0]} does not match driver batch {n}"
+            es = es.expand(n, -1)
+        Rd, td, zd = self._emtn(xd)
+        em, theta = self.warp_generator_c2d._em_theta(Rd, td, zd, es)
+        proj = ops.warp_fused(src["vc2d"], em, theta, sum_d=True, f32=keep_stages, split=True)
+        assert proj.shape[1:] == (1, 64, 64, 96), f"Expected vc2d_warped shape (_, 96, 16, 64, 64), got {proj.shape}"
+        xhat = self.G2d._forward_cl(proj)
+        pyramids = self.image_pyramid(xhat)
+        if keep_stages:
+            return xhat, pyramids, dict(Rd=Rd, td=td, zd=zd, em_c2d=em, theta_c2d=theta, projected=proj)
+        return xhat, pyramids
+
+    def forward(self, xs, xd):
+        assert xs.shape[0] == xd.shape[0], f"Expected zs and es to have the same shape (Bs == Bd), got {xs.shape[0]} and {xd.shape[0]}"
+        src = self.encode_source(xs)
+        return self.drive(src, xd)

@@ -1,0 +1,378 @@
+"""Tensor-level wrappers over the C ABI (include/mpb200.h).  PyTorch is used for device memory and streams only.
+
+Internal activation format (`Act`): channels-last [N, D, H, W, C] (2-D tensors carry D = 1), held as an fp32 tensor
+and/or a pair of bf16 planes (hi, lo) with x ~= hi + lo -- the operand format of the split-bf16 tensor-core
+convolution.  Every function launches on the current torch CUDA stream and never synchronises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as _lib
+from .lib import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, ConvDesc  # noqa: F401
+
+LAUNCHES = 0   # number of libmpb200 kernel launches issued by this process (bench.py reports it)
+PROFILE = None  # when a list: (kind, start_event, end_event, algorithmic_flops, algorithmic_bytes) per hot launch
+
+
+class _Prof:
+    """CUDA-event bracket on the launching stream, active only while `PROFILE` is a list (bench.py roofline leg)."""
+    __slots__ = ("kind", "flops", "bytes", "e0")
+
+    def __init__(self, kind, flops=0, nbytes=0):
+        self.kind, self.flops, self.bytes, self.e0 = kind, flops, nbytes, None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.kind, self.e0, e1, self.flops, self.bytes))
+        return False
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk_cuda(t: torch.Tensor, dtype, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: libmpb200 kernels need a CUDA tensor (got {t.device}); there is no CPU fallback")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{what}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{what}: tensor must be contiguous")
+
+
+class Act:
+    """Channels-last activation [N, D, H, W, C]: `f32` and/or the split pair (`hi`, `lo`)."""
+    __slots__ = ("f32", "hi", "lo", "shape")
+
+    def __init__(self, shape, f32=None, hi=None, lo=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.f32, self.hi, self.lo = f32, hi, lo
+
+    @property
+    def N(self): return self.shape[0]
+    @property
+    def D(self): return self.shape[1]
+    @property
+    def H(self): return self.shape[2]
+    @property
+    def W(self): return self.shape[3]
+    @property
+    def C(self): return self.shape[4]
+    @property
+    def S(self): return self.shape[1] * self.shape[2] * self.shape[3]
+
+    @property
+    def device(self):
+        return (self.f32 if self.f32 is not None else self.hi).device
+
+    def has_split(self):
+        return self.hi is not None
+
+
+def _alloc(shape, device, f32: bool, split: bool):
+    a = Act(shape)
+    if f32:
+        a.f32 = torch.empty(shape, dtype=torch.float32, device=device)
+    if split:
+        a.hi = torch.empty(shape, dtype=torch.bfloat16, device=device)
+        a.lo = torch.empty(shape, dtype=torch.bfloat16, device=device)
+    return a
+
+
+# ----------------------------------------------------------------------------------------------------- layout
+def from_nchw(x: torch.Tensor, f32: bool = False, split: bool = True) -> Act:
+    """NCHW / NCDHW fp32 -> Act."""
+    _chk_cuda(x, torch.float32, "from_nchw")
+    if x.dim() == 4:
+        N, C, H, W = x.shape
+        D = 1
+    else:
+        N, C, D, H, W = x.shape
+    out = _alloc((N, D, H, W, C), x.device, f32, split)
+    L = _lib.load()
+    _lib.check(L.mp_nchw_to_cl(_p(x), _p(out.f32), _p(out.hi), _p(out.lo), N, C, D * H * W, _stream()), "mp_nchw_to_cl")
+    _count()
+    return out
+
+
+def to_nchw(a: Act, ndim: int = 5) -> torch.Tensor:
+    N, D, H, W, C = a.shape
+    out = torch.empty((N, C, D, H, W) if ndim == 5 else (N, C, H, W), dtype=torch.float32, device=a.device)
+    L = _lib.load()
+    _lib.check(L.mp_cl_to_nchw(_p(a.f32), _p(a.hi), _p(a.lo), _p(out), N, C, D * H * W, _stream()), "mp_cl_to_nchw")
+    _count()
+    return out
+
+
+def ensure_split(a: Act) -> Act:
+    if a.hi is None:
+        a.hi = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+        a.lo = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+        L = _lib.load()
+        _lib.check(L.mp_split(_p(a.f32), _p(a.hi), _p(a.lo), a.f32.numel(), _stream()), "mp_split")
+        _count()
+    return a
+
+
+def avgpool2(a: Act, pool_d: int, f32: bool = True, split: bool = False) -> Act:
+    N, D, H, W, C = a.shape
+    out = _alloc((N, D // pool_d, H // 2, W // 2, C), a.device, f32, split)
+    L = _lib.load()
+    _lib.check(L.mp_avgpool2_cl(_p(a.f32), _p(out.f32), _p(out.hi), _p(out.lo), N, D, H, W, C, pool_d, _stream()),
+               "mp_avgpool2_cl")
+    _count()
+    return out
+
+
+def upsample2x_linear(a: Act, up_d: int, f32: bool = False, split: bool = True) -> Act:
+    N, D, H, W, C = a.shape
+    out = _alloc((N, D * up_d, H * 2, W * 2, C), a.device, f32, split)
+    L = _lib.load()
+    _lib.check(L.mp_upsample2x_linear_cl(_p(a.f32), _p(a.hi), _p(a.lo), _p(out.f32), _p(out.hi), _p(out.lo), N, D, H, W,
+                                         C, up_d, _stream()), "mp_upsample2x_linear_cl")
+    _count()
+    return out
+
+
+def upsample_nearest(a: Act, scale: Sequence[int], f32: bool = False, split: bool = True) -> Act:
+    N, D, H, W, C = a.shape
+    sd, sh, sw = scale
+    out = _alloc((N, D * sd, H * sh, W * sw, C), a.device, f32, split)
+    L = _lib.load()
+    _lib.check(L.mp_upsample_nearest_cl(_p(a.f32), _p(out.f32), _p(out.hi), _p(out.lo), N, D, H, W, C, sd, sh, sw,
+                                        _stream()), "mp_upsample_nearest_cl")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- norm
+def new_stats(N: int, G: int, device) -> torch.Tensor:
+    return torch.zeros((N, G, 2), dtype=torch.float64, device=device)
+
+
+def gn_stats(a: Act, G: int) -> torch.Tensor:
+    st = new_stats(a.N, G, a.device)
+    L = _lib.load()
+    _lib.check(L.mp_gn_stats(_p(a.f32), _p(st), a.N, a.S, a.C, G, _stream()), "mp_gn_stats")
+    _count()
+    return st
+
+
+def gn_finalize(stats: torch.Tensor, a_shape, G: int, gamma=None, beta=None, gamma2=None, beta2=None,
+                eps: float = 1e-5) -> torch.Tensor:
+    N, D, H, W, C = a_shape
+    ab = torch.empty((N, C, 2), dtype=torch.float32, device=stats.device)
+    L = _lib.load()
+    _lib.check(L.mp_gn_finalize(_p(stats), _p(gamma), _p(beta), _p(gamma2), _p(beta2), _p(ab), N, D * H * W, C, G,
+                                eps, _stream()), "mp_gn_finalize")
+    _count()
+    return ab
+
+
+def affine_act(a: Act, ab: Optional[torch.Tensor], res: Optional[Act] = None, act: int = ACT_NONE, f32: bool = False,
+               split: bool = True) -> Act:
+    out = _alloc(a.shape, a.device, f32, split)
+    rf = res.f32 if res is not None else None
+    rh = res.hi if (res is not None and rf is None) else None
+    rl = res.lo if (res is not None and rf is None) else None
+    L = _lib.load()
+    _lib.check(L.mp_affine_act_cl(_p(a.f32), _p(ab), _p(rf), _p(rh), _p(rl), _p(out.f32), _p(out.hi), _p(out.lo), a.N,
+                                  a.S, a.C, act, _stream()), "mp_affine_act_cl")
+    _count()
+    return out
+
+
+def group_norm_act(a: Act, G: int, stats: Optional[torch.Tensor] = None, gamma=None, beta=None, gamma2=None,
+                   beta2=None, res: Optional[Act] = None, act: int = ACT_RELU, f32: bool = False,
+                   split: bool = True) -> Act:
+    """act(GroupNorm_G(a) [*gamma2 + beta2] [+ res]); `stats` come from a conv epilogue when available."""
+    if stats is None:
+        stats = gn_stats(a, G)
+    ab = gn_finalize(stats, a.shape, G, gamma, beta, gamma2, beta2)
+    return affine_act(a, ab, res, act, f32, split)
+
+
+# ----------------------------------------------------------------------------------------------------- conv
+class PackedConv:
+    """Weights of one convolution in kernel format: split-bf16 [Cout_pad, taps*Cin] (tap-major, cin-minor) + bias."""
+    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k")
+
+    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k):
+        self.w_hi, self.w_lo, self.bias = w_hi, w_lo, bias
+        self.Cin, self.Cout, self.Cout_pad, self.k = Cin, Cout, Cout_pad, tuple(k)
+
+
+def standardize_weight(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d_WS / Conv3D_WS weight transform (model.py:61-69, 77-86), evaluated in float64."""
+    w = w.double()
+    dims = tuple(range(1, w.dim()))
+    w = w - w.mean(dim=dims, keepdim=True)
+    std = w.reshape(w.size(0), -1).std(dim=1).view(-1, *([1] * (w.dim() - 1))) + 1e-5
+    return w / std
+
+
+def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: dict, eps: float = 1e-5):
+    """conv -> BatchNorm(eval) == conv with w*s, (b-mean)*s+beta, s = gamma/sqrt(var+eps); float64 (model.py:605-616)."""
+    s = bn["weight"].double() / torch.sqrt(bn["running_var"].double() + eps)
+    w = w.double() * s.view(-1, *([1] * (w.dim() - 1)))
+    b0 = b.double() if b is not None else torch.zeros_like(s)
+    return w, (b0 - bn["running_mean"].double()) * s + bn["bias"].double()
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> PackedConv:
+    """weight (Cout, Cin, [kd,] kh, kw) float32/64 -> PackedConv on `device`."""
+    device = device or weight.device
+    w = weight.detach().to(device=device, dtype=torch.float64)
+    if w.dim() == 4:
+        w = w.unsqueeze(2)
+    Cout, Cin, kd, kh, kw = w.shape
+    wk = w.permute(0, 2, 3, 4, 1).reshape(Cout, kd * kh * kw * Cin).to(torch.float32)
+    Cout_pad = (Cout + 15) // 16 * 16
+    if Cout_pad != Cout:
+        wk = torch.cat([wk, torch.zeros(Cout_pad - Cout, wk.shape[1], device=device)], 0)
+    hi = wk.to(torch.bfloat16)
+    lo = (wk - hi.float()).to(torch.bfloat16)
+    b = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
+    return PackedConv(hi.contiguous(), lo.contiguous(), b, Cin, Cout, Cout_pad, (kd, kh, kw))
+
+
+_CONV_MODE = os.environ.get("MPB200_CONV", "auto")   # auto | tc | simt
+
+
+def set_conv_mode(mode: str) -> None:
+    global _CONV_MODE
+    assert mode in ("auto", "tc", "simt")
+    _CONV_MODE = mode
+
+
+def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE, f32: bool = True,
+         split: bool = False, stats_groups: int = 0, mode: Optional[str] = None
+         ) -> Tuple[Act, Optional[torch.Tensor]]:
+    """act(conv(a) + bias + res) -> (Act, GroupNorm statistics of the written values or None)."""
+    if a.hi is None:
+        ensure_split(a)
+    N, D, H, W, C = a.shape
+    if C != pw.Cin:
+        raise RuntimeError(f"conv: activation has {C} channels, weights expect {pw.Cin}")
+    out = _alloc((N, D, H, W, pw.Cout), a.device, f32, split)
+    stats = new_stats(N, stats_groups, a.device) if stats_groups else None
+    d = ConvDesc()
+    d.in_hi, d.in_lo, d.w_hi, d.w_lo, d.bias = _p(a.hi), _p(a.lo), _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias)
+    if res is not None:
+        if res.shape != out.shape:
+            raise RuntimeError(f"conv: residual shape {res.shape} != output shape {out.shape}")
+        if res.f32 is not None:
+            d.res_f32 = _p(res.f32)
+        else:
+            d.res_hi, d.res_lo = _p(res.hi), _p(res.lo)
+    d.out_f32, d.out_hi, d.out_lo, d.stats = _p(out.f32), _p(out.hi), _p(out.lo), _p(stats)
+    d.N, d.D, d.H, d.W, d.Cin, d.Cout = N, D, H, W, pw.Cin, pw.Cout
+    d.KD, d.KH, d.KW = pw.k
+    d.Cout_pad, d.gn_groups, d.act = pw.Cout_pad, stats_groups, act
+    L = _lib.load()
+    mode = mode or _CONV_MODE
+    use_tc = mode == "tc" or (mode == "auto" and L.mp_conv_tc_supported(ctypes.byref(d)) == 1)
+    flops = 2 * N * D * H * W * pw.Cout * pw.Cin * pw.k[0] * pw.k[1] * pw.k[2]
+    with _Prof("conv_tc" if use_tc else "conv_simt", flops):
+        if use_tc:
+            _lib.check(L.mp_conv_tc(ctypes.byref(d), _stream()), "mp_conv_tc")
+        else:
+            _lib.check(L.mp_conv_simt(ctypes.byref(d), _stream()), "mp_conv_simt")
+    _count()
+    return out, stats
+
+
+# ----------------------------------------------------------------------------------------------------- warping
+def grid_sample3d(v: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
+    """F.grid_sample(v, grid, 'bilinear', 'border', align_corners=True) for NCDHW fp32 (model.py:1062)."""
+    _chk_cuda(v, torch.float32, "grid_sample3d v")
+    _chk_cuda(grid, torch.float32, "grid_sample3d grid")
+    N, C, D, H, W = v.shape
+    Ng, Do, Ho, Wo, three = grid.shape
+    if Ng != N or three != 3:
+        raise RuntimeError("grid_sample3d: grid must be [N, Do, Ho, Wo, 3]")
+    out = torch.empty((N, C, Do, Ho, Wo), dtype=torch.float32, device=v.device)
+    L = _lib.load()
+    _lib.check(L.mp_grid_sample3d(_p(v), _p(grid), _p(out), N, C, D, H, W, Do, Ho, Wo, _stream()), "mp_grid_sample3d")
+    _count()
+    return out
+
+
+def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(v, torch.float32, "apply_warping_field v")
+    _chk_cuda(warp_field, torch.float32, "apply_warping_field warp_field")
+    N, C, D, H, W = v.shape
+    Nf, three, Df, Hf, Wf = warp_field.shape
+    if Nf != N or three != 3:
+        raise RuntimeError("apply_warping_field: warp_field must be [N, 3, Df, Hf, Wf]")
+    out = torch.empty_like(v)
+    L = _lib.load()
+    _lib.check(L.mp_apply_warping_field(_p(v), _p(warp_field), _p(out), N, C, D, H, W, Df, Hf, Wf, _stream()),
+               "mp_apply_warping_field")
+    _count()
+    return out
+
+
+def warp_field(em_cl: torch.Tensor, theta: torch.Tensor, G: int = 64) -> torch.Tensor:
+    """em_cl [N,E,E,E,3] fp32, theta [N,3,4] -> [N,3,G,G,G] (model.py:965-973)."""
+    _chk_cuda(em_cl, torch.float32, "warp_field em")
+    _chk_cuda(theta, torch.float32, "warp_field theta")
+    N, E = em_cl.shape[0], em_cl.shape[1]
+    out = torch.empty((N, 3, G, G, G), dtype=torch.float32, device=em_cl.device)
+    L = _lib.load()
+    _lib.check(L.mp_warp_field(_p(em_cl), _p(theta), _p(out), N, E, G, _stream()), "mp_warp_field")
+    _count()
+    return out
+
+
+def warp_fused(v: Act, em_cl: torch.Tensor, theta: torch.Tensor, sum_d: bool, G: int = 64, f32: bool = True,
+               split: bool = False) -> Act:
+    """Fused flow->grid->trilinear gather on a CL volume (+ optional sum over D).  v.N may be 1 (shared source)."""
+    _chk_cuda(em_cl, torch.float32, "warp_fused em")
+    _chk_cuda(theta, torch.float32, "warp_fused theta")
+    N, E = em_cl.shape[0], em_cl.shape[1]
+    Nv, D, H, W, C = v.shape
+    out = _alloc((N, 1 if sum_d else D, H, W, C), em_cl.device, f32, split)
+    L = _lib.load()
+    # algorithmic bytes: source volume(s) + 16^3 flow + the outputs actually written
+    nbytes = Nv * D * H * W * C * 4 + N * E * E * E * 3 * 4
+    nbytes += N * (1 if sum_d else D) * H * W * C * 4 * (int(f32) + int(split))
+    with _Prof("warp_fused_sum" if sum_d else "warp_fused", 0, nbytes):
+        _lib.check(L.mp_warp_fused_cl(_p(v.f32), _p(em_cl), _p(theta), _p(out.f32), _p(out.hi), _p(out.lo), N, Nv, C,
+                                      D, H, W, E, G, 1 if sum_d else 0, _stream()), "mp_warp_fused_cl")
+    _count()
+    return out
+
+
+def blur_subsample(x: torch.Tensor, kernel2d: torch.Tensor, step: int) -> torch.Tensor:
+    _chk_cuda(x, torch.float32, "blur_subsample x")
+    _chk_cuda(kernel2d, torch.float32, "blur_subsample kernel")
+    N, C, H, W = x.shape
+    ks = kernel2d.shape[-1]
+    out = torch.empty((N, C, H // step, W // step), dtype=torch.float32, device=x.device)
+    L = _lib.load()
+    _lib.check(L.mp_blur_subsample(_p(x), _p(kernel2d), _p(out), N, C, H, W, ks, step, _stream()), "mp_blur_subsample")
+    _count()
+    return out

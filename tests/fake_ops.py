@@ -1,0 +1,203 @@
+"""TEST-ONLY torch-CPU emulation of the libmpb200 entry points, installed over `megaportrait_hack_b200.ops`.
+
+Purpose: exercise the HOST logic of the product modules (weight packing, BatchNorm / weight-standardisation /
+1x1-chain folding, row permutations, layout bookkeeping, residual wiring, split-bf16 operand format) against the
+oracle on a box without a GPU.  It emulates what each kernel computes, including the bf16 hi/lo operand rounding,
+with ATen CPU ops.  It is never imported by the product and never used by a `-m gpu` test.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+from megaportrait_hack_b200 import model as M
+from megaportrait_hack_b200 import ops
+from megaportrait_hack_b200.ops import Act
+
+
+def _split(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def _val(a: Act) -> torch.Tensor:
+    return a.f32 if a.f32 is not None else a.hi.float() + a.lo.float()
+
+
+def _mk(x: torch.Tensor, f32: bool, split: bool) -> Act:
+    a = Act(tuple(x.shape))
+    if f32:
+        a.f32 = x.contiguous()
+    if split:
+        a.hi, a.lo = _split(x.contiguous())
+    return a
+
+
+def _to_ncdhw(x):  # [N,D,H,W,C] -> [N,C,D,H,W]
+    return x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def _to_cl(x):
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def _act(v, code):
+    if code == ops.ACT_RELU:
+        return F.relu(v)
+    if code == ops.ACT_RELU_TANH:
+        return torch.tanh(F.relu(v))
+    if code == ops.ACT_SIGMOID:
+        return torch.sigmoid(v)
+    return v
+
+
+def from_nchw(x, f32=False, split=True):
+    if x.dim() == 4:
+        x = x.unsqueeze(2)
+    return _mk(_to_cl(x), f32, split)
+
+
+def to_nchw(a, ndim=5):
+    y = _to_ncdhw(_val(a))
+    return y if ndim == 5 else y.squeeze(2)
+
+
+def ensure_split(a):
+    if a.hi is None:
+        a.hi, a.lo = _split(a.f32)
+    return a
+
+
+def avgpool2(a, pool_d, f32=True, split=False):
+    y = F.avg_pool3d(_to_ncdhw(a.f32), (pool_d, 2, 2), (pool_d, 2, 2))
+    return _mk(_to_cl(y), f32, split)
+
+
+def upsample2x_linear(a, up_d, f32=False, split=True):
+    x = _to_ncdhw(_val(a))
+    if up_d == 1:
+        y = F.interpolate(x.squeeze(2), scale_factor=2, mode="bilinear", align_corners=True).unsqueeze(2)
+    else:
+        y = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+    return _mk(_to_cl(y), f32, split)
+
+
+def upsample_nearest(a, scale, f32=False, split=True):
+    y = F.interpolate(_to_ncdhw(a.f32), scale_factor=tuple(float(s) for s in scale), mode="nearest")
+    return _mk(_to_cl(y), f32, split)
+
+
+def new_stats(N, G, device):
+    return torch.zeros((N, G, 2), dtype=torch.float64)
+
+
+def _stats_of(v, G):
+    N, C = v.shape[0], v.shape[-1]
+    x = v.double().reshape(N, -1, G, C // G)
+    return torch.stack((x.sum(dim=(1, 3)), (x * x).sum(dim=(1, 3))), dim=-1)
+
+
+def gn_stats(a, G):
+    return _stats_of(a.f32, G)
+
+
+def gn_finalize(stats, a_shape, G, gamma=None, beta=None, gamma2=None, beta2=None, eps=1e-5):
+    N, D, H, W, C = a_shape
+    cnt = D * H * W * (C // G)
+    mean = stats[..., 0] / cnt
+    var = (stats[..., 1] / cnt - mean * mean).clamp_min(0)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    a = rstd.repeat_interleave(C // G, dim=1)
+    b = (-mean * rstd).repeat_interleave(C // G, dim=1)
+    if gamma is not None:
+        a, b = a * gamma.double(), b * gamma.double()
+    if beta is not None:
+        b = b + beta.double()
+    if gamma2 is not None:
+        a, b = a * gamma2.double(), b * gamma2.double()
+    if beta2 is not None:
+        b = b + beta2.double()
+    return torch.stack((a, b), dim=-1).float()
+
+
+def affine_act(a, ab, res=None, act=ops.ACT_NONE, f32=False, split=True):
+    v = a.f32
+    if ab is not None:
+        v = v * ab[:, None, None, None, :, 0] + ab[:, None, None, None, :, 1]
+    if res is not None:
+        v = v + _val(res)
+    return _mk(_act(v, act), f32, split)
+
+
+def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=0, mode=None):
+    ensure_split(a)
+    x = _to_ncdhw(a.hi.float() + a.lo.float())
+    kd, kh, kw = pw.k
+    w = (pw.w_hi.float() + pw.w_lo.float())[: pw.Cout].view(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3)
+    y = F.conv3d(x, w.contiguous(), pw.bias, padding=(kd // 2, kh // 2, kw // 2))
+    v = _to_cl(y)
+    if res is not None:
+        v = v + _val(res)
+    v = _act(v, act)
+    st = _stats_of(v, stats_groups) if stats_groups else None
+    return _mk(v, f32, split), st
+
+
+def grid_sample3d(v, grid):
+    return F.grid_sample(v, grid, mode="bilinear", padding_mode="border", align_corners=True)
+
+
+def apply_warping_field_ncdhw(v, wf):
+    import gbase_oracle as O
+    return O.apply_warping_field(v, wf)
+
+
+def warp_field(em_cl, theta, G=64):
+    N = em_cl.shape[0]
+    rt = F.affine_grid(theta, (N, 1, G, G, G), align_corners=False).permute(0, 4, 1, 2, 3)
+    em = em_cl.permute(0, 4, 1, 2, 3)
+    if em.shape[2] > 1 or em.abs().sum() > 0:
+        rt = rt + F.interpolate(em, size=(G, G, G), mode="trilinear", align_corners=False)
+    return rt.contiguous()
+
+
+def warp_fused(v, em_cl, theta, sum_d, G=64, f32=True, split=False):
+    import gbase_oracle as O
+    N = em_cl.shape[0]
+    vol = _to_ncdhw(v.f32)
+    if vol.shape[0] == 1 and N > 1:
+        vol = vol.expand(N, -1, -1, -1, -1)
+    out = O.apply_warping_field(vol, warp_field(em_cl, theta, G))
+    if sum_d:
+        out = out.sum(dim=2, keepdim=True)
+    return _mk(_to_cl(out), f32, split)
+
+
+def blur_subsample(x, kernel2d, step):
+    ks = kernel2d.shape[-1]
+    C = x.shape[1]
+    y = F.conv2d(F.pad(x, (ks // 2,) * 4), kernel2d.view(1, 1, ks, ks).repeat(C, 1, 1, 1), groups=C)
+    return y[:, :, ::step, ::step].contiguous()
+
+
+_NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample_nearest", "new_stats",
+          "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
+          "warp_fused", "blur_subsample"]
+
+
+@contextlib.contextmanager
+def installed():
+    saved = {n: getattr(ops, n) for n in _NAMES}
+    saved_req = M._require_inference
+    try:
+        for n in _NAMES:
+            setattr(ops, n, globals()[n])
+        M._require_inference = lambda *a, **k: None
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)
+        M._require_inference = saved_req

@@ -1,0 +1,135 @@
+"""Stage and end-to-end parity of the B200 Gbase path against the CPU oracle (same seeded weights, same inputs).
+Runs on the B200 box: `pytest -m gpu`.  Tolerances: RGB max-abs <= 1e-3 (BASELINE.json north_star); every
+intermediate stage <= 2e-4 relative to its abs-max (RGB is insensitive to the warp path)."""
+import os
+
+import pytest
+import torch
+
+from conftest import load_frames, synthetic_pair
+
+pytestmark = pytest.mark.gpu
+
+RGB_TOL = 1e-3
+STAGE_TOL = 2e-4
+MOTION_TOL = 2e-2     # Emtn / ResNet-50 descriptor run as stock cuDNN modules with TF32 allowed (not hot-path rows)
+
+
+def _ncdhw(a):
+    v = a.f32 if a.f32 is not None else a.hi.float() + a.lo.float()
+    return v.permute(0, 4, 1, 2, 3).contiguous().cpu()
+
+
+def rel(got, ref):
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def gbase(seeded_sd):
+    from megaportrait_hack_b200 import lib, model, seeded
+    lib.build()
+    G = model.Gbase().eval()
+    main = {k: v for k, v in seeded_sd.items() if not k.startswith(seeded.ROTNET_PREFIX)}
+    missing = G.load_state_dict(main, strict=False)
+    assert not missing.unexpected_keys and all(k.startswith("image_pyramid.") for k in missing.missing_keys)
+    G.motionEncoder.rotation_net.model.load_state_dict(
+        {k[len(seeded.ROTNET_PREFIX):]: v for k, v in seeded_sd.items() if k.startswith(seeded.ROTNET_PREFIX)})
+    return G.to("cuda")
+
+
+@pytest.fixture(scope="module")
+def oracle_synth(seeded_sd):
+    import gbase_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    xs, xd = synthetic_pair(3)
+    with torch.no_grad():
+        rgb, pyr, st = O.gbase_forward_shared_source(xs, xd, seeded_sd, stages=True)
+    return xs, xd, rgb, pyr, st
+
+
+def test_stage_parity_exact_motion(gbase, oracle_synth):
+    """Every hot-path stage against the oracle, with Emtn / descriptor in exact fp32 so stages are comparable."""
+    xs, xd, rgb_o, pyr_o, st = oracle_synth
+    gbase.tf32_motion = False
+    gbase.appearanceEncoder.tf32_descriptor = False
+    try:
+        src = gbase.encode_source(xs.cuda(), keep_stages=True)
+        rgb, pyr, drv = gbase.drive(src, xd.cuda(), keep_stages=True)
+    finally:
+        gbase.tf32_motion = True
+        gbase.appearanceEncoder.tf32_descriptor = True
+    checks = {
+        "vs": (_ncdhw(src["vs"]), st["vs"], STAGE_TOL), "es": (src["es"].cpu(), st["es"], STAGE_TOL),
+        "zs": (src["zs"].cpu(), st["zs"], STAGE_TOL), "ts": (src["ts"].cpu(), st["ts"], STAGE_TOL),
+        "Rs": (src["Rs"].cpu(), st["Rs"], STAGE_TOL),
+        "vc": (_ncdhw(src["vc"]), st["vc"], STAGE_TOL), "vc2d": (_ncdhw(src["vc2d"]), st["vc2d"], STAGE_TOL),
+        "zd": (drv["zd"].cpu(), st["zd"], STAGE_TOL), "td": (drv["td"].cpu(), st["td"], STAGE_TOL),
+        "projected": (_ncdhw(drv["projected"]).squeeze(2), st["projected"], STAGE_TOL),
+    }
+    errs = {k: rel(g, r) for k, (g, r, _) in checks.items()}
+    print("stage rel errors:", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, (g, r, tol) in checks.items():
+        assert errs[k] <= tol, f"stage {k}: {errs[k]:.3e} > {tol}"
+    assert (rgb.cpu() - rgb_o).abs().max().item() <= RGB_TOL
+    for k in pyr_o:
+        assert (pyr[k].cpu() - pyr_o[k]).abs().max().item() <= RGB_TOL
+
+
+def test_rgb_parity_default_settings_shared_source(gbase, oracle_synth):
+    """BASELINE config 2 semantics (1 source x N drivers) with the bench's settings (TF32 motion encoder)."""
+    xs, xd, rgb_o, pyr_o, st = oracle_synth
+    src = gbase.encode_source(xs.cuda(), keep_stages=True)
+    rgb, pyr, drv = gbase.drive(src, xd.cuda(), keep_stages=True)
+    err = (rgb.cpu() - rgb_o).abs().max().item()
+    print("rgb max-abs (tf32 motion):", err, "zd rel:", rel(drv["zd"].cpu(), st["zd"]))
+    assert err <= RGB_TOL
+    assert rel(drv["zd"].cpu(), st["zd"]) <= MOTION_TOL
+    assert rel(_ncdhw(src["vc2d"]), st["vc2d"]) <= 5 * STAGE_TOL
+
+
+def test_forward_signature_and_real_frames(gbase, seeded_sd):
+    """BASELINE config 1: the two real junk/ frames through `Gbase.forward(xs, xd) -> (img, pyramids)`."""
+    import gbase_oracle as O
+    xs, xd = load_frames()
+    with torch.no_grad():
+        rgb_o, pyr_o = O.gbase_forward(xs, xd, seeded_sd)
+        out = gbase(xs.cuda(), xd.cuda())
+    assert isinstance(out, tuple) and len(out) == 2 and set(out[1]) == {"prediction_0.5", "prediction_0.25"}
+    assert out[0].shape == (1, 3, 512, 512) and out[1]["prediction_0.25"].shape == (1, 3, 128, 128)
+    assert (out[0].cpu() - rgb_o).abs().max().item() <= RGB_TOL
+    assert (out[1]["prediction_0.5"].cpu() - pyr_o["prediction_0.5"]).abs().max().item() <= RGB_TOL
+
+
+def test_batch_invariance_and_determinism(gbase):
+    xs, xd = synthetic_pair(4)
+    src = gbase.encode_source(xs.cuda())
+    a, _ = gbase.drive(src, xd.cuda())
+    b, _ = gbase.drive(src, xd.cuda())
+    assert torch.equal(a, b), "run-to-run determinism"
+    c, _ = gbase.drive(src, xd[1:3].cuda())
+    assert (a[1:3] - c).abs().max().item() <= 2e-5, "batch invariance"
+    # reference semantics Bs == Bd (model.py:993): per-sample sources
+    full, _ = gbase(xs.expand(2, -1, -1, -1).contiguous().cuda(), xd[:2].cuda())
+    assert (full - a[:2]).abs().max().item() <= 2e-5
+
+
+def test_module_level_dropins(gbase, oracle_synth):
+    """The PairwiseTransferLoss access pattern (model.py:2192-2214): sub-modules called one by one on NCDHW tensors."""
+    from megaportrait_hack_b200 import model
+    xs, xd, rgb_o, pyr_o, st = oracle_synth
+    w = gbase.warp_generator_s2c(st["Rs"].cuda(), st["ts"].cuda(), st["zs"].cuda(), st["es"].cuda())
+    assert w.shape == (1, 3, 64, 64, 64) and rel(w.cpu(), st["w_s2c"]) <= STAGE_TOL
+    vc = model.apply_warping_field(st["vs"].cuda(), w)
+    assert rel(vc.cpu(), st["vc"]) <= STAGE_TOL
+    vc2d = gbase.G3d(st["vc"].cuda())
+    assert rel(vc2d.cpu(), st["vc2d"]) <= STAGE_TOL
+    img = gbase.G2d(st["projected"].cuda())
+    assert (img.cpu() - st["rgb"]).abs().max().item() <= RGB_TOL
+    with pytest.raises(AssertionError):
+        gbase.warp_generator_c2d(st["Rs"].cuda(), st["ts"].cuda(), st["zs"].cuda(), st["es"].cuda().repeat(2, 1))
+
+
+def test_no_cpu_fallback(gbase):
+    from megaportrait_hack_b200 import model
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.G2d(96).eval()(torch.zeros(1, 96, 64, 64))

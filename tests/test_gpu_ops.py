@@ -1,0 +1,274 @@
+"""Op-level parity of every libmpb200 kernel family (through the C ABI) against ATen-CPU fp32 / the oracle.
+Runs on the B200 box: `pytest -m gpu`."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from megaportrait_hack_b200 import lib, ops as _ops
+    lib.build()
+    lib.load()
+    assert lib.load().mp_device_supported() == 1, "tests must run on an sm_100 device"
+    return _ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def cl_to_ncdhw(t):
+    return t.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def val(a):
+    return (a.f32 if a.f32 is not None else a.hi.float() + a.lo.float()).cpu()
+
+
+def relerr(got, ref):
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+# ----------------------------------------------------------------------------------------------------- layout
+@pytest.mark.parametrize("shape", [(2, 3, 1, 40, 52), (1, 96, 4, 8, 16), (3, 70, 2, 5, 7)])
+def test_layout_roundtrip_and_split(ops, shape):
+    x = rnd(*shape, seed=1)
+    a = ops.from_nchw(x.to(DEV), f32=True, split=True)
+    assert torch.equal(a.f32.cpu(), x.permute(0, 2, 3, 4, 1).contiguous())
+    # split planes: hi = RNE bf16, hi + lo carries >= 16 mantissa bits
+    hi = a.hi.float().cpu()
+    assert torch.equal(hi, a.f32.cpu().to(torch.bfloat16).float())
+    rec = (a.hi.float() + a.lo.float()).cpu()
+    assert ((rec - a.f32.cpu()).abs() <= a.f32.cpu().abs() * 2.0 ** -16 + 1e-38).all()
+    assert torch.equal(ops.to_nchw(ops.Act(a.shape, f32=a.f32), 5).cpu(), x)
+    back = ops.to_nchw(ops.Act(a.shape, hi=a.hi, lo=a.lo), 5).cpu()
+    assert torch.equal(back, rec.permute(0, 4, 1, 2, 3).contiguous())
+
+
+def test_avgpool_and_upsample(ops):
+    x = rnd(2, 8, 4, 6, 10, seed=2)
+    a = ops.from_nchw(x.to(DEV), f32=True, split=True)
+    p3 = ops.avgpool2(a, 2, f32=True, split=False)
+    assert relerr(cl_to_ncdhw(val(p3)), F.avg_pool3d(x, 2, 2)) < 1e-6
+    p2 = ops.avgpool2(a, 1, f32=True, split=False)
+    assert relerr(cl_to_ncdhw(val(p2)), F.avg_pool3d(x, (1, 2, 2), (1, 2, 2))) < 1e-6
+    u3 = ops.upsample2x_linear(ops.Act(a.shape, f32=a.f32), 2, f32=True, split=False)
+    assert relerr(cl_to_ncdhw(val(u3)), F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)) < 2e-6
+    u2 = ops.upsample2x_linear(ops.Act(a.shape, f32=a.f32), 1, f32=True, split=False)
+    ref2 = torch.stack([F.interpolate(x[:, :, d], scale_factor=2, mode="bilinear", align_corners=True)
+                        for d in range(x.shape[2])], dim=2)
+    assert relerr(cl_to_ncdhw(val(u2)), ref2) < 2e-6
+    # split-in / split-out variant
+    u2s = ops.upsample2x_linear(ops.Act(a.shape, hi=a.hi, lo=a.lo), 1, f32=False, split=True)
+    assert relerr(cl_to_ncdhw(val(u2s)), ref2) < 4e-5
+    un = ops.upsample_nearest(ops.Act(a.shape, f32=a.f32), (1, 2, 2), f32=True, split=False)
+    assert torch.equal(cl_to_ncdhw(val(un)), F.interpolate(x, scale_factor=(1.0, 2.0, 2.0), mode="nearest"))
+    un = ops.upsample_nearest(ops.Act(a.shape, f32=a.f32), (2, 2, 2), f32=True, split=False)
+    assert torch.equal(cl_to_ncdhw(val(un)), F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+@pytest.mark.parametrize("C,G", [(96, 32), (64, 32), (32, 32), (3, 1), (768, 32)])
+def test_group_norm(ops, C, G):
+    x = rnd(2, C, 3, 8, 8, seed=3) * 2 + 0.7
+    gamma, beta = rnd(C, seed=4) * 0.2 + 1, rnd(C, seed=5) * 0.1
+    g2, b2 = rnd(C, seed=6) * 0.2 + 1, rnd(C, seed=7) * 0.1
+    res = rnd(2, C, 3, 8, 8, seed=8)
+    a = ops.from_nchw(x.to(DEV), f32=True, split=False)
+    r = ops.from_nchw(res.to(DEV), f32=True, split=False)
+    out = ops.group_norm_act(a, G, None, gamma.to(DEV), beta.to(DEV), g2.to(DEV), b2.to(DEV), res=r,
+                             act=ops.ACT_RELU, f32=True, split=True)
+    ref = F.relu(F.group_norm(x, G, gamma, beta) * g2.view(1, C, 1, 1, 1) + b2.view(1, C, 1, 1, 1) + res)
+    assert relerr(cl_to_ncdhw(out.f32.cpu()), ref) < 3e-6
+    assert relerr(cl_to_ncdhw((out.hi.float() + out.lo.float()).cpu()), ref) < 3e-5
+    out = ops.group_norm_act(a, G, None, act=ops.ACT_RELU_TANH, f32=True, split=False)
+    assert relerr(cl_to_ncdhw(out.f32.cpu()), torch.tanh(F.relu(F.group_norm(x, G)))) < 3e-6
+
+
+# ----------------------------------------------------------------------------------------------------- conv
+CONV_CASES = [
+    # name,            N, Cin, Cout, D,  H,   W,  k,         tc?
+    ("stem7x7",        1, 3,   64,   1,  40,  48, (1, 7, 7), False),
+    ("head64to3",      1, 64,  3,    1,  16,  128, (1, 3, 3), True),
+    ("g2d_512",        2, 512, 512,  1,  64,  64, (1, 3, 3), True),
+    ("g2d_in_1x1",     2, 96,  512,  1,  64,  64, (1, 1, 1), True),
+    ("g2d_up_w128",    1, 256, 128,  1,  16,  128, (1, 3, 3), True),
+    ("g2d_up_w256",    1, 128, 64,   1,  4,   256, (1, 3, 3), True),
+    ("vol96",          1, 96,  96,   16, 64,  64, (3, 3, 3), True),
+    ("g3d_192",        1, 96,  192,  8,  32,  32, (3, 3, 3), True),
+    ("g3d_384",        1, 192, 384,  4,  16,  16, (3, 3, 3), True),
+    ("g3d_768",        1, 384, 768,  2,  8,   8,  (3, 3, 3), True),
+    ("g3d_sc_1x1",     1, 768, 384,  2,  8,   8,  (1, 1, 1), True),
+    ("flow_l1",        3, 512, 256,  4,  1,   1,  (3, 3, 3), False),
+    ("flow_l2",        3, 256, 128,  8,  2,   2,  (3, 3, 3), False),
+    ("flow_l4",        2, 64,  32,   16, 8,   8,  (3, 3, 3), True),
+    ("flow_head",      2, 32,  3,    16, 16,  16, (3, 3, 3), True),
+]
+
+
+def _conv_case(ops, case, mode, with_extras):
+    name, N, Cin, Cout, D, H, W, k, _ = case
+    fan_in = Cin * k[0] * k[1] * k[2]
+    x = rnd(N, Cin, D, H, W, seed=11)
+    w = rnd(Cout, Cin, *k, seed=12) / math.sqrt(fan_in)
+    b = rnd(Cout, seed=13) * 0.1
+    ref = F.conv3d(x, w, b, padding=tuple(i // 2 for i in k))
+    a = ops.from_nchw(x.to(DEV), f32=False, split=True)
+    pw = ops.pack_conv(w, b, DEV)
+    res = None
+    G = 0
+    act = ops.ACT_NONE
+    if with_extras:
+        r = rnd(N, Cout, D, H, W, seed=14)
+        res = ops.from_nchw(r.to(DEV), f32=True, split=False)
+        act = ops.ACT_RELU
+        ref = F.relu(ref + r)
+        G = 32 if Cout % 32 == 0 else 1
+    out, st = ops.conv(a, pw, res=res, act=act, f32=True, split=True, stats_groups=G, mode=mode)
+    torch.cuda.synchronize()
+    got = cl_to_ncdhw(out.f32.cpu())
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item() / scale
+    assert err < 3e-5, f"{name}/{mode}: rel-to-absmax err {err:.3e}"
+    got_s = cl_to_ncdhw((out.hi.float() + out.lo.float()).cpu())
+    assert (got_s - ref).abs().max().item() / scale < 6e-5
+    if G:
+        cpg = Cout // G
+        v = out.f32.double().cpu().reshape(N, -1, G, cpg)
+        ref_st = torch.stack((v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))), dim=-1)
+        assert torch.allclose(st.cpu(), ref_st, rtol=1e-6, atol=1e-6 * ref_st.abs().max().item())
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("extras", [False, True], ids=["plain", "res_relu_stats"])
+def test_conv_simt(ops, case, extras):
+    if case[0] in ("vol96", "g2d_512") and extras:
+        pytest.skip("large case covered once")
+    _conv_case(ops, case, "simt", extras)
+
+
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[-1]], ids=[c[0] for c in CONV_CASES if c[-1]])
+@pytest.mark.parametrize("extras", [False, True], ids=["plain", "res_relu_stats"])
+def test_conv_tc(ops, case, extras):
+    _conv_case(ops, case, "tc", extras)
+
+
+def test_conv_tc_rejects_unsupported(ops):
+    x = rnd(1, 3, 1, 16, 16, seed=1)
+    a = ops.from_nchw(x.to(DEV))
+    pw = ops.pack_conv(rnd(16, 3, 3, 3, seed=2), None, DEV)
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        ops.conv(a, pw, mode="tc")
+
+
+# ----------------------------------------------------------------------------------------------------- warping
+def _grids(kind, N, D, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "spread":       # identity + U(-0.1, 0.1): touches the whole volume, mostly coalesced
+        zz, yy, xx = torch.meshgrid(torch.linspace(-1, 1, D), torch.linspace(-1, 1, H), torch.linspace(-1, 1, W),
+                                    indexing="ij")
+        base = torch.stack((xx, yy, zz), -1)[None].repeat(N, 1, 1, 1, 1)
+        return base + (torch.rand(N, D, H, W, 3, generator=g) - 0.5) * 0.2
+    if kind == "adversarial":  # random gather + border clamp
+        return (torch.rand(N, D, H, W, 3, generator=g) - 0.5) * 3.0
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["spread", "adversarial"])
+def test_grid_sample3d(ops, kind):
+    N, C, D, H, W = 2, 12, 16, 64, 64
+    v = rnd(N, C, D, H, W, seed=2)
+    grid = _grids(kind, N, D, H, W, 3 if kind == "spread" else 4)
+    ref = F.grid_sample(v, grid, mode="bilinear", padding_mode="border", align_corners=True)
+    got = ops.grid_sample3d(v.to(DEV), grid.to(DEV)).cpu()
+    assert (got - ref).abs().max().item() <= 1e-5
+
+
+def test_grid_sample3d_different_output_size(ops):
+    v = rnd(1, 5, 7, 9, 11, seed=5)
+    grid = (torch.rand(1, 3, 4, 6, 3, generator=torch.Generator().manual_seed(6)) - 0.5) * 2.4
+    ref = F.grid_sample(v, grid, mode="bilinear", padding_mode="border", align_corners=True)
+    assert (ops.grid_sample3d(v.to(DEV), grid.to(DEV)).cpu() - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("amp", [1.0, 40.0])
+def test_apply_warping_field_matches_oracle(ops, amp):
+    import gbase_oracle as O
+    g = torch.Generator().manual_seed(8)
+    v = torch.randn(2, 10, 16, 64, 64, generator=g)
+    wf = (torch.rand(2, 3, 64, 64, 64, generator=g) - 0.3) * amp   # amp=40 leaves the degenerate corner regime
+    ref = O.apply_warping_field(v, wf)
+    got = ops.apply_warping_field_ncdhw(v.to(DEV), wf.to(DEV)).cpu()
+    assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def _theta(N, seed, invert):
+    import gbase_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    R = (torch.rand(N, 3, generator=g) - 0.5) * 120
+    t = (torch.rand(N, 3, generator=g) - 0.5) * 0.4
+    return O.affine_3x4(R, t, invert).contiguous()
+
+
+def test_warp_field_and_fused_warp(ops):
+    import gbase_oracle as O
+    N, C = 3, 96
+    g = torch.Generator().manual_seed(9)
+    em = torch.rand(N, 3, 16, 16, 16, generator=g)                 # FlowField range [0,1)
+    theta = _theta(N, 10, True)
+    rt = F.affine_grid(theta, (N, 1, 64, 64, 64), align_corners=False).permute(0, 4, 1, 2, 3)
+    w64_ref = rt + F.interpolate(em, size=(64, 64, 64), mode="trilinear", align_corners=False)
+    em_cl = em.permute(0, 2, 3, 4, 1).contiguous().to(DEV)
+    w64 = ops.warp_field(em_cl, theta.to(DEV), 64).cpu()
+    assert (w64 - w64_ref).abs().max().item() <= 2e-6 * w64_ref.abs().max().item()
+    # fused: per-sample volumes, then one shared volume, with and without the depth sum
+    v = torch.randn(N, C, 16, 64, 64, generator=g)
+    ref = O.apply_warping_field(v, w64_ref)
+    va = ops.from_nchw(v.to(DEV), f32=True, split=False)
+    out = ops.warp_fused(va, em_cl, theta.to(DEV), sum_d=False, f32=True, split=True)
+    tol = 2e-5 * ref.abs().max().item()
+    assert (cl_to_ncdhw(out.f32.cpu()) - ref).abs().max().item() <= tol
+    assert (cl_to_ncdhw((out.hi.float() + out.lo.float()).cpu()) - ref).abs().max().item() <= 3 * tol
+    out = ops.warp_fused(va, em_cl, theta.to(DEV), sum_d=True, f32=True, split=False)
+    assert (cl_to_ncdhw(out.f32.cpu()).squeeze(2) - ref.sum(2)).abs().max().item() <= 16 * tol
+    v1 = ops.from_nchw(v[:1].contiguous().to(DEV), f32=True, split=False)
+    ref1 = O.apply_warping_field(v[:1].expand(N, -1, -1, -1, -1), w64_ref).sum(2)
+    out = ops.warp_fused(v1, em_cl, theta.to(DEV), sum_d=True, f32=True, split=False)
+    assert (cl_to_ncdhw(out.f32.cpu()).squeeze(2) - ref1).abs().max().item() <= 16 * tol
+
+
+def test_fused_warp_non_degenerate_flow(ops):
+    """The reference chain only ever samples corner voxels; drive the fused kernel with a large
+    synthetic 'flow' so that the whole volume is gathered."""
+    import gbase_oracle as O
+    N, C = 2, 96
+    g = torch.Generator().manual_seed(12)
+    em = torch.rand(N, 3, 16, 16, 16, generator=g) * 50.0
+    theta = _theta(N, 13, False) * 8.0
+    rt = F.affine_grid(theta, (N, 1, 64, 64, 64), align_corners=False).permute(0, 4, 1, 2, 3)
+    w64_ref = rt + F.interpolate(em, size=(64, 64, 64), mode="trilinear", align_corners=False)
+    v = torch.randn(N, C, 16, 64, 64, generator=g)
+    ref = O.apply_warping_field(v, w64_ref)
+    va = ops.from_nchw(v.to(DEV), f32=True, split=False)
+    out = ops.warp_fused(va, em.permute(0, 2, 3, 4, 1).contiguous().to(DEV), theta.to(DEV), sum_d=False)
+    got = cl_to_ncdhw(out.f32.cpu())
+    # coordinates of magnitude ~50 carry ~4e-6 absolute rounding => allow 1e-4 on O(1) data
+    assert (got - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    assert ((got - ref).abs() > 1e-5).float().mean().item() < 0.02
+
+
+def test_blur_subsample(ops):
+    import gbase_oracle as O
+    x = torch.rand(2, 3, 64, 96, generator=torch.Generator().manual_seed(14))
+    ref = O.image_pyramid(x)
+    for s, step in ((0.5, 2), (0.25, 4)):
+        k, _ = O.gaussian_kernel(s, 3)
+        got = ops.blur_subsample(x.to(DEV), k[0, 0].contiguous().to(DEV), step).cpu()
+        assert (got - ref["prediction_" + str(s)]).abs().max().item() <= 2e-6
