@@ -28,7 +28,8 @@ int mp_conv_validate(const mp_conv_desc* d, const char* who);
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;    // v1 kernel
+constexpr int NUM_THREADS2 = 320;   // v2: producer + MMA + 8 epilogue warps
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
@@ -49,7 +50,19 @@ struct TcParams {
   double* stats;
   int gn_groups, act;
   int64_t S;
+  int tiles_n, total_tiles;   // persistent kernel: tile id = m_tile * tiles_n + n_tile (n fastest => A shared in L2)
+  uint32_t epi_off;           // byte offset (from the aligned smem base) of the epilogue staging area
+  int b_resident;             // 1: the whole weight tile [taps*Cin x BN] stays in smem for the CTA's lifetime
+  uint32_t bres_off;          // byte offset of the resident weight area
 };
+
+struct __align__(16) bf16x8 {
+  bf16 v[8];
+};
+
+constexpr int EPI_COLS = 32;                 // epilogue column chunk
+constexpr int EPI_PITCH = EPI_COLS + 4;      // floats per staged row (+4: conflict-free 16-byte row writes)
+constexpr uint32_t EPI_BYTES = TILE_M * EPI_PITCH * 4 + TILE_M * 8;   // staging tile + per-row output offsets
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,7 +142,329 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// ------------------------------------------------------------------------------------------------ kernel
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ kernel v2
+// Persistent: grid = min(#tiles, #SMs); every role walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// TMEM holds TWO accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.  The epilogue stages 32-column
+// chunks in shared memory (padded rows) and writes them out with warp-contiguous 16-byte stores.
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
+k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* epi = reinterpret_cast<float*>(gen_base + p.epi_off);                    // [128][EPI_PITCH]
+  long long* row_off = reinterpret_cast<long long*>(gen_base + p.epi_off + TILE_M * EPI_PITCH * 4);   // [128]
+  const uint32_t bars = smem_base + p.epi_off + EPI_BYTES;   // full[S], empty[S], tmem_full[2], tmem_empty[2], bres
+  const uint32_t bres_bar = bars + (2 * p.STAGES + 4) * 8;
+  const uint32_t tmem_slot = bars + (2 * p.STAGES + 5) * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto full_bar = [&](int s) { return bars + s * 8; };
+  auto empty_bar = [&](int s) { return bars + (p.STAGES + s) * 8; };
+  auto tfull_bar = [&](int b) { return bars + (2 * p.STAGES + b) * 8; };
+  auto tempty_bar = [&](int b) { return bars + (2 * p.STAGES + 2 + b) * 8; };
+  const int taps = p.KD * p.KH * p.KW;
+  const int num_kb = taps * p.num_cchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);      // one arrival per epilogue warp
+    }
+    mbar_init(bres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int tile, int& n, int& d0, int& h0, int& w0, int& n0) {
+    n0 = (tile % p.tiles_n) * p.BN;
+    int t = tile / p.tiles_n;
+    w0 = (t % p.tiles_w) * p.BW; t /= p.tiles_w;
+    h0 = (t % p.tiles_h) * p.BH; t /= p.tiles_h;
+    d0 = (t % p.tiles_d) * p.BD;
+    n = t / p.tiles_d;
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      const int pd = p.KD / 2, ph = p.KH / 2, pw = p.KW / 2;
+      uint32_t kb = 0;
+      if (p.b_resident && (int)blockIdx.x < p.total_tiles) {
+        // tiles_n == 1: every tile of this CTA uses the same weights -> fetch them once
+        mbar_expect_tx(bres_bar, (uint32_t)num_kb * 2u * p.b_bytes);
+        for (int i = 0; i < num_kb; ++i) {
+          const uint32_t sb = smem_base + p.bres_off + (uint32_t)i * 2u * p.b_bytes;
+          tma_load_2d(sb, &map_b_hi, bres_bar, i * p.CCHUNK, 0);
+          tma_load_2d(sb + p.b_bytes, &map_b_lo, bres_bar, i * p.CCHUNK, 0);
+        }
+      }
+      const uint32_t tx = p.b_resident ? 2 * p.a_bytes : 2 * p.a_bytes + 2 * p.b_bytes;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n, d0, h0, w0, n0;
+        tile_coords(tile, n, d0, h0, w0, n0);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
+          for (int cc = 0; cc < p.num_cchunks; ++cc, ++kb) {
+            const int s = kb % p.STAGES;
+            const uint32_t ph_bit = (kb / p.STAGES) & 1;
+            mbar_wait(empty_bar(s), ph_bit ^ 1);
+            const uint32_t sa = smem_base + s * p.stage_bytes;
+            mbar_expect_tx(full_bar(s), tx);
+            const int c0 = cc * p.CCHUNK;
+            tma_load_5d(sa, &map_a_hi, full_bar(s), c0, w0 + kw - pw, h0 + kh - ph, d0 + kd - pd, n);
+            tma_load_5d(sa + p.a_bytes, &map_a_lo, full_bar(s), c0, w0 + kw - pw, h0 + kh - ph, d0 + kd - pd, n);
+            if (!p.b_resident) {
+              tma_load_2d(sa + 2 * p.a_bytes, &map_b_hi, full_bar(s), tap * p.Cin + c0, n0);
+              tma_load_2d(sa + 2 * p.a_bytes + p.b_bytes, &map_b_lo, full_bar(s), tap * p.Cin + c0, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const int ksteps = p.CCHUNK / 16;
+      uint32_t kb = 0, it = 0;
+      if (p.b_resident && (int)blockIdx.x < p.total_tiles) mbar_wait(bres_bar, 0);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t b = it & 1;
+        mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + b * p.BN;
+        for (int i = 0; i < num_kb; ++i, ++kb) {
+          const int s = kb % p.STAGES;
+          const uint32_t ph_bit = (kb / p.STAGES) & 1;
+          mbar_wait(full_bar(s), ph_bit);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + s * p.stage_bytes;
+          const uint32_t a_hi = sa, a_lo = sa + p.a_bytes;
+          const uint32_t b_hi = p.b_resident ? smem_base + p.bres_off + (uint32_t)i * 2u * p.b_bytes : sa + 2 * p.a_bytes;
+          const uint32_t b_lo = b_hi + p.b_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t ko = k * 32;
+            const uint64_t dah = make_smem_desc(a_hi + ko, p.sbo, p.layout_type);
+            const uint64_t dal = make_smem_desc(a_lo + ko, p.sbo, p.layout_type);
+            const uint64_t dbh = make_smem_desc(b_hi + ko, p.sbo, p.layout_type);
+            const uint64_t dbl = make_smem_desc(b_lo + ko, p.sbo, p.layout_type);
+            umma_bf16(d_tmem, dal, dbh, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, dah, dbl, p.idesc, 1u);
+            umma_bf16(d_tmem, dah, dbh, p.idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(b));
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9, 256 threads)
+    // Warp w may touch TMEM lanes (w % 4) * 32 .. +31; the two warps that share a lane quarter split every 32-column
+    // chunk into halves of 16 columns.  Two warps per scheduler keep the dependent-issue latency hidden.
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int half = (warp - 2) >> 2;          // which 16 columns of a chunk
+    const int r = q * 32 + lane;               // accumulator row == position inside the tile
+    const int et = threadIdx.x - 64;           // 0..255
+    const int cpg = p.gn_groups > 0 ? p.Cout / p.gn_groups : 1;
+    const bool vec4 = (p.Cout % 4) == 0, vec8 = (p.Cout % 8) == 0;
+    const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int n, d0, h0, w0, n0;
+      tile_coords(tile, n, d0, h0, w0, n0);
+      const uint32_t b = it & 1;
+      const int ww = r % p.BW, hh = (r / p.BW) % p.BH, dd = r / (p.BW * p.BH);
+      const int64_t pos = (((int64_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
+      const int64_t obase = pos * p.Cout;
+      if (half == 0) row_off[r] = obase;
+      mbar_wait(tfull_bar(b), (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = 0; c0 < p.BN; c0 += EPI_COLS) {
+        const int co0 = n0 + c0;
+        if (co0 >= p.Cout) break;              // padded output channels (uniform across the CTA)
+        const int ncol = min(min(EPI_COLS, p.BN - c0), p.Cout - co0);   // valid columns in this chunk (uniform)
+        const int hc = half * 16;              // my first column inside the chunk
+        const bool mine = hc < ncol;           // warp-uniform
+        const bool fast = (ncol == EPI_COLS) && vec4;
+        float v[16];
+        if (mine) {
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.BN + c0 + hc), v);
+          if (fast) {
+            if (bias_vec) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + hc + i));
+                v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+              }
+            } else if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co0 + hc + i);
+            }
+            if (p.res_f32) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 rr = *reinterpret_cast<const float4*>(p.res_f32 + obase + co0 + hc + i);
+                v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+              }
+            } else if (p.res_hi) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 rr = mp_load_split4(p.res_hi, p.res_lo, obase + co0 + hc + i);
+                v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (hc + i < ncol) {
+                const int64_t o = obase + co0 + hc + i;
+                if (p.bias) v[i] += __ldg(p.bias + co0 + hc + i);
+                if (p.res_f32) v[i] += p.res_f32[o];
+                else if (p.res_hi) v[i] += mp_join(p.res_hi[o], p.res_lo[o]);
+              }
+            }
+          }
+          if (p.act == MP_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (p.act != MP_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = mp_apply_act(v[i], p.act);
+          }
+          // stage my half row (16-byte stores; row pitch 36 floats => conflict-free across the warp)
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(epi + r * EPI_PITCH + hc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        epi_bar();
+        // ---- write-out: warp-contiguous rows (256 threads)
+        if (p.out_f32) {
+          if (vec4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int row = j * 32 + (et >> 3), cq = (et & 7) * 4;
+              if (cq < ncol)
+                *reinterpret_cast<float4*>(p.out_f32 + row_off[row] + co0 + cq) =
+                    *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + cq);
+            }
+          } else {
+            for (int j = 0; j < 16; ++j) {
+              const int row = j * 8 + (et >> 5);
+              if (lane < ncol) p.out_f32[row_off[row] + co0 + lane] = epi[row * EPI_PITCH + lane];
+            }
+          }
+        }
+        if (p.out_hi) {
+          if (vec8) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int row = j * 64 + (et >> 2), c8 = (et & 3) * 8;
+              if (c8 < ncol) {
+                const float4 x0 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8);
+                const float4 x1 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8 + 4);
+                const int64_t o = row_off[row] + co0 + c8;
+                bf16x8 h, l;
+                mp_split2(x0.x, h.v[0], l.v[0]); mp_split2(x0.y, h.v[1], l.v[1]); mp_split2(x0.z, h.v[2], l.v[2]);
+                mp_split2(x0.w, h.v[3], l.v[3]); mp_split2(x1.x, h.v[4], l.v[4]); mp_split2(x1.y, h.v[5], l.v[5]);
+                mp_split2(x1.z, h.v[6], l.v[6]); mp_split2(x1.w, h.v[7], l.v[7]);
+                *reinterpret_cast<bf16x8*>(p.out_hi + o) = h;
+                *reinterpret_cast<bf16x8*>(p.out_lo + o) = l;
+              }
+            }
+          } else {
+            for (int j = 0; j < 16; ++j) {
+              const int row = j * 8 + (et >> 5);
+              if (lane < ncol) {
+                const int64_t o = row_off[row] + co0 + lane;
+                mp_split2(epi[row * EPI_PITCH + lane], p.out_hi[o], p.out_lo[o]);
+              }
+            }
+          }
+        }
+        if (p.stats) {
+          // column sums over 16-row slabs: thread (slab = et / 32, col = lane)
+          if (lane < ncol) {
+            const int slab = et >> 5;
+            float sm = 0.f, sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = epi[(slab * 16 + j) * EPI_PITCH + lane];
+              sm += x; sq += x * x;
+            }
+            atomicAdd(&s_stats[2 * (c0 + lane)], (double)sm);
+            atomicAdd(&s_stats[2 * (c0 + lane) + 1], (double)sq);
+          }
+        }
+        epi_bar();                              // staging buffer may be overwritten
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(b));
+      if (p.stats) {
+        for (int c = et; c < p.BN; c += 256) {
+          const int co = n0 + c;
+          if (co < p.Cout) {
+            double* st = p.stats + ((int64_t)n * p.gn_groups + co / cpg) * 2;
+            atomicAdd(st, s_stats[2 * c]);
+            atomicAdd(st + 1, s_stats[2 * c + 1]);
+          }
+          s_stats[2 * c] = 0.0;
+          s_stats[2 * c + 1] = 0.0;
+        }
+        epi_bar();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel v1
+// First-generation kernel (one tile per CTA, epilogue not overlapped); kept for A/B runs (MPB200_TC_V1=1).
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
@@ -353,7 +688,15 @@ struct Plan {
   int tiles_m, tiles_n;
   uint32_t smem_bytes;
   CUtensorMapSwizzle swz;
+  bool v1;
 };
+
+bool use_v1() {
+  static int v = [] { const char* e = getenv("MPB200_TC_V1"); return (e && atoi(e)) ? 1 : 0; }();
+  return v != 0;
+}
+
+int g_num_sms[64] = {0};
 
 int next_pow2(int v) { int r = 32; while (r < v) r <<= 1; return r; }
 
@@ -379,7 +722,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.tiles_w = d->W / p.BW; p.tiles_h = d->H / p.BH; p.tiles_d = d->D / p.BD;
   pl.tiles_m = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
   // N tile: largest multiple-of-16 divisor of Cout_pad up to the cap, shrunk while the grid under-fills the GPU
-  static int bn_cap = [] { const char* e = getenv("MPB200_TC_BN_MAX"); int v = e ? atoi(e) : 128; return v < 16 ? 16 : (v > 256 ? 256 : v); }();
+  static int bn_cap = [] { const char* e = getenv("MPB200_TC_BN_MAX"); int v = e ? atoi(e) : 256; return v < 16 ? 16 : (v > 256 ? 256 : v); }();
   const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
   p.BN = 0;
   for (int c : cands)
@@ -387,16 +730,43 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   if (!p.BN) return fail("no N tile");
   while ((int64_t)pl.tiles_m * (d->Cout_pad / p.BN) < 148 && p.BN % 32 == 0 && p.BN > 32) p.BN /= 2;
   pl.tiles_n = d->Cout_pad / p.BN;
+  pl.v1 = use_v1();
+  const uint32_t fixed = 1024 /*align slack*/ + 1024 /*barriers, tmem slot*/ + 2 * 256 * sizeof(double) +
+                         (pl.v1 ? 0 : EPI_BYTES);
+  // weight-resident mode: one N tile and the whole [taps*Cin x BN] weight tile (hi+lo) fits beside >= 3 A stages;
+  // try the widest channel chunk first, then narrower ones (smaller A stages).
+  static int allow_res = [] { const char* e = getenv("MPB200_TC_NO_BRES"); return (e && atoi(e)) ? 0 : 1; }();
+  p.b_resident = 0;
+  const uint32_t ktot = (uint32_t)d->KD * d->KH * d->KW * d->Cin;
+  const uint32_t bres_bytes = ktot * (uint32_t)p.BN * 4u;
+  if (!pl.v1 && allow_res && pl.tiles_n == 1 && pl.tiles_m >= 4 * 148 && bres_bytes < SMEM_LIMIT) {
+    for (int cc = p.CCHUNK; cc >= 16; cc /= 2) {
+      const uint32_t a_stage = 2u * TILE_M * cc * 2u;
+      if (fixed + bres_bytes + 3 * a_stage <= SMEM_LIMIT && bres_bytes < (1u << 20)) {
+        p.b_resident = 1;
+        p.CCHUNK = cc;
+        p.layout_type = cc == 64 ? 2u : cc == 32 ? 4u : 6u;
+        pl.swz = cc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : cc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+        p.sbo = 8u * cc * 2u;
+        p.num_cchunks = d->Cin / cc;
+        break;
+      }
+    }
+  }
   p.a_bytes = TILE_M * p.CCHUNK * 2;
   p.b_bytes = p.BN * p.CCHUNK * 2;
-  p.stage_bytes = 2 * p.a_bytes + 2 * p.b_bytes;
-  const uint32_t fixed = 1024 /*align slack*/ + 1024 /*barriers, tmem slot*/ + 2 * 256 * sizeof(double);
-  int stages = (int)((SMEM_LIMIT - fixed) / p.stage_bytes);
+  p.stage_bytes = p.b_resident ? 2 * p.a_bytes : 2 * p.a_bytes + 2 * p.b_bytes;
+  const uint32_t avail = SMEM_LIMIT - fixed - (p.b_resident ? bres_bytes : 0);
+  int stages = (int)(avail / p.stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return fail("tile does not fit shared memory");
   p.STAGES = stages;
-  pl.smem_bytes = fixed + stages * p.stage_bytes;
-  p.tmem_cols = next_pow2(p.BN);
+  pl.smem_bytes = fixed + stages * p.stage_bytes + (p.b_resident ? bres_bytes : 0);
+  p.bres_off = stages * p.stage_bytes;
+  p.epi_off = p.bres_off + (p.b_resident ? bres_bytes : 0);
+  p.tmem_cols = next_pow2(pl.v1 ? p.BN : 2 * p.BN);
+  p.tiles_n = pl.tiles_n;
+  p.total_tiles = pl.tiles_m * pl.tiles_n;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   p.KD = d->KD; p.KH = d->KH; p.KW = d->KW;
@@ -404,7 +774,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.out_f32 = d->out_f32; p.out_hi = (bf16*)d->out_hi; p.out_lo = (bf16*)d->out_lo;
   p.stats = d->stats; p.gn_groups = d->gn_groups; p.act = d->act;
   p.S = (int64_t)d->D * d->H * d->W;
-  if (pl.tiles_m > 0x7fffffff) return fail("too many tiles");
+  if ((int64_t)pl.tiles_m * pl.tiles_n > 0x7fffffff) return fail("too many tiles");
   return 0;
 }
 
@@ -458,13 +828,24 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
       cudaError_t ae = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+      if (ae == cudaSuccess)
+        ae = cudaFuncSetAttribute(k_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
       MP_REQUIRE(ae == cudaSuccess, "mp_conv_tc: cannot opt in to %u B shared memory: %s", SMEM_LIMIT,
                  cudaGetErrorString(ae));
-      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+      if (dev >= 0 && dev < 64) {
+        attr_done[dev] = true;
+        cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+      }
+    }
+    if (pl.v1) {
+      dim3 grid((unsigned)pl.tiles_m, (unsigned)pl.tiles_n);
+      k_conv_tc<<<grid, NUM_THREADS, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p);
+    } else {
+      int sms = (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) ? g_num_sms[dev] : 148;
+      int grid = pl.p.total_tiles < sms ? pl.p.total_tiles : sms;
+      k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p);
     }
   }
-  dim3 grid((unsigned)pl.tiles_m, (unsigned)pl.tiles_n);
-  k_conv_tc<<<grid, NUM_THREADS, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p);
   MP_LAUNCH_CHECK("mp_conv_tc");
   return 0;
 }

@@ -110,6 +110,10 @@ CONV_CASES = [
     ("flow_l2",        3, 256, 128,  8,  2,   2,  (3, 3, 3), False),
     ("flow_l4",        2, 64,  32,   16, 8,   8,  (3, 3, 3), True),
     ("flow_head",      2, 32,  3,    16, 16,  16, (3, 3, 3), True),
+    # >= 592 M tiles and a single N tile: weight-resident mode of the persistent kernel
+    ("res_64to64",     2, 64,  64,   1,  256, 256, (1, 3, 3), True),
+    ("res_1x1_128to64", 2, 128, 64,  1,  256, 256, (1, 1, 1), True),
+    ("res_head64to3",  1, 64,  3,    1,  256, 512, (1, 3, 3), True),
 ]
 
 
