@@ -161,6 +161,150 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// Drain one 128 x BN accumulator (TMEM columns tmem_acc .. +BN of this warp's lane quarter) through the staging
+// buffer: bias + residual + activation, warp-contiguous stores, per-column GroupNorm partial sums into s_stats.
+// Called by all 256 epilogue threads; contains CTA-level named barriers.
+__device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, long long* row_off, double* s_stats,
+                                               uint32_t tmem_acc, int n0, int64_t obase, int half, int r, int et,
+                                               int lane) {
+  const bool vec4 = (p.Cout % 4) == 0, vec8 = (p.Cout % 8) == 0;
+  const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+  if (half == 0) row_off[r] = obase;
+  for (int c0 = 0; c0 < p.BN; c0 += EPI_COLS) {
+    const int co0 = n0 + c0;
+    if (co0 >= p.Cout) break;              // padded output channels (uniform across the CTA)
+    const int ncol = min(min(EPI_COLS, p.BN - c0), p.Cout - co0);   // valid columns in this chunk (uniform)
+    const int hc = half * 16;              // my first column inside the chunk
+    const bool mine = hc < ncol;           // warp-uniform
+    const bool fast = (ncol == EPI_COLS) && vec4;
+    float v[16];
+    if (mine) {
+      tmem_ld16(tmem_acc + (uint32_t)(c0 + hc), v);
+      if (fast) {
+        if (bias_vec) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + hc + i));
+            v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+          }
+        } else if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co0 + hc + i);
+        }
+        if (p.res_f32) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 rr = *reinterpret_cast<const float4*>(p.res_f32 + obase + co0 + hc + i);
+            v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+          }
+        } else if (p.res_hi) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 rr = mp_load_split4(p.res_hi, p.res_lo, obase + co0 + hc + i);
+            v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (hc + i < ncol) {
+            const int64_t o = obase + co0 + hc + i;
+            if (p.bias) v[i] += __ldg(p.bias + co0 + hc + i);
+            if (p.res_f32) v[i] += p.res_f32[o];
+            else if (p.res_hi) v[i] += mp_join(p.res_hi[o], p.res_lo[o]);
+          }
+        }
+      }
+      if (p.act == MP_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      } else if (p.act != MP_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = mp_apply_act(v[i], p.act);
+      }
+      // stage my half row (16-byte stores; row pitch 36 floats => conflict-free across the warp)
+#pragma unroll
+      for (int i = 0; i < 16; i += 4)
+        *reinterpret_cast<float4*>(epi + r * EPI_PITCH + hc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    epi_bar();
+    // ---- write-out: warp-contiguous rows (256 threads)
+    if (p.out_f32) {
+      if (vec4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = j * 32 + (et >> 3), cq = (et & 7) * 4;
+          if (cq < ncol)
+            *reinterpret_cast<float4*>(p.out_f32 + row_off[row] + co0 + cq) =
+                *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + cq);
+        }
+      } else {
+        for (int j = 0; j < 16; ++j) {
+          const int row = j * 8 + (et >> 5);
+          if (lane < ncol) p.out_f32[row_off[row] + co0 + lane] = epi[row * EPI_PITCH + lane];
+        }
+      }
+    }
+    if (p.out_hi) {
+      if (vec8) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int row = j * 64 + (et >> 2), c8 = (et & 3) * 8;
+          if (c8 < ncol) {
+            const float4 x0 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8);
+            const float4 x1 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8 + 4);
+            const int64_t o = row_off[row] + co0 + c8;
+            bf16x8 h, l;
+            mp_split2(x0.x, h.v[0], l.v[0]); mp_split2(x0.y, h.v[1], l.v[1]); mp_split2(x0.z, h.v[2], l.v[2]);
+            mp_split2(x0.w, h.v[3], l.v[3]); mp_split2(x1.x, h.v[4], l.v[4]); mp_split2(x1.y, h.v[5], l.v[5]);
+            mp_split2(x1.z, h.v[6], l.v[6]); mp_split2(x1.w, h.v[7], l.v[7]);
+            *reinterpret_cast<bf16x8*>(p.out_hi + o) = h;
+            *reinterpret_cast<bf16x8*>(p.out_lo + o) = l;
+          }
+        }
+      } else {
+        for (int j = 0; j < 16; ++j) {
+          const int row = j * 8 + (et >> 5);
+          if (lane < ncol) {
+            const int64_t o = row_off[row] + co0 + lane;
+            mp_split2(epi[row * EPI_PITCH + lane], p.out_hi[o], p.out_lo[o]);
+          }
+        }
+      }
+    }
+    if (p.stats) {
+      // column sums over 16-row slabs: thread (slab = et / 32, col = lane)
+      if (lane < ncol) {
+        const int slab = et >> 5;
+        float sm = 0.f, sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float x = epi[(slab * 16 + j) * EPI_PITCH + lane];
+          sm += x; sq += x * x;
+        }
+        atomicAdd(&s_stats[2 * (c0 + lane)], (double)sm);
+        atomicAdd(&s_stats[2 * (c0 + lane) + 1], (double)sq);
+      }
+    }
+    epi_bar();                              // staging buffer may be overwritten
+  }
+}
+
+__device__ __forceinline__ void epilogue_flush_stats(const TcParams& p, double* s_stats, int n, int n0, int et) {
+  const int cpg = p.gn_groups > 0 ? p.Cout / p.gn_groups : 1;
+  for (int c = et; c < p.BN; c += 256) {
+    const int co = n0 + c;
+    if (co < p.Cout) {
+      double* st = p.stats + ((int64_t)n * p.gn_groups + co / cpg) * 2;
+      atomicAdd(st, s_stats[2 * c]);
+      atomicAdd(st + 1, s_stats[2 * c + 1]);
+    }
+    s_stats[2 * c] = 0.0;
+    s_stats[2 * c + 1] = 0.0;
+  }
+  epi_bar();
+}
+
 // ------------------------------------------------------------------------------------------------ kernel v2
 // Persistent: grid = min(#tiles, #SMs); every role walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 // TMEM holds TWO accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.  The epilogue stages 32-column
@@ -304,9 +448,6 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     const int half = (warp - 2) >> 2;          // which 16 columns of a chunk
     const int r = q * 32 + lane;               // accumulator row == position inside the tile
     const int et = threadIdx.x - 64;           // 0..255
-    const int cpg = p.gn_groups > 0 ? p.Cout / p.gn_groups : 1;
-    const bool vec4 = (p.Cout % 4) == 0, vec8 = (p.Cout % 8) == 0;
-    const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int n, d0, h0, w0, n0;
@@ -315,144 +456,197 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       const int ww = r % p.BW, hh = (r / p.BW) % p.BH, dd = r / (p.BW * p.BH);
       const int64_t pos = (((int64_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
       const int64_t obase = pos * p.Cout;
-      if (half == 0) row_off[r] = obase;
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c0 = 0; c0 < p.BN; c0 += EPI_COLS) {
-        const int co0 = n0 + c0;
-        if (co0 >= p.Cout) break;              // padded output channels (uniform across the CTA)
-        const int ncol = min(min(EPI_COLS, p.BN - c0), p.Cout - co0);   // valid columns in this chunk (uniform)
-        const int hc = half * 16;              // my first column inside the chunk
-        const bool mine = hc < ncol;           // warp-uniform
-        const bool fast = (ncol == EPI_COLS) && vec4;
-        float v[16];
-        if (mine) {
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.BN + c0 + hc), v);
-          if (fast) {
-            if (bias_vec) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + hc + i));
-                v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
-              }
-            } else if (p.bias) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co0 + hc + i);
-            }
-            if (p.res_f32) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 rr = *reinterpret_cast<const float4*>(p.res_f32 + obase + co0 + hc + i);
-                v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
-              }
-            } else if (p.res_hi) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 rr = mp_load_split4(p.res_hi, p.res_lo, obase + co0 + hc + i);
-                v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (hc + i < ncol) {
-                const int64_t o = obase + co0 + hc + i;
-                if (p.bias) v[i] += __ldg(p.bias + co0 + hc + i);
-                if (p.res_f32) v[i] += p.res_f32[o];
-                else if (p.res_hi) v[i] += mp_join(p.res_hi[o], p.res_lo[o]);
-              }
-            }
-          }
-          if (p.act == MP_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          } else if (p.act != MP_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = mp_apply_act(v[i], p.act);
-          }
-          // stage my half row (16-byte stores; row pitch 36 floats => conflict-free across the warp)
-#pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(epi + r * EPI_PITCH + hc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-        epi_bar();
-        // ---- write-out: warp-contiguous rows (256 threads)
-        if (p.out_f32) {
-          if (vec4) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int row = j * 32 + (et >> 3), cq = (et & 7) * 4;
-              if (cq < ncol)
-                *reinterpret_cast<float4*>(p.out_f32 + row_off[row] + co0 + cq) =
-                    *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + cq);
-            }
-          } else {
-            for (int j = 0; j < 16; ++j) {
-              const int row = j * 8 + (et >> 5);
-              if (lane < ncol) p.out_f32[row_off[row] + co0 + lane] = epi[row * EPI_PITCH + lane];
-            }
-          }
-        }
-        if (p.out_hi) {
-          if (vec8) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int row = j * 64 + (et >> 2), c8 = (et & 3) * 8;
-              if (c8 < ncol) {
-                const float4 x0 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8);
-                const float4 x1 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8 + 4);
-                const int64_t o = row_off[row] + co0 + c8;
-                bf16x8 h, l;
-                mp_split2(x0.x, h.v[0], l.v[0]); mp_split2(x0.y, h.v[1], l.v[1]); mp_split2(x0.z, h.v[2], l.v[2]);
-                mp_split2(x0.w, h.v[3], l.v[3]); mp_split2(x1.x, h.v[4], l.v[4]); mp_split2(x1.y, h.v[5], l.v[5]);
-                mp_split2(x1.z, h.v[6], l.v[6]); mp_split2(x1.w, h.v[7], l.v[7]);
-                *reinterpret_cast<bf16x8*>(p.out_hi + o) = h;
-                *reinterpret_cast<bf16x8*>(p.out_lo + o) = l;
-              }
-            }
-          } else {
-            for (int j = 0; j < 16; ++j) {
-              const int row = j * 8 + (et >> 5);
-              if (lane < ncol) {
-                const int64_t o = row_off[row] + co0 + lane;
-                mp_split2(epi[row * EPI_PITCH + lane], p.out_hi[o], p.out_lo[o]);
-              }
-            }
-          }
-        }
-        if (p.stats) {
-          // column sums over 16-row slabs: thread (slab = et / 32, col = lane)
-          if (lane < ncol) {
-            const int slab = et >> 5;
-            float sm = 0.f, sq = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float x = epi[(slab * 16 + j) * EPI_PITCH + lane];
-              sm += x; sq += x * x;
-            }
-            atomicAdd(&s_stats[2 * (c0 + lane)], (double)sm);
-            atomicAdd(&s_stats[2 * (c0 + lane) + 1], (double)sq);
-          }
-        }
-        epi_bar();                              // staging buffer may be overwritten
-      }
+      epilogue_drain(p, epi, row_off, s_stats, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.BN), n0, obase,
+                     half, r, et, lane);
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(b));
-      if (p.stats) {
-        for (int c = et; c < p.BN; c += 256) {
-          const int co = n0 + c;
-          if (co < p.Cout) {
-            double* st = p.stats + ((int64_t)n * p.gn_groups + co / cpg) * 2;
-            atomicAdd(st, s_stats[2 * c]);
-            atomicAdd(st + 1, s_stats[2 * c + 1]);
-          }
-          s_stats[2 * c] = 0.0;
-          s_stats[2 * c + 1] = 0.0;
-        }
-        epi_bar();
+      if (p.stats) epilogue_flush_stats(p, s_stats, n, n0, et);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel v3 (slab)
+// 3x3(x3) convolutions with few output channels are bound by the L2 -> shared-memory feed of the A operand when
+// every filter tap re-fetches its own shifted 128-position box.  Here the output tile is an (MT*BH) x BW patch
+// (BH*BW = 128, BW a multiple of 8) and ONE TMA box of (MT*BH + 2) x BW pixel rows -- the patch plus its vertical
+// halo, shifted by the horizontal tap kw -- serves all three vertical taps of all MT accumulators: tap kh of
+// accumulator t simply starts (t*BH + kh)*BW pixel rows into the slab, which keeps the UMMA descriptor start
+// 1024-byte aligned (BW % 8 == 0), so the swizzle phase is unchanged.  A traffic drops 2.7x (MT = 2: 34 rows
+// instead of 96) and the weight tile of a tap is shared by the MT accumulators.  A slabs and B tiles travel in two
+// independent mbarrier rings.
+struct SlabExtra {
+  int MT, SA, SB;
+  uint32_t a_plane_bytes;     // one plane of one slab
+  uint32_t b_ring_off;        // byte offset of the B ring
+};
+
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
+k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p,
+           const SlabExtra x) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* epi = reinterpret_cast<float*>(gen_base + p.epi_off);
+  long long* row_off = reinterpret_cast<long long*>(gen_base + p.epi_off + TILE_M * EPI_PITCH * 4);
+  // barriers: fullA[SA], emptyA[SA], fullB[SB], emptyB[SB], tmem_full[2], tmem_empty[2]
+  const uint32_t bars = smem_base + p.epi_off + EPI_BYTES;
+  auto fullA = [&](int i) { return bars + i * 8; };
+  auto emptyA = [&](int i) { return bars + (x.SA + i) * 8; };
+  auto fullB = [&](int i) { return bars + (2 * x.SA + i) * 8; };
+  auto emptyB = [&](int i) { return bars + (2 * x.SA + x.SB + i) * 8; };
+  auto tfull_bar = [&](int b) { return bars + (2 * x.SA + 2 * x.SB + b) * 8; };
+  auto tempty_bar = [&](int b) { return bars + (2 * x.SA + 2 * x.SB + 2 + b) * 8; };
+  const uint32_t tmem_slot = bars + (2 * x.SA + 2 * x.SB + 4) * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_stage = 2 * x.a_plane_bytes, b_stage = 2 * p.b_bytes;
+  const uint32_t row_bytes = (uint32_t)p.CCHUNK * 2u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < x.SA; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), 1); }
+    for (int i = 0; i < x.SB; ++i) { mbar_init(fullB(i), 1); mbar_init(emptyB(i), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // super-tile id -> (n, d, h0, w0, n0); tiles_h counts super-tiles of MT*BH rows, tiles_d = D (BD = 1)
+  auto tile_coords = [&](int tile, int& n, int& d0, int& h0, int& w0, int& n0) {
+    n0 = (tile % p.tiles_n) * p.BN;
+    int t = tile / p.tiles_n;
+    w0 = (t % p.tiles_w) * p.BW; t /= p.tiles_w;
+    h0 = (t % p.tiles_h) * (p.BH * x.MT); t /= p.tiles_h;
+    d0 = t % p.tiles_d;
+    n = t / p.tiles_d;
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      const int pd = p.KD / 2, pw = p.KW / 2;
+      uint32_t ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n, d0, h0, w0, n0;
+        tile_coords(tile, n, d0, h0, w0, n0);
+        for (int kd = 0; kd < p.KD; ++kd)
+          for (int kw = 0; kw < p.KW; ++kw)
+            for (int cc = 0; cc < p.num_cchunks; ++cc) {
+              const int c0 = cc * p.CCHUNK;
+              {
+                const int sidx = ia % x.SA;
+                mbar_wait(emptyA(sidx), ((ia / x.SA) & 1) ^ 1);
+                const uint32_t sa = smem_base + sidx * a_stage;
+                mbar_expect_tx(fullA(sidx), a_stage);
+                tma_load_5d(sa, &map_a_hi, fullA(sidx), c0, w0 + kw - pw, h0 - 1, d0 + kd - pd, n);
+                tma_load_5d(sa + x.a_plane_bytes, &map_a_lo, fullA(sidx), c0, w0 + kw - pw, h0 - 1, d0 + kd - pd, n);
+                ++ia;
+              }
+              for (int kh = 0; kh < 3; ++kh, ++ib) {
+                const int sidx = ib % x.SB;
+                mbar_wait(emptyB(sidx), ((ib / x.SB) & 1) ^ 1);
+                const uint32_t sb = smem_base + x.b_ring_off + sidx * b_stage;
+                mbar_expect_tx(fullB(sidx), b_stage);
+                const int tap = (kd * 3 + kh) * p.KW + kw;
+                tma_load_2d(sb, &map_b_hi, fullB(sidx), tap * p.Cin + c0, n0);
+                tma_load_2d(sb + p.b_bytes, &map_b_lo, fullB(sidx), tap * p.Cin + c0, n0);
+              }
+            }
       }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const int ksteps = p.CCHUNK / 16;
+      uint32_t ia = 0, ib = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t b = it & 1;
+        mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem0 = tmem_base + b * (uint32_t)(x.MT * p.BN);
+        bool first = true;
+        for (int g = 0; g < p.KD * p.KW * p.num_cchunks; ++g, ++ia) {
+          const int sidx = ia % x.SA;
+          mbar_wait(fullA(sidx), (ia / x.SA) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + sidx * a_stage;
+          for (int kh = 0; kh < 3; ++kh, ++ib) {
+            const int bidx = ib % x.SB;
+            mbar_wait(fullB(bidx), (ib / x.SB) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t b_hi = smem_base + x.b_ring_off + bidx * b_stage, b_lo = b_hi + p.b_bytes;
+            for (int t = 0; t < x.MT; ++t) {
+              const uint32_t a_hi = sa + (uint32_t)((t * p.BH + kh) * p.BW) * row_bytes;
+              const uint32_t a_lo = a_hi + x.a_plane_bytes;
+              const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.BN);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t ko = k * 32;
+                const uint64_t dah = make_smem_desc(a_hi + ko, p.sbo, p.layout_type);
+                const uint64_t dal = make_smem_desc(a_lo + ko, p.sbo, p.layout_type);
+                const uint64_t dbh = make_smem_desc(b_hi + ko, p.sbo, p.layout_type);
+                const uint64_t dbl = make_smem_desc(b_lo + ko, p.sbo, p.layout_type);
+                umma_bf16(d_tmem, dal, dbh, p.idesc, (first && k == 0) ? 0u : 1u);
+                umma_bf16(d_tmem, dah, dbl, p.idesc, 1u);
+                umma_bf16(d_tmem, dah, dbh, p.idesc, 1u);
+              }
+            }
+            first = false;
+            umma_commit(emptyB(bidx));
+          }
+          umma_commit(emptyA(sidx));
+        }
+        umma_commit(tfull_bar(b));
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int n, d0, h0, w0, n0;
+      tile_coords(tile, n, d0, h0, w0, n0);
+      const uint32_t b = it & 1;
+      mbar_wait(tfull_bar(b), (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int t = 0; t < x.MT; ++t) {
+        const int ww = r % p.BW, hh = r / p.BW;
+        const int64_t pos = (((int64_t)n * p.D + d0) * p.H + h0 + t * p.BH + hh) * p.W + w0 + ww;
+        epilogue_drain(p, epi, row_off, s_stats,
+                       tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * x.MT + t) * p.BN), n0, pos * p.Cout,
+                       half, r, et, lane);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(b));
+      if (p.stats) epilogue_flush_stats(p, s_stats, n, n0, et);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -689,6 +883,8 @@ struct Plan {
   uint32_t smem_bytes;
   CUtensorMapSwizzle swz;
   bool v1;
+  bool slab;
+  SlabExtra x;
 };
 
 bool use_v1() {
@@ -731,6 +927,53 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   while ((int64_t)pl.tiles_m * (d->Cout_pad / p.BN) < 148 && p.BN % 32 == 0 && p.BN > 32) p.BN /= 2;
   pl.tiles_n = d->Cout_pad / p.BN;
   pl.v1 = use_v1();
+  pl.slab = false;
+  // ---- slab (vertical-halo reuse) kernel for 3x3(x3) convolutions with <= 128 output channels
+  static int allow_slab = [] { const char* e = getenv("MPB200_TC_NO_SLAB"); return (e && atoi(e)) ? 0 : 1; }();
+  if (!pl.v1 && allow_slab && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) && d->Cout_pad <= 128 &&
+      d->W % 8 == 0 && d->H % 16 == 0) {
+    const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + EPI_BYTES;
+    const int bn = d->Cout_pad;
+    const uint32_t b_stage = 2u * bn * p.CCHUNK * 2u;
+    for (int mt = (d->H % 32 == 0 && 4 * bn <= 512) ? 2 : 1; mt >= 1 && !pl.slab; --mt) {
+      const uint32_t a_plane = (uint32_t)(mt * 16 + 2) * 8u * p.CCHUNK * 2u;
+      for (int sa = 3; sa >= 2 && !pl.slab; --sa) {
+        if (fixed_s + sa * 2 * a_plane + 3 * b_stage > SMEM_LIMIT) continue;
+        int sb = (int)((SMEM_LIMIT - fixed_s - sa * 2 * a_plane) / b_stage);
+        if (sb > 8) sb = 8;
+        pl.slab = true;
+        pl.x.MT = mt; pl.x.SA = sa; pl.x.SB = sb;
+        pl.x.a_plane_bytes = a_plane;
+        pl.x.b_ring_off = sa * 2 * a_plane;
+        p.BN = bn;
+        pl.tiles_n = 1;
+        p.BW = 8; p.BH = 16; p.BD = 1;
+        p.tiles_w = d->W / 8; p.tiles_h = d->H / (16 * mt); p.tiles_d = d->D;
+        pl.tiles_m = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
+        p.a_bytes = a_plane;
+        p.b_bytes = (uint32_t)bn * p.CCHUNK * 2u;
+        p.stage_bytes = 0;
+        p.STAGES = sa;
+        p.b_resident = 0;
+        p.bres_off = 0;
+        p.epi_off = pl.x.b_ring_off + sb * b_stage;
+        pl.smem_bytes = fixed_s + p.epi_off;
+        p.tmem_cols = next_pow2(2 * mt * bn);
+        p.tiles_n = 1;
+        p.total_tiles = pl.tiles_m;
+      }
+    }
+  }
+  if (pl.slab) {
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.KD = d->KD; p.KH = d->KH; p.KW = d->KW;
+    p.bias = d->bias; p.res_f32 = d->res_f32; p.res_hi = (const bf16*)d->res_hi; p.res_lo = (const bf16*)d->res_lo;
+    p.out_f32 = d->out_f32; p.out_hi = (bf16*)d->out_hi; p.out_lo = (bf16*)d->out_lo;
+    p.stats = d->stats; p.gn_groups = d->gn_groups; p.act = d->act;
+    p.S = (int64_t)d->D * d->H * d->W;
+    return 0;
+  }
   const uint32_t fixed = 1024 /*align slack*/ + 1024 /*barriers, tmem slot*/ + 2 * 256 * sizeof(double) +
                          (pl.v1 ? 0 : EPI_BYTES);
   // weight-resident mode: one N tile and the whole [taps*Cin x BN] weight tile (hi+lo) fits beside >= 3 A stages;
@@ -782,7 +1025,8 @@ int encode_act_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const
   cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->D, (cuuint64_t)d->N};
   cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->W, (cuuint64_t)d->Cin * 2 * d->W * d->H,
                            (cuuint64_t)d->Cin * 2 * d->W * d->H * d->D};
-  cuuint32_t box[5] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BW, (cuuint32_t)pl.p.BH, (cuuint32_t)pl.p.BD, 1};
+  cuuint32_t box[5] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BW,
+                       (cuuint32_t)(pl.slab ? pl.x.MT * pl.p.BH + 2 : pl.p.BH), (cuuint32_t)pl.p.BD, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = get_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -830,6 +1074,8 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
       cudaError_t ae = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
       if (ae == cudaSuccess)
         ae = cudaFuncSetAttribute(k_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+      if (ae == cudaSuccess)
+        ae = cudaFuncSetAttribute(k_conv_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
       MP_REQUIRE(ae == cudaSuccess, "mp_conv_tc: cannot opt in to %u B shared memory: %s", SMEM_LIMIT,
                  cudaGetErrorString(ae));
       if (dev >= 0 && dev < 64) {
@@ -843,7 +1089,10 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
     } else {
       int sms = (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) ? g_num_sms[dev] : 148;
       int grid = pl.p.total_tiles < sms ? pl.p.total_tiles : sms;
-      k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p);
+      if (pl.slab)
+        k_conv_tc3<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p, pl.x);
+      else
+        k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p);
     }
   }
   MP_LAUNCH_CHECK("mp_conv_tc");

@@ -44,9 +44,19 @@ class CustomResNet50(nn.Module):
         self.conv_reduce = nn.Conv2d(1024, 512, kernel_size=1)
 
     def forward(self, x):
-        x = F.relu(self.bn1(self.conv1(x)))
-        x = self.maxpool(x)
-        x = self.layer3(self.layer2(self.layer1(x)))
+        if self.training or torch.is_grad_enabled():
+            x = F.relu(self.bn1(self.conv1(x)))
+            x = self.maxpool(x)
+            x = self.layer3(self.layer2(self.layer1(x)))
+        else:
+            sig = _versions(self)
+            c = self.__dict__.get("_mp_plan")
+            if c is None or c[0] != sig:
+                with torch.no_grad():
+                    c = (sig, _FoldedResNetTrunk(self.conv1, self.bn1, self.maxpool,
+                                                 [self.layer1, self.layer2, self.layer3]))
+                self.__dict__["_mp_plan"] = c
+            x = c[1](x)
         x = self.adaptive_avg_pool(x)
         return self.conv_reduce(x)
 
@@ -120,6 +130,65 @@ class SixDRepNet_Detector:
         return ortho6d_to_euler_deg(x[:, :6]), x[:, 6:]
 
 
+def _fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
+    """conv -> BatchNorm(eval) as one conv (float64 fold), channels_last weights."""
+    s = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+    w = conv.weight.double() * s.view(-1, 1, 1, 1)
+    b0 = conv.bias.double() if conv.bias is not None else torch.zeros_like(s)
+    b = (b0 - bn.running_mean.double()) * s + bn.bias.double()
+    out = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding,
+                    conv.dilation, conv.groups, bias=True).to(conv.weight.device)
+    out.weight.data = w.float().contiguous(memory_format=torch.channels_last)
+    out.bias.data = b.float()
+    return out.eval()
+
+
+class _FoldedResNetTrunk(nn.Module):
+    """Inference plan of a torchvision-style ResNet trunk: BatchNorm folded into the convolutions, channels_last,
+    in-place ReLU.  Same arithmetic as the stock eval-mode modules up to fp32 rounding; built lazily from the live
+    parameters and never registered (so `state_dict()` keeps the reference's keys)."""
+
+    def __init__(self, conv1, bn1, maxpool, layers, tail=None):
+        super().__init__()
+        self.stem = _fold_conv_bn(conv1, bn1)
+        self.maxpool = maxpool
+        blocks = []
+        for layer in layers:
+            for blk in layer:
+                kind = type(blk).__name__
+                if kind == "BasicBlock":
+                    convs = [_fold_conv_bn(blk.conv1, blk.bn1), _fold_conv_bn(blk.conv2, blk.bn2)]
+                else:   # Bottleneck
+                    convs = [_fold_conv_bn(blk.conv1, blk.bn1), _fold_conv_bn(blk.conv2, blk.bn2),
+                             _fold_conv_bn(blk.conv3, blk.bn3)]
+                down = None if blk.downsample is None else _fold_conv_bn(blk.downsample[0], blk.downsample[1])
+                blocks.append((nn.ModuleList(convs), down))
+        self.convs = nn.ModuleList([c for c, _ in blocks])
+        self.downs = nn.ModuleList([d if d is not None else nn.Identity() for _, d in blocks])
+        self.has_down = [d is not None for _, d in blocks]
+
+    def forward(self, x):
+        x = F.relu_(self.stem(x.contiguous(memory_format=torch.channels_last)))
+        x = self.maxpool(x)
+        for convs, down, hd in zip(self.convs, self.downs, self.has_down):
+            idt = down(x) if hd else x
+            y = x
+            for i, c in enumerate(convs):
+                y = c(y)
+                if i + 1 < len(convs):
+                    y = F.relu_(y)
+            x = F.relu_(y.add_(idt))
+        return x
+
+
+def _versions(mod: nn.Module):
+    s, dev = 0, None
+    for t in list(mod.parameters()) + list(mod.buffers()):
+        s += t._version + (t.data_ptr() & 0xFFFF)
+        dev = t.device
+    return (s, str(dev))
+
+
 class Emtn(nn.Module):
     """model.py:869-907.  forward(x) -> (rotations [B,3] degrees, translation [B,3], expression z [B,512])."""
 
@@ -138,9 +207,32 @@ class Emtn(nn.Module):
         self.rotation_net.model._apply(fn, *a, **k)
         return super()._apply(fn, *a, **k)
 
+    def _plans(self):
+        sig = (_versions(self.head_pose_net), _versions(self.expression_net))
+        c = self.__dict__.get("_mp_plans")
+        if c is None or c[0] != sig:
+            hp, ex = self.head_pose_net, self.expression_net
+            with torch.no_grad():
+                c = (sig, (_FoldedResNetTrunk(hp.conv1, hp.bn1, hp.maxpool, [hp.layer1, hp.layer2, hp.layer3, hp.layer4]),
+                           _FoldedResNetTrunk(ex[0], ex[1], ex[3], [ex[4], ex[5], ex[6], ex[7]])))
+            self.__dict__["_mp_plans"] = c
+        return c[1]
+
     def forward(self, x):
-        rotations, _ = self.rotation_net.predict(x)
-        head_pose = self.head_pose_net(x)
-        translation = head_pose[:, 3:]
-        expression = self.fc(torch.flatten(self.expression_net(x), start_dim=1))
+        if self.training or torch.is_grad_enabled():
+            # stock path (train-mode BatchNorm / autograd), exactly the reference's module graph
+            rotations, _ = self.rotation_net.predict(x)
+            head_pose = self.head_pose_net(x)
+            translation = head_pose[:, 3:]
+            expression = self.fc(torch.flatten(self.expression_net(x), start_dim=1))
+            return rotations, translation, expression
+        # inference plan: BatchNorm folded, channels_last (no NCHW<->NHWC transposes around the cuDNN kernels)
+        hp_trunk, ex_trunk = self._plans()
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        self.rotation_net.model.to(memory_format=torch.channels_last)
+        rotations, _ = self.rotation_net.predict(xcl)
+        hp = torch.flatten(F.adaptive_avg_pool2d(hp_trunk(xcl), 1), 1)
+        translation = self.head_pose_net.fc(hp)[:, 3:]
+        ex = F.adaptive_avg_pool2d(F.adaptive_avg_pool2d(ex_trunk(xcl), 1), FEATURE_SIZE)   # model.py:880-881
+        expression = self.fc(torch.flatten(ex, start_dim=1))
         return rotations, translation, expression

@@ -114,6 +114,11 @@ CONV_CASES = [
     ("res_64to64",     2, 64,  64,   1,  256, 256, (1, 3, 3), True),
     ("res_1x1_128to64", 2, 128, 64,  1,  256, 256, (1, 1, 1), True),
     ("res_head64to3",  1, 64,  3,    1,  256, 512, (1, 3, 3), True),
+    # slab (vertical-halo reuse) kernel: MT = 2 and MT = 1, all three swizzle widths, 2-D and 3-D
+    ("slab_128",       2, 128, 128,  1,  64,  64, (1, 3, 3), True),
+    ("slab_3d_64",     1, 64,  64,   4,  32,  16, (3, 3, 3), True),
+    ("slab_c16_mt1",   1, 16,  48,   1,  16,  8,  (1, 3, 3), True),
+    ("slab_c32_h48",   1, 32,  96,   2,  48,  16, (3, 3, 3), True),
 ]
 
 

@@ -69,6 +69,10 @@ def main():
         conv_case("g2d_in_1x1_96to512_b32", 32, 96, 512, 1, 64, 64, (1, 1, 1), r)
         conv_case("g2d_64_512x512_b32", 32, 64, 64, 1, 512, 512, (1, 3, 3), r, split_out=False)
         conv_case("g2d_sc_128to64_1x1_b32", 32, 128, 64, 1, 512, 512, (1, 1, 1), r, split_out=False, act=ops.ACT_NONE)
+        conv_case("g2d_128to64_512x512_b32", 32, 128, 64, 1, 512, 512, (1, 3, 3), r)
+        conv_case("g2d_up2_256to128_b32", 32, 256, 128, 1, 256, 256, (1, 3, 3), r)
+        conv_case("g2d_head_64to3_b32", 32, 64, 3, 1, 512, 512, (1, 3, 3), r, split_out=False, act=ops.ACT_SIGMOID)
+        conv_case("eapp_64to128_512_b1", 1, 64, 128, 1, 512, 512, (1, 3, 3), r, split_out=False, act=ops.ACT_NONE)
         conv_case("g2d_up1_512to256_b32", 32, 512, 256, 1, 128, 128, (1, 3, 3), r)
         conv_case("vol96_16x64x64_b1", 1, 96, 96, 16, 64, 64, (3, 3, 3), r, split_out=False, act=ops.ACT_NONE)
         conv_case("eapp_128_512x512_b1", 1, 128, 128, 1, 512, 512, (1, 3, 3), r, split_out=False, act=ops.ACT_NONE)
