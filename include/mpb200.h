@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPB200_ABI_VERSION 1
+#define MPB200_ABI_VERSION 2
 
 /* activation codes shared by several entry points */
 enum { MP_ACT_NONE = 0, MP_ACT_RELU = 1, MP_ACT_RELU_TANH = 2, MP_ACT_SIGMOID = 3 };
@@ -90,6 +90,13 @@ typedef struct mp_conv_desc {
   int Cout_pad;           /* rows in the packed weight matrix (>= Cout, multiple of 16) */
   int gn_groups;
   int act;                /* MP_ACT_* applied after bias + residual */
+  /* --- ABI v2 extensions (0 = default) --------------------------------------------------------------------- */
+  int stride;             /* 1 (default) or 2 on H and W: output grid is (D, H/stride, W/stride); resnet/RepVGG
+                             stride-2 3x3 (pad 1) and 1x1 convolutions (resnet.py:101-118, mysixdrepnet.py:1230-1246) */
+  int in_c_off;           /* first input channel read (grouped convolutions run one launch per group) */
+  int in_C;               /* channels per position of the input tensor (default Cin) */
+  int out_c_off;          /* first output channel written */
+  int out_C;              /* channels per position of the output / residual tensors (default Cout) */
 } mp_conv_desc;
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores fed by TMA (3-pass split-bf16, fp32 accumulate in TMEM).
@@ -100,6 +107,14 @@ int mp_conv_tc(const mp_conv_desc* desc, void* stream);
 int mp_conv_simt(const mp_conv_desc* desc, void* stream);
 /* 1 if mp_conv_tc accepts the shape. */
 int mp_conv_tc_supported(const mp_conv_desc* desc);
+
+/* ---------------------------------------------------------------- pooling (motion encoder trunks) ---------- */
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on a split CL tensor [N,1,H,W,C] -> [N,1,H/2,W/2,C] (resnet.py:196). */
+int mp_maxpool3x3s2_cl(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int N, int H, int W, int C,
+                       void* stream);
+/* nn.AdaptiveAvgPool2d(1) on a CL tensor (fp32 if in_f32 != NULL else split): [N,S,C] -> out [N,C] fp32. */
+int mp_global_avgpool_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out, int N, int64_t S, int C,
+                         void* stream);
 
 /* ---------------------------------------------------------------- warping ----------------------------------- */
 /* F.grid_sample(v, grid, 'bilinear', 'border', align_corners=True) for 5-D input (model.py:1062).

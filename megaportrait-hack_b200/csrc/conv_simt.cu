@@ -21,9 +21,10 @@ struct ConvArgs {
   float* out_f32;
   bf16 *out_hi, *out_lo;
   double* stats;
-  int N, D, H, W, Cin, Cout, KD, KH, KW, gn_groups, act;
-  int64_t M;      // N*D*H*W
-  int64_t S;      // D*H*W
+  int N, D, H, W, Cin, Cout, KD, KH, KW, gn_groups, act;   // H, W: INPUT extents
+  int Ho, Wo, stride, in_c_off, in_C, out_c_off, out_C;
+  int64_t M;      // N*D*Ho*Wo
+  int64_t S;      // D*Ho*Wo
   int Ktot;       // taps*Cin
 };
 
@@ -44,14 +45,14 @@ __global__ void __launch_bounds__(THREADS) k_conv_simt(ConvArgs a) {
   int an = 0, ad = 0, ah = 0, aw = 0;
   if (arow_ok) {
     int64_t r = am;
-    aw = (int)(r % a.W); r /= a.W;
-    ah = (int)(r % a.H); r /= a.H;
+    aw = (int)(r % a.Wo); r /= a.Wo;
+    ah = (int)(r % a.Ho); r /= a.Ho;
     ad = (int)(r % a.D);
     an = (int)(r / a.D);
   }
   const int bco = n0 + lrow;
   const bool brow_ok = bco < a.Cout;
-  const bool vec_ok = (a.Cin % 4) == 0;
+  const bool vec_ok = ((a.Cin | a.in_C | a.in_c_off) % 4) == 0;
 
   float acc[4][4];
 #pragma unroll
@@ -64,9 +65,11 @@ __global__ void __launch_bounds__(THREADS) k_conv_simt(ConvArgs a) {
     for (int kh = 0; kh < a.KH; ++kh)
       for (int kw = 0; kw < a.KW; ++kw) {
         const int tap = (kd * a.KH + kh) * a.KW + kw;
-        const int id = ad + kd - pd, ih = ah + kh - ph, iw = aw + kw - pw;
+        // taps that are out of bounds for every position (extent-1 axes of the FlowField tower) carry only zeros
+        if ((a.D == 1 && kd != pd) || (a.H == 1 && kh != ph) || (a.W == 1 && kw != pw)) continue;
+        const int id = ad + kd - pd, ih = ah * a.stride + kh - ph, iw = aw * a.stride + kw - pw;
         const bool in_ok = arow_ok && id >= 0 && id < a.D && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
-        const int64_t in_base = ((((int64_t)an * a.D + id) * a.H + ih) * a.W + iw) * a.Cin;
+        const int64_t in_base = ((((int64_t)an * a.D + id) * a.H + ih) * a.W + iw) * a.in_C + a.in_c_off;
         for (int c0 = 0; c0 < a.Cin; c0 += BK) {
           // ---- A chunk
           float av[4] = {0.f, 0.f, 0.f, 0.f};
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(THREADS) k_conv_simt(ConvArgs a) {
     for (int j = 0; j < 4; ++j) {
       const int co = n0 + tx * 4 + j;
       if (co >= a.Cout) continue;
-      const int64_t o = m * a.Cout + co;
+      const int64_t o = m * a.out_C + a.out_c_off + co;
       float v = acc[i][j];
       if (a.bias) v += a.bias[co];
       if (a.res_f32) v += a.res_f32[o];
@@ -180,6 +183,12 @@ int mp_conv_validate(const mp_conv_desc* d, const char* who) {
   MP_REQUIRE(d->KD % 2 == 1 && d->KH % 2 == 1 && d->KW % 2 == 1, "%s: kernel extents must be odd", who);
   MP_REQUIRE(d->Cout_pad >= d->Cout, "%s: Cout_pad < Cout", who);
   MP_REQUIRE(!d->stats || (d->gn_groups > 0 && d->Cout % d->gn_groups == 0), "%s: bad gn_groups", who);
+  MP_REQUIRE(d->stride >= 0 && d->stride <= 2, "%s: stride must be 1 or 2", who);
+  MP_REQUIRE(d->in_c_off >= 0 && d->out_c_off >= 0, "%s: negative channel offset", who);
+  MP_REQUIRE(d->in_C == 0 || d->in_C >= d->in_c_off + d->Cin, "%s: input channel window exceeds in_C", who);
+  MP_REQUIRE(d->out_C == 0 || d->out_C >= d->out_c_off + d->Cout, "%s: output channel window exceeds out_C", who);
+  MP_REQUIRE(d->in_C != 0 || d->in_c_off == 0, "%s: in_c_off needs in_C", who);
+  MP_REQUIRE(d->out_C != 0 || d->out_c_off == 0, "%s: out_c_off needs out_C", who);
   return 0;
 }
 
@@ -192,7 +201,12 @@ extern "C" int mp_conv_simt(const mp_conv_desc* d, void* stream) {
   a.out_f32 = d->out_f32; a.out_hi = (bf16*)d->out_hi; a.out_lo = (bf16*)d->out_lo; a.stats = d->stats;
   a.N = d->N; a.D = d->D; a.H = d->H; a.W = d->W; a.Cin = d->Cin; a.Cout = d->Cout;
   a.KD = d->KD; a.KH = d->KH; a.KW = d->KW; a.gn_groups = d->gn_groups; a.act = d->act;
-  a.S = (int64_t)d->D * d->H * d->W;
+  a.stride = d->stride > 0 ? d->stride : 1;
+  MP_REQUIRE(d->H % a.stride == 0 && d->W % a.stride == 0, "mp_conv_simt: H, W must be multiples of the stride");
+  a.Ho = d->H / a.stride; a.Wo = d->W / a.stride;
+  a.in_c_off = d->in_c_off; a.in_C = d->in_C > 0 ? d->in_C : d->Cin;
+  a.out_c_off = d->out_c_off; a.out_C = d->out_C > 0 ? d->out_C : d->Cout;
+  a.S = (int64_t)d->D * a.Ho * a.Wo;
   a.M = a.S * d->N;
   a.Ktot = d->KD * d->KH * d->KW * d->Cin;
   int64_t gx = (a.M + BM - 1) / BM;

@@ -52,6 +52,7 @@ struct TcParams {
   int64_t S;
   int tiles_n, total_tiles;   // persistent kernel: tile id = m_tile * tiles_n + n_tile (n fastest => A shared in L2)
   uint32_t epi_off;           // byte offset (from the aligned smem base) of the epilogue staging area
+  int stride, in_c_off, out_C, out_c_off;   // ABI v2: H/W stride, channel windows (D/H/W below are OUTPUT dims)
   int b_resident;             // 1: the whole weight tile [taps*Cin x BN] stays in smem for the CTA's lifetime
   uint32_t bres_off;          // byte offset of the resident weight area
 };
@@ -127,6 +128,41 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Lean issue path: the upper descriptor word (SBO | version | layout) is constant per kernel, the lower word is
+// (smem address >> 4) | LBO; stepping 16 bf16 along K inside the swizzle atom adds 2 to the lower word.
+__device__ __forceinline__ uint32_t desc_hi_word(uint32_t sbo, uint32_t layout_type) {
+  return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo_word(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_lean(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one K-chunk (KS k-steps) of the 3-pass split product into accumulator tmem_d
+template <int KS>
+__device__ __forceinline__ void umma_chunk(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                           uint32_t hi, uint32_t idesc, uint32_t acc_first) {
+  const uint32_t ah = desc_lo_word(a_hi), al = desc_lo_word(a_lo), bh = desc_lo_word(b_hi), bl = desc_lo_word(b_lo);
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    umma_bf16_lean(tmem_d, al + 2 * k, bh + 2 * k, hi, idesc, k == 0 ? acc_first : 1u);
+    umma_bf16_lean(tmem_d, ah + 2 * k, bl + 2 * k, hi, idesc, 1u);
+    umma_bf16_lean(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc, 1u);
+  }
+}
+__device__ __forceinline__ void umma_chunk_dyn(int ksteps, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                               uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc_first) {
+  if (ksteps == 4) umma_chunk<4>(tmem_d, a_hi, a_lo, b_hi, b_lo, hi, idesc, acc_first);
+  else if (ksteps == 2) umma_chunk<2>(tmem_d, a_hi, a_lo, b_hi, b_lo, hi, idesc, acc_first);
+  else umma_chunk<1>(tmem_d, a_hi, a_lo, b_hi, b_lo, hi, idesc, acc_first);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -167,7 +203,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, long long* row_off, double* s_stats,
                                                uint32_t tmem_acc, int n0, int64_t obase, int half, int r, int et,
                                                int lane) {
-  const bool vec4 = (p.Cout % 4) == 0, vec8 = (p.Cout % 8) == 0;
+  const bool vec4 = ((p.out_C | p.out_c_off | p.Cout) % 4) == 0, vec8 = ((p.out_C | p.out_c_off | p.Cout) % 8) == 0;
   const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
   if (half == 0) row_off[r] = obase;
   for (int c0 = 0; c0 < p.BN; c0 += EPI_COLS) {
@@ -395,8 +431,9 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             const uint32_t sa = smem_base + s * p.stage_bytes;
             mbar_expect_tx(full_bar(s), tx);
             const int c0 = cc * p.CCHUNK;
-            tma_load_5d(sa, &map_a_hi, full_bar(s), c0, w0 + kw - pw, h0 + kh - ph, d0 + kd - pd, n);
-            tma_load_5d(sa + p.a_bytes, &map_a_lo, full_bar(s), c0, w0 + kw - pw, h0 + kh - ph, d0 + kd - pd, n);
+            const int ci = c0 + p.in_c_off, wi = w0 * p.stride + kw - pw, hi_ = h0 * p.stride + kh - ph;
+            tma_load_5d(sa, &map_a_hi, full_bar(s), ci, wi, hi_, d0 + kd - pd, n);
+            tma_load_5d(sa + p.a_bytes, &map_a_lo, full_bar(s), ci, wi, hi_, d0 + kd - pd, n);
             if (!p.b_resident) {
               tma_load_2d(sa + 2 * p.a_bytes, &map_b_hi, full_bar(s), tap * p.Cin + c0, n0);
               tma_load_2d(sa + 2 * p.a_bytes + p.b_bytes, &map_b_lo, full_bar(s), tap * p.Cin + c0, n0);
@@ -409,6 +446,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     // ===================================================================== MMA issuer
     if (lane == 0) {
       const int ksteps = p.CCHUNK / 16;
+      const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
       uint32_t kb = 0, it = 0;
       if (p.b_resident && (int)blockIdx.x < p.total_tiles) mbar_wait(bres_bar, 0);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -425,16 +463,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
           const uint32_t a_hi = sa, a_lo = sa + p.a_bytes;
           const uint32_t b_hi = p.b_resident ? smem_base + p.bres_off + (uint32_t)i * 2u * p.b_bytes : sa + 2 * p.a_bytes;
           const uint32_t b_lo = b_hi + p.b_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint32_t ko = k * 32;
-            const uint64_t dah = make_smem_desc(a_hi + ko, p.sbo, p.layout_type);
-            const uint64_t dal = make_smem_desc(a_lo + ko, p.sbo, p.layout_type);
-            const uint64_t dbh = make_smem_desc(b_hi + ko, p.sbo, p.layout_type);
-            const uint64_t dbl = make_smem_desc(b_lo + ko, p.sbo, p.layout_type);
-            umma_bf16(d_tmem, dal, dbh, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(d_tmem, dah, dbl, p.idesc, 1u);
-            umma_bf16(d_tmem, dah, dbh, p.idesc, 1u);
-          }
+          umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, i > 0 ? 1u : 0u);
           umma_commit(empty_bar(s));
         }
         umma_commit(tfull_bar(b));
@@ -455,7 +484,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       const uint32_t b = it & 1;
       const int ww = r % p.BW, hh = (r / p.BW) % p.BH, dd = r / (p.BW * p.BH);
       const int64_t pos = (((int64_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
-      const int64_t obase = pos * p.Cout;
+      const int64_t obase = pos * p.out_C + p.out_c_off;
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       epilogue_drain(p, epi, row_off, s_stats, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.BN), n0, obase,
@@ -564,8 +593,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
                 mbar_wait(emptyA(sidx), ((ia / x.SA) & 1) ^ 1);
                 const uint32_t sa = smem_base + sidx * a_stage;
                 mbar_expect_tx(fullA(sidx), a_stage);
-                tma_load_5d(sa, &map_a_hi, fullA(sidx), c0, w0 + kw - pw, h0 - 1, d0 + kd - pd, n);
-                tma_load_5d(sa + x.a_plane_bytes, &map_a_lo, fullA(sidx), c0, w0 + kw - pw, h0 - 1, d0 + kd - pd, n);
+                tma_load_5d(sa, &map_a_hi, fullA(sidx), c0 + p.in_c_off, w0 + kw - pw, h0 - 1, d0 + kd - pd, n);
+                tma_load_5d(sa + x.a_plane_bytes, &map_a_lo, fullA(sidx), c0 + p.in_c_off, w0 + kw - pw, h0 - 1,
+                            d0 + kd - pd, n);
                 ++ia;
               }
               for (int kh = 0; kh < 3; ++kh, ++ib) {
@@ -584,6 +614,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     // ===================================================================== MMA issuer
     if (lane == 0) {
       const int ksteps = p.CCHUNK / 16;
+      const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
       uint32_t ia = 0, ib = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const uint32_t b = it & 1;
@@ -605,16 +636,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
               const uint32_t a_hi = sa + (uint32_t)((t * p.BH + kh) * p.BW) * row_bytes;
               const uint32_t a_lo = a_hi + x.a_plane_bytes;
               const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.BN);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t ko = k * 32;
-                const uint64_t dah = make_smem_desc(a_hi + ko, p.sbo, p.layout_type);
-                const uint64_t dal = make_smem_desc(a_lo + ko, p.sbo, p.layout_type);
-                const uint64_t dbh = make_smem_desc(b_hi + ko, p.sbo, p.layout_type);
-                const uint64_t dbl = make_smem_desc(b_lo + ko, p.sbo, p.layout_type);
-                umma_bf16(d_tmem, dal, dbh, p.idesc, (first && k == 0) ? 0u : 1u);
-                umma_bf16(d_tmem, dah, dbl, p.idesc, 1u);
-                umma_bf16(d_tmem, dah, dbh, p.idesc, 1u);
-              }
+              umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, first ? 0u : 1u);
             }
             first = false;
             umma_commit(emptyB(bidx));
@@ -640,8 +662,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         const int ww = r % p.BW, hh = r / p.BW;
         const int64_t pos = (((int64_t)n * p.D + d0) * p.H + h0 + t * p.BH + hh) * p.W + w0 + ww;
         epilogue_drain(p, epi, row_off, s_stats,
-                       tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * x.MT + t) * p.BN), n0, pos * p.Cout,
-                       half, r, et, lane);
+                       tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * x.MT + t) * p.BN), n0,
+                       pos * p.out_C + p.out_c_off, half, r, et, lane);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -908,14 +930,23 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
                                                                          : CU_TENSOR_MAP_SWIZZLE_32B;
   p.sbo = 8u * p.CCHUNK * 2u;
   p.num_cchunks = d->Cin / p.CCHUNK;
+  // ABI v2 fields
+  p.stride = d->stride > 0 ? d->stride : 1;
+  p.in_c_off = d->in_c_off;
+  p.out_C = d->out_C > 0 ? d->out_C : d->Cout;
+  p.out_c_off = d->out_c_off;
+  if (p.stride != 1 && p.stride != 2) return fail("stride must be 1 or 2");
+  if (d->H % p.stride || d->W % p.stride) return fail("H, W must be multiples of the stride");
+  if (p.in_c_off % 8) return fail("in_c_off must be a multiple of 8 (16-byte TMA coordinate granularity)");
+  const int Ho = d->H / p.stride, Wo = d->W / p.stride;
   // output tile box
   auto pow2_le = [](int v, int cap) { int r = 1; while (r * 2 <= v && r * 2 <= cap) r *= 2; return r; };
-  p.BW = pow2_le(d->W, TILE_M);
-  p.BH = pow2_le(d->H, TILE_M / p.BW);
+  p.BW = pow2_le(Wo, TILE_M);
+  p.BH = pow2_le(Ho, TILE_M / p.BW);
   p.BD = pow2_le(d->D, TILE_M / (p.BW * p.BH));
   if (p.BW * p.BH * p.BD != TILE_M) return fail("fewer than 128 positions per sample box");
-  if (d->W % p.BW || d->H % p.BH || d->D % p.BD) return fail("grid not divisible by the tile box");
-  p.tiles_w = d->W / p.BW; p.tiles_h = d->H / p.BH; p.tiles_d = d->D / p.BD;
+  if (Wo % p.BW || Ho % p.BH || d->D % p.BD) return fail("grid not divisible by the tile box");
+  p.tiles_w = Wo / p.BW; p.tiles_h = Ho / p.BH; p.tiles_d = d->D / p.BD;
   pl.tiles_m = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
   // N tile: largest multiple-of-16 divisor of Cout_pad up to the cap, shrunk while the grid under-fills the GPU
   static int bn_cap = [] { const char* e = getenv("MPB200_TC_BN_MAX"); int v = e ? atoi(e) : 256; return v < 16 ? 16 : (v > 256 ? 256 : v); }();
@@ -930,8 +961,10 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   pl.slab = false;
   // ---- slab (vertical-halo reuse) kernel for 3x3(x3) convolutions with <= 128 output channels
   static int allow_slab = [] { const char* e = getenv("MPB200_TC_NO_SLAB"); return (e && atoi(e)) ? 0 : 1; }();
-  if (!pl.v1 && allow_slab && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) && d->Cout_pad <= 128 &&
-      d->W % 8 == 0 && d->H % 16 == 0) {
+  if (pl.v1 && (p.stride != 1 || p.in_c_off || p.out_c_off || p.out_C != d->Cout || (d->in_C > 0 && d->in_C != d->Cin)))
+    return fail("v1 kernel has no stride / channel-window support");
+  if (!pl.v1 && allow_slab && p.stride == 1 && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) &&
+      d->Cout_pad <= 128 && d->W % 8 == 0 && d->H % 16 == 0) {
     const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + EPI_BYTES;
     const int bn = d->Cout_pad;
     const uint32_t b_stage = 2u * bn * p.CCHUNK * 2u;
@@ -966,12 +999,12 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   }
   if (pl.slab) {
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-    p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.D = d->D; p.H = Ho; p.W = Wo; p.Cin = d->Cin; p.Cout = d->Cout;
     p.KD = d->KD; p.KH = d->KH; p.KW = d->KW;
     p.bias = d->bias; p.res_f32 = d->res_f32; p.res_hi = (const bf16*)d->res_hi; p.res_lo = (const bf16*)d->res_lo;
     p.out_f32 = d->out_f32; p.out_hi = (bf16*)d->out_hi; p.out_lo = (bf16*)d->out_lo;
     p.stats = d->stats; p.gn_groups = d->gn_groups; p.act = d->act;
-    p.S = (int64_t)d->D * d->H * d->W;
+    p.S = (int64_t)d->D * Ho * Wo;
     return 0;
   }
   const uint32_t fixed = 1024 /*align slack*/ + 1024 /*barriers, tmem slot*/ + 2 * 256 * sizeof(double) +
@@ -1011,23 +1044,25 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.tiles_n = pl.tiles_n;
   p.total_tiles = pl.tiles_m * pl.tiles_n;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-  p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.D = d->D; p.H = Ho; p.W = Wo; p.Cin = d->Cin; p.Cout = d->Cout;
   p.KD = d->KD; p.KH = d->KH; p.KW = d->KW;
   p.bias = d->bias; p.res_f32 = d->res_f32; p.res_hi = (const bf16*)d->res_hi; p.res_lo = (const bf16*)d->res_lo;
   p.out_f32 = d->out_f32; p.out_hi = (bf16*)d->out_hi; p.out_lo = (bf16*)d->out_lo;
   p.stats = d->stats; p.gn_groups = d->gn_groups; p.act = d->act;
-  p.S = (int64_t)d->D * d->H * d->W;
+  p.S = (int64_t)d->D * Ho * Wo;
   if ((int64_t)pl.tiles_m * pl.tiles_n > 0x7fffffff) return fail("too many tiles");
   return 0;
 }
 
 int encode_act_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const Plan& pl) {
-  cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->D, (cuuint64_t)d->N};
-  cuuint64_t strides[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->W, (cuuint64_t)d->Cin * 2 * d->W * d->H,
-                           (cuuint64_t)d->Cin * 2 * d->W * d->H * d->D};
-  cuuint32_t box[5] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BW,
-                       (cuuint32_t)(pl.slab ? pl.x.MT * pl.p.BH + 2 : pl.p.BH), (cuuint32_t)pl.p.BD, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const cuuint64_t C = (cuuint64_t)(d->in_C > 0 ? d->in_C : d->Cin);
+  const cuuint32_t st = (cuuint32_t)pl.p.stride;
+  cuuint64_t dims[5] = {C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->D, (cuuint64_t)d->N};
+  cuuint64_t strides[4] = {C * 2, C * 2 * d->W, C * 2 * d->W * d->H, C * 2 * d->W * d->H * d->D};
+  // with elementStrides = s the box spans BW*s input elements and TMA keeps every s-th one (BW of them)
+  cuuint32_t box[5] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BW * st,
+                       (cuuint32_t)(pl.slab ? pl.x.MT * pl.p.BH + 2 : pl.p.BH * st), (cuuint32_t)pl.p.BD, 1};
+  cuuint32_t estr[5] = {1, st, st, 1, 1};
   CUresult r = get_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

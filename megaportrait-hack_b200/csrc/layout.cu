@@ -317,3 +317,74 @@ extern "C" int mp_blur_subsample(const float* x, const float* kernel, float* out
   MP_LAUNCH_CHECK("mp_blur_subsample");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ motion-encoder pools
+// MaxPool2d(3, stride 2, padding 1) on split CL tensors: one thread = one output pixel x 4 channels.
+__global__ void k_maxpool3x3s2_cl(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
+                                  bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int N, int H, int W, int C) {
+  const int C4 = C >> 2, Ho = H >> 1, Wo = W >> 1;
+  int64_t total = (int64_t)N * Ho * Wo * C4;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int c4 = (int)(t % C4);
+  int64_t p = t / C4;
+  int wo = (int)(p % Wo); p /= Wo;
+  int ho = (int)(p % Ho);
+  int n = (int)(p / Ho);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int i = 0; i < 3; ++i) {
+    int y = ho * 2 + i - 1;
+    if (y < 0 || y >= H) continue;
+    for (int j = 0; j < 3; ++j) {
+      int x = wo * 2 + j - 1;
+      if (x < 0 || x >= W) continue;
+      float4 v = mp_load_split4(in_hi, in_lo, (((int64_t)n * H + y) * W + x) * C + c4 * 4);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  mp_store_split4(out_hi, out_lo, t * 4, m);
+}
+
+extern "C" int mp_maxpool3x3s2_cl(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int N, int H, int W,
+                                  int C, void* stream) {
+  MP_REQUIRE(in_hi && in_lo && out_hi && out_lo, "mp_maxpool3x3s2_cl: null pointer");
+  MP_REQUIRE(N > 0 && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "mp_maxpool3x3s2_cl: bad dims");
+  int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
+  k_maxpool3x3s2_cl<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(
+      (const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi, (bf16*)out_lo, N, H, W, C);
+  MP_LAUNCH_CHECK("mp_maxpool3x3s2_cl");
+  return 0;
+}
+
+// AdaptiveAvgPool2d(1): grid (C/32 column groups, N); block 32 x 8: 8 row-walkers per channel, smem reduce.
+__global__ void k_global_avgpool_cl(const float* __restrict__ in_f32, const bf16* __restrict__ in_hi,
+                                    const bf16* __restrict__ in_lo, float* __restrict__ out, int64_t S, int C) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C) {
+    for (int64_t s = threadIdx.y; s < S; s += 8) {
+      int64_t o = ((int64_t)n * S + s) * C + c;
+      acc += in_f32 ? in_f32[o] : mp_join(in_hi[o], in_lo[o]);
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[(int64_t)n * C + c] = t / (float)S;
+  }
+}
+
+extern "C" int mp_global_avgpool_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out, int N,
+                                    int64_t S, int C, void* stream) {
+  MP_REQUIRE(out && (in_f32 || (in_hi && in_lo)), "mp_global_avgpool_cl: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && S > 0 && C > 0, "mp_global_avgpool_cl: bad dims");
+  dim3 grid((C + 31) / 32, N), block(32, 8);
+  k_global_avgpool_cl<<<grid, block, 0, mp_stream(stream)>>>(in_f32, (const bf16*)in_hi, (const bf16*)in_lo, out, S, C);
+  MP_LAUNCH_CHECK("mp_global_avgpool_cl");
+  return 0;
+}

@@ -1,9 +1,9 @@
-"""Motion encoder `Emtn` and the `CustomResNet50` descriptor branch as stock PyTorch modules.
+"""Motion encoder `Emtn` (model.py:869-907) and the `CustomResNet50` descriptor branch
+(model.py:136-173, row a7): module definitions with the reference's attribute names and state_dict keys.
 
-SURVEY.md section 8: `Emtn` (model.py:869-907) is on Gbase's call path but is NOT one of the hot-path rows this
-round (it is row f-1, "next"); `CustomResNet50` (model.py:136-173) is a secondary row that "may stay on cuDNN at
-first".  Both therefore run as ordinary torch/cuDNN modules here, with the reference's attribute names and
-state_dict keys, so that `Gbase.forward` is complete and checkpoints load with strict=True.
+Inference on a CUDA device runs both on libmpb200 kernels (`emtn_cuda.py`, `backend = "mpb200"`, the default).
+`backend = "cudnn"` selects a stock cuDNN plan (BatchNorm folded, channels_last) that also serves CPU tensors and is
+kept as the GPU incumbent for A/B timing; train mode / autograd use the plain module graph.
 """
 from __future__ import annotations
 
@@ -42,12 +42,16 @@ class CustomResNet50(nn.Module):
         self.layer3 = resnet.layer3
         self.adaptive_avg_pool = nn.AdaptiveAvgPool2d(FEATURE_SIZE_AVG_POOL)
         self.conv_reduce = nn.Conv2d(1024, 512, kernel_size=1)
+        self.backend = "mpb200"
 
     def forward(self, x):
         if self.training or torch.is_grad_enabled():
             x = F.relu(self.bn1(self.conv1(x)))
             x = self.maxpool(x)
             x = self.layer3(self.layer2(self.layer1(x)))
+        elif x.is_cuda and getattr(self, "backend", "mpb200") == "mpb200":
+            from . import emtn_cuda
+            return emtn_cuda.resnet50_descriptor(self, x)
         else:
             sig = _versions(self)
             c = self.__dict__.get("_mp_plan")
@@ -201,6 +205,7 @@ class Emtn(nn.Module):
         self.expression_net = nn.Sequential(*list(model.children())[:-1])
         self.expression_net.adaptive_pool = nn.AdaptiveAvgPool2d(FEATURE_SIZE)
         self.fc = nn.Linear(2048, COMPRESS_DIM)
+        self.backend = "mpb200"
 
     def _apply(self, fn, *a, **k):
         # the detector is not a registered sub-module (reference quirk); keep it on the same device/dtype anyway
@@ -226,7 +231,10 @@ class Emtn(nn.Module):
             translation = head_pose[:, 3:]
             expression = self.fc(torch.flatten(self.expression_net(x), start_dim=1))
             return rotations, translation, expression
-        # inference plan: BatchNorm folded, channels_last (no NCHW<->NHWC transposes around the cuDNN kernels)
+        if x.is_cuda and getattr(self, "backend", "mpb200") == "mpb200":
+            from . import emtn_cuda          # libmpb200 tcgen05 kernels
+            return emtn_cuda.emtn_forward(self, x)
+        # stock cuDNN plan: BatchNorm folded, channels_last (no NCHW<->NHWC transposes around the cuDNN kernels)
         hp_trunk, ex_trunk = self._plans()
         xcl = x.contiguous(memory_format=torch.channels_last)
         self.rotation_net.model.to(memory_format=torch.channels_last)

@@ -1,0 +1,170 @@
+"""libmpb200 inference plans for the motion encoder `Emtn` and the ResNet-50 descriptor branch
+(row a7): the three conv trunks of `Emtn.forward` (model.py:888-907) -- two CIFAR-style ResNet-18s (resnet.py:160-310)
+and the RepVGG-B1g2 deploy backbone of 6DRepNet (mysixdrepnet.py:30-69, 1215-1290) -- and `CustomResNet50`
+(model.py:136-173) run on the same tcgen05 split-bf16 convolution kernels as the generator:
+
+  * BatchNorm (eval) folded into the preceding convolution in float64;
+  * RGB stems run on the tensor-core kernel with their 3 input channels zero-padded to 16;
+  * stride-2 convolutions use TMA element strides, grouped convolutions one launch per group on channel windows;
+  * MaxPool2d(3,2,1) and the global average pools are small HBM-bound kernels; the final Linear layers (<= 2048x512)
+    are plain library GEMMs (`F.linear`).
+
+Plans are built lazily from the live parameters, cached on parameter versions, and never registered as sub-modules
+(the reference's state_dict keys are untouched).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, Act
+
+RGB_PAD = 16
+
+
+def rgb16(x: torch.Tensor) -> Act:
+    """NCHW fp32 [N,3,H,W] -> split channels-last activation with the channel axis zero-padded to 16."""
+    xp = F.pad(x, (0, 0, 0, 0, 0, RGB_PAD - x.shape[1]))
+    return ops.from_nchw(xp.contiguous(), f32=False, split=True)
+
+
+def _bn(bn: nn.BatchNorm2d) -> dict:
+    return {"weight": bn.weight.detach(), "bias": bn.bias.detach(), "running_mean": bn.running_mean,
+            "running_var": bn.running_var}
+
+
+def _pack_conv_bn(conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_pad: int = 0) -> ops.PackedConv:
+    w, b = conv.weight.detach(), (None if conv.bias is None else conv.bias.detach())
+    if bn is not None:
+        w, b = ops.fold_bn(w, b, _bn(bn), bn.eps)
+    return ops.pack_conv(w, b, conv.weight.device, cin_pad=cin_pad)
+
+
+class ResNetTrunkPlan:
+    """torchvision-style ResNet trunk (BasicBlock or Bottleneck): stem conv+bn+relu, MaxPool(3,2,1), residual stages."""
+
+    def __init__(self, conv1: nn.Conv2d, bn1: nn.BatchNorm2d, layers):
+        self.stem = _pack_conv_bn(conv1, bn1, cin_pad=RGB_PAD)
+        self.stem_stride = conv1.stride[0]
+        self.blocks: List[Tuple] = []
+        for layer in layers:
+            for blk in layer:
+                ds = None
+                if blk.downsample is not None:
+                    ds = (_pack_conv_bn(blk.downsample[0], blk.downsample[1]), blk.downsample[0].stride[0])
+                if type(blk).__name__ == "BasicBlock":
+                    convs = [(_pack_conv_bn(blk.conv1, blk.bn1), blk.conv1.stride[0]),
+                             (_pack_conv_bn(blk.conv2, blk.bn2), 1)]
+                else:   # Bottleneck (v1.5: the stride sits on conv2)
+                    convs = [(_pack_conv_bn(blk.conv1, blk.bn1), 1),
+                             (_pack_conv_bn(blk.conv2, blk.bn2), blk.conv2.stride[0]),
+                             (_pack_conv_bn(blk.conv3, blk.bn3), 1)]
+                self.blocks.append((convs, ds))
+
+    def features(self, x16: Act, last_f32: bool = False) -> Act:
+        h, _ = ops.conv(x16, self.stem, act=ACT_RELU, f32=False, split=True, stride=self.stem_stride)
+        h = ops.maxpool3x3s2(h)
+        for bi, (convs, ds) in enumerate(self.blocks):
+            idt = h if ds is None else ops.conv(h, ds[0], stride=ds[1], f32=True)[0]
+            t = h
+            for pw, s in convs[:-1]:
+                t, _ = ops.conv(t, pw, stride=s, act=ACT_RELU, f32=False, split=True)
+            last = last_f32 and bi == len(self.blocks) - 1
+            h, _ = ops.conv(t, convs[-1][0], stride=convs[-1][1], res=idt, act=ACT_RELU, f32=last, split=not last)
+        return h
+
+    def pooled(self, x16: Act) -> torch.Tensor:
+        return ops.global_avgpool(self.features(x16))
+
+
+class RepVGGPlan:
+    """RepVGG deploy backbone: 3x3 conv + ReLU blocks, stride 2 at stage heads, groups = 2 on even layers."""
+
+    def __init__(self, backbone: nn.Module):
+        self.blocks: List[Tuple] = []
+        stages = [backbone.layer0] + [b for li in range(1, 5) for b in getattr(backbone, f"layer{li}")]
+        for blk in stages:
+            conv = blk.rbr_reparam
+            g, s, cout = conv.groups, conv.stride[0], conv.out_channels
+            w, b = conv.weight.detach(), conv.bias.detach()
+            if g == 1:
+                packs = [ops.pack_conv(w, b, w.device, cin_pad=RGB_PAD if conv.in_channels == 3 else 0)]
+            else:
+                cg = cout // g
+                packs = [ops.pack_conv(w[i * cg:(i + 1) * cg], b[i * cg:(i + 1) * cg], w.device) for i in range(g)]
+            self.blocks.append((s, g, packs, cout))
+
+    def pooled(self, x16: Act) -> torch.Tensor:
+        h = x16
+        for s, g, packs, cout in self.blocks:
+            if g == 1:
+                h, _ = ops.conv(h, packs[0], stride=s, act=ACT_RELU, f32=False, split=True)
+            else:
+                N, D, H, W, C = h.shape
+                out = ops._alloc((N, 1, H // s, W // s, cout), h.device, False, True)
+                for i, pw in enumerate(packs):
+                    ops.conv(h, pw, stride=s, act=ACT_RELU, in_c_off=i * (C // g), out=out, out_c_off=i * (cout // g))
+                h = out
+        return ops.global_avgpool(h)
+
+
+def _versions(*mods) -> tuple:
+    s, dev = 0, None
+    for m in mods:
+        for t in list(m.parameters()) + list(m.buffers()):
+            s += t._version + (t.data_ptr() & 0xFFFF)
+            dev = t.device
+    return (s, str(dev))
+
+
+def emtn_plans(emtn):
+    hp, ex, rot = emtn.head_pose_net, emtn.expression_net, emtn.rotation_net.model
+    sig = _versions(hp, ex, rot)
+    c = emtn.__dict__.get("_mp_cuda_plans")
+    if c is None or c[0] != sig:
+        with torch.no_grad():
+            c = (sig, (ResNetTrunkPlan(hp.conv1, hp.bn1, [hp.layer1, hp.layer2, hp.layer3, hp.layer4]),
+                       ResNetTrunkPlan(ex[0], ex[1], [ex[4], ex[5], ex[6], ex[7]]),
+                       RepVGGPlan(rot)))
+        emtn.__dict__["_mp_cuda_plans"] = c
+    return c[1]
+
+
+def emtn_forward(emtn, x: torch.Tensor):
+    """Emtn.forward (model.py:888-907) on libmpb200 kernels: -> (Euler degrees [B,3], translation [B,3], z [B,512])."""
+    from .emtn import ortho6d_to_euler_deg
+    hp_plan, ex_plan, rot_plan = emtn_plans(emtn)
+    x16 = rgb16(x.float())
+    rot = emtn.rotation_net.model
+    x6 = F.linear(rot_plan.pooled(x16), rot.linear_reg.weight, rot.linear_reg.bias)
+    rotations = ortho6d_to_euler_deg(x6[:, :6])
+    head_pose = F.linear(hp_plan.pooled(x16), emtn.head_pose_net.fc.weight, emtn.head_pose_net.fc.bias)
+    translation = head_pose[:, 3:]
+    # AdaptiveAvgPool2d(1) then AdaptiveAvgPool2d((2,2)) (model.py:880-881): every channel replicated 2x2, NCHW flatten
+    feat = ex_plan.pooled(x16).repeat_interleave(4, dim=1)
+    expression = F.linear(feat, emtn.fc.weight, emtn.fc.bias)
+    return rotations, translation, expression
+
+
+def resnet50_descriptor(r50, x: torch.Tensor) -> torch.Tensor:
+    """CustomResNet50.forward (model.py:156-173) on libmpb200 kernels -> (B, 512, 2, 2) NCHW."""
+    sig = _versions(r50)
+    c = r50.__dict__.get("_mp_cuda_plan")
+    if c is None or c[0] != sig:
+        with torch.no_grad():
+            c = (sig, (ResNetTrunkPlan(r50.conv1, r50.bn1, [r50.layer1, r50.layer2, r50.layer3]),
+                       ops.pack_conv(r50.conv_reduce.weight, r50.conv_reduce.bias, r50.conv_reduce.weight.device)))
+        r50.__dict__["_mp_cuda_plan"] = c
+    trunk, reduce_pw = c[1]
+    h = trunk.features(rgb16(x.float()), last_f32=True)           # [N,1,32,32,1024] fp32
+    # AdaptiveAvgPool2d(2) on a 32x32 map == four successive 2x2 average pools (uniform blocks)
+    while h.shape[2] > 2:
+        h = ops.avgpool2(h, 1, f32=True, split=False)
+    if h.shape[2] != 2 or h.shape[3] != 2:
+        raise RuntimeError(f"CustomResNet50: unexpected feature map {h.shape} (expects 512x512 inputs)")
+    out, _ = ops.conv(h, reduce_pw, f32=True)                      # 1x1 1024->512 on the 2x2 map
+    return ops.to_nchw(out, 4)

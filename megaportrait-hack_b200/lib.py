@@ -56,6 +56,7 @@ class ConvDesc(Structure):
         ("out_f32", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p), ("stats", c_void_p),
         ("N", c_int), ("D", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
         ("KD", c_int), ("KH", c_int), ("KW", c_int), ("Cout_pad", c_int), ("gn_groups", c_int), ("act", c_int),
+        ("stride", c_int), ("in_c_off", c_int), ("in_C", c_int), ("out_c_off", c_int), ("out_C", c_int),
     ]
 
 
@@ -73,6 +74,8 @@ _SIGNATURES = {
     "mp_gn_stats": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P]),
     "mp_gn_finalize": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_float, _P]),
     "mp_affine_act_cl": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P]),
+    "mp_maxpool3x3s2_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "mp_global_avgpool_cl": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, _P]),
     "mp_conv_tc": (c_int, [POINTER(ConvDesc), _P]),
     "mp_conv_simt": (c_int, [POINTER(ConvDesc), _P]),
     "mp_conv_tc_supported": (c_int, [POINTER(ConvDesc)]),
@@ -101,7 +104,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mp_abi_version() != 1:
+    if lib.mp_abi_version() != 2:
         raise RuntimeError("libmpb200.so ABI version mismatch")
     _lib = lib
     return lib

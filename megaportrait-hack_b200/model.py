@@ -465,17 +465,19 @@ class Eapp(nn.Module, _Packed):
         self.avgpool = nn.AvgPool2d(kernel_size=2, stride=2, padding=0)
         self.custom_resnet50 = CustomResNet50()
         self.fc = torch.nn.Linear(2048, COMPRESS_DIM)
-        self.tf32_descriptor = True   # cuDNN TF32 for the (non hot-path) ResNet-50 descriptor branch
+        self.tf32_descriptor = True   # only used by the stock cuDNN backend of the ResNet-50 descriptor branch
 
     def _build_plan(self):
         dev = self.conv.weight.device
-        return {"stem": ops.pack_conv(self.conv.weight, self.conv.bias, dev),
+        # RGB stem on the tensor-core kernel: 3 input channels zero-padded to 16
+        return {"stem": ops.pack_conv(self.conv.weight, self.conv.bias, dev, cin_pad=16),
                 "c1": ops.pack_conv(self.conv_1.weight, self.conv_1.bias, dev)}
 
     def _volume_cl(self, x: torch.Tensor) -> Act:
         """x NCHW fp32 [B,3,512,512] -> vs channels-last [B,16,64,64,96] (f32 + split)."""
         P = self._plan()
-        a = ops.from_nchw(x, f32=False, split=True)
+        from .emtn_cuda import rgb16
+        a = rgb16(x)
         out, st = ops.conv(a, P["stem"], f32=True, split=True, stats_groups=32)
         for blk in (self.resblock_128, self.resblock_256, self.resblock_512):
             y = blk._forward_cl(out, st)
@@ -647,7 +649,7 @@ class Gbase(nn.Module):
         self.G3d = G3d(in_channels=96)
         self.G2d = G2d(in_channels=96)
         self.image_pyramid = ImagePyramide(scales=[0.5, 0.25], num_channels=3)
-        self.tf32_motion = True   # cuDNN TF32 for Emtn (not a hot-path row this round)
+        self.tf32_motion = True   # only used when motionEncoder.backend == "cudnn" (stock incumbent path)
 
     def _emtn(self, x):
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=bool(self.tf32_motion)):

@@ -241,12 +241,15 @@ def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: dict, eps: float = 1
     return w, (b0 - bn["running_mean"].double()) * s + bn["bias"].double()
 
 
-def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> PackedConv:
-    """weight (Cout, Cin, [kd,] kh, kw) float32/64 -> PackedConv on `device`."""
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, cin_pad: int = 0) -> PackedConv:
+    """weight (Cout, Cin, [kd,] kh, kw) float32/64 -> PackedConv on `device`.  `cin_pad` zero-pads the input-channel
+    axis (RGB stems run on the tensor-core kernel with their 3 channels padded to 16)."""
     device = device or weight.device
     w = weight.detach().to(device=device, dtype=torch.float64)
     if w.dim() == 4:
         w = w.unsqueeze(2)
+    if cin_pad and cin_pad > w.shape[1]:
+        w = torch.cat([w, torch.zeros(w.shape[0], cin_pad - w.shape[1], *w.shape[2:], dtype=w.dtype, device=device)], 1)
     Cout, Cin, kd, kh, kw = w.shape
     wk = w.permute(0, 2, 3, 4, 1).reshape(Cout, kd * kh * kw * Cin).to(torch.float32)
     Cout_pad = (Cout + 15) // 16 * 16
@@ -268,15 +271,22 @@ def set_conv_mode(mode: str) -> None:
 
 
 def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE, f32: bool = True,
-         split: bool = False, stats_groups: int = 0, mode: Optional[str] = None
-         ) -> Tuple[Act, Optional[torch.Tensor]]:
-    """act(conv(a) + bias + res) -> (Act, GroupNorm statistics of the written values or None)."""
+         split: bool = False, stats_groups: int = 0, mode: Optional[str] = None, stride: int = 1, in_c_off: int = 0,
+         out: Optional[Act] = None, out_c_off: int = 0) -> Tuple[Act, Optional[torch.Tensor]]:
+    """act(conv(a) + bias + res) -> (Act, GroupNorm statistics of the written values or None).
+
+    `stride` (1|2) applies to H and W.  `in_c_off` selects the window [in_c_off, in_c_off + pw.Cin) of a's channels;
+    `out` / `out_c_off` write into the channel window of an existing activation (grouped convolutions)."""
     if a.hi is None:
         ensure_split(a)
     N, D, H, W, C = a.shape
-    if C != pw.Cin:
-        raise RuntimeError(f"conv: activation has {C} channels, weights expect {pw.Cin}")
-    out = _alloc((N, D, H, W, pw.Cout), a.device, f32, split)
+    if in_c_off + pw.Cin > C or (in_c_off == 0 and out is None and C != pw.Cin):
+        raise RuntimeError(f"conv: activation has {C} channels, weights expect {pw.Cin} (+{in_c_off})")
+    Ho, Wo = H // stride, W // stride
+    if out is None:
+        out = _alloc((N, D, Ho, Wo, pw.Cout), a.device, f32, split)
+    elif out.shape[:4] != (N, D, Ho, Wo) or out_c_off + pw.Cout > out.shape[4]:
+        raise RuntimeError(f"conv: output window does not fit {out.shape}")
     stats = new_stats(N, stats_groups, a.device) if stats_groups else None
     d = ConvDesc()
     d.in_hi, d.in_lo, d.w_hi, d.w_lo, d.bias = _p(a.hi), _p(a.lo), _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias)
@@ -291,10 +301,11 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     d.N, d.D, d.H, d.W, d.Cin, d.Cout = N, D, H, W, pw.Cin, pw.Cout
     d.KD, d.KH, d.KW = pw.k
     d.Cout_pad, d.gn_groups, d.act = pw.Cout_pad, stats_groups, act
+    d.stride, d.in_c_off, d.in_C, d.out_c_off, d.out_C = stride, in_c_off, C, out_c_off, out.shape[4]
     L = _lib.load()
     mode = mode or _CONV_MODE
     use_tc = mode == "tc" or (mode == "auto" and L.mp_conv_tc_supported(ctypes.byref(d)) == 1)
-    flops = 2 * N * D * H * W * pw.Cout * pw.Cin * pw.k[0] * pw.k[1] * pw.k[2]
+    flops = 2 * N * D * Ho * Wo * pw.Cout * pw.Cin * pw.k[0] * pw.k[1] * pw.k[2]
     with _Prof("conv_tc" if use_tc else "conv_simt", flops):
         if use_tc:
             _lib.check(L.mp_conv_tc(ctypes.byref(d), _stream()), "mp_conv_tc")
@@ -302,6 +313,30 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
             _lib.check(L.mp_conv_simt(ctypes.byref(d), _stream()), "mp_conv_simt")
     _count()
     return out, stats
+
+
+def maxpool3x3s2(a: Act) -> Act:
+    """nn.MaxPool2d(3, 2, 1) on a split 2-D activation."""
+    N, D, H, W, C = a.shape
+    assert D == 1
+    ensure_split(a)
+    out = _alloc((N, 1, H // 2, W // 2, C), a.device, False, True)
+    L = _lib.load()
+    _lib.check(L.mp_maxpool3x3s2_cl(_p(a.hi), _p(a.lo), _p(out.hi), _p(out.lo), N, H, W, C, _stream()),
+               "mp_maxpool3x3s2_cl")
+    _count()
+    return out
+
+
+def global_avgpool(a: Act) -> torch.Tensor:
+    """nn.AdaptiveAvgPool2d(1) + flatten: -> [N, C] fp32."""
+    N, D, H, W, C = a.shape
+    out = torch.empty((N, C), dtype=torch.float32, device=a.device)
+    L = _lib.load()
+    _lib.check(L.mp_global_avgpool_cl(_p(a.f32), _p(a.hi), _p(a.lo), _p(out), N, D * H * W, C, _stream()),
+               "mp_global_avgpool_cl")
+    _count()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------- warping

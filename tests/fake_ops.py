@@ -132,18 +132,47 @@ def affine_act(a, ab, res=None, act=ops.ACT_NONE, f32=False, split=True):
     return _mk(_act(v, act), f32, split)
 
 
-def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=0, mode=None):
+def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=0, mode=None, stride=1, in_c_off=0,
+         out=None, out_c_off=0):
     ensure_split(a)
-    x = _to_ncdhw(a.hi.float() + a.lo.float())
+    x = _to_ncdhw(a.hi.float() + a.lo.float())[:, in_c_off:in_c_off + pw.Cin]
     kd, kh, kw = pw.k
     w = (pw.w_hi.float() + pw.w_lo.float())[: pw.Cout].view(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3)
-    y = F.conv3d(x, w.contiguous(), pw.bias, padding=(kd // 2, kh // 2, kw // 2))
+    y = F.conv3d(x, w.contiguous(), pw.bias, stride=(1, stride, stride), padding=(kd // 2, kh // 2, kw // 2))
     v = _to_cl(y)
     if res is not None:
-        v = v + _val(res)
+        rv = _val(res)
+        v = v + (rv if out is None else rv[..., out_c_off:out_c_off + pw.Cout])
     v = _act(v, act)
     st = _stats_of(v, stats_groups) if stats_groups else None
+    if out is not None:
+        if out.f32 is not None:
+            out.f32[..., out_c_off:out_c_off + pw.Cout] = v
+        if out.hi is not None:
+            h, l = _split(v)
+            out.hi[..., out_c_off:out_c_off + pw.Cout] = h
+            out.lo[..., out_c_off:out_c_off + pw.Cout] = l
+        return out, st
     return _mk(v, f32, split), st
+
+
+def _alloc(shape, device, f32, split):
+    a = Act(shape)
+    if f32:
+        a.f32 = torch.zeros(shape)
+    if split:
+        a.hi = torch.zeros(shape, dtype=torch.bfloat16)
+        a.lo = torch.zeros(shape, dtype=torch.bfloat16)
+    return a
+
+
+def maxpool3x3s2(a):
+    y = F.max_pool2d(_to_ncdhw(_val(a)).squeeze(2), 3, 2, 1).unsqueeze(2)
+    return _mk(_to_cl(y), False, True)
+
+
+def global_avgpool(a):
+    return _val(a).mean(dim=(1, 2, 3))
 
 
 def grid_sample3d(v, grid):
@@ -185,7 +214,7 @@ def blur_subsample(x, kernel2d, step):
 
 _NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
-          "warp_fused", "blur_subsample"]
+          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc"]
 
 
 @contextlib.contextmanager

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 RGB_TOL = 1e-3
 STAGE_TOL = 2e-4
-MOTION_TOL = 2e-2     # Emtn / ResNet-50 descriptor run as stock cuDNN modules with TF32 allowed (not hot-path rows)
+MOTION_TOL = 2e-4     # Emtn / ResNet-50 descriptor also run on the split-bf16 tcgen05 kernels (fp32-grade)
 
 
 def _ncdhw(a):
@@ -127,6 +127,28 @@ def test_module_level_dropins(gbase, oracle_synth):
     assert (img.cpu() - st["rgb"]).abs().max().item() <= RGB_TOL
     with pytest.raises(AssertionError):
         gbase.warp_generator_c2d(st["Rs"].cuda(), st["ts"].cuda(), st["zs"].cuda(), st["es"].cuda().repeat(2, 1))
+
+
+def test_motion_encoder_and_descriptor_on_libmpb200(gbase, oracle_synth, seeded_sd):
+    """Row f-1 / a7: Emtn (2x ResNet-18 + RepVGG-B1g2) and CustomResNet50 on the tcgen05 kernels vs the oracle, and the
+    stock cuDNN backend (fp32) as a second opinion."""
+    import gbase_oracle as O
+    from megaportrait_hack_b200 import ops
+    xs, xd, rgb_o, pyr_o, st = oracle_synth
+    l0 = ops.LAUNCHES
+    R, t, z = gbase.motionEncoder(xd.cuda())
+    assert ops.LAUNCHES - l0 > 100, "Emtn must run on libmpb200 kernels"
+    assert rel(z.cpu(), st["zd"]) <= STAGE_TOL and rel(t.cpu(), st["td"]) <= STAGE_TOL
+    assert rel(R.cpu(), st["Rd"]) <= STAGE_TOL
+    vs, es = gbase.appearanceEncoder(xs.cuda())
+    assert rel(es.cpu(), st["es"]) <= STAGE_TOL and rel(vs.cpu(), st["vs"]) <= STAGE_TOL
+    gbase.motionEncoder.backend = "cudnn"
+    try:
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            R2, t2, z2 = gbase.motionEncoder(xd.cuda())
+    finally:
+        gbase.motionEncoder.backend = "mpb200"
+    assert rel(z2.cpu(), st["zd"]) <= STAGE_TOL
 
 
 def test_no_cpu_fallback(gbase):

@@ -281,3 +281,66 @@ def test_blur_subsample(ops):
         k, _ = O.gaussian_kernel(s, 3)
         got = ops.blur_subsample(x.to(DEV), k[0, 0].contiguous().to(DEV), step).cpu()
         assert (got - ref["prediction_" + str(s)]).abs().max().item() <= 2e-6
+
+
+# ----------------------------------------------------------------------------------------------------- ABI v2
+STRIDE_CASES = [
+    # name,          N, Cin, Cout, H,   W,   k, stride
+    ("s2_3x3",       2, 64,  128,  64,  64,  3, 2),
+    ("s2_1x1",       2, 128, 256,  32,  32,  1, 2),
+    ("s2_3x3_w256",  1, 64,  64,   32,  512, 3, 2),
+    ("s1_rgb_stem",  2, 3,   64,   64,  64,  3, 1),
+    ("s2_rgb_stem",  2, 3,   64,   64,  128, 3, 2),
+    ("s2_7x7_stem",  1, 3,   64,   128, 128, 7, 2),
+]
+
+
+@pytest.mark.parametrize("case", STRIDE_CASES, ids=[c[0] for c in STRIDE_CASES])
+@pytest.mark.parametrize("mode", ["tc", "simt"])
+def test_conv_stride_and_rgb_padding(ops, case, mode):
+    name, N, Cin, Cout, H, W, k, stride = case
+    x = rnd(N, Cin, H, W, seed=21)
+    w = rnd(Cout, Cin, k, k, seed=22) / math.sqrt(Cin * k * k)
+    b = rnd(Cout, seed=23) * 0.1
+    ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=k // 2))
+    pad = 16 if Cin == 3 else 0
+    xin = F.pad(x, (0, 0, 0, 0, 0, pad - Cin)) if pad else x
+    a = ops.from_nchw(xin.to(DEV), f32=False, split=True)
+    pw = ops.pack_conv(w, b, DEV, cin_pad=pad)
+    out, _ = ops.conv(a, pw, act=ops.ACT_RELU, f32=True, split=True, stride=stride, mode=mode)
+    got = cl_to_ncdhw(out.f32.cpu()).squeeze(2)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 3e-5, name
+
+
+@pytest.mark.parametrize("mode", ["tc", "simt"])
+@pytest.mark.parametrize("stride", [1, 2])
+def test_grouped_conv_via_channel_windows(ops, mode, stride):
+    """RepVGG-B1g2 layers (mysixdrepnet.py:1262-1290): groups = 2, one launch per group on channel windows."""
+    N, Cin, Cout, H, W, g = 2, 128, 256, 32, 32, 2
+    x = rnd(N, Cin, H, W, seed=31)
+    w = rnd(Cout, Cin // g, 3, 3, seed=32) / math.sqrt(Cin // g * 9)
+    b = rnd(Cout, seed=33) * 0.1
+    ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=1, groups=g))
+    a = ops.from_nchw(x.to(DEV), f32=False, split=True)
+    out = ops._alloc((N, 1, H // stride, W // stride, Cout), DEV, True, True)
+    cg = Cout // g
+    for i in range(g):
+        pw = ops.pack_conv(w[i * cg:(i + 1) * cg], b[i * cg:(i + 1) * cg], DEV)
+        ops.conv(a, pw, act=ops.ACT_RELU, stride=stride, in_c_off=i * (Cin // g), out=out, out_c_off=i * cg, mode=mode)
+    got = cl_to_ncdhw(out.f32.cpu()).squeeze(2)
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 3e-5
+    got_s = cl_to_ncdhw((out.hi.float() + out.lo.float()).cpu()).squeeze(2)
+    assert (got_s - ref).abs().max().item() / ref.abs().max().item() < 6e-5
+
+
+def test_maxpool_and_global_avgpool(ops):
+    x = rnd(3, 64, 32, 48, seed=41)
+    a = ops.from_nchw(x.to(DEV), f32=True, split=True)
+    xs = (a.hi.float() + a.lo.float()).cpu().permute(0, 4, 1, 2, 3).squeeze(2)      # values as the kernel sees them
+    got = ops.maxpool3x3s2(ops.Act(a.shape, hi=a.hi, lo=a.lo))
+    assert torch.equal(cl_to_ncdhw(val(got)).squeeze(2), F.max_pool2d(xs, 3, 2, 1))
+    gap = ops.global_avgpool(ops.Act(a.shape, f32=a.f32)).cpu()
+    assert (gap - x.mean(dim=(2, 3))).abs().max().item() < 1e-6
+    gap = ops.global_avgpool(ops.Act(a.shape, hi=a.hi, lo=a.lo)).cpu()
+    assert (gap - xs.mean(dim=(2, 3))).abs().max().item() < 1e-6
