@@ -171,21 +171,11 @@ def run_b200(args):
     del xd_all
     xs_d, xd_d = xs_h.to(dev), xd_h.to(dev)
     rgb_h = torch.empty((B, 3, 512, 512), dtype=torch.float32).pin_memory()
-    n_vol = 16 * 64 * 64 * 96
-    bcast = torch.empty(n_vol + 512, dtype=torch.float32, device=dev) if world > 1 else None
+    from megaportrait_hack_b200.engine import ShardedGbase
+    sharded = ShardedGbase(G)   # rank 0 encodes; the path's only collective is one 25.2 MB broadcast of vc2d + es
 
     def step(xs, xd):
-        if world == 1:
-            src = G.encode_source(xs)
-        else:
-            if rank == 0:
-                s = G.encode_source(xs)
-                bcast[:n_vol].copy_(s["vc2d"].f32.view(-1))
-                bcast[n_vol:].copy_(s["es"].view(-1))
-            dist.broadcast(bcast, 0)   # the path's only collective: encoded source volume + descriptor, 25.2 MB
-            src = {"vc2d": ops.Act((1, 16, 64, 64, 96), f32=bcast[:n_vol].view(1, 16, 64, 64, 96)),
-                   "es": bcast[n_vol:].view(1, 512)}
-        return G.drive(src, xd)
+        return sharded.step(xs, xd)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -243,7 +233,13 @@ def run_b200(args):
 
     pk = peaks()
     agg = {}
+    if args.dump_launches:
+        with open(args.dump_launches, "w") as f:
+            for kind, a, b, fl, by in prof:
+                t_ms = a.elapsed_time(b)
+                f.write(f"{t_ms:9.4f} ms  {fl / t_ms / 1e9 if fl else 0:8.1f} TFLOP/s  {by / t_ms / 1e6 if by else 0:8.1f} GB/s  {kind}\n")
     for kind, a, b, fl, by in prof:
+        kind = kind.split("|")[0]
         d = agg.setdefault(kind, {"ms": 0.0, "flops": 0, "bytes": 0, "n": 0})
         d["ms"] += a.elapsed_time(b); d["flops"] += fl; d["bytes"] += by; d["n"] += 1
     step_ms = ms / args.steps
@@ -314,6 +310,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--drivers-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default="", help="write the per-launch CUDA-event profile of one step here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

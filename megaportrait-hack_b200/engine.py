@@ -1,0 +1,76 @@
+"""Driver-frame sharding over the GPUs of one node.
+
+The path shards by driver frame: in eval mode nothing couples two samples, so rank r drives frames
+[r*N/P, (r+1)*N/P) of a batch that shares one source.  The only data-path collective is ONE broadcast of the encoded
+source state -- the canonical volume `vc2d` (96x16x64x64 fp32 = 25 165 824 B) and the descriptor `es` (2 048 B),
+packed into a single buffer -- from the encoding rank.  Outputs stay rank-local.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import Act
+
+VOL_SHAPE = (1, 16, 64, 64, 96)          # channels-last [N, D, H, W, C]
+VOL_NUMEL = 16 * 64 * 64 * 96
+ES_NUMEL = 512
+STATE_NUMEL = VOL_NUMEL + ES_NUMEL
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of n_total driver frames: the first (n_total % world) ranks take one extra."""
+    base, extra = divmod(n_total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def pack_source(src: Dict[str, object], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """{'vc2d': Act (1 sample, fp32), 'es': [1,512]} -> one flat fp32 buffer (the broadcast payload)."""
+    vol = src["vc2d"].f32
+    es = src["es"]
+    if vol.numel() != VOL_NUMEL or es.numel() != ES_NUMEL:
+        raise RuntimeError(f"pack_source expects one source sample, got {tuple(vol.shape)} / {tuple(es.shape)}")
+    if out is None:
+        out = torch.empty(STATE_NUMEL, dtype=torch.float32, device=vol.device)
+    out[:VOL_NUMEL].copy_(vol.reshape(-1))
+    out[VOL_NUMEL:].copy_(es.reshape(-1))
+    return out
+
+
+def unpack_source(flat: torch.Tensor) -> Dict[str, object]:
+    """Views into the flat buffer (no copy)."""
+    return {"vc2d": Act(VOL_SHAPE, f32=flat[:VOL_NUMEL].view(VOL_SHAPE)), "es": flat[VOL_NUMEL:].view(1, ES_NUMEL)}
+
+
+class ShardedGbase:
+    """One process per GPU.  `step(xs, xd_local)`: rank `src_rank` encodes the source, one broadcast, every rank drives
+    its own frames.  With world size 1 no collective is issued."""
+
+    def __init__(self, gbase, group=None, src_rank: int = 0):
+        import torch.distributed as dist
+        self.G = gbase
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.src_rank = src_rank
+        self._buf: Optional[torch.Tensor] = None
+
+    def broadcast_source(self, src: Optional[Dict[str, object]], device) -> Dict[str, object]:
+        if self.world == 1:
+            return src
+        if self._buf is None or self._buf.device != torch.device(device):
+            self._buf = torch.empty(STATE_NUMEL, dtype=torch.float32, device=device)
+        if self.rank == self.src_rank:
+            pack_source(src, self._buf)
+        self.dist.broadcast(self._buf, self.src_rank, group=self.group)
+        return unpack_source(self._buf)
+
+    @torch.no_grad()
+    def step(self, xs: torch.Tensor, xd_local: torch.Tensor):
+        src = self.G.encode_source(xs) if self.rank == self.src_rank else None
+        src = self.broadcast_source(src, xd_local.device)
+        return self.G.drive(src, xd_local)

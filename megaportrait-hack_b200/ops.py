@@ -306,7 +306,8 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     mode = mode or _CONV_MODE
     use_tc = mode == "tc" or (mode == "auto" and L.mp_conv_tc_supported(ctypes.byref(d)) == 1)
     flops = 2 * N * D * Ho * Wo * pw.Cout * pw.Cin * pw.k[0] * pw.k[1] * pw.k[2]
-    with _Prof("conv_tc" if use_tc else "conv_simt", flops):
+    with _Prof(("conv_tc" if use_tc else "conv_simt") +
+               f"|{N}x{D}x{H}x{W} {pw.Cin}->{pw.Cout} k{pw.k[0]}{pw.k[1]}{pw.k[2]} s{stride}", flops):
         if use_tc:
             _lib.check(L.mp_conv_tc(ctypes.byref(d), _stream()), "mp_conv_tc")
         else:

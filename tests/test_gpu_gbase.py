@@ -136,15 +136,17 @@ def test_motion_encoder_and_descriptor_on_libmpb200(gbase, oracle_synth, seeded_
     from megaportrait_hack_b200 import ops
     xs, xd, rgb_o, pyr_o, st = oracle_synth
     l0 = ops.LAUNCHES
-    R, t, z = gbase.motionEncoder(xd.cuda())
-    assert ops.LAUNCHES - l0 > 100, "Emtn must run on libmpb200 kernels"
+    with torch.no_grad():
+        R, t, z = gbase.motionEncoder(xd.cuda())
+    assert ops.LAUNCHES - l0 > 50, "Emtn must run on libmpb200 kernels"
     assert rel(z.cpu(), st["zd"]) <= STAGE_TOL and rel(t.cpu(), st["td"]) <= STAGE_TOL
     assert rel(R.cpu(), st["Rd"]) <= STAGE_TOL
-    vs, es = gbase.appearanceEncoder(xs.cuda())
+    with torch.no_grad():
+        vs, es = gbase.appearanceEncoder(xs.cuda())
     assert rel(es.cpu(), st["es"]) <= STAGE_TOL and rel(vs.cpu(), st["vs"]) <= STAGE_TOL
     gbase.motionEncoder.backend = "cudnn"
     try:
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             R2, t2, z2 = gbase.motionEncoder(xd.cuda())
     finally:
         gbase.motionEncoder.backend = "mpb200"
