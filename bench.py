@@ -279,7 +279,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16x3 split (fp32-grade products, fp32 accumulate); motion encoder tf32",
+        "vs_baseline": None, "dtype": "bf16x3 split (fp32-grade products: hi*hi+hi*lo+lo*hi, fp32 accumulate in TMEM)",
         "data": "synthetic",
         "config": {"workload": f"Gbase inference, 1 src x {B} drv per GPU, 512x512 (BASELINE config "
                                f"{'2' if world == 1 else '3 share'}); source re-encoded every step",

@@ -136,6 +136,12 @@ int mp_warp_field(const float* em_cl, const float* theta, float* out, int N, int
 int mp_warp_fused_cl(const float* v, const float* em_cl, const float* theta, float* out_f32, void* out_hi,
                      void* out_lo, int N, int Nv, int C, int D, int H, int W, int E, int G, int sum_d, void* stream);
 
+/* 3x3 convolution head with few output channels (G2d's 64->3 RGB conv + Sigmoid, model.py:750-751), second half:
+ * y [N,H,W,Ct] CL fp32 holds the 9*Co per-tap partial products of a 1x1 convolution: channel index (kh*3+kw)*Co + co;
+ * out [N,Co,H,W] NCHW fp32 = act(bias + sum over the 3x3 neighbourhood).  Co = 3. */
+int mp_tap_sum3x3_cl(const float* y, const float* bias, float* out, int N, int H, int W, int Co, int Ct, int act,
+                     void* stream);
+
 /* ---------------------------------------------------------------- image pyramid ----------------------------- */
 /* AntiAliasInterpolation2d (model.py:683-691): zero-pad, depthwise ks x ks filter, nearest subsample by `step`.
  * x [N,C,H,W] fp32 NCHW, kernel [ks*ks] (same for every channel), out [N,C,H/step,W/step]. */

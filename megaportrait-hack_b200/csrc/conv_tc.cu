@@ -53,6 +53,8 @@ struct TcParams {
   int tiles_n, total_tiles;   // persistent kernel: tile id = m_tile * tiles_n + n_tile (n fastest => A shared in L2)
   uint32_t epi_off;           // byte offset (from the aligned smem base) of the epilogue staging area
   int stride, in_c_off, out_C, out_c_off;   // ABI v2: H/W stride, channel windows (D/H/W below are OUTPUT dims)
+  int dualb, acc_w;           // dual-B mode: D[:, 0:BN] += Al*Bh ; D[:, 0:2BN] += Ah*[Bh|Bl]; acc_w = TMEM columns per acc
+  uint32_t idesc2;            // instruction descriptor with N = 2*BN
   int b_resident;             // 1: the whole weight tile [taps*Cin x BN] stays in smem for the CTA's lifetime
   uint32_t bres_off;          // byte offset of the resident weight area
 };
@@ -157,6 +159,24 @@ __device__ __forceinline__ void umma_chunk(uint32_t tmem_d, uint32_t a_hi, uint3
     umma_bf16_lean(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc, 1u);
   }
 }
+// dual-B variant: two MMAs per K step -- Ah x [Bh|Bl] (N = 2*BN, Bl follows Bh in shared memory) and Al x Bh (N = BN)
+template <int KS>
+__device__ __forceinline__ void umma_chunk_dual(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                uint32_t hi, uint32_t idesc, uint32_t idesc2, uint32_t acc_first) {
+  const uint32_t ah = desc_lo_word(a_hi), al = desc_lo_word(a_lo), bh = desc_lo_word(b_hi);
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    umma_bf16_lean(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc2, k == 0 ? acc_first : 1u);
+    umma_bf16_lean(tmem_d, al + 2 * k, bh + 2 * k, hi, idesc, 1u);
+  }
+}
+__device__ __forceinline__ void umma_chunk_dual_dyn(int ksteps, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
+                                                    uint32_t b_hi, uint32_t hi, uint32_t idesc, uint32_t idesc2,
+                                                    uint32_t acc_first) {
+  if (ksteps == 4) umma_chunk_dual<4>(tmem_d, a_hi, a_lo, b_hi, hi, idesc, idesc2, acc_first);
+  else if (ksteps == 2) umma_chunk_dual<2>(tmem_d, a_hi, a_lo, b_hi, hi, idesc, idesc2, acc_first);
+  else umma_chunk_dual<1>(tmem_d, a_hi, a_lo, b_hi, hi, idesc, idesc2, acc_first);
+}
 __device__ __forceinline__ void umma_chunk_dyn(int ksteps, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
                                                uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc_first) {
   if (ksteps == 4) umma_chunk<4>(tmem_d, a_hi, a_lo, b_hi, b_lo, hi, idesc, acc_first);
@@ -200,7 +220,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 // Drain one 128 x BN accumulator (TMEM columns tmem_acc .. +BN of this warp's lane quarter) through the staging
 // buffer: bias + residual + activation, warp-contiguous stores, per-column GroupNorm partial sums into s_stats.
 // Called by all 256 epilogue threads; contains CTA-level named barriers.
-__device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, long long* row_off, double* s_stats,
+__device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, long long* row_off, float* s_stats,
                                                uint32_t tmem_acc, int n0, int64_t obase, int half, int r, int et,
                                                int lane) {
   const bool vec4 = ((p.out_C | p.out_c_off | p.Cout) % 4) == 0, vec8 = ((p.out_C | p.out_c_off | p.Cout) % 8) == 0;
@@ -216,6 +236,12 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
     float v[16];
     if (mine) {
       tmem_ld16(tmem_acc + (uint32_t)(c0 + hc), v);
+      if (p.dualb) {                           // Ah*Bl partial products live BN columns further
+        float v2[16];
+        tmem_ld16(tmem_acc + (uint32_t)(p.BN + c0 + hc), v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+      }
       if (fast) {
         if (bias_vec) {
 #pragma unroll
@@ -318,25 +344,25 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
           const float x = epi[(slab * 16 + j) * EPI_PITCH + lane];
           sm += x; sq += x * x;
         }
-        atomicAdd(&s_stats[2 * (c0 + lane)], (double)sm);
-        atomicAdd(&s_stats[2 * (c0 + lane) + 1], (double)sq);
+        atomicAdd(&s_stats[2 * (c0 + lane)], sm);          // native fp32 shared-memory reduction (per-tile sums)
+        atomicAdd(&s_stats[2 * (c0 + lane) + 1], sq);
       }
     }
     epi_bar();                              // staging buffer may be overwritten
   }
 }
 
-__device__ __forceinline__ void epilogue_flush_stats(const TcParams& p, double* s_stats, int n, int n0, int et) {
+__device__ __forceinline__ void epilogue_flush_stats(const TcParams& p, float* s_stats, int n, int n0, int et) {
   const int cpg = p.gn_groups > 0 ? p.Cout / p.gn_groups : 1;
   for (int c = et; c < p.BN; c += 256) {
     const int co = n0 + c;
     if (co < p.Cout) {
       double* st = p.stats + ((int64_t)n * p.gn_groups + co / cpg) * 2;
-      atomicAdd(st, s_stats[2 * c]);
-      atomicAdd(st + 1, s_stats[2 * c + 1]);
+      atomicAdd(st, (double)s_stats[2 * c]);
+      atomicAdd(st + 1, (double)s_stats[2 * c + 1]);
     }
-    s_stats[2 * c] = 0.0;
-    s_stats[2 * c + 1] = 0.0;
+    s_stats[2 * c] = 0.f;
+    s_stats[2 * c + 1] = 0.f;
   }
   epi_bar();
 }
@@ -357,7 +383,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   const uint32_t bres_bar = bars + (2 * p.STAGES + 4) * 8;
   const uint32_t tmem_slot = bars + (2 * p.STAGES + 5) * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
-  double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
+  float* s_stats = reinterpret_cast<float*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return bars + s * 8; };
@@ -389,7 +415,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -453,7 +479,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         const uint32_t b = it & 1;
         mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + b * p.BN;
+        const uint32_t d_tmem = tmem_base + b * (uint32_t)p.acc_w;
         for (int i = 0; i < num_kb; ++i, ++kb) {
           const int s = kb % p.STAGES;
           const uint32_t ph_bit = (kb / p.STAGES) & 1;
@@ -463,7 +489,8 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
           const uint32_t a_hi = sa, a_lo = sa + p.a_bytes;
           const uint32_t b_hi = p.b_resident ? smem_base + p.bres_off + (uint32_t)i * 2u * p.b_bytes : sa + 2 * p.a_bytes;
           const uint32_t b_lo = b_hi + p.b_bytes;
-          umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, i > 0 ? 1u : 0u);
+          if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, i > 0 ? 1u : 0u);
+          else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, i > 0 ? 1u : 0u);
           umma_commit(empty_bar(s));
         }
         umma_commit(tfull_bar(b));
@@ -487,8 +514,8 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       const int64_t obase = pos * p.out_C + p.out_c_off;
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      epilogue_drain(p, epi, row_off, s_stats, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.BN), n0, obase,
-                     half, r, et, lane);
+      epilogue_drain(p, epi, row_off, s_stats, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.acc_w), n0,
+                     obase, half, r, et, lane);
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -538,7 +565,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   auto tempty_bar = [&](int b) { return bars + (2 * x.SA + 2 * x.SB + 2 + b) * 8; };
   const uint32_t tmem_slot = bars + (2 * x.SA + 2 * x.SB + 4) * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
-  double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));
+  float* s_stats = reinterpret_cast<float*>(gen_base + (tmem_slot + 8 - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_stage = 2 * x.a_plane_bytes, b_stage = 2 * p.b_bytes;
@@ -560,7 +587,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -620,7 +647,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         const uint32_t b = it & 1;
         mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem0 = tmem_base + b * (uint32_t)(x.MT * p.BN);
+        const uint32_t d_tmem0 = tmem_base + b * (uint32_t)(x.MT * p.acc_w);
         bool first = true;
         for (int g = 0; g < p.KD * p.KW * p.num_cchunks; ++g, ++ia) {
           const int sidx = ia % x.SA;
@@ -635,8 +662,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             for (int t = 0; t < x.MT; ++t) {
               const uint32_t a_hi = sa + (uint32_t)((t * p.BH + kh) * p.BW) * row_bytes;
               const uint32_t a_lo = a_hi + x.a_plane_bytes;
-              const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.BN);
-              umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, first ? 0u : 1u);
+              const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.acc_w);
+              if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, first ? 0u : 1u);
+              else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, first ? 0u : 1u);
             }
             first = false;
             umma_commit(emptyB(bidx));
@@ -662,7 +690,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         const int ww = r % p.BW, hh = r / p.BW;
         const int64_t pos = (((int64_t)n * p.D + d0) * p.H + h0 + t * p.BH + hh) * p.W + w0 + ww;
         epilogue_drain(p, epi, row_off, s_stats,
-                       tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * x.MT + t) * p.BN), n0,
+                       tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * x.MT + t) * p.acc_w), n0,
                        pos * p.out_C + p.out_c_off, half, r, et, lane);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -909,6 +937,11 @@ struct Plan {
   SlabExtra x;
 };
 
+bool allow_dual() {
+  static int v = [] { const char* e = getenv("MPB200_TC_NO_DUALB"); return (e && atoi(e)) ? 0 : 1; }();
+  return v != 0;
+}
+
 bool use_v1() {
   static int v = [] { const char* e = getenv("MPB200_TC_V1"); return (e && atoi(e)) ? 1 : 0; }();
   return v != 0;
@@ -991,7 +1024,9 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
         p.bres_off = 0;
         p.epi_off = pl.x.b_ring_off + sb * b_stage;
         pl.smem_bytes = fixed_s + p.epi_off;
-        p.tmem_cols = next_pow2(2 * mt * bn);
+        p.dualb = (allow_dual() && 2 * mt * 2 * bn <= 512) ? 1 : 0;
+        p.acc_w = p.dualb ? 2 * bn : bn;
+        p.tmem_cols = next_pow2(2 * mt * p.acc_w);
         p.tiles_n = 1;
         p.total_tiles = pl.tiles_m;
       }
@@ -999,6 +1034,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   }
   if (pl.slab) {
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
     p.D = d->D; p.H = Ho; p.W = Wo; p.Cin = d->Cin; p.Cout = d->Cout;
     p.KD = d->KD; p.KH = d->KH; p.KW = d->KW;
     p.bias = d->bias; p.res_f32 = d->res_f32; p.res_hi = (const bf16*)d->res_hi; p.res_lo = (const bf16*)d->res_lo;
@@ -1040,7 +1076,10 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   pl.smem_bytes = fixed + stages * p.stage_bytes + (p.b_resident ? bres_bytes : 0);
   p.bres_off = stages * p.stage_bytes;
   p.epi_off = p.bres_off + (p.b_resident ? bres_bytes : 0);
-  p.tmem_cols = next_pow2(pl.v1 ? p.BN : 2 * p.BN);
+  p.dualb = (!pl.v1 && allow_dual() && 2 * 2 * p.BN <= 512) ? 1 : 0;
+  p.acc_w = p.dualb ? 2 * p.BN : p.BN;
+  p.tmem_cols = next_pow2(pl.v1 ? p.BN : 2 * p.acc_w);
+  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   p.tiles_n = pl.tiles_n;
   p.total_tiles = pl.tiles_m * pl.tiles_n;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);

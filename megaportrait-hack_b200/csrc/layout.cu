@@ -231,11 +231,61 @@ __global__ void k_upsample2x_linear_cl(const float* __restrict__ in_f32, const b
   if (out_hi) mp_store_split4(out_hi, out_lo, o, acc);
 }
 
+// Split-in / split-out, 8 channels (16 bytes per plane) per thread: the G2d decoder's bilinear upsamples.
+struct __align__(16) bf16x8v {
+  bf16 v[8];
+};
+__global__ void k_upsample2x_bilinear_split8(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
+                                             bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int N, int H, int W,
+                                             int C) {
+  const int C8 = C >> 3;
+  const int Ho = H * 2, Wo = W * 2;
+  int64_t total = (int64_t)N * Ho * Wo * C8;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int c8 = (int)(t % C8);
+  int64_t p = t / C8;
+  int wo = (int)(p % Wo); p /= Wo;
+  int ho = (int)(p % Ho);
+  int n = (int)(p / Ho);
+  int h0, h1, w0, w1;
+  float lh, lw;
+  lin_src(ho, H, Ho, h0, h1, lh);
+  lin_src(wo, W, Wo, w0, w1, lw);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float wgt = (b ? lh : 1.f - lh) * (c ? lw : 1.f - lw);
+      const int64_t idx = (((int64_t)n * H + (b ? h1 : h0)) * W + (c ? w1 : w0)) * C + c8 * 8;
+      const bf16x8v h = *reinterpret_cast<const bf16x8v*>(in_hi + idx);
+      const bf16x8v l = *reinterpret_cast<const bf16x8v*>(in_lo + idx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += wgt * mp_join(h.v[i], l.v[i]);
+    }
+  }
+  bf16x8v oh, ol;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mp_split2(acc[i], oh.v[i], ol.v[i]);
+  *reinterpret_cast<bf16x8v*>(out_hi + t * 8) = oh;
+  *reinterpret_cast<bf16x8v*>(out_lo + t * 8) = ol;
+}
+
 extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out_f32,
                                        void* out_hi, void* out_lo, int N, int D, int H, int W, int C, int up_d,
                                        void* stream) {
   MP_REQUIRE((in_f32 || (in_hi && in_lo)) && (out_f32 || (out_hi && out_lo)), "mp_upsample2x_linear_cl: null pointer");
   MP_REQUIRE(C % 4 == 0 && (up_d == 1 || up_d == 2), "mp_upsample2x_linear_cl: bad dims");
+  if (!in_f32 && !out_f32 && D == 1 && up_d == 1 && C % 8 == 0) {
+    int64_t total8 = (int64_t)N * H * 2 * W * 2 * (C / 8);
+    k_upsample2x_bilinear_split8<<<(unsigned)((total8 + 255) / 256), 256, 0, mp_stream(stream)>>>(
+        (const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi, (bf16*)out_lo, N, H, W, C);
+    MP_LAUNCH_CHECK("mp_upsample2x_linear_cl");
+    return 0;
+  }
   int64_t total = (int64_t)N * D * up_d * H * 2 * W * 2 * (C / 4);
   unsigned grid = (unsigned)((total + 255) / 256);
   if (in_f32)
@@ -386,5 +436,49 @@ extern "C" int mp_global_avgpool_cl(const float* in_f32, const void* in_hi, cons
   dim3 grid((C + 31) / 32, N), block(32, 8);
   k_global_avgpool_cl<<<grid, block, 0, mp_stream(stream)>>>(in_f32, (const bf16*)in_hi, (const bf16*)in_lo, out, S, C);
   MP_LAUNCH_CHECK("mp_global_avgpool_cl");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ tap-sum head
+// A 3x3 convolution with very few output channels (the 64->3 RGB head of G2d, model.py:750) as a 1x1 convolution
+// that produces all 9*Co per-tap partial products per pixel (one tensor-core GEMM with N = 9*Co) followed by this
+// shift-and-add: out[n,co,h,w] = act(bias[co] + sum_{kh,kw} y[n, h+kh-1, w+kw-1, (kh*3+kw)*Co + co]), zero outside.
+// y is CL fp32 [N,H,W,Ct]; out is NCHW fp32.  One thread per output pixel; HBM-bound (reads y once, 9x from L1/L2).
+template <int CO>
+__global__ void k_tap_sum3x3(const float* __restrict__ y, const float* __restrict__ bias, float* __restrict__ out, int H,
+                             int W, int Ct, int act) {
+  const int64_t HW = (int64_t)H * W;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= HW) return;
+  const int n = blockIdx.y;
+  const int w = (int)(t % W), h = (int)(t / W);
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int hh = h + kh - 1;
+    if (hh < 0 || hh >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ww = w + kw - 1;
+      if (ww < 0 || ww >= W) continue;
+      const float* p = y + (((int64_t)n * H + hh) * W + ww) * Ct + (kh * 3 + kw) * CO;
+#pragma unroll
+      for (int c = 0; c < CO; ++c) acc[c] += __ldg(p + c);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CO; ++c) out[((int64_t)n * CO + c) * HW + t] = mp_apply_act(acc[c], act);
+}
+
+extern "C" int mp_tap_sum3x3_cl(const float* y, const float* bias, float* out, int N, int H, int W, int Co, int Ct,
+                                int act, void* stream) {
+  MP_REQUIRE(y && out, "mp_tap_sum3x3_cl: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && Ct >= 9 * Co, "mp_tap_sum3x3_cl: bad dims");
+  MP_REQUIRE(Co == 3, "mp_tap_sum3x3_cl: only Co = 3 is instantiated");
+  dim3 grid((unsigned)(((int64_t)H * W + 255) / 256), N);
+  k_tap_sum3x3<3><<<grid, 256, 0, mp_stream(stream)>>>(y, bias, out, H, W, Ct, act);
+  MP_LAUNCH_CHECK("mp_tap_sum3x3_cl");
   return 0;
 }

@@ -67,14 +67,36 @@ __device__ __forceinline__ void src_ac_false(int dst, int in_size, int out_size,
 // One thread = one output voxel (x fastest => coalesced grid reads and output writes) x a chunk of channels.
 constexpr int GS_CCHUNK = 8;
 
+// Gather `c1 - c0` channels for one output voxel.  Channels are processed four at a time with all 32 tap loads
+// issued before the first use, so each thread keeps 32 independent requests in flight (the kernel is latency-bound,
+// not bandwidth-bound, when written one channel at a time).
 __device__ __forceinline__ void gather_channels(const float* __restrict__ v, float* __restrict__ out, const Taps& t,
                                                 int c0, int c1, int64_t in_cs, int64_t out_cs) {
-  for (int c = c0; c < c1; ++c) {
+  int off[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) off[k] = t.off[k] >= 0 ? t.off[k] : t.off[0];   // skipped corners: weight 0, valid address
+  int c = c0;
+  for (; c + 4 <= c1; c += 4) {
+    float x[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* p = v + (int64_t)(c + j) * in_cs;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[j][k] = __ldg(p + off[k]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(x[j][k], t.w[k], acc);
+      out[(int64_t)(c + j) * out_cs] = acc;
+    }
+  }
+  for (; c < c1; ++c) {
     const float* p = v + (int64_t)c * in_cs;
     float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (t.off[k] >= 0) acc = fmaf(__ldg(p + t.off[k]), t.w[k], acc);
+    for (int k = 0; k < 8; ++k) acc = fmaf(__ldg(p + off[k]), t.w[k], acc);
     out[(int64_t)c * out_cs] = acc;
   }
 }

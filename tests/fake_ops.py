@@ -205,6 +205,19 @@ def warp_fused(v, em_cl, theta, sum_d, G=64, f32=True, split=False):
     return _mk(_to_cl(out), f32, split)
 
 
+def tap_sum3x3(y, bias, Co, act=ops.ACT_NONE):
+    v = y.f32[:, 0]                                    # [N,H,W,Ct]
+    N, H, W, Ct = v.shape
+    vp = F.pad(v, (0, 0, 1, 1, 1, 1))
+    out = torch.zeros(N, H, W, Co)
+    for kh in range(3):
+        for kw in range(3):
+            out += vp[:, kh:kh + H, kw:kw + W, (kh * 3 + kw) * Co:(kh * 3 + kw + 1) * Co]
+    if bias is not None:
+        out = out + bias
+    return _act(out, act).permute(0, 3, 1, 2).contiguous()
+
+
 def blur_subsample(x, kernel2d, step):
     ks = kernel2d.shape[-1]
     C = x.shape[1]
@@ -214,7 +227,7 @@ def blur_subsample(x, kernel2d, step):
 
 _NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
-          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc"]
+          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3"]
 
 
 @contextlib.contextmanager
