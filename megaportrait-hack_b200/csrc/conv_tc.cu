@@ -220,7 +220,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 // Drain one 128 x BN accumulator (TMEM columns tmem_acc .. +BN of this warp's lane quarter) through the staging
 // buffer: bias + residual + activation, warp-contiguous stores, per-column GroupNorm partial sums into s_stats.
 // Called by all 256 epilogue threads; contains CTA-level named barriers.
-__device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, long long* row_off, float* s_stats,
+__device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, long long* row_off, double* s_stats,
                                                uint32_t tmem_acc, int n0, int64_t obase, int half, int r, int et,
                                                int lane) {
   const bool vec4 = ((p.out_C | p.out_c_off | p.Cout) % 4) == 0, vec8 = ((p.out_C | p.out_c_off | p.Cout) % 8) == 0;
@@ -335,34 +335,48 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
       }
     }
     if (p.stats) {
-      // column sums over 16-row slabs: thread (slab = et / 32, col = lane)
+      // column sums over 16-row slabs: thread (slab = et / 32, col = lane) -> s_part[slab][col]; after the barrier one
+      // warp adds the 8 slabs in a fixed order (no atomics => bit-reproducible statistics)
+      float* s_part = reinterpret_cast<float*>(s_stats + 2 * 256);
+      const int slab = et >> 5;
+      float sm = 0.f, sq = 0.f;
       if (lane < ncol) {
-        const int slab = et >> 5;
-        float sm = 0.f, sq = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float x = epi[(slab * 16 + j) * EPI_PITCH + lane];
           sm += x; sq += x * x;
         }
-        atomicAdd(&s_stats[2 * (c0 + lane)], sm);          // native fp32 shared-memory reduction (per-tile sums)
-        atomicAdd(&s_stats[2 * (c0 + lane) + 1], sq);
       }
+      s_part[(slab * 32 + lane) * 2] = sm;
+      s_part[(slab * 32 + lane) * 2 + 1] = sq;
     }
     epi_bar();                              // staging buffer may be overwritten
+    if (p.stats && et < 32 && lane < ncol) {
+      const float* s_part = reinterpret_cast<const float*>(s_stats + 2 * 256);
+      double sm = 0.0, sq = 0.0;
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) {
+        sm += (double)s_part[(sl * 32 + lane) * 2];
+        sq += (double)s_part[(sl * 32 + lane) * 2 + 1];
+      }
+      s_stats[2 * (c0 + lane)] += sm;
+      s_stats[2 * (c0 + lane) + 1] += sq;
+    }
   }
 }
 
-__device__ __forceinline__ void epilogue_flush_stats(const TcParams& p, float* s_stats, int n, int n0, int et) {
+__device__ __forceinline__ void epilogue_flush_stats(const TcParams& p, double* s_stats, int n, int n0, int et) {
+  epi_bar();   // the last chunk's fixed-order slab reduction (threads 0..31) must have landed
   const int cpg = p.gn_groups > 0 ? p.Cout / p.gn_groups : 1;
   for (int c = et; c < p.BN; c += 256) {
     const int co = n0 + c;
     if (co < p.Cout) {
       double* st = p.stats + ((int64_t)n * p.gn_groups + co / cpg) * 2;
-      atomicAdd(st, (double)s_stats[2 * c]);
-      atomicAdd(st + 1, (double)s_stats[2 * c + 1]);
+      atomicAdd(st, s_stats[2 * c]);
+      atomicAdd(st + 1, s_stats[2 * c + 1]);
     }
-    s_stats[2 * c] = 0.f;
-    s_stats[2 * c + 1] = 0.f;
+    s_stats[2 * c] = 0.0;
+    s_stats[2 * c + 1] = 0.0;
   }
   epi_bar();
 }
@@ -383,7 +397,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   const uint32_t bres_bar = bars + (2 * p.STAGES + 4) * 8;
   const uint32_t tmem_slot = bars + (2 * p.STAGES + 5) * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
-  float* s_stats = reinterpret_cast<float*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
+  double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return bars + s * 8; };
@@ -415,7 +429,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.0;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -565,7 +579,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   auto tempty_bar = [&](int b) { return bars + (2 * x.SA + 2 * x.SB + 2 + b) * 8; };
   const uint32_t tmem_slot = bars + (2 * x.SA + 2 * x.SB + 4) * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
-  float* s_stats = reinterpret_cast<float*>(gen_base + (tmem_slot + 8 - smem_base));
+  double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_stage = 2 * x.a_plane_bytes, b_stage = 2 * p.b_bytes;
@@ -587,7 +601,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS2) s_stats[i] = 0.0;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -998,7 +1012,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     return fail("v1 kernel has no stride / channel-window support");
   if (!pl.v1 && allow_slab && p.stride == 1 && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) &&
       d->Cout_pad <= 128 && d->W % 8 == 0 && d->H % 16 == 0) {
-    const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + EPI_BYTES;
+    const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + 2048 /*s_part*/ + EPI_BYTES;
     const int bn = d->Cout_pad;
     const uint32_t b_stage = 2u * bn * p.CCHUNK * 2u;
     for (int mt = (d->H % 32 == 0 && 4 * bn <= 512) ? 2 : 1; mt >= 1 && !pl.slab; --mt) {
@@ -1044,7 +1058,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     return 0;
   }
   const uint32_t fixed = 1024 /*align slack*/ + 1024 /*barriers, tmem slot*/ + 2 * 256 * sizeof(double) +
-                         (pl.v1 ? 0 : EPI_BYTES);
+                         (pl.v1 ? 0 : EPI_BYTES + 2048 /*s_part*/);
   // weight-resident mode: one N tile and the whole [taps*Cin x BN] weight tile (hi+lo) fits beside >= 3 A stages;
   // try the widest channel chunk first, then narrower ones (smaller A stages).
   static int allow_res = [] { const char* e = getenv("MPB200_TC_NO_BRES"); return (e && atoi(e)) ? 0 : 1; }();

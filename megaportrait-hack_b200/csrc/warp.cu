@@ -361,3 +361,125 @@ extern "C" int mp_warp_fused_cl(const float* v, const float* em_cl, const float*
   MP_LAUNCH_CHECK("mp_warp_fused_cl");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ workspace variants
+// NCDHW gathers with data-dependent (jittery or random) grids are bound by L1 wavefronts: every lane's 4-byte tap
+// sits in a different 32-byte sector, and the other 28 bytes of that sector belong to the SAME channel, which the
+// lane does not need.  In channels-last order one sector holds 8 channels of the tap, i.e. exactly what the other
+// lanes of the warp want.  So: (1) transpose the volume to channels-last into a caller-provided workspace
+// (coalesced on both sides), (2) gather 16-byte channel vectors from it -- contiguous across the lanes of a warp for
+// ANY grid -- and transpose each 32-voxel x C result tile back through shared memory so that the NCDHW stores are
+// 128-byte rows.  ncu (profiles/): 23 sectors per request for the direct kernel on the "spread" grid, 4 here.
+constexpr int GW_VOX = 32;
+constexpr int GW_THREADS = 256;
+
+template <int MODE>   // 0: explicit grid [N,So,3]; 1: warp field [N,3,Df,Hf,Wf] (apply_warping_field semantics)
+__global__ void __launch_bounds__(GW_THREADS)
+k_gather_cl_to_ncdhw(const float* __restrict__ vcl, const float* __restrict__ aux, float* __restrict__ out, int C, int D,
+                     int H, int W, int Do, int Ho, int Wo, int Df, int Hf, int Wf) {
+  extern __shared__ float s_tile[];               // [C][GW_VOX + 1]
+  __shared__ int s_off[GW_VOX][8];
+  __shared__ float s_w[GW_VOX][8];
+  const int n = blockIdx.y;
+  const int64_t So = (int64_t)Do * Ho * Wo;
+  const int64_t s0 = (int64_t)blockIdx.x * GW_VOX;
+  const int C4 = C >> 2;
+  if (threadIdx.x < GW_VOX) {
+    const int64_t s = s0 + threadIdx.x;
+    Taps t;
+    if (s < So) {
+      float ix, iy, iz;
+      if (MODE == 0) {
+        const float* g = aux + ((int64_t)n * So + s) * 3;
+        ix = unnormalize_clip(g[0], W); iy = unnormalize_clip(g[1], H); iz = unnormalize_clip(g[2], D);
+      } else {
+        const int w = (int)(s % Wo), h = (int)((s / Wo) % Ho), d = (int)(s / ((int64_t)Wo * Ho));
+        int d0, d1, h0, h1, w0, w1;
+        float ld, lh, lw;
+        src_ac_true(d, Df, D, d0, d1, ld);
+        src_ac_true(h, Hf, H, h0, h1, lh);
+        src_ac_true(w, Wf, W, w0, w1, lw);
+        const int64_t fs = (int64_t)Df * Hf * Wf;
+        const float* f = aux + (int64_t)n * 3 * fs;
+        const float fx = resample_flow(f, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+        const float fy = resample_flow(f + fs, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+        const float fz = resample_flow(f + 2 * fs, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+        ix = unnormalize_clip(2.0f * (linspace_m1_1(w, W) + fx) / (float)(W - 1) - 1.0f, W);
+        iy = unnormalize_clip(2.0f * (linspace_m1_1(h, H) + fy) / (float)(H - 1) - 1.0f, H);
+        iz = unnormalize_clip(2.0f * (linspace_m1_1(d, D) + fz) / (float)(D - 1) - 1.0f, D);
+      }
+      make_taps(ix, iy, iz, D, H, W, t);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { t.off[k] = -1; t.w[k] = 0.f; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_off[threadIdx.x][k] = t.off[k]; s_w[threadIdx.x][k] = t.w[k]; }
+  }
+  __syncthreads();
+  const float* vn = vcl + (int64_t)n * D * H * W * C;
+  for (int it = threadIdx.x; it < GW_VOX * C4; it += GW_THREADS) {
+    const int vox = it / C4, q = it % C4;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int off = s_off[vox][k];
+      if (off >= 0) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(vn + (int64_t)off * C + q * 4));
+        const float wk = s_w[vox][k];
+        r.x = fmaf(x.x, wk, r.x); r.y = fmaf(x.y, wk, r.y); r.z = fmaf(x.z, wk, r.z); r.w = fmaf(x.w, wk, r.w);
+      }
+    }
+    float* tp = s_tile + (q * 4) * (GW_VOX + 1) + vox;
+    tp[0] = r.x; tp[GW_VOX + 1] = r.y; tp[2 * (GW_VOX + 1)] = r.z; tp[3 * (GW_VOX + 1)] = r.w;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  if (s0 + lane < So)
+    for (int c = wrp; c < C; c += GW_THREADS / 32)
+      out[((int64_t)n * C + c) * So + s0 + lane] = s_tile[c * (GW_VOX + 1) + lane];
+}
+
+extern "C" size_t mp_gather_workspace_bytes(int N, int C, int D, int H, int W) {
+  return (C % 4 == 0 && C <= 512) ? (size_t)N * C * D * H * W * sizeof(float) : 0;
+}
+
+static int gather_ws_common(int mode, const float* v, const float* aux, float* out, void* ws, size_t ws_bytes, int N, int C,
+                            int D, int H, int W, int Do, int Ho, int Wo, int Df, int Hf, int Wf, void* stream) {
+  const size_t need = mp_gather_workspace_bytes(N, C, D, H, W);
+  MP_REQUIRE(need > 0, "mp_*_ws: C must be a multiple of 4 and <= 512 (use the direct entry point)");
+  MP_REQUIRE(ws && ws_bytes >= need, "mp_*_ws: workspace too small (%zu < %zu)", ws_bytes, need);
+  MP_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "mp_*_ws: workspace must be 16-byte aligned");
+  if (int e = mp_nchw_to_cl(v, (float*)ws, nullptr, nullptr, N, C, (int64_t)D * H * W, stream)) return e;
+  const int64_t So = (int64_t)Do * Ho * Wo;
+  dim3 grid((unsigned)((So + GW_VOX - 1) / GW_VOX), N);
+  const size_t smem = (size_t)C * (GW_VOX + 1) * sizeof(float);
+  if (mode == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_gather_cl_to_ncdhw<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_gather_cl_to_ncdhw<0><<<grid, GW_THREADS, smem, mp_stream(stream)>>>((const float*)ws, aux, out, C, D, H, W, Do, Ho,
+                                                                         Wo, 0, 0, 0);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_gather_cl_to_ncdhw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_gather_cl_to_ncdhw<1><<<grid, GW_THREADS, smem, mp_stream(stream)>>>((const float*)ws, aux, out, C, D, H, W, Do, Ho,
+                                                                         Wo, Df, Hf, Wf);
+  }
+  MP_LAUNCH_CHECK("mp_gather_ws");
+  return 0;
+}
+
+extern "C" int mp_grid_sample3d_ws(const float* v, const float* grid, float* out, void* workspace, size_t workspace_bytes,
+                                   int N, int C, int D, int H, int W, int Do, int Ho, int Wo, void* stream) {
+  MP_REQUIRE(v && grid && out, "mp_grid_sample3d_ws: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && C > 0 && D > 0 && H > 0 && W > 0 && Do > 0 && Ho > 0 && Wo > 0,
+             "mp_grid_sample3d_ws: bad dims");
+  return gather_ws_common(0, v, grid, out, workspace, workspace_bytes, N, C, D, H, W, Do, Ho, Wo, 0, 0, 0, stream);
+}
+
+extern "C" int mp_apply_warping_field_ws(const float* v, const float* warp_field, float* out, void* workspace,
+                                         size_t workspace_bytes, int N, int C, int D, int H, int W, int Df, int Hf, int Wf,
+                                         void* stream) {
+  MP_REQUIRE(v && warp_field && out, "mp_apply_warping_field_ws: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && C > 0 && D > 1 && H > 1 && W > 1 && Df > 0 && Hf > 0 && Wf > 0,
+             "mp_apply_warping_field_ws: bad dims");
+  return gather_ws_common(1, v, warp_field, out, workspace, workspace_bytes, N, C, D, H, W, D, H, W, Df, Hf, Wf, stream);
+}

@@ -9,7 +9,7 @@ import ctypes
 import glob
 import os
 import subprocess
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -81,6 +81,10 @@ _SIGNATURES = {
     "mp_conv_tc_supported": (c_int, [POINTER(ConvDesc)]),
     "mp_grid_sample3d": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_apply_warping_field": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_gather_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mp_grid_sample3d_ws": (c_int, [_P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_apply_warping_field_ws": (c_int, [_P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_int, _P]),
     "mp_warp_field": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "mp_warp_fused_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, _P]),

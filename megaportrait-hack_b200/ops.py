@@ -341,7 +341,7 @@ def global_avgpool(a: Act) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------- warping
-def grid_sample3d(v: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
+def grid_sample3d(v: torch.Tensor, grid: torch.Tensor, direct: bool = False) -> torch.Tensor:
     """F.grid_sample(v, grid, 'bilinear', 'border', align_corners=True) for NCDHW fp32 (model.py:1062)."""
     _chk_cuda(v, torch.float32, "grid_sample3d v")
     _chk_cuda(grid, torch.float32, "grid_sample3d grid")
@@ -351,12 +351,20 @@ def grid_sample3d(v: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("grid_sample3d: grid must be [N, Do, Ho, Wo, 3]")
     out = torch.empty((N, C, Do, Ho, Wo), dtype=torch.float32, device=v.device)
     L = _lib.load()
-    _lib.check(L.mp_grid_sample3d(_p(v), _p(grid), _p(out), N, C, D, H, W, Do, Ho, Wo, _stream()), "mp_grid_sample3d")
-    _count()
+    ws_bytes = L.mp_gather_workspace_bytes(N, C, D, H, W) if not direct else 0
+    if ws_bytes:
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=v.device)
+        with _Prof("grid_sample3d", 0, N * (C * D * H * W + C * Do * Ho * Wo + 3 * Do * Ho * Wo) * 4):
+            _lib.check(L.mp_grid_sample3d_ws(_p(v), _p(grid), _p(out), _p(ws), ws_bytes, N, C, D, H, W, Do, Ho, Wo,
+                                             _stream()), "mp_grid_sample3d_ws")
+        _count(2)
+    else:
+        _lib.check(L.mp_grid_sample3d(_p(v), _p(grid), _p(out), N, C, D, H, W, Do, Ho, Wo, _stream()), "mp_grid_sample3d")
+        _count()
     return out
 
 
-def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor) -> torch.Tensor:
+def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor, direct: bool = False) -> torch.Tensor:
     _chk_cuda(v, torch.float32, "apply_warping_field v")
     _chk_cuda(warp_field, torch.float32, "apply_warping_field warp_field")
     N, C, D, H, W = v.shape
@@ -365,9 +373,16 @@ def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor) -> torc
         raise RuntimeError("apply_warping_field: warp_field must be [N, 3, Df, Hf, Wf]")
     out = torch.empty_like(v)
     L = _lib.load()
-    _lib.check(L.mp_apply_warping_field(_p(v), _p(warp_field), _p(out), N, C, D, H, W, Df, Hf, Wf, _stream()),
-               "mp_apply_warping_field")
-    _count()
+    ws_bytes = L.mp_gather_workspace_bytes(N, C, D, H, W) if not direct else 0
+    if ws_bytes:
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=v.device)
+        _lib.check(L.mp_apply_warping_field_ws(_p(v), _p(warp_field), _p(out), _p(ws), ws_bytes, N, C, D, H, W, Df, Hf,
+                                               Wf, _stream()), "mp_apply_warping_field_ws")
+        _count(2)
+    else:
+        _lib.check(L.mp_apply_warping_field(_p(v), _p(warp_field), _p(out), N, C, D, H, W, Df, Hf, Wf, _stream()),
+                   "mp_apply_warping_field")
+        _count()
     return out
 
 

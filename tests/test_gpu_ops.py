@@ -196,11 +196,16 @@ def test_grid_sample3d(ops, kind):
     v = rnd(N, C, D, H, W, seed=2)
     grid = _grids(kind, N, D, H, W, 3 if kind == "spread" else 4)
     ref = F.grid_sample(v, grid, mode="bilinear", padding_mode="border", align_corners=True)
-    got = ops.grid_sample3d(v.to(DEV), grid.to(DEV)).cpu()
-    assert (got - ref).abs().max().item() <= 1e-5
+    for direct in (False, True):     # channels-last workspace path and the direct NCDHW kernel
+        got = ops.grid_sample3d(v.to(DEV), grid.to(DEV), direct=direct).cpu()
+        assert (got - ref).abs().max().item() <= 1e-5
 
 
 def test_grid_sample3d_different_output_size(ops):
+    v8 = rnd(2, 8, 7, 9, 11, seed=5)
+    grid8 = (torch.rand(2, 3, 5, 7, 3, generator=torch.Generator().manual_seed(6)) - 0.5) * 2.4   # ragged 105 voxels
+    ref8 = F.grid_sample(v8, grid8, mode="bilinear", padding_mode="border", align_corners=True)
+    assert (ops.grid_sample3d(v8.to(DEV), grid8.to(DEV)).cpu() - ref8).abs().max().item() <= 1e-5
     v = rnd(1, 5, 7, 9, 11, seed=5)
     grid = (torch.rand(1, 3, 4, 6, 3, generator=torch.Generator().manual_seed(6)) - 0.5) * 2.4
     ref = F.grid_sample(v, grid, mode="bilinear", padding_mode="border", align_corners=True)
@@ -214,8 +219,9 @@ def test_apply_warping_field_matches_oracle(ops, amp):
     v = torch.randn(2, 10, 16, 64, 64, generator=g)
     wf = (torch.rand(2, 3, 64, 64, 64, generator=g) - 0.3) * amp   # amp=40 leaves the degenerate corner regime
     ref = O.apply_warping_field(v, wf)
-    got = ops.apply_warping_field_ncdhw(v.to(DEV), wf.to(DEV)).cpu()
-    assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    for direct in (False, True):
+        got = ops.apply_warping_field_ncdhw(v.to(DEV), wf.to(DEV), direct=direct).cpu()
+        assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
 
 
 def _theta(N, seed, invert):

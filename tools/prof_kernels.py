@@ -106,9 +106,11 @@ def main():
                 gd = grid.to(DEV)
                 by = B * 51118080
                 best, avg = timeit(lambda: ops.grid_sample3d(v, gd), r)
+                bd, _ = timeit(lambda: ops.grid_sample3d(v, gd, direct=True), r)
                 tb, _ = timeit(lambda: F.grid_sample(v, gd, mode="bilinear", padding_mode="border", align_corners=True), r)
                 print(f"grid_sample3d_b{B}_{label:12s} best {best:8.3f} ms  algorithmic {by / best / 1e6:8.1f} GB/s   "
-                      f"(ATen kernel: {tb:8.3f} ms, {by / tb / 1e6:8.1f} GB/s)", flush=True)
+                      f"(direct NCDHW kernel {bd:8.3f} ms, {by / bd / 1e6:8.1f} GB/s; ATen kernel: {tb:8.3f} ms, "
+                      f"{by / tb / 1e6:8.1f} GB/s)", flush=True)
 
 
 if __name__ == "__main__":
