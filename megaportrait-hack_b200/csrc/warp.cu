@@ -378,17 +378,18 @@ __global__ void __launch_bounds__(GW_THREADS)
 k_gather_cl_to_ncdhw(const float* __restrict__ vcl, const float* __restrict__ aux, float* __restrict__ out, int C, int D,
                      int H, int W, int Do, int Ho, int Wo, int Df, int Hf, int Wf) {
   extern __shared__ float s_tile[];               // [C][GW_VOX + 1]
+  __shared__ float s_pix[GW_VOX][3];
   __shared__ int s_off[GW_VOX][8];
   __shared__ float s_w[GW_VOX][8];
   const int n = blockIdx.y;
   const int64_t So = (int64_t)Do * Ho * Wo;
   const int64_t s0 = (int64_t)blockIdx.x * GW_VOX;
   const int C4 = C >> 2;
+  // phase A1: one thread per voxel -> clamped pixel coordinates
   if (threadIdx.x < GW_VOX) {
     const int64_t s = s0 + threadIdx.x;
-    Taps t;
+    float ix = 0.f, iy = 0.f, iz = 0.f;
     if (s < So) {
-      float ix, iy, iz;
       if (MODE == 0) {
         const float* g = aux + ((int64_t)n * So + s) * 3;
         ix = unnormalize_clip(g[0], W); iy = unnormalize_clip(g[1], H); iz = unnormalize_clip(g[2], D);
@@ -408,15 +409,25 @@ k_gather_cl_to_ncdhw(const float* __restrict__ vcl, const float* __restrict__ au
         iy = unnormalize_clip(2.0f * (linspace_m1_1(h, H) + fy) / (float)(H - 1) - 1.0f, H);
         iz = unnormalize_clip(2.0f * (linspace_m1_1(d, D) + fz) / (float)(D - 1) - 1.0f, D);
       }
-      make_taps(ix, iy, iz, D, H, W, t);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { t.off[k] = -1; t.w[k] = 0.f; }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { s_off[threadIdx.x][k] = t.off[k]; s_w[threadIdx.x][k] = t.w[k]; }
+    s_pix[threadIdx.x][0] = ix; s_pix[threadIdx.x][1] = iy; s_pix[threadIdx.x][2] = iz;
   }
   __syncthreads();
+  // phase A2: one thread per (voxel, corner) -> offset + weight (same arithmetic as make_taps)
+  for (int i = threadIdx.x; i < GW_VOX * 8; i += GW_THREADS) {
+    const int vox = i >> 3, k = i & 7;
+    const float ix = s_pix[vox][0], iy = s_pix[vox][1], iz = s_pix[vox][2];
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const float tx = ix - fx, ty = iy - fy, tz = iz - fz;
+    const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+    const int x = (int)fx + dx, y = (int)fy + dy, z = (int)fz + dz;
+    const float w = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+    const bool ok = (s0 + vox < So) && x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D;
+    s_off[vox][k] = ok ? (z * H + y) * W + x : -1;
+    s_w[vox][k] = ok ? w : 0.f;
+  }
+  __syncthreads();
+  // phase B: gather 16-byte channel vectors (contiguous across lanes for any grid), transpose through shared memory
   const float* vn = vcl + (int64_t)n * D * H * W * C;
   for (int it = threadIdx.x; it < GW_VOX * C4; it += GW_THREADS) {
     const int vox = it / C4, q = it % C4;
@@ -434,10 +445,11 @@ k_gather_cl_to_ncdhw(const float* __restrict__ vcl, const float* __restrict__ au
     tp[0] = r.x; tp[GW_VOX + 1] = r.y; tp[2 * (GW_VOX + 1)] = r.z; tp[3 * (GW_VOX + 1)] = r.w;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  if (s0 + lane < So)
-    for (int c = wrp; c < C; c += GW_THREADS / 32)
-      out[((int64_t)n * C + c) * So + s0 + lane] = s_tile[c * (GW_VOX + 1) + lane];
+  // phase C: NCDHW stores, GW_VOX consecutive voxels (256 bytes) per channel row
+  for (int i = threadIdx.x; i < C * GW_VOX; i += GW_THREADS) {
+    const int c = i / GW_VOX, vox = i % GW_VOX;
+    if (s0 + vox < So) out[((int64_t)n * C + c) * So + s0 + vox] = s_tile[c * (GW_VOX + 1) + vox];
+  }
 }
 
 extern "C" size_t mp_gather_workspace_bytes(int N, int C, int D, int H, int W) {

@@ -40,6 +40,19 @@ class _Prof:
         return False
 
 
+def _profiled(fn):
+    """Bracket a wrapper with CUDA events while `PROFILE` is a list (per-launch dump of bench.py)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        if PROFILE is None:
+            return fn(*a, **k)
+        with _Prof(fn.__name__):
+            return fn(*a, **k)
+    return wrapper
+
+
 def _count(n: int = 1) -> None:
     global LAUNCHES
     LAUNCHES += n
@@ -102,6 +115,7 @@ def _alloc(shape, device, f32: bool, split: bool):
 
 
 # ----------------------------------------------------------------------------------------------------- layout
+@_profiled
 def from_nchw(x: torch.Tensor, f32: bool = False, split: bool = True) -> Act:
     """NCHW / NCDHW fp32 -> Act."""
     _chk_cuda(x, torch.float32, "from_nchw")
@@ -117,6 +131,7 @@ def from_nchw(x: torch.Tensor, f32: bool = False, split: bool = True) -> Act:
     return out
 
 
+@_profiled
 def to_nchw(a: Act, ndim: int = 5) -> torch.Tensor:
     N, D, H, W, C = a.shape
     out = torch.empty((N, C, D, H, W) if ndim == 5 else (N, C, H, W), dtype=torch.float32, device=a.device)
@@ -126,6 +141,7 @@ def to_nchw(a: Act, ndim: int = 5) -> torch.Tensor:
     return out
 
 
+@_profiled
 def ensure_split(a: Act) -> Act:
     if a.hi is None:
         a.hi = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
@@ -136,6 +152,7 @@ def ensure_split(a: Act) -> Act:
     return a
 
 
+@_profiled
 def avgpool2(a: Act, pool_d: int, f32: bool = True, split: bool = False) -> Act:
     N, D, H, W, C = a.shape
     out = _alloc((N, D // pool_d, H // 2, W // 2, C), a.device, f32, split)
@@ -146,6 +163,7 @@ def avgpool2(a: Act, pool_d: int, f32: bool = True, split: bool = False) -> Act:
     return out
 
 
+@_profiled
 def upsample2x_linear(a: Act, up_d: int, f32: bool = False, split: bool = True) -> Act:
     N, D, H, W, C = a.shape
     out = _alloc((N, D * up_d, H * 2, W * 2, C), a.device, f32, split)
@@ -156,6 +174,7 @@ def upsample2x_linear(a: Act, up_d: int, f32: bool = False, split: bool = True) 
     return out
 
 
+@_profiled
 def upsample_nearest(a: Act, scale: Sequence[int], f32: bool = False, split: bool = True) -> Act:
     N, D, H, W, C = a.shape
     sd, sh, sw = scale
@@ -172,6 +191,7 @@ def new_stats(N: int, G: int, device) -> torch.Tensor:
     return torch.zeros((N, G, 2), dtype=torch.float64, device=device)
 
 
+@_profiled
 def gn_stats(a: Act, G: int) -> torch.Tensor:
     st = new_stats(a.N, G, a.device)
     L = _lib.load()
@@ -180,6 +200,7 @@ def gn_stats(a: Act, G: int) -> torch.Tensor:
     return st
 
 
+@_profiled
 def gn_finalize(stats: torch.Tensor, a_shape, G: int, gamma=None, beta=None, gamma2=None, beta2=None,
                 eps: float = 1e-5) -> torch.Tensor:
     N, D, H, W, C = a_shape
@@ -191,6 +212,7 @@ def gn_finalize(stats: torch.Tensor, a_shape, G: int, gamma=None, beta=None, gam
     return ab
 
 
+@_profiled
 def affine_act(a: Act, ab: Optional[torch.Tensor], res: Optional[Act] = None, act: int = ACT_NONE, f32: bool = False,
                split: bool = True) -> Act:
     out = _alloc(a.shape, a.device, f32, split)
@@ -316,6 +338,7 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     return out, stats
 
 
+@_profiled
 def maxpool3x3s2(a: Act) -> Act:
     """nn.MaxPool2d(3, 2, 1) on a split 2-D activation."""
     N, D, H, W, C = a.shape
@@ -329,6 +352,7 @@ def maxpool3x3s2(a: Act) -> Act:
     return out
 
 
+@_profiled
 def global_avgpool(a: Act) -> torch.Tensor:
     """nn.AdaptiveAvgPool2d(1) + flatten: -> [N, C] fp32."""
     N, D, H, W, C = a.shape
@@ -424,6 +448,7 @@ def pack_tap_head(weight: torch.Tensor, device=None) -> PackedConv:
     return pack_conv(w, None, device or weight.device)
 
 
+@_profiled
 def tap_sum3x3(y: Act, bias: Optional[torch.Tensor], Co: int, act: int = ACT_NONE) -> torch.Tensor:
     """Second half of the tap-sum conv head: y CL fp32 [N,1,H,W,Ct] -> NCHW fp32 [N,Co,H,W]."""
     N, D, H, W, Ct = y.shape
@@ -434,6 +459,7 @@ def tap_sum3x3(y: Act, bias: Optional[torch.Tensor], Co: int, act: int = ACT_NON
     return out
 
 
+@_profiled
 def blur_subsample(x: torch.Tensor, kernel2d: torch.Tensor, step: int) -> torch.Tensor:
     _chk_cuda(x, torch.float32, "blur_subsample x")
     _chk_cuda(kernel2d, torch.float32, "blur_subsample kernel")
