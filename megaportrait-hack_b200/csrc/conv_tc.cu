@@ -53,6 +53,8 @@ struct TcParams {
   int tiles_n, total_tiles;   // persistent kernel: tile id = m_tile * tiles_n + n_tile (n fastest => A shared in L2)
   uint32_t epi_off;           // byte offset (from the aligned smem base) of the epilogue staging area
   int stride, in_c_off, out_C, out_c_off;   // ABI v2: H/W stride, channel windows (D/H/W below are OUTPUT dims)
+  int N, BNb;                 // batch size; samples per tile box (> 1 when one sample has fewer than 128 positions)
+  unsigned long long tap_mask;   // bit t set: filter tap t overlaps the input for at least one position (<= 64 taps)
   int dualb, acc_w;           // dual-B mode: D[:, 0:BN] += Al*Bh ; D[:, 0:2BN] += Ah*[Bh|Bl]; acc_w = TMEM columns per acc
   uint32_t idesc2;            // instruction descriptor with N = 2*BN
   int b_resident;             // 1: the whole weight tile [taps*Cin x BN] stays in smem for the CTA's lifetime
@@ -222,10 +224,10 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 // Called by all 256 epilogue threads; contains CTA-level named barriers.
 __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, long long* row_off, double* s_stats,
                                                uint32_t tmem_acc, int n0, int64_t obase, int half, int r, int et,
-                                               int lane) {
+                                               int lane, bool row_valid = true) {
   const bool vec4 = ((p.out_C | p.out_c_off | p.Cout) % 4) == 0, vec8 = ((p.out_C | p.out_c_off | p.Cout) % 8) == 0;
   const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
-  if (half == 0) row_off[r] = obase;
+  if (half == 0) row_off[r] = row_valid ? obase : -1;   // rows of samples beyond the batch are never stored
   for (int c0 = 0; c0 < p.BN; c0 += EPI_COLS) {
     const int co0 = n0 + c0;
     if (co0 >= p.Cout) break;              // padded output channels (uniform across the CTA)
@@ -242,7 +244,10 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += v2[i];
       }
-      if (fast) {
+      if (!row_valid) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      } else if (fast) {
         if (bias_vec) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -277,7 +282,8 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
           }
         }
       }
-      if (p.act == MP_ACT_RELU) {
+      if (!row_valid) {
+      } else if (p.act == MP_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
       } else if (p.act != MP_ACT_NONE) {
@@ -296,14 +302,14 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int row = j * 32 + (et >> 3), cq = (et & 7) * 4;
-          if (cq < ncol)
+          if (cq < ncol && row_off[row] >= 0)
             *reinterpret_cast<float4*>(p.out_f32 + row_off[row] + co0 + cq) =
                 *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + cq);
         }
       } else {
         for (int j = 0; j < 16; ++j) {
           const int row = j * 8 + (et >> 5);
-          if (lane < ncol) p.out_f32[row_off[row] + co0 + lane] = epi[row * EPI_PITCH + lane];
+          if (lane < ncol && row_off[row] >= 0) p.out_f32[row_off[row] + co0 + lane] = epi[row * EPI_PITCH + lane];
         }
       }
     }
@@ -312,7 +318,7 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int row = j * 64 + (et >> 2), c8 = (et & 3) * 8;
-          if (c8 < ncol) {
+          if (c8 < ncol && row_off[row] >= 0) {
             const float4 x0 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8);
             const float4 x1 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8 + 4);
             const int64_t o = row_off[row] + co0 + c8;
@@ -327,7 +333,7 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
       } else {
         for (int j = 0; j < 16; ++j) {
           const int row = j * 8 + (et >> 5);
-          if (lane < ncol) {
+          if (lane < ncol && row_off[row] >= 0) {
             const int64_t o = row_off[row] + co0 + lane;
             mp_split2(epi[row * EPI_PITCH + lane], p.out_hi[o], p.out_lo[o]);
           }
@@ -405,7 +411,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   auto tfull_bar = [&](int b) { return bars + (2 * p.STAGES + b) * 8; };
   auto tempty_bar = [&](int b) { return bars + (2 * p.STAGES + 2 + b) * 8; };
   const int taps = p.KD * p.KH * p.KW;
-  const int num_kb = taps * p.num_cchunks;
+  const int num_kb = __popcll(p.tap_mask) * p.num_cchunks;   // taps that are out of bounds everywhere are skipped
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.STAGES; ++s) {
@@ -441,7 +447,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     w0 = (t % p.tiles_w) * p.BW; t /= p.tiles_w;
     h0 = (t % p.tiles_h) * p.BH; t /= p.tiles_h;
     d0 = (t % p.tiles_d) * p.BD;
-    n = t / p.tiles_d;
+    n = (t / p.tiles_d) * p.BNb;           // first sample of the tile box
   };
 
   if (warp == 0) {
@@ -463,6 +469,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         int n, d0, h0, w0, n0;
         tile_coords(tile, n, d0, h0, w0, n0);
         for (int tap = 0; tap < taps; ++tap) {
+          if (!((p.tap_mask >> tap) & 1ull)) continue;
           const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
           for (int cc = 0; cc < p.num_cchunks; ++cc, ++kb) {
             const int s = kb % p.STAGES;
@@ -523,13 +530,16 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       int n, d0, h0, w0, n0;
       tile_coords(tile, n, d0, h0, w0, n0);
       const uint32_t b = it & 1;
-      const int ww = r % p.BW, hh = (r / p.BW) % p.BH, dd = r / (p.BW * p.BH);
-      const int64_t pos = (((int64_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
+      const int sbox = p.BW * p.BH * p.BD;
+      const int ni = r / sbox, rr = r - ni * sbox;
+      const int ww = rr % p.BW, hh = (rr / p.BW) % p.BH, dd = rr / (p.BW * p.BH);
+      const bool row_valid = n + ni < p.N;
+      const int64_t pos = (((int64_t)(n + ni) * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
       const int64_t obase = pos * p.out_C + p.out_c_off;
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       epilogue_drain(p, epi, row_off, s_stats, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.acc_w), n0,
-                     obase, half, r, et, lane);
+                     obase, half, r, et, lane, row_valid);
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -991,10 +1001,30 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.BW = pow2_le(Wo, TILE_M);
   p.BH = pow2_le(Ho, TILE_M / p.BW);
   p.BD = pow2_le(d->D, TILE_M / (p.BW * p.BH));
-  if (p.BW * p.BH * p.BD != TILE_M) return fail("fewer than 128 positions per sample box");
   if (Wo % p.BW || Ho % p.BH || d->D % p.BD) return fail("grid not divisible by the tile box");
   p.tiles_w = Wo / p.BW; p.tiles_h = Ho / p.BH; p.tiles_d = d->D / p.BD;
-  pl.tiles_m = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
+  p.N = d->N;
+  p.BNb = 1;
+  if (p.BW * p.BH * p.BD != TILE_M) {
+    // fewer than 128 positions per sample (FlowField tower, model.py:446-456): the tile box spans several samples
+    const int sbox = p.BW * p.BH * p.BD;
+    if (TILE_M % sbox || p.tiles_w * p.tiles_h * p.tiles_d != 1) return fail("sample grid is not a power-of-two box");
+    if (d->stats) return fail("fused GroupNorm statistics need >= 128 positions per sample");
+    if (use_v1()) return fail("v1 kernel has no batch-in-tile support");
+    p.BNb = TILE_M / sbox;
+  }
+  pl.tiles_m = ((d->N + p.BNb - 1) / p.BNb) * p.tiles_d * p.tiles_h * p.tiles_w;
+  p.tap_mask = 0;
+  {
+    const int pd = d->KD / 2, ph = d->KH / 2, pw = d->KW / 2;
+    for (int kd = 0; kd < d->KD; ++kd)
+      for (int kh = 0; kh < d->KH; ++kh)
+        for (int kw = 0; kw < d->KW; ++kw) {
+          const bool live = abs(kd - pd) < d->D && abs(kh - ph) < d->H && abs(kw - pw) < d->W;
+          if (live) p.tap_mask |= 1ull << ((kd * d->KH + kh) * d->KW + kw);
+        }
+  }
+  if (d->KD * d->KH * d->KW > 64) return fail("more than 64 filter taps");
   // N tile: largest multiple-of-16 divisor of Cout_pad up to the cap, shrunk while the grid under-fills the GPU
   static int bn_cap = [] { const char* e = getenv("MPB200_TC_BN_MAX"); int v = e ? atoi(e) : 256; return v < 16 ? 16 : (v > 256 ? 256 : v); }();
   const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
@@ -1065,7 +1095,9 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.b_resident = 0;
   const uint32_t ktot = (uint32_t)d->KD * d->KH * d->KW * d->Cin;
   const uint32_t bres_bytes = ktot * (uint32_t)p.BN * 4u;
-  if (!pl.v1 && allow_res && pl.tiles_n == 1 && pl.tiles_m >= 4 * 148 && bres_bytes < SMEM_LIMIT) {
+  const int ntaps = d->KD * d->KH * d->KW;
+  const bool all_taps = p.tap_mask == (ntaps == 64 ? ~0ull : ((1ull << ntaps) - 1ull));
+  if (!pl.v1 && allow_res && all_taps && pl.tiles_n == 1 && pl.tiles_m >= 4 * 148 && bres_bytes < SMEM_LIMIT) {
     for (int cc = p.CCHUNK; cc >= 16; cc /= 2) {
       const uint32_t a_stage = 2u * TILE_M * cc * 2u;
       if (fixed + bres_bytes + 3 * a_stage <= SMEM_LIMIT && bres_bytes < (1u << 20)) {
@@ -1114,7 +1146,8 @@ int encode_act_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const
   cuuint64_t strides[4] = {C * 2, C * 2 * d->W, C * 2 * d->W * d->H, C * 2 * d->W * d->H * d->D};
   // with elementStrides = s the box spans BW*s input elements and TMA keeps every s-th one (BW of them)
   cuuint32_t box[5] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BW * st,
-                       (cuuint32_t)(pl.slab ? pl.x.MT * pl.p.BH + 2 : pl.p.BH * st), (cuuint32_t)pl.p.BD, 1};
+                       (cuuint32_t)(pl.slab ? pl.x.MT * pl.p.BH + 2 : pl.p.BH * st), (cuuint32_t)pl.p.BD,
+                       (cuuint32_t)(pl.slab ? 1 : pl.p.BNb)};
   cuuint32_t estr[5] = {1, st, st, 1, 1};
   CUresult r = get_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

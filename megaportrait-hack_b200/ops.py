@@ -309,7 +309,10 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
         out = _alloc((N, D, Ho, Wo, pw.Cout), a.device, f32, split)
     elif out.shape[:4] != (N, D, Ho, Wo) or out_c_off + pw.Cout > out.shape[4]:
         raise RuntimeError(f"conv: output window does not fit {out.shape}")
-    stats = new_stats(N, stats_groups, a.device) if stats_groups else None
+    # the tensor-core kernel fuses GroupNorm statistics only when a sample has >= 128 output positions; the tiny
+    # FlowField volumes (4..32 positions per sample) get theirs from the stand-alone reduction instead
+    late_stats = bool(stats_groups) and (D * Ho * Wo < 128) and (out.f32 is not None)
+    stats = new_stats(N, stats_groups, a.device) if (stats_groups and not late_stats) else None
     d = ConvDesc()
     d.in_hi, d.in_lo, d.w_hi, d.w_lo, d.bias = _p(a.hi), _p(a.lo), _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias)
     if res is not None:
@@ -322,7 +325,7 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     d.out_f32, d.out_hi, d.out_lo, d.stats = _p(out.f32), _p(out.hi), _p(out.lo), _p(stats)
     d.N, d.D, d.H, d.W, d.Cin, d.Cout = N, D, H, W, pw.Cin, pw.Cout
     d.KD, d.KH, d.KW = pw.k
-    d.Cout_pad, d.gn_groups, d.act = pw.Cout_pad, stats_groups, act
+    d.Cout_pad, d.gn_groups, d.act = pw.Cout_pad, (0 if late_stats else stats_groups), act
     d.stride, d.in_c_off, d.in_C, d.out_c_off, d.out_C = stride, in_c_off, C, out_c_off, out.shape[4]
     L = _lib.load()
     mode = mode or _CONV_MODE

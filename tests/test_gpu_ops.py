@@ -106,8 +106,10 @@ CONV_CASES = [
     ("g3d_384",        1, 192, 384,  4,  16,  16, (3, 3, 3), True),
     ("g3d_768",        1, 384, 768,  2,  8,   8,  (3, 3, 3), True),
     ("g3d_sc_1x1",     1, 768, 384,  2,  8,   8,  (1, 1, 1), True),
-    ("flow_l1",        3, 512, 256,  4,  1,   1,  (3, 3, 3), False),
-    ("flow_l2",        3, 256, 128,  8,  2,   2,  (3, 3, 3), False),
+    ("flow_l1",        3, 512, 256,  4,  1,   1,  (3, 3, 3), True),    # 4 positions / sample: batch-in-tile box,
+    ("flow_l2",        3, 256, 128,  8,  2,   2,  (3, 3, 3), True),    # dead taps skipped, ragged last tile
+    ("flow_l1_b33",    33, 512, 256, 4,  1,   1,  (3, 3, 3), True),
+    ("flow_rc_1x1",    5, 512, 256,  4,  1,   1,  (1, 1, 1), True),
     ("flow_l4",        2, 64,  32,   16, 8,   8,  (3, 3, 3), True),
     ("flow_head",      2, 32,  3,    16, 16,  16, (3, 3, 3), True),
     # >= 592 M tiles and a single N tile: weight-resident mode of the persistent kernel
