@@ -338,6 +338,8 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
         else:
             _lib.check(L.mp_conv_simt(ctypes.byref(d), _stream()), "mp_conv_simt")
     _count()
+    if late_stats:
+        stats = gn_stats(out, stats_groups)
     return out, stats
 
 
