@@ -244,12 +244,21 @@ def run_b200(args):
         d["ms"] += a.elapsed_time(b); d["flops"] += fl; d["bytes"] += by; d["n"] += 1
     step_ms = ms / args.steps
     roof = None
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        t = tj.get("k_conv_tc2|32x1x64x64 512->512 k133 s1")
+        if t:
+            traffic = {"dram_bytes_per_launch": t["dram_bytes"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"],
+                       "launch": "G2d 512->512 3x3 @64x64 x32 (16 of the step's conv launches)", "source": t["source"]}
+    except Exception:
+        traffic = None
     if "conv_tc" in agg:
         c = agg["conv_tc"]
         ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, 3-pass split-bf16)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": None, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
+                "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "mma_passes": 3, "raw_tensor_frac": 3 * ach / pk["tf_sustained"], "launches": c["n"],
                 "avg_launch_ms": c["ms"] / c["n"], "share_of_step": c["ms"] / step_ms,
                 "algorithmic_gflop_per_launch": c["flops"] / c["n"] / 1e9}

@@ -1045,7 +1045,8 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + 2048 /*s_part*/ + EPI_BYTES;
     const int bn = d->Cout_pad;
     const uint32_t b_stage = 2u * bn * p.CCHUNK * 2u;
-    for (int mt = (d->H % 32 == 0 && 4 * bn <= 512) ? 2 : 1; mt >= 1 && !pl.slab; --mt) {
+    static int mt_cap = [] { const char* e = getenv("MPB200_TC_SLAB_MT"); return e ? atoi(e) : 2; }();
+    for (int mt = (d->H % 32 == 0 && 4 * bn <= 512 && mt_cap >= 2) ? 2 : 1; mt >= 1 && !pl.slab; --mt) {
       const uint32_t a_plane = (uint32_t)(mt * 16 + 2) * 8u * p.CCHUNK * 2u;
       for (int sa = 3; sa >= 2 && !pl.slab; --sa) {
         if (fixed_s + sa * 2 * a_plane + 3 * b_stage > SMEM_LIMIT) continue;

@@ -77,6 +77,12 @@ def main():
         conv_case("vol96_16x64x64_b1", 1, 96, 96, 16, 64, 64, (3, 3, 3), r, split_out=False, act=ops.ACT_NONE)
         conv_case("eapp_128_512x512_b1", 1, 128, 128, 1, 512, 512, (1, 3, 3), r, split_out=False, act=ops.ACT_NONE)
         conv_case("g3d_768_2x8x8_b1", 1, 768, 768, 2, 8, 8, (3, 3, 3), r, split_out=False, act=ops.ACT_NONE)
+    if sel("small"):
+        conv_case("g2d_128to64_512x512_b32", 32, 128, 64, 1, 512, 512, (1, 3, 3), r)
+        conv_case("g2d_64_512x512_b32", 32, 64, 64, 1, 512, 512, (1, 3, 3), r, split_out=False)
+        conv_case("g2d_up2_256to128_b32", 32, 256, 128, 1, 256, 256, (1, 3, 3), r)
+        conv_case("r18_64_256x256_b32", 32, 64, 64, 1, 256, 256, (1, 3, 3), r)
+        conv_case("vol96_16x64x64_b1", 1, 96, 96, 16, 64, 64, (3, 3, 3), r, split_out=False, act=ops.ACT_NONE)
     if sel("simt"):
         conv_case("g2d_512_64x64_b4", 4, 512, 512, 1, 64, 64, (1, 3, 3), r, mode="simt")
     if sel("warp"):
