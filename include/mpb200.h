@@ -40,6 +40,9 @@ int mp_nchw_to_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, i
 /* CL -> NCDHW fp32; source is in_f32 if non-NULL else the split pair. */
 int mp_cl_to_nchw(const float* in_f32, const void* in_hi, const void* in_lo, float* out, int N, int C, int64_t S,
                   void* stream);
+/* NCHW fp32 with C <= 16 channels (RGB frames) -> split CL [N,S,16], channel axis zero-padded to 16: the input of the
+ * tensor-core stems (nn.Conv2d(3, 64, ...), model.py:211; resnet.py:192; mysixdrepnet.py:1230). */
+int mp_nchw_to_cl_pad16(const float* in, void* out_hi, void* out_lo, int N, int C, int64_t S, void* stream);
 /* fp32 -> split planes, elementwise (n elements). */
 int mp_split(const float* in, void* out_hi, void* out_lo, int64_t n, void* stream);
 

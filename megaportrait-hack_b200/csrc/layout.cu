@@ -482,3 +482,36 @@ extern "C" int mp_tap_sum3x3_cl(const float* y, const float* bias, float* out, i
   MP_LAUNCH_CHECK("mp_tap_sum3x3_cl");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ RGB stem input
+// NCHW fp32 [N,C,S] (C <= 16, the RGB frames) -> split channels-last [N,S,16] with the channel axis zero-padded to 16:
+// the operand of the tensor-core stems (one thread per position, coalesced plane reads, two 32-byte row writes).
+struct __align__(16) bf16x8p {
+  bf16 v[8];
+};
+__global__ void k_nchw_to_cl_pad16(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo, int C,
+                                   int64_t S) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int n = blockIdx.y;
+  bf16x8p h[2], l[2];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const float v = c < C ? in[((int64_t)n * C + c) * S + s] : 0.f;
+    mp_split2(v, h[c >> 3].v[c & 7], l[c >> 3].v[c & 7]);
+  }
+  const int64_t o = ((int64_t)n * S + s) * 16;
+  *reinterpret_cast<bf16x8p*>(hi + o) = h[0];
+  *reinterpret_cast<bf16x8p*>(hi + o + 8) = h[1];
+  *reinterpret_cast<bf16x8p*>(lo + o) = l[0];
+  *reinterpret_cast<bf16x8p*>(lo + o + 8) = l[1];
+}
+
+extern "C" int mp_nchw_to_cl_pad16(const float* in, void* out_hi, void* out_lo, int N, int C, int64_t S, void* stream) {
+  MP_REQUIRE(in && out_hi && out_lo, "mp_nchw_to_cl_pad16: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && C > 0 && C <= 16 && S > 0, "mp_nchw_to_cl_pad16: bad dims");
+  dim3 grid((unsigned)((S + 255) / 256), N);
+  k_nchw_to_cl_pad16<<<grid, 256, 0, mp_stream(stream)>>>(in, (bf16*)out_hi, (bf16*)out_lo, C, S);
+  MP_LAUNCH_CHECK("mp_nchw_to_cl_pad16");
+  return 0;
+}

@@ -28,8 +28,7 @@ RGB_PAD = 16
 
 def rgb16(x: torch.Tensor) -> Act:
     """NCHW fp32 [N,3,H,W] -> split channels-last activation with the channel axis zero-padded to 16."""
-    xp = F.pad(x, (0, 0, 0, 0, 0, RGB_PAD - x.shape[1]))
-    return ops.from_nchw(xp.contiguous(), f32=False, split=True)
+    return ops.from_nchw_pad16(x.contiguous())
 
 
 def _bn(bn: nn.BatchNorm2d) -> dict:
@@ -49,6 +48,8 @@ class ResNetTrunkPlan:
 
     def __init__(self, conv1: nn.Conv2d, bn1: nn.BatchNorm2d, layers):
         self.stem = _pack_conv_bn(conv1, bn1, cin_pad=RGB_PAD)
+        self.stem_wb = ops.fold_bn(conv1.weight.detach(), None if conv1.bias is None else conv1.bias.detach(),
+                                   _bn(bn1), bn1.eps)
         self.stem_stride = conv1.stride[0]
         self.blocks: List[Tuple] = []
         for layer in layers:
@@ -79,6 +80,45 @@ class ResNetTrunkPlan:
 
     def pooled(self, x16: Act) -> torch.Tensor:
         return ops.global_avgpool(self.features(x16))
+
+
+class DualResNet18Plan:
+    """The two CIFAR-style ResNet-18 trunks of Emtn (head pose, expression) read the same frame: their stems run as ONE
+    3->128 convolution (+ one max-pool), and layer1 (64 channels each, no down-sampling) runs in lock-step on shared
+    128-channel tensors through channel windows, so the 512x512 input and the 128-channel stem output are touched
+    once instead of twice.  From layer2 on the two trunks are independent."""
+
+    def __init__(self, a: ResNetTrunkPlan, b: ResNetTrunkPlan):
+        self.a, self.b = a, b
+        (wa, ba), (wb, bb) = a.stem_wb, b.stem_wb
+        self.c = wa.shape[0]
+        self.stem = ops.pack_conv(torch.cat([wa, wb], 0), torch.cat([ba, bb], 0), wa.device, cin_pad=RGB_PAD)
+
+    def pooled(self, x16: Act):
+        c = self.c
+        h, _ = ops.conv(x16, self.stem, act=ACT_RELU, f32=False, split=True)
+        h = ops.maxpool3x3s2(h)
+        n_lock = 0
+        while (n_lock < len(self.a.blocks) and self.a.blocks[n_lock][1] is None and self.b.blocks[n_lock][1] is None
+               and self.a.blocks[n_lock][0][0][1] == 1):
+            out = ops._alloc(h.shape, h.device, False, True)
+            for j, pl in enumerate((self.a, self.b)):
+                convs, _ds = pl.blocks[n_lock]
+                t, _ = ops.conv(h, convs[0][0], act=ACT_RELU, f32=False, split=True, in_c_off=j * c)
+                ops.conv(t, convs[1][0], res=h, act=ACT_RELU, out=out, out_c_off=j * c)
+            h = out
+            n_lock += 1
+        feats = []
+        for j, pl in enumerate((self.a, self.b)):
+            g, off = h, j * c
+            for bi in range(n_lock, len(pl.blocks)):
+                convs, ds = pl.blocks[bi]
+                win = off if bi == n_lock else 0
+                idt = g if ds is None else ops.conv(g, ds[0], stride=ds[1], f32=True, in_c_off=win)[0]
+                t, _ = ops.conv(g, convs[0][0], stride=convs[0][1], act=ACT_RELU, f32=False, split=True, in_c_off=win)
+                g, _ = ops.conv(t, convs[1][0], res=idt, act=ACT_RELU, f32=False, split=True)
+            feats.append(ops.global_avgpool(g))
+        return feats
 
 
 class RepVGGPlan:
@@ -127,9 +167,9 @@ def emtn_plans(emtn):
     c = emtn.__dict__.get("_mp_cuda_plans")
     if c is None or c[0] != sig:
         with torch.no_grad():
-            c = (sig, (ResNetTrunkPlan(hp.conv1, hp.bn1, [hp.layer1, hp.layer2, hp.layer3, hp.layer4]),
-                       ResNetTrunkPlan(ex[0], ex[1], [ex[4], ex[5], ex[6], ex[7]]),
-                       RepVGGPlan(rot)))
+            pa = ResNetTrunkPlan(hp.conv1, hp.bn1, [hp.layer1, hp.layer2, hp.layer3, hp.layer4])
+            pb = ResNetTrunkPlan(ex[0], ex[1], [ex[4], ex[5], ex[6], ex[7]])
+            c = (sig, (DualResNet18Plan(pa, pb), RepVGGPlan(rot)))
         emtn.__dict__["_mp_cuda_plans"] = c
     return c[1]
 
@@ -137,15 +177,16 @@ def emtn_plans(emtn):
 def emtn_forward(emtn, x: torch.Tensor):
     """Emtn.forward (model.py:888-907) on libmpb200 kernels: -> (Euler degrees [B,3], translation [B,3], z [B,512])."""
     from .emtn import ortho6d_to_euler_deg
-    hp_plan, ex_plan, rot_plan = emtn_plans(emtn)
+    dual_plan, rot_plan = emtn_plans(emtn)
     x16 = rgb16(x.float())
     rot = emtn.rotation_net.model
     x6 = F.linear(rot_plan.pooled(x16), rot.linear_reg.weight, rot.linear_reg.bias)
     rotations = ortho6d_to_euler_deg(x6[:, :6])
-    head_pose = F.linear(hp_plan.pooled(x16), emtn.head_pose_net.fc.weight, emtn.head_pose_net.fc.bias)
+    f_hp, f_ex = dual_plan.pooled(x16)
+    head_pose = F.linear(f_hp, emtn.head_pose_net.fc.weight, emtn.head_pose_net.fc.bias)
     translation = head_pose[:, 3:]
     # AdaptiveAvgPool2d(1) then AdaptiveAvgPool2d((2,2)) (model.py:880-881): every channel replicated 2x2, NCHW flatten
-    feat = ex_plan.pooled(x16).repeat_interleave(4, dim=1)
+    feat = f_ex.repeat_interleave(4, dim=1)
     expression = F.linear(feat, emtn.fc.weight, emtn.fc.bias)
     return rotations, translation, expression
 

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "mp_device_supported": (c_int, []),
     "mp_nchw_to_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int64, _P]),
     "mp_cl_to_nchw": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int64, _P]),
+    "mp_nchw_to_cl_pad16": (c_int, [_P, _P, _P, c_int, c_int, c_int64, _P]),
     "mp_split": (c_int, [_P, _P, _P, c_int64, _P]),
     "mp_avgpool2_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_upsample2x_linear_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

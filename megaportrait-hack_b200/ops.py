@@ -132,6 +132,18 @@ def from_nchw(x: torch.Tensor, f32: bool = False, split: bool = True) -> Act:
 
 
 @_profiled
+def from_nchw_pad16(x: torch.Tensor) -> Act:
+    """NCHW fp32 [N,C<=16,H,W] -> split channels-last activation with 16 (zero-padded) channels."""
+    _chk_cuda(x, torch.float32, "from_nchw_pad16")
+    N, C, H, W = x.shape
+    out = _alloc((N, 1, H, W, 16), x.device, False, True)
+    L = _lib.load()
+    _lib.check(L.mp_nchw_to_cl_pad16(_p(x), _p(out.hi), _p(out.lo), N, C, H * W, _stream()), "mp_nchw_to_cl_pad16")
+    _count()
+    return out
+
+
+@_profiled
 def to_nchw(a: Act, ndim: int = 5) -> torch.Tensor:
     N, D, H, W, C = a.shape
     out = torch.empty((N, C, D, H, W) if ndim == 5 else (N, C, H, W), dtype=torch.float32, device=a.device)
@@ -302,7 +314,7 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     if a.hi is None:
         ensure_split(a)
     N, D, H, W, C = a.shape
-    if in_c_off + pw.Cin > C or (in_c_off == 0 and out is None and C != pw.Cin):
+    if in_c_off + pw.Cin > C:
         raise RuntimeError(f"conv: activation has {C} channels, weights expect {pw.Cin} (+{in_c_off})")
     Ho, Wo = H // stride, W // stride
     if out is None:

@@ -60,6 +60,10 @@ def from_nchw(x, f32=False, split=True):
     return _mk(_to_cl(x), f32, split)
 
 
+def from_nchw_pad16(x):
+    return from_nchw(F.pad(x, (0, 0, 0, 0, 0, 16 - x.shape[1])), False, True)
+
+
 def to_nchw(a, ndim=5):
     y = _to_ncdhw(_val(a))
     return y if ndim == 5 else y.squeeze(2)
@@ -227,7 +231,7 @@ def blur_subsample(x, kernel2d, step):
 
 _NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
-          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3"]
+          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3", "from_nchw_pad16"]
 
 
 @contextlib.contextmanager

@@ -366,3 +366,13 @@ def test_tap_sum_head_matches_conv3x3(ops):
     got = ops.tap_sum3x3(y, b.to(DEV), Co, ops.ACT_SIGMOID).cpu()
     assert got.shape == ref.shape
     assert (got - ref).abs().max().item() < 2e-5
+
+
+def test_rgb_pad16_layout(ops):
+    x = rnd(3, 3, 40, 24, seed=61)
+    a = ops.from_nchw_pad16(x.to(DEV))
+    assert a.shape == (3, 1, 40, 24, 16)
+    v = (a.hi.float() + a.lo.float()).cpu()
+    assert torch.equal(a.hi.float().cpu()[..., :3], x.permute(0, 2, 3, 1).unsqueeze(1).to(torch.bfloat16).float())
+    assert (v[..., :3] - x.permute(0, 2, 3, 1).unsqueeze(1)).abs().max().item() <= 2.0 ** -16 * x.abs().max().item()
+    assert (v[..., 3:] == 0).all()
