@@ -525,12 +525,15 @@ def compute_rotation_matrix(rotation):
 def _affine_3x4(rotation, translation, invert: bool) -> torch.Tensor:
     """First three rows of [R|t] or of its inverse (model.py:790-803) as a contiguous [B,3,4] fp32 tensor."""
     B = rotation.shape[0]
-    A = torch.eye(4, device=rotation.device, dtype=torch.float32).repeat(B, 1, 1)
-    A[:, :3, :3] = compute_rotation_matrix(rotation.float())
-    A[:, :3, 3] = translation.float()
+    R = compute_rotation_matrix(rotation.float())
+    t = translation.float().unsqueeze(-1)
     if invert:
-        A = torch.inverse(A)
-    return A[:, :3].contiguous()
+        # inverse of the rigid transform [R|t; 0 0 0 1] in closed form ([R^T | -R^T t]); the reference calls
+        # torch.inverse on the same matrix (model.py:803) -- identical up to fp32 rounding, but free of the host
+        # synchronisation of the LU path, so the step can be captured in a CUDA graph
+        Rt = R.transpose(1, 2)
+        return torch.cat((Rt, -torch.matmul(Rt, t)), dim=2).contiguous()
+    return torch.cat((R, t), dim=2).contiguous()
 
 
 def compute_rt_warp(rotation, translation, invert=False, grid_size=64):

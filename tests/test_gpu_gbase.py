@@ -157,3 +157,20 @@ def test_no_cpu_fallback(gbase):
     from megaportrait_hack_b200 import model
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model.G2d(96).eval()(torch.zeros(1, 96, 64, 64))
+
+
+def test_cuda_graph_engine_matches_eager(gbase):
+    """engine.GraphedGbase replays encode_source / drive from CUDA graphs: same numbers as the eager calls."""
+    from megaportrait_hack_b200.engine import GraphedGbase
+    xs, xd = synthetic_pair(2)
+    eager, pyr_e = gbase.drive(gbase.encode_source(xs.cuda()), xd.cuda())
+    eng = GraphedGbase(gbase, 2, "cuda")
+    for _ in range(2):      # second replay: static buffers are reused correctly
+        out, pyr = eng.step(xs.cuda(), xd.cuda())
+        torch.cuda.synchronize()
+        assert (out - eager).abs().max().item() <= 1e-6
+        assert (pyr["prediction_0.5"] - pyr_e["prediction_0.5"]).abs().max().item() <= 1e-6
+    xd2 = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(9))
+    out2, _ = eng.step(xs.cuda(), xd2.cuda())
+    ref2, _ = gbase.drive(gbase.encode_source(xs.cuda()), xd2.cuda())
+    assert (out2 - ref2).abs().max().item() <= 1e-6
