@@ -1044,38 +1044,66 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
       d->Cout_pad <= 128 && d->W % 8 == 0 && d->H % 16 == 0) {
     const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + 2048 /*s_part*/ + EPI_BYTES;
     const int bn = d->Cout_pad;
-    const uint32_t b_stage = 2u * bn * p.CCHUNK * 2u;
     static int mt_cap = [] { const char* e = getenv("MPB200_TC_SLAB_MT"); return e ? atoi(e) : 2; }();
-    for (int mt = (d->H % 32 == 0 && 4 * bn <= 512 && mt_cap >= 2) ? 2 : 1; mt >= 1 && !pl.slab; --mt) {
-      const uint32_t a_plane = (uint32_t)(mt * 16 + 2) * 8u * p.CCHUNK * 2u;
-      for (int sa = 3; sa >= 2 && !pl.slab; --sa) {
-        if (fixed_s + sa * 2 * a_plane + 3 * b_stage > SMEM_LIMIT) continue;
-        int sb = (int)((SMEM_LIMIT - fixed_s - sa * 2 * a_plane) / b_stage);
-        if (sb > 8) sb = 8;
-        pl.slab = true;
-        pl.x.MT = mt; pl.x.SA = sa; pl.x.SB = sb;
-        pl.x.a_plane_bytes = a_plane;
-        pl.x.b_ring_off = sa * 2 * a_plane;
-        p.BN = bn;
-        pl.tiles_n = 1;
-        p.BW = 8; p.BH = 16; p.BD = 1;
-        p.tiles_w = d->W / 8; p.tiles_h = d->H / (16 * mt); p.tiles_d = d->D;
-        pl.tiles_m = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
-        p.a_bytes = a_plane;
-        p.b_bytes = (uint32_t)bn * p.CCHUNK * 2u;
-        p.stage_bytes = 0;
-        p.STAGES = sa;
-        p.b_resident = 0;
-        p.bres_off = 0;
-        p.epi_off = pl.x.b_ring_off + sb * b_stage;
-        pl.smem_bytes = fixed_s + p.epi_off;
-        p.dualb = (allow_dual() && 2 * mt * 2 * bn <= 512) ? 1 : 0;
-        p.acc_w = p.dualb ? 2 * bn : bn;
-        p.tmem_cols = next_pow2(2 * mt * p.acc_w);
-        p.tiles_n = 1;
-        p.total_tiles = pl.tiles_m;
+    static int cc_force = [] { const char* e = getenv("MPB200_TC_SLAB_CC"); return e ? atoi(e) : 0; }();
+    static int sb_want = [] { const char* e = getenv("MPB200_TC_SLAB_SB"); int v = e ? atoi(e) : 3; return v < 2 ? 2 : v; }();
+    // The weight ring must be deep enough to cover the TMA latency (a B tile feeds only MT*CCHUNK/16*2 MMAs):
+    // prefer the widest channel chunk that still leaves >= sb_want weight stages, else the deepest ring found.
+    // Measured on B200 (profiles/): the widest channel chunk wins (64-byte TMA rows and twice the barrier traffic cost
+    // more than a deeper weight ring buys), two accumulators per weight tile win over one; so: widest chunk first,
+    // then MT = 2 before MT = 1, then the deepest A ring that leaves >= sb_want weight stages.
+    auto choose = [&](int mt_first) -> bool {
+      int best_cc = 0, best_sa = 0, best_sb = 0, best_mt = 0;
+      for (int cc = (cc_force ? cc_force : p.CCHUNK); cc >= 16 && !best_cc; cc = (cc_force ? 0 : cc / 2)) {
+        if (d->Cin % cc) continue;
+        for (int mt_try = mt_first; mt_try >= 1 && !best_cc; --mt_try) {
+          const uint32_t b_stage = 2u * bn * cc * 2u;
+          const uint32_t a_plane = (uint32_t)(mt_try * 16 + 2) * 8u * cc * 2u;
+          for (int sa = 3; sa >= 2; --sa) {
+            if (fixed_s + sa * 2 * a_plane + sb_want * b_stage > SMEM_LIMIT) continue;
+            int sb = (int)((SMEM_LIMIT - fixed_s - sa * 2 * a_plane) / b_stage);
+            if (sb > 12) sb = 12;
+            best_sb = sb; best_cc = cc; best_sa = sa; best_mt = mt_try;
+            break;
+          }
+        }
       }
-    }
+      const int mt = best_mt;
+      if (!best_cc) return false;
+      const int cc = best_cc, sa = best_sa, sb = best_sb;
+      const uint32_t b_stage = 2u * bn * cc * 2u;
+      const uint32_t a_plane = (uint32_t)(mt * 16 + 2) * 8u * cc * 2u;
+      pl.slab = true;
+      pl.x.MT = mt; pl.x.SA = sa; pl.x.SB = sb;
+      pl.x.a_plane_bytes = a_plane;
+      pl.x.b_ring_off = sa * 2 * a_plane;
+      p.CCHUNK = cc;
+      p.layout_type = cc == 64 ? 2u : cc == 32 ? 4u : 6u;
+      pl.swz = cc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : cc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+      p.sbo = 8u * cc * 2u;
+      p.num_cchunks = d->Cin / cc;
+      p.BN = bn;
+      pl.tiles_n = 1;
+      p.BW = 8; p.BH = 16; p.BD = 1; p.BNb = 1;
+      p.tiles_w = d->W / 8; p.tiles_h = d->H / (16 * mt); p.tiles_d = d->D;
+      pl.tiles_m = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
+      p.a_bytes = a_plane;
+      p.b_bytes = (uint32_t)bn * cc * 2u;
+      p.stage_bytes = 0;
+      p.STAGES = sa;
+      p.b_resident = 0;
+      p.bres_off = 0;
+      p.epi_off = pl.x.b_ring_off + sb * b_stage;
+      pl.smem_bytes = fixed_s + p.epi_off;
+      p.dualb = (allow_dual() && 2 * mt * 2 * bn <= 512) ? 1 : 0;
+      p.acc_w = p.dualb ? 2 * bn : bn;
+      p.tmem_cols = next_pow2(2 * mt * p.acc_w);
+      p.tiles_n = 1;
+      p.total_tiles = pl.tiles_m;
+      return true;
+    };
+    const bool mt2_ok = d->H % 32 == 0 && mt_cap >= 2 && 2 * 2 * bn <= 512;
+    choose(mt2_ok ? 2 : 1);
   }
   if (pl.slab) {
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
