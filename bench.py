@@ -177,7 +177,7 @@ def run_b200(args):
     if not args.no_graphs:
         try:
             graphed = GraphedGbase(G, B, dev)
-            graph_note = "on: encode_source and drive each replayed from a CUDA graph"
+            graph_note = "on: {encode_source || motion encoder} and render replayed from two CUDA graphs"
         except Exception as e:   # capture is an optimisation; the eager path is the same kernels
             graphed, graph_note = None, f"off (capture failed: {type(e).__name__}: {str(e)[:120]})"
             torch.cuda.synchronize()

@@ -77,12 +77,15 @@ class ShardedGbase:
 
 
 class GraphedGbase:
-    """`ShardedGbase.step` with the two halves captured in CUDA graphs (fixed shapes: one 512x512 source, `n_drivers`
-    driver frames per rank).  A step launches ~470 kernels whose host-side enqueue costs about as much as their GPU
-    time; replaying two graphs removes that cost.  Inputs are copied into static buffers, outputs are static tensors
-    that the next `step` overwrites.  The broadcast between the two graphs stays an eager NCCL call."""
+    """`ShardedGbase.step` replayed from CUDA graphs (fixed shapes: one 512x512 source, `n_drivers` driver frames per
+    rank).  A step launches ~470 kernels whose host-side enqueue costs about as much as their GPU time; replaying
+    graphs removes that cost.  Graph 1 runs the source encode (source rank only; batch 1, many small kernels) on a
+    forked stream CONCURRENTLY with the motion encoder of the driver frames (independent of the source); the broadcast
+    of the packed source state stays an eager NCCL call; graph 2 renders.  Inputs are copied into static buffers,
+    outputs are static tensors that the next `step` overwrites."""
 
-    def __init__(self, gbase, n_drivers: int, device, group=None, src_rank: int = 0, warmup: int = 2):
+    def __init__(self, gbase, n_drivers: int, device, group=None, src_rank: int = 0, warmup: int = 2,
+                 overlap: bool = True):
         self.sh = ShardedGbase(gbase, group=group, src_rank=src_rank)
         self.G = gbase
         dev = torch.device(device)
@@ -97,22 +100,30 @@ class GraphedGbase:
             for _ in range(warmup):     # plans packed, TMA encoder resolved, cuBLAS / allocator warm
                 src = gbase.encode_source(self.xs)
                 pack_source(src, self.flat)
-                gbase.drive(unpack_source(self.flat), self.xd)
+                gbase.drive_render(unpack_source(self.flat), gbase.drive_motion(self.xd))
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.g_enc = None
         l0 = ops.LAUNCHES
-        if self.is_src:
-            self.g_enc = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_enc), torch.no_grad():
-                src = gbase.encode_source(self.xs)
-                pack_source(src, self.flat)
-        self.enc_launches = ops.LAUNCHES - l0
+        self.g_pre = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_pre), torch.no_grad():
+            main = torch.cuda.current_stream(dev)
+            if self.is_src and overlap:
+                fork = torch.cuda.Stream(dev)
+                fork.wait_stream(main)
+                with torch.cuda.stream(fork):
+                    pack_source(gbase.encode_source(self.xs), self.flat)
+                self.motion = gbase.drive_motion(self.xd)
+                main.wait_stream(fork)
+            else:
+                if self.is_src:
+                    pack_source(gbase.encode_source(self.xs), self.flat)
+                self.motion = gbase.drive_motion(self.xd)
+        self.pre_launches = ops.LAUNCHES - l0
         l0 = ops.LAUNCHES
-        self.g_drv = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_drv), torch.no_grad():
-            self.out = gbase.drive(unpack_source(self.flat), self.xd)
-        self.drv_launches = ops.LAUNCHES - l0
+        self.g_render = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_render), torch.no_grad():
+            self.out = gbase.drive_render(unpack_source(self.flat), self.motion)
+        self.render_launches = ops.LAUNCHES - l0
 
     @torch.no_grad()
     def step(self, xs: torch.Tensor, xd_local: torch.Tensor):
@@ -120,10 +131,10 @@ class GraphedGbase:
         self.xd.copy_(xd_local, non_blocking=True)
         if self.is_src:
             self.xs.copy_(xs, non_blocking=True)
-            self.g_enc.replay()
-            ops._count(self.enc_launches)
+        self.g_pre.replay()
+        ops._count(self.pre_launches)
         if self.sh.world > 1:
             self.sh.dist.broadcast(self.flat, self.sh.src_rank, group=self.sh.group)
-        self.g_drv.replay()
-        ops._count(self.drv_launches)
+        self.g_render.replay()
+        ops._count(self.render_launches)
         return self.out

@@ -680,16 +680,21 @@ class Gbase(nn.Module):
         return src
 
     @torch.no_grad()
-    def drive(self, src: Dict[str, object], xd, keep_stages: bool = False):
-        """Per-driver half (model.py:1145, 1163-1180).  `src["vc2d"]` may hold 1 sample (shared source) or len(xd)."""
+    def drive_motion(self, xd):
+        """Driver-only part of the per-driver half (model.py:1145): Emtn(xd) -> (Rd, td, zd).  Independent of the
+        source, so it can run concurrently with `encode_source` (engine.GraphedGbase does)."""
         _require_inference(self, xd)
-        xd = _as_f32_cuda(xd)
-        n = xd.shape[0]
+        return self._emtn(_as_f32_cuda(xd))
+
+    @torch.no_grad()
+    def drive_render(self, src: Dict[str, object], motion, keep_stages: bool = False):
+        """C2D warp generator, fused warp + depth sum, G2d, pyramid (model.py:1163-1180)."""
+        Rd, td, zd = motion
+        n = zd.shape[0]
         es = src["es"]
         if es.shape[0] != n:
             assert es.shape[0] == 1, f"source batch {es.shape[0]} does not match driver batch {n}"
             es = es.expand(n, -1)
-        Rd, td, zd = self._emtn(xd)
         em, theta = self.warp_generator_c2d._em_theta(Rd, td, zd, es)
         proj = ops.warp_fused(src["vc2d"], em, theta, sum_d=True, f32=keep_stages, split=True)
         assert proj.shape[1:] == (1, 64, 64, 96), f"Expected vc2d_warped shape (_, 96, 16, 64, 64), got {proj.shape}"
@@ -698,6 +703,11 @@ class Gbase(nn.Module):
         if keep_stages:
             return xhat, pyramids, dict(Rd=Rd, td=td, zd=zd, em_c2d=em, theta_c2d=theta, projected=proj)
         return xhat, pyramids
+
+    @torch.no_grad()
+    def drive(self, src: Dict[str, object], xd, keep_stages: bool = False):
+        """Per-driver half (model.py:1145, 1163-1180).  `src["vc2d"]` may hold 1 sample (shared source) or len(xd)."""
+        return self.drive_render(src, self.drive_motion(xd), keep_stages)
 
     def forward(self, xs, xd):
         assert xs.shape[0] == xd.shape[0], f"Expected zs and es to have the same shape (Bs == Bd), got {xs.shape[0]} and {xd.shape[0]}"
