@@ -235,43 +235,42 @@ __global__ void k_upsample2x_linear_cl(const float* __restrict__ in_f32, const b
 struct __align__(16) bf16x8v {
   bf16 v[8];
 };
-__global__ void k_upsample2x_bilinear_split8(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
-                                             bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int N, int H, int W,
-                                             int C) {
+__global__ void __launch_bounds__(256)
+k_upsample2x_bilinear_split8(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
+                             bf16* __restrict__ out_lo, int H, int W, int C) {
+  // grid: x = chunks of (wo, c8) pairs of one output row, y = output row, z = sample  (no 64-bit divisions)
   const int C8 = C >> 3;
   const int Ho = H * 2, Wo = W * 2;
-  int64_t total = (int64_t)N * Ho * Wo * C8;
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  int c8 = (int)(t % C8);
-  int64_t p = t / C8;
-  int wo = (int)(p % Wo); p /= Wo;
-  int ho = (int)(p % Ho);
-  int n = (int)(p / Ho);
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= Wo * C8) return;
+  const int wo = idx / C8, c8 = idx - wo * C8;
+  const int ho = blockIdx.y, n = blockIdx.z;
   int h0, h1, w0, w1;
   float lh, lw;
   lin_src(ho, H, Ho, h0, h1, lh);
   lin_src(wo, W, Wo, w0, w1, lw);
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll
-  for (int b = 0; b < 2; ++b) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const float wgt = (b ? lh : 1.f - lh) * (c ? lw : 1.f - lw);
-      const int64_t idx = (((int64_t)n * H + (b ? h1 : h0)) * W + (c ? w1 : w0)) * C + c8 * 8;
-      const bf16x8v h = *reinterpret_cast<const bf16x8v*>(in_hi + idx);
-      const bf16x8v l = *reinterpret_cast<const bf16x8v*>(in_lo + idx);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += wgt * mp_join(h.v[i], l.v[i]);
-    }
-  }
+  const int64_t row0 = ((int64_t)n * H + h0) * W, row1 = ((int64_t)n * H + h1) * W;
+  const int64_t i00 = (row0 + w0) * C + c8 * 8, i01 = (row0 + w1) * C + c8 * 8;
+  const int64_t i10 = (row1 + w0) * C + c8 * 8, i11 = (row1 + w1) * C + c8 * 8;
+  // all eight 16-byte loads are issued before the first use
+  const bf16x8v h00 = *reinterpret_cast<const bf16x8v*>(in_hi + i00), l00 = *reinterpret_cast<const bf16x8v*>(in_lo + i00);
+  const bf16x8v h01 = *reinterpret_cast<const bf16x8v*>(in_hi + i01), l01 = *reinterpret_cast<const bf16x8v*>(in_lo + i01);
+  const bf16x8v h10 = *reinterpret_cast<const bf16x8v*>(in_hi + i10), l10 = *reinterpret_cast<const bf16x8v*>(in_lo + i10);
+  const bf16x8v h11 = *reinterpret_cast<const bf16x8v*>(in_hi + i11), l11 = *reinterpret_cast<const bf16x8v*>(in_lo + i11);
+  const float w00 = (1.f - lh) * (1.f - lw), w01 = (1.f - lh) * lw, w10 = lh * (1.f - lw), w11 = lh * lw;
   bf16x8v oh, ol;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) mp_split2(acc[i], oh.v[i], ol.v[i]);
-  *reinterpret_cast<bf16x8v*>(out_hi + t * 8) = oh;
-  *reinterpret_cast<bf16x8v*>(out_lo + t * 8) = ol;
+  for (int i = 0; i < 8; ++i) {
+    // same accumulation order as the generic kernel: taps (h0,w0), (h0,w1), (h1,w0), (h1,w1)
+    float acc = w00 * mp_join(h00.v[i], l00.v[i]);
+    acc += w01 * mp_join(h01.v[i], l01.v[i]);
+    acc += w10 * mp_join(h10.v[i], l10.v[i]);
+    acc += w11 * mp_join(h11.v[i], l11.v[i]);
+    mp_split2(acc, oh.v[i], ol.v[i]);
+  }
+  const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C8 + c8) * 8;
+  *reinterpret_cast<bf16x8v*>(out_hi + o) = oh;
+  *reinterpret_cast<bf16x8v*>(out_lo + o) = ol;
 }
 
 extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out_f32,
@@ -279,10 +278,10 @@ extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, c
                                        void* stream) {
   MP_REQUIRE((in_f32 || (in_hi && in_lo)) && (out_f32 || (out_hi && out_lo)), "mp_upsample2x_linear_cl: null pointer");
   MP_REQUIRE(C % 4 == 0 && (up_d == 1 || up_d == 2), "mp_upsample2x_linear_cl: bad dims");
-  if (!in_f32 && !out_f32 && D == 1 && up_d == 1 && C % 8 == 0) {
-    int64_t total8 = (int64_t)N * H * 2 * W * 2 * (C / 8);
-    k_upsample2x_bilinear_split8<<<(unsigned)((total8 + 255) / 256), 256, 0, mp_stream(stream)>>>(
-        (const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi, (bf16*)out_lo, N, H, W, C);
+  if (!in_f32 && !out_f32 && D == 1 && up_d == 1 && C % 8 == 0 && H * 2 <= 65535 && N <= 65535) {
+    dim3 g8((unsigned)((W * 2 * (C / 8) + 255) / 256), (unsigned)(H * 2), (unsigned)N);
+    k_upsample2x_bilinear_split8<<<g8, 256, 0, mp_stream(stream)>>>((const bf16*)in_hi, (const bf16*)in_lo,
+                                                                     (bf16*)out_hi, (bf16*)out_lo, H, W, C);
     MP_LAUNCH_CHECK("mp_upsample2x_linear_cl");
     return 0;
   }
@@ -370,38 +369,49 @@ extern "C" int mp_blur_subsample(const float* x, const float* kernel, float* out
 
 // ------------------------------------------------------------------------------------------------ motion-encoder pools
 // MaxPool2d(3, stride 2, padding 1) on split CL tensors: one thread = one output pixel x 4 channels.
-__global__ void k_maxpool3x3s2_cl(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
-                                  bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int N, int H, int W, int C) {
-  const int C4 = C >> 2, Ho = H >> 1, Wo = W >> 1;
-  int64_t total = (int64_t)N * Ho * Wo * C4;
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  int c4 = (int)(t % C4);
-  int64_t p = t / C4;
-  int wo = (int)(p % Wo); p /= Wo;
-  int ho = (int)(p % Ho);
-  int n = (int)(p / Ho);
-  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  for (int i = 0; i < 3; ++i) {
-    int y = ho * 2 + i - 1;
+__global__ void __launch_bounds__(256)
+k_maxpool3x3s2_cl(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
+                  bf16* __restrict__ out_lo, int H, int W, int C) {
+  // grid: x = chunks of (wo, c8) pairs of one output row, y = output row, z = sample; 8 channels (16 B) per thread
+  const int C8 = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= Wo * C8) return;
+  const int wo = idx / C8, c8 = idx - wo * C8;
+  const int ho = blockIdx.y, n = blockIdx.z;
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int y = ho * 2 + a - 1;
     if (y < 0 || y >= H) continue;
-    for (int j = 0; j < 3; ++j) {
-      int x = wo * 2 + j - 1;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int x = wo * 2 + b - 1;
       if (x < 0 || x >= W) continue;
-      float4 v = mp_load_split4(in_hi, in_lo, (((int64_t)n * H + y) * W + x) * C + c4 * 4);
-      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      const int64_t i = (((int64_t)n * H + y) * W + x) * C + c8 * 8;
+      const bf16x8v h = *reinterpret_cast<const bf16x8v*>(in_hi + i);
+      const bf16x8v l = *reinterpret_cast<const bf16x8v*>(in_lo + i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], mp_join(h.v[k], l.v[k]));
     }
   }
-  mp_store_split4(out_hi, out_lo, t * 4, m);
+  bf16x8v oh, ol;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mp_split2(m[k], oh.v[k], ol.v[k]);
+  const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C8 + c8) * 8;
+  *reinterpret_cast<bf16x8v*>(out_hi + o) = oh;
+  *reinterpret_cast<bf16x8v*>(out_lo + o) = ol;
 }
 
 extern "C" int mp_maxpool3x3s2_cl(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int N, int H, int W,
                                   int C, void* stream) {
   MP_REQUIRE(in_hi && in_lo && out_hi && out_lo, "mp_maxpool3x3s2_cl: null pointer");
-  MP_REQUIRE(N > 0 && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "mp_maxpool3x3s2_cl: bad dims");
-  int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
-  k_maxpool3x3s2_cl<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(
-      (const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi, (bf16*)out_lo, N, H, W, C);
+  MP_REQUIRE(N > 0 && N <= 65535 && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && H / 2 <= 65535,
+             "mp_maxpool3x3s2_cl: bad dims");
+  dim3 grid((unsigned)(((W / 2) * (C / 8) + 255) / 256), (unsigned)(H / 2), (unsigned)N);
+  k_maxpool3x3s2_cl<<<grid, 256, 0, mp_stream(stream)>>>((const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi,
+                                                         (bf16*)out_lo, H, W, C);
   MP_LAUNCH_CHECK("mp_maxpool3x3s2_cl");
   return 0;
 }
