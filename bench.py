@@ -283,8 +283,17 @@ def run_b200(args):
     if args.dump_launches:
         with open(args.dump_launches, "w") as f:
             for kind, a, b, fl, by in prof:
+                if kind.startswith("stage:"):
+                    continue
                 t_ms = a.elapsed_time(b)
                 f.write(f"{t_ms:9.4f} ms  {fl / t_ms / 1e9 if fl else 0:8.1f} TFLOP/s  {by / t_ms / 1e6 if by else 0:8.1f} GB/s  {kind}\n")
+    stages = {}
+    for kind, a, b, fl, by in prof:
+        if kind.startswith("stage:"):
+            t_ms = a.elapsed_time(b)
+            stages[kind[6:]] = {"ms": round(t_ms, 3),
+                                "useful_tflops": round(fl / (t_ms * 1e-3) / 1e12, 1) if fl else None}
+    prof = [x for x in prof if not x[0].startswith("stage:")]
     for kind, a, b, fl, by in prof:
         kind = kind.split("|")[0]
         d = agg.setdefault(kind, {"ms": 0.0, "flops": 0, "bytes": 0, "n": 0})
@@ -352,6 +361,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": roof,
         "kernels": extra,
+        "stages_eager_step": stages,
         "cpu_baseline": cpu,
         "useful_tflops_whole_step": (B * FLOPS_PER_DRIVER + FLOPS_SOURCE) * world / (step_ms * 1e-3) / 1e12,
     }

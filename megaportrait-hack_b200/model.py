@@ -667,13 +667,19 @@ class Gbase(nn.Module):
         if self.training:
             raise NotImplementedError("Gbase: train mode is not implemented on the B200 path (SURVEY.md 8f-2)")
         xs = _as_f32_cuda(xs)
-        vs = self.appearanceEncoder._volume_cl(xs)
-        es = self.appearanceEncoder._descriptor(xs)
-        Rs, ts, zs = self._emtn(xs)
-        em, theta = self.warp_generator_s2c._em_theta(Rs, ts, zs, es)
-        vc = ops.warp_fused(vs, em, theta, sum_d=False, f32=True, split=True)
-        assert vc.shape[1:] == (16, 64, 64, 96), f"Expected vc shape (_, 96, 16, 64, 64), got {vc.shape}"
-        vc2d = self.G3d._forward_cl(vc)
+        B = xs.shape[0]
+        with ops.stage("Eapp.volume", 866.5e9 * B):
+            vs = self.appearanceEncoder._volume_cl(xs)
+        with ops.stage("Eapp.descriptor", 34.4e9 * B):
+            es = self.appearanceEncoder._descriptor(xs)
+        with ops.stage("Emtn(source)", 235.6e9 * B):
+            Rs, ts, zs = self._emtn(xs)
+        with ops.stage("WarpGeneratorS2C", 0.5e9 * B):
+            em, theta = self.warp_generator_s2c._em_theta(Rs, ts, zs, es)
+        with ops.stage("warp(vs)+G3d", 163.1e9 * B):
+            vc = ops.warp_fused(vs, em, theta, sum_d=False, f32=True, split=True)
+            assert vc.shape[1:] == (16, 64, 64, 96), f"Expected vc shape (_, 96, 16, 64, 64), got {vc.shape}"
+            vc2d = self.G3d._forward_cl(vc)
         src = {"vc2d": vc2d, "es": es}
         if keep_stages:
             src.update(vs=vs, Rs=Rs, ts=ts, zs=zs, em_s2c=em, theta_s2c=theta, vc=vc)
@@ -684,7 +690,8 @@ class Gbase(nn.Module):
         """Driver-only part of the per-driver half (model.py:1145): Emtn(xd) -> (Rd, td, zd).  Independent of the
         source, so it can run concurrently with `encode_source` (engine.GraphedGbase does)."""
         _require_inference(self, xd)
-        return self._emtn(_as_f32_cuda(xd))
+        with ops.stage("Emtn(drivers)", 235.6e9 * xd.shape[0]):
+            return self._emtn(_as_f32_cuda(xd))
 
     @torch.no_grad()
     def drive_render(self, src: Dict[str, object], motion, keep_stages: bool = False):
@@ -695,11 +702,15 @@ class Gbase(nn.Module):
         if es.shape[0] != n:
             assert es.shape[0] == 1, f"source batch {es.shape[0]} does not match driver batch {n}"
             es = es.expand(n, -1)
-        em, theta = self.warp_generator_c2d._em_theta(Rd, td, zd, es)
-        proj = ops.warp_fused(src["vc2d"], em, theta, sum_d=True, f32=keep_stages, split=True)
+        with ops.stage("WarpGeneratorC2D", 0.5e9 * n):
+            em, theta = self.warp_generator_c2d._em_theta(Rd, td, zd, es)
+        with ops.stage("warp(vc2d)+sumD"):
+            proj = ops.warp_fused(src["vc2d"], em, theta, sum_d=True, f32=keep_stages, split=True)
         assert proj.shape[1:] == (1, 64, 64, 96), f"Expected vc2d_warped shape (_, 96, 16, 64, 64), got {proj.shape}"
-        xhat = self.G2d._forward_cl(proj)
-        pyramids = self.image_pyramid(xhat)
+        with ops.stage("G2d", 504.6e9 * n):
+            xhat = self.G2d._forward_cl(proj)
+        with ops.stage("ImagePyramide", 0.31e9 * n):
+            pyramids = self.image_pyramid(xhat)
         if keep_stages:
             return xhat, pyramids, dict(Rd=Rd, td=td, zd=zd, em_c2d=em, theta_c2d=theta, projected=proj)
         return xhat, pyramids

@@ -40,6 +40,20 @@ class _Prof:
         return False
 
 
+class stage:
+    """`with ops.stage("G3d"):` -- stage-level CUDA-event bracket, recorded only while `PROFILE` is a list."""
+
+    def __init__(self, name: str, flops: float = 0.0):
+        self.p = _Prof("stage:" + name, flops)
+
+    def __enter__(self):
+        self.p.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self.p.__exit__(*exc)
+
+
 def _profiled(fn):
     """Bracket a wrapper with CUDA events while `PROFILE` is a list (per-launch dump of bench.py)."""
     import functools
