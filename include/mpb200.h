@@ -12,7 +12,9 @@
  *     never throws, never exits;
  *   - "NCDHW" = the reference's contiguous fp32 layout; "CL" = channels-last [N, D, H, W, C] (2-D tensors use D=1);
  *   - "split" = a pair of bf16 planes (hi, lo) with x ~= hi + lo (16 mantissa bits): the operand format of the
- *     3-pass bf16 tensor-core convolution.
+ *     3-pass bf16 tensor-core convolution;
+ *   - "fp16 plane" = one fp16 value per element: the activation format of the two-pass MP_PREC_F16X2 convolutions
+ *     that serve the pooled motion-encoder trunks.
  */
 #ifndef MPB200_H
 #define MPB200_H
@@ -24,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPB200_ABI_VERSION 2
+#define MPB200_ABI_VERSION 3
 
 /* activation codes shared by several entry points */
 enum { MP_ACT_NONE = 0, MP_ACT_RELU = 1, MP_ACT_RELU_TANH = 2, MP_ACT_SIGMOID = 3 };
@@ -100,7 +102,16 @@ typedef struct mp_conv_desc {
   int in_C;               /* channels per position of the input tensor (default Cin) */
   int out_c_off;          /* first output channel written */
   int out_C;              /* channels per position of the output / residual tensors (default Cout) */
+  /* --- ABI v3 extension (0 = default) ---------------------------------------------------------------------- */
+  int prec;               /* MP_PREC_SPLIT_BF16 (0): 3-pass split-bf16 as described above.
+                             MP_PREC_F16X2 (1): two-pass fp16 for the pooled encoder trunks (Emtn, model.py:888-907):
+                             in_hi / res_hi / out_hi are SINGLE fp16 planes (in_lo, res_lo, out_lo ignored; x rounded
+                             to 11 significant bits), w_hi = fp16(w), w_lo = fp16((w - w_hi) * 2048); the kernel
+                             accumulates x*w_hi and x*w_lo in fp32 and adds the second sum scaled by 2^-11.
+                             mp_conv_tc only. */
 } mp_conv_desc;
+
+enum { MP_PREC_SPLIT_BF16 = 0, MP_PREC_F16X2 = 1 };
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores fed by TMA (3-pass split-bf16, fp32 accumulate in TMEM).
  * Requires Cin % 16 == 0 and a 128-position output tile that is a box of the (D,H,W) grid. */
@@ -118,6 +129,17 @@ int mp_maxpool3x3s2_cl(const void* in_hi, const void* in_lo, void* out_hi, void*
 /* nn.AdaptiveAvgPool2d(1) on a CL tensor (fp32 if in_f32 != NULL else split): [N,S,C] -> out [N,C] fp32. */
 int mp_global_avgpool_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out, int N, int64_t S, int C,
                          void* stream);
+
+/* ---------------------------------------------------------------- fp16 single-plane trunk operators -------- */
+/* RGB stem as a GEMM: NCHW fp32 frames [N,C<=3,H,W] -> fp16 CL patches [N, H/stride, W/stride, 32], channel
+ * (kh*3+kw)*C + c holds in[n, c, ho*stride+kh-1, wo*stride+kw-1] (zero outside the frame), channels >= 9*C are zero:
+ * the 3x3 (pad 1) stems nn.Conv2d(3, 64, 3, stride) of the motion-encoder trunks (resnet.py:192,
+ * mysixdrepnet.py:1230) then run as one 1x1 convolution with K = 32 on the tensor cores. */
+int mp_im2col3x3_f16(const float* in, void* out_h, int N, int C, int H, int W, int stride, void* stream);
+/* nn.MaxPool2d(3, 2, 1) on an fp16 CL tensor [N,1,H,W,C] -> [N,1,H/2,W/2,C] (resnet.py:196). */
+int mp_maxpool3x3s2_cl_f16(const void* in_h, void* out_h, int N, int H, int W, int C, void* stream);
+/* nn.AdaptiveAvgPool2d(1) on an fp16 CL tensor [N,S,C] -> out [N,C] fp32 (fp32 accumulation). */
+int mp_global_avgpool_cl_f16(const void* in_h, float* out, int N, int64_t S, int C, void* stream);
 
 /* ---------------------------------------------------------------- warping ----------------------------------- */
 /* F.grid_sample(v, grid, 'bilinear', 'border', align_corners=True) for 5-D input (model.py:1062).

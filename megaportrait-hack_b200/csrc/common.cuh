@@ -1,6 +1,7 @@
 // Shared helpers for libmpb200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,6 +39,16 @@ __device__ __forceinline__ float mp_apply_act(float v, int act) {
     default: return v;
   }
 }
+
+// fp16 single-plane activations (MP_PREC_F16X2 convolutions): round-to-nearest-even, saturating at the fp16 range.
+typedef __half f16;
+__device__ __forceinline__ f16 mp_to_f16(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
+struct __align__(16) f16x8 {
+  f16 v[8];
+};
+struct __align__(8) f16x4 {
+  f16 v[4];
+};
 
 // 4 consecutive channels <-> 8-byte bf16x4 vectors
 struct __align__(8) bf16x4 {

@@ -59,6 +59,9 @@ struct TcParams {
   uint32_t idesc2;            // instruction descriptor with N = 2*BN
   int b_resident;             // 1: the whole weight tile [taps*Cin x BN] stays in smem for the CTA's lifetime
   uint32_t bres_off;          // byte offset of the resident weight area
+  int prec;                   // MP_PREC_SPLIT_BF16 | MP_PREC_F16X2 (single fp16 activation plane, fp16 hi / scaled-lo weights)
+  uint32_t a_planes;          // activation planes per stage: 2 (hi, lo) or 1 (fp16)
+  float lo_scale;             // weight of the [Bl] column half in the epilogue: 1 (bf16 split) or 2^-11 (fp16 scaled lo)
 };
 
 struct __align__(16) bf16x8 {
@@ -172,6 +175,20 @@ __device__ __forceinline__ void umma_chunk_dual(uint32_t tmem_d, uint32_t a_hi, 
     umma_bf16_lean(tmem_d, al + 2 * k, bh + 2 * k, hi, idesc, 1u);
   }
 }
+// fp16 two-pass variant: ONE MMA per K step, Ah x [Bh|Bl'] (N = 2*BN); the activation has no lo plane
+template <int KS>
+__device__ __forceinline__ void umma_chunk_h(uint32_t tmem_d, uint32_t a_hi, uint32_t b_hi, uint32_t hi, uint32_t idesc2,
+                                             uint32_t acc_first) {
+  const uint32_t ah = desc_lo_word(a_hi), bh = desc_lo_word(b_hi);
+#pragma unroll
+  for (int k = 0; k < KS; ++k) umma_bf16_lean(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc2, k == 0 ? acc_first : 1u);
+}
+__device__ __forceinline__ void umma_chunk_h_dyn(int ksteps, uint32_t tmem_d, uint32_t a_hi, uint32_t b_hi, uint32_t hi,
+                                                 uint32_t idesc2, uint32_t acc_first) {
+  if (ksteps == 4) umma_chunk_h<4>(tmem_d, a_hi, b_hi, hi, idesc2, acc_first);
+  else if (ksteps == 2) umma_chunk_h<2>(tmem_d, a_hi, b_hi, hi, idesc2, acc_first);
+  else umma_chunk_h<1>(tmem_d, a_hi, b_hi, hi, idesc2, acc_first);
+}
 __device__ __forceinline__ void umma_chunk_dual_dyn(int ksteps, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo,
                                                     uint32_t b_hi, uint32_t hi, uint32_t idesc, uint32_t idesc2,
                                                     uint32_t acc_first) {
@@ -242,7 +259,7 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
         float v2[16];
         tmem_ld16(tmem_acc + (uint32_t)(p.BN + c0 + hc), v2);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v2[i], p.lo_scale, v[i]);
       }
       if (!row_valid) {
 #pragma unroll
@@ -264,6 +281,13 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
             const float4 rr = *reinterpret_cast<const float4*>(p.res_f32 + obase + co0 + hc + i);
             v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
           }
+        } else if (p.res_hi && p.prec == MP_PREC_F16X2) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const f16x4 rr = *reinterpret_cast<const f16x4*>(reinterpret_cast<const f16*>(p.res_hi) + obase + co0 + hc + i);
+            v[i] += __half2float(rr.v[0]); v[i + 1] += __half2float(rr.v[1]);
+            v[i + 2] += __half2float(rr.v[2]); v[i + 3] += __half2float(rr.v[3]);
+          }
         } else if (p.res_hi) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -278,6 +302,7 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
             const int64_t o = obase + co0 + hc + i;
             if (p.bias) v[i] += __ldg(p.bias + co0 + hc + i);
             if (p.res_f32) v[i] += p.res_f32[o];
+            else if (p.res_hi && p.prec == MP_PREC_F16X2) v[i] += __half2float(reinterpret_cast<const f16*>(p.res_hi)[o]);
             else if (p.res_hi) v[i] += mp_join(p.res_hi[o], p.res_lo[o]);
           }
         }
@@ -313,7 +338,28 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
         }
       }
     }
-    if (p.out_hi) {
+    if (p.out_hi && p.prec == MP_PREC_F16X2) {
+      f16* oh = reinterpret_cast<f16*>(p.out_hi);
+      if (vec8) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int row = j * 64 + (et >> 2), c8 = (et & 3) * 8;
+          if (c8 < ncol && row_off[row] >= 0) {
+            const float4 x0 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8);
+            const float4 x1 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8 + 4);
+            f16x8 h;
+            h.v[0] = mp_to_f16(x0.x); h.v[1] = mp_to_f16(x0.y); h.v[2] = mp_to_f16(x0.z); h.v[3] = mp_to_f16(x0.w);
+            h.v[4] = mp_to_f16(x1.x); h.v[5] = mp_to_f16(x1.y); h.v[6] = mp_to_f16(x1.z); h.v[7] = mp_to_f16(x1.w);
+            *reinterpret_cast<f16x8*>(oh + row_off[row] + co0 + c8) = h;
+          }
+        }
+      } else {
+        for (int j = 0; j < 16; ++j) {
+          const int row = j * 8 + (et >> 5);
+          if (lane < ncol && row_off[row] >= 0) oh[row_off[row] + co0 + lane] = mp_to_f16(epi[row * EPI_PITCH + lane]);
+        }
+      }
+    } else if (p.out_hi) {
       if (vec8) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -464,7 +510,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
           tma_load_2d(sb + p.b_bytes, &map_b_lo, bres_bar, i * p.CCHUNK, 0);
         }
       }
-      const uint32_t tx = p.b_resident ? 2 * p.a_bytes : 2 * p.a_bytes + 2 * p.b_bytes;
+      const uint32_t tx = p.a_planes * p.a_bytes + (p.b_resident ? 0u : 2 * p.b_bytes);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int n, d0, h0, w0, n0;
         tile_coords(tile, n, d0, h0, w0, n0);
@@ -480,10 +526,10 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             const int c0 = cc * p.CCHUNK;
             const int ci = c0 + p.in_c_off, wi = w0 * p.stride + kw - pw, hi_ = h0 * p.stride + kh - ph;
             tma_load_5d(sa, &map_a_hi, full_bar(s), ci, wi, hi_, d0 + kd - pd, n);
-            tma_load_5d(sa + p.a_bytes, &map_a_lo, full_bar(s), ci, wi, hi_, d0 + kd - pd, n);
+            if (p.a_planes == 2) tma_load_5d(sa + p.a_bytes, &map_a_lo, full_bar(s), ci, wi, hi_, d0 + kd - pd, n);
             if (!p.b_resident) {
-              tma_load_2d(sa + 2 * p.a_bytes, &map_b_hi, full_bar(s), tap * p.Cin + c0, n0);
-              tma_load_2d(sa + 2 * p.a_bytes + p.b_bytes, &map_b_lo, full_bar(s), tap * p.Cin + c0, n0);
+              tma_load_2d(sa + p.a_planes * p.a_bytes, &map_b_hi, full_bar(s), tap * p.Cin + c0, n0);
+              tma_load_2d(sa + p.a_planes * p.a_bytes + p.b_bytes, &map_b_lo, full_bar(s), tap * p.Cin + c0, n0);
             }
           }
         }
@@ -508,9 +554,11 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + s * p.stage_bytes;
           const uint32_t a_hi = sa, a_lo = sa + p.a_bytes;
-          const uint32_t b_hi = p.b_resident ? smem_base + p.bres_off + (uint32_t)i * 2u * p.b_bytes : sa + 2 * p.a_bytes;
+          const uint32_t b_hi =
+              p.b_resident ? smem_base + p.bres_off + (uint32_t)i * 2u * p.b_bytes : sa + p.a_planes * p.a_bytes;
           const uint32_t b_lo = b_hi + p.b_bytes;
-          if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, i > 0 ? 1u : 0u);
+          if (p.prec == MP_PREC_F16X2) umma_chunk_h_dyn(ksteps, d_tmem, a_hi, b_hi, dhi, p.idesc2, i > 0 ? 1u : 0u);
+          else if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, i > 0 ? 1u : 0u);
           else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, i > 0 ? 1u : 0u);
           umma_commit(empty_bar(s));
         }
@@ -592,7 +640,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_stage = 2 * x.a_plane_bytes, b_stage = 2 * p.b_bytes;
+  const uint32_t a_stage = p.a_planes * x.a_plane_bytes, b_stage = 2 * p.b_bytes;
   const uint32_t row_bytes = (uint32_t)p.CCHUNK * 2u;
 
   if (threadIdx.x == 0) {
@@ -645,8 +693,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
                 const uint32_t sa = smem_base + sidx * a_stage;
                 mbar_expect_tx(fullA(sidx), a_stage);
                 tma_load_5d(sa, &map_a_hi, fullA(sidx), c0 + p.in_c_off, w0 + kw - pw, h0 - 1, d0 + kd - pd, n);
-                tma_load_5d(sa + x.a_plane_bytes, &map_a_lo, fullA(sidx), c0 + p.in_c_off, w0 + kw - pw, h0 - 1,
-                            d0 + kd - pd, n);
+                if (p.a_planes == 2)
+                  tma_load_5d(sa + x.a_plane_bytes, &map_a_lo, fullA(sidx), c0 + p.in_c_off, w0 + kw - pw, h0 - 1,
+                              d0 + kd - pd, n);
                 ++ia;
               }
               for (int kh = 0; kh < 3; ++kh, ++ib) {
@@ -687,7 +736,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
               const uint32_t a_hi = sa + (uint32_t)((t * p.BH + kh) * p.BW) * row_bytes;
               const uint32_t a_lo = a_hi + x.a_plane_bytes;
               const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.acc_w);
-              if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, first ? 0u : 1u);
+              if (p.prec == MP_PREC_F16X2) umma_chunk_h_dyn(ksteps, d_tmem, a_hi, b_hi, dhi, p.idesc2, first ? 0u : 1u);
+              else if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, first ? 0u : 1u);
               else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, first ? 0u : 1u);
             }
             first = false;
@@ -981,6 +1031,15 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   auto fail = [&](const char* why) { return report ? mp_set_error("mp_conv_tc: unsupported shape: %s", why) : 1; };
   if (d->Cin % 16 != 0) return fail("Cin % 16 != 0");
   if (d->Cout_pad % 16 != 0) return fail("Cout_pad % 16 != 0");
+  if (d->prec != MP_PREC_SPLIT_BF16 && d->prec != MP_PREC_F16X2) return fail("unknown prec");
+  const bool f16x2 = d->prec == MP_PREC_F16X2;
+  if (f16x2 && use_v1()) return fail("v1 kernel has no fp16 two-pass mode");
+  p.prec = d->prec;
+  p.a_planes = f16x2 ? 1u : 2u;
+  p.lo_scale = f16x2 ? 1.0f / 2048.0f : 1.0f;
+  const uint32_t ap = p.a_planes;
+  // kind::f16 instruction descriptor: D = f32 (bit 4); A/B format bf16 = 1 at bits 7 / 10, fp16 = 0
+  const uint32_t idesc_fmt = (1u << 4) | (f16x2 ? 0u : ((1u << 7) | (1u << 10)));
   p.CCHUNK = (d->Cin % 64 == 0) ? 64 : (d->Cin % 32 == 0) ? 32 : 16;
   p.layout_type = p.CCHUNK == 64 ? 2u : p.CCHUNK == 32 ? 4u : 6u;
   pl.swz = p.CCHUNK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : p.CCHUNK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -1030,7 +1089,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
   p.BN = 0;
   for (int c : cands)
-    if (c <= bn_cap && d->Cout_pad % c == 0) { p.BN = c; break; }
+    if (c <= bn_cap && (!f16x2 || c <= 128) && d->Cout_pad % c == 0) { p.BN = c; break; }   // fp16 mode: N = 2*BN <= 256
   if (!p.BN) return fail("no N tile");
   while ((int64_t)pl.tiles_m * (d->Cout_pad / p.BN) < 148 && p.BN % 32 == 0 && p.BN > 32) p.BN /= 2;
   pl.tiles_n = d->Cout_pad / p.BN;
@@ -1060,8 +1119,8 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
           const uint32_t b_stage = 2u * bn * cc * 2u;
           const uint32_t a_plane = (uint32_t)(mt_try * 16 + 2) * 8u * cc * 2u;
           for (int sa = 3; sa >= 2; --sa) {
-            if (fixed_s + sa * 2 * a_plane + sb_want * b_stage > SMEM_LIMIT) continue;
-            int sb = (int)((SMEM_LIMIT - fixed_s - sa * 2 * a_plane) / b_stage);
+            if (fixed_s + sa * ap * a_plane + sb_want * b_stage > SMEM_LIMIT) continue;
+            int sb = (int)((SMEM_LIMIT - fixed_s - sa * ap * a_plane) / b_stage);
             if (sb > 12) sb = 12;
             best_sb = sb; best_cc = cc; best_sa = sa; best_mt = mt_try;
             break;
@@ -1076,7 +1135,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
       pl.slab = true;
       pl.x.MT = mt; pl.x.SA = sa; pl.x.SB = sb;
       pl.x.a_plane_bytes = a_plane;
-      pl.x.b_ring_off = sa * 2 * a_plane;
+      pl.x.b_ring_off = sa * ap * a_plane;
       p.CCHUNK = cc;
       p.layout_type = cc == 64 ? 2u : cc == 32 ? 4u : 6u;
       pl.swz = cc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : cc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -1095,7 +1154,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
       p.bres_off = 0;
       p.epi_off = pl.x.b_ring_off + sb * b_stage;
       pl.smem_bytes = fixed_s + p.epi_off;
-      p.dualb = (allow_dual() && 2 * mt * 2 * bn <= 512) ? 1 : 0;
+      p.dualb = ((allow_dual() || f16x2) && 2 * mt * 2 * bn <= 512) ? 1 : 0;
       p.acc_w = p.dualb ? 2 * bn : bn;
       p.tmem_cols = next_pow2(2 * mt * p.acc_w);
       p.tiles_n = 1;
@@ -1106,8 +1165,9 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     choose(mt2_ok ? 2 : 1);
   }
   if (pl.slab) {
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-    p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    if (f16x2 && !p.dualb) return fail("fp16 two-pass mode needs the [Bh|Bl] column layout (BN <= 128)");
+    p.idesc = idesc_fmt | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    p.idesc2 = idesc_fmt | ((uint32_t)(2 * p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
     p.D = d->D; p.H = Ho; p.W = Wo; p.Cin = d->Cin; p.Cout = d->Cout;
     p.KD = d->KD; p.KH = d->KH; p.KW = d->KW;
     p.bias = d->bias; p.res_f32 = d->res_f32; p.res_hi = (const bf16*)d->res_hi; p.res_lo = (const bf16*)d->res_lo;
@@ -1128,7 +1188,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   const bool all_taps = p.tap_mask == (ntaps == 64 ? ~0ull : ((1ull << ntaps) - 1ull));
   if (!pl.v1 && allow_res && all_taps && pl.tiles_n == 1 && pl.tiles_m >= 4 * 148 && bres_bytes < SMEM_LIMIT) {
     for (int cc = p.CCHUNK; cc >= 16; cc /= 2) {
-      const uint32_t a_stage = 2u * TILE_M * cc * 2u;
+      const uint32_t a_stage = ap * TILE_M * cc * 2u;
       if (fixed + bres_bytes + 3 * a_stage <= SMEM_LIMIT && bres_bytes < (1u << 20)) {
         p.b_resident = 1;
         p.CCHUNK = cc;
@@ -1142,7 +1202,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   }
   p.a_bytes = TILE_M * p.CCHUNK * 2;
   p.b_bytes = p.BN * p.CCHUNK * 2;
-  p.stage_bytes = p.b_resident ? 2 * p.a_bytes : 2 * p.a_bytes + 2 * p.b_bytes;
+  p.stage_bytes = p.b_resident ? ap * p.a_bytes : ap * p.a_bytes + 2 * p.b_bytes;
   const uint32_t avail = SMEM_LIMIT - fixed - (p.b_resident ? bres_bytes : 0);
   int stages = (int)(avail / p.stage_bytes);
   if (stages > 8) stages = 8;
@@ -1151,13 +1211,14 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   pl.smem_bytes = fixed + stages * p.stage_bytes + (p.b_resident ? bres_bytes : 0);
   p.bres_off = stages * p.stage_bytes;
   p.epi_off = p.bres_off + (p.b_resident ? bres_bytes : 0);
-  p.dualb = (!pl.v1 && allow_dual() && 2 * 2 * p.BN <= 512) ? 1 : 0;
+  p.dualb = (!pl.v1 && (allow_dual() || f16x2) && 2 * 2 * p.BN <= 512) ? 1 : 0;
+  if (f16x2 && !p.dualb) return fail("fp16 two-pass mode needs the [Bh|Bl] column layout (BN <= 128)");
   p.acc_w = p.dualb ? 2 * p.BN : p.BN;
   p.tmem_cols = next_pow2(pl.v1 ? p.BN : 2 * p.acc_w);
-  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  p.idesc2 = idesc_fmt | ((uint32_t)(2 * p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   p.tiles_n = pl.tiles_n;
   p.total_tiles = pl.tiles_m * pl.tiles_n;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  p.idesc = idesc_fmt | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   p.D = d->D; p.H = Ho; p.W = Wo; p.Cin = d->Cin; p.Cout = d->Cout;
   p.KD = d->KD; p.KH = d->KH; p.KW = d->KW;
   p.bias = d->bias; p.res_f32 = d->res_f32; p.res_hi = (const bf16*)d->res_hi; p.res_lo = (const bf16*)d->res_lo;
@@ -1178,7 +1239,8 @@ int encode_act_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const
                        (cuuint32_t)(pl.slab ? pl.x.MT * pl.p.BH + 2 : pl.p.BH * st), (cuuint32_t)pl.p.BD,
                        (cuuint32_t)(pl.slab ? 1 : pl.p.BNb)};
   cuuint32_t estr[5] = {1, st, st, 1, 1};
-  CUresult r = get_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+  const CUtensorMapDataType dt = pl.p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = get_encoder()(m, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(activation) failed (%d)", (int)r);
@@ -1190,7 +1252,8 @@ int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const P
   cuuint64_t strides[1] = {ktot * 2};
   cuuint32_t box[2] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BN};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  const CUtensorMapDataType dt = pl.p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = get_encoder()(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
@@ -1213,7 +1276,7 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
              "mp_conv_tc: operands must be 16-byte aligned");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (int e = encode_act_map(&ma_hi, d->in_hi, d, pl)) return e;
-  if (int e = encode_act_map(&ma_lo, d->in_lo, d, pl)) return e;
+  if (int e = encode_act_map(&ma_lo, pl.p.a_planes == 2 ? d->in_lo : d->in_hi, d, pl)) return e;   // unused when 1 plane
   if (int e = encode_w_map(&mb_hi, d->w_hi, d, pl)) return e;
   if (int e = encode_w_map(&mb_lo, d->w_lo, d, pl)) return e;
   {

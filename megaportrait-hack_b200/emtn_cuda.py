@@ -9,11 +9,20 @@ and the RepVGG-B1g2 deploy backbone of 6DRepNet (mysixdrepnet.py:30-69, 1215-129
   * MaxPool2d(3,2,1) and the global average pools are small HBM-bound kernels; the final Linear layers (<= 2048x512)
     are plain library GEMMs (`F.linear`).
 
+Precision.  `Emtn`'s three trunks end in global average pools, which average the operand-rounding noise of the
+convolutions away, so they run the two-pass fp16 convolution (`PREC_F16X2`: activations as ONE fp16 plane, weights as
+fp16 hi + scaled fp16 lo, fp32 accumulation): against the CPU oracle R, t and z then differ by <= 2e-5 (relative L2;
+tests/test_gpu_gbase.py holds them to 2e-4 of abs-max) while the convolutions need 2/3 of the tensor-pipe work and half
+of the activation bytes.  Their 3x3 RGB stems run as a 1x1 convolution over 32 patch channels written by
+`mp_im2col3x3_f16`.  `MPB200_EMTN_PREC=split` selects the three-pass split-bf16 plans instead (A/B runs); the
+ResNet-50 descriptor (`es` feeds both warp generators un-pooled) always runs split-bf16.
+
 Plans are built lazily from the live parameters, cached on parameter versions, and never registered as sub-modules
 (the reference's state_dict keys are untouched).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -21,9 +30,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .ops import ACT_NONE, ACT_RELU, Act
+from .ops import ACT_NONE, ACT_RELU, PREC_F16X2, PREC_SPLIT_BF16, Act
 
 RGB_PAD = 16
+EMTN_PREC = PREC_SPLIT_BF16 if os.environ.get("MPB200_EMTN_PREC", "f16x2") == "split" else PREC_F16X2
 
 
 def rgb16(x: torch.Tensor) -> Act:
@@ -36,34 +46,35 @@ def _bn(bn: nn.BatchNorm2d) -> dict:
             "running_var": bn.running_var}
 
 
-def _pack_conv_bn(conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_pad: int = 0) -> ops.PackedConv:
+def _pack_conv_bn(conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], cin_pad: int = 0,
+                  prec: int = PREC_SPLIT_BF16) -> ops.PackedConv:
     w, b = conv.weight.detach(), (None if conv.bias is None else conv.bias.detach())
     if bn is not None:
         w, b = ops.fold_bn(w, b, _bn(bn), bn.eps)
-    return ops.pack_conv(w, b, conv.weight.device, cin_pad=cin_pad)
+    return ops.pack_conv(w, b, conv.weight.device, cin_pad=cin_pad, prec=prec)
 
 
 class ResNetTrunkPlan:
     """torchvision-style ResNet trunk (BasicBlock or Bottleneck): stem conv+bn+relu, MaxPool(3,2,1), residual stages."""
 
-    def __init__(self, conv1: nn.Conv2d, bn1: nn.BatchNorm2d, layers):
-        self.stem = _pack_conv_bn(conv1, bn1, cin_pad=RGB_PAD)
+    def __init__(self, conv1: nn.Conv2d, bn1: nn.BatchNorm2d, layers, prec: int = PREC_SPLIT_BF16):
+        self.prec = prec
         self.stem_wb = ops.fold_bn(conv1.weight.detach(), None if conv1.bias is None else conv1.bias.detach(),
                                    _bn(bn1), bn1.eps)
+        self.stem = None if prec == PREC_F16X2 else _pack_conv_bn(conv1, bn1, cin_pad=RGB_PAD)   # fp16: see DualResNet18Plan
         self.stem_stride = conv1.stride[0]
         self.blocks: List[Tuple] = []
+        pk = lambda c, b: _pack_conv_bn(c, b, prec=prec)
         for layer in layers:
             for blk in layer:
                 ds = None
                 if blk.downsample is not None:
-                    ds = (_pack_conv_bn(blk.downsample[0], blk.downsample[1]), blk.downsample[0].stride[0])
+                    ds = (pk(blk.downsample[0], blk.downsample[1]), blk.downsample[0].stride[0])
                 if type(blk).__name__ == "BasicBlock":
-                    convs = [(_pack_conv_bn(blk.conv1, blk.bn1), blk.conv1.stride[0]),
-                             (_pack_conv_bn(blk.conv2, blk.bn2), 1)]
+                    convs = [(pk(blk.conv1, blk.bn1), blk.conv1.stride[0]), (pk(blk.conv2, blk.bn2), 1)]
                 else:   # Bottleneck (v1.5: the stride sits on conv2)
-                    convs = [(_pack_conv_bn(blk.conv1, blk.bn1), 1),
-                             (_pack_conv_bn(blk.conv2, blk.bn2), blk.conv2.stride[0]),
-                             (_pack_conv_bn(blk.conv3, blk.bn3), 1)]
+                    convs = [(pk(blk.conv1, blk.bn1), 1), (pk(blk.conv2, blk.bn2), blk.conv2.stride[0]),
+                             (pk(blk.conv3, blk.bn3), 1)]
                 self.blocks.append((convs, ds))
 
     def features(self, x16: Act, last_f32: bool = False) -> Act:
@@ -89,22 +100,29 @@ class DualResNet18Plan:
     once instead of twice.  From layer2 on the two trunks are independent."""
 
     def __init__(self, a: ResNetTrunkPlan, b: ResNetTrunkPlan):
-        self.a, self.b = a, b
+        assert a.prec == b.prec
+        self.a, self.b, self.prec = a, b, a.prec
         (wa, ba), (wb, bb) = a.stem_wb, b.stem_wb
         self.c = wa.shape[0]
-        self.stem = ops.pack_conv(torch.cat([wa, wb], 0), torch.cat([ba, bb], 0), wa.device, cin_pad=RGB_PAD)
+        w, bias = torch.cat([wa, wb], 0), torch.cat([ba, bb], 0)
+        if self.prec == PREC_F16X2:
+            self.stem = ops.pack_stem3x3_f16(w, bias, wa.device)      # 1x1 over the 32 im2col patch channels
+        else:
+            self.stem = ops.pack_conv(w, bias, wa.device, cin_pad=RGB_PAD)
 
-    def pooled(self, x16: Act):
-        c = self.c
-        h, _ = ops.conv(x16, self.stem, act=ACT_RELU, f32=False, split=True)
-        h = ops.maxpool3x3s2(h)
+    def pooled(self, x_in):
+        """x_in: the fp16 patch tensor of `ops.im2col3x3_f16(x, 1)` (fp16 plans) or the padded split frame `rgb16(x)`."""
+        c, half = self.c, self.prec == PREC_F16X2
+        fmt = dict(f32=False, h16=True) if half else dict(f32=False, split=True)    # format of every intermediate
+        h, _ = ops.conv(x_in, self.stem, act=ACT_RELU, **fmt)
+        h = ops.maxpool3x3s2_f16(h) if half else ops.maxpool3x3s2(h)
         n_lock = 0
         while (n_lock < len(self.a.blocks) and self.a.blocks[n_lock][1] is None and self.b.blocks[n_lock][1] is None
                and self.a.blocks[n_lock][0][0][1] == 1):
-            out = ops._alloc(h.shape, h.device, False, True)
+            out = ops._alloc(h.shape, h.device, False, not half, half)
             for j, pl in enumerate((self.a, self.b)):
                 convs, _ds = pl.blocks[n_lock]
-                t, _ = ops.conv(h, convs[0][0], act=ACT_RELU, f32=False, split=True, in_c_off=j * c)
+                t, _ = ops.conv(h, convs[0][0], act=ACT_RELU, in_c_off=j * c, **fmt)
                 ops.conv(t, convs[1][0], res=h, act=ACT_RELU, out=out, out_c_off=j * c)
             h = out
             n_lock += 1
@@ -114,42 +132,56 @@ class DualResNet18Plan:
             for bi in range(n_lock, len(pl.blocks)):
                 convs, ds = pl.blocks[bi]
                 win = off if bi == n_lock else 0
-                idt = g if ds is None else ops.conv(g, ds[0], stride=ds[1], f32=True, in_c_off=win)[0]
-                t, _ = ops.conv(g, convs[0][0], stride=convs[0][1], act=ACT_RELU, f32=False, split=True, in_c_off=win)
-                g, _ = ops.conv(t, convs[1][0], res=idt, act=ACT_RELU, f32=False, split=True)
-            feats.append(ops.global_avgpool(g))
+                if ds is None:
+                    idt = g
+                elif half:
+                    idt = ops.conv(g, ds[0], stride=ds[1], in_c_off=win, **fmt)[0]
+                else:
+                    idt = ops.conv(g, ds[0], stride=ds[1], f32=True, in_c_off=win)[0]
+                t, _ = ops.conv(g, convs[0][0], stride=convs[0][1], act=ACT_RELU, in_c_off=win, **fmt)
+                g, _ = ops.conv(t, convs[1][0], res=idt, act=ACT_RELU, **fmt)
+            feats.append(ops.global_avgpool_f16(g) if half else ops.global_avgpool(g))
         return feats
 
 
 class RepVGGPlan:
     """RepVGG deploy backbone: 3x3 conv + ReLU blocks, stride 2 at stage heads, groups = 2 on even layers."""
 
-    def __init__(self, backbone: nn.Module):
+    def __init__(self, backbone: nn.Module, prec: int = PREC_SPLIT_BF16):
+        self.prec = prec
         self.blocks: List[Tuple] = []
         stages = [backbone.layer0] + [b for li in range(1, 5) for b in getattr(backbone, f"layer{li}")]
         for blk in stages:
             conv = blk.rbr_reparam
             g, s, cout = conv.groups, conv.stride[0], conv.out_channels
             w, b = conv.weight.detach(), conv.bias.detach()
-            if g == 1:
-                packs = [ops.pack_conv(w, b, w.device, cin_pad=RGB_PAD if conv.in_channels == 3 else 0)]
+            if g == 1 and conv.in_channels == 3 and prec == PREC_F16X2:
+                packs = [ops.pack_stem3x3_f16(w, b, w.device)]       # layer0 on im2col patches: stride handled there
+                s = 1
+            elif g == 1:
+                packs = [ops.pack_conv(w, b, w.device, cin_pad=RGB_PAD if conv.in_channels == 3 else 0, prec=prec)]
             else:
                 cg = cout // g
-                packs = [ops.pack_conv(w[i * cg:(i + 1) * cg], b[i * cg:(i + 1) * cg], w.device) for i in range(g)]
+                packs = [ops.pack_conv(w[i * cg:(i + 1) * cg], b[i * cg:(i + 1) * cg], w.device, prec=prec)
+                         for i in range(g)]
             self.blocks.append((s, g, packs, cout))
+        self.stem_stride = backbone.layer0.rbr_reparam.stride[0]
 
-    def pooled(self, x16: Act) -> torch.Tensor:
-        h = x16
+    def pooled(self, x_in) -> torch.Tensor:
+        """x_in: `ops.im2col3x3_f16(x, self.stem_stride)` (fp16 plans) or `rgb16(x)`."""
+        half = self.prec == PREC_F16X2
+        fmt = dict(f32=False, h16=True) if half else dict(f32=False, split=True)
+        h = x_in
         for s, g, packs, cout in self.blocks:
             if g == 1:
-                h, _ = ops.conv(h, packs[0], stride=s, act=ACT_RELU, f32=False, split=True)
+                h, _ = ops.conv(h, packs[0], stride=s, act=ACT_RELU, **fmt)
             else:
                 N, D, H, W, C = h.shape
-                out = ops._alloc((N, 1, H // s, W // s, cout), h.device, False, True)
+                out = ops._alloc((N, 1, H // s, W // s, cout), h.device, False, not half, half)
                 for i, pw in enumerate(packs):
                     ops.conv(h, pw, stride=s, act=ACT_RELU, in_c_off=i * (C // g), out=out, out_c_off=i * (cout // g))
                 h = out
-        return ops.global_avgpool(h)
+        return ops.global_avgpool_f16(h) if half else ops.global_avgpool(h)
 
 
 def _versions(*mods) -> tuple:
@@ -163,13 +195,13 @@ def _versions(*mods) -> tuple:
 
 def emtn_plans(emtn):
     hp, ex, rot = emtn.head_pose_net, emtn.expression_net, emtn.rotation_net.model
-    sig = _versions(hp, ex, rot)
+    sig = _versions(hp, ex, rot) + (EMTN_PREC,)
     c = emtn.__dict__.get("_mp_cuda_plans")
     if c is None or c[0] != sig:
         with torch.no_grad():
-            pa = ResNetTrunkPlan(hp.conv1, hp.bn1, [hp.layer1, hp.layer2, hp.layer3, hp.layer4])
-            pb = ResNetTrunkPlan(ex[0], ex[1], [ex[4], ex[5], ex[6], ex[7]])
-            c = (sig, (DualResNet18Plan(pa, pb), RepVGGPlan(rot)))
+            pa = ResNetTrunkPlan(hp.conv1, hp.bn1, [hp.layer1, hp.layer2, hp.layer3, hp.layer4], prec=EMTN_PREC)
+            pb = ResNetTrunkPlan(ex[0], ex[1], [ex[4], ex[5], ex[6], ex[7]], prec=EMTN_PREC)
+            c = (sig, (DualResNet18Plan(pa, pb), RepVGGPlan(rot, prec=EMTN_PREC)))
         emtn.__dict__["_mp_cuda_plans"] = c
     return c[1]
 
@@ -178,11 +210,15 @@ def emtn_forward(emtn, x: torch.Tensor):
     """Emtn.forward (model.py:888-907) on libmpb200 kernels: -> (Euler degrees [B,3], translation [B,3], z [B,512])."""
     from .emtn import ortho6d_to_euler_deg
     dual_plan, rot_plan = emtn_plans(emtn)
-    x16 = rgb16(x.float())
+    x = x.float().contiguous()
+    if dual_plan.prec == PREC_F16X2:
+        in_rot, in_dual = ops.im2col3x3_f16(x, rot_plan.stem_stride), ops.im2col3x3_f16(x, 1)
+    else:
+        in_rot = in_dual = rgb16(x)
     rot = emtn.rotation_net.model
-    x6 = F.linear(rot_plan.pooled(x16), rot.linear_reg.weight, rot.linear_reg.bias)
+    x6 = F.linear(rot_plan.pooled(in_rot), rot.linear_reg.weight, rot.linear_reg.bias)
     rotations = ortho6d_to_euler_deg(x6[:, :6])
-    f_hp, f_ex = dual_plan.pooled(x16)
+    f_hp, f_ex = dual_plan.pooled(in_dual)
     head_pose = F.linear(f_hp, emtn.head_pose_net.fc.weight, emtn.head_pose_net.fc.bias)
     translation = head_pose[:, 3:]
     # AdaptiveAvgPool2d(1) then AdaptiveAvgPool2d((2,2)) (model.py:880-881): every channel replicated 2x2, NCHW flatten

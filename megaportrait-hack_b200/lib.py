@@ -20,6 +20,8 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
 
 ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID = 0, 1, 2, 3
+PREC_SPLIT_BF16, PREC_F16X2 = 0, 1   # mp_conv_desc.prec
+ABI_VERSION = 3
 
 
 def sources():
@@ -57,6 +59,7 @@ class ConvDesc(Structure):
         ("N", c_int), ("D", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
         ("KD", c_int), ("KH", c_int), ("KW", c_int), ("Cout_pad", c_int), ("gn_groups", c_int), ("act", c_int),
         ("stride", c_int), ("in_c_off", c_int), ("in_C", c_int), ("out_c_off", c_int), ("out_C", c_int),
+        ("prec", c_int),
     ]
 
 
@@ -77,6 +80,9 @@ _SIGNATURES = {
     "mp_affine_act_cl": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, _P]),
     "mp_maxpool3x3s2_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "mp_global_avgpool_cl": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, _P]),
+    "mp_im2col3x3_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_maxpool3x3s2_cl_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "mp_global_avgpool_cl_f16": (c_int, [_P, _P, c_int, c_int64, c_int, _P]),
     "mp_conv_tc": (c_int, [POINTER(ConvDesc), _P]),
     "mp_conv_simt": (c_int, [POINTER(ConvDesc), _P]),
     "mp_conv_tc_supported": (c_int, [POINTER(ConvDesc)]),
@@ -110,7 +116,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mp_abi_version() != 2:
+    if lib.mp_abi_version() != ABI_VERSION:
         raise RuntimeError("libmpb200.so ABI version mismatch")
     _lib = lib
     return lib

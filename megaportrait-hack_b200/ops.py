@@ -2,7 +2,8 @@
 
 Internal activation format (`Act`): channels-last [N, D, H, W, C] (2-D tensors carry D = 1), held as an fp32 tensor
 and/or a pair of bf16 planes (hi, lo) with x ~= hi + lo -- the operand format of the split-bf16 tensor-core
-convolution.  Every function launches on the current torch CUDA stream and never synchronises.
+convolution.  The pooled motion-encoder trunks (Emtn) use a third form, one fp16 plane `h16`, consumed by the
+two-pass `PREC_F16X2` convolution.  Every function launches on the current torch CUDA stream and never synchronises.
 """
 from __future__ import annotations
 
@@ -13,7 +14,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import lib as _lib
-from .lib import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, ConvDesc  # noqa: F401
+from .lib import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, PREC_F16X2, PREC_SPLIT_BF16, ConvDesc  # noqa: F401
 
 LAUNCHES = 0   # number of libmpb200 kernel launches issued by this process (bench.py reports it)
 PROFILE = None  # when a list: (kind, start_event, end_event, algorithmic_flops, algorithmic_bytes) per hot launch
@@ -90,12 +91,12 @@ def _chk_cuda(t: torch.Tensor, dtype, what: str) -> None:
 
 
 class Act:
-    """Channels-last activation [N, D, H, W, C]: `f32` and/or the split pair (`hi`, `lo`)."""
-    __slots__ = ("f32", "hi", "lo", "shape")
+    """Channels-last activation [N, D, H, W, C]: `f32` and/or the split pair (`hi`, `lo`) and/or one fp16 plane `h16`."""
+    __slots__ = ("f32", "hi", "lo", "h16", "shape")
 
-    def __init__(self, shape, f32=None, hi=None, lo=None):
+    def __init__(self, shape, f32=None, hi=None, lo=None, h16=None):
         self.shape = tuple(int(s) for s in shape)
-        self.f32, self.hi, self.lo = f32, hi, lo
+        self.f32, self.hi, self.lo, self.h16 = f32, hi, lo, h16
 
     @property
     def N(self): return self.shape[0]
@@ -112,19 +113,21 @@ class Act:
 
     @property
     def device(self):
-        return (self.f32 if self.f32 is not None else self.hi).device
+        return next(t for t in (self.f32, self.hi, self.h16) if t is not None).device
 
     def has_split(self):
         return self.hi is not None
 
 
-def _alloc(shape, device, f32: bool, split: bool):
+def _alloc(shape, device, f32: bool, split: bool, h16: bool = False):
     a = Act(shape)
     if f32:
         a.f32 = torch.empty(shape, dtype=torch.float32, device=device)
     if split:
         a.hi = torch.empty(shape, dtype=torch.bfloat16, device=device)
         a.lo = torch.empty(shape, dtype=torch.bfloat16, device=device)
+    if h16:
+        a.h16 = torch.empty(shape, dtype=torch.float16, device=device)
     return a
 
 
@@ -265,11 +268,11 @@ def group_norm_act(a: Act, G: int, stats: Optional[torch.Tensor] = None, gamma=N
 # ----------------------------------------------------------------------------------------------------- conv
 class PackedConv:
     """Weights of one convolution in kernel format: split-bf16 [Cout_pad, taps*Cin] (tap-major, cin-minor) + bias."""
-    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k")
+    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k", "prec")
 
-    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k):
+    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k, prec=PREC_SPLIT_BF16):
         self.w_hi, self.w_lo, self.bias = w_hi, w_lo, bias
-        self.Cin, self.Cout, self.Cout_pad, self.k = Cin, Cout, Cout_pad, tuple(k)
+        self.Cin, self.Cout, self.Cout_pad, self.k, self.prec = Cin, Cout, Cout_pad, tuple(k), prec
 
 
 def standardize_weight(w: torch.Tensor) -> torch.Tensor:
@@ -289,9 +292,14 @@ def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: dict, eps: float = 1
     return w, (b0 - bn["running_mean"].double()) * s + bn["bias"].double()
 
 
-def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, cin_pad: int = 0) -> PackedConv:
+F16_LO_SCALE = 2048.0   # PREC_F16X2: w_lo holds (w - fp16(w)) * 2^11 so that it stays in fp16's normal range
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, cin_pad: int = 0,
+              prec: int = PREC_SPLIT_BF16) -> PackedConv:
     """weight (Cout, Cin, [kd,] kh, kw) float32/64 -> PackedConv on `device`.  `cin_pad` zero-pads the input-channel
-    axis (RGB stems run on the tensor-core kernel with their 3 channels padded to 16)."""
+    axis (RGB stems run on the tensor-core kernel with their 3 channels padded to 16).  `prec` selects the operand
+    format: split-bf16 planes, or fp16 hi + scaled fp16 lo for the two-pass convolution."""
     device = device or weight.device
     w = weight.detach().to(device=device, dtype=torch.float64)
     if w.dim() == 4:
@@ -303,10 +311,24 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, c
     Cout_pad = (Cout + 15) // 16 * 16
     if Cout_pad != Cout:
         wk = torch.cat([wk, torch.zeros(Cout_pad - Cout, wk.shape[1], device=device)], 0)
-    hi = wk.to(torch.bfloat16)
-    lo = (wk - hi.float()).to(torch.bfloat16)
+    if prec == PREC_F16X2:
+        hi = wk.to(torch.float16)
+        lo = ((wk - hi.float()) * F16_LO_SCALE).to(torch.float16)
+    else:
+        hi = wk.to(torch.bfloat16)
+        lo = (wk - hi.float()).to(torch.bfloat16)
     b = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
-    return PackedConv(hi.contiguous(), lo.contiguous(), b, Cin, Cout, Cout_pad, (kd, kh, kw))
+    return PackedConv(hi.contiguous(), lo.contiguous(), b, Cin, Cout, Cout_pad, (kd, kh, kw), prec)
+
+
+def pack_stem3x3_f16(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> PackedConv:
+    """3x3 RGB stem weight (Cout, 3, 3, 3) -> 1x1 PREC_F16X2 PackedConv over the 32 patch channels written by
+    `im2col3x3_f16` (channel (kh*3+kw)*3 + c, zero-padded from 27 to 32)."""
+    Cout, Cin, kh, kw = weight.shape
+    assert (Cin, kh, kw) == (3, 3, 3), weight.shape
+    w = weight.detach().double().permute(0, 2, 3, 1).reshape(Cout, 27)
+    w = torch.cat([w, torch.zeros(Cout, 5, dtype=w.dtype, device=w.device)], 1).reshape(Cout, 32, 1, 1)
+    return pack_conv(w, bias, device or weight.device, prec=PREC_F16X2)
 
 
 _CONV_MODE = os.environ.get("MPB200_CONV", "auto")   # auto | tc | simt
@@ -320,19 +342,30 @@ def set_conv_mode(mode: str) -> None:
 
 def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE, f32: bool = True,
          split: bool = False, stats_groups: int = 0, mode: Optional[str] = None, stride: int = 1, in_c_off: int = 0,
-         out: Optional[Act] = None, out_c_off: int = 0) -> Tuple[Act, Optional[torch.Tensor]]:
+         out: Optional[Act] = None, out_c_off: int = 0, h16: bool = False) -> Tuple[Act, Optional[torch.Tensor]]:
     """act(conv(a) + bias + res) -> (Act, GroupNorm statistics of the written values or None).
+
+    `pw.prec == PREC_F16X2` runs the two-pass fp16 kernel: `a` (and `res`, unless it is fp32) must carry an fp16 plane
+    and `h16=True` asks for an fp16 output plane.
 
     `stride` (1|2) applies to H and W.  `in_c_off` selects the window [in_c_off, in_c_off + pw.Cin) of a's channels;
     `out` / `out_c_off` write into the channel window of an existing activation (grouped convolutions)."""
-    if a.hi is None:
+    half = pw.prec == PREC_F16X2
+    if half:
+        if a.h16 is None:
+            raise RuntimeError("conv: a PREC_F16X2 convolution needs an fp16 activation plane")
+        if split or stats_groups or (res is not None and res.f32 is None and res.h16 is None):
+            raise RuntimeError("conv: PREC_F16X2 supports fp32 / fp16 outputs and residuals only, no GroupNorm statistics")
+    elif h16:
+        raise RuntimeError("conv: fp16 output planes are produced by PREC_F16X2 convolutions only")
+    elif a.hi is None:
         ensure_split(a)
     N, D, H, W, C = a.shape
     if in_c_off + pw.Cin > C:
         raise RuntimeError(f"conv: activation has {C} channels, weights expect {pw.Cin} (+{in_c_off})")
     Ho, Wo = H // stride, W // stride
     if out is None:
-        out = _alloc((N, D, Ho, Wo, pw.Cout), a.device, f32, split)
+        out = _alloc((N, D, Ho, Wo, pw.Cout), a.device, f32, split, h16)
     elif out.shape[:4] != (N, D, Ho, Wo) or out_c_off + pw.Cout > out.shape[4]:
         raise RuntimeError(f"conv: output window does not fit {out.shape}")
     # the tensor-core kernel fuses GroupNorm statistics only when a sample has >= 128 output positions; the tiny
@@ -340,15 +373,19 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     late_stats = bool(stats_groups) and (D * Ho * Wo < 128) and (out.f32 is not None)
     stats = new_stats(N, stats_groups, a.device) if (stats_groups and not late_stats) else None
     d = ConvDesc()
-    d.in_hi, d.in_lo, d.w_hi, d.w_lo, d.bias = _p(a.hi), _p(a.lo), _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias)
+    d.w_hi, d.w_lo, d.bias, d.prec = _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias), pw.prec
+    d.in_hi, d.in_lo = (_p(a.h16), None) if half else (_p(a.hi), _p(a.lo))
     if res is not None:
         if res.shape != out.shape:
             raise RuntimeError(f"conv: residual shape {res.shape} != output shape {out.shape}")
         if res.f32 is not None:
             d.res_f32 = _p(res.f32)
+        elif half:
+            d.res_hi = _p(res.h16)
         else:
             d.res_hi, d.res_lo = _p(res.hi), _p(res.lo)
-    d.out_f32, d.out_hi, d.out_lo, d.stats = _p(out.f32), _p(out.hi), _p(out.lo), _p(stats)
+    d.out_f32, d.stats = _p(out.f32), _p(stats)
+    d.out_hi, d.out_lo = (_p(out.h16), None) if half else (_p(out.hi), _p(out.lo))
     d.N, d.D, d.H, d.W, d.Cin, d.Cout = N, D, H, W, pw.Cin, pw.Cout
     d.KD, d.KH, d.KW = pw.k
     d.Cout_pad, d.gn_groups, d.act = pw.Cout_pad, (0 if late_stats else stats_groups), act
@@ -357,7 +394,9 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     mode = mode or _CONV_MODE
     use_tc = mode == "tc" or (mode == "auto" and L.mp_conv_tc_supported(ctypes.byref(d)) == 1)
     flops = 2 * N * D * Ho * Wo * pw.Cout * pw.Cin * pw.k[0] * pw.k[1] * pw.k[2]
-    with _Prof(("conv_tc" if use_tc else "conv_simt") +
+    if half and not use_tc:
+        raise RuntimeError(f"conv: shape {a.shape} x {pw.Cin}->{pw.Cout} is not supported by the fp16 two-pass kernel")
+    with _Prof(("conv_tc" if use_tc else "conv_simt") + ("_h" if half else "") +
                f"|{N}x{D}x{H}x{W} {pw.Cin}->{pw.Cout} k{pw.k[0]}{pw.k[1]}{pw.k[2]} s{stride}", flops):
         if use_tc:
             _lib.check(L.mp_conv_tc(ctypes.byref(d), _stream()), "mp_conv_tc")
@@ -391,6 +430,42 @@ def global_avgpool(a: Act) -> torch.Tensor:
     L = _lib.load()
     _lib.check(L.mp_global_avgpool_cl(_p(a.f32), _p(a.hi), _p(a.lo), _p(out), N, D * H * W, C, _stream()),
                "mp_global_avgpool_cl")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- fp16 trunk ops
+@_profiled
+def im2col3x3_f16(x: torch.Tensor, stride: int = 1) -> Act:
+    """NCHW fp32 RGB frames [N,3,H,W] -> fp16 CL patches [N,1,H/stride,W/stride,32] (see `pack_stem3x3_f16`)."""
+    _chk_cuda(x, torch.float32, "im2col3x3_f16")
+    N, C, H, W = x.shape
+    out = _alloc((N, 1, H // stride, W // stride, 32), x.device, False, False, True)
+    L = _lib.load()
+    _lib.check(L.mp_im2col3x3_f16(_p(x), _p(out.h16), N, C, H, W, stride, _stream()), "mp_im2col3x3_f16")
+    _count()
+    return out
+
+
+@_profiled
+def maxpool3x3s2_f16(a: Act) -> Act:
+    """nn.MaxPool2d(3, 2, 1) on an fp16 2-D activation."""
+    N, D, H, W, C = a.shape
+    assert D == 1 and a.h16 is not None
+    out = _alloc((N, 1, H // 2, W // 2, C), a.device, False, False, True)
+    L = _lib.load()
+    _lib.check(L.mp_maxpool3x3s2_cl_f16(_p(a.h16), _p(out.h16), N, H, W, C, _stream()), "mp_maxpool3x3s2_cl_f16")
+    _count()
+    return out
+
+
+@_profiled
+def global_avgpool_f16(a: Act) -> torch.Tensor:
+    """nn.AdaptiveAvgPool2d(1) + flatten on an fp16 activation: -> [N, C] fp32."""
+    N, D, H, W, C = a.shape
+    out = torch.empty((N, C), dtype=torch.float32, device=a.device)
+    L = _lib.load()
+    _lib.check(L.mp_global_avgpool_cl_f16(_p(a.h16), _p(out), N, D * H * W, C, _stream()), "mp_global_avgpool_cl_f16")
     _count()
     return out
 

@@ -23,16 +23,24 @@ def _split(x):
     return hi, lo
 
 
+def _f16(x):
+    return x.clamp(-65504.0, 65504.0).to(torch.float16)
+
+
 def _val(a: Act) -> torch.Tensor:
-    return a.f32 if a.f32 is not None else a.hi.float() + a.lo.float()
+    if a.f32 is not None:
+        return a.f32
+    return a.h16.float() if a.hi is None else a.hi.float() + a.lo.float()
 
 
-def _mk(x: torch.Tensor, f32: bool, split: bool) -> Act:
+def _mk(x: torch.Tensor, f32: bool, split: bool, h16: bool = False) -> Act:
     a = Act(tuple(x.shape))
     if f32:
         a.f32 = x.contiguous()
     if split:
         a.hi, a.lo = _split(x.contiguous())
+    if h16:
+        a.h16 = _f16(x.contiguous())
     return a
 
 
@@ -137,11 +145,19 @@ def affine_act(a, ab, res=None, act=ops.ACT_NONE, f32=False, split=True):
 
 
 def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=0, mode=None, stride=1, in_c_off=0,
-         out=None, out_c_off=0):
-    ensure_split(a)
-    x = _to_ncdhw(a.hi.float() + a.lo.float())[:, in_c_off:in_c_off + pw.Cin]
+         out=None, out_c_off=0, h16=False):
+    half = pw.prec == ops.PREC_F16X2
     kd, kh, kw = pw.k
-    w = (pw.w_hi.float() + pw.w_lo.float())[: pw.Cout].view(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3)
+    if half:     # two-pass fp16: one fp16 activation plane, fp16 hi + scaled fp16 lo weights
+        assert a.h16 is not None and not split and not stats_groups
+        x = _to_ncdhw(a.h16.float())[:, in_c_off:in_c_off + pw.Cin]
+        wf = pw.w_hi.float() + pw.w_lo.float() / ops.F16_LO_SCALE
+    else:
+        assert not h16
+        ensure_split(a)
+        x = _to_ncdhw(a.hi.float() + a.lo.float())[:, in_c_off:in_c_off + pw.Cin]
+        wf = pw.w_hi.float() + pw.w_lo.float()
+    w = wf[: pw.Cout].view(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3)
     y = F.conv3d(x, w.contiguous(), pw.bias, stride=(1, stride, stride), padding=(kd // 2, kh // 2, kw // 2))
     v = _to_cl(y)
     if res is not None:
@@ -156,18 +172,39 @@ def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=
             h, l = _split(v)
             out.hi[..., out_c_off:out_c_off + pw.Cout] = h
             out.lo[..., out_c_off:out_c_off + pw.Cout] = l
+        if out.h16 is not None:
+            out.h16[..., out_c_off:out_c_off + pw.Cout] = _f16(v)
         return out, st
-    return _mk(v, f32, split), st
+    return _mk(v, f32, split, h16), st
 
 
-def _alloc(shape, device, f32, split):
+def _alloc(shape, device, f32, split, h16=False):
     a = Act(shape)
     if f32:
         a.f32 = torch.zeros(shape)
     if split:
         a.hi = torch.zeros(shape, dtype=torch.bfloat16)
         a.lo = torch.zeros(shape, dtype=torch.bfloat16)
+    if h16:
+        a.h16 = torch.zeros(shape, dtype=torch.float16)
     return a
+
+
+def im2col3x3_f16(x, stride=1):
+    N, C, H, W = x.shape
+    cols = F.unfold(x, 3, padding=1, stride=stride)                     # [N, C*9, L], row c*9 + kh*3 + kw
+    cols = cols.view(N, C, 9, H // stride, W // stride).permute(0, 3, 4, 2, 1).reshape(N, H // stride, W // stride, 9 * C)
+    cols = F.pad(cols, (0, 32 - 9 * C)).unsqueeze(1)                    # channel (kh*3+kw)*C + c, zero-padded to 32
+    return _mk(cols, False, False, True)
+
+
+def maxpool3x3s2_f16(a):
+    y = F.max_pool2d(_to_ncdhw(a.h16.float()).squeeze(2), 3, 2, 1).unsqueeze(2)
+    return _mk(_to_cl(y), False, False, True)
+
+
+def global_avgpool_f16(a):
+    return a.h16.float().mean(dim=(1, 2, 3))
 
 
 def maxpool3x3s2(a):
@@ -231,7 +268,8 @@ def blur_subsample(x, kernel2d, step):
 
 _NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
-          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3", "from_nchw_pad16"]
+          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3", "from_nchw_pad16",
+          "im2col3x3_f16", "maxpool3x3s2_f16", "global_avgpool_f16"]
 
 
 @contextlib.contextmanager

@@ -82,5 +82,5 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(so, name), f"libmpb200.so does not export {name}"
     assert set(lib.EXPORTS) == declared
-    assert lib.load().mp_abi_version() == 2
-    assert ctypes.sizeof(lib.ConvDesc) == 12 * 8 + 18 * 4   # 17 ints + tail padding
+    assert lib.load().mp_abi_version() == lib.ABI_VERSION == 3
+    assert ctypes.sizeof(lib.ConvDesc) == 12 * 8 + 18 * 4   # 12 pointers + 18 ints

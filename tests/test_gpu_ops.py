@@ -376,3 +376,118 @@ def test_rgb_pad16_layout(ops):
     assert torch.equal(a.hi.float().cpu()[..., :3], x.permute(0, 2, 3, 1).unsqueeze(1).to(torch.bfloat16).float())
     assert (v[..., :3] - x.permute(0, 2, 3, 1).unsqueeze(1)).abs().max().item() <= 2.0 ** -16 * x.abs().max().item()
     assert (v[..., 3:] == 0).all()
+
+
+# ----------------------------------------------------------------------------------------------------- ABI v3: fp16 two-pass
+def _f16(x):
+    return x.clamp(-65504.0, 65504.0).to(torch.float16)
+
+
+def _h16_act(ops, x):
+    """NCDHW fp32 -> Act holding one fp16 plane (values rounded on the host: the kernels under test consume it as is)."""
+    cl = x.permute(0, 2, 3, 4, 1).contiguous()
+    return ops.Act(tuple(cl.shape), h16=_f16(cl).to(DEV))
+
+
+F16X2_CASES = [
+    # name,          N, Cin, Cout, H,   W,  k, stride, in_C, in_off, residual
+    ("stem_1x1_k32", 2, 32,  128,  256, 256, 1, 1, 32, 0,   False),   # im2col stem: weight-resident persistent kernel
+    ("slab_64_win",  2, 64,  64,   64,  64, 3, 1, 128, 64,  True),    # slab kernel, channel windows, fp16 residual
+    ("slab_128",     1, 128, 128,  32,  32, 3, 1, 128, 0,   True),
+    ("s2_3x3",       2, 64,  128,  64,  64, 3, 2, 128, 64,  False),   # stride 2 through TMA element strides
+    ("s2_1x1_ds",    2, 128, 256,  32,  32, 1, 2, 128, 0,   False),   # down-sample shortcut
+    ("wide_512",     2, 256, 512,  16,  16, 3, 1, 256, 0,   True),    # four N tiles of 128
+    ("tail_2048",    1, 512, 2048, 32,  32, 3, 2, 512, 0,   False),   # RepVGG last stage
+    ("c16",          1, 16,  48,   16,  16, 3, 1, 16,  0,   False),   # 32-byte swizzle rows, padded Cout
+]
+
+
+@pytest.mark.parametrize("case", F16X2_CASES, ids=[c[0] for c in F16X2_CASES])
+def test_conv_f16x2(ops, case):
+    name, N, Cin, Cout, H, W, k, stride, in_C, in_off, with_res = case
+    x = rnd(N, in_C, 1, H, W, seed=21) * 1.5
+    w = rnd(Cout, Cin, k, k, seed=22) / math.sqrt(Cin * k * k)
+    b = rnd(Cout, seed=23) * 0.1
+    a = _h16_act(ops, x)
+    pw = ops.pack_conv(w, b, DEV, prec=ops.PREC_F16X2)
+    assert pw.w_hi.dtype == torch.float16 and pw.prec == ops.PREC_F16X2
+    # the kernel's exact operands: fp16(x) and w_hi + w_lo / 2048 (within 2^-21 of w)
+    wq = (pw.w_hi.float() + pw.w_lo.float() / ops.F16_LO_SCALE).cpu()[:Cout].view(Cout, 1, k, k, Cin).permute(0, 4, 1, 2, 3)
+    assert (wq.squeeze(2) - w).abs().max().item() <= w.abs().max().item() * 2.0 ** -20
+    xq = _f16(x).float()[:, in_off:in_off + Cin]
+    ref = F.conv3d(xq, wq.contiguous(), b, stride=(1, stride, stride), padding=(0, k // 2, k // 2))
+    res = None
+    if with_res:
+        r = rnd(N, Cout, 1, H // stride, W // stride, seed=24)
+        res = _h16_act(ops, r)
+        ref = ref + _f16(r).float()
+    ref = F.relu(ref)
+    out, st = ops.conv(a, pw, res=res, act=ops.ACT_RELU, f32=True, h16=True, stride=stride, in_c_off=in_off, mode="tc")
+    torch.cuda.synchronize()
+    assert st is None and out.hi is None and out.h16.dtype == torch.float16
+    got = cl_to_ncdhw(out.f32.cpu())
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() / scale < 2e-5, name
+    # the fp16 plane is the round-to-nearest image of the fp32 result
+    assert torch.equal(out.h16.cpu(), _f16(out.f32.cpu()))
+    # against the un-rounded problem the error is the 11-bit activation rounding only
+    full = F.conv3d(x[:, in_off:in_off + Cin], w.unsqueeze(2), b, stride=(1, stride, stride), padding=(0, k // 2, k // 2))
+    if with_res:
+        full = full + r
+    assert (got - F.relu(full)).abs().max().item() / scale < 1e-3
+
+
+def test_conv_f16x2_output_window_and_errors(ops):
+    # grouped convolution through channel windows, fp16 in / fp16 out (RepVGG even layers)
+    N, C, H, W, g = 2, 128, 32, 32, 2
+    x = rnd(N, C, 1, H, W, seed=31)
+    w = rnd(C, C // g, 3, 3, seed=32) / math.sqrt(C // g * 9)
+    b = rnd(C, seed=33) * 0.1
+    a = _h16_act(ops, x)
+    out = ops._alloc((N, 1, H, W, C), DEV, False, False, True)
+    cg = C // g
+    for i in range(g):
+        pw = ops.pack_conv(w[i * cg:(i + 1) * cg], b[i * cg:(i + 1) * cg], DEV, prec=ops.PREC_F16X2)
+        ops.conv(a, pw, act=ops.ACT_RELU, in_c_off=i * cg, out=out, out_c_off=i * cg)
+    ref = F.relu(F.conv2d(_f16(x).float().squeeze(2), w, b, padding=1, groups=g))
+    got = out.h16.float().cpu().squeeze(1).permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 6e-4      # fp16 output rounding (2^-11)
+    # contract violations surface as RuntimeError, never as a silent fallback
+    pw = ops.pack_conv(w[:cg], b[:cg], DEV, prec=ops.PREC_F16X2)
+    with pytest.raises(RuntimeError, match="fp16 activation plane"):
+        ops.conv(ops.from_nchw(x.to(DEV)), pw)
+    with pytest.raises(RuntimeError, match="PREC_F16X2"):
+        ops.conv(a, pw, stats_groups=32)
+    with pytest.raises(RuntimeError, match="PREC_F16X2 convolutions only"):
+        ops.conv(ops.from_nchw(x.to(DEV)), ops.pack_conv(w[:cg, :, :, :].repeat(1, 2, 1, 1), None, DEV), h16=True)
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+@pytest.mark.parametrize("H,W", [(40, 56), (32, 64)], ids=["ragged", "tiled"])
+def test_im2col_stem_matches_conv3x3(ops, stride, H, W):
+    N, Co = 3, 64
+    x = torch.rand(N, 3, H, W, generator=torch.Generator().manual_seed(41))
+    w = rnd(Co, 3, 3, 3, seed=42) / math.sqrt(27)
+    b = rnd(Co, seed=43) * 0.1
+    p = ops.im2col3x3_f16(x.to(DEV), stride)
+    assert p.shape == (N, 1, H // stride, W // stride, 32)
+    cols = F.unfold(x, 3, padding=1, stride=stride).view(N, 3, 9, H // stride, W // stride).permute(0, 3, 4, 2, 1)
+    exp = F.pad(cols.reshape(N, H // stride, W // stride, 27), (0, 5))
+    assert torch.equal(p.h16.cpu().squeeze(1), _f16(exp))
+    pw = ops.pack_stem3x3_f16(w, b, DEV)
+    assert pw.Cin == 32 and pw.k == (1, 1, 1)
+    if (H // stride) * (W // stride) % 128 == 0:
+        out, _ = ops.conv(p, pw, act=ops.ACT_RELU, f32=True, h16=True, mode="tc")
+        ref = F.relu(F.conv2d(_f16(x).float(), w, b, stride=stride, padding=1))
+        got = out.f32.cpu().squeeze(1).permute(0, 3, 1, 2)
+        assert (got - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+def test_maxpool_and_global_avgpool_f16(ops):
+    x = rnd(3, 64, 1, 36, 52, seed=51)
+    a = _h16_act(ops, x)
+    xq = _f16(x).float().squeeze(2)
+    mp = ops.maxpool3x3s2_f16(a)
+    assert torch.equal(mp.h16.float().cpu().squeeze(1).permute(0, 3, 1, 2), F.max_pool2d(xq, 3, 2, 1))
+    gap = ops.global_avgpool_f16(a).cpu()
+    assert (gap - xq.mean(dim=(2, 3))).abs().max().item() < 1e-5

@@ -37,6 +37,11 @@ def test_pipeline_wiring_against_oracle(setup, seeded_sd):
     assert rel(v(src["vc2d"]), st["vc2d"]) < 1e-4
     assert rel(v(drv["projected"]).squeeze(2), st["projected"]) < 1e-4
     assert rel(w, st["w_c2d"]) < 1e-4
+    # motion encoder on the two-pass fp16 plans (im2col stems, fp16 activation planes): pooled outputs stay fp32-grade
+    for k in ("Rs", "ts", "zs"):
+        assert rel(src[k], st[k]) < 1e-4, k
+    for k in ("Rd", "td", "zd"):
+        assert rel(drv[k], st[k]) < 1e-4, k
     # split-bf16 (3-pass) operand format keeps RGB ~40x inside the 1e-3 budget
     assert (rgb - rgb_o).abs().max().item() < 1e-4
     assert (pyr["prediction_0.25"] - pyr_o["prediction_0.25"]).abs().max().item() < 1e-4
