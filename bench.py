@@ -319,6 +319,13 @@ def run_b200(args):
                 "avg_launch_ms": c["ms"] / c["n"], "share_of_step": c["ms"] / step_ms,
                 "algorithmic_gflop_per_launch": c["flops"] / c["n"] / 1e9}
     extra = {}
+    if "conv_tc_h" in agg:     # two-pass fp16 convolutions of the motion-encoder trunks
+        c = agg["conv_tc_h"]
+        ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+        extra["conv_tc_f16x2"] = {"kernel": "k_conv_tc2/3, MP_PREC_F16X2 (Emtn trunks)", "bound": "tensor", "achieved": ach,
+                                  "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                                  "mma_passes": 2, "raw_tensor_frac": 2 * ach / pk["tf_sustained"], "launches": c["n"],
+                                  "ms": c["ms"], "share_of_step": c["ms"] / step_ms}
     for kind in ("warp_fused_sum", "warp_fused", "conv_simt"):
         if kind in agg:
             c = agg[kind]
@@ -344,7 +351,8 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16x3 split (fp32-grade products: hi*hi+hi*lo+lo*hi, fp32 accumulate in TMEM)",
+        "vs_baseline": None, "dtype": "bf16x3 split (fp32-grade products: hi*hi+hi*lo+lo*hi, fp32 accumulate in TMEM); motion-encoder trunks: "
+                                    "fp16x2 (fp16 activations x fp16 hi+lo weights, fp32 accumulate)",
         "data": "synthetic",
         "config": {"workload": f"Gbase inference, 1 src x {B} drv per GPU, 512x512 (BASELINE config "
                                f"{'2' if world == 1 else '3 share'}); source re-encoded every step",

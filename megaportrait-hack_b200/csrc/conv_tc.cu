@@ -1161,7 +1161,9 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
       p.total_tiles = pl.tiles_m;
       return true;
     };
-    const bool mt2_ok = d->H % 32 == 0 && mt_cap >= 2 && 2 * 2 * bn <= 512;
+    // fp16 two-pass mode always uses the [Bh|Bl] accumulator layout (2*bn TMEM columns per accumulator, two tiles in
+    // flight), so two accumulators per weight tile fit only up to bn = 64
+    const bool mt2_ok = d->H % 32 == 0 && mt_cap >= 2 && 2 * 2 * bn <= 512 && (!f16x2 || 2 * 2 * 2 * bn <= 512);
     choose(mt2_ok ? 2 : 1);
   }
   if (pl.slab) {
