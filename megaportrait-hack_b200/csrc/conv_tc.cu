@@ -62,6 +62,11 @@ struct TcParams {
   int prec;                   // MP_PREC_SPLIT_BF16 | MP_PREC_F16X2 (single fp16 activation plane, fp16 hi / scaled-lo weights)
   uint32_t a_planes;          // activation planes per stage: 2 (hi, lo) or 1 (fp16)
   float lo_scale;             // weight of the [Bl] column half in the epilogue: 1 (bf16 split) or 2^-11 (fp16 scaled lo)
+  int epi_tma;                // 1: fp16 output tile staged in swizzled shared memory and written by TMA bulk stores
+  uint32_t tma_off;           // byte offset (1024-aligned) of the two TMA staging buffers
+  uint32_t tma_buf_bytes;     // one staging buffer: (BN / 64) sub-tiles of [128 rows][64 fp16] = 16 KB each
+  uint32_t tma_nbuf;          // 1 or 2 staging buffers
+  uint32_t epi_bytes;         // size of the register-store staging area (0 when the TMA-store epilogue is used)
 };
 
 struct __align__(16) bf16x8 {
@@ -114,6 +119,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// ---- TMA bulk store (shared -> global) of a 5-D box, bulk-group completion
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo, uint32_t layout_type) {
   // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
@@ -417,6 +434,69 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
   }
 }
 
+// fp16 two-pass epilogue, TMA-store flavour: the warp owning TMEM lane quarter q and column-block parity `half`
+// drains 32-column blocks of one 128 x BN accumulator -- [Bh] + 2^-11 [Bl] + bias (+ fp16 residual), activation,
+// round to fp16 -- into a 128B-swizzled staging tile ((BN/64) sub-tiles of [128 rows][64 fp16]) that one thread then
+// writes to HBM with TMA bulk stores.  No per-thread global stores, no barrier inside the column loop.
+__device__ __forceinline__ void epilogue_stage_h(const TcParams& p, uint32_t stage, uint32_t tmem_acc, int n0,
+                                                 int64_t obase, int half, int r, bool row_valid) {
+  const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+  const f16* res = reinterpret_cast<const f16*>(p.res_hi);
+  for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+    float v[32], v2[32];
+    tmem_ld32(tmem_acc + (uint32_t)c0, v);
+    tmem_ld32(tmem_acc + (uint32_t)(p.BN + c0), v2);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(v2[i], p.lo_scale, v[i]);
+    const int co0 = n0 + c0;
+    if (bias_vec) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + i));
+        v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+      }
+    } else if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + co0 + i);
+    }
+    if (res && row_valid) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(res + obase + co0 + i);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(h2[k]);
+          v[i + 2 * k] += f.x; v[i + 2 * k + 1] += f.y;
+        }
+      }
+    }
+    if (p.act == MP_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (p.act != MP_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = mp_apply_act(v[i], p.act);
+    }
+    // 32 columns = four 16-byte chunks of this row; chunk index XOR (row & 7) = the 128B TMA swizzle
+    const uint32_t sub = stage + (uint32_t)(c0 >> 6) * 16384u + (uint32_t)r * 128u;
+    const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __half2 h = __floats2half2_rn(fminf(fmaxf(v[8 * j + 2 * k], -65504.f), 65504.f),
+                                            fminf(fmaxf(v[8 * j + 2 * k + 1], -65504.f), 65504.f));
+        w[k] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      const uint32_t addr = sub + (((ch0 + (uint32_t)j) ^ ((uint32_t)r & 7u)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                   : "memory");
+    }
+  }
+}
+
 __device__ __forceinline__ void epilogue_flush_stats(const TcParams& p, double* s_stats, int n, int n0, int et) {
   epi_bar();   // the last chunk's fixed-order slab reduction (threads 0..31) must have landed
   const int cpg = p.gn_groups > 0 ? p.Cout / p.gn_groups : 1;
@@ -439,13 +519,14 @@ __device__ __forceinline__ void epilogue_flush_stats(const TcParams& p, double* 
 // chunks in shared memory (padded rows) and writes them out with warp-contiguous 16-byte stores.
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+           const __grid_constant__ CUtensorMap map_out, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   float* epi = reinterpret_cast<float*>(gen_base + p.epi_off);                    // [128][EPI_PITCH]
   long long* row_off = reinterpret_cast<long long*>(gen_base + p.epi_off + TILE_M * EPI_PITCH * 4);   // [128]
-  const uint32_t bars = smem_base + p.epi_off + EPI_BYTES;   // full[S], empty[S], tmem_full[2], tmem_empty[2], bres
+  const uint32_t bars = smem_base + p.epi_off + p.epi_bytes;   // full[S], empty[S], tmem_full[2], tmem_empty[2], bres
   const uint32_t bres_bar = bars + (2 * p.STAGES + 4) * 8;
   const uint32_t tmem_slot = bars + (2 * p.STAGES + 5) * 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
@@ -586,6 +667,27 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       const int64_t obase = pos * p.out_C + p.out_c_off;
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (p.epi_tma) {
+        const uint32_t stage = smem_base + p.tma_off + (p.tma_nbuf == 2 ? b : 0u) * p.tma_buf_bytes;
+        if (et == 0) {                         // the bulk store that last read this staging buffer has drained it
+          if (p.tma_nbuf == 2) bulk_wait_read<1>();
+          else bulk_wait_read<0>();
+        }
+        epi_bar();
+        epilogue_stage_h(p, stage, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.acc_w), n0, obase, half, r,
+                         row_valid);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(b));
+        fence_proxy_async();                   // generic-proxy staging writes -> visible to the TMA engine
+        epi_bar();
+        if (et == 0) {
+          for (int sub = 0; sub < (p.BN >> 6); ++sub)
+            tma_store_5d(&map_out, stage + (uint32_t)sub * 16384u, p.out_c_off + n0 + sub * 64, w0, h0, d0, n);
+          bulk_commit();
+        }
+        continue;
+      }
       epilogue_drain(p, epi, row_off, s_stats, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.acc_w), n0,
                      obase, half, r, et, lane, row_valid);
       // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -594,6 +696,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       if (lane == 0) mbar_arrive(tempty_bar(b));
       if (p.stats) epilogue_flush_stats(p, s_stats, n, n0, et);
     }
+    if (p.epi_tma && et == 0) bulk_wait_all();   // outstanding bulk stores must finish reading shared memory
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -620,15 +723,15 @@ struct SlabExtra {
 
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p,
-           const SlabExtra x) {
+           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+           const __grid_constant__ CUtensorMap map_out, const TcParams p, const SlabExtra x) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   float* epi = reinterpret_cast<float*>(gen_base + p.epi_off);
   long long* row_off = reinterpret_cast<long long*>(gen_base + p.epi_off + TILE_M * EPI_PITCH * 4);
   // barriers: fullA[SA], emptyA[SA], fullB[SB], emptyB[SB], tmem_full[2], tmem_empty[2]
-  const uint32_t bars = smem_base + p.epi_off + EPI_BYTES;
+  const uint32_t bars = smem_base + p.epi_off + p.epi_bytes;
   auto fullA = [&](int i) { return bars + i * 8; };
   auto emptyA = [&](int i) { return bars + (x.SA + i) * 8; };
   auto fullB = [&](int i) { return bars + (2 * x.SA + i) * 8; };
@@ -753,7 +856,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int et = threadIdx.x - 64;
-    uint32_t it = 0;
+    uint32_t it = 0, se = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int n, d0, h0, w0, n0;
       tile_coords(tile, n, d0, h0, w0, n0);
@@ -763,15 +866,33 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       for (int t = 0; t < x.MT; ++t) {
         const int ww = r % p.BW, hh = r / p.BW;
         const int64_t pos = (((int64_t)n * p.D + d0) * p.H + h0 + t * p.BH + hh) * p.W + w0 + ww;
-        epilogue_drain(p, epi, row_off, s_stats,
-                       tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * x.MT + t) * p.acc_w), n0,
-                       pos * p.out_C + p.out_c_off, half, r, et, lane);
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * x.MT + t) * p.acc_w);
+        if (p.epi_tma) {
+          const uint32_t stage = smem_base + p.tma_off + (p.tma_nbuf == 2 ? (se & 1u) : 0u) * p.tma_buf_bytes;
+          ++se;
+          if (et == 0) {
+            if (p.tma_nbuf == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
+          epi_bar();
+          epilogue_stage_h(p, stage, tacc, n0, pos * p.out_C + p.out_c_off, half, r, true);
+          fence_proxy_async();
+          epi_bar();
+          if (et == 0) {
+            for (int sub = 0; sub < (p.BN >> 6); ++sub)
+              tma_store_5d(&map_out, stage + (uint32_t)sub * 16384u, p.out_c_off + n0 + sub * 64, w0, h0 + t * p.BH, d0, n);
+            bulk_commit();
+          }
+        } else {
+          epilogue_drain(p, epi, row_off, s_stats, tacc, n0, pos * p.out_C + p.out_c_off, half, r, et, lane);
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(b));
       if (p.stats) epilogue_flush_stats(p, s_stats, n, n0, et);
     }
+    if (p.epi_tma && et == 0) bulk_wait_all();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -1021,6 +1142,21 @@ bool use_v1() {
   return v != 0;
 }
 
+bool allow_tma_epi() {
+  static int v = [] { const char* e = getenv("MPB200_TC_NO_TMA_EPI"); return (e && atoi(e)) ? 0 : 1; }();
+  return v != 0;
+}
+
+// TMA-store epilogue: fp16 output plane only, whole 64-channel sub-tiles, 16-byte aligned channel windows
+bool tma_epi_ok(const mp_conv_desc* d, int bn) {
+  const int out_C = d->out_C > 0 ? d->out_C : d->Cout;
+  // worth it where the epilogue, not the main loop, bounds a tile: K = taps*Cin up to 1152
+  if ((int64_t)d->KD * d->KH * d->KW * d->Cin > 1152) return false;
+  return allow_tma_epi() && d->prec == MP_PREC_F16X2 && d->out_hi && !d->out_f32 && !d->stats && bn % 64 == 0 &&
+         d->Cout == d->Cout_pad && out_C % 8 == 0 && d->out_c_off % 8 == 0 &&
+         (!d->res_hi || (reinterpret_cast<uintptr_t>(d->res_hi) & 15) == 0) && !d->res_f32;
+}
+
 int g_num_sms[64] = {0};
 
 int next_pow2(int v) { int r = 32; while (r < v) r <<= 1; return r; }
@@ -1101,8 +1237,11 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     return fail("v1 kernel has no stride / channel-window support");
   if (!pl.v1 && allow_slab && p.stride == 1 && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) &&
       d->Cout_pad <= 128 && d->W % 8 == 0 && d->H % 16 == 0) {
-    const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + 2048 /*s_part*/ + EPI_BYTES;
     const int bn = d->Cout_pad;
+    const bool tma_s = tma_epi_ok(d, bn);
+    const uint32_t nbuf_s = bn <= 64 ? 2u : 1u;      // 32 KB of staging either way
+    const uint32_t tma_bytes_s = tma_s ? nbuf_s * (uint32_t)(bn / 64) * 16384u + 1024u /*alignment*/ : 0u;
+    const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + 2048 /*s_part*/ + (tma_s ? 0u : EPI_BYTES) + tma_bytes_s;
     static int mt_cap = [] { const char* e = getenv("MPB200_TC_SLAB_MT"); return e ? atoi(e) : 2; }();
     static int cc_force = [] { const char* e = getenv("MPB200_TC_SLAB_CC"); return e ? atoi(e) : 0; }();
     static int sb_want = [] { const char* e = getenv("MPB200_TC_SLAB_SB"); int v = e ? atoi(e) : 3; return v < 2 ? 2 : v; }();
@@ -1152,8 +1291,13 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
       p.STAGES = sa;
       p.b_resident = 0;
       p.bres_off = 0;
-      p.epi_off = pl.x.b_ring_off + sb * b_stage;
-      pl.smem_bytes = fixed_s + p.epi_off;
+      p.epi_tma = tma_s ? 1 : 0;
+      p.tma_off = (pl.x.b_ring_off + sb * b_stage + 1023u) & ~1023u;
+      p.tma_buf_bytes = tma_s ? (uint32_t)(bn / 64) * 16384u : 0u;
+      p.tma_nbuf = nbuf_s;
+      p.epi_bytes = tma_s ? 0u : EPI_BYTES;
+      p.epi_off = tma_s ? p.tma_off + p.tma_nbuf * p.tma_buf_bytes : pl.x.b_ring_off + sb * b_stage;
+      pl.smem_bytes = fixed_s + pl.x.b_ring_off + sb * b_stage;
       p.dualb = ((allow_dual() || f16x2) && 2 * mt * 2 * bn <= 512) ? 1 : 0;
       p.acc_w = p.dualb ? 2 * bn : bn;
       p.tmem_cols = next_pow2(2 * mt * p.acc_w);
@@ -1178,8 +1322,12 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     p.S = (int64_t)d->D * Ho * Wo;
     return 0;
   }
+  const bool tma_g = !pl.v1 && tma_epi_ok(d, p.BN);
+  // two staging buffers where shared memory is plentiful (narrow tiles, tiny K); one otherwise
+  const uint32_t nbuf_g = (p.BN <= 64 || (int64_t)d->KD * d->KH * d->KW * d->Cin <= 128) ? 2u : 1u;
+  const uint32_t tma_bytes_g = tma_g ? nbuf_g * (uint32_t)(p.BN / 64) * 16384u + 1024u /*alignment*/ : 0u;
   const uint32_t fixed = 1024 /*align slack*/ + 1024 /*barriers, tmem slot*/ + 2 * 256 * sizeof(double) +
-                         (pl.v1 ? 0 : EPI_BYTES + 2048 /*s_part*/);
+                         (pl.v1 ? 0 : (tma_g ? 0u : EPI_BYTES) + 2048 /*s_part*/) + tma_bytes_g;
   // weight-resident mode: one N tile and the whole [taps*Cin x BN] weight tile (hi+lo) fits beside >= 3 A stages;
   // try the widest channel chunk first, then narrower ones (smaller A stages).
   static int allow_res = [] { const char* e = getenv("MPB200_TC_NO_BRES"); return (e && atoi(e)) ? 0 : 1; }();
@@ -1212,7 +1360,12 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.STAGES = stages;
   pl.smem_bytes = fixed + stages * p.stage_bytes + (p.b_resident ? bres_bytes : 0);
   p.bres_off = stages * p.stage_bytes;
-  p.epi_off = p.bres_off + (p.b_resident ? bres_bytes : 0);
+  p.epi_tma = tma_g ? 1 : 0;
+  p.tma_off = (p.bres_off + (p.b_resident ? bres_bytes : 0) + 1023u) & ~1023u;
+  p.tma_buf_bytes = tma_g ? (uint32_t)(p.BN / 64) * 16384u : 0u;
+  p.tma_nbuf = nbuf_g;
+  p.epi_bytes = (tma_g || pl.v1) ? 0u : EPI_BYTES;
+  p.epi_off = tma_g ? p.tma_off + p.tma_nbuf * p.tma_buf_bytes : p.bres_off + (p.b_resident ? bres_bytes : 0);
   p.dualb = (!pl.v1 && (allow_dual() || f16x2) && 2 * 2 * p.BN <= 512) ? 1 : 0;
   if (f16x2 && !p.dualb) return fail("fp16 two-pass mode needs the [Bh|Bl] column layout (BN <= 128)");
   p.acc_w = p.dualb ? 2 * p.BN : p.BN;
@@ -1248,6 +1401,20 @@ int encode_act_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(activation) failed (%d)", (int)r);
 }
 
+// fp16 output plane as a 5-D tensor (C, W, H, D, N) of OUTPUT extents; box = one 64-channel sub-tile of the tile box
+int encode_out_map(CUtensorMap* m, void* ptr, const mp_conv_desc* d, const Plan& pl) {
+  const TcParams& p = pl.p;
+  const cuuint64_t C = (cuuint64_t)p.out_C;
+  cuuint64_t dims[5] = {C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)d->N};
+  cuuint64_t strides[4] = {C * 2, C * 2 * p.W, C * 2 * p.W * p.H, C * 2 * p.W * p.H * p.D};
+  cuuint32_t box[5] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BD, (cuuint32_t)(pl.slab ? 1 : p.BNb)};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = get_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, ptr, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
+}
+
 int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const Plan& pl) {
   const cuuint64_t ktot = (cuuint64_t)d->KD * d->KH * d->KW * d->Cin;
   cuuint64_t dims[2] = {ktot, (cuuint64_t)d->Cout_pad};
@@ -1281,6 +1448,11 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
   if (int e = encode_act_map(&ma_lo, pl.p.a_planes == 2 ? d->in_lo : d->in_hi, d, pl)) return e;   // unused when 1 plane
   if (int e = encode_w_map(&mb_hi, d->w_hi, d, pl)) return e;
   if (int e = encode_w_map(&mb_lo, d->w_lo, d, pl)) return e;
+  CUtensorMap mo = mb_hi;          // placeholder when the kernel stores with ordinary instructions
+  if (pl.p.epi_tma) {
+    MP_REQUIRE((reinterpret_cast<uintptr_t>(d->out_hi) & 15) == 0, "mp_conv_tc: output must be 16-byte aligned");
+    if (int e = encode_out_map(&mo, d->out_hi, d, pl)) return e;
+  }
   {
     static bool attr_done[64] = {false};
     int dev = 0;
@@ -1305,9 +1477,9 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
       int sms = (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) ? g_num_sms[dev] : 148;
       int grid = pl.p.total_tiles < sms ? pl.p.total_tiles : sms;
       if (pl.slab)
-        k_conv_tc3<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p, pl.x);
+        k_conv_tc3<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, pl.p, pl.x);
       else
-        k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p);
+        k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, pl.p);
     }
   }
   MP_LAUNCH_CHECK("mp_conv_tc");

@@ -430,6 +430,11 @@ def test_conv_f16x2(ops, case):
     assert (got - ref).abs().max().item() / scale < 2e-5, name
     # the fp16 plane is the round-to-nearest image of the fp32 result
     assert torch.equal(out.h16.cpu(), _f16(out.f32.cpu()))
+    # fp16-only output: whole 64-channel tiles leave through the TMA-store epilogue (swizzled staging + bulk store),
+    # which must agree bit for bit with the register-store epilogue above
+    out2, _ = ops.conv(a, pw, res=res, act=ops.ACT_RELU, f32=False, h16=True, stride=stride, in_c_off=in_off, mode="tc")
+    torch.cuda.synchronize()
+    assert out2.f32 is None and torch.equal(out2.h16.cpu(), out.h16.cpu()), name
     # against the un-rounded problem the error is the 11-bit activation rounding only
     full = F.conv3d(x[:, in_off:in_off + Cin], w.unsqueeze(2), b, stride=(1, stride, stride), padding=(0, k // 2, k // 2))
     if with_res:
@@ -449,6 +454,7 @@ def test_conv_f16x2_output_window_and_errors(ops):
     for i in range(g):
         pw = ops.pack_conv(w[i * cg:(i + 1) * cg], b[i * cg:(i + 1) * cg], DEV, prec=ops.PREC_F16X2)
         ops.conv(a, pw, act=ops.ACT_RELU, in_c_off=i * cg, out=out, out_c_off=i * cg)
+    torch.cuda.synchronize()
     ref = F.relu(F.conv2d(_f16(x).float().squeeze(2), w, b, padding=1, groups=g))
     got = out.h16.float().cpu().squeeze(1).permute(0, 3, 1, 2)
     assert (got - ref).abs().max().item() / ref.abs().max().item() < 6e-4      # fp16 output rounding (2^-11)

@@ -55,6 +55,22 @@ def conv_case(name, N, Cin, Cout, D, H, W, k, reps, mode="tc", act=ops.ACT_RELU,
           f"(raw bf16 x3 {3 * fl / best / 1e9:8.1f})", flush=True)
 
 
+def conv_case_h(name, N, Cin, Cout, H, W, k, reps, stride=1, res=False):
+    """MP_PREC_F16X2 convolution (fp16 activation plane in / out) at a motion-encoder shape."""
+    g = torch.Generator().manual_seed(0)
+    a = ops.Act((N, 1, H, W, Cin), h16=torch.randn(N, 1, H, W, Cin, generator=g).to(DEV).half())
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    pw = ops.pack_conv(w, torch.zeros(Cout), DEV, prec=ops.PREC_F16X2)
+    r = ops.Act((N, 1, H // stride, W // stride, Cout),
+                h16=torch.randn(N, 1, H // stride, W // stride, Cout, generator=g).to(DEV).half()) if res else None
+    fn = lambda: ops.conv(a, pw, res=r, act=ops.ACT_RELU, f32=False, h16=True, stride=stride, mode="tc")
+    best, avg = timeit(fn, reps)
+    fl = 2.0 * N * (H // stride) * (W // stride) * Cout * Cin * k * k
+    by = N * H * W * Cin * 2 + N * (H // stride) * (W // stride) * Cout * 2 * (2 if res else 1)
+    print(f"{name:28s} f16x2: best {best:8.3f} ms avg {avg:8.3f} ms  useful {fl / best / 1e9:8.1f} TFLOP/s "
+          f"(raw x2 {2 * fl / best / 1e9:8.1f})  activations {by / best / 1e6:8.1f} GB/s", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
@@ -83,6 +99,12 @@ def main():
         conv_case("g2d_up2_256to128_b32", 32, 256, 128, 1, 256, 256, (1, 3, 3), r)
         conv_case("r18_64_256x256_b32", 32, 64, 64, 1, 256, 256, (1, 3, 3), r)
         conv_case("vol96_16x64x64_b1", 1, 96, 96, 16, 64, 64, (3, 3, 3), r, split_out=False, act=ops.ACT_NONE)
+    if sel("f16"):
+        conv_case_h("emtn_stem_k32_512_b32", 32, 32, 128, 512, 512, 1, r)
+        conv_case_h("r18_64_256x256_b32_h", 32, 64, 64, 256, 256, 3, r)
+        conv_case_h("r18_64_256x256_b32_h_res", 32, 64, 64, 256, 256, 3, r, res=True)
+        conv_case_h("r18_128_128x128_b32_h", 32, 128, 128, 128, 128, 3, r)
+        conv_case_h("r18_512_32x32_b32_h", 32, 512, 512, 32, 32, 3, r)
     if sel("simt"):
         conv_case("g2d_512_64x64_b4", 4, 512, 512, 1, 64, 64, (1, 3, 3), r, mode="simt")
     if sel("warp"):
