@@ -175,6 +175,13 @@ int mp_warp_fused_cl(const float* v, const float* em_cl, const float* theta, flo
 int mp_tap_sum3x3_cl(const float* y, const float* bias, float* out, int N, int H, int W, int Co, int Ct, int act,
                      void* stream);
 
+/* G2d output head fused into one pass (model.py:748-751): GroupNorm(32,64) -> ReLU -> Conv2d(64,3,3,pad 1) -> act.
+ * x [N,H,W,Cin] CL fp32 (the last decoder block's output), ab [N][Cin][2] from mp_gn_finalize, weight_host [Cout][Cin][3][3]
+ * and bias_host [Cout] (may be NULL) are HOST pointers (the weights travel as kernel parameters), out [N,Cout,H,W] NCHW
+ * fp32.  Cin = 64, Cout = 3.  fp32 FMA arithmetic. */
+int mp_gn_relu_conv3x3_head(const float* x, const float* ab, const float* weight_host, const float* bias_host, float* out,
+                            int N, int H, int W, int Cin, int Cout, int act, void* stream);
+
 /* ---------------------------------------------------------------- image pyramid ----------------------------- */
 /* AntiAliasInterpolation2d (model.py:683-691): zero-pad, depthwise ks x ks filter, nearest subsample by `step`.
  * x [N,C,H,W] fp32 NCHW, kernel [ks*ks] (same for every channel), out [N,C,H/step,W/step]. */

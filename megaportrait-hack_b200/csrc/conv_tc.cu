@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -67,7 +68,13 @@ struct TcParams {
   uint32_t tma_buf_bytes;     // one staging buffer: (BN / 64) sub-tiles of [128 rows][64 fp16] = 16 KB each
   uint32_t tma_nbuf;          // 1 or 2 staging buffers
   uint32_t epi_bytes;         // size of the register-store staging area (0 when the TMA-store epilogue is used)
+  unsigned int* sched;        // dynamic tile scheduler: {next-tile counter, finished-CTA counter}, or NULL = static walk
 };
+
+constexpr int SQ = 4;         // depth of the in-CTA tile-id queue (producer -> MMA issuer + epilogue warps)
+
+// Global scheduler slots: both words are zero between launches (the last CTA of a launch resets them).
+__device__ unsigned int g_sched[1024][2];
 
 struct __align__(16) bf16x8 {
   bf16 v[8];
@@ -513,6 +520,32 @@ __device__ __forceinline__ void epilogue_flush_stats(const TcParams& p, double* 
   epi_bar();
 }
 
+// ---- tile scheduler.  The TMA producer thread owns the tile sequence of its CTA: the first tile is blockIdx.x, every
+// further one is drawn from a global atomic counter (p.sched) -- so a CTA that starts late, because another stream's
+// kernel still held its SM, simply takes fewer tiles instead of delaying the whole launch -- or, with p.sched == NULL,
+// the static walk blockIdx.x + k*gridDim.x.  Tile ids reach the MMA issuer and the epilogue warps through a small
+// shared-memory queue guarded by mbarriers; -1 ends the walk.
+__device__ __forceinline__ int sched_next(const TcParams& p, int tile) {
+  return p.sched ? (int)(gridDim.x + atomicAdd(p.sched, 1u)) : tile + (int)gridDim.x;
+}
+__device__ __forceinline__ void sched_publish(uint32_t sfull, uint32_t sempty, volatile int* s_tile, uint32_t k, int tile) {
+  const uint32_t slot = k % SQ;
+  mbar_wait(sempty + slot * 8, ((k / SQ) & 1) ^ 1);
+  s_tile[slot] = tile;
+  mbar_arrive(sfull + slot * 8);            // release: the store above is visible to whoever acquires the barrier
+}
+__device__ __forceinline__ int sched_read(uint32_t sfull, volatile int* s_tile, uint32_t k) {
+  const uint32_t slot = k % SQ;
+  mbar_wait(sfull + slot * 8, (k / SQ) & 1);
+  return s_tile[slot];
+}
+__device__ __forceinline__ void sched_finish(const TcParams& p) {
+  if (p.sched) {                            // every CTA draws exactly one out-of-range id, then checks out
+    const unsigned prev = atomicAdd(p.sched + 1, 1u);
+    if (prev == gridDim.x - 1) { p.sched[0] = 0u; p.sched[1] = 0u; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel v2
 // Persistent: grid = min(#tiles, #SMs); every role walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 // TMEM holds TWO accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.  The epilogue stages 32-column
@@ -528,7 +561,9 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   long long* row_off = reinterpret_cast<long long*>(gen_base + p.epi_off + TILE_M * EPI_PITCH * 4);   // [128]
   const uint32_t bars = smem_base + p.epi_off + p.epi_bytes;   // full[S], empty[S], tmem_full[2], tmem_empty[2], bres
   const uint32_t bres_bar = bars + (2 * p.STAGES + 4) * 8;
-  const uint32_t tmem_slot = bars + (2 * p.STAGES + 5) * 8;
+  const uint32_t sfull = bars + (2 * p.STAGES + 5) * 8, sempty = sfull + SQ * 8;       // tile-id queue barriers
+  volatile int* s_tile = reinterpret_cast<volatile int*>(gen_base + (sempty + SQ * 8 - smem_base));
+  const uint32_t tmem_slot = sempty + SQ * 8 + SQ * 4;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
 
@@ -550,6 +585,10 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       mbar_init(tempty_bar(b), 8);      // one arrival per epilogue warp
     }
     mbar_init(bres_bar, 1);
+    for (int i = 0; i < SQ; ++i) {
+      mbar_init(sfull + i * 8, 1);
+      mbar_init(sempty + i * 8, 9);     // the MMA thread + one lane of each epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
@@ -592,7 +631,11 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         }
       }
       const uint32_t tx = p.a_planes * p.a_bytes + (p.b_resident ? 0u : 2 * p.b_bytes);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int tile = blockIdx.x;
+      for (uint32_t tk = 0;; ++tk) {
+        sched_publish(sfull, sempty, s_tile, tk, tile < p.total_tiles ? tile : -1);
+        if (tile >= p.total_tiles) break;
+        const int next_tile = sched_next(p, tile);      // drawn early: the atomic's latency hides behind this tile's loads
         int n, d0, h0, w0, n0;
         tile_coords(tile, n, d0, h0, w0, n0);
         for (int tap = 0; tap < taps; ++tap) {
@@ -614,7 +657,9 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             }
           }
         }
+        tile = next_tile;
       }
+      sched_finish(p);
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -623,7 +668,10 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
       uint32_t kb = 0, it = 0;
       if (p.b_resident && (int)blockIdx.x < p.total_tiles) mbar_wait(bres_bar, 0);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (;; ++it) {
+        const int tile = sched_read(sfull, s_tile, it);
+        mbar_arrive(sempty + (it % SQ) * 8);
+        if (tile < 0) break;
         const uint32_t b = it & 1;
         mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -655,7 +703,11 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     const int r = q * 32 + lane;               // accumulator row == position inside the tile
     const int et = threadIdx.x - 64;           // 0..255
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (;; ++it) {
+      const int tile = sched_read(sfull, s_tile, it);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty + (it % SQ) * 8);
+      if (tile < 0) break;
       int n, d0, h0, w0, n0;
       tile_coords(tile, n, d0, h0, w0, n0);
       const uint32_t b = it & 1;
@@ -738,7 +790,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   auto emptyB = [&](int i) { return bars + (2 * x.SA + x.SB + i) * 8; };
   auto tfull_bar = [&](int b) { return bars + (2 * x.SA + 2 * x.SB + b) * 8; };
   auto tempty_bar = [&](int b) { return bars + (2 * x.SA + 2 * x.SB + 2 + b) * 8; };
-  const uint32_t tmem_slot = bars + (2 * x.SA + 2 * x.SB + 4) * 8;
+  const uint32_t sfull = bars + (2 * x.SA + 2 * x.SB + 4) * 8, sempty = sfull + SQ * 8;   // tile-id queue barriers
+  volatile int* s_tile = reinterpret_cast<volatile int*>(gen_base + (sempty + SQ * 8 - smem_base));
+  const uint32_t tmem_slot = sempty + SQ * 8 + SQ * 4;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));
 
@@ -750,6 +804,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     for (int i = 0; i < x.SA; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), 1); }
     for (int i = 0; i < x.SB; ++i) { mbar_init(fullB(i), 1); mbar_init(emptyB(i), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+    for (int i = 0; i < SQ; ++i) { mbar_init(sfull + i * 8, 1); mbar_init(sempty + i * 8, 9); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
@@ -783,7 +838,11 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     if (lane == 0) {
       const int pd = p.KD / 2, pw = p.KW / 2;
       uint32_t ia = 0, ib = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int tile = blockIdx.x;
+      for (uint32_t tk = 0;; ++tk) {
+        sched_publish(sfull, sempty, s_tile, tk, tile < p.total_tiles ? tile : -1);
+        if (tile >= p.total_tiles) break;
+        const int next_tile = sched_next(p, tile);
         int n, d0, h0, w0, n0;
         tile_coords(tile, n, d0, h0, w0, n0);
         for (int kd = 0; kd < p.KD; ++kd)
@@ -811,7 +870,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
                 tma_load_2d(sb + p.b_bytes, &map_b_lo, fullB(sidx), tap * p.Cin + c0, n0);
               }
             }
+        tile = next_tile;
       }
+      sched_finish(p);
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -819,7 +880,10 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       const int ksteps = p.CCHUNK / 16;
       const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
       uint32_t ia = 0, ib = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (;; ++it) {
+        const int tile = sched_read(sfull, s_tile, it);
+        mbar_arrive(sempty + (it % SQ) * 8);
+        if (tile < 0) break;
         const uint32_t b = it & 1;
         mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -857,7 +921,11 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     const int r = q * 32 + lane;
     const int et = threadIdx.x - 64;
     uint32_t it = 0, se = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (;; ++it) {
+      const int tile = sched_read(sfull, s_tile, it);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty + (it % SQ) * 8);
+      if (tile < 0) break;
       int n, d0, h0, w0, n0;
       tile_coords(tile, n, d0, h0, w0, n0);
       const uint32_t b = it & 1;
@@ -1469,6 +1537,21 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
         attr_done[dev] = true;
         cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
       }
+    }
+    // dynamic tile scheduling (default; MPB200_TC_STATIC=1 restores the static walk): a rotating pool of self-resetting
+    // counter slots, so concurrent launches on different streams never share one
+    static int dyn = [] { const char* e = getenv("MPB200_TC_STATIC"); return (e && atoi(e)) ? 0 : 1; }();
+    pl.p.sched = nullptr;
+    if (dyn && !pl.v1) {
+      static unsigned int* base[64] = {nullptr};
+      static std::atomic<unsigned> next_slot{0};
+      const int di = (dev >= 0 && dev < 64) ? dev : 0;
+      if (!base[di]) {
+        void* sym = nullptr;
+        MP_REQUIRE(cudaGetSymbolAddress(&sym, g_sched) == cudaSuccess, "mp_conv_tc: cannot resolve the scheduler slots");
+        base[di] = static_cast<unsigned int*>(sym);
+      }
+      pl.p.sched = base[di] + 2 * (next_slot.fetch_add(1) % 1024u);
     }
     if (pl.v1) {
       dim3 grid((unsigned)pl.tiles_m, (unsigned)pl.tiles_n);

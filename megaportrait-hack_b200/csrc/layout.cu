@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------ errors / misc
@@ -273,15 +275,88 @@ k_upsample2x_bilinear_split8(const bf16* __restrict__ in_hi, const bf16* __restr
   *reinterpret_cast<bf16x8v*>(out_lo + o) = ol;
 }
 
+// Same operator, one thread = a 2 x 2 block of output pixels x 8 channels.  With align_corners=True the source step is
+// (in-1)/(out-1) < 1/2, so the four outputs draw their taps from a 3 x 3 input patch: 18 loads instead of 32, and the
+// bf16 pair -> fp32 joins (the bulk of the instruction stream: the one-output-per-thread kernel is issue-bound, ncu
+// issue-active 81 %) are done once per patch element.  Tap order and weights are exactly those of the kernel above.
+__global__ void __launch_bounds__(256)
+k_upsample2x_bilinear_split8_2x2(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
+                                 bf16* __restrict__ out_lo, int H, int W, int C) {
+  // grid: x = chunks of (input column j, c8) pairs, y = input row i (output rows 2i, 2i+1), z = sample
+  const int C8 = C >> 3;
+  const int Ho = H * 2, Wo = W * 2;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= W * C8) return;
+  const int j = idx / C8, c8 = idx - j * C8;
+  const int i = blockIdx.y, n = blockIdx.z;
+  int h0a, h1a, h0b, h1b, w0a, w1a, w0b, w1b;
+  float lha, lhb, lwa, lwb;
+  lin_src(2 * i, H, Ho, h0a, h1a, lha);
+  lin_src(2 * i + 1, H, Ho, h0b, h1b, lhb);
+  lin_src(2 * j, W, Wo, w0a, w1a, lwa);
+  lin_src(2 * j + 1, W, Wo, w0b, w1b, lwb);
+  const bool dh = h0b != h0a, dw = w0b != w0a;
+  int rr[3] = {h0a, min(h0a + 1, H - 1), min(h0a + 2, H - 1)};
+  int cc[3] = {w0a, min(w0a + 1, W - 1), min(w0a + 2, W - 1)};
+  float P[3][3][8];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int64_t o = ((((int64_t)n * H + rr[a]) * W + cc[b]) * C8 + c8) * 8;
+      const bf16x8v h = *reinterpret_cast<const bf16x8v*>(in_hi + o), l = *reinterpret_cast<const bf16x8v*>(in_lo + o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) P[a][b][k] = mp_join(h.v[k], l.v[k]);
+    }
+  // rows feeding output row 2i+1: (dh ? rows 1,2 : rows 0,1); same for columns
+  float Q[2][3][8];
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      Q[0][b][k] = dh ? P[1][b][k] : P[0][b][k];
+      Q[1][b][k] = dh ? P[2][b][k] : P[1][b][k];
+    }
+  auto emit = [&](int ho, int wo, const float (*top)[8], const float (*bot)[8], bool shift, float lh, float lw) {
+    // taps (h0,w0), (h0,w1), (h1,w0), (h1,w1) in this order, weights (1-lh)(1-lw), (1-lh)lw, lh(1-lw), lh*lw
+    const float w00 = (1.f - lh) * (1.f - lw), w01 = (1.f - lh) * lw, w10 = lh * (1.f - lw), w11 = lh * lw;
+    bf16x8v oh, ol;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v00 = shift ? top[1][k] : top[0][k], v01 = shift ? top[2][k] : top[1][k];
+      const float v10 = shift ? bot[1][k] : bot[0][k], v11 = shift ? bot[2][k] : bot[1][k];
+      float acc = w00 * v00;
+      acc += w01 * v01;
+      acc += w10 * v10;
+      acc += w11 * v11;
+      mp_split2(acc, oh.v[k], ol.v[k]);
+    }
+    const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C8 + c8) * 8;
+    *reinterpret_cast<bf16x8v*>(out_hi + o) = oh;
+    *reinterpret_cast<bf16x8v*>(out_lo + o) = ol;
+  };
+  emit(2 * i, 2 * j, P[0], P[1], false, lha, lwa);
+  emit(2 * i, 2 * j + 1, P[0], P[1], dw, lha, lwb);
+  emit(2 * i + 1, 2 * j, Q[0], Q[1], false, lhb, lwa);
+  emit(2 * i + 1, 2 * j + 1, Q[0], Q[1], dw, lhb, lwb);
+}
+
 extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out_f32,
                                        void* out_hi, void* out_lo, int N, int D, int H, int W, int C, int up_d,
                                        void* stream) {
   MP_REQUIRE((in_f32 || (in_hi && in_lo)) && (out_f32 || (out_hi && out_lo)), "mp_upsample2x_linear_cl: null pointer");
   MP_REQUIRE(C % 4 == 0 && (up_d == 1 || up_d == 2), "mp_upsample2x_linear_cl: bad dims");
   if (!in_f32 && !out_f32 && D == 1 && up_d == 1 && C % 8 == 0 && H * 2 <= 65535 && N <= 65535) {
-    dim3 g8((unsigned)((W * 2 * (C / 8) + 255) / 256), (unsigned)(H * 2), (unsigned)N);
-    k_upsample2x_bilinear_split8<<<g8, 256, 0, mp_stream(stream)>>>((const bf16*)in_hi, (const bf16*)in_lo,
-                                                                     (bf16*)out_hi, (bf16*)out_lo, H, W, C);
+    static int one_px = [] { const char* e = getenv("MPB200_UPSAMPLE_1PX"); return (e && atoi(e)) ? 1 : 0; }();
+    if (one_px) {
+      dim3 g8((unsigned)((W * 2 * (C / 8) + 255) / 256), (unsigned)(H * 2), (unsigned)N);
+      k_upsample2x_bilinear_split8<<<g8, 256, 0, mp_stream(stream)>>>((const bf16*)in_hi, (const bf16*)in_lo,
+                                                                       (bf16*)out_hi, (bf16*)out_lo, H, W, C);
+    } else {
+      dim3 g4((unsigned)((W * (C / 8) + 255) / 256), (unsigned)H, (unsigned)N);
+      k_upsample2x_bilinear_split8_2x2<<<g4, 256, 0, mp_stream(stream)>>>((const bf16*)in_hi, (const bf16*)in_lo,
+                                                                           (bf16*)out_hi, (bf16*)out_lo, H, W, C);
+    }
     MP_LAUNCH_CHECK("mp_upsample2x_linear_cl");
     return 0;
   }

@@ -96,6 +96,7 @@ _SIGNATURES = {
     "mp_warp_fused_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, _P]),
     "mp_tap_sum3x3_cl": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_gn_relu_conv3x3_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_blur_subsample": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 

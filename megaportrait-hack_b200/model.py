@@ -422,9 +422,9 @@ class G2d(nn.Module, _Packed):
         b = w2 @ b1 + b2
         return {"in": ops.pack_conv(w, b, dev),
                 "gn": (_f32c(self.final_conv[0].weight), _f32c(self.final_conv[0].bias)),
-                # 64->3 3x3 head as a 1x1 GEMM with 27 per-tap outputs + a shift-and-add (ops.tap_sum3x3)
-                "out": ops.pack_tap_head(self.final_conv[2].weight, dev),
-                "out_bias": _f32c(self.final_conv[2].bias)}
+                # GroupNorm -> ReLU -> 64->3 3x3 -> Sigmoid runs as one fused pass; its weights travel as kernel parameters
+                "head_w": self.final_conv[2].weight.detach().float().cpu().contiguous(),
+                "head_b": self.final_conv[2].bias.detach().float().cpu().contiguous()}
 
     def _forward_cl(self, x: Act) -> torch.Tensor:
         """x: split channels-last [N,1,64,64,96] -> RGB NCHW fp32 [N,3,512,512]."""
@@ -437,9 +437,8 @@ class G2d(nn.Module, _Packed):
             u = ops.upsample2x_linear(h, 1, f32=False, split=True)
             last = i == 2
             h, st = up[1]._forward_cl(u, f32=last, split=not last, stats_groups=32 if last else 0)
-        g = ops.group_norm_act(h, 32, st, *P["gn"], act=ACT_RELU, split=True)
-        y, _ = ops.conv(g, P["out"], f32=True)
-        return ops.tap_sum3x3(y, P["out_bias"], 3, ACT_SIGMOID)
+        ab = ops.gn_finalize(st, h.shape, 32, *P["gn"])
+        return ops.gn_relu_conv3x3_head(h, ab, P["head_w"], P["head_b"], ACT_SIGMOID)
 
     def forward(self, x):
         _require_inference(self, x)

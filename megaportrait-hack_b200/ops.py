@@ -566,6 +566,26 @@ def tap_sum3x3(y: Act, bias: Optional[torch.Tensor], Co: int, act: int = ACT_NON
 
 
 @_profiled
+def gn_relu_conv3x3_head(a: Act, ab: torch.Tensor, weight_host: torch.Tensor, bias_host: Optional[torch.Tensor],
+                         act: int = ACT_SIGMOID) -> torch.Tensor:
+    """act(conv3x3(relu(a * ab[...,0] + ab[...,1]))) in one pass: a CL fp32 [N,1,H,W,64], ab [N,64,2] (gn_finalize),
+    weight_host (3,64,3,3) / bias_host (3,) contiguous fp32 CPU tensors -> NCHW fp32 [N,3,H,W] (model.py:748-751)."""
+    N, D, H, W, C = a.shape
+    if a.f32 is None or D != 1:
+        raise RuntimeError("gn_relu_conv3x3_head: needs a 2-D fp32 channels-last activation")
+    for t in (weight_host, bias_host):
+        if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise RuntimeError("gn_relu_conv3x3_head: weights must be contiguous fp32 CPU tensors")
+    Co = weight_host.shape[0]
+    out = torch.empty((N, Co, H, W), dtype=torch.float32, device=a.device)
+    L = _lib.load()
+    _lib.check(L.mp_gn_relu_conv3x3_head(_p(a.f32), _p(ab), _p(weight_host), _p(bias_host), _p(out), N, H, W, C, Co, act,
+                                         _stream()), "mp_gn_relu_conv3x3_head")
+    _count()
+    return out
+
+
+@_profiled
 def blur_subsample(x: torch.Tensor, kernel2d: torch.Tensor, step: int) -> torch.Tensor:
     _chk_cuda(x, torch.float32, "blur_subsample x")
     _chk_cuda(kernel2d, torch.float32, "blur_subsample kernel")

@@ -259,6 +259,11 @@ def tap_sum3x3(y, bias, Co, act=ops.ACT_NONE):
     return _act(out, act).permute(0, 3, 1, 2).contiguous()
 
 
+def gn_relu_conv3x3_head(a, ab, weight_host, bias_host, act=ops.ACT_SIGMOID):
+    v = F.relu(a.f32 * ab[:, None, None, None, :, 0] + ab[:, None, None, None, :, 1])
+    return _act(F.conv2d(_to_ncdhw(v).squeeze(2), weight_host, bias_host, padding=1), act)
+
+
 def blur_subsample(x, kernel2d, step):
     ks = kernel2d.shape[-1]
     C = x.shape[1]
@@ -269,7 +274,7 @@ def blur_subsample(x, kernel2d, step):
 _NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
           "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3", "from_nchw_pad16",
-          "im2col3x3_f16", "maxpool3x3s2_f16", "global_avgpool_f16"]
+          "im2col3x3_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]
 
 
 @contextlib.contextmanager

@@ -497,3 +497,34 @@ def test_maxpool_and_global_avgpool_f16(ops):
     assert torch.equal(mp.h16.float().cpu().squeeze(1).permute(0, 3, 1, 2), F.max_pool2d(xq, 3, 2, 1))
     gap = ops.global_avgpool_f16(a).cpu()
     assert (gap - xq.mean(dim=(2, 3))).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 64, 96), (1, 21, 45)], ids=["tiled", "ragged"])
+def test_fused_gn_relu_conv_head(ops, N, H, W):
+    """G2d.final_conv in one kernel (model.py:748-751): GroupNorm affine -> ReLU -> 3x3 64->3 -> Sigmoid."""
+    x = rnd(N, 64, H, W, seed=61) * 2 + 0.3
+    gamma, beta = rnd(64, seed=62) * 0.2 + 1, rnd(64, seed=63) * 0.1
+    w = rnd(3, 64, 3, 3, seed=64) / math.sqrt(64 * 9)
+    b = rnd(3, seed=65) * 0.1
+    ref = torch.sigmoid(F.conv2d(F.relu(F.group_norm(x, 32, gamma, beta)), w, b, padding=1))
+    a = ops.from_nchw(x.to(DEV), f32=True, split=False)
+    ab = ops.gn_finalize(ops.gn_stats(a, 32), a.shape, 32, gamma.to(DEV), beta.to(DEV))
+    got = ops.gn_relu_conv3x3_head(a, ab, w.contiguous(), b.contiguous(), ops.ACT_SIGMOID).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 2e-6
+    with pytest.raises(RuntimeError, match="CPU tensors"):
+        ops.gn_relu_conv3x3_head(a, ab, w.to(DEV), b)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 6, 10), (1, 64, 33, 7), (3, 8, 1, 1)], ids=["small", "odd", "1x1"])
+def test_bilinear_upsample_split_2x2_blocks(ops, shape):
+    """The G2d decoder's upsample (model.py:733-743): split in / split out, one thread per 2x2 output block."""
+    N, C, H, W = shape
+    x = rnd(N, C, 1, H, W, seed=71)
+    a = ops.from_nchw(x.to(DEV), f32=False, split=True)
+    u = ops.upsample2x_linear(a, 1, f32=False, split=True)
+    xq = (a.hi.float() + a.lo.float()).cpu().permute(0, 4, 1, 2, 3).squeeze(2)
+    ref = F.interpolate(xq, scale_factor=2, mode="bilinear", align_corners=True)
+    got = (u.hi.float() + u.lo.float()).cpu().squeeze(1).permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())

@@ -105,6 +105,23 @@ def main():
         conv_case_h("r18_64_256x256_b32_h_res", 32, 64, 64, 256, 256, 3, r, res=True)
         conv_case_h("r18_128_128x128_b32_h", 32, 128, 128, 128, 128, 3, r)
         conv_case_h("r18_512_32x32_b32_h", 32, 512, 512, 32, 32, 3, r)
+    if sel("up"):
+        g = torch.Generator().manual_seed(3)
+        for (C, H) in ((512, 64), (256, 128), (128, 256)):
+            a = ops.Act((32, 1, H, H, C), f32=torch.randn(32, 1, H, H, C, generator=g).to(DEV))
+            ops.ensure_split(a)
+            a.f32 = None
+            best, avg = timeit(lambda: ops.upsample2x_linear(a, 1, f32=False, split=True), r)
+            by = 32 * H * H * C * 4 * 5
+            print(f"upsample2x_split_{C}x{H}       best {best:8.3f} ms avg {avg:8.3f} ms  {by / best / 1e6:8.1f} GB/s", flush=True)
+    if sel("head"):
+        g = torch.Generator().manual_seed(4)
+        a = ops.Act((32, 1, 512, 512, 64), f32=torch.randn(32, 1, 512, 512, 64, generator=g).to(DEV))
+        ab = torch.rand(32, 64, 2, generator=g).to(DEV)
+        w, b = torch.randn(3, 64, 3, 3, generator=g) / 24, torch.zeros(3)
+        best, avg = timeit(lambda: ops.gn_relu_conv3x3_head(a, ab, w, b), r)
+        by = 32 * 512 * 512 * (64 + 3) * 4
+        print(f"gn_relu_conv3x3_head_b32     best {best:8.3f} ms avg {avg:8.3f} ms  {by / best / 1e6:8.1f} GB/s", flush=True)
     if sel("simt"):
         conv_case("g2d_512_64x64_b4", 4, 512, 512, 1, 64, 64, (1, 3, 3), r, mode="simt")
     if sel("warp"):
