@@ -68,6 +68,7 @@ struct TcParams {
   uint32_t tma_buf_bytes;     // one staging buffer: (BN / 64) sub-tiles of [128 rows][64 fp16] = 16 KB each
   uint32_t tma_nbuf;          // 1 or 2 staging buffers
   uint32_t epi_bytes;         // size of the register-store staging area (0 when the TMA-store epilogue is used)
+  int b_merged;               // 1: map_b_hi is a 3-D map (K, Cout_pad, plane) and one TMA load fetches [Bh | Bl]
   unsigned int* sched;        // dynamic tile scheduler: {next-tile counter, finished-CTA counter}, or NULL = static walk
 };
 
@@ -139,6 +140,23 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// weight tile(s) of one K chunk: [Bh | Bl] in one 3-D load when the two planes are one allocation, else two 2-D loads
+__device__ __forceinline__ void load_b(const TcParams& p, uint32_t dst, const CUtensorMap* mh, const CUtensorMap* ml,
+                                       uint32_t bar, int k0, int n0) {
+  if (p.b_merged) {
+    tma_load_3d(dst, mh, bar, k0, n0, 0);
+  } else {
+    tma_load_2d(dst, mh, bar, k0, n0);
+    tma_load_2d(dst + p.b_bytes, ml, bar, k0, n0);
+  }
+}
+
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo, uint32_t layout_type) {
   // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
   uint64_t d = 0;
@@ -176,6 +194,29 @@ __device__ __forceinline__ void umma_bf16_lean(uint32_t tmem_d, uint32_t a_lo, u
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Issue paths of the persistent kernels: called by ALL 32 lanes of the MMA warp in lock-step; `elect.sync` picks the one
+// lane that issues.  (Issuing from inside an `if (lane == 0)` region instead makes the compiler wrap every UTCHMMA /
+// UTCBAR in an active-lane loop -- ELECT, PLOP3, BRA.U.ANY -- which, on a single dependent instruction stream, capped
+// the 64-cycle N = 128 MMAs at ~37 % tensor-pipe utilisation: ncu, profiles/r2_*.)
+__device__ __forceinline__ void umma_lean_e(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
 // one K-chunk (KS k-steps) of the 3-pass split product into accumulator tmem_d
 template <int KS>
 __device__ __forceinline__ void umma_chunk(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
@@ -183,9 +224,9 @@ __device__ __forceinline__ void umma_chunk(uint32_t tmem_d, uint32_t a_hi, uint3
   const uint32_t ah = desc_lo_word(a_hi), al = desc_lo_word(a_lo), bh = desc_lo_word(b_hi), bl = desc_lo_word(b_lo);
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
-    umma_bf16_lean(tmem_d, al + 2 * k, bh + 2 * k, hi, idesc, k == 0 ? acc_first : 1u);
-    umma_bf16_lean(tmem_d, ah + 2 * k, bl + 2 * k, hi, idesc, 1u);
-    umma_bf16_lean(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc, 1u);
+    umma_lean_e(tmem_d, al + 2 * k, bh + 2 * k, hi, idesc, k == 0 ? acc_first : 1u);
+    umma_lean_e(tmem_d, ah + 2 * k, bl + 2 * k, hi, idesc, 1u);
+    umma_lean_e(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc, 1u);
   }
 }
 // dual-B variant: two MMAs per K step -- Ah x [Bh|Bl] (N = 2*BN, Bl follows Bh in shared memory) and Al x Bh (N = BN)
@@ -195,8 +236,8 @@ __device__ __forceinline__ void umma_chunk_dual(uint32_t tmem_d, uint32_t a_hi, 
   const uint32_t ah = desc_lo_word(a_hi), al = desc_lo_word(a_lo), bh = desc_lo_word(b_hi);
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
-    umma_bf16_lean(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc2, k == 0 ? acc_first : 1u);
-    umma_bf16_lean(tmem_d, al + 2 * k, bh + 2 * k, hi, idesc, 1u);
+    umma_lean_e(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc2, k == 0 ? acc_first : 1u);
+    umma_lean_e(tmem_d, al + 2 * k, bh + 2 * k, hi, idesc, 1u);
   }
 }
 // fp16 two-pass variant: ONE MMA per K step, Ah x [Bh|Bl'] (N = 2*BN); the activation has no lo plane
@@ -205,7 +246,7 @@ __device__ __forceinline__ void umma_chunk_h(uint32_t tmem_d, uint32_t a_hi, uin
                                              uint32_t acc_first) {
   const uint32_t ah = desc_lo_word(a_hi), bh = desc_lo_word(b_hi);
 #pragma unroll
-  for (int k = 0; k < KS; ++k) umma_bf16_lean(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc2, k == 0 ? acc_first : 1u);
+  for (int k = 0; k < KS; ++k) umma_lean_e(tmem_d, ah + 2 * k, bh + 2 * k, hi, idesc2, k == 0 ? acc_first : 1u);
 }
 __device__ __forceinline__ void umma_chunk_h_dyn(int ksteps, uint32_t tmem_d, uint32_t a_hi, uint32_t b_hi, uint32_t hi,
                                                  uint32_t idesc2, uint32_t acc_first) {
@@ -567,7 +608,8 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so role code stays on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return bars + s * 8; };
   auto empty_bar = [&](int s) { return bars + (p.STAGES + s) * 8; };
   auto tfull_bar = [&](int b) { return bars + (2 * p.STAGES + b) * 8; };
@@ -605,7 +647,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // uniform for the compiler
 
   auto tile_coords = [&](int tile, int& n, int& d0, int& h0, int& w0, int& n0) {
     n0 = (tile % p.tiles_n) * p.BN;
@@ -626,8 +668,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         mbar_expect_tx(bres_bar, (uint32_t)num_kb * 2u * p.b_bytes);
         for (int i = 0; i < num_kb; ++i) {
           const uint32_t sb = smem_base + p.bres_off + (uint32_t)i * 2u * p.b_bytes;
-          tma_load_2d(sb, &map_b_hi, bres_bar, i * p.CCHUNK, 0);
-          tma_load_2d(sb + p.b_bytes, &map_b_lo, bres_bar, i * p.CCHUNK, 0);
+          load_b(p, sb, &map_b_hi, &map_b_lo, bres_bar, i * p.CCHUNK, 0);
         }
       }
       const uint32_t tx = p.a_planes * p.a_bytes + (p.b_resident ? 0u : 2 * p.b_bytes);
@@ -652,8 +693,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             tma_load_5d(sa, &map_a_hi, full_bar(s), ci, wi, hi_, d0 + kd - pd, n);
             if (p.a_planes == 2) tma_load_5d(sa + p.a_bytes, &map_a_lo, full_bar(s), ci, wi, hi_, d0 + kd - pd, n);
             if (!p.b_resident) {
-              tma_load_2d(sa + p.a_planes * p.a_bytes, &map_b_hi, full_bar(s), tap * p.Cin + c0, n0);
-              tma_load_2d(sa + p.a_planes * p.a_bytes + p.b_bytes, &map_b_lo, full_bar(s), tap * p.Cin + c0, n0);
+              load_b(p, sa + p.a_planes * p.a_bytes, &map_b_hi, &map_b_lo, full_bar(s), tap * p.Cin + c0, n0);
             }
           }
         }
@@ -662,15 +702,16 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       sched_finish(p);
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (whole warp, elected lane issues)
+    {
       const int ksteps = p.CCHUNK / 16;
       const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
       uint32_t kb = 0, it = 0;
       if (p.b_resident && (int)blockIdx.x < p.total_tiles) mbar_wait(bres_bar, 0);
       for (;; ++it) {
-        const int tile = sched_read(sfull, s_tile, it);
-        mbar_arrive(sempty + (it % SQ) * 8);
+        const int tile = __shfl_sync(0xffffffffu, sched_read(sfull, s_tile, it), 0);   // uniform loop exit
+        if (lane == 0) mbar_arrive(sempty + (it % SQ) * 8);
+        __syncwarp();
         if (tile < 0) break;
         const uint32_t b = it & 1;
         mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
@@ -689,9 +730,9 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
           if (p.prec == MP_PREC_F16X2) umma_chunk_h_dyn(ksteps, d_tmem, a_hi, b_hi, dhi, p.idesc2, i > 0 ? 1u : 0u);
           else if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, i > 0 ? 1u : 0u);
           else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, i > 0 ? 1u : 0u);
-          umma_commit(empty_bar(s));
+          umma_commit_e(empty_bar(s));
         }
-        umma_commit(tfull_bar(b));
+        umma_commit_e(tfull_bar(b));
       }
     }
   } else {
@@ -796,7 +837,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so role code stays on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t a_stage = p.a_planes * x.a_plane_bytes, b_stage = 2 * p.b_bytes;
   const uint32_t row_bytes = (uint32_t)p.CCHUNK * 2u;
 
@@ -821,7 +863,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // uniform for the compiler
 
   // super-tile id -> (n, d, h0, w0, n0); tiles_h counts super-tiles of MT*BH rows, tiles_d = D (BD = 1)
   auto tile_coords = [&](int tile, int& n, int& d0, int& h0, int& w0, int& n0) {
@@ -866,8 +908,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
                 const uint32_t sb = smem_base + x.b_ring_off + sidx * b_stage;
                 mbar_expect_tx(fullB(sidx), b_stage);
                 const int tap = (kd * 3 + kh) * p.KW + kw;
-                tma_load_2d(sb, &map_b_hi, fullB(sidx), tap * p.Cin + c0, n0);
-                tma_load_2d(sb + p.b_bytes, &map_b_lo, fullB(sidx), tap * p.Cin + c0, n0);
+                load_b(p, sb, &map_b_hi, &map_b_lo, fullB(sidx), tap * p.Cin + c0, n0);
               }
             }
         tile = next_tile;
@@ -875,14 +916,15 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       sched_finish(p);
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (whole warp, elected lane issues)
+    {
       const int ksteps = p.CCHUNK / 16;
       const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
       uint32_t ia = 0, ib = 0, it = 0;
       for (;; ++it) {
-        const int tile = sched_read(sfull, s_tile, it);
-        mbar_arrive(sempty + (it % SQ) * 8);
+        const int tile = __shfl_sync(0xffffffffu, sched_read(sfull, s_tile, it), 0);   // uniform loop exit
+        if (lane == 0) mbar_arrive(sempty + (it % SQ) * 8);
+        __syncwarp();
         if (tile < 0) break;
         const uint32_t b = it & 1;
         mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);
@@ -908,11 +950,11 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
               else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, first ? 0u : 1u);
             }
             first = false;
-            umma_commit(emptyB(bidx));
+            umma_commit_e(emptyB(bidx));
           }
-          umma_commit(emptyA(sidx));
+          umma_commit_e(emptyA(sidx));
         }
-        umma_commit(tfull_bar(b));
+        umma_commit_e(tfull_bar(b));
       }
     }
   } else {
@@ -983,7 +1025,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so role code stays on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return bars + s * 8; };
   auto empty_bar = [&](int s) { return bars + (p.STAGES + s) * 8; };
   const uint32_t tmem_full_bar = bars + 2 * p.STAGES * 8;
@@ -1021,7 +1064,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // uniform for the compiler
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -1307,7 +1350,8 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
       d->Cout_pad <= 128 && d->W % 8 == 0 && d->H % 16 == 0) {
     const int bn = d->Cout_pad;
     const bool tma_s = tma_epi_ok(d, bn);
-    const uint32_t nbuf_s = bn <= 64 ? 2u : 1u;      // 32 KB of staging either way
+    static int nbuf_env = [] { const char* e = getenv("MPB200_TC_TMA_NBUF"); return e ? atoi(e) : 0; }();
+    const uint32_t nbuf_s = nbuf_env ? (uint32_t)nbuf_env : (bn <= 64 ? 2u : 1u);      // 32 KB of staging either way
     const uint32_t tma_bytes_s = tma_s ? nbuf_s * (uint32_t)(bn / 64) * 16384u + 1024u /*alignment*/ : 0u;
     const uint32_t fixed_s = 1024 + 1024 + 2 * 256 * sizeof(double) + 2048 /*s_part*/ + (tma_s ? 0u : EPI_BYTES) + tma_bytes_s;
     static int mt_cap = [] { const char* e = getenv("MPB200_TC_SLAB_MT"); return e ? atoi(e) : 2; }();
@@ -1485,6 +1529,16 @@ int encode_out_map(CUtensorMap* m, void* ptr, const mp_conv_desc* d, const Plan&
 
 int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const Plan& pl) {
   const cuuint64_t ktot = (cuuint64_t)d->KD * d->KH * d->KW * d->Cin;
+  if (pl.p.b_merged) {     // both planes in one box: (K chunk, BN rows, 2 planes) -> [Bh tile | Bl tile] in shared memory
+    const CUtensorMapDataType dt3 = pl.p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    cuuint64_t dims3[3] = {ktot, (cuuint64_t)d->Cout_pad, 2};
+    cuuint64_t strides3[2] = {ktot * 2, ktot * 2 * (cuuint64_t)d->Cout_pad};
+    cuuint32_t box3[3] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BN, 2};
+    cuuint32_t estr3[3] = {1, 1, 1};
+    CUresult r3 = get_encoder()(m, dt3, 3, const_cast<void*>(ptr), dims3, strides3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r3 == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(weights, 3-D) failed (%d)", (int)r3);
+  }
   cuuint64_t dims[2] = {ktot, (cuuint64_t)d->Cout_pad};
   cuuint64_t strides[1] = {ktot * 2};
   cuuint32_t box[2] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BN};
@@ -1511,11 +1565,18 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
   if (int e = make_plan(d, pl, true)) return e;
   MP_REQUIRE((((uintptr_t)d->in_hi | (uintptr_t)d->in_lo | (uintptr_t)d->w_hi | (uintptr_t)d->w_lo) & 15) == 0,
              "mp_conv_tc: operands must be 16-byte aligned");
+  {
+    static int no_merge = [] { const char* e = getenv("MPB200_TC_NO_BMERGE"); return (e && atoi(e)) ? 1 : 0; }();
+    const size_t plane = (size_t)d->KD * d->KH * d->KW * d->Cin * d->Cout_pad * 2;
+    pl.p.b_merged = (!no_merge && !pl.v1 &&
+                     reinterpret_cast<const char*>(d->w_lo) == reinterpret_cast<const char*>(d->w_hi) + plane) ? 1 : 0;
+  }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (int e = encode_act_map(&ma_hi, d->in_hi, d, pl)) return e;
   if (int e = encode_act_map(&ma_lo, pl.p.a_planes == 2 ? d->in_lo : d->in_hi, d, pl)) return e;   // unused when 1 plane
   if (int e = encode_w_map(&mb_hi, d->w_hi, d, pl)) return e;
-  if (int e = encode_w_map(&mb_lo, d->w_lo, d, pl)) return e;
+  if (pl.p.b_merged) mb_lo = mb_hi;
+  else if (int e = encode_w_map(&mb_lo, d->w_lo, d, pl)) return e;
   CUtensorMap mo = mb_hi;          // placeholder when the kernel stores with ordinary instructions
   if (pl.p.epi_tma) {
     MP_REQUIRE((reinterpret_cast<uintptr_t>(d->out_hi) & 15) == 0, "mp_conv_tc: output must be 16-byte aligned");

@@ -4,7 +4,8 @@
 // channel) scale/shift pairs of mp_gn_finalize.  The un-fused chain (affine pass writing split planes, a 64->27 tensor-core
 // GEMM, a shift-and-add pass) moved 2.1 GB four times; here x is read once and only the 3-channel image is written.
 //
-// CTA = 8 x 32 output pixels (128 threads, two vertically adjacent pixels per thread).  The normalised, rectified
+// CTA = 8 x 32 output pixels; 256 threads = two channel halves (32 input channels each, partial sums merged through
+// shared memory) x 128 pixel-pair owners (two vertically adjacent pixels per thread).  The normalised, rectified
 // 10 x 34 halo tile is staged channel-major in shared memory (odd pitch: conflict-free transposed fill, conflict-free
 // row reads); the 64*9*3 weights travel as a __grid_constant__ kernel parameter, so every FFMA takes its weight straight
 // from the constant bank.  fp32 FMA throughout.  Two CTAs per SM: one fills while the other computes.
@@ -17,7 +18,7 @@ constexpr int HO = 3;              // output channels
 constexpr int TH = 8, TW = 32;     // output tile
 constexpr int PH = TH + 2, PW = TW + 2;
 constexpr int PITCH = PH * PW + 1; // 341 floats per channel (odd)
-constexpr int HEAD_THREADS = 128;
+constexpr int HEAD_THREADS = 256;   // two channel halves x (4 row pairs x 32 columns)
 
 struct HeadWeights {
   float w[HC][9][HO];              // [cin][kh*3+kw][cout]
@@ -69,13 +70,32 @@ k_gn_relu_conv3x3_head(const float* __restrict__ x, const float* __restrict__ ab
   }
   __syncthreads();
   // ---- compute: thread = column tx, rows 2*ty and 2*ty + 1 of the tile
-  const int tx = tid & 31, ty = tid >> 5;
+  const int tx = tid & 31, ty = (tid >> 5) & 3, chalf = tid >> 7;
   float acc0[HO], acc1[HO];
 #pragma unroll
-  for (int o = 0; o < HO; ++o) acc0[o] = acc1[o] = wt.bias[o];
+  for (int o = 0; o < HO; ++o) acc0[o] = acc1[o] = chalf ? 0.f : wt.bias[o];
   const float* sp = s + (2 * ty) * PW + tx;
+  if (chalf == 0) {
 #pragma unroll
-  for (int c = 0; c < HC; ++c) {
+    for (int c = 0; c < HC / 2; ++c) {
+      float v[4][3];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[r][k] = sp[c * PITCH + r * PW + k];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int o = 0; o < HO; ++o) {
+            acc0[o] = fmaf(v[kh][kw], wt.w[c][kh * 3 + kw][o], acc0[o]);
+            acc1[o] = fmaf(v[kh + 1][kw], wt.w[c][kh * 3 + kw][o], acc1[o]);
+          }
+    }
+  } else {
+#pragma unroll
+  for (int c = HC / 2; c < HC; ++c) {
     float v[4][3];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -90,6 +110,24 @@ k_gn_relu_conv3x3_head(const float* __restrict__ x, const float* __restrict__ ab
           acc0[o] = fmaf(v[kh][kw], wt.w[c][kh * 3 + kw][o], acc0[o]);
           acc1[o] = fmaf(v[kh + 1][kw], wt.w[c][kh * 3 + kw][o], acc1[o]);
         }
+  }
+  }
+  // merge the two channel halves (fixed order: lower half + upper half), then the lower-half threads store
+  __syncthreads();
+  float* red = s;                  // the tile is dead: reuse [6][128] floats
+  if (chalf) {
+#pragma unroll
+    for (int o = 0; o < HO; ++o) {
+      red[(2 * o) * 128 + (tid & 127)] = acc0[o];
+      red[(2 * o + 1) * 128 + (tid & 127)] = acc1[o];
+    }
+  }
+  __syncthreads();
+  if (chalf) return;
+#pragma unroll
+  for (int o = 0; o < HO; ++o) {
+    acc0[o] += red[(2 * o) * 128 + tid];
+    acc1[o] += red[(2 * o + 1) * 128 + tid];
   }
   const int ya = y0 + 2 * ty, xa = x0 + tx;
   if (xa < W) {

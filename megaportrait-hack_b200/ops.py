@@ -318,7 +318,8 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, c
         hi = wk.to(torch.bfloat16)
         lo = (wk - hi.float()).to(torch.bfloat16)
     b = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
-    return PackedConv(hi.contiguous(), lo.contiguous(), b, Cin, Cout, Cout_pad, (kd, kh, kw), prec)
+    planes = torch.stack((hi, lo)).contiguous()      # one allocation: the kernel then fetches [hi | lo] with ONE TMA load
+    return PackedConv(planes[0], planes[1], b, Cin, Cout, Cout_pad, (kd, kh, kw), prec)
 
 
 def pack_stem3x3_f16(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> PackedConv:
