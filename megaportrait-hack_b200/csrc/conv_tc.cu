@@ -662,7 +662,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     // ===================================================================== TMA producer
     if (lane == 0) {
       const int pd = p.KD / 2, ph = p.KH / 2, pw = p.KW / 2;
-      uint32_t kb = 0;
+      uint32_t s = 0, ph_bit = 1;      // ring position; the producer waits on the "empty" phase, which starts at parity 1
       if (p.b_resident && (int)blockIdx.x < p.total_tiles) {
         // tiles_n == 1: every tile of this CTA uses the same weights -> fetch them once
         mbar_expect_tx(bres_bar, (uint32_t)num_kb * 2u * p.b_bytes);
@@ -679,13 +679,12 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         const int next_tile = sched_next(p, tile);      // drawn early: the atomic's latency hides behind this tile's loads
         int n, d0, h0, w0, n0;
         tile_coords(tile, n, d0, h0, w0, n0);
+        int kw = -1, kh = 0, kd = 0;                  // tap -> (kd, kh, kw) without divisions
         for (int tap = 0; tap < taps; ++tap) {
+          if (++kw == p.KW) { kw = 0; if (++kh == p.KH) { kh = 0; ++kd; } }
           if (!((p.tap_mask >> tap) & 1ull)) continue;
-          const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
-          for (int cc = 0; cc < p.num_cchunks; ++cc, ++kb) {
-            const int s = kb % p.STAGES;
-            const uint32_t ph_bit = (kb / p.STAGES) & 1;
-            mbar_wait(empty_bar(s), ph_bit ^ 1);
+          for (int cc = 0; cc < p.num_cchunks; ++cc) {
+            mbar_wait(empty_bar(s), ph_bit);
             const uint32_t sa = smem_base + s * p.stage_bytes;
             mbar_expect_tx(full_bar(s), tx);
             const int c0 = cc * p.CCHUNK;
@@ -695,6 +694,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             if (!p.b_resident) {
               load_b(p, sa + p.a_planes * p.a_bytes, &map_b_hi, &map_b_lo, full_bar(s), tap * p.Cin + c0, n0);
             }
+            if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
           }
         }
         tile = next_tile;
@@ -706,7 +706,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     {
       const int ksteps = p.CCHUNK / 16;
       const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
-      uint32_t kb = 0, it = 0;
+      uint32_t it = 0, s = 0, ph_bit = 0;        // smem ring position / phase (no div/mod on the issue path)
       if (p.b_resident && (int)blockIdx.x < p.total_tiles) mbar_wait(bres_bar, 0);
       for (;; ++it) {
         const int tile = __shfl_sync(0xffffffffu, sched_read(sfull, s_tile, it), 0);   // uniform loop exit
@@ -717,9 +717,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + b * (uint32_t)p.acc_w;
-        for (int i = 0; i < num_kb; ++i, ++kb) {
-          const int s = kb % p.STAGES;
-          const uint32_t ph_bit = (kb / p.STAGES) & 1;
+        for (int i = 0; i < num_kb; ++i) {
           mbar_wait(full_bar(s), ph_bit);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + s * p.stage_bytes;
@@ -731,6 +729,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
           else if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, i > 0 ? 1u : 0u);
           else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, i > 0 ? 1u : 0u);
           umma_commit_e(empty_bar(s));
+          if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
         }
         umma_commit_e(tfull_bar(b));
       }
@@ -879,7 +878,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     // ===================================================================== TMA producer
     if (lane == 0) {
       const int pd = p.KD / 2, pw = p.KW / 2;
-      uint32_t ia = 0, ib = 0;
+      uint32_t sidx = 0, a_ph = 1, bidx = 0, b_ph = 1;   // producer waits on the "empty" phase: starts at parity 1
       int tile = blockIdx.x;
       for (uint32_t tk = 0;; ++tk) {
         sched_publish(sfull, sempty, s_tile, tk, tile < p.total_tiles ? tile : -1);
@@ -892,23 +891,22 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             for (int cc = 0; cc < p.num_cchunks; ++cc) {
               const int c0 = cc * p.CCHUNK;
               {
-                const int sidx = ia % x.SA;
-                mbar_wait(emptyA(sidx), ((ia / x.SA) & 1) ^ 1);
+                mbar_wait(emptyA(sidx), a_ph);
                 const uint32_t sa = smem_base + sidx * a_stage;
                 mbar_expect_tx(fullA(sidx), a_stage);
                 tma_load_5d(sa, &map_a_hi, fullA(sidx), c0 + p.in_c_off, w0 + kw - pw, h0 - 1, d0 + kd - pd, n);
                 if (p.a_planes == 2)
                   tma_load_5d(sa + x.a_plane_bytes, &map_a_lo, fullA(sidx), c0 + p.in_c_off, w0 + kw - pw, h0 - 1,
                               d0 + kd - pd, n);
-                ++ia;
+                if (++sidx == (uint32_t)x.SA) { sidx = 0; a_ph ^= 1u; }
               }
-              for (int kh = 0; kh < 3; ++kh, ++ib) {
-                const int sidx = ib % x.SB;
-                mbar_wait(emptyB(sidx), ((ib / x.SB) & 1) ^ 1);
-                const uint32_t sb = smem_base + x.b_ring_off + sidx * b_stage;
-                mbar_expect_tx(fullB(sidx), b_stage);
+              for (int kh = 0; kh < 3; ++kh) {
+                mbar_wait(emptyB(bidx), b_ph);
+                const uint32_t sb = smem_base + x.b_ring_off + bidx * b_stage;
+                mbar_expect_tx(fullB(bidx), b_stage);
                 const int tap = (kd * 3 + kh) * p.KW + kw;
-                load_b(p, sb, &map_b_hi, &map_b_lo, fullB(sidx), tap * p.Cin + c0, n0);
+                load_b(p, sb, &map_b_hi, &map_b_lo, fullB(bidx), tap * p.Cin + c0, n0);
+                if (++bidx == (uint32_t)x.SB) { bidx = 0; b_ph ^= 1u; }
               }
             }
         tile = next_tile;
@@ -920,7 +918,9 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     {
       const int ksteps = p.CCHUNK / 16;
       const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
-      uint32_t ia = 0, ib = 0, it = 0;
+      uint32_t it = 0, sidx = 0, a_ph = 0, bidx = 0, b_ph = 0;   // ring positions / phases (no div/mod on the issue path)
+      const int groups = p.KD * p.KW * p.num_cchunks;
+      const uint32_t kh_step = (uint32_t)p.BW * row_bytes, acc_step = (uint32_t)(p.BH * p.BW) * row_bytes;
       for (;; ++it) {
         const int tile = __shfl_sync(0xffffffffu, sched_read(sfull, s_tile, it), 0);   // uniform loop exit
         if (lane == 0) mbar_arrive(sempty + (it % SQ) * 8);
@@ -931,18 +931,16 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem0 = tmem_base + b * (uint32_t)(x.MT * p.acc_w);
         bool first = true;
-        for (int g = 0; g < p.KD * p.KW * p.num_cchunks; ++g, ++ia) {
-          const int sidx = ia % x.SA;
-          mbar_wait(fullA(sidx), (ia / x.SA) & 1);
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(fullA(sidx), a_ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + sidx * a_stage;
-          for (int kh = 0; kh < 3; ++kh, ++ib) {
-            const int bidx = ib % x.SB;
-            mbar_wait(fullB(bidx), (ib / x.SB) & 1);
+          for (int kh = 0; kh < 3; ++kh) {
+            mbar_wait(fullB(bidx), b_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t b_hi = smem_base + x.b_ring_off + bidx * b_stage, b_lo = b_hi + p.b_bytes;
             for (int t = 0; t < x.MT; ++t) {
-              const uint32_t a_hi = sa + (uint32_t)((t * p.BH + kh) * p.BW) * row_bytes;
+              const uint32_t a_hi = sa + (uint32_t)t * acc_step + (uint32_t)kh * kh_step;
               const uint32_t a_lo = a_hi + x.a_plane_bytes;
               const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.acc_w);
               if (p.prec == MP_PREC_F16X2) umma_chunk_h_dyn(ksteps, d_tmem, a_hi, b_hi, dhi, p.idesc2, first ? 0u : 1u);
@@ -951,8 +949,10 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             }
             first = false;
             umma_commit_e(emptyB(bidx));
+            if (++bidx == (uint32_t)x.SB) { bidx = 0; b_ph ^= 1u; }
           }
           umma_commit_e(emptyA(sidx));
+          if (++sidx == (uint32_t)x.SA) { sidx = 0; a_ph ^= 1u; }
         }
         umma_commit_e(tfull_bar(b));
       }
