@@ -109,6 +109,14 @@ typedef struct mp_conv_desc {
                              to 11 significant bits), w_hi = fp16(w), w_lo = fp16((w - w_hi) * 2048); the kernel
                              accumulates x*w_hi and x*w_lo in fp32 and adds the second sum scaled by 2^-11.
                              mp_conv_tc only. */
+  /* Fused 1x1 shortcut (mp_conv_tc only; 0 / NULL = none): out = act(conv(in) + conv1x1_stride2(in2) + bias + res).
+   * The residual blocks whose shortcut is Conv2d(1x1) + BatchNorm folded in (ResBlock2D, model.py:616-640; the
+   * down-sampling BasicBlock / Bottleneck, resnet.py:101-118) add it inside the accumulator instead of through HBM:
+   * in2 is a second activation [N, D, H/stride*stride2, W/stride*stride2, in2_C] in the same operand format as `in`,
+   * its Cin2 channels (window starting at in2_c_off) extend K: packed weight rows are [taps*Cin | Cin2] long. */
+  int Cin2, in2_C, in2_c_off, stride2;
+  const void* in2_hi;
+  const void* in2_lo;
 } mp_conv_desc;
 
 enum { MP_PREC_SPLIT_BF16 = 0, MP_PREC_F16X2 = 1 };

@@ -198,6 +198,7 @@ int mp_conv_validate(const mp_conv_desc* d, const char* who) {
 extern "C" int mp_conv_simt(const mp_conv_desc* d, void* stream) {
   if (int e = mp_conv_validate(d, "mp_conv_simt")) return e;
   MP_REQUIRE(d->prec == MP_PREC_SPLIT_BF16, "mp_conv_simt: only the split-bf16 operand format is implemented");
+  MP_REQUIRE(d->Cin2 == 0, "mp_conv_simt: the fused 1x1 shortcut is implemented by mp_conv_tc only");
   ConvArgs a;
   a.in_hi = (const bf16*)d->in_hi; a.in_lo = (const bf16*)d->in_lo;
   a.w_hi = (const bf16*)d->w_hi; a.w_lo = (const bf16*)d->w_lo;

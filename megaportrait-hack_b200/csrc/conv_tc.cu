@@ -68,6 +68,8 @@ struct TcParams {
   uint32_t tma_buf_bytes;     // one staging buffer: (BN / 64) sub-tiles of [128 rows][64 fp16] = 16 KB each
   uint32_t tma_nbuf;          // 1 or 2 staging buffers
   uint32_t epi_bytes;         // size of the register-store staging area (0 when the TMA-store epilogue is used)
+  int num_cchunks2, k2_off;   // fused 1x1 shortcut: channel chunks of the second source, K offset of its weights
+  int stride2, in2_c_off;
   int b_merged;               // 1: map_b_hi is a 3-D map (K, Cout_pad, plane) and one TMA load fetches [Bh | Bl]
   unsigned int* sched;        // dynamic tile scheduler: {next-tile counter, finished-CTA counter}, or NULL = static walk
 };
@@ -594,7 +596,8 @@ __device__ __forceinline__ void sched_finish(const TcParams& p) {
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-           const __grid_constant__ CUtensorMap map_out, const TcParams p) {
+           const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_a2_hi,
+           const __grid_constant__ CUtensorMap map_a2_lo, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -615,7 +618,8 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   auto tfull_bar = [&](int b) { return bars + (2 * p.STAGES + b) * 8; };
   auto tempty_bar = [&](int b) { return bars + (2 * p.STAGES + 2 + b) * 8; };
   const int taps = p.KD * p.KH * p.KW;
-  const int num_kb = __popcll(p.tap_mask) * p.num_cchunks;   // taps that are out of bounds everywhere are skipped
+  // K blocks per tile: live taps (taps that are out of bounds everywhere are skipped) + the fused shortcut's chunks
+  const int num_kb = __popcll(p.tap_mask) * p.num_cchunks + p.num_cchunks2;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.STAGES; ++s) {
@@ -696,6 +700,17 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             }
             if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
           }
+        }
+        for (int cc = 0; cc < p.num_cchunks2; ++cc) {      // fused 1x1 shortcut: centre tap of the second source
+          mbar_wait(empty_bar(s), ph_bit);
+          const uint32_t sa = smem_base + s * p.stage_bytes;
+          mbar_expect_tx(full_bar(s), tx);
+          const int c0 = cc * p.CCHUNK;
+          tma_load_5d(sa, &map_a2_hi, full_bar(s), c0 + p.in2_c_off, w0 * p.stride2, h0 * p.stride2, d0, n);
+          if (p.a_planes == 2)
+            tma_load_5d(sa + p.a_bytes, &map_a2_lo, full_bar(s), c0 + p.in2_c_off, w0 * p.stride2, h0 * p.stride2, d0, n);
+          if (!p.b_resident) load_b(p, sa + p.a_planes * p.a_bytes, &map_b_hi, &map_b_lo, full_bar(s), p.k2_off + c0, n0);
+          if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
         }
         tile = next_tile;
       }
@@ -816,7 +831,8 @@ struct SlabExtra {
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-           const __grid_constant__ CUtensorMap map_out, const TcParams p, const SlabExtra x) {
+           const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_a2_hi,
+           const __grid_constant__ CUtensorMap map_a2_lo, const TcParams p, const SlabExtra x) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -909,6 +925,22 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
                 if (++bidx == (uint32_t)x.SB) { bidx = 0; b_ph ^= 1u; }
               }
             }
+        for (int cc = 0; cc < p.num_cchunks2; ++cc) {      // fused 1x1 shortcut: one slab (centre column) + one weight tile
+          const int c0 = cc * p.CCHUNK;
+          mbar_wait(emptyA(sidx), a_ph);
+          const uint32_t sa = smem_base + sidx * a_stage;
+          mbar_expect_tx(fullA(sidx), a_stage);
+          tma_load_5d(sa, &map_a2_hi, fullA(sidx), c0 + p.in2_c_off, w0 * p.stride2, (h0 - 1) * p.stride2, d0, n);
+          if (p.a_planes == 2)
+            tma_load_5d(sa + x.a_plane_bytes, &map_a2_lo, fullA(sidx), c0 + p.in2_c_off, w0 * p.stride2,
+                        (h0 - 1) * p.stride2, d0, n);
+          if (++sidx == (uint32_t)x.SA) { sidx = 0; a_ph ^= 1u; }
+          mbar_wait(emptyB(bidx), b_ph);
+          const uint32_t sb = smem_base + x.b_ring_off + bidx * b_stage;
+          mbar_expect_tx(fullB(bidx), b_stage);
+          load_b(p, sb, &map_b_hi, &map_b_lo, fullB(bidx), p.k2_off + c0, n0);
+          if (++bidx == (uint32_t)x.SB) { bidx = 0; b_ph ^= 1u; }
+        }
         tile = next_tile;
       }
       sched_finish(p);
@@ -951,6 +983,26 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             umma_commit_e(emptyB(bidx));
             if (++bidx == (uint32_t)x.SB) { bidx = 0; b_ph ^= 1u; }
           }
+          umma_commit_e(emptyA(sidx));
+          if (++sidx == (uint32_t)x.SA) { sidx = 0; a_ph ^= 1u; }
+        }
+        for (int g = 0; g < p.num_cchunks2; ++g) {           // fused 1x1 shortcut: the slab's centre row offset (kh = 1)
+          mbar_wait(fullA(sidx), a_ph);
+          mbar_wait(fullB(bidx), b_ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + sidx * a_stage;
+          const uint32_t b_hi = smem_base + x.b_ring_off + bidx * b_stage, b_lo = b_hi + p.b_bytes;
+          for (int t = 0; t < x.MT; ++t) {
+            const uint32_t a_hi = sa + (uint32_t)t * acc_step + kh_step;
+            const uint32_t a_lo = a_hi + x.a_plane_bytes;
+            const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.acc_w);
+            if (p.prec == MP_PREC_F16X2) umma_chunk_h_dyn(ksteps, d_tmem, a_hi, b_hi, dhi, p.idesc2, first ? 0u : 1u);
+            else if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, first ? 0u : 1u);
+            else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, first ? 0u : 1u);
+          }
+          first = false;
+          umma_commit_e(emptyB(bidx));
+          if (++bidx == (uint32_t)x.SB) { bidx = 0; b_ph ^= 1u; }
           umma_commit_e(emptyA(sidx));
           if (++sidx == (uint32_t)x.SA) { sidx = 0; a_ph ^= 1u; }
         }
@@ -1285,9 +1337,21 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.a_planes = f16x2 ? 1u : 2u;
   p.lo_scale = f16x2 ? 1.0f / 2048.0f : 1.0f;
   const uint32_t ap = p.a_planes;
+  // fused 1x1 shortcut (second source appended to K)
+  if (d->Cin2 < 0 || (d->Cin2 > 0 && (!d->in2_hi || (!f16x2 && !d->in2_lo)))) return fail("bad second source");
+  if (d->Cin2 > 0 && use_v1()) return fail("v1 kernel has no fused shortcut");
+  if (d->Cin2 % 16 != 0) return fail("Cin2 % 16 != 0");
+  p.stride2 = d->stride2 > 0 ? d->stride2 : 1;
+  p.in2_c_off = d->in2_c_off;
+  if (p.stride2 != 1 && p.stride2 != 2) return fail("stride2 must be 1 or 2");
+  if (d->Cin2 > 0 && (d->in2_c_off % 8 || (d->in2_C > 0 && d->in2_C < d->in2_c_off + d->Cin2))) return fail("bad second-source channel window");
+  p.k2_off = d->KD * d->KH * d->KW * d->Cin;
   // kind::f16 instruction descriptor: D = f32 (bit 4); A/B format bf16 = 1 at bits 7 / 10, fp16 = 0
   const uint32_t idesc_fmt = (1u << 4) | (f16x2 ? 0u : ((1u << 7) | (1u << 10)));
-  p.CCHUNK = (d->Cin % 64 == 0) ? 64 : (d->Cin % 32 == 0) ? 32 : 16;
+  {
+    const int cboth = d->Cin | d->Cin2;          // the channel chunk must divide both sources
+    p.CCHUNK = (cboth % 64 == 0) ? 64 : (cboth % 32 == 0) ? 32 : 16;
+  }
   p.layout_type = p.CCHUNK == 64 ? 2u : p.CCHUNK == 32 ? 4u : 6u;
   pl.swz = p.CCHUNK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : p.CCHUNK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                                          : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -1365,7 +1429,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     auto choose = [&](int mt_first) -> bool {
       int best_cc = 0, best_sa = 0, best_sb = 0, best_mt = 0;
       for (int cc = (cc_force ? cc_force : p.CCHUNK); cc >= 16 && !best_cc; cc = (cc_force ? 0 : cc / 2)) {
-        if (d->Cin % cc) continue;
+        if (d->Cin % cc || d->Cin2 % cc) continue;
         for (int mt_try = mt_first; mt_try >= 1 && !best_cc; --mt_try) {
           const uint32_t b_stage = 2u * bn * cc * 2u;
           const uint32_t a_plane = (uint32_t)(mt_try * 16 + 2) * 8u * cc * 2u;
@@ -1392,6 +1456,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
       pl.swz = cc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : cc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
       p.sbo = 8u * cc * 2u;
       p.num_cchunks = d->Cin / cc;
+      p.num_cchunks2 = d->Cin2 / cc;
       p.BN = bn;
       pl.tiles_n = 1;
       p.BW = 8; p.BH = 16; p.BD = 1; p.BNb = 1;
@@ -1444,7 +1509,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   // try the widest channel chunk first, then narrower ones (smaller A stages).
   static int allow_res = [] { const char* e = getenv("MPB200_TC_NO_BRES"); return (e && atoi(e)) ? 0 : 1; }();
   p.b_resident = 0;
-  const uint32_t ktot = (uint32_t)d->KD * d->KH * d->KW * d->Cin;
+  const uint32_t ktot = (uint32_t)d->KD * d->KH * d->KW * d->Cin + (uint32_t)d->Cin2;
   const uint32_t bres_bytes = ktot * (uint32_t)p.BN * 4u;
   const int ntaps = d->KD * d->KH * d->KW;
   const bool all_taps = p.tap_mask == (ntaps == 64 ? ~0ull : ((1ull << ntaps) - 1ull));
@@ -1462,6 +1527,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
       }
     }
   }
+  p.num_cchunks2 = d->Cin2 / p.CCHUNK;
   p.a_bytes = TILE_M * p.CCHUNK * 2;
   p.b_bytes = p.BN * p.CCHUNK * 2;
   p.stage_bytes = p.b_resident ? ap * p.a_bytes : ap * p.a_bytes + 2 * p.b_bytes;
@@ -1527,8 +1593,26 @@ int encode_out_map(CUtensorMap* m, void* ptr, const mp_conv_desc* d, const Plan&
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
 }
 
+// second source of the fused shortcut: [N, D, Ho*stride2, Wo*stride2, in2_C]; same tile box as the main operand, centre tap
+int encode_act2_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const Plan& pl) {
+  const TcParams& p = pl.p;
+  const cuuint64_t C = (cuuint64_t)(d->in2_C > 0 ? d->in2_C : d->Cin2);
+  const cuuint32_t st = (cuuint32_t)p.stride2;
+  const cuuint64_t W2 = (cuuint64_t)p.W * st, H2 = (cuuint64_t)p.H * st;       // p.W / p.H are OUTPUT extents
+  cuuint64_t dims[5] = {C, W2, H2, (cuuint64_t)d->D, (cuuint64_t)d->N};
+  cuuint64_t strides[4] = {C * 2, C * 2 * W2, C * 2 * W2 * H2, C * 2 * W2 * H2 * d->D};
+  cuuint32_t box[5] = {(cuuint32_t)p.CCHUNK, (cuuint32_t)p.BW * st,
+                       (cuuint32_t)((pl.slab ? pl.x.MT * p.BH + 2 : p.BH) * st), (cuuint32_t)p.BD,
+                       (cuuint32_t)(pl.slab ? 1 : p.BNb)};
+  cuuint32_t estr[5] = {1, st, st, 1, 1};
+  const CUtensorMapDataType dt = p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = get_encoder()(m, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(second source) failed (%d)", (int)r);
+}
+
 int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const Plan& pl) {
-  const cuuint64_t ktot = (cuuint64_t)d->KD * d->KH * d->KW * d->Cin;
+  const cuuint64_t ktot = (cuuint64_t)d->KD * d->KH * d->KW * d->Cin + (cuuint64_t)d->Cin2;
   if (pl.p.b_merged) {     // both planes in one box: (K chunk, BN rows, 2 planes) -> [Bh tile | Bl tile] in shared memory
     const CUtensorMapDataType dt3 = pl.p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     cuuint64_t dims3[3] = {ktot, (cuuint64_t)d->Cout_pad, 2};
@@ -1567,7 +1651,7 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
              "mp_conv_tc: operands must be 16-byte aligned");
   {
     static int no_merge = [] { const char* e = getenv("MPB200_TC_NO_BMERGE"); return (e && atoi(e)) ? 1 : 0; }();
-    const size_t plane = (size_t)d->KD * d->KH * d->KW * d->Cin * d->Cout_pad * 2;
+    const size_t plane = ((size_t)d->KD * d->KH * d->KW * d->Cin + d->Cin2) * d->Cout_pad * 2;
     pl.p.b_merged = (!no_merge && !pl.v1 &&
                      reinterpret_cast<const char*>(d->w_lo) == reinterpret_cast<const char*>(d->w_hi) + plane) ? 1 : 0;
   }
@@ -1577,6 +1661,12 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
   if (int e = encode_w_map(&mb_hi, d->w_hi, d, pl)) return e;
   if (pl.p.b_merged) mb_lo = mb_hi;
   else if (int e = encode_w_map(&mb_lo, d->w_lo, d, pl)) return e;
+  CUtensorMap ma2_hi = ma_hi, ma2_lo = ma_lo;     // placeholders when there is no fused shortcut
+  if (d->Cin2 > 0) {
+    MP_REQUIRE((((uintptr_t)d->in2_hi | (uintptr_t)d->in2_lo) & 15) == 0, "mp_conv_tc: second source must be 16-byte aligned");
+    if (int e = encode_act2_map(&ma2_hi, d->in2_hi, d, pl)) return e;
+    if (int e = encode_act2_map(&ma2_lo, pl.p.a_planes == 2 ? d->in2_lo : d->in2_hi, d, pl)) return e;
+  }
   CUtensorMap mo = mb_hi;          // placeholder when the kernel stores with ordinary instructions
   if (pl.p.epi_tma) {
     MP_REQUIRE((reinterpret_cast<uintptr_t>(d->out_hi) & 15) == 0, "mp_conv_tc: output must be 16-byte aligned");
@@ -1621,9 +1711,11 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
       int sms = (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) ? g_num_sms[dev] : 148;
       int grid = pl.p.total_tiles < sms ? pl.p.total_tiles : sms;
       if (pl.slab)
-        k_conv_tc3<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, pl.p, pl.x);
+        k_conv_tc3<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
+                                                                               pl.p, pl.x);
       else
-        k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, pl.p);
+        k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
+                                                                               pl.p);
     }
   }
   MP_LAUNCH_CHECK("mp_conv_tc");

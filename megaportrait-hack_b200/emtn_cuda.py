@@ -65,28 +65,37 @@ class ResNetTrunkPlan:
         self.stem_stride = conv1.stride[0]
         self.blocks: List[Tuple] = []
         pk = lambda c, b: _pack_conv_bn(c, b, prec=prec)
+
+        def pk_last(c, b, blk):
+            """Last convolution of a block; a down-sampling shortcut (1x1 conv + BN, resnet.py:101-118) is folded and
+            fused into its accumulator as extra K columns, so the shortcut tensor never exists in HBM."""
+            if blk.downsample is None:
+                return pk(c, b)
+            w, bias = ops.fold_bn(c.weight.detach(), None if c.bias is None else c.bias.detach(), _bn(b), b.eps)
+            dc, dbn = blk.downsample[0], blk.downsample[1]
+            sc = ops.fold_bn(dc.weight.detach(), None if dc.bias is None else dc.bias.detach(), _bn(dbn), dbn.eps)
+            return ops.pack_conv(w, bias, c.weight.device, prec=prec, shortcut=sc)
+
         for layer in layers:
             for blk in layer:
-                ds = None
-                if blk.downsample is not None:
-                    ds = (pk(blk.downsample[0], blk.downsample[1]), blk.downsample[0].stride[0])
+                ds = None if blk.downsample is None else blk.downsample[0].stride[0]     # stride of the fused shortcut
                 if type(blk).__name__ == "BasicBlock":
-                    convs = [(pk(blk.conv1, blk.bn1), blk.conv1.stride[0]), (pk(blk.conv2, blk.bn2), 1)]
+                    convs = [(pk(blk.conv1, blk.bn1), blk.conv1.stride[0]), (pk_last(blk.conv2, blk.bn2, blk), 1)]
                 else:   # Bottleneck (v1.5: the stride sits on conv2)
                     convs = [(pk(blk.conv1, blk.bn1), 1), (pk(blk.conv2, blk.bn2), blk.conv2.stride[0]),
-                             (pk(blk.conv3, blk.bn3), 1)]
+                             (pk_last(blk.conv3, blk.bn3, blk), 1)]
                 self.blocks.append((convs, ds))
 
     def features(self, x16: Act, last_f32: bool = False) -> Act:
         h, _ = ops.conv(x16, self.stem, act=ACT_RELU, f32=False, split=True, stride=self.stem_stride)
         h = ops.maxpool3x3s2(h)
         for bi, (convs, ds) in enumerate(self.blocks):
-            idt = h if ds is None else ops.conv(h, ds[0], stride=ds[1], f32=True)[0]
             t = h
             for pw, s in convs[:-1]:
                 t, _ = ops.conv(t, pw, stride=s, act=ACT_RELU, f32=False, split=True)
             last = last_f32 and bi == len(self.blocks) - 1
-            h, _ = ops.conv(t, convs[-1][0], stride=convs[-1][1], res=idt, act=ACT_RELU, f32=last, split=not last)
+            link = dict(res=h) if ds is None else dict(src2=h, stride2=ds)       # identity residual | fused 1x1 shortcut
+            h, _ = ops.conv(t, convs[-1][0], stride=convs[-1][1], act=ACT_RELU, f32=last, split=not last, **link)
         return h
 
     def pooled(self, x16: Act) -> torch.Tensor:
@@ -132,14 +141,9 @@ class DualResNet18Plan:
             for bi in range(n_lock, len(pl.blocks)):
                 convs, ds = pl.blocks[bi]
                 win = off if bi == n_lock else 0
-                if ds is None:
-                    idt = g
-                elif half:
-                    idt = ops.conv(g, ds[0], stride=ds[1], in_c_off=win, **fmt)[0]
-                else:
-                    idt = ops.conv(g, ds[0], stride=ds[1], f32=True, in_c_off=win)[0]
                 t, _ = ops.conv(g, convs[0][0], stride=convs[0][1], act=ACT_RELU, in_c_off=win, **fmt)
-                g, _ = ops.conv(t, convs[1][0], res=idt, act=ACT_RELU, **fmt)
+                link = dict(res=g) if ds is None else dict(src2=g, stride2=ds, in2_c_off=win)
+                g, _ = ops.conv(t, convs[1][0], act=ACT_RELU, **link, **fmt)
             feats.append(ops.global_avgpool_f16(g) if half else ops.global_avgpool(g))
         return feats
 

@@ -60,6 +60,8 @@ class ConvDesc(Structure):
         ("KD", c_int), ("KH", c_int), ("KW", c_int), ("Cout_pad", c_int), ("gn_groups", c_int), ("act", c_int),
         ("stride", c_int), ("in_c_off", c_int), ("in_C", c_int), ("out_c_off", c_int), ("out_C", c_int),
         ("prec", c_int),
+        ("Cin2", c_int), ("in2_C", c_int), ("in2_c_off", c_int), ("stride2", c_int),
+        ("in2_hi", c_void_p), ("in2_lo", c_void_p),
     ]
 
 

@@ -369,19 +369,21 @@ class ResBlock2D(nn.Module, _Packed):
         dev = self.conv1.weight.device
         w1, b1 = ops.fold_bn(self.conv1.weight.detach(), self.conv1.bias.detach(), self._bn(self.bn1), self.bn1.eps)
         w2, b2 = ops.fold_bn(self.conv2.weight.detach(), self.conv2.bias.detach(), self._bn(self.bn2), self.bn2.eps)
-        P = {"c1": ops.pack_conv(w1, b1, dev), "c2": ops.pack_conv(w2, b2, dev), "sc": None}
+        sc = None
         if isinstance(self.shortcut, nn.Sequential):
-            ws, bs = ops.fold_bn(self.shortcut[0].weight.detach(), self.shortcut[0].bias.detach(),
-                                 self._bn(self.shortcut[1]), self.shortcut[1].eps)
-            P["sc"] = ops.pack_conv(ws, bs, dev)
-        return P
+            # Conv2d(1x1) + BatchNorm shortcut: folded, then fused into conv2's accumulator as extra K columns, so the
+            # shortcut tensor never exists in HBM (out = relu(W2 * t + Ws . x + b2 + bs))
+            sc = ops.fold_bn(self.shortcut[0].weight.detach(), self.shortcut[0].bias.detach(),
+                             self._bn(self.shortcut[1]), self.shortcut[1].eps)
+        return {"c1": ops.pack_conv(w1, b1, dev), "c2": ops.pack_conv(w2, b2, dev, shortcut=sc), "fused_sc": sc is not None}
 
     def _forward_cl(self, x: Act, f32: bool = False, split: bool = True, stats_groups: int = 0):
         """x: split.  Returns (Act, stats or None)."""
         P = self._plan()
-        idt = x if P["sc"] is None else ops.conv(x, P["sc"], f32=True)[0]
         t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, split=True)
-        return ops.conv(t, P["c2"], res=idt, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
+        if P["fused_sc"]:
+            return ops.conv(t, P["c2"], src2=x, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
+        return ops.conv(t, P["c2"], res=x, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
 
     def forward(self, x):
         _require_inference(self, x)

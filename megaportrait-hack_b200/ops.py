@@ -268,11 +268,12 @@ def group_norm_act(a: Act, G: int, stats: Optional[torch.Tensor] = None, gamma=N
 # ----------------------------------------------------------------------------------------------------- conv
 class PackedConv:
     """Weights of one convolution in kernel format: split-bf16 [Cout_pad, taps*Cin] (tap-major, cin-minor) + bias."""
-    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k", "prec")
+    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k", "prec", "Cin2")
 
-    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k, prec=PREC_SPLIT_BF16):
+    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k, prec=PREC_SPLIT_BF16, Cin2=0):
         self.w_hi, self.w_lo, self.bias = w_hi, w_lo, bias
         self.Cin, self.Cout, self.Cout_pad, self.k, self.prec = Cin, Cout, Cout_pad, tuple(k), prec
+        self.Cin2 = Cin2          # > 0: rows are [taps*Cin | Cin2]: a 1x1 shortcut over a second source is fused in
 
 
 def standardize_weight(w: torch.Tensor) -> torch.Tensor:
@@ -296,7 +297,7 @@ F16_LO_SCALE = 2048.0   # PREC_F16X2: w_lo holds (w - fp16(w)) * 2^11 so that it
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, cin_pad: int = 0,
-              prec: int = PREC_SPLIT_BF16) -> PackedConv:
+              prec: int = PREC_SPLIT_BF16, shortcut: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None) -> PackedConv:
     """weight (Cout, Cin, [kd,] kh, kw) float32/64 -> PackedConv on `device`.  `cin_pad` zero-pads the input-channel
     axis (RGB stems run on the tensor-core kernel with their 3 channels padded to 16).  `prec` selects the operand
     format: split-bf16 planes, or fp16 hi + scaled fp16 lo for the two-pass convolution."""
@@ -307,7 +308,19 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, c
     if cin_pad and cin_pad > w.shape[1]:
         w = torch.cat([w, torch.zeros(w.shape[0], cin_pad - w.shape[1], *w.shape[2:], dtype=w.dtype, device=device)], 1)
     Cout, Cin, kd, kh, kw = w.shape
-    wk = w.permute(0, 2, 3, 4, 1).reshape(Cout, kd * kh * kw * Cin).to(torch.float32)
+    wk = w.permute(0, 2, 3, 4, 1).reshape(Cout, kd * kh * kw * Cin)
+    Cin2 = 0
+    if shortcut is not None:
+        # `shortcut` = (weight (Cout, Cin2, 1, 1[, 1]), bias): a 1x1 convolution of a second source added inside the
+        # accumulator (ResBlock2D / down-sampling ResNet blocks): its columns extend K, its bias joins the bias
+        ws, bs = shortcut
+        ws = ws.detach().to(device=device, dtype=torch.float64).reshape(Cout, -1)
+        Cin2 = ws.shape[1]
+        wk = torch.cat([wk, ws], 1)
+        if bs is not None:
+            bias = bs if bias is None else bias.detach().to(device=device, dtype=torch.float64) + \
+                bs.detach().to(device=device, dtype=torch.float64)
+    wk = wk.to(torch.float32)
     Cout_pad = (Cout + 15) // 16 * 16
     if Cout_pad != Cout:
         wk = torch.cat([wk, torch.zeros(Cout_pad - Cout, wk.shape[1], device=device)], 0)
@@ -319,7 +332,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, c
         lo = (wk - hi.float()).to(torch.bfloat16)
     b = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
     planes = torch.stack((hi, lo)).contiguous()      # one allocation: the kernel then fetches [hi | lo] with ONE TMA load
-    return PackedConv(planes[0], planes[1], b, Cin, Cout, Cout_pad, (kd, kh, kw), prec)
+    return PackedConv(planes[0], planes[1], b, Cin, Cout, Cout_pad, (kd, kh, kw), prec, Cin2)
 
 
 def pack_stem3x3_f16(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> PackedConv:
@@ -343,9 +356,12 @@ def set_conv_mode(mode: str) -> None:
 
 def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE, f32: bool = True,
          split: bool = False, stats_groups: int = 0, mode: Optional[str] = None, stride: int = 1, in_c_off: int = 0,
-         out: Optional[Act] = None, out_c_off: int = 0, h16: bool = False) -> Tuple[Act, Optional[torch.Tensor]]:
+         out: Optional[Act] = None, out_c_off: int = 0, h16: bool = False, src2: Optional[Act] = None,
+         stride2: int = 1, in2_c_off: int = 0) -> Tuple[Act, Optional[torch.Tensor]]:
     """act(conv(a) + bias + res) -> (Act, GroupNorm statistics of the written values or None).
 
+    `src2` feeds the fused 1x1 shortcut of a `pack_conv(..., shortcut=...)` plan: an activation in the same operand
+    format whose grid is `stride2` times the output grid.
     `pw.prec == PREC_F16X2` runs the two-pass fp16 kernel: `a` (and `res`, unless it is fp32) must carry an fp16 plane
     and `h16=True` asks for an fp16 output plane.
 
@@ -391,14 +407,26 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     d.KD, d.KH, d.KW = pw.k
     d.Cout_pad, d.gn_groups, d.act = pw.Cout_pad, (0 if late_stats else stats_groups), act
     d.stride, d.in_c_off, d.in_C, d.out_c_off, d.out_C = stride, in_c_off, C, out_c_off, out.shape[4]
+    if pw.Cin2:
+        if src2 is None or src2.shape[:4] != (N, D, Ho * stride2, Wo * stride2) or in2_c_off + pw.Cin2 > src2.shape[4]:
+            raise RuntimeError(f"conv: the fused shortcut needs a second source on a {stride2}x grid with {pw.Cin2} channels")
+        if half and src2.h16 is None:
+            raise RuntimeError("conv: a PREC_F16X2 shortcut source needs an fp16 activation plane")
+        if not half and src2.hi is None:
+            ensure_split(src2)
+        d.Cin2, d.in2_C, d.in2_c_off, d.stride2 = pw.Cin2, src2.shape[4], in2_c_off, stride2
+        d.in2_hi, d.in2_lo = (_p(src2.h16), None) if half else (_p(src2.hi), _p(src2.lo))
+    elif src2 is not None:
+        raise RuntimeError("conv: src2 given but the packed weights hold no fused shortcut")
     L = _lib.load()
     mode = mode or _CONV_MODE
     use_tc = mode == "tc" or (mode == "auto" and L.mp_conv_tc_supported(ctypes.byref(d)) == 1)
-    flops = 2 * N * D * Ho * Wo * pw.Cout * pw.Cin * pw.k[0] * pw.k[1] * pw.k[2]
+    flops = 2 * N * D * Ho * Wo * pw.Cout * (pw.Cin * pw.k[0] * pw.k[1] * pw.k[2] + pw.Cin2)
     if half and not use_tc:
         raise RuntimeError(f"conv: shape {a.shape} x {pw.Cin}->{pw.Cout} is not supported by the fp16 two-pass kernel")
     with _Prof(("conv_tc" if use_tc else "conv_simt") + ("_h" if half else "") +
-               f"|{N}x{D}x{H}x{W} {pw.Cin}->{pw.Cout} k{pw.k[0]}{pw.k[1]}{pw.k[2]} s{stride}", flops):
+               f"|{N}x{D}x{H}x{W} {pw.Cin}->{pw.Cout} k{pw.k[0]}{pw.k[1]}{pw.k[2]} s{stride}" +
+               (f" +sc{pw.Cin2}" if pw.Cin2 else ""), flops):
         if use_tc:
             _lib.check(L.mp_conv_tc(ctypes.byref(d), _stream()), "mp_conv_tc")
         else:

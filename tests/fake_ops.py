@@ -145,7 +145,7 @@ def affine_act(a, ab, res=None, act=ops.ACT_NONE, f32=False, split=True):
 
 
 def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=0, mode=None, stride=1, in_c_off=0,
-         out=None, out_c_off=0, h16=False):
+         out=None, out_c_off=0, h16=False, src2=None, stride2=1, in2_c_off=0):
     half = pw.prec == ops.PREC_F16X2
     kd, kh, kw = pw.k
     if half:     # two-pass fp16: one fp16 activation plane, fp16 hi + scaled fp16 lo weights
@@ -157,8 +157,13 @@ def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=
         ensure_split(a)
         x = _to_ncdhw(a.hi.float() + a.lo.float())[:, in_c_off:in_c_off + pw.Cin]
         wf = pw.w_hi.float() + pw.w_lo.float()
-    w = wf[: pw.Cout].view(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3)
+    kmain = kd * kh * kw * pw.Cin
+    w = wf[: pw.Cout, :kmain].reshape(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3)
     y = F.conv3d(x, w.contiguous(), pw.bias, stride=(1, stride, stride), padding=(kd // 2, kh // 2, kw // 2))
+    if pw.Cin2:     # fused 1x1 shortcut over the second source
+        x2 = _to_ncdhw(src2.h16.float() if half else src2.hi.float() + src2.lo.float())[:, in2_c_off:in2_c_off + pw.Cin2]
+        w2 = wf[: pw.Cout, kmain:].reshape(pw.Cout, pw.Cin2, 1, 1, 1)
+        y = y + F.conv3d(x2, w2.contiguous(), None, stride=(1, stride2, stride2))
     v = _to_cl(y)
     if res is not None:
         rv = _val(res)

@@ -528,3 +528,44 @@ def test_bilinear_upsample_split_2x2_blocks(ops, shape):
     got = (u.hi.float() + u.lo.float()).cpu().squeeze(1).permute(0, 3, 1, 2)
     assert got.shape == ref.shape
     assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+# ----------------------------------------------------------------------------------------------------- fused 1x1 shortcut
+SHORTCUT_CASES = [
+    # name,        N, Cin, Cout, H,  W,  k, Cin2, stride2, in2_C, in2_off, prec
+    ("g2d_up3",    2, 64,  64,   64, 64, 3, 128,  1,       128,   0,       0),    # slab kernel, MT = 2, split-bf16
+    ("g2d_up1",    1, 256, 256,  32, 32, 3, 512,  1,       512,   0,       0),    # general kernel, two N tiles
+    ("r50_conv3",  2, 64,  256,  32, 32, 1, 128,  2,       128,   0,       0),    # 1x1 main + stride-2 1x1 shortcut
+    ("r18_l2_h",   2, 128, 128,  32, 32, 3, 64,   2,       128,   64,      1),    # fp16 two-pass, slab, windowed source
+    ("r18_l4_h",   2, 512, 512,  16, 16, 3, 256,  2,       256,   0,       1),    # fp16 two-pass, general kernel
+]
+
+
+@pytest.mark.parametrize("case", SHORTCUT_CASES, ids=[c[0] for c in SHORTCUT_CASES])
+def test_conv_fused_1x1_shortcut(ops, case):
+    """out = relu(conv_kxk(t) + conv_1x1_stride2(x) + b): the shortcut is accumulated in TMEM (ResBlock2D model.py:616-640,
+    down-sampling ResNet blocks resnet.py:101-118) instead of travelling through HBM as a residual tensor."""
+    name, N, Cin, Cout, H, W, k, Cin2, s2, in2_C, off, prec = case
+    half = prec == 1
+    t = rnd(N, Cin, 1, H, W, seed=81)
+    x = rnd(N, in2_C, 1, H * s2, W * s2, seed=82)
+    w = rnd(Cout, Cin, k, k, seed=83) / math.sqrt(Cin * k * k)
+    ws = rnd(Cout, Cin2, 1, 1, seed=84) / math.sqrt(Cin2)
+    b, bs = rnd(Cout, seed=85) * 0.1, rnd(Cout, seed=86) * 0.1
+    pw = ops.pack_conv(w, b, DEV, prec=prec, shortcut=(ws, bs))
+    assert pw.Cin2 == Cin2 and pw.w_hi.shape[1] == Cin * k * k + Cin2
+    if half:
+        ta, xa = _h16_act(ops, t), _h16_act(ops, x)
+        tq, xq = _f16(t).float(), _f16(x).float()
+        out, _ = ops.conv(ta, pw, act=ops.ACT_RELU, f32=True, h16=True, src2=xa, stride2=s2, in2_c_off=off, mode="tc")
+    else:
+        ta, xa = ops.from_nchw(t.to(DEV)), ops.from_nchw(x.to(DEV))
+        tq, xq = t, x
+        out, _ = ops.conv(ta, pw, act=ops.ACT_RELU, f32=True, split=True, src2=xa, stride2=s2, in2_c_off=off, mode="tc")
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(tq.squeeze(2), w, b, padding=k // 2) +
+                 F.conv2d(xq.squeeze(2)[:, off:off + Cin2], ws, bs, stride=s2))
+    got = out.f32.cpu().squeeze(1).permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 3e-5, name
+    with pytest.raises(RuntimeError, match="second source"):
+        ops.conv(ta, pw, mode="tc")
