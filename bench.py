@@ -199,6 +199,19 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if args.profile_step:
+        # `ncu --profile-from-start off ...`: warm up, then expose exactly ONE eager step to the profiler and exit
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 1)):
+                sharded.step(xs_d, xd_d)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
+            sharded.step(xs_d, xd_d)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     with torch.no_grad():
         for _ in range(args.warmup):
             step(xs_d, xd_d)
@@ -388,6 +401,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--dump-launches", default="", help="write the per-launch CUDA-event profile of one step here")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, bracket ONE eager step with cudaProfilerStart/Stop and exit (ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
