@@ -31,6 +31,7 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 192;    // v1 kernel
 constexpr int NUM_THREADS2 = 320;   // v2: producer + MMA + 8 epilogue warps
+constexpr int NUM_THREADS3 = 352;   // v3 (slab): + a second MMA-issuing warp (one accumulator each when MT = 2)
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
@@ -828,7 +829,7 @@ struct SlabExtra {
   uint32_t b_ring_off;        // byte offset of the B ring
 };
 
-__global__ void __launch_bounds__(NUM_THREADS2, 1)
+__global__ void __launch_bounds__(NUM_THREADS3, 1)
 k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
            const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_a2_hi,
@@ -858,10 +859,13 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   const uint32_t row_bytes = (uint32_t)p.CCHUNK * 2u;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < x.SA; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), 1); }
-    for (int i = 0; i < x.SB; ++i) { mbar_init(fullB(i), 1); mbar_init(emptyB(i), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
-    for (int i = 0; i < SQ; ++i) { mbar_init(sfull + i * 8, 1); mbar_init(sempty + i * 8, 9); }
+    // with MT = 2 accumulators per weight tile TWO warps issue MMAs (one accumulator each): every "consumed" barrier then
+    // collects one tcgen05.commit per issuer
+    const uint32_t nissue = x.MT == 2 ? 2u : 1u;
+    for (int i = 0; i < x.SA; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), nissue); }
+    for (int i = 0; i < x.SB; ++i) { mbar_init(fullB(i), 1); mbar_init(emptyB(i), nissue); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), nissue); mbar_init(tempty_bar(b), 8); }
+    for (int i = 0; i < SQ; ++i) { mbar_init(sfull + i * 8, 1); mbar_init(sempty + i * 8, 8 + nissue); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
@@ -945,9 +949,12 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       }
       sched_finish(p);
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (whole warp, elected lane issues)
-    {
+  } else if (warp == 1 || warp == 10) {
+    // ===================================================================== MMA issuers (whole warp, elected lane issues)
+    // warp 1 owns accumulator 0 (and all of them when MT = 1); warp 10 owns accumulator 1 when MT = 2: the single
+    // dependent instruction stream of one issuing warp cannot keep 64-cycle (N <= 128) MMAs back to back
+    const int t0 = warp == 1 ? 0 : 1, tstep = x.MT == 2 ? 2 : 1;
+    if (t0 < x.MT && (warp == 1 || x.MT == 2)) {
       const int ksteps = p.CCHUNK / 16;
       const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
       uint32_t it = 0, sidx = 0, a_ph = 0, bidx = 0, b_ph = 0;   // ring positions / phases (no div/mod on the issue path)
@@ -971,7 +978,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             mbar_wait(fullB(bidx), b_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t b_hi = smem_base + x.b_ring_off + bidx * b_stage, b_lo = b_hi + p.b_bytes;
-            for (int t = 0; t < x.MT; ++t) {
+            for (int t = t0; t < x.MT; t += tstep) {
               const uint32_t a_hi = sa + (uint32_t)t * acc_step + (uint32_t)kh * kh_step;
               const uint32_t a_lo = a_hi + x.a_plane_bytes;
               const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.acc_w);
@@ -992,7 +999,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + sidx * a_stage;
           const uint32_t b_hi = smem_base + x.b_ring_off + bidx * b_stage, b_lo = b_hi + p.b_bytes;
-          for (int t = 0; t < x.MT; ++t) {
+          for (int t = t0; t < x.MT; t += tstep) {
             const uint32_t a_hi = sa + (uint32_t)t * acc_step + kh_step;
             const uint32_t a_lo = a_hi + x.a_plane_bytes;
             const uint32_t d_tmem = d_tmem0 + (uint32_t)(t * p.acc_w);
@@ -1711,7 +1718,7 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
       int sms = (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) ? g_num_sms[dev] : 148;
       int grid = pl.p.total_tiles < sms ? pl.p.total_tiles : sms;
       if (pl.slab)
-        k_conv_tc3<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
+        k_conv_tc3<<<grid, NUM_THREADS3, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
                                                                                pl.p, pl.x);
       else
         k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
