@@ -489,11 +489,25 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
 // drains 32-column blocks of one 128 x BN accumulator -- [Bh] + 2^-11 [Bl] + bias (+ fp16 residual), activation,
 // round to fp16 -- into a 128B-swizzled staging tile ((BN/64) sub-tiles of [128 rows][64 fp16]) that one thread then
 // writes to HBM with TMA bulk stores.  No per-thread global stores, no barrier inside the column loop.
+// The fp16 residual of this thread's row (32 columns per block, at most two blocks for BN <= 128) is fetched into
+// registers BEFORE the thread waits for the accumulator, so its latency hides behind the MMAs of the tile.
+__device__ __forceinline__ void residual_prefetch_h(const TcParams& p, int n0, int64_t obase, int half, bool row_valid,
+                                                    uint4 rp[8]) {
+  const f16* res = reinterpret_cast<const f16*>(p.res_hi);
+  if (!res || !row_valid) return;
+  int blk = 0;
+  for (int c0 = half * 32; c0 < p.BN && blk < 2; c0 += 64, ++blk) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rp[blk * 4 + i] = *reinterpret_cast<const uint4*>(res + obase + n0 + c0 + i * 8);
+  }
+}
+
 __device__ __forceinline__ void epilogue_stage_h(const TcParams& p, uint32_t stage, uint32_t tmem_acc, int n0,
-                                                 int64_t obase, int half, int r, bool row_valid) {
+                                                 int64_t obase, int half, int r, bool row_valid, const uint4 rp[8]) {
   const bool bias_vec = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
   const f16* res = reinterpret_cast<const f16*>(p.res_hi);
-  for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+  int blk = 0;
+  for (int c0 = half * 32; c0 < p.BN; c0 += 64, ++blk) {
     float v[32], v2[32];
     tmem_ld32(tmem_acc + (uint32_t)c0, v);
     tmem_ld32(tmem_acc + (uint32_t)(p.BN + c0), v2);
@@ -513,7 +527,9 @@ __device__ __forceinline__ void epilogue_stage_h(const TcParams& p, uint32_t sta
     if (res && row_valid) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(res + obase + co0 + i);
+        // blocks 0 and 1 come from the prefetch registers (static indexing keeps them in registers)
+        const uint4 raw = blk == 0 ? rp[i >> 3] : blk == 1 ? rp[4 + (i >> 3)]
+                                                           : *reinterpret_cast<const uint4*>(res + obase + co0 + i);
         const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -773,6 +789,8 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       const bool row_valid = n + ni < p.N;
       const int64_t pos = (((int64_t)(n + ni) * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
       const int64_t obase = pos * p.out_C + p.out_c_off;
+      uint4 rp[8];
+      if (p.epi_tma) residual_prefetch_h(p, n0, obase, half, row_valid, rp);
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (p.epi_tma) {
@@ -783,7 +801,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
         }
         epi_bar();
         epilogue_stage_h(p, stage, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.acc_w), n0, obase, half, r,
-                         row_valid);
+                         row_valid, rp);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(b));
@@ -1030,11 +1048,22 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       int n, d0, h0, w0, n0;
       tile_coords(tile, n, d0, h0, w0, n0);
       const uint32_t b = it & 1;
+      const int ww = r % p.BW, hh = r / p.BW;
+      // MT <= 2: both accumulators' residual rows are in flight (in two statically indexed register sets) while the MMAs
+      // of the tile finish
+      uint4 rp0[8], rp1[8];
+      auto obase_of = [&](int t) {
+        const int64_t pos = (((int64_t)n * p.D + d0) * p.H + h0 + t * p.BH + hh) * p.W + w0 + ww;
+        return pos * p.out_C + p.out_c_off;
+      };
+      if (p.epi_tma) {
+        residual_prefetch_h(p, n0, obase_of(0), half, true, rp0);
+        if (x.MT == 2) residual_prefetch_h(p, n0, obase_of(1), half, true, rp1);
+      }
       mbar_wait(tfull_bar(b), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int t = 0; t < x.MT; ++t) {
-        const int ww = r % p.BW, hh = r / p.BW;
-        const int64_t pos = (((int64_t)n * p.D + d0) * p.H + h0 + t * p.BH + hh) * p.W + w0 + ww;
+      auto drain = [&](int t, const uint4* rp) {
+        const int64_t obase = obase_of(t);
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b * x.MT + t) * p.acc_w);
         if (p.epi_tma) {
           const uint32_t stage = smem_base + p.tma_off + (p.tma_nbuf == 2 ? (se & 1u) : 0u) * p.tma_buf_bytes;
@@ -1044,7 +1073,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             else bulk_wait_read<0>();
           }
           epi_bar();
-          epilogue_stage_h(p, stage, tacc, n0, pos * p.out_C + p.out_c_off, half, r, true);
+          epilogue_stage_h(p, stage, tacc, n0, obase, half, r, true, rp);
           fence_proxy_async();
           epi_bar();
           if (et == 0) {
@@ -1053,9 +1082,11 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
             bulk_commit();
           }
         } else {
-          epilogue_drain(p, epi, row_off, s_stats, tacc, n0, pos * p.out_C + p.out_c_off, half, r, et, lane);
+          epilogue_drain(p, epi, row_off, s_stats, tacc, n0, obase, half, r, et, lane);
         }
-      }
+      };
+      drain(0, rp0);
+      if (x.MT == 2) drain(1, rp1);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(b));
