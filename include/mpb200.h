@@ -117,9 +117,19 @@ typedef struct mp_conv_desc {
   int Cin2, in2_C, in2_c_off, stride2;
   const void* in2_hi;
   const void* in2_lo;
+  /* MP_PREC_F16_Q8 (prec = 2): fp16 main product + both cross terms in FP8 (e4m3) -- two pass-units instead of three.
+   * Operand format "F16_Q8": hi = fp16 plane; lo = a byte plane with 2 bytes per element, laid out per 64-channel
+   * group as [64 x e4m3(x)] [64 x e4m3((x - fp16(x)) * 2048)] (weights: [e4m3(wl * 2048 * sw)] [e4m3(w * sw)], sw a
+   * power of two); the kernel accumulates fp16(x)*fp16(w) with kind::f16 MMAs and x8*wl8 + xl8*w8 with kind::f8f6f4
+   * MMAs (twice the rate) side by side in TMEM and adds the second sum scaled by corr_scale = 1 / (2048 * sw).
+   * Channels must be multiples of 64.  out_fmt / res_fmt select the plane format of out_hi/out_lo and res_hi/res_lo
+   * independently of `prec` (0 = the native format of `prec`), so format changes ride on a convolution's epilogue. */
+  int out_fmt, res_fmt;
+  float corr_scale;
 } mp_conv_desc;
 
-enum { MP_PREC_SPLIT_BF16 = 0, MP_PREC_F16X2 = 1 };
+enum { MP_PREC_SPLIT_BF16 = 0, MP_PREC_F16X2 = 1, MP_PREC_F16_Q8 = 2 };
+enum { MP_FMT_NATIVE = 0, MP_FMT_SPLIT_BF16 = 1, MP_FMT_F16 = 2, MP_FMT_F16_Q8 = 3 };
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores fed by TMA (3-pass split-bf16, fp32 accumulate in TMEM).
  * Requires Cin % 16 == 0 and a 128-position output tile that is a box of the (D,H,W) grid. */

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -49,6 +50,29 @@ struct __align__(16) f16x8 {
 struct __align__(8) f16x4 {
   f16 v[4];
 };
+
+// "F16_Q8" operand format (MP_PREC_F16_Q8): fp16 plane + byte plane; per 64-channel group the byte plane holds
+// [64 x e4m3(x)] [64 x e4m3((x - fp16(x)) * 2048)].  Byte offset of channel ch inside a position's 2*C bytes:
+__device__ __forceinline__ int mp_q8_off(int ch) { return ((ch >> 6) << 7) + (ch & 63); }
+__device__ __forceinline__ uint16_t mp_e4m3x2(float a, float b) {
+  return (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ float mp_e4m3_to_float(uint8_t v) {
+  return __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)v, __NV_E4M3)));
+}
+// 8 consecutive channels -> (fp16 x 8, e4m3(x) x 8, e4m3((x - fp16 x) * 2048) x 8)
+__device__ __forceinline__ void mp_hq_pack8(const float* x, f16x8& h, uint2& a8, uint2& al8) {
+  float l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h.v[i] = mp_to_f16(x[i]);
+    l[i] = (x[i] - __half2float(h.v[i])) * 2048.f;
+  }
+  a8.x = (uint32_t)mp_e4m3x2(x[0], x[1]) | ((uint32_t)mp_e4m3x2(x[2], x[3]) << 16);
+  a8.y = (uint32_t)mp_e4m3x2(x[4], x[5]) | ((uint32_t)mp_e4m3x2(x[6], x[7]) << 16);
+  al8.x = (uint32_t)mp_e4m3x2(l[0], l[1]) | ((uint32_t)mp_e4m3x2(l[2], l[3]) << 16);
+  al8.y = (uint32_t)mp_e4m3x2(l[4], l[5]) | ((uint32_t)mp_e4m3x2(l[6], l[7]) << 16);
+}
 
 // 4 consecutive channels <-> 8-byte bf16x4 vectors
 struct __align__(8) bf16x4 {

@@ -177,10 +177,12 @@ __global__ void __launch_bounds__(THREADS) k_conv_simt(ConvArgs a) {
 
 int mp_conv_validate(const mp_conv_desc* d, const char* who) {
   MP_REQUIRE(d, "%s: null descriptor", who);
-  MP_REQUIRE(d->prec == MP_PREC_SPLIT_BF16 || d->prec == MP_PREC_F16X2, "%s: unknown prec", who);
+  MP_REQUIRE(d->prec == MP_PREC_SPLIT_BF16 || d->prec == MP_PREC_F16X2 || d->prec == MP_PREC_F16_Q8, "%s: unknown prec", who);
+  MP_REQUIRE(d->prec != MP_PREC_F16_Q8 || d->corr_scale > 0.f, "%s: MP_PREC_F16_Q8 needs corr_scale", who);
   const bool one_plane = d->prec == MP_PREC_F16X2;
   MP_REQUIRE(d->in_hi && (d->in_lo || one_plane) && d->w_hi && d->w_lo, "%s: null operand", who);
-  MP_REQUIRE(d->out_f32 || (d->out_hi && (d->out_lo || one_plane)), "%s: no output", who);
+  MP_REQUIRE(d->out_f32 || (d->out_hi && (d->out_lo || (one_plane && d->out_fmt != MP_FMT_SPLIT_BF16 && d->out_fmt != MP_FMT_F16_Q8) || d->out_fmt == MP_FMT_F16)),
+             "%s: no output", who);
   MP_REQUIRE(!one_plane || !d->stats, "%s: fused GroupNorm statistics are not available in fp16 two-pass mode", who);
   MP_REQUIRE(d->N > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "%s: bad dims", who);
   MP_REQUIRE(d->KD % 2 == 1 && d->KH % 2 == 1 && d->KW % 2 == 1, "%s: kernel extents must be odd", who);
@@ -199,6 +201,7 @@ extern "C" int mp_conv_simt(const mp_conv_desc* d, void* stream) {
   if (int e = mp_conv_validate(d, "mp_conv_simt")) return e;
   MP_REQUIRE(d->prec == MP_PREC_SPLIT_BF16, "mp_conv_simt: only the split-bf16 operand format is implemented");
   MP_REQUIRE(d->Cin2 == 0, "mp_conv_simt: the fused 1x1 shortcut is implemented by mp_conv_tc only");
+  MP_REQUIRE(d->out_fmt <= MP_FMT_SPLIT_BF16 && d->res_fmt <= MP_FMT_SPLIT_BF16, "mp_conv_simt: split-bf16 planes only");
   ConvArgs a;
   a.in_hi = (const bf16*)d->in_hi; a.in_lo = (const bf16*)d->in_lo;
   a.w_hi = (const bf16*)d->w_hi; a.w_lo = (const bf16*)d->w_lo;

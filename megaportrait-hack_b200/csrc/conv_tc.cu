@@ -71,6 +71,7 @@ struct TcParams {
   uint32_t epi_bytes;         // size of the register-store staging area (0 when the TMA-store epilogue is used)
   int num_cchunks2, k2_off;   // fused 1x1 shortcut: channel chunks of the second source, K offset of its weights
   int stride2, in2_c_off;
+  int out_fmt, res_fmt;       // effective MP_FMT_* of (out_hi, out_lo) and (res_hi, res_lo)
   int b_merged;               // 1: map_b_hi is a 3-D map (K, Cout_pad, plane) and one TMA load fetches [Bh | Bl]
   unsigned int* sched;        // dynamic tile scheduler: {next-tile counter, finished-CTA counter}, or NULL = static walk
 };
@@ -220,6 +221,27 @@ __device__ __forceinline__ void umma_commit_e(uint32_t bar) {
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
       : "memory");
 }
+// FP8 (e4m3 x e4m3) MMA: K = 32 bytes per instruction, i.e. the same 32-byte descriptor step as a K = 16 fp16 MMA
+__device__ __forceinline__ void umma_f8_e(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// cross terms of one 64-channel chunk: A bytes [x8 | xl8] (128 per row) against B bytes [wl8 | w8]: four K = 32 MMAs
+template <int KS>
+__device__ __forceinline__ void umma_chunk_q8(uint32_t tmem_d, uint32_t a_q, uint32_t b_q, uint32_t hi, uint32_t idesc,
+                                              uint32_t acc_first) {
+  const uint32_t aq = desc_lo_word(a_q), bq = desc_lo_word(b_q);
+#pragma unroll
+  for (int k = 0; k < KS; ++k) umma_f8_e(tmem_d, aq + 2 * k, bq + 2 * k, hi, idesc, k == 0 ? acc_first : 1u);
+}
 // one K-chunk (KS k-steps) of the 3-pass split product into accumulator tmem_d
 template <int KS>
 __device__ __forceinline__ void umma_chunk(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
@@ -349,12 +371,20 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
             const float4 rr = *reinterpret_cast<const float4*>(p.res_f32 + obase + co0 + hc + i);
             v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
           }
-        } else if (p.res_hi && p.prec == MP_PREC_F16X2) {
+        } else if (p.res_hi && p.res_fmt != MP_FMT_SPLIT_BF16) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const f16x4 rr = *reinterpret_cast<const f16x4*>(reinterpret_cast<const f16*>(p.res_hi) + obase + co0 + hc + i);
             v[i] += __half2float(rr.v[0]); v[i + 1] += __half2float(rr.v[1]);
             v[i + 2] += __half2float(rr.v[2]); v[i + 3] += __half2float(rr.v[3]);
+          }
+          if (p.res_fmt == MP_FMT_F16_Q8) {     // x = fp16 plane + e4m3 low part / 2048 (16 channels = 16 bytes)
+            const int ch = p.out_c_off + co0 + hc;
+            const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.res_lo) +
+                                                              2 * (obase - p.out_c_off) + mp_q8_off(ch) + 64);
+            const uint8_t* b8 = reinterpret_cast<const uint8_t*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(mp_e4m3_to_float(b8[i]), 1.0f / 2048.0f, v[i]);
           }
         } else if (p.res_hi) {
 #pragma unroll
@@ -370,7 +400,7 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
             const int64_t o = obase + co0 + hc + i;
             if (p.bias) v[i] += __ldg(p.bias + co0 + hc + i);
             if (p.res_f32) v[i] += p.res_f32[o];
-            else if (p.res_hi && p.prec == MP_PREC_F16X2) v[i] += __half2float(reinterpret_cast<const f16*>(p.res_hi)[o]);
+            else if (p.res_hi && p.res_fmt == MP_FMT_F16) v[i] += __half2float(reinterpret_cast<const f16*>(p.res_hi)[o]);
             else if (p.res_hi) v[i] += mp_join(p.res_hi[o], p.res_lo[o]);
           }
         }
@@ -406,7 +436,27 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
         }
       }
     }
-    if (p.out_hi && p.prec == MP_PREC_F16X2) {
+    if (p.out_hi && p.out_fmt == MP_FMT_F16_Q8) {
+      // fp16 plane + byte plane (vec8 is guaranteed: channel counts are multiples of 64)
+      f16* oh = reinterpret_cast<f16*>(p.out_hi);
+      uint8_t* oq = reinterpret_cast<uint8_t*>(p.out_lo);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int row = j * 64 + (et >> 2), c8 = (et & 3) * 8;
+        if (c8 < ncol && row_off[row] >= 0) {
+          const float4 x0 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8);
+          const float4 x1 = *reinterpret_cast<const float4*>(epi + row * EPI_PITCH + c8 + 4);
+          const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          f16x8 h;
+          uint2 a8, al8;
+          mp_hq_pack8(xs, h, a8, al8);
+          *reinterpret_cast<f16x8*>(oh + row_off[row] + co0 + c8) = h;
+          uint8_t* q = oq + 2 * (row_off[row] - p.out_c_off) + mp_q8_off(p.out_c_off + co0 + c8);
+          *reinterpret_cast<uint2*>(q) = a8;
+          *reinterpret_cast<uint2*>(q + 64) = al8;
+        }
+      }
+    } else if (p.out_hi && p.out_fmt == MP_FMT_F16) {
       f16* oh = reinterpret_cast<f16*>(p.out_hi);
       if (vec8) {
 #pragma unroll
@@ -610,7 +660,7 @@ __device__ __forceinline__ void sched_finish(const TcParams& p) {
 // Persistent: grid = min(#tiles, #SMs); every role walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 // TMEM holds TWO accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.  The epilogue stages 32-column
 // chunks in shared memory (padded rows) and writes them out with warp-contiguous 16-byte stores.
-__global__ void __launch_bounds__(NUM_THREADS2, 1)
+__global__ void __launch_bounds__(NUM_THREADS3, 1)
 k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
            const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_a2_hi,
@@ -639,18 +689,21 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   const int num_kb = __popcll(p.tap_mask) * p.num_cchunks + p.num_cchunks2;
 
   if (threadIdx.x == 0) {
+    // MP_PREC_F16_Q8: two MMA-issuing warps (warp 1: fp16 main product, warp 10: FP8 cross terms), so every barrier
+    // that tracks MMA completion collects one tcgen05.commit per issuer
+    const uint32_t nissue = p.prec == MP_PREC_F16_Q8 ? 2u : 1u;
     for (int s = 0; s < p.STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), nissue);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1);
+      mbar_init(tfull_bar(b), nissue);
       mbar_init(tempty_bar(b), 8);      // one arrival per epilogue warp
     }
     mbar_init(bres_bar, 1);
     for (int i = 0; i < SQ; ++i) {
       mbar_init(sfull + i * 8, 1);
-      mbar_init(sempty + i * 8, 9);     // the MMA thread + one lane of each epilogue warp
+      mbar_init(sempty + i * 8, 8 + nissue);     // the MMA warp(s) + one lane of each epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
@@ -733,9 +786,12 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       }
       sched_finish(p);
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (whole warp, elected lane issues)
-    {
+  } else if (warp == 1 || warp == 10) {
+    // ===================================================================== MMA issuers (whole warp, elected lane issues)
+    // warp 10 exists for MP_PREC_F16_Q8 only: it issues the FP8 cross-term MMAs into the accumulator's second column
+    // half while warp 1 issues the fp16 main product into the first
+    const bool q8_issuer = warp == 10;
+    if (!q8_issuer || p.prec == MP_PREC_F16_Q8) {
       const int ksteps = p.CCHUNK / 16;
       const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
       uint32_t it = 0, s = 0, ph_bit = 0;        // smem ring position / phase (no div/mod on the issue path)
@@ -757,7 +813,11 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
           const uint32_t b_hi =
               p.b_resident ? smem_base + p.bres_off + (uint32_t)i * 2u * p.b_bytes : sa + p.a_planes * p.a_bytes;
           const uint32_t b_lo = b_hi + p.b_bytes;
-          if (p.prec == MP_PREC_F16X2) umma_chunk_h_dyn(ksteps, d_tmem, a_hi, b_hi, dhi, p.idesc2, i > 0 ? 1u : 0u);
+          if (p.prec == MP_PREC_F16_Q8) {
+            // 64-channel chunks: [fp16 x fp16] -> columns [0, BN), [x8|xl8] x [wl8|w8] -> columns [BN, 2 BN)
+            if (q8_issuer) umma_chunk_q8<4>(d_tmem + (uint32_t)p.BN, a_lo, b_lo, dhi, p.idesc, i > 0 ? 1u : 0u);
+            else umma_chunk_h<4>(d_tmem, a_hi, b_hi, dhi, p.idesc, i > 0 ? 1u : 0u);
+          } else if (p.prec == MP_PREC_F16X2) umma_chunk_h_dyn(ksteps, d_tmem, a_hi, b_hi, dhi, p.idesc2, i > 0 ? 1u : 0u);
           else if (p.dualb) umma_chunk_dual_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, dhi, p.idesc, p.idesc2, i > 0 ? 1u : 0u);
           else umma_chunk_dyn(ksteps, d_tmem, a_hi, a_lo, b_hi, b_lo, dhi, p.idesc, i > 0 ? 1u : 0u);
           umma_commit_e(empty_bar(s));
@@ -1353,6 +1413,8 @@ bool tma_epi_ok(const mp_conv_desc* d, int bn) {
   const int out_C = d->out_C > 0 ? d->out_C : d->Cout;
   // worth it where the epilogue, not the main loop, bounds a tile: K = taps*Cin up to 1152
   if ((int64_t)d->KD * d->KH * d->KW * d->Cin > 1152) return false;
+  if (d->out_fmt > MP_FMT_F16 || d->res_fmt > MP_FMT_F16 || d->out_fmt == MP_FMT_SPLIT_BF16 || d->res_fmt == MP_FMT_SPLIT_BF16)
+    return false;
   return allow_tma_epi() && d->prec == MP_PREC_F16X2 && d->out_hi && !d->out_f32 && !d->stats && bn % 64 == 0 &&
          d->Cout == d->Cout_pad && out_C % 8 == 0 && d->out_c_off % 8 == 0 &&
          (!d->res_hi || (reinterpret_cast<uintptr_t>(d->res_hi) & 15) == 0) && !d->res_f32;
@@ -1368,12 +1430,25 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   auto fail = [&](const char* why) { return report ? mp_set_error("mp_conv_tc: unsupported shape: %s", why) : 1; };
   if (d->Cin % 16 != 0) return fail("Cin % 16 != 0");
   if (d->Cout_pad % 16 != 0) return fail("Cout_pad % 16 != 0");
-  if (d->prec != MP_PREC_SPLIT_BF16 && d->prec != MP_PREC_F16X2) return fail("unknown prec");
+  if (d->prec != MP_PREC_SPLIT_BF16 && d->prec != MP_PREC_F16X2 && d->prec != MP_PREC_F16_Q8) return fail("unknown prec");
   const bool f16x2 = d->prec == MP_PREC_F16X2;
+  const bool f16q8 = d->prec == MP_PREC_F16_Q8;
+  if (f16q8 && use_v1()) return fail("v1 kernel has no fp16 + fp8 mode");
+  if (f16q8 && (d->Cin % 64 || d->Cin2 % 64)) return fail("fp16 + fp8 mode needs input channels in multiples of 64");
+  {
+    const int native = f16q8 ? MP_FMT_F16_Q8 : f16x2 ? MP_FMT_F16 : MP_FMT_SPLIT_BF16;
+    p.out_fmt = d->out_fmt ? d->out_fmt : native;
+    p.res_fmt = d->res_fmt ? d->res_fmt : native;
+    if (p.out_fmt < MP_FMT_SPLIT_BF16 || p.out_fmt > MP_FMT_F16_Q8 || p.res_fmt < MP_FMT_SPLIT_BF16 || p.res_fmt > MP_FMT_F16_Q8)
+      return fail("unknown out_fmt / res_fmt");
+    const int out_C = d->out_C > 0 ? d->out_C : d->Cout;
+    if ((p.out_fmt == MP_FMT_F16_Q8 && d->out_hi) || (p.res_fmt == MP_FMT_F16_Q8 && d->res_hi))
+      if (out_C % 64 || d->out_c_off % 64 || d->Cout % 64) return fail("the fp16 + fp8 plane format needs 64-channel groups");
+  }
   if (f16x2 && use_v1()) return fail("v1 kernel has no fp16 two-pass mode");
   p.prec = d->prec;
   p.a_planes = f16x2 ? 1u : 2u;
-  p.lo_scale = f16x2 ? 1.0f / 2048.0f : 1.0f;
+  p.lo_scale = f16x2 ? 1.0f / 2048.0f : f16q8 ? d->corr_scale : 1.0f;
   const uint32_t ap = p.a_planes;
   // fused 1x1 shortcut (second source appended to K)
   if (d->Cin2 < 0 || (d->Cin2 > 0 && (!d->in2_hi || (!f16x2 && !d->in2_lo)))) return fail("bad second source");
@@ -1385,7 +1460,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   if (d->Cin2 > 0 && (d->in2_c_off % 8 || (d->in2_C > 0 && d->in2_C < d->in2_c_off + d->Cin2))) return fail("bad second-source channel window");
   p.k2_off = d->KD * d->KH * d->KW * d->Cin;
   // kind::f16 instruction descriptor: D = f32 (bit 4); A/B format bf16 = 1 at bits 7 / 10, fp16 = 0
-  const uint32_t idesc_fmt = (1u << 4) | (f16x2 ? 0u : ((1u << 7) | (1u << 10)));
+  const uint32_t idesc_fmt = (1u << 4) | ((f16x2 || f16q8) ? 0u : ((1u << 7) | (1u << 10)));
   {
     const int cboth = d->Cin | d->Cin2;          // the channel chunk must divide both sources
     p.CCHUNK = (cboth % 64 == 0) ? 64 : (cboth % 32 == 0) ? 32 : 16;
@@ -1438,7 +1513,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
   p.BN = 0;
   for (int c : cands)
-    if (c <= bn_cap && (!f16x2 || c <= 128) && d->Cout_pad % c == 0) { p.BN = c; break; }   // fp16 mode: N = 2*BN <= 256
+    if (c <= bn_cap && (!(f16x2 || f16q8) || c <= 128) && d->Cout_pad % c == 0) { p.BN = c; break; }   // two column halves
   if (!p.BN) return fail("no N tile");
   while ((int64_t)pl.tiles_m * (d->Cout_pad / p.BN) < 148 && p.BN % 32 == 0 && p.BN > 32) p.BN /= 2;
   pl.tiles_n = d->Cout_pad / p.BN;
@@ -1448,7 +1523,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   static int allow_slab = [] { const char* e = getenv("MPB200_TC_NO_SLAB"); return (e && atoi(e)) ? 0 : 1; }();
   if (pl.v1 && (p.stride != 1 || p.in_c_off || p.out_c_off || p.out_C != d->Cout || (d->in_C > 0 && d->in_C != d->Cin)))
     return fail("v1 kernel has no stride / channel-window support");
-  if (!pl.v1 && allow_slab && p.stride == 1 && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) &&
+  if (!pl.v1 && allow_slab && !f16q8 && p.stride == 1 && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) &&
       d->Cout_pad <= 128 && d->W % 8 == 0 && d->H % 16 == 0) {
     const int bn = d->Cout_pad;
     const bool tma_s = tma_epi_ok(d, bn);
@@ -1582,8 +1657,9 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.tma_nbuf = nbuf_g;
   p.epi_bytes = (tma_g || pl.v1) ? 0u : EPI_BYTES;
   p.epi_off = tma_g ? p.tma_off + p.tma_nbuf * p.tma_buf_bytes : p.bres_off + (p.b_resident ? bres_bytes : 0);
-  p.dualb = (!pl.v1 && (allow_dual() || f16x2) && 2 * 2 * p.BN <= 512) ? 1 : 0;
-  if (f16x2 && !p.dualb) return fail("fp16 two-pass mode needs the [Bh|Bl] column layout (BN <= 128)");
+  p.dualb = (!pl.v1 && (allow_dual() || f16x2 || f16q8) && 2 * 2 * p.BN <= 512) ? 1 : 0;
+  if ((f16x2 || f16q8) && !p.dualb) return fail("fp16 modes need the two-half accumulator layout (BN <= 128)");
+  if (f16q8 && p.CCHUNK != 64) return fail("fp16 + fp8 mode needs 64-channel K chunks");
   p.acc_w = p.dualb ? 2 * p.BN : p.BN;
   p.tmem_cols = next_pow2(pl.v1 ? p.BN : 2 * p.acc_w);
   p.idesc2 = idesc_fmt | ((uint32_t)(2 * p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
@@ -1610,7 +1686,7 @@ int encode_act_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const
                        (cuuint32_t)(pl.slab ? pl.x.MT * pl.p.BH + 2 : pl.p.BH * st), (cuuint32_t)pl.p.BD,
                        (cuuint32_t)(pl.slab ? 1 : pl.p.BNb)};
   cuuint32_t estr[5] = {1, st, st, 1, 1};
-  const CUtensorMapDataType dt = pl.p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = pl.p.prec != MP_PREC_SPLIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = get_encoder()(m, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1643,7 +1719,7 @@ int encode_act2_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, cons
                        (cuuint32_t)((pl.slab ? pl.x.MT * p.BH + 2 : p.BH) * st), (cuuint32_t)p.BD,
                        (cuuint32_t)(pl.slab ? 1 : p.BNb)};
   cuuint32_t estr[5] = {1, st, st, 1, 1};
-  const CUtensorMapDataType dt = p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = p.prec != MP_PREC_SPLIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = get_encoder()(m, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(second source) failed (%d)", (int)r);
@@ -1652,7 +1728,7 @@ int encode_act2_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, cons
 int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const Plan& pl) {
   const cuuint64_t ktot = (cuuint64_t)d->KD * d->KH * d->KW * d->Cin + (cuuint64_t)d->Cin2;
   if (pl.p.b_merged) {     // both planes in one box: (K chunk, BN rows, 2 planes) -> [Bh tile | Bl tile] in shared memory
-    const CUtensorMapDataType dt3 = pl.p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapDataType dt3 = pl.p.prec != MP_PREC_SPLIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     cuuint64_t dims3[3] = {ktot, (cuuint64_t)d->Cout_pad, 2};
     cuuint64_t strides3[2] = {ktot * 2, ktot * 2 * (cuuint64_t)d->Cout_pad};
     cuuint32_t box3[3] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BN, 2};
@@ -1665,7 +1741,7 @@ int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const P
   cuuint64_t strides[1] = {ktot * 2};
   cuuint32_t box[2] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BN};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt = pl.p.prec == MP_PREC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = pl.p.prec != MP_PREC_SPLIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = get_encoder()(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1752,7 +1828,7 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
         k_conv_tc3<<<grid, NUM_THREADS3, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
                                                                                pl.p, pl.x);
       else
-        k_conv_tc2<<<grid, NUM_THREADS2, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
+        k_conv_tc2<<<grid, NUM_THREADS3, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
                                                                                pl.p);
     }
   }

@@ -20,7 +20,8 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC"]
 
 ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID = 0, 1, 2, 3
-PREC_SPLIT_BF16, PREC_F16X2 = 0, 1   # mp_conv_desc.prec
+PREC_SPLIT_BF16, PREC_F16X2, PREC_F16_Q8 = 0, 1, 2   # mp_conv_desc.prec
+FMT_NATIVE, FMT_SPLIT_BF16, FMT_F16, FMT_F16_Q8 = 0, 1, 2, 3   # mp_conv_desc.out_fmt / res_fmt
 ABI_VERSION = 3
 
 
@@ -62,6 +63,7 @@ class ConvDesc(Structure):
         ("prec", c_int),
         ("Cin2", c_int), ("in2_C", c_int), ("in2_c_off", c_int), ("stride2", c_int),
         ("in2_hi", c_void_p), ("in2_lo", c_void_p),
+        ("out_fmt", c_int), ("res_fmt", c_int), ("corr_scale", c_float),
     ]
 
 

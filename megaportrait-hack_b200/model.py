@@ -15,6 +15,8 @@ from __future__ import annotations
 import math
 from typing import Dict, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -22,6 +24,9 @@ import torch.nn.functional as F
 from . import ops
 from .emtn import COMPRESS_DIM, FEATURE_SIZE, FEATURE_SIZE_AVG_POOL, CustomResNet50, Emtn, SixDRepNet_Detector  # noqa: F401
 from .ops import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, Act
+
+# G2d's identity res-blocks on the fp16 + FP8 cross-term convolution (MPB200_G2D_PREC=split selects three-pass split-bf16)
+_Q8_ENABLED = os.environ.get("MPB200_G2D_PREC", "q8") != "split"
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")   # model.py:51 (kept for callers that read it)
 
@@ -366,20 +371,35 @@ class ResBlock2D(nn.Module, _Packed):
                                       "(SURVEY.md 8f-2); call .eval()")
         if self.downsample:
             raise NotImplementedError("ResBlock2D(downsample=True) is never used by the reference hot path")
-        dev = self.conv1.weight.device
-        w1, b1 = ops.fold_bn(self.conv1.weight.detach(), self.conv1.bias.detach(), self._bn(self.bn1), self.bn1.eps)
-        w2, b2 = ops.fold_bn(self.conv2.weight.detach(), self.conv2.bias.detach(), self._bn(self.bn2), self.bn2.eps)
         sc = None
         if isinstance(self.shortcut, nn.Sequential):
             # Conv2d(1x1) + BatchNorm shortcut: folded, then fused into conv2's accumulator as extra K columns, so the
             # shortcut tensor never exists in HBM (out = relu(W2 * t + Ws . x + b2 + bs))
             sc = ops.fold_bn(self.shortcut[0].weight.detach(), self.shortcut[0].bias.detach(),
                              self._bn(self.shortcut[1]), self.shortcut[1].eps)
-        return {"c1": ops.pack_conv(w1, b1, dev), "c2": ops.pack_conv(w2, b2, dev, shortcut=sc), "fused_sc": sc is not None}
+        # identity-shortcut blocks inside G2d run the fp16 + FP8 cross-term convolution (`G2d` sets `_mp_q8`): two
+        # pass-units instead of three at the same end-to-end accuracy (tests/precision_study.py)
+        prec = ops.PREC_F16_Q8 if (sc is None and getattr(self, "_mp_q8", False) and _Q8_ENABLED) else ops.PREC_SPLIT_BF16
+        c1, c2 = self._pack_pair(prec, sc)
+        return {"c1": c1, "c2": c2, "fused_sc": sc is not None, "q8": prec == ops.PREC_F16_Q8}
 
-    def _forward_cl(self, x: Act, f32: bool = False, split: bool = True, stats_groups: int = 0):
-        """x: split.  Returns (Act, stats or None)."""
+    def _pack_pair(self, prec, sc=None):
+        dev = self.conv1.weight.device
+        w1, b1 = ops.fold_bn(self.conv1.weight.detach(), self.conv1.bias.detach(), self._bn(self.bn1), self.bn1.eps)
+        w2, b2 = ops.fold_bn(self.conv2.weight.detach(), self.conv2.bias.detach(), self._bn(self.bn2), self.bn2.eps)
+        return ops.pack_conv(w1, b1, dev, prec=prec), ops.pack_conv(w2, b2, dev, shortcut=sc, prec=prec)
+
+    def _forward_cl(self, x: Act, f32: bool = False, split: bool = True, stats_groups: int = 0, hq_out: bool = False):
+        """x: split (or fp16 + FP8 planes for a `_mp_q8` block).  Returns (Act, stats or None)."""
         P = self._plan()
+        if P["q8"] and x.q8 is not None:
+            t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, hq=True)
+            return ops.conv(t, P["c2"], res=x, act=ACT_RELU, f32=f32, split=split and not hq_out, hq=hq_out)
+        if P["q8"]:          # a G2d block called on its own with split planes: three-pass packs, built on first use
+            if "c1_split" not in P:
+                P["c1_split"], P["c2_split"] = self._pack_pair(ops.PREC_SPLIT_BF16)
+            t, _ = ops.conv(x, P["c1_split"], act=ACT_RELU, f32=False, split=True)
+            return ops.conv(t, P["c2_split"], res=x, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
         t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, split=True)
         if P["fused_sc"]:
             return ops.conv(t, P["c2"], src2=x, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
@@ -400,6 +420,8 @@ class G2d(nn.Module, _Packed):
         self.reshape = nn.Conv2d(96, 1536, kernel_size=1)
         self.conv1x1 = nn.Conv2d(1536, 512, kernel_size=1)
         self.res_blocks = nn.Sequential(*[ResBlock2D(512, 512) for _ in range(8)])
+        for blk in self.res_blocks:
+            blk._mp_q8 = True     # identity res-blocks: fp16 + FP8 cross-term convolutions (see ResBlock2D._build_plan)
         self.upsample1 = nn.Sequential(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
                                        ResBlock2D(512, 256))
         self.upsample2 = nn.Sequential(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
@@ -431,9 +453,10 @@ class G2d(nn.Module, _Packed):
     def _forward_cl(self, x: Act) -> torch.Tensor:
         """x: split channels-last [N,1,64,64,96] -> RGB NCHW fp32 [N,3,512,512]."""
         P = self._plan()
-        h, _ = ops.conv(x, P["in"], f32=False, split=True)
-        for blk in self.res_blocks:
-            h, _ = blk._forward_cl(h)
+        q8 = _Q8_ENABLED and all(blk._plan()["q8"] for blk in self.res_blocks)
+        h, _ = ops.conv(x, P["in"], f32=False, split=not q8, hq=q8)
+        for i, blk in enumerate(self.res_blocks):
+            h, _ = blk._forward_cl(h, hq_out=q8 and i + 1 < len(self.res_blocks))
         st = None
         for i, up in enumerate((self.upsample1, self.upsample2, self.upsample3)):
             u = ops.upsample2x_linear(h, 1, f32=False, split=True)

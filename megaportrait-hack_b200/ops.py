@@ -8,13 +8,15 @@ two-pass `PREC_F16X2` convolution.  Every function launches on the current torch
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 from typing import Optional, Sequence, Tuple
 
 import torch
 
 from . import lib as _lib
-from .lib import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, PREC_F16X2, PREC_SPLIT_BF16, ConvDesc  # noqa: F401
+from .lib import (ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, FMT_F16_Q8, FMT_SPLIT_BF16, PREC_F16_Q8,  # noqa: F401
+                  PREC_F16X2, PREC_SPLIT_BF16, ConvDesc)
 
 LAUNCHES = 0   # number of libmpb200 kernel launches issued by this process (bench.py reports it)
 PROFILE = None  # when a list: (kind, start_event, end_event, algorithmic_flops, algorithmic_bytes) per hot launch
@@ -91,12 +93,13 @@ def _chk_cuda(t: torch.Tensor, dtype, what: str) -> None:
 
 
 class Act:
-    """Channels-last activation [N, D, H, W, C]: `f32` and/or the split pair (`hi`, `lo`) and/or one fp16 plane `h16`."""
-    __slots__ = ("f32", "hi", "lo", "h16", "shape")
+    """Channels-last activation [N, D, H, W, C]: `f32` and/or the split pair (`hi`, `lo`) and/or one fp16 plane `h16`
+    (optionally with the FP8 byte plane `q8` [N, D, H, W, 2C] of the "F16_Q8" operand format, include/mpb200.h)."""
+    __slots__ = ("f32", "hi", "lo", "h16", "q8", "shape")
 
-    def __init__(self, shape, f32=None, hi=None, lo=None, h16=None):
+    def __init__(self, shape, f32=None, hi=None, lo=None, h16=None, q8=None):
         self.shape = tuple(int(s) for s in shape)
-        self.f32, self.hi, self.lo, self.h16 = f32, hi, lo, h16
+        self.f32, self.hi, self.lo, self.h16, self.q8 = f32, hi, lo, h16, q8
 
     @property
     def N(self): return self.shape[0]
@@ -119,8 +122,10 @@ class Act:
         return self.hi is not None
 
 
-def _alloc(shape, device, f32: bool, split: bool, h16: bool = False):
+def _alloc(shape, device, f32: bool, split: bool, h16: bool = False, q8: bool = False):
     a = Act(shape)
+    if q8:
+        a.q8 = torch.empty(tuple(shape[:-1]) + (2 * shape[-1],), dtype=torch.uint8, device=device)
     if f32:
         a.f32 = torch.empty(shape, dtype=torch.float32, device=device)
     if split:
@@ -268,10 +273,11 @@ def group_norm_act(a: Act, G: int, stats: Optional[torch.Tensor] = None, gamma=N
 # ----------------------------------------------------------------------------------------------------- conv
 class PackedConv:
     """Weights of one convolution in kernel format: split-bf16 [Cout_pad, taps*Cin] (tap-major, cin-minor) + bias."""
-    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k", "prec", "Cin2")
+    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k", "prec", "Cin2", "corr_scale")
 
-    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k, prec=PREC_SPLIT_BF16, Cin2=0):
+    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k, prec=PREC_SPLIT_BF16, Cin2=0, corr_scale=0.0):
         self.w_hi, self.w_lo, self.bias = w_hi, w_lo, bias
+        self.corr_scale = corr_scale   # PREC_F16_Q8: weight of the FP8 cross-term accumulator, 1 / (2048 * sw)
         self.Cin, self.Cout, self.Cout_pad, self.k, self.prec = Cin, Cout, Cout_pad, tuple(k), prec
         self.Cin2 = Cin2          # > 0: rows are [taps*Cin | Cin2]: a 1x1 shortcut over a second source is fused in
 
@@ -294,6 +300,20 @@ def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: dict, eps: float = 1
 
 
 F16_LO_SCALE = 2048.0   # PREC_F16X2: w_lo holds (w - fp16(w)) * 2^11 so that it stays in fp16's normal range
+
+
+def e4m3(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest-even, saturating float -> float8_e4m3fn (what `__nv_cvt_float2_to_fp8x2(.., SATFINITE, E4M3)` does)."""
+    return x.float().clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+
+
+def q8_planes(x: torch.Tensor) -> torch.Tensor:
+    """fp32 channels-last [..., C] (C % 64 == 0) -> the byte plane [..., 2C] of the F16_Q8 operand format."""
+    h = x.clamp(-65504.0, 65504.0).to(torch.float16)
+    a8 = e4m3(x).view(torch.uint8)
+    al8 = e4m3((x - h.float()) * F16_LO_SCALE).view(torch.uint8)
+    lead = x.shape[:-1]
+    return torch.stack((a8.reshape(*lead, -1, 64), al8.reshape(*lead, -1, 64)), -2).reshape(*lead, -1)
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, cin_pad: int = 0,
@@ -324,7 +344,20 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, c
     Cout_pad = (Cout + 15) // 16 * 16
     if Cout_pad != Cout:
         wk = torch.cat([wk, torch.zeros(Cout_pad - Cout, wk.shape[1], device=device)], 0)
-    if prec == PREC_F16X2:
+    corr_scale = 0.0
+    if prec == PREC_F16_Q8:
+        # fp16 main plane + byte plane: per 64-wide K chunk [e4m3(wl * 2048 * sw) x 64 | e4m3(w * sw) x 64]
+        if wk.shape[1] % 64:
+            raise RuntimeError("pack_conv: PREC_F16_Q8 needs input channels in multiples of 64")
+        hi = wk.to(torch.float16)
+        amax = float(wk.abs().max())
+        sw = 2.0 ** (-math.floor(math.log2(amax))) if amax > 0 else 1.0        # max |w * sw| in [1, 2)
+        wl8 = e4m3((wk - hi.float()) * (F16_LO_SCALE * sw)).view(torch.uint8)
+        w8 = e4m3(wk * sw).view(torch.uint8)
+        q = torch.stack((wl8.view(Cout_pad, -1, 64), w8.view(Cout_pad, -1, 64)), 2).reshape(Cout_pad, -1)
+        corr_scale = 1.0 / (F16_LO_SCALE * sw)
+        hi, lo = hi.contiguous().view(torch.uint8), q.contiguous()            # both [Cout_pad, 2K] bytes
+    elif prec == PREC_F16X2:
         hi = wk.to(torch.float16)
         lo = ((wk - hi.float()) * F16_LO_SCALE).to(torch.float16)
     else:
@@ -332,7 +365,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, c
         lo = (wk - hi.float()).to(torch.bfloat16)
     b = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
     planes = torch.stack((hi, lo)).contiguous()      # one allocation: the kernel then fetches [hi | lo] with ONE TMA load
-    return PackedConv(planes[0], planes[1], b, Cin, Cout, Cout_pad, (kd, kh, kw), prec, Cin2)
+    return PackedConv(planes[0], planes[1], b, Cin, Cout, Cout_pad, (kd, kh, kw), prec, Cin2, corr_scale)
 
 
 def pack_stem3x3_f16(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> PackedConv:
@@ -343,6 +376,51 @@ def pack_stem3x3_f16(weight: torch.Tensor, bias: Optional[torch.Tensor], device=
     w = weight.detach().double().permute(0, 2, 3, 1).reshape(Cout, 27)
     w = torch.cat([w, torch.zeros(Cout, 5, dtype=w.dtype, device=w.device)], 1).reshape(Cout, 32, 1, 1)
     return pack_conv(w, bias, device or weight.device, prec=PREC_F16X2)
+
+
+def _conv_q8(a: Act, pw: PackedConv, res: Optional[Act], act: int, f32: bool, split: bool, stats_groups: int,
+             hq: bool) -> Tuple[Act, Optional[torch.Tensor]]:
+    """Convolutions around the F16_Q8 operand format (fp16 plane + FP8 byte plane): `pw.prec == PREC_F16_Q8` consumes it
+    (fp16 main product + FP8 cross terms), `hq=True` produces it -- from either kind of convolution, so the format change
+    rides on an epilogue.  Stride 1, no channel windows; the residual may be fp32, split or F16_Q8."""
+    q8_in = pw.prec == PREC_F16_Q8
+    if q8_in and (a.h16 is None or a.q8 is None):
+        raise RuntimeError("conv: a PREC_F16_Q8 convolution needs an activation with fp16 + FP8 planes")
+    if not q8_in and a.hi is None:
+        ensure_split(a)
+    if pw.Cin2 or pw.Cin != a.C or (hq and split):
+        raise RuntimeError("conv: unsupported F16_Q8 configuration")
+    N, D, H, W, C = a.shape
+    out = _alloc((N, D, H, W, pw.Cout), a.device, f32, split, hq, hq)
+    stats = new_stats(N, stats_groups, a.device) if stats_groups else None
+    d = ConvDesc()
+    d.w_hi, d.w_lo, d.bias, d.prec, d.corr_scale = _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias), pw.prec, pw.corr_scale
+    d.in_hi, d.in_lo = (_p(a.h16), _p(a.q8)) if q8_in else (_p(a.hi), _p(a.lo))
+    if res is not None:
+        if res.shape != out.shape:
+            raise RuntimeError(f"conv: residual shape {res.shape} != output shape {out.shape}")
+        if res.f32 is not None:
+            d.res_f32 = _p(res.f32)
+        elif res.q8 is not None:
+            d.res_hi, d.res_lo, d.res_fmt = _p(res.h16), _p(res.q8), FMT_F16_Q8
+        else:
+            d.res_hi, d.res_lo, d.res_fmt = _p(res.hi), _p(res.lo), FMT_SPLIT_BF16
+    d.out_f32, d.stats = _p(out.f32), _p(stats)
+    if hq:
+        d.out_hi, d.out_lo, d.out_fmt = _p(out.h16), _p(out.q8), FMT_F16_Q8
+    else:
+        d.out_hi, d.out_lo, d.out_fmt = _p(out.hi), _p(out.lo), FMT_SPLIT_BF16
+    d.N, d.D, d.H, d.W, d.Cin, d.Cout = N, D, H, W, pw.Cin, pw.Cout
+    d.KD, d.KH, d.KW = pw.k
+    d.Cout_pad, d.gn_groups, d.act = pw.Cout_pad, stats_groups, act
+    d.stride, d.in_C, d.out_C = 1, C, pw.Cout
+    L = _lib.load()
+    flops = 2 * N * D * H * W * pw.Cout * pw.Cin * pw.k[0] * pw.k[1] * pw.k[2]
+    with _Prof(("conv_tc_q8" if q8_in else "conv_tc") + f"|{N}x{D}x{H}x{W} {pw.Cin}->{pw.Cout} k{pw.k[0]}{pw.k[1]}{pw.k[2]} s1",
+               flops):
+        _lib.check(L.mp_conv_tc(ctypes.byref(d), _stream()), "mp_conv_tc")
+    _count()
+    return out, stats
 
 
 _CONV_MODE = os.environ.get("MPB200_CONV", "auto")   # auto | tc | simt
@@ -357,7 +435,7 @@ def set_conv_mode(mode: str) -> None:
 def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE, f32: bool = True,
          split: bool = False, stats_groups: int = 0, mode: Optional[str] = None, stride: int = 1, in_c_off: int = 0,
          out: Optional[Act] = None, out_c_off: int = 0, h16: bool = False, src2: Optional[Act] = None,
-         stride2: int = 1, in2_c_off: int = 0) -> Tuple[Act, Optional[torch.Tensor]]:
+         stride2: int = 1, in2_c_off: int = 0, hq: bool = False) -> Tuple[Act, Optional[torch.Tensor]]:
     """act(conv(a) + bias + res) -> (Act, GroupNorm statistics of the written values or None).
 
     `src2` feeds the fused 1x1 shortcut of a `pack_conv(..., shortcut=...)` plan: an activation in the same operand
@@ -367,6 +445,8 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
 
     `stride` (1|2) applies to H and W.  `in_c_off` selects the window [in_c_off, in_c_off + pw.Cin) of a's channels;
     `out` / `out_c_off` write into the channel window of an existing activation (grouped convolutions)."""
+    if pw.prec == PREC_F16_Q8 or hq:
+        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq)
     half = pw.prec == PREC_F16X2
     if half:
         if a.h16 is None:

@@ -27,10 +27,21 @@ def _f16(x):
     return x.clamp(-65504.0, 65504.0).to(torch.float16)
 
 
+def _q8_decode(q8):
+    """byte plane [..., 2C] -> (e4m3(x), e4m3((x - fp16 x) * 2048)) as fp32 [..., C] each"""
+    lead = q8.shape[:-1]
+    g = q8.reshape(*lead, -1, 2, 64).view(torch.float8_e4m3fn).float()
+    return g[..., 0, :].reshape(*lead, -1), g[..., 1, :].reshape(*lead, -1)
+
+
 def _val(a: Act) -> torch.Tensor:
     if a.f32 is not None:
         return a.f32
-    return a.h16.float() if a.hi is None else a.hi.float() + a.lo.float()
+    if a.hi is not None:
+        return a.hi.float() + a.lo.float()
+    if a.q8 is not None:          # F16_Q8: fp16 plane + low part / 2048
+        return a.h16.float() + _q8_decode(a.q8)[1] / ops.F16_LO_SCALE
+    return a.h16.float()
 
 
 def _mk(x: torch.Tensor, f32: bool, split: bool, h16: bool = False) -> Act:
@@ -144,8 +155,36 @@ def affine_act(a, ab, res=None, act=ops.ACT_NONE, f32=False, split=True):
     return _mk(_act(v, act), f32, split)
 
 
+def _conv_q8(a, pw, res, act, f32, split, stats_groups, hq):
+    """fp16 main product + FP8 cross terms (PREC_F16_Q8) and / or F16_Q8 output planes, as the kernel computes them."""
+    kd, kh, kw = pw.k
+    pad = (kd // 2, kh // 2, kw // 2)
+    shape_w = lambda m: m[: pw.Cout].reshape(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3).contiguous()
+    if pw.prec == ops.PREC_F16_Q8:
+        wh = pw.w_hi.view(torch.float16).float()
+        wl8, w8 = _q8_decode(pw.w_lo)
+        a8, al8 = _q8_decode(a.q8)
+        y = F.conv3d(_to_ncdhw(a.h16.float()), shape_w(wh), pw.bias, padding=pad)
+        corr = F.conv3d(_to_ncdhw(a8), shape_w(wl8), None, padding=pad) + F.conv3d(_to_ncdhw(al8), shape_w(w8), None, padding=pad)
+        y = y + corr * pw.corr_scale
+    else:
+        ensure_split(a)
+        y = F.conv3d(_to_ncdhw(a.hi.float() + a.lo.float()), shape_w(pw.w_hi.float() + pw.w_lo.float()), pw.bias, padding=pad)
+    v = _to_cl(y)
+    if res is not None:
+        v = v + _val(res)
+    v = _act(v, act)
+    st = _stats_of(v, stats_groups) if stats_groups else None
+    out = _mk(v, f32, split, hq)
+    if hq:
+        out.q8 = ops.q8_planes(v.contiguous())
+    return out, st
+
+
 def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=0, mode=None, stride=1, in_c_off=0,
-         out=None, out_c_off=0, h16=False, src2=None, stride2=1, in2_c_off=0):
+         out=None, out_c_off=0, h16=False, src2=None, stride2=1, in2_c_off=0, hq=False):
+    if pw.prec == ops.PREC_F16_Q8 or hq:
+        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq)
     half = pw.prec == ops.PREC_F16X2
     kd, kh, kw = pw.k
     if half:     # two-pass fp16: one fp16 activation plane, fp16 hi + scaled fp16 lo weights

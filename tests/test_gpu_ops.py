@@ -569,3 +569,67 @@ def test_conv_fused_1x1_shortcut(ops, case):
     assert (got - ref).abs().max().item() / ref.abs().max().item() < 3e-5, name
     with pytest.raises(RuntimeError, match="second source"):
         ops.conv(ta, pw, mode="tc")
+
+
+# ----------------------------------------------------------------------------------------------------- fp16 + FP8 cross terms
+def _q8_decode(q8):
+    lead = q8.shape[:-1]
+    g = q8.reshape(*lead, -1, 2, 64).view(torch.float8_e4m3fn).float()
+    return g[..., 0, :].reshape(*lead, -1), g[..., 1, :].reshape(*lead, -1)
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W,k", [(512, 512, 32, 32, 3), (64, 128, 16, 16, 1), (128, 64, 16, 32, 3)],
+                         ids=["g2d_res", "k1", "n64"])
+def test_conv_f16_q8(ops, Cin, Cout, H, W, k):
+    """MP_PREC_F16_Q8: fp16 x fp16 main product (kind::f16) + the two cross terms as e4m3 x e4m3 (kind::f8f6f4) in a second
+    TMEM accumulator, issued by two warps; checked against the same arithmetic on the CPU and against fp32."""
+    N = 2
+    x = rnd(N, Cin, 1, H, W, seed=91) * 1.3
+    r = rnd(N, Cout, 1, H, W, seed=92)
+    w = rnd(Cout, Cin, k, k, seed=93) / math.sqrt(Cin * k * k)
+    b = rnd(Cout, seed=94) * 0.1
+    # producer side: a split-bf16 1x1 identity-like conv is overkill; build the F16_Q8 planes with the host packer, which
+    # the epilogue must reproduce bit for bit (checked below on the output planes)
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous()
+    a = ops.Act(tuple(xcl.shape), h16=_f16(xcl).to(DEV), q8=ops.q8_planes(xcl).to(DEV))
+    rcl = r.permute(0, 2, 3, 4, 1).contiguous()
+    res = ops.Act(tuple(rcl.shape), h16=_f16(rcl).to(DEV), q8=ops.q8_planes(rcl).to(DEV))
+    pw = ops.pack_conv(w, b, DEV, prec=ops.PREC_F16_Q8)
+    assert pw.prec == ops.PREC_F16_Q8 and pw.corr_scale > 0
+    out, _ = ops.conv(a, pw, res=res, act=ops.ACT_RELU, f32=True, hq=True)
+    torch.cuda.synchronize()
+    # exact emulation of the kernel's operands
+    wh = pw.w_hi.cpu().view(torch.float16).float()
+    wl8, w8 = _q8_decode(pw.w_lo.cpu())
+    a8, al8 = _q8_decode(a.q8.cpu())
+    shp = lambda m: m[:Cout].reshape(Cout, k, k, Cin).permute(0, 3, 1, 2).contiguous()
+    ncl = lambda t: t.squeeze(1).permute(0, 3, 1, 2).contiguous()
+    y = F.conv2d(ncl(a.h16.float().cpu()), shp(wh), b, padding=k // 2)
+    y = y + (F.conv2d(ncl(a8), shp(wl8), None, padding=k // 2) + F.conv2d(ncl(al8), shp(w8), None, padding=k // 2)) * pw.corr_scale
+    rv = res.h16.float().cpu() + _q8_decode(res.q8.cpu())[1] / 2048.0
+    ref = F.relu(y + ncl(rv))
+    got = ncl(out.f32.cpu())
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() / scale < 2e-5
+    # F16_Q8 output planes = host packer applied to the fp32 result
+    assert torch.equal(out.h16.cpu(), _f16(out.f32.cpu()))
+    assert torch.equal(out.q8.cpu(), ops.q8_planes(out.f32.cpu()))
+    # and the whole thing is an fp32-grade convolution: cross terms at e4m3 precision leave ~2^-16 relative error
+    full = F.relu(F.conv2d(x.squeeze(2), w, b, padding=k // 2) + r.squeeze(2))
+    assert (got - full).abs().max().item() / scale < 1e-4
+
+
+def test_conv_split_in_f16_q8_out_and_back(ops):
+    """Format changes ride on epilogues: split-bf16 conv -> F16_Q8 planes; F16_Q8 conv -> split-bf16 planes."""
+    N, C, H, W = 1, 64, 16, 16
+    x = rnd(N, C, 1, H, W, seed=95)
+    w = rnd(128, C, 1, 1, seed=96) / 8
+    a = ops.from_nchw(x.to(DEV))
+    o1, _ = ops.conv(a, ops.pack_conv(w, None, DEV), f32=True, hq=True)
+    assert torch.equal(o1.q8.cpu(), ops.q8_planes(o1.f32.cpu())) and torch.equal(o1.h16.cpu(), _f16(o1.f32.cpu()))
+    w2 = rnd(64, 128, 3, 3, seed=97) / math.sqrt(128 * 9)
+    o2, _ = ops.conv(o1, ops.pack_conv(w2, None, DEV, prec=ops.PREC_F16_Q8), f32=True, split=True)
+    ref = F.conv2d(o1.f32.cpu().squeeze(1).permute(0, 3, 1, 2), w2, None, padding=1)
+    got = o2.f32.cpu().squeeze(1).permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 1e-4
+    assert ((o2.hi.float() + o2.lo.float()).cpu() - o2.f32.cpu()).abs().max().item() <= 2.0 ** -15 * o2.f32.abs().max().item()
