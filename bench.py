@@ -322,15 +322,24 @@ def run_b200(args):
                        "launch": "G2d 512->512 3x3 @64x64 x32 (16 of the step's conv launches)", "source": t["source"]}
     except Exception:
         traffic = None
-    if "conv_tc" in agg:
-        c = agg["conv_tc"]
-        ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, 3-pass split-bf16)",
+    fam = [(k, agg[k], passes) for k, passes in (("conv_tc", 3), ("conv_tc_h", 2), ("conv_tc_q8", 2)) if k in agg]
+    if fam:
+        # the dominant kernel family: k_conv_tc2 / k_conv_tc3 in its three operand modes (pass-units per product: 3 for
+        # split-bf16, 2 for fp16x2, 2 for fp16 + FP8 cross terms: one fp16 pass + two FP8 passes at twice the rate)
+        ms_all = sum(c["ms"] for _, c, _ in fam)
+        fl_all = sum(c["flops"] for _, c, _ in fam)
+        raw_all = sum(c["flops"] * ps for _, c, ps in fam)
+        n_all = sum(c["n"] for _, c, _ in fam)
+        ach = fl_all / (ms_all * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_conv_tc2 / k_conv_tc3 (tcgen05 implicit-GEMM conv; split-bf16 x3, fp16 x2 and "
+                                             "fp16 + e4m3 cross-term operand modes)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                 "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
-                "mma_passes": 3, "raw_tensor_frac": 3 * ach / pk["tf_sustained"], "launches": c["n"],
-                "avg_launch_ms": c["ms"] / c["n"], "share_of_step": c["ms"] / step_ms,
-                "algorithmic_gflop_per_launch": c["flops"] / c["n"] / 1e9}
+                "mma_passes": raw_all / fl_all, "raw_tensor_frac": raw_all / (ms_all * 1e-3) / 1e12 / pk["tf_sustained"],
+                "launches": n_all, "avg_launch_ms": ms_all / n_all, "share_of_step": ms_all / step_ms,
+                "algorithmic_gflop_per_launch": fl_all / n_all / 1e9,
+                "modes": {k: {"launches": c["n"], "ms": c["ms"], "useful_tflops": c["flops"] / (c["ms"] * 1e-3) / 1e12,
+                              "pass_units": ps} for k, c, ps in fam}}
     extra = {}
     if "conv_tc_h" in agg:     # two-pass fp16 convolutions of the motion-encoder trunks
         c = agg["conv_tc_h"]
@@ -339,6 +348,14 @@ def run_b200(args):
                                   "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                                   "mma_passes": 2, "raw_tensor_frac": 2 * ach / pk["tf_sustained"], "launches": c["n"],
                                   "ms": c["ms"], "share_of_step": c["ms"] / step_ms}
+    if "conv_tc_q8" in agg:    # fp16 main product + FP8 cross terms (G2d identity res-blocks)
+        c = agg["conv_tc_q8"]
+        ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
+        extra["conv_tc_f16_q8"] = {"kernel": "k_conv_tc2, MP_PREC_F16_Q8 (G2d res-blocks)", "bound": "tensor", "achieved": ach,
+                                   "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                                   "mma_passes": 2, "raw_tensor_frac": 2 * ach / pk["tf_sustained"], "launches": c["n"],
+                                   "ms": c["ms"], "share_of_step": c["ms"] / step_ms,
+                                   "note": "pass-units: one fp16 pass + two FP8 passes at twice the rate"}
     for kind in ("warp_fused_sum", "warp_fused", "conv_simt"):
         if kind in agg:
             c = agg[kind]
@@ -349,6 +366,39 @@ def run_b200(args):
             if c["flops"]:
                 e.update(tflops=c["flops"] / (c["ms"] * 1e-3) / 1e12)
             extra[kind] = e
+
+    # ---- grid_sample op leg (the second half of BASELINE.json's metric): F.grid_sample(v, grid, 'bilinear', 'border',
+    # align_corners=True) on a (8, 96, 16, 64, 64) volume (201 MB in + 201 MB out: larger than L2) with the "spread" grid of
+    # SURVEY.md 8d (identity + U(-0.1, 0.1)), through the reference-layout C-ABI entry point, CUDA events, best of 5
+    gs = None
+    try:
+        with torch.no_grad():
+            gB = 8
+            g2 = torch.Generator().manual_seed(2)
+            v = torch.randn(gB, 96, 16, 64, 64, generator=g2).to(dev)
+            zz, yy, xx = torch.meshgrid(torch.linspace(-1, 1, 16), torch.linspace(-1, 1, 64), torch.linspace(-1, 1, 64),
+                                        indexing="ij")
+            grid = (torch.stack((xx, yy, zz), -1)[None].repeat(gB, 1, 1, 1, 1) +
+                    (torch.rand(gB, 16, 64, 64, 3, generator=torch.Generator().manual_seed(3)) - 0.5) * 0.2).to(dev)
+            ops.grid_sample3d(v, grid)
+            ts = []
+            for _ in range(5):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                ops.grid_sample3d(v, grid)
+                a1.record()
+                torch.cuda.synchronize()
+                ts.append(a0.elapsed_time(a1))
+            nbytes = gB * 51118080
+            gbs = nbytes / (min(ts) * 1e-3) / 1e9
+            gs = {"op": "mp_grid_sample3d_ws (NCDHW in/out, channels-last workspace gather)", "batch": gB, "grid": "spread",
+                  "ms": min(ts), "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                  "frac": gbs / pk["hbm_gbs"], "algorithmic_bytes": nbytes,
+                  "note": "generic-grid trilinear gather: 8 taps per output re-read the volume through L2 -> L1 "
+                          "(DESIGN.md section 5); the pipeline itself uses the fused channels-last warp kernels above"}
+            del v, grid
+    except Exception as e:      # the op leg must never take the headline number down with it
+        gs = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -364,8 +414,9 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16x3 split (fp32-grade products: hi*hi+hi*lo+lo*hi, fp32 accumulate in TMEM); motion-encoder trunks: "
-                                    "fp16x2 (fp16 activations x fp16 hi+lo weights, fp32 accumulate)",
+        "vs_baseline": None, "dtype": "bf16x3 split (fp32-grade products: hi*hi+hi*lo+lo*hi, fp32 accumulate in TMEM); G2d res-blocks: fp16 "
+                                    "main product + e4m3 cross terms; motion-encoder trunks: fp16x2 (fp16 activations x fp16 "
+                                    "hi+lo weights, fp32 accumulate)",
         "data": "synthetic",
         "config": {"workload": f"Gbase inference, 1 src x {B} drv per GPU, 512x512 (BASELINE config "
                                f"{'2' if world == 1 else '3 share'}); source re-encoded every step",
@@ -382,6 +433,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": roof,
         "kernels": extra,
+        "grid_sample": gs,
         "stages_eager_step": stages,
         "cpu_baseline": cpu,
         "useful_tflops_whole_step": (B * FLOPS_PER_DRIVER + FLOPS_SOURCE) * world / (step_ms * 1e-3) / 1e12,
