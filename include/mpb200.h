@@ -200,6 +200,14 @@ int mp_tap_sum3x3_cl(const float* y, const float* bias, float* out, int N, int H
 int mp_gn_relu_conv3x3_head(const float* x, const float* ab, const float* weight_host, const float* bias_host, float* out,
                             int N, int H, int W, int Cin, int Cout, int act, void* stream);
 
+/* ---------------------------------------------------------------- frame I/O ------------- */
+/* inference.py:16-20: transforms.ToTensor() + Normalize([mean],[std]) -- uint8 HWC [N,H,W,3] -> fp32 NCHW [N,3,H,W]. */
+int mp_frames_u8_to_f32(const void* in_u8, float* out, int N, int H, int W, float mean, float std, void* stream);
+/* inference.py:36-43: ((x + shift) * scale * 255).astype(uint8), CHW -> HWC, optional channel reversal
+ * (cv2.cvtColor(.., COLOR_BGR2RGB)) -- fp32 NCHW [N,3,H,W] -> uint8 HWC [N,H,W,3]; values are clamped to [0, 255]. */
+int mp_frames_f32_to_u8(const float* in, void* out_u8, int N, int H, int W, float shift, float scale, int reverse_channels,
+                        void* stream);
+
 /* ---------------------------------------------------------------- image pyramid ----------------------------- */
 /* AntiAliasInterpolation2d (model.py:683-691): zero-pad, depthwise ks x ks filter, nearest subsample by `step`.
  * x [N,C,H,W] fp32 NCHW, kernel [ks*ks] (same for every channel), out [N,C,H/step,W/step]. */

@@ -695,6 +695,37 @@ def gn_relu_conv3x3_head(a: Act, ab: torch.Tensor, weight_host: torch.Tensor, bi
 
 
 @_profiled
+def frames_u8_to_f32(frames: torch.Tensor, mean: float = 0.5, std: float = 0.5) -> torch.Tensor:
+    """uint8 HWC frames [N,H,W,3] on the device -> fp32 NCHW [N,3,H,W] = Normalize(mean, std)(ToTensor(frame))
+    (reference inference.py:16-20)."""
+    _chk_cuda(frames, torch.uint8, "frames_u8_to_f32")
+    N, H, W, C = frames.shape
+    if C != 3:
+        raise RuntimeError("frames_u8_to_f32: frames must be [N, H, W, 3]")
+    out = torch.empty((N, 3, H, W), dtype=torch.float32, device=frames.device)
+    L = _lib.load()
+    _lib.check(L.mp_frames_u8_to_f32(_p(frames), _p(out), N, H, W, mean, std, _stream()), "mp_frames_u8_to_f32")
+    _count()
+    return out
+
+
+@_profiled
+def frames_f32_to_u8(x: torch.Tensor, shift: float = 1.0, scale: float = 0.5, reverse_channels: bool = True) -> torch.Tensor:
+    """fp32 NCHW [N,3,H,W] -> uint8 HWC [N,H,W,3] = ((x + shift) * scale * 255).astype(uint8), channels reversed like
+    cv2.cvtColor(.., COLOR_BGR2RGB) (reference inference.py:36-43)."""
+    _chk_cuda(x, torch.float32, "frames_f32_to_u8")
+    N, C, H, W = x.shape
+    if C != 3:
+        raise RuntimeError("frames_f32_to_u8: x must be [N, 3, H, W]")
+    out = torch.empty((N, H, W, 3), dtype=torch.uint8, device=x.device)
+    L = _lib.load()
+    _lib.check(L.mp_frames_f32_to_u8(_p(x), _p(out), N, H, W, shift, scale, 1 if reverse_channels else 0, _stream()),
+               "mp_frames_f32_to_u8")
+    _count()
+    return out
+
+
+@_profiled
 def blur_subsample(x: torch.Tensor, kernel2d: torch.Tensor, step: int) -> torch.Tensor:
     _chk_cuda(x, torch.float32, "blur_subsample x")
     _chk_cuda(kernel2d, torch.float32, "blur_subsample kernel")

@@ -633,3 +633,20 @@ def test_conv_split_in_f16_q8_out_and_back(ops):
     got = o2.f32.cpu().squeeze(1).permute(0, 3, 1, 2)
     assert (got - ref).abs().max().item() / ref.abs().max().item() < 1e-4
     assert ((o2.hi.float() + o2.lo.float()).cpu() - o2.f32.cpu()).abs().max().item() <= 2.0 ** -15 * o2.f32.abs().max().item()
+
+
+def test_frame_io_matches_reference_preprocessing(ops):
+    """inference.py:16-20 / 36-43: ToTensor + Normalize(0.5, 0.5) in, ((x + 1) / 2 * 255).astype(uint8) + channel swap out."""
+    g = torch.Generator().manual_seed(101)
+    u8 = torch.randint(0, 256, (3, 40, 56, 3), generator=g, dtype=torch.uint8)
+    x = ops.frames_u8_to_f32(u8.to(DEV)).cpu()
+    ref = ((u8.float() / 255.0).permute(0, 3, 1, 2) - 0.5) / 0.5
+    assert x.shape == ref.shape and (x - ref).abs().max().item() < 1e-6
+    y = torch.rand(3, 3, 40, 56, generator=g) * 2.4 - 1.2            # includes values outside [-1, 1]
+    got = ops.frames_f32_to_u8(y.to(DEV)).cpu()
+    v = ((y + 1) / 2 * 255).clamp(0, 255)
+    exp = v.to(torch.uint8).permute(0, 2, 3, 1).flip(-1)
+    diff = (got.int() - exp.int()).abs()
+    assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 1e-3      # ties at integer boundaries only
+    back = ops.frames_f32_to_u8(x.to(DEV), reverse_channels=False).cpu()          # round trip: truncation may lose one count
+    assert (back.int() - u8.int()).abs().max().item() <= 1
