@@ -316,7 +316,7 @@ def run_b200(args):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        t = tj.get("k_conv_tc2|32x1x64x64 512->512 k133 s1")
+        t = tj.get("k_conv_tc2|32x1x64x64 512->512 k133 s1 (MP_PREC_F16_Q8)") or tj.get("k_conv_tc2|32x1x64x64 512->512 k133 s1")
         if t:
             traffic = {"dram_bytes_per_launch": t["dram_bytes"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"],
                        "launch": "G2d 512->512 3x3 @64x64 x32 (16 of the step's conv launches)", "source": t["source"]}

@@ -122,6 +122,17 @@ def main():
         best, avg = timeit(lambda: ops.gn_relu_conv3x3_head(a, ab, w, b), r)
         by = 32 * 512 * 512 * (64 + 3) * 4
         print(f"gn_relu_conv3x3_head_b32     best {best:8.3f} ms avg {avg:8.3f} ms  {by / best / 1e6:8.1f} GB/s", flush=True)
+    if sel("q8"):
+        # G2d identity res-block convolution in the fp16 + FP8 cross-term mode
+        g = torch.Generator().manual_seed(5)
+        xcl = torch.randn(32, 1, 64, 64, 512, generator=g)
+        a = ops.Act(tuple(xcl.shape), h16=xcl.half().to(DEV), q8=ops.q8_planes(xcl).to(DEV))
+        w = torch.randn(512, 512, 3, 3, generator=g) / math.sqrt(512 * 9)
+        pw = ops.pack_conv(w, torch.zeros(512), DEV, prec=ops.PREC_F16_Q8)
+        best, avg = timeit(lambda: ops.conv(a, pw, res=a, act=ops.ACT_RELU, f32=False, hq=True), r)
+        fl = 2.0 * 32 * 64 * 64 * 512 * 512 * 9
+        print(f"g2d_512_64x64_b32_q8         best {best:8.3f} ms avg {avg:8.3f} ms  useful {fl / best / 1e9:8.1f} TFLOP/s "
+              f"(pass-units x2 {2 * fl / best / 1e9:8.1f})", flush=True)
     if sel("simt"):
         conv_case("g2d_512_64x64_b4", 4, 512, 512, 1, 64, 64, (1, 3, 3), r, mode="simt")
     if sel("warp"):
