@@ -76,7 +76,9 @@ k_gn_relu_conv3x3_head(const float* __restrict__ x, const float* __restrict__ ab
   for (int o = 0; o < HO; ++o) acc0[o] = acc1[o] = chalf ? 0.f : wt.bias[o];
   const float* sp = s + (2 * ty) * PW + tx;
   if (chalf == 0) {
-#pragma unroll
+    // partially unrolled: the fully unrolled body (3 500 FFMAs, ~70 KB of SASS) thrashed the instruction cache (ncu:
+    // "no instruction" was the top stall); with a rolled loop the weights are fetched by uniform-indexed LDCU
+#pragma unroll 2
     for (int c = 0; c < HC / 2; ++c) {
       float v[4][3];
 #pragma unroll
@@ -94,7 +96,7 @@ k_gn_relu_conv3x3_head(const float* __restrict__ x, const float* __restrict__ ab
           }
     }
   } else {
-#pragma unroll
+#pragma unroll 2
   for (int c = HC / 2; c < HC; ++c) {
     float v[4][3];
 #pragma unroll
