@@ -187,17 +187,6 @@ __device__ __forceinline__ uint32_t desc_hi_word(uint32_t sbo, uint32_t layout_t
   return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
 }
 __device__ __forceinline__ uint32_t desc_lo_word(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
-__device__ __forceinline__ void umma_bf16_lean(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
-                                               uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "mov.b64 da, {%1, %3};\n\t"
-      "mov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // Issue paths of the persistent kernels: called by ALL 32 lanes of the MMA warp in lock-step; `elect.sync` picks the one
 // lane that issues.  (Issuing from inside an `if (lane == 0)` region instead makes the compiler wrap every UTCHMMA /
 // UTCBAR in an active-lane loop -- ELECT, PLOP3, BRA.U.ANY -- which, on a single dependent instruction stream, capped

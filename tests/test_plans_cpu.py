@@ -48,3 +48,58 @@ def test_planner_rejects_what_the_kernel_cannot_do(L):
     assert so.mp_conv_tc_supported(ctypes.byref(_desc(L, 1, 64, 64, 3, 64, 3, 1, 3, 0))) == 0      # Cin % 16
     assert so.mp_conv_tc_supported(ctypes.byref(_desc(L, 1, 64, 64, 64, 64, 3, 1, 64, 7))) == 0    # unknown prec
     assert so.mp_conv_tc_supported(ctypes.byref(_desc(L, 1, 63, 64, 64, 64, 3, 1, 64, 1))) == 0    # ragged grid
+
+
+def _desc2(lib, N, H, W, Cin, Cout, k, prec, Cin2=0, stride2=1, in2_C=0, in2_off=0):
+    d = _desc(lib, N, H, W, Cin, Cout, k, 1, Cin, prec)
+    d.Cin2, d.stride2, d.in2_C, d.in2_c_off = Cin2, stride2, in2_C or Cin2, in2_off
+    d.in2_hi = d.in2_lo = 256
+    d.corr_scale = 2.0 ** -14
+    return d
+
+
+@pytest.mark.parametrize("N", [1, 32])
+def test_fused_shortcut_and_fp8_shapes_are_planned(L, N):
+    so = L.load()
+    cases = [
+        # G2d up-blocks (split-bf16): conv2 + fused 1x1 shortcut (model.py:616-640)
+        (128, 128, 256, 256, 3, 0, 512, 1), (256, 256, 128, 128, 3, 0, 256, 1), (512, 512, 64, 64, 3, 0, 128, 1),
+        # down-sampling ResNet-18 blocks of Emtn (fp16 two-pass), windowed / stride-2 second source
+        (128, 128, 128, 128, 3, 1, 64, 2, 128, 64), (64, 64, 256, 256, 3, 1, 128, 2), (32, 32, 512, 512, 3, 1, 256, 2),
+        # ResNet-50 bottlenecks of the descriptor branch: 1x1 conv3 + 1x1 shortcut
+        (128, 128, 64, 256, 1, 0, 64, 1), (64, 64, 128, 512, 1, 0, 256, 2), (32, 32, 256, 1024, 1, 0, 512, 2),
+        # G2d identity res-blocks and input conv in the fp16 + FP8 cross-term mode
+        (64, 64, 512, 512, 3, 2), (64, 64, 64, 128, 1, 2),
+    ]
+    for c in cases:
+        assert so.mp_conv_tc_supported(ctypes.byref(_desc2(L, N, *c))) == 1, (N, c)
+    # the fp16 + FP8 format needs 64-channel groups; a shortcut must share the main operand's channel chunking
+    assert so.mp_conv_tc_supported(ctypes.byref(_desc2(L, 1, 64, 64, 96, 128, 3, 2))) == 0
+    assert so.mp_conv_tc_supported(ctypes.byref(_desc2(L, 1, 64, 64, 64, 64, 3, 0, 24, 1))) == 0
+
+
+def test_operand_packing_accuracy():
+    """Host packers of the three operand formats reproduce the weights to the advertised number of bits (CPU only)."""
+    import torch
+    from megaportrait_hack_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(64, 128, 3, 3, generator=g) / 34
+    wk = w.permute(0, 2, 3, 1).reshape(64, -1)
+    p0 = ops.pack_conv(w, None)
+    assert ((p0.w_hi.float() + p0.w_lo.float()) - wk).abs().max() <= wk.abs().max() * 2.0 ** -16
+    p1 = ops.pack_conv(w, None, prec=ops.PREC_F16X2)
+    assert ((p1.w_hi.float() + p1.w_lo.float() / ops.F16_LO_SCALE) - wk).abs().max() <= wk.abs().max() * 2.0 ** -20
+    p2 = ops.pack_conv(w, None, prec=ops.PREC_F16_Q8)
+    hi = p2.w_hi.view(torch.float16).float()
+    q = p2.w_lo.reshape(64, -1, 2, 64).view(torch.float8_e4m3fn).float()
+    wl8, w8 = q[:, :, 0].reshape(64, -1), q[:, :, 1].reshape(64, -1)
+    assert p2.w_hi.data_ptr() + p2.w_hi.numel() == p2.w_lo.data_ptr()          # one allocation: single-TMA [hi | lo] loads
+    assert ((hi + wl8 * p2.corr_scale) - wk).abs().max() <= wk.abs().max() * 2.0 ** -15      # fp16 + e4m3 low part
+    sw = 1.0 / (ops.F16_LO_SCALE * p2.corr_scale)
+    assert (w8 / sw - wk).abs().max() <= wk.abs().max() * 2.0 ** -4 and 1.0 <= (wk * sw).abs().max() < 2.0
+    # activation planes: fp16 plane + [e4m3(x) | e4m3((x - fp16 x) * 2048)] per 64-channel group
+    x = torch.randn(2, 1, 3, 5, 128, generator=g) * 3
+    qx = ops.q8_planes(x).reshape(2, 1, 3, 5, 2, 2, 64).view(torch.float8_e4m3fn).float()
+    x8, xl8 = qx[..., 0, :].reshape(x.shape), qx[..., 1, :].reshape(x.shape)
+    assert (x8 - x).abs().max() <= x.abs().max() * 2.0 ** -4
+    assert ((x.half().float() + xl8 / 2048) - x).abs().max() <= x.abs().max() * 2.0 ** -15
