@@ -1,20 +1,29 @@
 // Implicit-GEMM convolution on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM) fed by TMA.  sm_100a only.
 //
-// GEMM view of a "same" convolution with stride 1 (nn.Conv2d / nn.Conv3d(k, padding=k//2)):
+// GEMM view of a "same" convolution (nn.Conv2d / nn.Conv3d(k, padding=k//2), stride 1 or 2 on H/W):
 //     D[m, co] = sum_{tap, ci} A[m + shift(tap), ci] * Wt[co, tap, ci]        m = output position, fp32 accumulate
-// Layout: activations channels-last [N, D, H, W, C] as TWO bf16 planes (hi, lo; x ~= hi + lo), weights packed
-// [Cout_pad][taps*Cin] (K-major) as two bf16 planes.  fp32-grade products come from three bf16 MMAs per K step:
-//     hi*hi + lo*hi + hi*lo      (the lo*lo term, ~2^-18 relative, is dropped)
+// Layout: activations channels-last [N, D, H, W, C], weights packed [Cout_pad][taps*Cin (+ Cin2)] (K-major).  Three
+// operand formats (mp_conv_desc.prec):
+//     split-bf16  two bf16 planes (hi, lo); products hi*hi + lo*hi + hi*lo, three MMA passes (lo*lo ~2^-18 dropped);
+//     fp16 x2     one fp16 activation plane, fp16 hi + scaled fp16 lo weights: ONE MMA A x [Wh | Wl'] per K step;
+//     fp16 + q8   fp16 x fp16 main product (kind::f16) + both cross terms as e4m3 x e4m3 (kind::f8f6f4) in a second
+//                 accumulator, issued by two warps.
 //
-// One CTA computes a 128-position x BN-channel tile.  The 128 positions are a (BD, BH, BW) box of the output
-// grid, so for every filter tap the A operand is the same box shifted by (kd-pd, kh-ph, kw-pw): ONE 5-D TMA tile
-// load per (tap, 64-channel chunk), with the zero padding supplied by TMA's out-of-bounds fill.  No im2col buffer
-// ever exists in HBM.  The box lands in shared memory as 128 rows x (CCHUNK*2) bytes with the 128B/64B/32B swizzle
-// that the UMMA shared-memory descriptor expects for a K-major operand.
+// A CTA computes 128-position x BN-channel tiles.  The 128 positions are a (BD, BH, BW) box of the output grid, so for
+// every filter tap the A operand is the same box shifted by (kd-pd, kh-ph, kw-pw): ONE 5-D TMA tile load per (tap,
+// channel chunk), zero padding supplied by TMA's out-of-bounds fill, stride 2 by TMA element strides.  No im2col buffer
+// ever exists in HBM.  The box lands in shared memory as 128 rows x (CCHUNK*2) bytes with the 128B/64B/32B swizzle that
+// the UMMA shared-memory descriptor expects for a K-major operand.  An optional second source (fused 1x1 shortcut)
+// appends Cin2/CCHUNK K-chunks whose A tiles come from another tensor map.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (TMEM -> registers -> bias/residual/activation/GroupNorm statistics -> HBM).
-// Pipelines: STAGES-deep smem ring (full/empty mbarriers, tcgen05.commit frees a slot), one tmem_full barrier.
+// Kernels: k_conv_tc2 (general: persistent, BN up to 256, smem ring of 2-8 stages, optional resident weights),
+// k_conv_tc3 (slab: 3x3(x3) with Cout <= 128, one (MT*16+2) x 8 pixel slab serves the three vertical taps of MT
+// accumulators), k_conv_tc (first generation, kept for A/B runs).  Warp roles in the persistent kernels (352 threads):
+// warp 0 = TMA producer + tile scheduler (tile ids drawn from a global atomic counter, published to the other roles
+// through a shared-memory queue), warp 1 (+ warp 10 when a tile has two independently issued accumulators) = MMA issue,
+// whole warp converged with one elected lane issuing, warps 2..9 = epilogue (TMEM -> registers -> bias / residual /
+// activation / GroupNorm statistics -> shared-memory staging -> coalesced stores, or swizzled staging + TMA bulk stores
+// for fp16 outputs).  TMEM holds two tiles' accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
