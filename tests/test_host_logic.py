@@ -68,3 +68,16 @@ def test_folding_helpers():
     rec = (pw.w_hi.float() + pw.w_lo.float())[:8].view(8, 3, 3, 4).permute(0, 3, 1, 2)
     assert (rec - w).abs().max() <= w.abs().max() * 2.0 ** -16
     assert (pw.w_hi[8:] == 0).all()
+
+
+def test_pipeline_wiring_with_split_bf16_switches():
+    """The A/B switches (three-pass split-bf16 for the motion encoder and for G2d's res-blocks) are read at import time:
+    re-run the wiring test in a fresh interpreter with both set, so the alternative plans stay healthy."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, MPB200_EMTN_PREC="split", MPB200_G2D_PREC="split")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_host_logic.py"), "-q", "-x",
+                        "-k", "test_pipeline_wiring_against_oracle"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
