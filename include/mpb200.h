@@ -172,6 +172,19 @@ int mp_grid_sample3d_ws(const float* v, const float* grid, float* out, void* wor
 int mp_apply_warping_field_ws(const float* v, const float* warp_field, float* out, void* workspace,
                               size_t workspace_bytes, int N, int C, int D, int H, int W, int Df, int Hf, int Wf,
                               void* stream);
+/* Brick-staged variants of the two NCDHW drop-ins (same results bit for bit): per output tile the cells that its
+ * voxels sample are bounded, the covering (d,h,w) brick of every channel is fetched ONCE by a TMA box load into shared
+ * memory (zero fill outside the volume = ATen's within_bounds test), the 8 taps are read from shared memory with the
+ * tile's voxels bucketed by bank so that jittery grids stay conflict-free, and each result tile leaves through one TMA
+ * box store.  Tiles whose sampling region does not fit the brick fall back to direct gathers inside the same kernel.
+ * No workspace, no whole-volume transpose.  Requires W % 4 == 0, Wo % 4 == 0, D/H/W <= 1023, 16-byte aligned v / out.
+ * flags: bit 0 = do not bucket by bank (A/B).  mp_gs_brick_tune: {tz, ty, tx, BD, BH, BW, threads, groups} overrides,
+ * 0 = automatic (test / profiling hook; process-wide). */
+int mp_grid_sample3d_brick(const float* v, const float* grid, float* out, int N, int C, int D, int H, int W, int Do,
+                           int Ho, int Wo, int flags, void* stream);
+int mp_apply_warping_field_brick(const float* v, const float* warp_field, float* out, int N, int C, int D, int H,
+                                 int W, int Df, int Hf, int Wf, int flags, void* stream);
+int mp_gs_brick_tune(const int* cfg, int n);
 /* apply_warping_field(v, warp_field) (model.py:1028-1065) in the reference layout: v [N,C,D,H,W],
  * warp_field [N,3,Df,Hf,Wf] -> out [N,C,D,H,W]; the flow resample, identity grid, the reference's
  * re-normalisation and the trilinear border gather run in one kernel. */

@@ -580,8 +580,24 @@ def global_avgpool_f16(a: Act) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------- warping
-def grid_sample3d(v: torch.Tensor, grid: torch.Tensor, direct: bool = False) -> torch.Tensor:
-    """F.grid_sample(v, grid, 'bilinear', 'border', align_corners=True) for NCDHW fp32 (model.py:1062)."""
+def _brick_ok(W: int, Wo: int, D: int, H: int, *tensors) -> bool:
+    """Shapes the brick-staged kernels accept (16-byte TMA rows, 10-bit packed cells, aligned bases)."""
+    return W % 4 == 0 and Wo % 4 == 0 and max(D, H, W) <= 1023 and all(t.data_ptr() % 16 == 0 for t in tensors)
+
+
+def gs_brick_tune(cfg: Sequence[int] = ()) -> None:
+    """Profiling hook: {tz, ty, tx, BD, BH, BW, threads, groups} overrides of the brick kernels (0 / () = automatic)."""
+    arr = (ctypes.c_int * 8)(*([int(c) for c in cfg] + [0] * (8 - len(cfg))))
+    _lib.check(_lib.load().mp_gs_brick_tune(arr, 8), "mp_gs_brick_tune")
+
+
+def grid_sample3d(v: torch.Tensor, grid: torch.Tensor, direct: bool = False, impl: Optional[str] = None,
+                  bucket: bool = True) -> torch.Tensor:
+    """F.grid_sample(v, grid, 'bilinear', 'border', align_corners=True) for NCDHW fp32 (model.py:1062).
+
+    `impl`: "brick" (default where the shape allows: TMA-staged bricks in shared memory, per-tile fallback to direct
+    gathers), "ws" (channels-last workspace copy + gather: the better choice for random-permutation grids), "direct"
+    (plain NCDHW gather).  All three give the same bits."""
     _chk_cuda(v, torch.float32, "grid_sample3d v")
     _chk_cuda(grid, torch.float32, "grid_sample3d grid")
     N, C, D, H, W = v.shape
@@ -590,10 +606,19 @@ def grid_sample3d(v: torch.Tensor, grid: torch.Tensor, direct: bool = False) -> 
         raise RuntimeError("grid_sample3d: grid must be [N, Do, Ho, Wo, 3]")
     out = torch.empty((N, C, Do, Ho, Wo), dtype=torch.float32, device=v.device)
     L = _lib.load()
-    ws_bytes = L.mp_gather_workspace_bytes(N, C, D, H, W) if not direct else 0
+    if impl is None:
+        impl = "direct" if direct else ("brick" if _brick_ok(W, Wo, D, H, v, out) else "ws")
+    nbytes = N * (C * D * H * W + C * Do * Ho * Wo + 3 * Do * Ho * Wo) * 4
+    if impl == "brick":
+        with _Prof("grid_sample3d", 0, nbytes):
+            _lib.check(L.mp_grid_sample3d_brick(_p(v), _p(grid), _p(out), N, C, D, H, W, Do, Ho, Wo, 0 if bucket else 1,
+                                                _stream()), "mp_grid_sample3d_brick")
+        _count()
+        return out
+    ws_bytes = L.mp_gather_workspace_bytes(N, C, D, H, W) if impl == "ws" else 0
     if ws_bytes:
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=v.device)
-        with _Prof("grid_sample3d", 0, N * (C * D * H * W + C * Do * Ho * Wo + 3 * Do * Ho * Wo) * 4):
+        with _Prof("grid_sample3d", 0, nbytes):
             _lib.check(L.mp_grid_sample3d_ws(_p(v), _p(grid), _p(out), _p(ws), ws_bytes, N, C, D, H, W, Do, Ho, Wo,
                                              _stream()), "mp_grid_sample3d_ws")
         _count(2)
@@ -603,7 +628,9 @@ def grid_sample3d(v: torch.Tensor, grid: torch.Tensor, direct: bool = False) -> 
     return out
 
 
-def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor, direct: bool = False) -> torch.Tensor:
+def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor, direct: bool = False,
+                              impl: Optional[str] = None) -> torch.Tensor:
+    """apply_warping_field(v, warp_field) (model.py:1028-1065), NCDHW fp32; `impl` as in `grid_sample3d`."""
     _chk_cuda(v, torch.float32, "apply_warping_field v")
     _chk_cuda(warp_field, torch.float32, "apply_warping_field warp_field")
     N, C, D, H, W = v.shape
@@ -612,7 +639,14 @@ def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor, direct:
         raise RuntimeError("apply_warping_field: warp_field must be [N, 3, Df, Hf, Wf]")
     out = torch.empty_like(v)
     L = _lib.load()
-    ws_bytes = L.mp_gather_workspace_bytes(N, C, D, H, W) if not direct else 0
+    if impl is None:
+        impl = "direct" if direct else ("brick" if (_brick_ok(W, W, D, H, v, out) and min(D, H, W) > 1) else "ws")
+    if impl == "brick":
+        _lib.check(L.mp_apply_warping_field_brick(_p(v), _p(warp_field), _p(out), N, C, D, H, W, Df, Hf, Wf, 0, _stream()),
+                   "mp_apply_warping_field_brick")
+        _count()
+        return out
+    ws_bytes = L.mp_gather_workspace_bytes(N, C, D, H, W) if impl == "ws" else 0
     if ws_bytes:
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=v.device)
         _lib.check(L.mp_apply_warping_field_ws(_p(v), _p(warp_field), _p(out), _p(ws), ws_bytes, N, C, D, H, W, Df, Hf,

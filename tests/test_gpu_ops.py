@@ -192,38 +192,130 @@ def _grids(kind, N, D, H, W, seed):
     raise ValueError(kind)
 
 
+IMPLS = ("brick", "ws", "direct")
+
+
+def _gs_ref(v, grid):
+    return F.grid_sample(v, grid, mode="bilinear", padding_mode="border", align_corners=True)
+
+
 @pytest.mark.parametrize("kind", ["spread", "adversarial"])
 def test_grid_sample3d(ops, kind):
+    """All three implementations (TMA-staged bricks, channels-last workspace, direct NCDHW gather) vs ATen-CPU, and
+    against each other bit for bit (they share the coordinate arithmetic)."""
     N, C, D, H, W = 2, 12, 16, 64, 64
     v = rnd(N, C, D, H, W, seed=2)
     grid = _grids(kind, N, D, H, W, 3 if kind == "spread" else 4)
-    ref = F.grid_sample(v, grid, mode="bilinear", padding_mode="border", align_corners=True)
-    for direct in (False, True):     # channels-last workspace path and the direct NCDHW kernel
-        got = ops.grid_sample3d(v.to(DEV), grid.to(DEV), direct=direct).cpu()
-        assert (got - ref).abs().max().item() <= 1e-5
+    ref = _gs_ref(v, grid)
+    got = {impl: ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl=impl).cpu() for impl in IMPLS}
+    got["brick_nobucket"] = ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="brick", bucket=False).cpu()
+    for impl, g in got.items():
+        assert (g - ref).abs().max().item() <= 1e-5, impl
+    assert torch.equal(got["brick"], got["direct"]) and torch.equal(got["brick_nobucket"], got["direct"])
+
+
+def test_grid_sample3d_brick_is_default_and_covers_all_channels(ops):
+    """96 channels, batch 3: several channel groups per tile and uneven groups; default impl == brick."""
+    N, C, D, H, W = 3, 96, 16, 64, 64
+    v = rnd(N, C, D, H, W, seed=21)
+    grid = _grids("spread", N, D, H, W, 22)
+    ref = _gs_ref(v, grid)
+    l0 = ops.LAUNCHES
+    got = ops.grid_sample3d(v.to(DEV), grid.to(DEV)).cpu()
+    assert ops.LAUNCHES - l0 == 1, "default path must be the single brick kernel"
+    assert (got - ref).abs().max().item() <= 1e-5
+    for groups in (1, 5, 7, 12):          # uneven channel splits (96 = 7 x 13 + 5)
+        ops.gs_brick_tune([0, 0, 0, 0, 0, 0, 0, groups])
+        try:
+            g2 = ops.grid_sample3d(v.to(DEV), grid.to(DEV)).cpu()
+        finally:
+            ops.gs_brick_tune()
+        assert torch.equal(g2, got), groups
+
+
+@pytest.mark.parametrize("kind", ["degenerate", "smooth", "border", "mixed", "nan"])
+def test_grid_sample3d_brick_edge_grids(ops, kind):
+    """Grids that exercise the brick kernel's branches: everything in one cell (natural order, broadcasts), a smooth
+    shift (no bucketing needed), coordinates beyond the border (clamp + zero-filled far corner), a batch where one
+    sample fits the bricks and the other falls back tile by tile, NaN coordinates."""
+    N, C, D, H, W = 2, 10, 16, 64, 64
+    v = rnd(N, C, D, H, W, seed=31)
+    g = torch.Generator().manual_seed(32)
+    zz, yy, xx = torch.meshgrid(torch.linspace(-1, 1, D), torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+    base = torch.stack((xx, yy, zz), -1)[None].repeat(N, 1, 1, 1, 1)
+    if kind == "degenerate":      # the reference's corner-only regime: every voxel samples cell (0..1, 0..1, 0..1)
+        grid = -1.0 + torch.rand(N, D, H, W, 3, generator=g) * torch.tensor([2.0 / 63, 2.0 / 63, 2.0 / 15])
+    elif kind == "smooth":
+        grid = base + torch.tensor([0.043, -0.031, 0.02])
+    elif kind == "border":        # up to 2 cells outside on every side
+        grid = base * 1.06 + (torch.rand(N, D, H, W, 3, generator=g) - 0.5) * 0.05
+    elif kind == "mixed":
+        grid = base + (torch.rand(N, D, H, W, 3, generator=g) - 0.5) * 0.2
+        grid[1] = (torch.rand(D, H, W, 3, generator=g) - 0.5) * 3.0
+    else:
+        grid = base + (torch.rand(N, D, H, W, 3, generator=g) - 0.5) * 0.1
+        grid[0, 3, 5, 7, 0] = float("nan")
+        grid[1, 8, 60, 63, 2] = float("nan")
+    want = ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="direct").cpu()
+    got = ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="brick").cpu()
+    assert torch.equal(got, want)
+    if kind != "nan":
+        assert (got - _gs_ref(v, grid)).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [((2, 8, 7, 9, 12), (3, 5, 8)), ((1, 5, 16, 64, 64), (4, 6, 4)), ((1, 6, 5, 20, 200), (9, 30, 100)),
+                                   ((2, 4, 16, 64, 64), (16, 64, 64))],
+                         ids=["ragged", "small_out", "wide", "full"])
+@pytest.mark.parametrize("tile", [None, (2, 8, 32), (1, 16, 64)], ids=["auto", "t2x8x32", "t1x16x64"])
+def test_grid_sample3d_brick_shapes_and_tiles(ops, shape, tile):
+    """Input / output extents that do not divide the tile, rows wider than a tile, and other tile shapes."""
+    (N, C, D, H, W), (Do, Ho, Wo) = shape
+    v = rnd(N, C, D, H, W, seed=41)
+    grid = (torch.rand(N, Do, Ho, Wo, 3, generator=torch.Generator().manual_seed(42)) - 0.5) * 2.4
+    if D == 16:                      # local grid so that the staged path (not only the fallback) runs
+        zz, yy, xx = torch.meshgrid(torch.linspace(-1, 1, Do), torch.linspace(-1, 1, Ho), torch.linspace(-1, 1, Wo), indexing="ij")
+        grid = torch.stack((xx, yy, zz), -1)[None].repeat(N, 1, 1, 1, 1) + grid * 0.03
+    ref = _gs_ref(v, grid)
+    if tile is not None:
+        ops.gs_brick_tune(list(tile))
+    try:
+        got = ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="brick").cpu()
+    finally:
+        ops.gs_brick_tune()
+    assert (got - ref).abs().max().item() <= 1e-5
 
 
 def test_grid_sample3d_different_output_size(ops):
-    v8 = rnd(2, 8, 7, 9, 11, seed=5)
+    v8 = rnd(2, 8, 7, 9, 11, seed=5)        # W = 11: not a multiple of 4 -> the default falls back to the workspace path
     grid8 = (torch.rand(2, 3, 5, 7, 3, generator=torch.Generator().manual_seed(6)) - 0.5) * 2.4   # ragged 105 voxels
-    ref8 = F.grid_sample(v8, grid8, mode="bilinear", padding_mode="border", align_corners=True)
+    ref8 = _gs_ref(v8, grid8)
     assert (ops.grid_sample3d(v8.to(DEV), grid8.to(DEV)).cpu() - ref8).abs().max().item() <= 1e-5
     v = rnd(1, 5, 7, 9, 11, seed=5)
     grid = (torch.rand(1, 3, 4, 6, 3, generator=torch.Generator().manual_seed(6)) - 0.5) * 2.4
-    ref = F.grid_sample(v, grid, mode="bilinear", padding_mode="border", align_corners=True)
+    ref = _gs_ref(v, grid)
     assert (ops.grid_sample3d(v.to(DEV), grid.to(DEV)).cpu() - ref).abs().max().item() <= 1e-5
+    with pytest.raises(RuntimeError, match="multiples of 4"):
+        ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="brick")
 
 
-@pytest.mark.parametrize("amp", [1.0, 40.0])
+@pytest.mark.parametrize("amp", [1.0, 3.0, 40.0])
 def test_apply_warping_field_matches_oracle(ops, amp):
     import gbase_oracle as O
     g = torch.Generator().manual_seed(8)
     v = torch.randn(2, 10, 16, 64, 64, generator=g)
-    wf = (torch.rand(2, 3, 64, 64, 64, generator=g) - 0.3) * amp   # amp=40 leaves the degenerate corner regime
+    # amp = 1: the reference's degenerate corner regime; 3: a few cells of displacement (staged bricks); 40: far gathers
+    wf = (torch.rand(2, 3, 64, 64, 64, generator=g) - 0.3) * amp
+    if amp == 3.0:      # pixel coordinate = identity in [-1, 1] + flow (SURVEY appendix B): add the index ramp back
+        zz, yy, xx = torch.meshgrid(torch.linspace(0, 15, 64), torch.linspace(0, 63, 64), torch.linspace(0, 63, 64), indexing="ij")
+        lin = torch.stack((torch.linspace(-1, 1, 64)[None, None, :].expand(64, 64, 64),
+                           torch.linspace(-1, 1, 64)[None, :, None].expand(64, 64, 64),
+                           torch.linspace(-1, 1, 64)[:, None, None].expand(64, 64, 64)))
+        wf = wf * torch.tensor([1.0, 1.0, 0.25]).view(1, 3, 1, 1, 1) + (torch.stack((xx, yy, zz)) - lin)[None]
     ref = O.apply_warping_field(v, wf)
-    for direct in (False, True):
-        got = ops.apply_warping_field_ncdhw(v.to(DEV), wf.to(DEV), direct=direct).cpu()
+    outs = [ops.apply_warping_field_ncdhw(v.to(DEV), wf.to(DEV), impl=impl).cpu() for impl in IMPLS]
+    for got in outs:
         assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    assert torch.equal(outs[0], outs[2])
 
 
 def _theta(N, seed, invert):
