@@ -102,6 +102,70 @@ def synthetic_inputs(n_drivers_total: int):
     return xs, xd
 
 
+GS_ALG_BYTES = 51118080       # (2 * 96 * 16 * 64 * 64 + 3 * 16 * 64 * 64) * 4 per sample
+
+
+def gs_grid(kind: str, B: int, dev):
+    """The three grids of SURVEY.md 8d for a (16, 64, 64) volume."""
+    import torch
+    D, H, W = 16, 64, 64
+    zz, yy, xx = torch.meshgrid(torch.linspace(-1, 1, D), torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+    base = torch.stack((xx, yy, zz), -1)[None]
+    if kind == "spread":            # identity + U(-0.1, 0.1), seed 3
+        return (base + (torch.rand(B, D, H, W, 3, generator=torch.Generator().manual_seed(3)) - 0.5) * 0.2).to(dev)
+    if kind == "adversarial":       # U(-1.5, 1.5), seed 4
+        return ((torch.rand(B, D, H, W, 3, generator=torch.Generator().manual_seed(4)) - 0.5) * 3.0).to(dev)
+    # reference-faithful: what a10 -> a11 hands to F.grid_sample (SURVEY appendix B): 2 (id + flow) / (size - 1) - 1 with
+    # id = linspace(-1, 1) and flow in [0, 1): every voxel samples the first cells of the volume
+    flow = torch.rand(B, D, H, W, 3, generator=torch.Generator().manual_seed(5))
+    return (2.0 * (base + flow) / torch.tensor([W - 1.0, H - 1.0, D - 1.0]) - 1.0).to(dev)
+
+
+def grid_sample_leg(dev, pk, batches=(1, 32), reps=7):
+    import torch
+    from megaportrait_hack_b200 import ops
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            fn()
+            a1.record()
+            torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        return statistics.median(ts)
+
+    cells = []
+    with torch.no_grad():
+        for B in batches:
+            v = torch.randn(B, 96, 16, 64, 64, generator=torch.Generator().manual_seed(2)).to(dev)
+            out = torch.empty_like(v)
+            nbytes = B * GS_ALG_BYTES
+            for kind in ("reference", "spread", "adversarial"):
+                grid = gs_grid(kind, B, dev)
+                # random-permutation grids: nothing fits a brick, the channels-last workspace gather is the right tool
+                impl = "ws" if kind == "adversarial" else "brick"
+                ms = timed(lambda: ops.grid_sample3d(v, grid, impl=impl))
+                ms_copy = timed(lambda: (out.copy_(v), grid.sum()))
+                gbs = nbytes / ms / 1e6
+                cells.append({"batch": B, "grid": kind, "impl": impl, "ms": ms, "achieved": gbs, "unit": "GB/s",
+                              "frac": gbs / pk["hbm_gbs"], "copy_same_bytes_ms": ms_copy,
+                              "frac_of_copy": ms_copy / ms})
+                del grid
+            del v, out
+    head = next(c for c in cells if c["batch"] == 32 and c["grid"] == "spread")
+    return {"op": "mp_grid_sample3d_brick (TMA-staged bricks; NCDHW in/out, no workspace copy) / mp_grid_sample3d_ws for "
+                  "the adversarial grid", "bound": "hbm", "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "algorithmic_bytes_per_sample": GS_ALG_BYTES, "l2": "flushed before every timed launch", "timing": f"median of {reps}",
+            "batch": head["batch"], "grid": head["grid"], "ms": head["ms"], "achieved": head["achieved"], "frac": head["frac"],
+            "cells": cells}
+
+
 # ------------------------------------------------------------------------------------------------- reference arm
 def cpu_forward_sample(pairs: int, sd, xs, xd):
     """`Gbase(xs.expand(pairs), xd[:pairs])` with the reference's semantics (everything recomputed per pair)."""
@@ -367,36 +431,14 @@ def run_b200(args):
                 e.update(tflops=c["flops"] / (c["ms"] * 1e-3) / 1e12)
             extra[kind] = e
 
-    # ---- grid_sample op leg (the second half of BASELINE.json's metric): F.grid_sample(v, grid, 'bilinear', 'border',
-    # align_corners=True) on a (8, 96, 16, 64, 64) volume (201 MB in + 201 MB out: larger than L2) with the "spread" grid of
-    # SURVEY.md 8d (identity + U(-0.1, 0.1)), through the reference-layout C-ABI entry point, CUDA events, best of 5
+    # ---- grid_sample op leg (the second half of BASELINE.json's metric): F.grid_sample(v, grid, 'bilinear',
+    # 'border', align_corners=True), v ~ N(0,1) seed 2 of shape (B, 96, 16, 64, 64), B in {1, 32}, the three grids of 8d,
+    # through the reference-layout C-ABI entry points; CUDA events on the launching stream, L2 flushed (256 MB write)
+    # before every timed launch, median of 7.  "copy" = the same bytes through torch's copy kernel + a read of the grid:
+    # what a launch of this size can reach under the same harness (at B = 1 a 51 MB launch is latency-bound).
     gs = None
     try:
-        with torch.no_grad():
-            gB = 8
-            g2 = torch.Generator().manual_seed(2)
-            v = torch.randn(gB, 96, 16, 64, 64, generator=g2).to(dev)
-            zz, yy, xx = torch.meshgrid(torch.linspace(-1, 1, 16), torch.linspace(-1, 1, 64), torch.linspace(-1, 1, 64),
-                                        indexing="ij")
-            grid = (torch.stack((xx, yy, zz), -1)[None].repeat(gB, 1, 1, 1, 1) +
-                    (torch.rand(gB, 16, 64, 64, 3, generator=torch.Generator().manual_seed(3)) - 0.5) * 0.2).to(dev)
-            ops.grid_sample3d(v, grid)
-            ts = []
-            for _ in range(5):
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                ops.grid_sample3d(v, grid)
-                a1.record()
-                torch.cuda.synchronize()
-                ts.append(a0.elapsed_time(a1))
-            nbytes = gB * 51118080
-            gbs = nbytes / (min(ts) * 1e-3) / 1e9
-            gs = {"op": "mp_grid_sample3d_ws (NCDHW in/out, channels-last workspace gather)", "batch": gB, "grid": "spread",
-                  "ms": min(ts), "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                  "frac": gbs / pk["hbm_gbs"], "algorithmic_bytes": nbytes,
-                  "note": "generic-grid trilinear gather: 8 taps per output re-read the volume through L2 -> L1 "
-                          "(DESIGN.md section 5); the pipeline itself uses the fused channels-last warp kernels above"}
-            del v, grid
+        gs = grid_sample_leg(dev, pk)
     except Exception as e:      # the op leg must never take the headline number down with it
         gs = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
 

@@ -177,13 +177,18 @@ int mp_apply_warping_field_ws(const float* v, const float* warp_field, float* ou
  * memory (zero fill outside the volume = ATen's within_bounds test), the 8 taps are read from shared memory with the
  * tile's voxels bucketed by bank so that jittery grids stay conflict-free, and each result tile leaves through one TMA
  * box store.  Tiles whose sampling region does not fit the brick fall back to direct gathers inside the same kernel.
- * No workspace, no whole-volume transpose.  Requires W % 4 == 0, Wo % 4 == 0, D/H/W <= 1023, 16-byte aligned v / out.
+ * No whole-volume transpose.  Requires W % 4 == 0, Wo % 4 == 0, D/H/W <= 1023, 16-byte aligned v / out.
+ * workspace (optional, caller-owned, mp_gs_brick_workspace_bytes: one byte per output tile): when given, the kernel
+ * records which tiles it served and a second launch gathers the others at full occupancy (exits at once when there are
+ * none); when NULL, unfit tiles are gathered inside the brick kernel (slow for grids that are mostly unfit).
  * flags: bit 0 = do not bucket by bank (A/B).  mp_gs_brick_tune: {tz, ty, tx, BD, BH, BW, threads, groups} overrides,
  * 0 = automatic (test / profiling hook; process-wide). */
-int mp_grid_sample3d_brick(const float* v, const float* grid, float* out, int N, int C, int D, int H, int W, int Do,
-                           int Ho, int Wo, int flags, void* stream);
-int mp_apply_warping_field_brick(const float* v, const float* warp_field, float* out, int N, int C, int D, int H,
-                                 int W, int Df, int Hf, int Wf, int flags, void* stream);
+size_t mp_gs_brick_workspace_bytes(int N, int Do, int Ho, int Wo);
+int mp_grid_sample3d_brick(const float* v, const float* grid, float* out, void* workspace, size_t workspace_bytes, int N,
+                           int C, int D, int H, int W, int Do, int Ho, int Wo, int flags, void* stream);
+int mp_apply_warping_field_brick(const float* v, const float* warp_field, float* out, void* workspace,
+                                 size_t workspace_bytes, int N, int C, int D, int H, int W, int Df, int Hf, int Wf,
+                                 int flags, void* stream);
 int mp_gs_brick_tune(const int* cfg, int n);
 /* apply_warping_field(v, warp_field) (model.py:1028-1065) in the reference layout: v [N,C,D,H,W],
  * warp_field [N,3,Df,Hf,Wf] -> out [N,C,D,H,W]; the flow resample, identity grid, the reference's

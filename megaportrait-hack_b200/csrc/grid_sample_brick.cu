@@ -32,10 +32,10 @@
 
 namespace {
 
-constexpr int GB_MAX_THREADS = 512;
+constexpr int GB_MAX_THREADS = 1024;     // two builds: 512 threads (<= 128 registers) and 1024 threads (<= 64)
 constexpr int GB_NB = 4;            // brick ring: two channel pairs
-constexpr int GB_VPT = 8;           // voxels per thread while the taps are built (tile_vox <= GB_VPT * threads)
-constexpr int GB_RPW = 10;          // warp rows per warp in the channel loop (tap records live in registers)
+constexpr int GB_TILE_MAX = 4096;   // voxels per tile: each thread builds GB_TILE_MAX / T taps ...
+constexpr int GB_ROWS_MAX = 160;    // ... and each warp keeps GB_ROWS_MAX / (T / 32) warp rows of tap records in registers
 constexpr uint32_t GB_SMEM_LIMIT = 227 * 1024;
 
 struct __align__(16) TapRec {
@@ -47,6 +47,7 @@ struct GbParams {
   const float* v;
   const float* aux;     // MODE 0: grid [N, Do, Ho, Wo, 3]; MODE 1: warp field [N, 3, Df, Hf, Wf]
   float* out;
+  unsigned char* fitmap;   // [N, tiles]: 1 = the tile was served from bricks; NULL = unfit tiles gather inside the kernel
   int C, D, H, W, Do, Ho, Wo, Df, Hf, Wf;
   int tz, ty, tx, tile_vox;
   int tiles_z, tiles_y, tiles_x;
@@ -106,15 +107,83 @@ struct Misc {
 //   [off_stage, off_stage + 4 * stage_bytes) two staging buffers x two channels; before the channel loop, together with
 //                                            brick 3: the slot table (GB_RPW * warps * 32 tap records)
 //   [off_misc, ...)                          mbarriers, bounding box, bucket histograms
+// clamped pixel coordinates of output voxel (w, h, d) of sample n: from 3 grid values (MODE 0) or from the warp field
+// (MODE 1: flow resample, identity grid, the reference's re-normalisation -- model.py:1036-1058)
+template <int MODE>
+__device__ __forceinline__ void gb_pix(const GbParams& p, int n, int w, int h, int d, const float* g, float& ix, float& iy,
+                                       float& iz) {
+  if (MODE == 0) {
+    ix = unnormalize_clip(g[0], p.W); iy = unnormalize_clip(g[1], p.H); iz = unnormalize_clip(g[2], p.D);
+  } else {
+    int d0, d1, h0, h1, w0, w1;
+    float ld, lh, lw;
+    src_ac_true(d, p.Df, p.D, d0, d1, ld);
+    src_ac_true(h, p.Hf, p.H, h0, h1, lh);
+    src_ac_true(w, p.Wf, p.W, w0, w1, lw);
+    const int64_t fs = (int64_t)p.Df * p.Hf * p.Wf;
+    const float* f = p.aux + (int64_t)n * 3 * fs;
+    const float fx = resample_flow(f, p.Df, p.Hf, p.Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+    const float fy = resample_flow(f + fs, p.Df, p.Hf, p.Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+    const float fz = resample_flow(f + 2 * fs, p.Df, p.Hf, p.Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+    ix = unnormalize_clip(2.0f * (linspace_m1_1(w, p.W) + fx) / (float)(p.W - 1) - 1.0f, p.W);
+    iy = unnormalize_clip(2.0f * (linspace_m1_1(h, p.H) + fy) / (float)(p.H - 1) - 1.0f, p.H);
+    iz = unnormalize_clip(2.0f * (linspace_m1_1(d, p.D) + fz) / (float)(p.D - 1) - 1.0f, p.D);
+  }
+}
+
+// taps of cell (x0, y0, z0) + fractions for direct global gathers (same arithmetic as make_taps)
+__device__ __forceinline__ void gb_cell_taps(const GbParams& p, int x0, int y0, int z0, float ftx, float fty, float ftz, Taps& tp) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+    const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
+    const float wgt = (dx ? ftx : 1.f - ftx) * (dy ? fty : 1.f - fty) * (dz ? ftz : 1.f - ftz);
+    const bool ok = x < p.W && y < p.H && z < p.D;
+    tp.off[k] = ok ? (z * p.H + y) * p.W + x : -1;
+    tp.w[k] = ok ? wgt : 0.f;
+  }
+}
+
+// Second pass (only when the caller passed a fit map): tiles whose sampling region did not fit the brick, gathered
+// straight from global memory at full occupancy.  One CTA = one tile x one share of the channels.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_gs_unfit(const GbParams p, int shares) {
+  const int n = blockIdx.z;
+  const int tiles = p.tiles_x * p.tiles_y * p.tiles_z;
+  if (p.fitmap[(int64_t)n * tiles + blockIdx.x]) return;
+  int t = blockIdx.x;
+  const int tix = t % p.tiles_x; t /= p.tiles_x;
+  const int tiy = t % p.tiles_y; t /= p.tiles_y;
+  const int ox0 = tix * p.tx, oy0 = tiy * p.ty, oz0 = t * p.tz;
+  const int cb = p.C / shares, ce = p.C % shares;
+  const int c0 = blockIdx.y * cb + min((int)blockIdx.y, ce), nch = cb + ((int)blockIdx.y < ce ? 1 : 0);
+  const int64_t S = (int64_t)p.D * p.H * p.W, So = (int64_t)p.Do * p.Ho * p.Wo;
+  const float* vn = p.v + ((int64_t)n * p.C + c0) * S;
+  float* on = p.out + ((int64_t)n * p.C + c0) * So;
+  for (int vid = threadIdx.x; vid < p.tile_vox; vid += blockDim.x) {
+    const int lx = vid % p.tx, ly = (vid / p.tx) % p.ty, lz = vid / (p.tx * p.ty);
+    const int w = ox0 + lx, h = oy0 + ly, d = oz0 + lz;
+    if (w >= p.Wo || h >= p.Ho || d >= p.Do) continue;
+    const int64_t s = ((int64_t)d * p.Ho + h) * p.Wo + w;
+    float ix, iy, iz;
+    gb_pix<MODE>(p, n, w, h, d, p.aux + ((int64_t)n * So + s) * 3, ix, iy, iz);
+    Taps tp;
+    make_taps(ix, iy, iz, p.D, p.H, p.W, tp);
+    gather_channels(vn, on + s, tp, 0, nch, S, So);
+  }
+}
+
 // NS warp rows of one channel pair, branch-free (empty slots read offset 0 and skip the store), so that the loads of
 // all NS slots can be in flight together.
-template <int NS>
-__device__ __forceinline__ void gb_slots(const int (&m_ov)[GB_RPW], const float (&m_tx)[GB_RPW], const float (&m_ty)[GB_RPW],
-                                         const float (&m_tz)[GB_RPW], const float* __restrict__ bka,
+template <int NS, int O1, int O2, int RPW>
+__device__ __forceinline__ void gb_slots(const int (&m_ov)[RPW], const float (&m_tx)[RPW], const float (&m_ty)[RPW],
+                                         const float (&m_tz)[RPW], const float* __restrict__ bka,
                                          const float* __restrict__ bkb, float* __restrict__ sta, float* __restrict__ stb,
-                                         int o1, int o2) {
+                                         int o1r, int o2r) {
+  const int o1 = O1 > 0 ? O1 : o1r, o2 = O1 > 0 ? O2 : o2r;     // brick row / slice pitch: immediates when known
 #pragma unroll
-  for (int j = 0; j < NS; ++j) {
+  for (int j = 0; j < (NS < RPW ? NS : RPW); ++j) {
     const bool ok = m_ov[j] >= 0;
     const int off = ok ? (m_ov[j] & 0xffff) : 0, vid = m_ov[j] >> 16;
     const float* qa = bka + off;
@@ -145,10 +214,11 @@ __device__ __forceinline__ void gb_slots(const int (&m_ov)[GB_RPW], const float 
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(GB_MAX_THREADS, 1)
+template <int MODE, int O1, int O2, int T>
+__global__ void __launch_bounds__(T, 1)
 k_grid_sample_brick(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
                     const GbParams p) {
+  constexpr int GB_VPT = GB_TILE_MAX / T, GB_RPW = GB_ROWS_MAX / (T / 32);
   extern __shared__ uint8_t smem_raw[];
   // 128-byte alignment by an OFFSET into the shared array (an integer round trip would turn every access below into a
   // generic-address load with 64-bit address arithmetic)
@@ -229,24 +299,7 @@ k_grid_sample_brick(const __grid_constant__ CUtensorMap map_in, const __grid_con
     const int w = ox0 + lx, h = oy0 + ly, d = oz0 + lz;
     if (w >= p.Wo || h >= p.Ho || d >= p.Do) continue;
     float ix, iy, iz;
-    if (MODE == 0) {
-      const float* g = bricks + vid * 3;
-      ix = unnormalize_clip(g[0], p.W); iy = unnormalize_clip(g[1], p.H); iz = unnormalize_clip(g[2], p.D);
-    } else {
-      int d0, d1, h0, h1, w0, w1;
-      float ld, lh, lw;
-      src_ac_true(d, p.Df, p.D, d0, d1, ld);
-      src_ac_true(h, p.Hf, p.H, h0, h1, lh);
-      src_ac_true(w, p.Wf, p.W, w0, w1, lw);
-      const int64_t fs = (int64_t)p.Df * p.Hf * p.Wf;
-      const float* f = p.aux + (int64_t)n * 3 * fs;
-      const float fx = resample_flow(f, p.Df, p.Hf, p.Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
-      const float fy = resample_flow(f + fs, p.Df, p.Hf, p.Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
-      const float fz = resample_flow(f + 2 * fs, p.Df, p.Hf, p.Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
-      ix = unnormalize_clip(2.0f * (linspace_m1_1(w, p.W) + fx) / (float)(p.W - 1) - 1.0f, p.W);
-      iy = unnormalize_clip(2.0f * (linspace_m1_1(h, p.H) + fy) / (float)(p.H - 1) - 1.0f, p.H);
-      iz = unnormalize_clip(2.0f * (linspace_m1_1(d, p.D) + fz) / (float)(p.D - 1) - 1.0f, p.D);
-    }
+    gb_pix<MODE>(p, n, w, h, d, bricks + vid * 3, ix, iy, iz);
     const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
     int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
     a_tx[j] = ix - fx; a_ty[j] = iy - fy; a_tz[j] = iz - fz;
@@ -270,6 +323,10 @@ k_grid_sample_brick(const __grid_constant__ CUtensorMap map_in, const __grid_con
   const int zb = (p.D + 1 <= p.BD) ? 0 : misc->bmin[2];
   const bool fit = (misc->bmax[0] + 1 - xb < p.BW) && (misc->bmax[1] + 1 - yb < p.BH) && (misc->bmax[2] + 1 - zb < p.BD);
 
+  if (p.fitmap) {
+    if (tid == 0 && grp == 0) p.fitmap[(int64_t)n * (p.tiles_x * p.tiles_y * p.tiles_z) + blockIdx.x] = fit ? 1 : 0;
+    if (!fit) return;                 // k_gs_unfit gathers this tile at full occupancy
+  }
   if (!fit) {
     // ------------------------------------------------------------ fallback: direct global gathers for this tile
     const int64_t S = (int64_t)p.D * p.H * p.W;
@@ -285,15 +342,7 @@ k_grid_sample_brick(const __grid_constant__ CUtensorMap map_in, const __grid_con
       if (cell < 0) continue;
       const int x0 = cell & 1023, y0 = (cell >> 10) & 1023, z0 = cell >> 20;
       Taps tp;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
-        const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
-        const float wgt = (dx ? ftx : 1.f - ftx) * (dy ? fty : 1.f - fty) * (dz ? ftz : 1.f - ftz);
-        const bool ok = x < p.W && y < p.H && z < p.D;
-        tp.off[k] = ok ? (z * p.H + y) * p.W + x : -1;
-        tp.w[k] = ok ? wgt : 0.f;
-      }
+      gb_cell_taps(p, x0, y0, z0, ftx, fty, ftz, tp);
       const int vid = (warp * GB_VPT + j) * 32 + lane;
       const int lx = vid % p.tx, ly = (vid / p.tx) % p.ty, lz = vid / (p.tx * p.ty);
       const int64_t s = ((int64_t)(oz0 + lz) * p.Ho + (oy0 + ly)) * p.Wo + (ox0 + lx);
@@ -395,16 +444,16 @@ k_grid_sample_brick(const __grid_constant__ CUtensorMap map_in, const __grid_con
     float* sta = stage + ((ca >> 1) & 1) * 2 * stage_f;
     float* stb = sta + stage_f;
     switch (nslots) {
-      case 10: gb_slots<10>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 9: gb_slots<9>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 8: gb_slots<8>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 7: gb_slots<7>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 6: gb_slots<6>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 5: gb_slots<5>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 4: gb_slots<4>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 3: gb_slots<3>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 2: gb_slots<2>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
-      case 1: gb_slots<1>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 10: gb_slots<10, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 9: gb_slots<9, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 8: gb_slots<8, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 7: gb_slots<7, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 6: gb_slots<6, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 5: gb_slots<5, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 4: gb_slots<4, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 3: gb_slots<3, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 2: gb_slots<2, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
+      case 1: gb_slots<1, O1, O2, GB_RPW>(m_ov, m_tx, m_ty, m_tz, bka, bkb, sta, stb, o1, o2); break;
       default: break;
     }
     fence_proxy_async();                 // my staged values -> visible to the TMA store
@@ -461,8 +510,16 @@ int g_tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-int launch_brick(int mode, const float* v, const float* aux, float* out, int N, int C, int D, int H, int W, int Do, int Ho,
-                 int Wo, int Df, int Hf, int Wf, int flags, void* stream, const char* who) {
+void tile_shape(int Do, int Ho, int Wo, int threads, int& tz, int& ty, int& tx) {
+  const int T = threads > 512 ? 1024 : 512;
+  tx = g_tune[2] ? g_tune[2] : (Wo < 64 ? Wo : 64);
+  ty = g_tune[1] ? g_tune[1] : (Ho < 16 ? Ho : 16);
+  tz = g_tune[0] ? g_tune[0] : (Do < 4 ? Do : 4);
+  while (tz > 1 && tz * ty * tx > GB_TILE_MAX / T * threads) --tz;
+}
+
+int launch_brick(int mode, const float* v, const float* aux, float* out, void* workspace, size_t workspace_bytes, int N, int C,
+                 int D, int H, int W, int Do, int Ho, int Wo, int Df, int Hf, int Wf, int flags, void* stream, const char* who) {
   MP_REQUIRE(encoder() != nullptr, "%s: cuTensorMapEncodeTiled not available from the driver", who);
   MP_REQUIRE(W % 4 == 0 && Wo % 4 == 0, "%s: W and Wo must be multiples of 4 (16-byte TMA rows); use the direct entry point", who);
   MP_REQUIRE(D <= 1023 && H <= 1023 && W <= 1023, "%s: volume extents above 1023 are not supported", who);
@@ -471,14 +528,13 @@ int launch_brick(int mode, const float* v, const float* aux, float* out, int N, 
   p.v = v; p.aux = aux; p.out = out;
   p.C = C; p.D = D; p.H = H; p.W = W; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.Df = Df; p.Hf = Hf; p.Wf = Wf;
   // output tile: whole rows up to 64 wide, 16 rows, as many slices as 4096 voxels allow (at most 4)
-  p.tx = g_tune[2] ? g_tune[2] : (Wo < 64 ? Wo : 64);
-  p.ty = g_tune[1] ? g_tune[1] : (Ho < 16 ? Ho : 16);
-  p.tz = g_tune[0] ? g_tune[0] : (Do < 4 ? Do : 4);
-  const int threads = g_tune[6] ? g_tune[6] : GB_MAX_THREADS;
+  const int threads = g_tune[6] ? g_tune[6] : 512;
+  tile_shape(Do, Ho, Wo, threads, p.tz, p.ty, p.tx);
   MP_REQUIRE(threads % 32 == 0 && threads >= 32 && threads <= GB_MAX_THREADS, "%s: bad thread count", who);
-  while (p.tz > 1 && p.tz * p.ty * p.tx > GB_VPT * threads) --p.tz;
-  MP_REQUIRE(p.tx % 4 == 0 && p.tx <= 256 && p.ty <= 256 && p.tz <= 256 && p.tz * p.ty * p.tx <= GB_VPT * threads,
-             "%s: bad tile (at most %d voxels)", who, GB_VPT * threads);
+  const int T = threads > 512 ? 1024 : 512;                 // kernel build: registers per thread, taps per thread
+  const int vpt = GB_TILE_MAX / T, rpw = GB_ROWS_MAX / (T / 32);
+  MP_REQUIRE(p.tx % 4 == 0 && p.tx <= 256 && p.ty <= 256 && p.tz <= 256 && p.tz * p.ty * p.tx <= vpt * threads,
+             "%s: bad tile (at most %d voxels)", who, vpt * threads);
   p.tile_vox = p.tz * p.ty * p.tx;
   p.tiles_x = (Wo + p.tx - 1) / p.tx; p.tiles_y = (Ho + p.ty - 1) / p.ty; p.tiles_z = (Do + p.tz - 1) / p.tz;
   // brick: tile extent + a halo of 4 cells (y, x) / 1 cell (z) on each side + the far corner, capped by the volume
@@ -496,7 +552,7 @@ int launch_brick(int mode, const float* v, const float* aux, float* out, int N, 
   const uint32_t smem = p.off_misc + (uint32_t)sizeof(Misc) + 128u;
   // scratch that aliases the ring before the channel loop: raw grid over bricks 0-1.., slot table over brick 3 + staging
   MP_REQUIRE((uint32_t)p.tile_vox * 12u <= p.off_misc || mode != 0, "%s: ring too small for the grid scratch", who);
-  p.rows_cap = min(GB_RPW * (threads / 32), (int)((p.brick_bytes + 4u * p.stage_bytes) / 512u));
+  p.rows_cap = min(rpw * (threads / 32), (int)((p.brick_bytes + 4u * p.stage_bytes) / 512u));
   MP_REQUIRE((p.tile_vox + 31) / 32 <= p.rows_cap, "%s: slot table does not fit", who);
   MP_REQUIRE(smem <= GB_SMEM_LIMIT, "%s: tile/brick configuration needs %u B of shared memory", who, smem);
   // channel groups: enough CTAs to fill the SMs, at least ~8 channels per CTA to amortise phase A
@@ -524,17 +580,38 @@ int launch_brick(int mode, const float* v, const float* aux, float* out, int N, 
   CUtensorMap mi, mo;
   if (int e = encode_vol_map(&mi, v, (int64_t)N * C, D, H, W, p.BD, p.BH, p.BW)) return e;
   if (int e = encode_vol_map(&mo, out, (int64_t)N * C, Do, Ho, Wo, p.tz, p.ty, p.tx)) return e;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[mode]) {
-    cudaError_t ae = mode == 0
-        ? cudaFuncSetAttribute(k_grid_sample_brick<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM_LIMIT)
-        : cudaFuncSetAttribute(k_grid_sample_brick<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM_LIMIT);
+  // the (16, 64, 64) volume's brick (BW = 68, BH = 24) gets its pitches as immediates
+  const bool fixed = p.BW == 68 && p.BH == 24;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const GbParams);
+  KernelFn fn;
+  if (T == 512)
+    fn = mode == 0 ? (fixed ? k_grid_sample_brick<0, 68, 68 * 24, 512> : k_grid_sample_brick<0, 0, 0, 512>)
+                   : (fixed ? k_grid_sample_brick<1, 68, 68 * 24, 512> : k_grid_sample_brick<1, 0, 0, 512>);
+  else
+    fn = mode == 0 ? (fixed ? k_grid_sample_brick<0, 68, 68 * 24, 1024> : k_grid_sample_brick<0, 0, 0, 1024>)
+                   : (fixed ? k_grid_sample_brick<1, 68, 68 * 24, 1024> : k_grid_sample_brick<1, 0, 0, 1024>);
+  static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+  const int ai = mode * 4 + (fixed ? 2 : 0) + (T == 512 ? 0 : 1);
+  if (!attr_done[ai]) {
+    cudaError_t ae = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM_LIMIT);
     MP_REQUIRE(ae == cudaSuccess, "%s: cannot opt in to %u B shared memory: %s", who, GB_SMEM_LIMIT, cudaGetErrorString(ae));
-    attr_done[mode] = true;
+    attr_done[ai] = true;
   }
   dim3 grid((unsigned)(tiles / N), (unsigned)ng, (unsigned)N);
-  if (mode == 0) k_grid_sample_brick<0><<<grid, threads, smem, mp_stream(stream)>>>(mi, mo, p);
-  else k_grid_sample_brick<1><<<grid, threads, smem, mp_stream(stream)>>>(mi, mo, p);
+  p.fitmap = nullptr;
+  if (workspace) {
+    MP_REQUIRE(workspace_bytes >= (size_t)tiles, "%s: workspace too small (%zu < %lld)", who, workspace_bytes, (long long)tiles);
+    p.fitmap = static_cast<unsigned char*>(workspace);
+  }
+  fn<<<grid, threads, smem, mp_stream(stream)>>>(mi, mo, p);
+  if (p.fitmap) {
+    MP_LAUNCH_CHECK(who);
+    // 8 channels per CTA like the plain gather kernel; CTAs of served tiles exit on their first load (one byte)
+    const int shares = (C + GS_CCHUNK - 1) / GS_CCHUNK;
+    dim3 g2((unsigned)(tiles / N), (unsigned)shares, (unsigned)N);
+    if (mode == 0) k_gs_unfit<0><<<g2, 256, 0, mp_stream(stream)>>>(p, shares);
+    else k_gs_unfit<1><<<g2, 256, 0, mp_stream(stream)>>>(p, shares);
+  }
   MP_LAUNCH_CHECK(who);
   return 0;
 }
@@ -546,19 +623,27 @@ extern "C" int mp_gs_brick_tune(const int* cfg, int n) {
   return 0;
 }
 
-extern "C" int mp_grid_sample3d_brick(const float* v, const float* grid, float* out, int N, int C, int D, int H, int W,
-                                      int Do, int Ho, int Wo, int flags, void* stream) {
+extern "C" size_t mp_gs_brick_workspace_bytes(int N, int Do, int Ho, int Wo) {
+  int tz, ty, tx;
+  tile_shape(Do, Ho, Wo, g_tune[6] ? g_tune[6] : 512, tz, ty, tx);
+  return (size_t)N * ((Wo + tx - 1) / tx) * ((Ho + ty - 1) / ty) * ((Do + tz - 1) / tz);
+}
+
+extern "C" int mp_grid_sample3d_brick(const float* v, const float* grid, float* out, void* workspace, size_t workspace_bytes,
+                                      int N, int C, int D, int H, int W, int Do, int Ho, int Wo, int flags, void* stream) {
   MP_REQUIRE(v && grid && out, "mp_grid_sample3d_brick: null pointer");
   MP_REQUIRE(N > 0 && N <= 65535 && C > 0 && D > 0 && H > 0 && W > 0 && Do > 0 && Ho > 0 && Wo > 0,
              "mp_grid_sample3d_brick: bad dims");
-  return launch_brick(0, v, grid, out, N, C, D, H, W, Do, Ho, Wo, 0, 0, 0, flags, stream, "mp_grid_sample3d_brick");
+  return launch_brick(0, v, grid, out, workspace, workspace_bytes, N, C, D, H, W, Do, Ho, Wo, 0, 0, 0, flags, stream,
+                      "mp_grid_sample3d_brick");
 }
 
-extern "C" int mp_apply_warping_field_brick(const float* v, const float* warp_field, float* out, int N, int C, int D,
-                                            int H, int W, int Df, int Hf, int Wf, int flags, void* stream) {
+extern "C" int mp_apply_warping_field_brick(const float* v, const float* warp_field, float* out, void* workspace,
+                                            size_t workspace_bytes, int N, int C, int D, int H, int W, int Df, int Hf, int Wf,
+                                            int flags, void* stream) {
   MP_REQUIRE(v && warp_field && out, "mp_apply_warping_field_brick: null pointer");
   MP_REQUIRE(N > 0 && N <= 65535 && C > 0 && D > 1 && H > 1 && W > 1 && Df > 0 && Hf > 0 && Wf > 0,
              "mp_apply_warping_field_brick: bad dims");
-  return launch_brick(1, v, warp_field, out, N, C, D, H, W, D, H, W, Df, Hf, Wf, flags, stream,
+  return launch_brick(1, v, warp_field, out, workspace, workspace_bytes, N, C, D, H, W, D, H, W, Df, Hf, Wf, flags, stream,
                       "mp_apply_warping_field_brick");
 }

@@ -96,9 +96,11 @@ _SIGNATURES = {
     "mp_grid_sample3d_ws": (c_int, [_P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_apply_warping_field_ws": (c_int, [_P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_int, _P]),
-    "mp_grid_sample3d_brick": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "mp_apply_warping_field_brick": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                             _P]),
+    "mp_gs_brick_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "mp_grid_sample3d_brick": (c_int, [_P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, _P]),
+    "mp_apply_warping_field_brick": (c_int, [_P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                             c_int, c_int, _P]),
     "mp_gs_brick_tune": (c_int, [POINTER(c_int), c_int]),
     "mp_warp_field": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "mp_warp_fused_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

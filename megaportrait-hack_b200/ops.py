@@ -591,13 +591,21 @@ def gs_brick_tune(cfg: Sequence[int] = ()) -> None:
     _lib.check(_lib.load().mp_gs_brick_tune(arr, 8), "mp_gs_brick_tune")
 
 
+def _brick_ws(L, N, Do, Ho, Wo, device, second_pass: bool):
+    if not second_pass:
+        return None, 0
+    nb = L.mp_gs_brick_workspace_bytes(N, Do, Ho, Wo)
+    return torch.empty(nb, dtype=torch.uint8, device=device), nb
+
+
 def grid_sample3d(v: torch.Tensor, grid: torch.Tensor, direct: bool = False, impl: Optional[str] = None,
-                  bucket: bool = True) -> torch.Tensor:
+                  bucket: bool = True, second_pass: bool = True) -> torch.Tensor:
     """F.grid_sample(v, grid, 'bilinear', 'border', align_corners=True) for NCDHW fp32 (model.py:1062).
 
-    `impl`: "brick" (default where the shape allows: TMA-staged bricks in shared memory, per-tile fallback to direct
-    gathers), "ws" (channels-last workspace copy + gather: the better choice for random-permutation grids), "direct"
-    (plain NCDHW gather).  All three give the same bits."""
+    `impl`: "brick" (default where the shape allows: TMA-staged bricks in shared memory; tiles whose sampling region does
+    not fit a brick are gathered by a second launch, or inside the brick kernel with `second_pass=False`), "ws"
+    (channels-last workspace copy + gather: the better choice for random-permutation grids), "direct" (plain NCDHW
+    gather).  All three give the same bits."""
     _chk_cuda(v, torch.float32, "grid_sample3d v")
     _chk_cuda(grid, torch.float32, "grid_sample3d grid")
     N, C, D, H, W = v.shape
@@ -610,10 +618,11 @@ def grid_sample3d(v: torch.Tensor, grid: torch.Tensor, direct: bool = False, imp
         impl = "direct" if direct else ("brick" if _brick_ok(W, Wo, D, H, v, out) else "ws")
     nbytes = N * (C * D * H * W + C * Do * Ho * Wo + 3 * Do * Ho * Wo) * 4
     if impl == "brick":
+        ws, nb = _brick_ws(L, N, Do, Ho, Wo, v.device, second_pass)
         with _Prof("grid_sample3d", 0, nbytes):
-            _lib.check(L.mp_grid_sample3d_brick(_p(v), _p(grid), _p(out), N, C, D, H, W, Do, Ho, Wo, 0 if bucket else 1,
-                                                _stream()), "mp_grid_sample3d_brick")
-        _count()
+            _lib.check(L.mp_grid_sample3d_brick(_p(v), _p(grid), _p(out), _p(ws), nb, N, C, D, H, W, Do, Ho, Wo,
+                                                0 if bucket else 1, _stream()), "mp_grid_sample3d_brick")
+        _count(2 if second_pass else 1)
         return out
     ws_bytes = L.mp_gather_workspace_bytes(N, C, D, H, W) if impl == "ws" else 0
     if ws_bytes:
@@ -642,9 +651,10 @@ def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor, direct:
     if impl is None:
         impl = "direct" if direct else ("brick" if (_brick_ok(W, W, D, H, v, out) and min(D, H, W) > 1) else "ws")
     if impl == "brick":
-        _lib.check(L.mp_apply_warping_field_brick(_p(v), _p(warp_field), _p(out), N, C, D, H, W, Df, Hf, Wf, 0, _stream()),
-                   "mp_apply_warping_field_brick")
-        _count()
+        ws, nb = _brick_ws(L, N, D, H, W, v.device, True)
+        _lib.check(L.mp_apply_warping_field_brick(_p(v), _p(warp_field), _p(out), _p(ws), nb, N, C, D, H, W, Df, Hf, Wf, 0,
+                                                  _stream()), "mp_apply_warping_field_brick")
+        _count(2)
         return out
     ws_bytes = L.mp_gather_workspace_bytes(N, C, D, H, W) if impl == "ws" else 0
     if ws_bytes:

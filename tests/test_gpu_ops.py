@@ -209,9 +209,11 @@ def test_grid_sample3d(ops, kind):
     ref = _gs_ref(v, grid)
     got = {impl: ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl=impl).cpu() for impl in IMPLS}
     got["brick_nobucket"] = ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="brick", bucket=False).cpu()
+    got["brick_inline"] = ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="brick", second_pass=False).cpu()
     for impl, g in got.items():
         assert (g - ref).abs().max().item() <= 1e-5, impl
-    assert torch.equal(got["brick"], got["direct"]) and torch.equal(got["brick_nobucket"], got["direct"])
+    for impl in ("brick", "brick_nobucket", "brick_inline"):
+        assert torch.equal(got[impl], got["direct"]), impl
 
 
 def test_grid_sample3d_brick_is_default_and_covers_all_channels(ops):
@@ -222,7 +224,7 @@ def test_grid_sample3d_brick_is_default_and_covers_all_channels(ops):
     ref = _gs_ref(v, grid)
     l0 = ops.LAUNCHES
     got = ops.grid_sample3d(v.to(DEV), grid.to(DEV)).cpu()
-    assert ops.LAUNCHES - l0 == 1, "default path must be the single brick kernel"
+    assert ops.LAUNCHES - l0 == 2, "default path = brick kernel + the (here empty) second pass for unfit tiles"
     assert (got - ref).abs().max().item() <= 1e-5
     for groups in (1, 5, 7, 12):          # uneven channel splits (96 = 7 x 13 + 5)
         ops.gs_brick_tune([0, 0, 0, 0, 0, 0, 0, groups])
@@ -259,6 +261,7 @@ def test_grid_sample3d_brick_edge_grids(ops, kind):
     want = ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="direct").cpu()
     got = ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="brick").cpu()
     assert torch.equal(got, want)
+    assert torch.equal(ops.grid_sample3d(v.to(DEV), grid.to(DEV), impl="brick", second_pass=False).cpu(), want)
     if kind != "nan":
         assert (got - _gs_ref(v, grid)).abs().max().item() <= 1e-5
 

@@ -70,19 +70,28 @@ def main():
             grid = make_grid(kind, B, dev)
             want = ops.grid_sample3d(v, grid, impl="direct") if args.check else None
             for impl in args.impls.split(","):
-                kw = dict(impl="brick", bucket=False) if impl == "brick_nobucket" else dict(impl=impl)
-                out = ops.grid_sample3d(v, grid, **kw)
-                if want is not None:
+                kw = {"brick_nobucket": dict(impl="brick", bucket=False),
+                      "brick_inline": dict(impl="brick", second_pass=False)}.get(impl, dict(impl=impl))
+                if impl == "copy":       # same bytes through torch's copy kernel + a grid-sized read: what this size can reach
+                    out = torch.empty_like(v)
+                    run = lambda: (out.copy_(v), grid.sum())
+                else:
+                    run = lambda: ops.grid_sample3d(v, grid, **kw)
+                if impl == "copy":
+                    run()
+                else:
+                    out = run()
+                if want is not None and impl != "copy":
                     assert torch.equal(out, want), (B, kind, impl)
                 for _ in range(2):
-                    ops.grid_sample3d(v, grid, **kw)
+                    run()
                 ts = []
                 for _ in range(args.reps):
                     if not args.no_flush:
                         flush.fill_(1)
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    ops.grid_sample3d(v, grid, **kw)
+                    run()
                     e1.record()
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
