@@ -1,9 +1,10 @@
 """Motion encoder `Emtn` (model.py:869-907) and the `CustomResNet50` descriptor branch
 (model.py:136-173, row a7): module definitions with the reference's attribute names and state_dict keys.
 
-Inference on a CUDA device runs both on libmpb200 kernels (`emtn_cuda.py`, `backend = "mpb200"`, the default).
-`backend = "cudnn"` selects a stock cuDNN plan (BatchNorm folded, channels_last) that also serves CPU tensors and is
-kept as the GPU incumbent for A/B timing; train mode / autograd use the plain module graph.
+`backend = "mpb200"` (the default) runs both on libmpb200 kernels (`emtn_cuda.py`): CUDA tensors, inference only --
+CPU tensors, train mode and autograd RAISE (no silent ATen fallback).  `backend = "cudnn"` is an explicit opt-in to the
+stock ATen / cuDNN graph (BatchNorm folded, channels_last; plain module graph in train mode or under autograd): the GPU
+incumbent for A/B timing and the second opinion of tests/test_gpu_gbase.py; it is never selected automatically.
 """
 from __future__ import annotations
 
@@ -45,13 +46,14 @@ class CustomResNet50(nn.Module):
         self.backend = "mpb200"
 
     def forward(self, x):
-        if self.training or torch.is_grad_enabled():
+        if getattr(self, "backend", "mpb200") == "mpb200":
+            _require_mpb200(self, x)
+            from . import emtn_cuda
+            return emtn_cuda.resnet50_descriptor(self, x)
+        if self.training or torch.is_grad_enabled():        # backend == "cudnn" (explicit opt-in): stock module graph
             x = F.relu(self.bn1(self.conv1(x)))
             x = self.maxpool(x)
             x = self.layer3(self.layer2(self.layer1(x)))
-        elif x.is_cuda and getattr(self, "backend", "mpb200") == "mpb200":
-            from . import emtn_cuda
-            return emtn_cuda.resnet50_descriptor(self, x)
         else:
             sig = _versions(self)
             c = self.__dict__.get("_mp_plan")
@@ -186,11 +188,22 @@ class _FoldedResNetTrunk(nn.Module):
 
 
 def _versions(mod: nn.Module):
-    s, dev = 0, None
-    for t in list(mod.parameters()) + list(mod.buffers()):
-        s += t._version + (t.data_ptr() & 0xFFFF)
-        dev = t.device
-    return (s, str(dev))
+    """Per-tensor (data_ptr, version) of every parameter / buffer + device (see model._sig for the `.data` caveat)."""
+    ts = list(mod.parameters()) + list(mod.buffers())
+    return (tuple((t.data_ptr(), t._version) for t in ts), str(ts[0].device) if ts else "")
+
+
+def _require_mpb200(mod: nn.Module, x: torch.Tensor) -> None:
+    """The libmpb200 backend serves CUDA tensors in inference mode only; everything else raises (no silent fallback)."""
+    if not x.is_cuda:
+        raise RuntimeError(f"{type(mod).__name__}: input is on {x.device}; the B200 path has no CPU fallback "
+                           "(set .backend = 'cudnn' explicitly to run the stock ATen graph)")
+    if mod.training:
+        raise NotImplementedError(f"{type(mod).__name__}: train-mode BatchNorm is not implemented on the B200 path "
+                                  "(SURVEY.md 8f-2); call .eval(), or set .backend = 'cudnn' for the stock ATen graph")
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in mod.parameters())):
+        raise NotImplementedError(f"{type(mod).__name__}: backward is not implemented on the B200 path (SURVEY.md "
+                                  "8f-2); call under torch.no_grad(), or set .backend = 'cudnn' for the stock ATen graph")
 
 
 class Emtn(nn.Module):
@@ -224,16 +237,18 @@ class Emtn(nn.Module):
         return c[1]
 
     def forward(self, x):
+        if getattr(self, "backend", "mpb200") == "mpb200":
+            _require_mpb200(self, x)
+            from . import emtn_cuda          # libmpb200 tcgen05 kernels (SURVEY.md row f-1)
+            with torch.no_grad():
+                return emtn_cuda.emtn_forward(self, x)
         if self.training or torch.is_grad_enabled():
-            # stock path (train-mode BatchNorm / autograd), exactly the reference's module graph
+            # backend == "cudnn" (explicit opt-in): train-mode BatchNorm / autograd on the reference's module graph
             rotations, _ = self.rotation_net.predict(x)
             head_pose = self.head_pose_net(x)
             translation = head_pose[:, 3:]
             expression = self.fc(torch.flatten(self.expression_net(x), start_dim=1))
             return rotations, translation, expression
-        if x.is_cuda and getattr(self, "backend", "mpb200") == "mpb200":
-            from . import emtn_cuda          # libmpb200 tcgen05 kernels (SURVEY.md row f-1)
-            return emtn_cuda.emtn_forward(self, x)
         # stock cuDNN plan: BatchNorm folded, channels_last (no NCHW<->NHWC transposes around the cuDNN kernels)
         hp_trunk, ex_trunk = self._plans()
         xcl = x.contiguous(memory_format=torch.channels_last)

@@ -42,14 +42,34 @@ def _require_inference(mod: nn.Module, *tensors) -> None:
                                   "call under torch.no_grad()")
 
 
+def _require_no_grad(mod: nn.Module, *tensors) -> None:
+    """Entry points that run under `torch.no_grad()` internally: called with autograd recording on and anything that
+    asks for a gradient (an input, or any parameter of `mod`), they would hand back detached outputs and the caller's
+    `.backward()` would silently train nothing (train.py:194, PairwiseTransferLoss model.py:2192-2214).  Raise instead."""
+    if not torch.is_grad_enabled():
+        return
+    if any(torch.is_tensor(t) and t.requires_grad for t in tensors) or any(p.requires_grad for p in mod.parameters()):
+        raise NotImplementedError(
+            f"{type(mod).__name__}: this B200 path is inference-only (backward = SURVEY.md 8f-2). Call it under "
+            "torch.no_grad() / torch.inference_mode(), or freeze the module with .requires_grad_(False)")
+
+
 def _sig(mod: nn.Module):
-    """Cheap change-detector for cached packed weights."""
-    s = 0
-    dev = None
-    for t in list(mod.parameters()) + list(mod.buffers()):
-        s += t._version + (t.data_ptr() & 0xFFFF)
-        dev = t.device
-    return (s, str(dev), mod.training)
+    """Change-detector for cached packed weights: per-tensor (data_ptr, version) of every parameter and buffer, the
+    device and the train flag.  In-place writes through `param.data` / `.data.copy_()` do NOT bump `_version`: after
+    such writes (EMA updates, hand-written checkpoint loaders) call `invalidate_plans(module)`."""
+    ts = list(mod.parameters()) + list(mod.buffers())
+    return (tuple((t.data_ptr(), t._version) for t in ts), str(ts[0].device) if ts else "", mod.training)
+
+
+def invalidate_plans(root: nn.Module) -> None:
+    """Drop every cached kernel-format weight plan under `root` (they are rebuilt on the next forward)."""
+    for m in root.modules():
+        for k in ("_mp_plan", "_mp_final", "_mp_plans", "_mp_cuda_plans", "_mp_cuda_plan"):
+            m.__dict__.pop(k, None)
+        det = getattr(m, "rotation_net", None)
+        if det is not None and hasattr(det, "model"):
+            det.model.__dict__.pop("_mp_plan", None)
 
 
 class _Packed:
@@ -63,6 +83,10 @@ class _Packed:
                 cache = (sig, self._build_plan())
             self.__dict__["_mp_plan"] = cache
         return cache[1]
+
+    def _load_from_state_dict(self, *a, **k):      # checkpoint loads copy through `.data`-like paths: drop the plan
+        self.__dict__.pop("_mp_plan", None)
+        return super()._load_from_state_dict(*a, **k)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -684,9 +708,12 @@ class Gbase(nn.Module):
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=bool(self.tf32_motion)):
             return self.motionEncoder(x)
 
-    @torch.no_grad()
     def encode_source(self, xs, keep_stages: bool = False) -> Dict[str, object]:
         """Source-only half (model.py:1141-1160): Eapp, Emtn(xs), S2C warp, G3d.  Returns the cached state."""
+        with torch.no_grad():       # non-reference, inference-only entry point: never records autograd
+            return self._encode_source(xs, keep_stages)
+
+    def _encode_source(self, xs, keep_stages: bool = False) -> Dict[str, object]:
         _require_inference(self, xs)
         if self.training:
             raise NotImplementedError("Gbase: train mode is not implemented on the B200 path (SURVEY.md 8f-2)")
@@ -709,17 +736,23 @@ class Gbase(nn.Module):
             src.update(vs=vs, Rs=Rs, ts=ts, zs=zs, em_s2c=em, theta_s2c=theta, vc=vc)
         return src
 
-    @torch.no_grad()
     def drive_motion(self, xd):
         """Driver-only part of the per-driver half (model.py:1145): Emtn(xd) -> (Rd, td, zd).  Independent of the
         source, so it can run concurrently with `encode_source` (engine.GraphedGbase does)."""
+        with torch.no_grad():
+            return self._drive_motion(xd)
+
+    def _drive_motion(self, xd):
         _require_inference(self, xd)
         with ops.stage("Emtn(drivers)", 235.6e9 * xd.shape[0]):
             return self._emtn(_as_f32_cuda(xd))
 
-    @torch.no_grad()
     def drive_render(self, src: Dict[str, object], motion, keep_stages: bool = False):
         """C2D warp generator, fused warp + depth sum, G2d, pyramid (model.py:1163-1180)."""
+        with torch.no_grad():
+            return self._drive_render(src, motion, keep_stages)
+
+    def _drive_render(self, src: Dict[str, object], motion, keep_stages: bool = False):
         Rd, td, zd = motion
         n = zd.shape[0]
         es = src["es"]
@@ -739,12 +772,14 @@ class Gbase(nn.Module):
             return xhat, pyramids, dict(Rd=Rd, td=td, zd=zd, em_c2d=em, theta_c2d=theta, projected=proj)
         return xhat, pyramids
 
-    @torch.no_grad()
     def drive(self, src: Dict[str, object], xd, keep_stages: bool = False):
         """Per-driver half (model.py:1145, 1163-1180).  `src["vc2d"]` may hold 1 sample (shared source) or len(xd)."""
         return self.drive_render(src, self.drive_motion(xd), keep_stages)
 
     def forward(self, xs, xd):
+        """model.py:1140-1180.  Inference-only: with autograd recording on and trainable parameters it raises
+        NotImplementedError rather than returning detached outputs."""
         assert xs.shape[0] == xd.shape[0], f"Expected zs and es to have the same shape (Bs == Bd), got {xs.shape[0]} and {xd.shape[0]}"
+        _require_no_grad(self, xs, xd)
         src = self.encode_source(xs)
         return self.drive(src, xd)

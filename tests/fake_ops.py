@@ -324,13 +324,16 @@ _NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear
 @contextlib.contextmanager
 def installed():
     saved = {n: getattr(ops, n) for n in _NAMES}
-    saved_req = M._require_inference
+    from megaportrait_hack_b200 import emtn as E
+    saved_req, saved_req2 = M._require_inference, E._require_mpb200
     try:
         for n in _NAMES:
             setattr(ops, n, globals()[n])
         M._require_inference = lambda *a, **k: None
+        E._require_mpb200 = lambda *a, **k: None      # the libmpb200 plans of Emtn / ResNet-50 run on the emulated kernels
         yield
     finally:
         for n, f in saved.items():
             setattr(ops, n, f)
         M._require_inference = saved_req
+        E._require_mpb200 = saved_req2

@@ -47,17 +47,12 @@ def oracle_synth(seeded_sd):
     return xs, xd, rgb, pyr, st
 
 
-def test_stage_parity_exact_motion(gbase, oracle_synth):
-    """Every hot-path stage against the oracle, with Emtn / descriptor in exact fp32 so stages are comparable."""
+def test_stage_parity(gbase, oracle_synth):
+    """Every hot-path stage against the oracle (default settings: split-bf16 generator, fp16x2 motion encoder, fp16 + e4m3
+    cross-term G2d res-blocks)."""
     xs, xd, rgb_o, pyr_o, st = oracle_synth
-    gbase.tf32_motion = False
-    gbase.appearanceEncoder.tf32_descriptor = False
-    try:
-        src = gbase.encode_source(xs.cuda(), keep_stages=True)
-        rgb, pyr, drv = gbase.drive(src, xd.cuda(), keep_stages=True)
-    finally:
-        gbase.tf32_motion = True
-        gbase.appearanceEncoder.tf32_descriptor = True
+    src = gbase.encode_source(xs.cuda(), keep_stages=True)
+    rgb, pyr, drv = gbase.drive(src, xd.cuda(), keep_stages=True)
     checks = {
         "vs": (_ncdhw(src["vs"]), st["vs"], STAGE_TOL), "es": (src["es"].cpu(), st["es"], STAGE_TOL),
         "zs": (src["zs"].cpu(), st["zs"], STAGE_TOL), "ts": (src["ts"].cpu(), st["ts"], STAGE_TOL),
@@ -75,16 +70,25 @@ def test_stage_parity_exact_motion(gbase, oracle_synth):
         assert (pyr[k].cpu() - pyr_o[k]).abs().max().item() <= RGB_TOL
 
 
-def test_rgb_parity_default_settings_shared_source(gbase, oracle_synth):
-    """BASELINE config 2 semantics (1 source x N drivers) with the bench's settings (TF32 motion encoder)."""
+def test_rgb_parity_shared_source_split_bf16_g2d(gbase, oracle_synth):
+    """BASELINE config 2 semantics (1 source x N drivers) with G2d's res-blocks forced onto the three-pass split-bf16
+    plans (what the pipeline uses when the F16_Q8 range check rejects a tensor): same budget."""
+    from megaportrait_hack_b200 import model
     xs, xd, rgb_o, pyr_o, st = oracle_synth
-    src = gbase.encode_source(xs.cuda(), keep_stages=True)
-    rgb, pyr, drv = gbase.drive(src, xd.cuda(), keep_stages=True)
+    saved = model._Q8_ENABLED
+    model._Q8_ENABLED = False
+    model.invalidate_plans(gbase.G2d)
+    try:
+        src = gbase.encode_source(xs.cuda(), keep_stages=True)
+        rgb, pyr, drv = gbase.drive(src, xd.cuda(), keep_stages=True)
+    finally:
+        model._Q8_ENABLED = saved
+        model.invalidate_plans(gbase.G2d)
     err = (rgb.cpu() - rgb_o).abs().max().item()
-    print("rgb max-abs (tf32 motion):", err, "zd rel:", rel(drv["zd"].cpu(), st["zd"]))
+    print("rgb max-abs (split-bf16 G2d):", err, "zd rel:", rel(drv["zd"].cpu(), st["zd"]))
     assert err <= RGB_TOL
     assert rel(drv["zd"].cpu(), st["zd"]) <= MOTION_TOL
-    assert rel(_ncdhw(src["vc2d"]), st["vc2d"]) <= 5 * STAGE_TOL
+    assert rel(_ncdhw(src["vc2d"]), st["vc2d"]) <= STAGE_TOL
 
 
 def test_forward_signature_and_real_frames(gbase, seeded_sd):
@@ -109,7 +113,8 @@ def test_batch_invariance_and_determinism(gbase):
     c, _ = gbase.drive(src, xd[1:3].cuda())
     assert (a[1:3] - c).abs().max().item() <= 1e-4, "batch invariance (cuDNN picks per-batch algorithms in Emtn)"
     # reference semantics Bs == Bd (model.py:993): per-sample sources
-    full, _ = gbase(xs.expand(2, -1, -1, -1).contiguous().cuda(), xd[:2].cuda())
+    with torch.no_grad():
+        full, _ = gbase(xs.expand(2, -1, -1, -1).contiguous().cuda(), xd[:2].cuda())
     assert (full - a[:2]).abs().max().item() <= 1e-4
 
 
