@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPB200_ABI_VERSION 3
+#define MPB200_ABI_VERSION 4
 
 /* activation codes shared by several entry points */
 enum { MP_ACT_NONE = 0, MP_ACT_RELU = 1, MP_ACT_RELU_TANH = 2, MP_ACT_SIGMOID = 3 };
@@ -126,6 +126,16 @@ typedef struct mp_conv_desc {
    * independently of `prec` (0 = the native format of `prec`), so format changes ride on a convolution's epilogue. */
   int out_fmt, res_fmt;
   float corr_scale;
+  /* Per-tensor power-of-two scale of an F16_Q8 byte plane (0 = 1): the plane holds [e4m3(x * s)] [e4m3((x - fp16 x) *
+   * 2048 * s)], so activations far from 1 in magnitude still use e4m3's 2^-6 .. 448 normal range (|x * s| > 448 would
+   * saturate the cross term, |x * s| < 2^-9 would drop it).  out_q8_scale: the scale this launch writes out_lo with;
+   * res_q8_scale: the scale res_lo was written with.  The scale of the INPUT plane is folded into corr_scale by the
+   * caller: corr_scale = 1 / (2048 * sw * s_in). */
+  float out_q8_scale, res_q8_scale;
+  /* fp16 weight planes (MP_PREC_F16X2, MP_PREC_F16_Q8) may be packed from w * sw, sw a power of two that moves the
+   * largest weight into [1, 2) -- so small weights do not sink into fp16's subnormal range; the kernel multiplies the
+   * finished accumulator by acc_scale = 1 / sw before bias / residual / activation (0 = 1). */
+  float acc_scale;
 } mp_conv_desc;
 
 enum { MP_PREC_SPLIT_BF16 = 0, MP_PREC_F16X2 = 1, MP_PREC_F16_Q8 = 2 };

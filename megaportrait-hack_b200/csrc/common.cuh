@@ -61,15 +61,17 @@ __device__ __forceinline__ float mp_e4m3_to_float(uint8_t v) {
   return __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)v, __NV_E4M3)));
 }
 // 8 consecutive channels -> (fp16 x 8, e4m3(x) x 8, e4m3((x - fp16 x) * 2048) x 8)
-__device__ __forceinline__ void mp_hq_pack8(const float* x, f16x8& h, uint2& a8, uint2& al8) {
-  float l[8];
+// `s` = the per-tensor power-of-two scale of the byte plane (exact: it only shifts exponents)
+__device__ __forceinline__ void mp_hq_pack8(const float* x, f16x8& h, uint2& a8, uint2& al8, float s = 1.f) {
+  float l[8], xs[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     h.v[i] = mp_to_f16(x[i]);
-    l[i] = (x[i] - __half2float(h.v[i])) * 2048.f;
+    l[i] = (x[i] - __half2float(h.v[i])) * (2048.f * s);
+    xs[i] = x[i] * s;
   }
-  a8.x = (uint32_t)mp_e4m3x2(x[0], x[1]) | ((uint32_t)mp_e4m3x2(x[2], x[3]) << 16);
-  a8.y = (uint32_t)mp_e4m3x2(x[4], x[5]) | ((uint32_t)mp_e4m3x2(x[6], x[7]) << 16);
+  a8.x = (uint32_t)mp_e4m3x2(xs[0], xs[1]) | ((uint32_t)mp_e4m3x2(xs[2], xs[3]) << 16);
+  a8.y = (uint32_t)mp_e4m3x2(xs[4], xs[5]) | ((uint32_t)mp_e4m3x2(xs[6], xs[7]) << 16);
   al8.x = (uint32_t)mp_e4m3x2(l[0], l[1]) | ((uint32_t)mp_e4m3x2(l[2], l[3]) << 16);
   al8.y = (uint32_t)mp_e4m3x2(l[4], l[5]) | ((uint32_t)mp_e4m3x2(l[6], l[7]) << 16);
 }

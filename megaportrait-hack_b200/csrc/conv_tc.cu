@@ -82,6 +82,8 @@ struct TcParams {
   int stride2, in2_c_off;
   int out_fmt, res_fmt;       // effective MP_FMT_* of (out_hi, out_lo) and (res_hi, res_lo)
   int b_merged;               // 1: map_b_hi is a 3-D map (K, Cout_pad, plane) and one TMA load fetches [Bh | Bl]
+  float acc_scale;            // fp16 weight planes were packed from w / acc_scale (a power of two)
+  float out_q8_scale, res_q8_inv;   // F16_Q8 byte planes: scale written / 1 / (2048 * scale of the residual plane)
   unsigned int* sched;        // dynamic tile scheduler: {next-tile counter, finished-CTA counter}, or NULL = static walk
 };
 
@@ -347,7 +349,7 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
         float v2[16];
         tmem_ld16(tmem_acc + (uint32_t)(p.BN + c0 + hc), v2);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(v2[i], p.lo_scale, v[i]);
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v2[i], p.lo_scale, v[i]) * p.acc_scale;
       }
       if (!row_valid) {
 #pragma unroll
@@ -382,7 +384,7 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
                                                               2 * (obase - p.out_c_off) + mp_q8_off(ch) + 64);
             const uint8_t* b8 = reinterpret_cast<const uint8_t*>(&raw);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaf(mp_e4m3_to_float(b8[i]), 1.0f / 2048.0f, v[i]);
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(mp_e4m3_to_float(b8[i]), p.res_q8_inv, v[i]);
           }
         } else if (p.res_hi) {
 #pragma unroll
@@ -447,7 +449,7 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, float* epi, lo
           const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
           f16x8 h;
           uint2 a8, al8;
-          mp_hq_pack8(xs, h, a8, al8);
+          mp_hq_pack8(xs, h, a8, al8, p.out_q8_scale);
           *reinterpret_cast<f16x8*>(oh + row_off[row] + co0 + c8) = h;
           uint8_t* q = oq + 2 * (row_off[row] - p.out_c_off) + mp_q8_off(p.out_c_off + co0 + c8);
           *reinterpret_cast<uint2*>(q) = a8;
@@ -560,7 +562,7 @@ __device__ __forceinline__ void epilogue_stage_h(const TcParams& p, uint32_t sta
     tmem_ld32(tmem_acc + (uint32_t)c0, v);
     tmem_ld32(tmem_acc + (uint32_t)(p.BN + c0), v2);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaf(v2[i], p.lo_scale, v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(v2[i], p.lo_scale, v[i]) * p.acc_scale;
     const int co0 = n0 + c0;
     if (bias_vec) {
 #pragma unroll
@@ -1447,6 +1449,9 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.prec = d->prec;
   p.a_planes = f16x2 ? 1u : 2u;
   p.lo_scale = f16x2 ? 1.0f / 2048.0f : f16q8 ? d->corr_scale : 1.0f;
+  p.acc_scale = ((f16x2 || f16q8) && d->acc_scale > 0.f) ? d->acc_scale : 1.0f;
+  p.out_q8_scale = d->out_q8_scale > 0.f ? d->out_q8_scale : 1.0f;
+  p.res_q8_inv = 1.0f / (2048.0f * (d->res_q8_scale > 0.f ? d->res_q8_scale : 1.0f));
   const uint32_t ap = p.a_planes;
   // fused 1x1 shortcut (second source appended to K)
   if (d->Cin2 < 0 || (d->Cin2 > 0 && (!d->in2_hi || (!f16x2 && !d->in2_lo)))) return fail("bad second source");

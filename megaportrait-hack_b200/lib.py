@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID = 0, 1, 2, 3
 PREC_SPLIT_BF16, PREC_F16X2, PREC_F16_Q8 = 0, 1, 2   # mp_conv_desc.prec
 FMT_NATIVE, FMT_SPLIT_BF16, FMT_F16, FMT_F16_Q8 = 0, 1, 2, 3   # mp_conv_desc.out_fmt / res_fmt
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def sources():
@@ -64,6 +64,7 @@ class ConvDesc(Structure):
         ("Cin2", c_int), ("in2_C", c_int), ("in2_c_off", c_int), ("stride2", c_int),
         ("in2_hi", c_void_p), ("in2_lo", c_void_p),
         ("out_fmt", c_int), ("res_fmt", c_int), ("corr_scale", c_float),
+        ("out_q8_scale", c_float), ("res_q8_scale", c_float), ("acc_scale", c_float),
     ]
 
 

@@ -89,6 +89,11 @@ class _Packed:
         return super()._load_from_state_dict(*a, **k)
 
 
+def _capturing(a) -> bool:
+    """True while the current CUDA stream is being captured into a graph (host syncs are illegal there)."""
+    return a.device.type == "cuda" and torch.cuda.is_current_stream_capturing()
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().float().contiguous()
 
@@ -413,12 +418,15 @@ class ResBlock2D(nn.Module, _Packed):
         w2, b2 = ops.fold_bn(self.conv2.weight.detach(), self.conv2.bias.detach(), self._bn(self.bn2), self.bn2.eps)
         return ops.pack_conv(w1, b1, dev, prec=prec), ops.pack_conv(w2, b2, dev, shortcut=sc, prec=prec)
 
-    def _forward_cl(self, x: Act, f32: bool = False, split: bool = True, stats_groups: int = 0, hq_out: bool = False):
-        """x: split (or fp16 + FP8 planes for a `_mp_q8` block).  Returns (Act, stats or None)."""
+    def _forward_cl(self, x: Act, f32: bool = False, split: bool = True, stats_groups: int = 0, hq_out: bool = False,
+                    q8_scales: Tuple[float, float] = (1.0, 1.0)):
+        """x: split (or fp16 + FP8 planes for a `_mp_q8` block).  Returns (Act, stats or None).  `q8_scales`: the
+        per-tensor scales of the FP8 byte planes this block writes (its inner activation, its output)."""
         P = self._plan()
         if P["q8"] and x.q8 is not None:
-            t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, hq=True)
-            return ops.conv(t, P["c2"], res=x, act=ACT_RELU, f32=f32, split=split and not hq_out, hq=hq_out)
+            t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, hq=True, out_q8_scale=q8_scales[0])
+            return ops.conv(t, P["c2"], res=x, act=ACT_RELU, f32=f32, split=split and not hq_out, hq=hq_out,
+                            out_q8_scale=q8_scales[1])
         if P["q8"]:          # a G2d block called on its own with split planes: three-pass packs, built on first use
             if "c1_split" not in P:
                 P["c1_split"], P["c2_split"] = self._pack_pair(ops.PREC_SPLIT_BF16)
@@ -474,13 +482,59 @@ class G2d(nn.Module, _Packed):
                 "head_w": self.final_conv[2].weight.detach().float().cpu().contiguous(),
                 "head_b": self.final_conv[2].bias.detach().float().cpu().contiguous()}
 
+    # fp16 + FP8 cross-term mode: safe range of a tensor's largest magnitude.  Above Q8_AMAX_LIMIT the fp16 main plane
+    # itself is close to overflow (65504): the chain then runs the three-pass split-bf16 plans instead.
+    Q8_AMAX_LIMIT = 16384.0
+
+    def _res_chain(self, h: Act, scales, collect=None) -> Act:
+        """The 8 identity res-blocks on F16_Q8 planes; `scales[1 + 2 i]`, `scales[2 + 2 i]` = byte-plane scales of block
+        i's inner activation and output.  `collect` (calibration) receives every F16_Q8 tensor of the chain."""
+        n = len(self.res_blocks)
+        for i, blk in enumerate(self.res_blocks):
+            P = blk._plan()
+            t, _ = ops.conv(h, P["c1"], act=ACT_RELU, f32=False, hq=True, out_q8_scale=scales[1 + 2 * i])
+            last = i + 1 == n
+            h2, _ = ops.conv(t, P["c2"], res=h, act=ACT_RELU, f32=False, split=last, hq=not last,
+                             out_q8_scale=scales[2 + 2 * i])
+            if collect is not None:
+                collect.append(t)
+                if not last:
+                    collect.append(h2)
+            h = h2
+        return h
+
+    def _q8_calibrate(self, x: Act, P) -> None:
+        """One pass of the res-block chain with unit scales to measure every F16_Q8 tensor's largest magnitude, then
+        per-tensor power-of-two scales for the FP8 byte planes (ops.q8_scale_for); tensors near the fp16 range switch
+        the chain to the split-bf16 plans.  Runs once per plan, outside CUDA-graph capture (one host sync)."""
+        ones = [1.0] * (1 + 2 * len(self.res_blocks))
+        h, _ = ops.conv(x, P["in"], f32=False, split=False, hq=True)
+        seen = [h]
+        self._res_chain(h, ones, collect=seen)
+        amax = torch.stack([t.h16.float().abs().amax() for t in seen]).cpu().tolist()
+        ok = all(a == a and a < self.Q8_AMAX_LIMIT for a in amax)       # NaN / inf / near-overflow -> fall back
+        P["q8_amax"] = amax
+        # (the last block writes split-bf16 planes: its output has no byte plane, the trailing 1.0 is never used)
+        P["q8_scales"] = [ops.q8_scale_for(a) for a in amax] + [1.0] if ok else None
+        P["q8_ok"] = ok
+
     def _forward_cl(self, x: Act) -> torch.Tensor:
         """x: split channels-last [N,1,64,64,96] -> RGB NCHW fp32 [N,3,512,512]."""
         P = self._plan()
         q8 = _Q8_ENABLED and all(blk._plan()["q8"] for blk in self.res_blocks)
-        h, _ = ops.conv(x, P["in"], f32=False, split=not q8, hq=q8)
-        for i, blk in enumerate(self.res_blocks):
-            h, _ = blk._forward_cl(h, hq_out=q8 and i + 1 < len(self.res_blocks))
+        scales = None
+        if q8:
+            if "q8_ok" not in P and not _capturing(x):
+                self._q8_calibrate(x, P)
+            q8 = P.get("q8_ok", True)
+            scales = P.get("q8_scales") or [1.0] * (1 + 2 * len(self.res_blocks))
+        if q8:
+            h, _ = ops.conv(x, P["in"], f32=False, split=False, hq=True, out_q8_scale=scales[0])
+            h = self._res_chain(h, scales)
+        else:
+            h, _ = ops.conv(x, P["in"], f32=False, split=True)
+            for blk in self.res_blocks:
+                h, _ = blk._forward_cl(h)
         st = None
         for i, up in enumerate((self.upsample1, self.upsample2, self.upsample3)):
             u = ops.upsample2x_linear(h, 1, f32=False, split=True)

@@ -94,12 +94,14 @@ def _chk_cuda(t: torch.Tensor, dtype, what: str) -> None:
 
 class Act:
     """Channels-last activation [N, D, H, W, C]: `f32` and/or the split pair (`hi`, `lo`) and/or one fp16 plane `h16`
-    (optionally with the FP8 byte plane `q8` [N, D, H, W, 2C] of the "F16_Q8" operand format, include/mpb200.h)."""
-    __slots__ = ("f32", "hi", "lo", "h16", "q8", "shape")
+    (optionally with the FP8 byte plane `q8` [N, D, H, W, 2C] of the "F16_Q8" operand format, include/mpb200.h, written
+    with the per-tensor power-of-two scale `q8_scale`)."""
+    __slots__ = ("f32", "hi", "lo", "h16", "q8", "shape", "q8_scale")
 
-    def __init__(self, shape, f32=None, hi=None, lo=None, h16=None, q8=None):
+    def __init__(self, shape, f32=None, hi=None, lo=None, h16=None, q8=None, q8_scale=1.0):
         self.shape = tuple(int(s) for s in shape)
         self.f32, self.hi, self.lo, self.h16, self.q8 = f32, hi, lo, h16, q8
+        self.q8_scale = float(q8_scale)
 
     @property
     def N(self): return self.shape[0]
@@ -273,11 +275,13 @@ def group_norm_act(a: Act, G: int, stats: Optional[torch.Tensor] = None, gamma=N
 # ----------------------------------------------------------------------------------------------------- conv
 class PackedConv:
     """Weights of one convolution in kernel format: split-bf16 [Cout_pad, taps*Cin] (tap-major, cin-minor) + bias."""
-    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k", "prec", "Cin2", "corr_scale")
+    __slots__ = ("w_hi", "w_lo", "bias", "Cin", "Cout", "Cout_pad", "k", "prec", "Cin2", "corr_scale", "acc_scale")
 
-    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k, prec=PREC_SPLIT_BF16, Cin2=0, corr_scale=0.0):
+    def __init__(self, w_hi, w_lo, bias, Cin, Cout, Cout_pad, k, prec=PREC_SPLIT_BF16, Cin2=0, corr_scale=0.0,
+                 acc_scale=1.0):
         self.w_hi, self.w_lo, self.bias = w_hi, w_lo, bias
-        self.corr_scale = corr_scale   # PREC_F16_Q8: weight of the FP8 cross-term accumulator, 1 / (2048 * sw)
+        self.corr_scale = corr_scale   # PREC_F16_Q8: weight of the FP8 cross-term accumulator, 1 / 2048 (per unit input scale)
+        self.acc_scale = acc_scale     # fp16 planes hold w / acc_scale (power of two): the kernel rescales the accumulator
         self.Cin, self.Cout, self.Cout_pad, self.k, self.prec = Cin, Cout, Cout_pad, tuple(k), prec
         self.Cin2 = Cin2          # > 0: rows are [taps*Cin | Cin2]: a 1x1 shortcut over a second source is fused in
 
@@ -307,11 +311,20 @@ def e4m3(x: torch.Tensor) -> torch.Tensor:
     return x.float().clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
 
 
-def q8_planes(x: torch.Tensor) -> torch.Tensor:
-    """fp32 channels-last [..., C] (C % 64 == 0) -> the byte plane [..., 2C] of the F16_Q8 operand format."""
+def q8_scale_for(amax: float, target: float = 96.0) -> float:
+    """Power-of-two scale that puts a tensor's largest magnitude near `target` (e4m3 keeps 3 mantissa bits from 2^-6 up
+    to 448): ~4.6x head-room above the calibrated maximum, 12 binades below it."""
+    if not (amax > 0.0) or not math.isfinite(amax):
+        return 1.0
+    return 2.0 ** round(math.log2(target / amax))
+
+
+def q8_planes(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """fp32 channels-last [..., C] (C % 64 == 0) -> the byte plane [..., 2C] of the F16_Q8 operand format, written with
+    the per-tensor power-of-two `scale` (what the convolution epilogue does with `out_q8_scale`)."""
     h = x.clamp(-65504.0, 65504.0).to(torch.float16)
-    a8 = e4m3(x).view(torch.uint8)
-    al8 = e4m3((x - h.float()) * F16_LO_SCALE).view(torch.uint8)
+    a8 = e4m3(x * scale).view(torch.uint8)
+    al8 = e4m3((x - h.float()) * (F16_LO_SCALE * scale)).view(torch.uint8)
     lead = x.shape[:-1]
     return torch.stack((a8.reshape(*lead, -1, 64), al8.reshape(*lead, -1, 64)), -2).reshape(*lead, -1)
 
@@ -344,18 +357,23 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, c
     Cout_pad = (Cout + 15) // 16 * 16
     if Cout_pad != Cout:
         wk = torch.cat([wk, torch.zeros(Cout_pad - Cout, wk.shape[1], device=device)], 0)
-    corr_scale = 0.0
+    corr_scale, acc_scale = 0.0, 1.0
+    if prec in (PREC_F16_Q8, PREC_F16X2):
+        # fp16 planes are formed from w * sw, sw the power of two that puts the largest weight into [1, 2): weights of
+        # any magnitude keep fp16's full 11 bits (no subnormals); the kernel multiplies the accumulator by 1 / sw
+        amax = float(wk.abs().max())
+        sw = 2.0 ** (-math.floor(math.log2(amax))) if (amax > 0 and math.isfinite(amax)) else 1.0
+        wk = wk * sw
+        acc_scale = 1.0 / sw
     if prec == PREC_F16_Q8:
-        # fp16 main plane + byte plane: per 64-wide K chunk [e4m3(wl * 2048 * sw) x 64 | e4m3(w * sw) x 64]
+        # fp16 main plane + byte plane: per 64-wide K chunk [e4m3(wl * 2048) x 64 | e4m3(w) x 64]
         if wk.shape[1] % 64:
             raise RuntimeError("pack_conv: PREC_F16_Q8 needs input channels in multiples of 64")
         hi = wk.to(torch.float16)
-        amax = float(wk.abs().max())
-        sw = 2.0 ** (-math.floor(math.log2(amax))) if amax > 0 else 1.0        # max |w * sw| in [1, 2)
-        wl8 = e4m3((wk - hi.float()) * (F16_LO_SCALE * sw)).view(torch.uint8)
-        w8 = e4m3(wk * sw).view(torch.uint8)
+        wl8 = e4m3((wk - hi.float()) * F16_LO_SCALE).view(torch.uint8)
+        w8 = e4m3(wk).view(torch.uint8)
         q = torch.stack((wl8.view(Cout_pad, -1, 64), w8.view(Cout_pad, -1, 64)), 2).reshape(Cout_pad, -1)
-        corr_scale = 1.0 / (F16_LO_SCALE * sw)
+        corr_scale = 1.0 / F16_LO_SCALE
         hi, lo = hi.contiguous().view(torch.uint8), q.contiguous()            # both [Cout_pad, 2K] bytes
     elif prec == PREC_F16X2:
         hi = wk.to(torch.float16)
@@ -365,7 +383,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None, c
         lo = (wk - hi.float()).to(torch.bfloat16)
     b = None if bias is None else bias.detach().to(device=device, dtype=torch.float32).contiguous()
     planes = torch.stack((hi, lo)).contiguous()      # one allocation: the kernel then fetches [hi | lo] with ONE TMA load
-    return PackedConv(planes[0], planes[1], b, Cin, Cout, Cout_pad, (kd, kh, kw), prec, Cin2, corr_scale)
+    return PackedConv(planes[0], planes[1], b, Cin, Cout, Cout_pad, (kd, kh, kw), prec, Cin2, corr_scale, acc_scale)
 
 
 def pack_stem3x3_f16(weight: torch.Tensor, bias: Optional[torch.Tensor], device=None) -> PackedConv:
@@ -379,7 +397,7 @@ def pack_stem3x3_f16(weight: torch.Tensor, bias: Optional[torch.Tensor], device=
 
 
 def _conv_q8(a: Act, pw: PackedConv, res: Optional[Act], act: int, f32: bool, split: bool, stats_groups: int,
-             hq: bool) -> Tuple[Act, Optional[torch.Tensor]]:
+             hq: bool, out_q8_scale: float = 1.0) -> Tuple[Act, Optional[torch.Tensor]]:
     """Convolutions around the F16_Q8 operand format (fp16 plane + FP8 byte plane): `pw.prec == PREC_F16_Q8` consumes it
     (fp16 main product + FP8 cross terms), `hq=True` produces it -- from either kind of convolution, so the format change
     rides on an epilogue.  Stride 1, no channel windows; the residual may be fp32, split or F16_Q8."""
@@ -392,9 +410,13 @@ def _conv_q8(a: Act, pw: PackedConv, res: Optional[Act], act: int, f32: bool, sp
         raise RuntimeError("conv: unsupported F16_Q8 configuration")
     N, D, H, W, C = a.shape
     out = _alloc((N, D, H, W, pw.Cout), a.device, f32, split, hq, hq)
+    out.q8_scale = float(out_q8_scale) if hq else 1.0
     stats = new_stats(N, stats_groups, a.device) if stats_groups else None
     d = ConvDesc()
-    d.w_hi, d.w_lo, d.bias, d.prec, d.corr_scale = _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias), pw.prec, pw.corr_scale
+    d.w_hi, d.w_lo, d.bias, d.prec = _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias), pw.prec
+    d.corr_scale = pw.corr_scale / a.q8_scale if q8_in else 0.0      # the input plane's scale leaves with the weight's
+    d.acc_scale = pw.acc_scale
+    d.out_q8_scale = out.q8_scale
     d.in_hi, d.in_lo = (_p(a.h16), _p(a.q8)) if q8_in else (_p(a.hi), _p(a.lo))
     if res is not None:
         if res.shape != out.shape:
@@ -402,7 +424,7 @@ def _conv_q8(a: Act, pw: PackedConv, res: Optional[Act], act: int, f32: bool, sp
         if res.f32 is not None:
             d.res_f32 = _p(res.f32)
         elif res.q8 is not None:
-            d.res_hi, d.res_lo, d.res_fmt = _p(res.h16), _p(res.q8), FMT_F16_Q8
+            d.res_hi, d.res_lo, d.res_fmt, d.res_q8_scale = _p(res.h16), _p(res.q8), FMT_F16_Q8, res.q8_scale
         else:
             d.res_hi, d.res_lo, d.res_fmt = _p(res.hi), _p(res.lo), FMT_SPLIT_BF16
     d.out_f32, d.stats = _p(out.f32), _p(stats)
@@ -435,9 +457,11 @@ def set_conv_mode(mode: str) -> None:
 def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE, f32: bool = True,
          split: bool = False, stats_groups: int = 0, mode: Optional[str] = None, stride: int = 1, in_c_off: int = 0,
          out: Optional[Act] = None, out_c_off: int = 0, h16: bool = False, src2: Optional[Act] = None,
-         stride2: int = 1, in2_c_off: int = 0, hq: bool = False) -> Tuple[Act, Optional[torch.Tensor]]:
+         stride2: int = 1, in2_c_off: int = 0, hq: bool = False,
+         out_q8_scale: float = 1.0) -> Tuple[Act, Optional[torch.Tensor]]:
     """act(conv(a) + bias + res) -> (Act, GroupNorm statistics of the written values or None).
 
+    `hq=True` writes the F16_Q8 plane pair (fp16 + FP8 bytes, the latter with the per-tensor power-of-two `out_q8_scale`).
     `src2` feeds the fused 1x1 shortcut of a `pack_conv(..., shortcut=...)` plan: an activation in the same operand
     format whose grid is `stride2` times the output grid.
     `pw.prec == PREC_F16X2` runs the two-pass fp16 kernel: `a` (and `res`, unless it is fp32) must carry an fp16 plane
@@ -446,7 +470,7 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     `stride` (1|2) applies to H and W.  `in_c_off` selects the window [in_c_off, in_c_off + pw.Cin) of a's channels;
     `out` / `out_c_off` write into the channel window of an existing activation (grouped convolutions)."""
     if pw.prec == PREC_F16_Q8 or hq:
-        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq)
+        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale)
     half = pw.prec == PREC_F16X2
     if half:
         if a.h16 is None:
@@ -470,7 +494,7 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     late_stats = bool(stats_groups) and (D * Ho * Wo < 128) and (out.f32 is not None)
     stats = new_stats(N, stats_groups, a.device) if (stats_groups and not late_stats) else None
     d = ConvDesc()
-    d.w_hi, d.w_lo, d.bias, d.prec = _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias), pw.prec
+    d.w_hi, d.w_lo, d.bias, d.prec, d.acc_scale = _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias), pw.prec, pw.acc_scale
     d.in_hi, d.in_lo = (_p(a.h16), None) if half else (_p(a.hi), _p(a.lo))
     if res is not None:
         if res.shape != out.shape:

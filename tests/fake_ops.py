@@ -39,8 +39,8 @@ def _val(a: Act) -> torch.Tensor:
         return a.f32
     if a.hi is not None:
         return a.hi.float() + a.lo.float()
-    if a.q8 is not None:          # F16_Q8: fp16 plane + low part / 2048
-        return a.h16.float() + _q8_decode(a.q8)[1] / ops.F16_LO_SCALE
+    if a.q8 is not None:          # F16_Q8: fp16 plane + low part / (2048 * per-tensor scale)
+        return a.h16.float() + _q8_decode(a.q8)[1] / (ops.F16_LO_SCALE * a.q8_scale)
     return a.h16.float()
 
 
@@ -155,7 +155,7 @@ def affine_act(a, ab, res=None, act=ops.ACT_NONE, f32=False, split=True):
     return _mk(_act(v, act), f32, split)
 
 
-def _conv_q8(a, pw, res, act, f32, split, stats_groups, hq):
+def _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale=1.0):
     """fp16 main product + FP8 cross terms (PREC_F16_Q8) and / or F16_Q8 output planes, as the kernel computes them."""
     kd, kh, kw = pw.k
     pad = (kd // 2, kh // 2, kw // 2)
@@ -164,9 +164,11 @@ def _conv_q8(a, pw, res, act, f32, split, stats_groups, hq):
         wh = pw.w_hi.view(torch.float16).float()
         wl8, w8 = _q8_decode(pw.w_lo)
         a8, al8 = _q8_decode(a.q8)
-        y = F.conv3d(_to_ncdhw(a.h16.float()), shape_w(wh), pw.bias, padding=pad)
+        y = F.conv3d(_to_ncdhw(a.h16.float()), shape_w(wh), None, padding=pad)
         corr = F.conv3d(_to_ncdhw(a8), shape_w(wl8), None, padding=pad) + F.conv3d(_to_ncdhw(al8), shape_w(w8), None, padding=pad)
-        y = y + corr * pw.corr_scale
+        y = (y + corr * (pw.corr_scale / a.q8_scale)) * pw.acc_scale
+        if pw.bias is not None:
+            y = y + pw.bias.view(1, -1, 1, 1, 1)
     else:
         ensure_split(a)
         y = F.conv3d(_to_ncdhw(a.hi.float() + a.lo.float()), shape_w(pw.w_hi.float() + pw.w_lo.float()), pw.bias, padding=pad)
@@ -177,20 +179,21 @@ def _conv_q8(a, pw, res, act, f32, split, stats_groups, hq):
     st = _stats_of(v, stats_groups) if stats_groups else None
     out = _mk(v, f32, split, hq)
     if hq:
-        out.q8 = ops.q8_planes(v.contiguous())
+        out.q8 = ops.q8_planes(v.contiguous(), out_q8_scale)
+        out.q8_scale = float(out_q8_scale)
     return out, st
 
 
 def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=0, mode=None, stride=1, in_c_off=0,
-         out=None, out_c_off=0, h16=False, src2=None, stride2=1, in2_c_off=0, hq=False):
+         out=None, out_c_off=0, h16=False, src2=None, stride2=1, in2_c_off=0, hq=False, out_q8_scale=1.0):
     if pw.prec == ops.PREC_F16_Q8 or hq:
-        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq)
+        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale)
     half = pw.prec == ops.PREC_F16X2
     kd, kh, kw = pw.k
     if half:     # two-pass fp16: one fp16 activation plane, fp16 hi + scaled fp16 lo weights
         assert a.h16 is not None and not split and not stats_groups
         x = _to_ncdhw(a.h16.float())[:, in_c_off:in_c_off + pw.Cin]
-        wf = pw.w_hi.float() + pw.w_lo.float() / ops.F16_LO_SCALE
+        wf = (pw.w_hi.float() + pw.w_lo.float() / ops.F16_LO_SCALE) * pw.acc_scale
     else:
         assert not h16
         ensure_split(a)

@@ -82,5 +82,6 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(so, name), f"libmpb200.so does not export {name}"
     assert set(lib.EXPORTS) == declared
-    assert lib.load().mp_abi_version() == lib.ABI_VERSION == 3
-    assert ctypes.sizeof(lib.ConvDesc) == 12 * 8 + 22 * 4 + 2 * 8 + 4 * 4   # 12 pointers, 22 ints, 2 pointers, 2 ints + float (+ pad)
+    assert lib.load().mp_abi_version() == lib.ABI_VERSION == 4
+    # 12 pointers, 22 ints, 2 pointers, 2 ints + 3 floats (+ pad to 8)
+    assert ctypes.sizeof(lib.ConvDesc) == 12 * 8 + 22 * 4 + 2 * 8 + 6 * 4

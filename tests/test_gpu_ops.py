@@ -506,8 +506,9 @@ def test_conv_f16x2(ops, case):
     a = _h16_act(ops, x)
     pw = ops.pack_conv(w, b, DEV, prec=ops.PREC_F16X2)
     assert pw.w_hi.dtype == torch.float16 and pw.prec == ops.PREC_F16X2
-    # the kernel's exact operands: fp16(x) and w_hi + w_lo / 2048 (within 2^-21 of w)
-    wq = (pw.w_hi.float() + pw.w_lo.float() / ops.F16_LO_SCALE).cpu()[:Cout].view(Cout, 1, k, k, Cin).permute(0, 4, 1, 2, 3)
+    # the kernel's exact operands: fp16(x) and (w_hi + w_lo / 2048) * acc_scale (within 2^-21 of w; the planes hold
+    # w / acc_scale, acc_scale a power of two)
+    wq = ((pw.w_hi.float() + pw.w_lo.float() / ops.F16_LO_SCALE) * pw.acc_scale).cpu()[:Cout].view(Cout, 1, k, k, Cin).permute(0, 4, 1, 2, 3)
     assert (wq.squeeze(2) - w).abs().max().item() <= w.abs().max().item() * 2.0 ** -20
     xq = _f16(x).float()[:, in_off:in_off + Cin]
     ref = F.conv3d(xq, wq.contiguous(), b, stride=(1, stride, stride), padding=(0, k // 2, k // 2))
@@ -699,8 +700,9 @@ def test_conv_f16_q8(ops, Cin, Cout, H, W, k):
     a8, al8 = _q8_decode(a.q8.cpu())
     shp = lambda m: m[:Cout].reshape(Cout, k, k, Cin).permute(0, 3, 1, 2).contiguous()
     ncl = lambda t: t.squeeze(1).permute(0, 3, 1, 2).contiguous()
-    y = F.conv2d(ncl(a.h16.float().cpu()), shp(wh), b, padding=k // 2)
+    y = F.conv2d(ncl(a.h16.float().cpu()), shp(wh), None, padding=k // 2)
     y = y + (F.conv2d(ncl(a8), shp(wl8), None, padding=k // 2) + F.conv2d(ncl(al8), shp(w8), None, padding=k // 2)) * pw.corr_scale
+    y = y * pw.acc_scale + b.view(1, -1, 1, 1)
     rv = res.h16.float().cpu() + _q8_decode(res.q8.cpu())[1] / 2048.0
     ref = F.relu(y + ncl(rv))
     got = ncl(out.f32.cpu())
@@ -712,6 +714,93 @@ def test_conv_f16_q8(ops, Cin, Cout, H, W, k):
     # and the whole thing is an fp32-grade convolution: cross terms at e4m3 precision leave ~2^-16 relative error
     full = F.relu(F.conv2d(x.squeeze(2), w, b, padding=k // 2) + r.squeeze(2))
     assert (got - full).abs().max().item() / scale < 1e-4
+
+
+def _q8_conv_err(ops, x, w, b, k, scale_in):
+    """fp16 + FP8 cross-term conv of x (planes written with `scale_in`) against fp32; error relative to the output abs-max."""
+    xcl = x.permute(0, 2, 3, 4, 1).contiguous()
+    a = ops.Act(tuple(xcl.shape), h16=_f16(xcl).to(DEV), q8=ops.q8_planes(xcl, scale_in).to(DEV), q8_scale=scale_in)
+    pw = ops.pack_conv(w, b, DEV, prec=ops.PREC_F16_Q8)
+    out, _ = ops.conv(a, pw, act=ops.ACT_NONE, f32=True)
+    ref = F.conv2d(x.squeeze(2).double(), w.double(), b.double(), padding=k // 2).float()
+    got = out.f32.cpu().squeeze(1).permute(0, 3, 1, 2)
+    return (got - ref).abs().max().item() / ref.abs().max().item()
+
+
+@pytest.mark.parametrize("ax", [-10, 0, 10], ids=lambda e: f"x2^{e}")
+@pytest.mark.parametrize("aw", [-10, 0, 10], ids=lambda e: f"w2^{e}")
+def test_conv_f16_q8_dynamic_range(ops, ax, aw):
+    """activations and weights scaled by 2^+-10.  The FP8 byte plane carries a per-tensor
+    power-of-two scale (ops.q8_scale_for: largest magnitude -> ~96, inside e4m3's 2^-6 .. 448 normal range) and the fp16
+    weight planes are packed from w * sw, so the convolution stays fp32-grade (<= 1e-4 of the output abs-max) at every
+    combination; with the unscaled byte plane the large-activation cases lose the cross term (x8 saturates at 448)."""
+    Cin, Cout, H, W, k = 256, 128, 16, 16, 3
+    x = rnd(2, Cin, 1, H, W, seed=101) * 1.3 * 2.0 ** ax
+    w = rnd(Cout, Cin, k, k, seed=102) / math.sqrt(Cin * k * k) * 2.0 ** aw
+    b = rnd(Cout, seed=103) * 0.1 * 2.0 ** (ax + aw)
+    s = ops.q8_scale_for(x.abs().max().item())
+    assert 32.0 <= x.abs().max().item() * s <= 256.0
+    err = _q8_conv_err(ops, x, w, b, k, s)
+    err_unscaled = _q8_conv_err(ops, x, w, b, k, 1.0)
+    print(f"x*2^{ax} w*2^{aw}: scale {s:g}: rel err {err:.2e} (unscaled byte plane: {err_unscaled:.2e})")
+    assert err <= 1e-4
+    if ax == 10:
+        assert err_unscaled > 2 * err        # e4m3(x) saturated: the scale is what keeps the cross term
+
+
+def test_conv_f16_q8_outlier_channels(ops):
+    """A few channels 200x larger than the rest (what trained BatchNorm-free trunks produce): the per-tensor scale follows
+    the outliers, the small channels drop to e4m3's low binades (still >= 2^-9 after scaling) -- result stays <= 1e-4."""
+    Cin, Cout, H, W, k = 256, 128, 16, 16, 3
+    x = rnd(2, Cin, 1, H, W, seed=111)
+    x[:, ::37] *= 200.0
+    w = rnd(Cout, Cin, k, k, seed=112) / math.sqrt(Cin * k * k)
+    b = rnd(Cout, seed=113) * 0.1
+    err = _q8_conv_err(ops, x, w, b, k, ops.q8_scale_for(x.abs().max().item()))
+    print("outlier channels: rel err", err)
+    assert err <= 1e-4
+
+
+@pytest.mark.parametrize("aw", [-10, 0, 10], ids=lambda e: f"w2^{e}")
+@pytest.mark.parametrize("ax", [-4, 0, 8], ids=lambda e: f"x2^{e}")
+def test_conv_f16x2_dynamic_range(ops, ax, aw):
+    """MP_PREC_F16X2 (motion-encoder trunks): one fp16 activation plane, so the activation range is fp16's (values below
+    2^-14 go subnormal, above 65504 clamp); weights of any magnitude are packed from w * sw.  Against the convolution of
+    the fp16-rounded activations with the exact weights: <= 2e-5."""
+    Cin, Cout, H, W, k = 128, 64, 16, 16, 3
+    x = rnd(2, Cin, 1, H, W, seed=121) * 2.0 ** ax
+    w = rnd(Cout, Cin, k, k, seed=122) / math.sqrt(Cin * k * k) * 2.0 ** aw
+    b = rnd(Cout, seed=123) * 0.1 * 2.0 ** (ax + aw)
+    a = _h16_act(ops, x)
+    out, _ = ops.conv(a, ops.pack_conv(w, b, DEV, prec=ops.PREC_F16X2), f32=True, h16=False, mode="tc")
+    ref = F.conv2d(_f16(x).double().squeeze(2), w.double(), b.double(), padding=k // 2).float()
+    got = out.f32.cpu().squeeze(1).permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    print(f"f16x2 x*2^{ax} w*2^{aw}: rel err {err:.2e}")
+    assert err <= 2e-5
+
+
+def test_g2d_q8_calibration_and_fallback(ops):
+    """G2d picks the byte-plane scales from one calibration pass and falls back to the three-pass split-bf16 plans when a
+    tensor of the res-block chain approaches the fp16 range; both must agree with the CPU oracle."""
+    import gbase_oracle as O
+    from megaportrait_hack_b200 import model, seeded
+    sd = {k[len("G2d."):]: v for k, v in seeded.seeded_state_dict(seed=0).items() if k.startswith("G2d.")}
+    g2d = model.G2d(96).eval()
+    g2d.load_state_dict(sd)
+    g2d = g2d.to(DEV)
+    full = {"G2d." + k: v for k, v in sd.items()}
+    for amp, expect_q8 in ((1.0, True), (64.0, True), (30000.0, False)):
+        p = rnd(2, 96, 64, 64, seed=131) * amp
+        model.invalidate_plans(g2d)
+        with torch.no_grad():
+            got = g2d(p.to(DEV)).cpu()
+            ref = O.g2d(p, full)
+        P = g2d._plan()
+        print(f"amp {amp:g}: q8_ok {P.get('q8_ok')} amax[0] {P['q8_amax'][0]:.3g} scales[:3] {(P.get('q8_scales') or [])[:3]} "
+              f"max-abs {(got - ref).abs().max().item():.2e}")
+        assert P["q8_ok"] is expect_q8
+        assert (got - ref).abs().max().item() <= 1e-3
 
 
 def test_conv_split_in_f16_q8_out_and_back(ops):
