@@ -9,8 +9,14 @@ source volume + descriptor (25.2 MB) when N > 1, then `drivers-per-gpu` driver f
 Emtn, C2D warp generator, fused warp + depth sum, G2d and the image pyramid (BASELINE config 2 at N = 1, config 3's
 per-GPU share at N > 1: weak scaling, 32 driver frames per GPU).  Nothing is cached across steps.
 
+Beside the headline the JSON line carries: `e2e` (pinned host buffers in and out every step), `roofline` + `kernels`
+(CUDA events around every launch of one eager step), `grid_sample` (the op benchmark of SURVEY.md 8d: B in {1, 32} x
+three grids), `parity_vs_n1` (per-frame checksums of every rank against one GPU), `strong_scaling` (BASELINE config 3:
+256 frames over the N GPUs), `config2A` (reference semantics `Gbase.forward(xs.expand(32), xd)`), `config1` (B = 1
+latency) and `cpu_baseline`.
+
 `--impl reference` times the reference algorithm on the host CPU (the oracle port of model.py; the Python reference
-itself does not travel to the GPU box) on a bounded sample of the same workload.
+itself does not travel to the GPU box) on a bounded sample of the same workload and prints the same `config`.
 """
 from __future__ import annotations
 
@@ -167,14 +173,63 @@ def grid_sample_leg(dev, pk, batches=(1, 32), reps=7):
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def cpu_forward_sample(pairs: int, sd, xs, xd):
-    """`Gbase(xs.expand(pairs), xd[:pairs])` with the reference's semantics (everything recomputed per pair)."""
+def workload_config(drivers_per_gpu: int, world: int) -> dict:
+    """The `config` object of BOTH arms (the driver compares them): the workload and nothing that depends on the
+    implementation.  One step = one source frame + `drivers_per_gpu` driver frames per GPU; the source-only half (Eapp,
+    Emtn(source), S2C warp, G3d) is evaluated once per step and shared by the step's driver frames -- SURVEY.md 8d
+    config 2 variant (B); variant (A), everything recomputed per pair, is reported beside it under `config2A` /
+    `per_pair`."""
+    return {"workload": f"Gbase inference, 1 src x {drivers_per_gpu} drv per GPU, 512x512 (BASELINE config "
+                        f"{'2' if world == 1 else '3, weak-scaling share'}); source half evaluated once per step, nothing "
+                        "cached across steps",
+            "drivers_per_gpu": drivers_per_gpu, "global_drivers": drivers_per_gpu * world,
+            "parallelism": f"driver-shard x{world}",
+            "collective": "none" if world == 1 else "1 broadcast of vc2d+es (25.2 MB) per step",
+            "weights": "seeded synthetic (megaportrait_hack_b200/seeded.py, seed 0)",
+            "inputs": "torch.rand, generator seed 1 (SURVEY.md 8d)"}
+
+
+CPU_SAMPLE_DRIVERS = 2
+
+
+def cpu_step_sample(sd, xs, xd):
+    """Bounded sample of one step on the host CPU (oracle = the reference's algorithm): the source half ONCE and the
+    per-driver half for CPU_SAMPLE_DRIVERS frames.  Returns (seconds for the source half, seconds per driver frame)."""
     import torch
     import gbase_oracle as O
+    k = CPU_SAMPLE_DRIVERS
     with torch.no_grad():
         t0 = time.perf_counter()
-        O.gbase_forward(xs.expand(pairs, -1, -1, -1).contiguous(), xd[:pairs].contiguous(), sd)
-        return time.perf_counter() - t0
+        src = O.encode_source(xs, sd)
+        t1 = time.perf_counter()
+        srcN = {kk: (v.expand(k, *v.shape[1:]) if torch.is_tensor(v) else v) for kk, v in src.items()}
+        O.drive(srcN, xd[:k].contiguous(), sd)
+        t2 = time.perf_counter()
+    return t1 - t0, (t2 - t1) / k
+
+
+def cpu_measure(sd, warmup: int, steps: int, drivers_per_step: int):
+    """-> dict: frames/s of the `drivers_per_step`-driver step extrapolated from the bounded samples (the per-driver half is
+    linear in the number of frames: eval mode has no cross-sample coupling), and the reference-semantics per-pair rate."""
+    xs, xd = synthetic_inputs(CPU_SAMPLE_DRIVERS)
+    for _ in range(warmup):
+        cpu_step_sample(sd, xs, xd)
+    ts, td = [], []
+    for _ in range(steps):
+        a, b = cpu_step_sample(sd, xs, xd)
+        ts.append(a); td.append(b)
+    t_src, t_drv = sum(ts) / len(ts), sum(td) / len(td)
+    step_s = t_src + drivers_per_step * t_drv
+    return {"value": drivers_per_step / step_s, "step_s_extrapolated": step_s, "source_half_s": t_src,
+            "per_driver_frame_s": t_drv, "per_pair_frames_per_s": 1.0 / (t_src + t_drv),
+            "sample_s_total": sum(ts) + CPU_SAMPLE_DRIVERS * sum(td)}
+
+
+def cpu_sample_note(drivers_per_step: int, warmup: int, steps: int) -> str:
+    return (f"oracle/gbase_oracle.py (CPU restatement of reference model.py, ATen fp32, all host threads): {warmup} warm-up + "
+            f"{steps} timed samples, each = the source half once + the per-driver half for {CPU_SAMPLE_DRIVERS} frames; "
+            f"frames/s of the {drivers_per_step}-driver step = {drivers_per_step} / (t_source + {drivers_per_step} * "
+            f"t_per_driver_frame)")
 
 
 def run_reference(args):
@@ -186,24 +241,22 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = seeded.seeded_state_dict(seed=0)
-    xs, xd = synthetic_inputs(1)
-    for _ in range(args.warmup):
-        cpu_forward_sample(1, sd, xs, xd)
-    t = 0.0
-    for _ in range(args.steps):
-        t += cpu_forward_sample(1, sd, xs, xd)
-    fps = args.steps / t
+    B = args.drivers_per_gpu
+    m = cpu_measure(sd, args.warmup, args.steps, B)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * m["step_s_extrapolated"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Gbase 1 src x 32 drv 512x512 (BASELINE config 2), bounded sample",
-                   "sample": "1 (src,drv) pair per step, full Gbase forward, eval, fp32"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "oracle/gbase_oracle.py (CPU restatement of reference model.py, ATen fp32), "
-                                   "1 pair per step"},
-        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(B, args.gpus),
+        "cpu_baseline": {"value": m["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": cpu_sample_note(B, args.warmup, args.steps)},
+        "e2e": {"value": m["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "per_pair": {"value": m["per_pair_frames_per_s"], "unit": UNIT,
+                     "note": "reference semantics Gbase(xs, xd) with Bs == Bd: source half recomputed for every pair "
+                             "(SURVEY.md 8d config 2 variant A)"},
+        "source_half_s": m["source_half_s"], "per_driver_frame_s": m["per_driver_frame_s"],
+        "cpu_sample_s_per_step": m["sample_s_total"] / max(args.steps, 1),
     }
     print(json.dumps(line), flush=True)
 
@@ -232,7 +285,8 @@ def run_b200(args):
     xs_h, xd_all = synthetic_inputs(B * world)
     xs_h = xs_h.pin_memory()
     xd_h = xd_all[rank * B:(rank + 1) * B].contiguous().pin_memory()
-    del xd_all
+    if rank != 0 or world == 1:
+        xd_all = None          # rank 0 keeps every rank's frames for the parity-vs-one-GPU leg
     xs_d, xd_d = xs_h.to(dev), xd_h.to(dev)
     rgb_h = torch.empty((B, 3, 512, 512), dtype=torch.float32).pin_memory()
     from megaportrait_hack_b200.engine import GraphedGbase, ShardedGbase
@@ -343,12 +397,90 @@ def run_b200(args):
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- parity at the measured configuration: per-frame checksums (float64 sum of the RGB frame) of one more step on
+    # every rank, against rank 0 driving the same frames alone (same kernels => the sums agree to the last bit)
+    parity = None
+    with torch.no_grad():
+        rgb, _ = step(xs_d, xd_d)
+        fp = rgb.double().sum(dim=(1, 2, 3))
+        if world > 1:
+            allfp = [torch.empty_like(fp) for _ in range(world)]
+            dist.all_gather(allfp, fp)
+            if rank == 0:
+                worst = 0.0
+                for r in range(world):
+                    xr = xd_all[r * B:(r + 1) * B].to(dev)
+                    ref, _ = G.drive(G.encode_source(xs_d), xr)
+                    worst = max(worst, ((ref.double().sum(dim=(1, 2, 3)) - allfp[r]).abs() / allfp[r].abs()).max().item())
+                    del xr, ref
+                parity = {"checked_frames": B * world, "max_rel_checksum_diff": worst, "ok": bool(worst <= 1e-9),
+                          "what": "per-frame float64 sum of RGB on every rank vs the same frame driven by rank 0 alone"}
+            dist.barrier()
+        else:
+            ref, _ = G.drive(G.encode_source(xs_d), xd_d)
+            worst = ((ref.double().sum(dim=(1, 2, 3)) - fp).abs() / fp.abs()).max().item()
+            parity = {"checked_frames": B, "max_rel_checksum_diff": worst, "ok": bool(worst <= 1e-9),
+                      "what": "per-frame float64 sum of RGB, graph replay vs eager Gbase.drive(encode_source(xs), xd)"}
+            del ref
+        torch.cuda.synchronize()
+
+    # ---- strong scaling (BASELINE config 3): 256 driver frames of ONE source over the N GPUs, 256 / N per GPU in chunks of
+    # `drivers_per_gpu`; the source is encoded and broadcast once per step
+    strong = None
+    if graphed is not None and args.strong_drivers > 0 and (args.strong_drivers % (B * world) == 0):
+        per = args.strong_drivers // world
+        with torch.no_grad():
+            xbig = xd_d.repeat(per // B, 1, 1, 1)
+            for _ in range(2):
+                graphed.step_chunks(xs_d, xbig)
+            sync_all()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.strong_steps):
+                graphed.step_chunks(xs_d, xbig)
+            s1.record()
+            sync_all()
+            strong_ms = s0.elapsed_time(s1) / args.strong_steps
+            del xbig
+        strong = strong_ms
+    # ---- BASELINE config 2 variant (A) and config 1 through the drop-in `Gbase.forward` (eager launches, rank 0, N = 1)
+    cfgA = cfg1 = None
+    if world == 1 and not args.no_extra_configs:
+        with torch.no_grad():
+            def timed_fwd(xs_in, xd_in, reps):
+                G(xs_in, xd_in)
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(reps):
+                    G(xs_in, xd_in)
+                f1.record()
+                torch.cuda.synchronize()
+                return f0.elapsed_time(f1) / reps
+            msA = timed_fwd(xs_d.expand(B, -1, -1, -1).contiguous(), xd_d, 3)
+            cfgA = {"value": B / (msA * 1e-3), "unit": UNIT, "ms_per_step": msA,
+                    "what": f"Gbase.forward(xs.expand({B}), xd): reference semantics, source half recomputed for every pair "
+                            "(SURVEY.md 8d config 2 variant A), eager launches through the drop-in forward()"}
+            ms1 = timed_fwd(xs_d, xd_d[:1].contiguous(), 5)
+            g1 = GraphedGbase(G, 1, dev)
+            g1.step(xs_d, xd_d[:1])
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(5):
+                g1.step(xs_d, xd_d[:1])
+            f1.record()
+            torch.cuda.synchronize()
+            cfg1 = {"latency_ms_eager_forward": ms1, "latency_ms_graph_replay": f0.elapsed_time(f1) / 5,
+                    "what": "BASELINE config 1 on B200: Gbase(xs, xd) with 1 source + 1 driver frame (device-resident inputs)"}
+            del g1
+
+    t = torch.tensor([ms, ms_e2e, strong if strong is not None else 0.0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, strong_ms = t.tolist()
     frames = B * world * args.steps
     if rank != 0:
         if world > 1:
@@ -446,12 +578,10 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        xs_c, xd_c = synthetic_inputs(2)
-        cpu_forward_sample(1, sd, xs_c, xd_c)                      # warm-up
-        tt = cpu_forward_sample(2, sd, xs_c, xd_c)
-        cpu = {"value": 2 / tt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "oracle/gbase_oracle.py fp32 on host CPU: 1 warm-up pair + 2 timed (src,drv) pairs, "
-                         "reference semantics (source re-encoded per pair)"}
+        m = cpu_measure(sd, 1, 3, B)        # 1 warm-up + 3 timed
+        cpu = {"value": m["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_note(B, 1, 3),
+               "per_pair_frames_per_s": m["per_pair_frames_per_s"], "source_half_s": m["source_half_s"],
+               "per_driver_frame_s": m["per_driver_frame_s"]}
 
     line = {
         "metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -460,13 +590,9 @@ def run_b200(args):
                                     "main product + e4m3 cross terms; motion-encoder trunks: fp16x2 (fp16 activations x fp16 "
                                     "hi+lo weights, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": f"Gbase inference, 1 src x {B} drv per GPU, 512x512 (BASELINE config "
-                               f"{'2' if world == 1 else '3 share'}); source re-encoded every step",
-                   "drivers_per_gpu": B, "global_drivers": B * world, "parallelism": f"driver-shard x{world}",
-                   "collective": "none" if world == 1 else "1 NCCL broadcast of vc2d+es (25.2 MB) per step",
-                   "l2": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2; no flush needed",
-                   "weights": "seeded synthetic (megaportrait_hack_b200/seeded.py, seed 0)",
-                   "cuda_graphs": graph_note},
+        "config": workload_config(B, world),
+        "engine": {"cuda_graphs": graph_note,
+                   "l2": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int((xs_h.numel() + xd_h.numel()) * 4 * world),
                 "d2h_bytes_per_step": int(rgb_h.numel() * 4 * world)},
@@ -476,6 +602,14 @@ def run_b200(args):
         "roofline": roof,
         "kernels": extra,
         "grid_sample": gs,
+        "parity_vs_n1": parity,
+        "strong_scaling": None if not strong_ms else {
+            "value": args.strong_drivers / (strong_ms * 1e-3), "unit": UNIT, "ms_per_step": strong_ms, "scaling": "strong",
+            "global_drivers": args.strong_drivers, "drivers_per_gpu": args.strong_drivers // world,
+            "what": "BASELINE config 3: 1 source x 256 driver frames over the N GPUs (256 / N per GPU in chunks of "
+                    f"{B}), source encoded + broadcast once per step; device-resident inputs, max over ranks"},
+        "config2A": cfgA,
+        "config1": cfg1,
         "stages_eager_step": stages,
         "cpu_baseline": cpu,
         "useful_tflops_whole_step": (B * FLOPS_PER_DRIVER + FLOPS_SOURCE) * world / (step_ms * 1e-3) / 1e12,
@@ -493,6 +627,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--drivers-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config 2(A) / config 1 legs")
+    ap.add_argument("--strong-drivers", type=int, default=256, help="global driver frames of the strong-scaling leg (0 = off)")
+    ap.add_argument("--strong-steps", type=int, default=3)
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--dump-launches", default="", help="write the per-launch CUDA-event profile of one step here")
     ap.add_argument("--profile-step", action="store_true",

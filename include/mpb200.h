@@ -8,6 +8,8 @@
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in `_host`;
  *   - every call is asynchronous and stream-ordered on `stream` (a cudaStream_t passed as void*); no hidden
  *     synchronisation, no default-stream use, no allocation except the per-process TMA-descriptor encoder lookup;
+ *     calls may come from any host thread and any number of streams / CUDA graphs per device (mp_conv_tc hands its
+ *     tile-scheduler counters out per stream and per captured launch);
  *   - return value 0 = success; non-zero = error, text available from mp_last_error() (thread-local);
  *     never throws, never exits;
  *   - "NCDHW" = the reference's contiguous fp32 layout; "CL" = channels-last [N, D, H, W, C] (2-D tensors use D=1);

@@ -30,6 +30,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -89,8 +90,11 @@ struct TcParams {
 
 constexpr int SQ = 4;         // depth of the in-CTA tile-id queue (producer -> MMA issuer + epilogue warps)
 
-// Global scheduler slots: both words are zero between launches (the last CTA of a launch resets them).
-__device__ unsigned int g_sched[1024][2];
+// Global scheduler slots: both words are zero between launches (the last CTA of a launch resets them).  Two launches that
+// may run at the same time never share a slot (sched_slot() below): eager launches rotate through a range private to
+// their stream, launches recorded into a CUDA graph get a slot that nothing else will ever use.
+constexpr unsigned SCHED_SLOTS = 65536, SCHED_EAGER = 32768, SCHED_RANGE = 2048;
+__device__ unsigned int g_sched[SCHED_SLOTS][2];
 
 struct __align__(16) bf16x8 {
   bf16 v[8];
@@ -1751,6 +1755,43 @@ int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const P
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
 }
 
+// One counter slot for a launch on `stream` (NULL = use the static walk).  Rules that keep concurrently running kernels
+// apart: (1) eager launches rotate through SCHED_RANGE slots owned by their stream -- launches on one stream are
+// serialised, so a slot is idle again long before the rotation returns to it; (2) a launch that is being captured into a
+// CUDA graph is baked into that graph for good, so it takes a slot from a bump allocator that never hands it out twice
+// (one graph cannot run concurrently with itself); (3) when either pool is exhausted (more than 16 streams, more than
+// 32768 captured launches per device) the launch falls back to the static tile walk.
+unsigned int* sched_slot(int dev, cudaStream_t stream) {
+  struct PerDevice {
+    unsigned int* base = nullptr;
+    std::unordered_map<cudaStream_t, unsigned> range_of, rot;
+    unsigned next_range = 0, next_captured = SCHED_EAGER;
+  };
+  static PerDevice state[64];
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  PerDevice& st = state[dev];
+  if (!st.base) {
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, g_sched) != cudaSuccess) return nullptr;
+    st.base = static_cast<unsigned int*>(sym);
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cs != cudaStreamCaptureStatusNone) {
+    if (st.next_captured >= SCHED_SLOTS) return nullptr;
+    return st.base + 2 * (st.next_captured++);
+  }
+  auto it = st.range_of.find(stream);
+  if (it == st.range_of.end()) {
+    if ((st.next_range + 1) * SCHED_RANGE > SCHED_EAGER) return nullptr;
+    it = st.range_of.emplace(stream, st.next_range++).first;
+  }
+  unsigned& r = st.rot[stream];
+  const unsigned slot = it->second * SCHED_RANGE + (r++ % SCHED_RANGE);
+  return st.base + 2 * slot;
+}
+
 }  // namespace
 
 extern "C" int mp_conv_tc_supported(const mp_conv_desc* d) {
@@ -1806,21 +1847,10 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
         cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
       }
     }
-    // dynamic tile scheduling (default; MPB200_TC_STATIC=1 restores the static walk): a rotating pool of self-resetting
-    // counter slots, so concurrent launches on different streams never share one
+    // dynamic tile scheduling (default; MPB200_TC_STATIC=1 restores the static walk)
     static int dyn = [] { const char* e = getenv("MPB200_TC_STATIC"); return (e && atoi(e)) ? 0 : 1; }();
     pl.p.sched = nullptr;
-    if (dyn && !pl.v1) {
-      static unsigned int* base[64] = {nullptr};
-      static std::atomic<unsigned> next_slot{0};
-      const int di = (dev >= 0 && dev < 64) ? dev : 0;
-      if (!base[di]) {
-        void* sym = nullptr;
-        MP_REQUIRE(cudaGetSymbolAddress(&sym, g_sched) == cudaSuccess, "mp_conv_tc: cannot resolve the scheduler slots");
-        base[di] = static_cast<unsigned int*>(sym);
-      }
-      pl.p.sched = base[di] + 2 * (next_slot.fetch_add(1) % 1024u);
-    }
+    if (dyn && !pl.v1) pl.p.sched = sched_slot((dev >= 0 && dev < 64) ? dev : 0, mp_stream(stream));
     if (pl.v1) {
       dim3 grid((unsigned)pl.tiles_m, (unsigned)pl.tiles_n);
       k_conv_tc<<<grid, NUM_THREADS, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p);

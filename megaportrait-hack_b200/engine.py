@@ -124,6 +124,14 @@ class GraphedGbase:
         with torch.cuda.graph(self.g_render), torch.no_grad():
             self.out = gbase.drive_render(unpack_source(self.flat), self.motion)
         self.render_launches = ops.LAUNCHES - l0
+        # motion encoder alone (further chunks of driver frames that share the already encoded source): results are
+        # copied into the static tensors that the render graph reads
+        l0 = ops.LAUNCHES
+        self.g_motion = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_motion), torch.no_grad():
+            for dst, src in zip(self.motion, gbase.drive_motion(self.xd)):
+                dst.copy_(src)
+        self.motion_launches = ops.LAUNCHES - l0
 
     @torch.no_grad()
     def step(self, xs: torch.Tensor, xd_local: torch.Tensor):
@@ -138,3 +146,26 @@ class GraphedGbase:
         self.g_render.replay()
         ops._count(self.render_launches)
         return self.out
+
+    @torch.no_grad()
+    def step_chunks(self, xs: torch.Tensor, xd_local: torch.Tensor, sink=None):
+        """One source, `xd_local.shape[0]` = k * n_drivers driver frames on this rank (BASELINE config 3 with 256 / N
+        frames per GPU): the source is encoded and broadcast ONCE, then every chunk of n_drivers frames runs the motion
+        encoder and the render graph.  `sink(i, out)` is called with the static outputs of chunk i before the next chunk
+        overwrites them (None: outputs are dropped, as in a throughput run)."""
+        n = self.xd.shape[0]
+        if xd_local.shape[0] % n:
+            raise RuntimeError(f"step_chunks: {xd_local.shape[0]} driver frames are not a multiple of the chunk size {n}")
+        for i in range(xd_local.shape[0] // n):
+            chunk = xd_local[i * n:(i + 1) * n]
+            if i == 0:
+                out = self.step(xs, chunk)
+            else:
+                self.xd.copy_(chunk, non_blocking=True)
+                self.g_motion.replay()
+                self.g_render.replay()
+                ops._count(self.motion_launches + self.render_launches)
+                out = self.out
+            if sink is not None:
+                sink(i, out)
+        return out
