@@ -85,7 +85,9 @@ def test_forward_refuses_to_return_detached_outputs(gbase):
 @pytest.mark.timeout(900)
 def test_two_rank_nccl_shards_match_single_gpu():
     """Real NCCL, 2 ranks (skipped on a 1-GPU box): shard outputs of ShardedGbase and GraphedGbase == the same frames
-    driven on one GPU, bit for bit (same kernels; the broadcast moves fp32 bytes)."""
+    driven on one GPU (<= 1e-6 against the same shard, i.e. the same batch size: the broadcast moves fp32 bytes and the
+    kernels are the same; <= 1e-4 against the full batch driven at once, the batch-invariance bound of
+    test_batch_invariance_and_determinism)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import socket
@@ -101,5 +103,6 @@ def test_two_rank_nccl_shards_match_single_gpu():
     res = json.loads(line[len("NCCL_SHARD_CHECK "):])
     print(res)
     for name in ("sharded", "graphed"):
-        assert res[name]["max_abs_vs_single_gpu"] <= 1e-6, res
+        assert res[name]["max_abs_vs_same_shard_on_one_gpu"] <= 1e-6, res
+        assert res[name]["max_abs_vs_full_batch_on_one_gpu"] <= 1e-4, res     # other batch size: batch-invariance bound
         assert res[name]["swap_visible"] > 2e-4, res      # frames differ by ~5e-4 with the seeded weights
