@@ -143,6 +143,10 @@ typedef struct mp_conv_desc {
 enum { MP_PREC_SPLIT_BF16 = 0, MP_PREC_F16X2 = 1, MP_PREC_F16_Q8 = 2 };
 enum { MP_FMT_NATIVE = 0, MP_FMT_SPLIT_BF16 = 1, MP_FMT_F16 = 2, MP_FMT_F16_Q8 = 3 };
 
+/* Drops the library's host-side caches (encoded TMA descriptors keyed by pointer + geometry; they hold no device
+ * memory and never dereference the pointer, so stale entries are harmless -- this only returns the host memory). */
+int mp_release_caches(void);
+
 /* Implicit-GEMM convolution on tcgen05 tensor cores fed by TMA (fp32 accumulate in TMEM; operand format by `prec`).
  * Requires Cin % 16 == 0 and a 128-position output tile that is a box of the (D,H,W) grid. */
 int mp_conv_tc(const mp_conv_desc* desc, void* stream);

@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <mutex>
@@ -1387,6 +1388,58 @@ EncodeTiledFn get_encoder() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs 1-2 us and a convolution launch needs up to 7 maps: at batch 1 that is a third of the
+// eager launch cost.  Descriptors depend only on (pointer, extents, strides, box, type, swizzle), and PyTorch's caching
+// allocator hands the same pointers out step after step, so the encoded maps are kept in a small per-process table
+// (bounded; cleared wholesale when full; mp_release_caches() empties it).
+struct MapKey {
+  uint64_t w[24];
+  bool operator==(const MapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.w) { h ^= x; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> c;
+  return c;
+}
+std::mutex g_map_mu;
+
+CUresult encode_cached(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
+                       const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                       CUtensorMapSwizzle swz, CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+  static int enabled = [] { const char* e = getenv("MPB200_NO_MAP_CACHE"); return (e && atoi(e)) ? 0 : 1; }();
+  if (!enabled) return get_encoder()(m, dt, rank, ptr, dims, strides, box, estr, il, swz, l2, oob);
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  k.w[0] = reinterpret_cast<uint64_t>(ptr);
+  k.w[1] = (uint64_t)dt | ((uint64_t)rank << 8) | ((uint64_t)il << 16) | ((uint64_t)swz << 24) | ((uint64_t)l2 << 32) |
+           ((uint64_t)oob << 40) | ((uint64_t)dev << 48);
+  for (cuuint32_t i = 0; i < rank; ++i) {
+    k.w[2 + i] = dims[i];
+    k.w[8 + i] = i + 1 < rank ? strides[i] : 0;
+    k.w[14 + i] = ((uint64_t)box[i] << 32) | estr[i];
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_map_mu);
+    auto it = map_cache().find(k);
+    if (it != map_cache().end()) { *m = it->second; return CUDA_SUCCESS; }
+  }
+  CUresult r = get_encoder()(m, dt, rank, ptr, dims, strides, box, estr, il, swz, l2, oob);
+  if (r == CUDA_SUCCESS) {
+    std::lock_guard<std::mutex> lock(g_map_mu);
+    if (map_cache().size() >= 16384) map_cache().clear();
+    map_cache().emplace(k, *m);
+  }
+  return r;
+}
+
 struct Plan {
   TcParams p;
   int tiles_m, tiles_n;
@@ -1694,7 +1747,7 @@ int encode_act_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const
                        (cuuint32_t)(pl.slab ? 1 : pl.p.BNb)};
   cuuint32_t estr[5] = {1, st, st, 1, 1};
   const CUtensorMapDataType dt = pl.p.prec != MP_PREC_SPLIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUresult r = get_encoder()(m, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = encode_cached(m, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(activation) failed (%d)", (int)r);
@@ -1708,7 +1761,7 @@ int encode_out_map(CUtensorMap* m, void* ptr, const mp_conv_desc* d, const Plan&
   cuuint64_t strides[4] = {C * 2, C * 2 * p.W, C * 2 * p.W * p.H, C * 2 * p.W * p.H * p.D};
   cuuint32_t box[5] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BD, (cuuint32_t)(pl.slab ? 1 : p.BNb)};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = get_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, ptr, dims, strides, box, estr,
+  CUresult r = encode_cached(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, ptr, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
@@ -1727,7 +1780,7 @@ int encode_act2_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, cons
                        (cuuint32_t)(pl.slab ? 1 : p.BNb)};
   cuuint32_t estr[5] = {1, st, st, 1, 1};
   const CUtensorMapDataType dt = p.prec != MP_PREC_SPLIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUresult r = get_encoder()(m, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = encode_cached(m, dt, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(second source) failed (%d)", (int)r);
 }
@@ -1740,7 +1793,7 @@ int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const P
     cuuint64_t strides3[2] = {ktot * 2, ktot * 2 * (cuuint64_t)d->Cout_pad};
     cuuint32_t box3[3] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BN, 2};
     cuuint32_t estr3[3] = {1, 1, 1};
-    CUresult r3 = get_encoder()(m, dt3, 3, const_cast<void*>(ptr), dims3, strides3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r3 = encode_cached(m, dt3, 3, const_cast<void*>(ptr), dims3, strides3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r3 == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(weights, 3-D) failed (%d)", (int)r3);
   }
@@ -1749,7 +1802,7 @@ int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const P
   cuuint32_t box[2] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BN};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = pl.p.prec != MP_PREC_SPLIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUresult r = get_encoder()(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = encode_cached(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
@@ -1793,6 +1846,12 @@ unsigned int* sched_slot(int dev, cudaStream_t stream) {
 }
 
 }  // namespace
+
+extern "C" int mp_release_caches(void) {
+  std::lock_guard<std::mutex> lock(g_map_mu);
+  map_cache().clear();
+  return 0;
+}
 
 extern "C" int mp_conv_tc_supported(const mp_conv_desc* d) {
   if (!d) return 0;

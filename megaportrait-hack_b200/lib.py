@@ -29,25 +29,71 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+STAMP_PATH = LIB_PATH + ".stamp"      # sha256 of every source, header and flag the library was built from
+OBJ_DIR = os.path.join(HERE, "build")
+
+
+def _headers():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h")))
+
+
+def _digest(paths) -> str:
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def source_digest() -> str:
+    return _digest(sources() + _headers())
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    """True when the library is missing or was built from different sources / flags (content hash, not mtime: a prebuilt
+    binary that travelled to another box is used only if it matches the sources that travelled with it)."""
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH)):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
-    return any(os.path.getmtime(p) > t for p in deps)
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != source_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into libmpb200.so for sm_100a (cross-compiles without a GPU)."""
+    """Compile every .cu under csrc/ for sm_100a (cross-compiles without a GPU) and link libmpb200.so.  Objects are
+    cached per source under build/ keyed on the content of the source, the headers and the flags, and compiled in
+    parallel."""
     if not force and not needs_build():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + sources()
-    if verbose:
-        print(" ".join(cmd))
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    hdrs = _headers()
+
+    def compile_one(src):
+        key = _digest([src] + hdrs)[:24]
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + "." + key + ".o")
+        if force or not os.path.exists(obj):
+            for old in glob.glob(os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".*.o")):
+                os.remove(old)
+            cmd = [nvcc] + cflags + ["-c", "-o", obj, src]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
+        raise RuntimeError(f"nvcc link failed:\n{r.stdout}\n{r.stderr}")
+    with open(STAMP_PATH, "w") as f:
+        f.write(source_digest() + "\n")
     return LIB_PATH
 
 
@@ -88,6 +134,7 @@ _SIGNATURES = {
     "mp_im2col3x3_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_maxpool3x3s2_cl_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "mp_global_avgpool_cl_f16": (c_int, [_P, _P, c_int, c_int64, c_int, _P]),
+    "mp_release_caches": (c_int, []),
     "mp_conv_tc": (c_int, [POINTER(ConvDesc), _P]),
     "mp_conv_simt": (c_int, [POINTER(ConvDesc), _P]),
     "mp_conv_tc_supported": (c_int, [POINTER(ConvDesc)]),
