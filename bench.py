@@ -444,7 +444,7 @@ def run_b200(args):
             del xbig
         strong = strong_ms
     # ---- BASELINE config 2 variant (A) and config 1 through the drop-in `Gbase.forward` (eager launches, rank 0, N = 1)
-    cfgA = cfg1 = None
+    cfgA = cfg1 = cfg4 = None
     if world == 1 and not args.no_extra_configs:
         with torch.no_grad():
             def timed_fwd(xs_in, xd_in, reps):
@@ -474,6 +474,38 @@ def run_b200(args):
             cfg1 = {"latency_ms_eager_forward": ms1, "latency_ms_graph_replay": f0.elapsed_time(f1) / 5,
                     "what": "BASELINE config 1 on B200: Gbase(xs, xd) with 1 source + 1 driver frame (device-resident inputs)"}
             del g1
+            # BASELINE config 4 (row f-3): the high-resolution stage.  Genh is fully convolutional (model.py:1349-1391):
+            # timed on a batch of 8 frames at 1024 x 1024, and GHR = Genh(Gbase(xs, xd)) on 8 (src, drv) pairs at 512 x 512
+            from megaportrait_hack_b200 import model as M, seeded as S
+            genh = M.Genh().eval()
+            genh.load_state_dict(S.genh_state_dict(0))
+            genh = genh.to(dev)
+            xg = torch.rand(8, 3, 1024, 1024, generator=torch.Generator().manual_seed(11)).to(dev) * 2 - 1
+
+            def timed(fn, reps):
+                fn()
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(reps):
+                    fn()
+                t1.record()
+                torch.cuda.synchronize()
+                return t0.elapsed_time(t1) / reps
+            ms_g = timed(lambda: genh(xg), 3)
+            hw = 1024 * 1024
+            blk = lambda px: 2 * 2 * px * 64 * 64 * 9            # one ResBlock2D(64, 64): two 3x3 convs
+            fl = 2 * hw * 64 * 3 * 49 + blk(hw) + blk(hw // 4) + blk(hw // 16) + 9 * blk(hw // 64) + blk(hw // 16) + \
+                blk(hw // 4) + blk(hw) + 2 * hw * 3 * 64 * 49
+            ghr = M.GHR().eval()
+            ghr.Gbase, ghr.Genh = G, genh
+            ms_h = timed(lambda: ghr(xs_d.expand(8, -1, -1, -1).contiguous(), xd_d[:8].contiguous()), 3)
+            cfg4 = {"genh_1024x1024_batch8": {"value": 8 / (ms_g * 1e-3), "unit": UNIT, "ms": ms_g,
+                                              "useful_tflops": 8 * fl / (ms_g * 1e-3) / 1e12},
+                    "ghr_512x512_8_pairs": {"value": 8 / (ms_h * 1e-3), "unit": UNIT, "ms": ms_h},
+                    "what": "BASELINE config 4: Genh (model.py:1349-1391, ResBlock2D(64) read as ResBlock2D(64, 64)) on 8 frames "
+                            "of 1024 x 1024, and GHR.forward = Genh(Gbase(xs, xd)[0]) on 8 pairs; eager launches, seeded weights"}
+            del genh, ghr, xg
 
     t = torch.tensor([ms, ms_e2e, strong if strong is not None else 0.0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
@@ -610,6 +642,7 @@ def run_b200(args):
                     f"{B}), source encoded + broadcast once per step; device-resident inputs, max over ranks"},
         "config2A": cfgA,
         "config1": cfg1,
+        "config4": cfg4,
         "stages_eager_step": stages,
         "cpu_baseline": cpu,
         "useful_tflops_whole_step": (B * FLOPS_PER_DRIVER + FLOPS_SOURCE) * world / (step_ms * 1e-3) / 1e12,

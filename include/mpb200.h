@@ -31,7 +31,7 @@ extern "C" {
 #define MPB200_ABI_VERSION 4
 
 /* activation codes shared by several entry points */
-enum { MP_ACT_NONE = 0, MP_ACT_RELU = 1, MP_ACT_RELU_TANH = 2, MP_ACT_SIGMOID = 3 };
+enum { MP_ACT_NONE = 0, MP_ACT_RELU = 1, MP_ACT_RELU_TANH = 2, MP_ACT_SIGMOID = 3, MP_ACT_TANH = 4 };
 
 int mp_abi_version(void);
 const char* mp_last_error(void);

@@ -37,6 +37,7 @@ __device__ __forceinline__ float mp_apply_act(float v, int act) {
     case MP_ACT_RELU: return fmaxf(v, 0.f);
     case MP_ACT_RELU_TANH: return tanhf(fmaxf(v, 0.f));
     case MP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case MP_ACT_TANH: return tanhf(v);
     default: return v;
   }
 }

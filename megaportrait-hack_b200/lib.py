@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-shared",
               "-Xcompiler", "-fPIC"]
 
-ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 PREC_SPLIT_BF16, PREC_F16X2, PREC_F16_Q8 = 0, 1, 2   # mp_conv_desc.prec
 FMT_NATIVE, FMT_SPLIT_BF16, FMT_F16, FMT_F16_Q8 = 0, 1, 2, 3   # mp_conv_desc.out_fmt / res_fmt
 ABI_VERSION = 4

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .emtn import COMPRESS_DIM, FEATURE_SIZE, FEATURE_SIZE_AVG_POOL, CustomResNet50, Emtn, SixDRepNet_Detector  # noqa: F401
-from .ops import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, Act
+from .ops import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, ACT_TANH, Act
 
 # G2d's identity res-blocks on the fp16 + FP8 cross-term convolution (MPB200_G2D_PREC=split selects three-pass split-bf16)
 _Q8_ENABLED = os.environ.get("MPB200_G2D_PREC", "q8") != "split"
@@ -837,3 +837,73 @@ class Gbase(nn.Module):
         _require_no_grad(self, xs, xd)
         src = self.encode_source(xs)
         return self.drive(src, xd)
+
+
+# ----------------------------------------------------------------------------------------------------- Genh / GHR
+class Genh(nn.Module, _Packed):
+    """model.py:1346-1391: 7x7 stem, 4 ResBlock2D with AvgPool2d between them, 8 ResBlock2D, 3 x
+    [bilinear x2, ResBlock2D], 7x7 conv to RGB, tanh -- fully convolutional, output size = input size.
+
+    One documented repair: the reference writes `ResBlock2D(64)` although `ResBlock2D.__init__(in_channels,
+    out_channels, downsample=False)` (model.py:601) has no default, so `Genh()` raises TypeError there (model.py:1354);
+    the only reading that type-checks and keeps the residual identity is `ResBlock2D(64, 64)`.  Attribute names and
+    state_dict keys are the reference's (`encoder.0.weight`, `encoder.1.conv1.weight`, ..., `decoder.6.weight`)."""
+
+    def __init__(self):
+        super().__init__()
+        rb = lambda: ResBlock2D(64, 64)
+        self.encoder = nn.Sequential(nn.Conv2d(3, 64, kernel_size=7, padding=3), rb(), nn.AvgPool2d(kernel_size=2, stride=2),
+                                     rb(), nn.AvgPool2d(kernel_size=2, stride=2), rb(),
+                                     nn.AvgPool2d(kernel_size=2, stride=2), rb())
+        self.res_blocks = nn.Sequential(*[rb() for _ in range(8)])
+        up = lambda: nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+        self.decoder = nn.Sequential(up(), rb(), up(), rb(), up(), rb(), nn.Conv2d(64, 3, kernel_size=7, padding=3), nn.Tanh())
+
+    def _build_plan(self):
+        dev = self.encoder[0].weight.device
+        return {"stem": ops.pack_conv(self.encoder[0].weight, self.encoder[0].bias, dev, cin_pad=16),
+                "out": ops.pack_conv(self.decoder[6].weight, self.decoder[6].bias, dev)}
+
+    def _forward_cl(self, x: torch.Tensor) -> torch.Tensor:
+        """x NCHW fp32 [B,3,H,W] (H, W multiples of 8) -> NCHW fp32 [B,3,H,W] in (-1, 1)."""
+        from .emtn_cuda import rgb16
+        P = self._plan()
+        h, _ = ops.conv(rgb16(x), P["stem"], f32=False, split=True)
+        for i in (1, 3, 5, 7):
+            pooled = i < 7
+            h, _ = self.encoder[i]._forward_cl(h, f32=pooled, split=not pooled)
+            if pooled:
+                h = ops.avgpool2(h, 1, f32=False, split=True)
+        for blk in self.res_blocks:
+            h, _ = blk._forward_cl(h)
+        for i in (1, 3, 5):
+            h = ops.upsample2x_linear(h, 1, f32=False, split=True)
+            h, _ = self.decoder[i]._forward_cl(h)
+        out, _ = ops.conv(h, P["out"], act=ACT_TANH, f32=True)
+        return ops.to_nchw(out, 4)
+
+    def forward(self, x):
+        _require_inference(self, x)
+        if self.training:
+            raise NotImplementedError("Genh: train mode is not implemented on the B200 path (SURVEY.md 8f-2)")
+        assert x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0, \
+            f"Genh expects (B, 3, H, W) with H, W multiples of 8 (three 2x poolings), got {tuple(x.shape)}"
+        with torch.no_grad():
+            return self._forward_cl(_as_f32_cuda(x))
+
+
+class GHR(nn.Module):
+    """model.py:1441-1450: `Genh(Gbase(xs, xd))`.  The reference hands Genh the whole `(image, pyramids)` tuple that
+    `Gbase.forward` returns (model.py:1180 vs 1447-1448) -- a TypeError as written; here the
+    image is taken, which is the only reading under which `README.md:214` (`GHR.Gbase.load_state_dict(...)`) and
+    `GHR.forward` run."""
+
+    def __init__(self):
+        super().__init__()
+        self.Gbase = Gbase()
+        self.Genh = Genh()
+
+    def forward(self, xs, xd):
+        xhat_base = self.Gbase(xs, xd)
+        xhat_base = xhat_base[0] if isinstance(xhat_base, tuple) else xhat_base
+        return self.Genh(xhat_base)

@@ -15,7 +15,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import lib as _lib
-from .lib import (ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, FMT_F16_Q8, FMT_SPLIT_BF16, PREC_F16_Q8,  # noqa: F401
+from .lib import (ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, ACT_TANH, FMT_F16_Q8, FMT_SPLIT_BF16, PREC_F16_Q8,  # noqa: F401
                   PREC_F16X2, PREC_SPLIT_BF16, ConvDesc)
 
 LAUNCHES = 0   # number of libmpb200 kernel launches issued by this process (bench.py reports it)

@@ -125,3 +125,14 @@ def apply_seeded(model: torch.nn.Module, seed: int = 0, rotnet: torch.nn.Module 
             rsd = rotnet.state_dict()
             for k, (shape, kind) in rcls.items():
                 rsd[k].copy_(seeded_tensor(ROTNET_PREFIX + k, shape, kind, seed))
+
+
+GENH_PREFIX = "Genh."
+
+
+def genh_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded weights of `Genh`, keyed like `Genh().state_dict()`; the generator of every tensor is
+    derived from "Genh." + key, so the reference's Genh, the oracle and the B200 module get the same values."""
+    from . import model
+    cls = classify_module_tensors(model.Genh())
+    return {k: seeded_tensor(GENH_PREFIX + k, shape, kind, seed) for k, (shape, kind) in cls.items()}

@@ -20,11 +20,11 @@ import sys as _sys
 from megaportrait_hack_b200.model import *  # noqa: F401,F403
 from megaportrait_hack_b200.model import (  # noqa: F401
     COMPRESS_DIM, FEATURE_SIZE, FEATURE_SIZE_AVG_POOL, AdaptiveGroupNorm, AntiAliasInterpolation2d, Conv2d_WS,
-    Conv3D_WS, CustomResNet50, Eapp, Emtn, FlowField, G2d, G3d, Gbase, ImagePyramide, ResBlock2D, ResBlock3D,
+    Conv3D_WS, CustomResNet50, Eapp, Emtn, FlowField, G2d, G3d, Gbase, Genh, GHR, ImagePyramide, ResBlock2D, ResBlock3D,
     ResBlock3D_Adaptive, ResBlock_Custom, SixDRepNet_Detector, WarpGeneratorC2D, WarpGeneratorS2C,
     apply_warping_field, compute_rotation_matrix, compute_rt_warp, device, invalidate_plans)
 
-_OUT_OF_SCOPE = ("PerceptualLoss", "IdentitySimilarityLoss", "PairwiseTransferLoss", "Discriminator", "Genh", "GHR",
+_OUT_OF_SCOPE = ("PerceptualLoss", "IdentitySimilarityLoss", "PairwiseTransferLoss", "Discriminator",
                  "Student", "crop_and_warp_face", "get_foreground_mask", "remove_background_and_convert_to_rgb",
                  "GazeBlinkLoss", "MPGazeLoss", "PatchGanEncoder", "GazeLoss", "Encoder", "Decoder", "UNet",
                  "cosine_loss", "contrastive_loss", "ResBlock", "PatchDiscriminator", "MultiscaleDiscriminator")

@@ -376,3 +376,28 @@ def gbase_forward_shared_source(xs1, xd, sd: SD, stages: bool = False):
     if stages:
         return drv["rgb"], drv["pyramids"], {**src, **drv}
     return drv["rgb"], drv["pyramids"]
+
+
+# ----------------------------------------------------------------------------- Genh / GHR (row f-3)
+def genh(x, sd: SD, p: str = "Genh"):
+    """Genh.forward, model.py:1349-1391, with `ResBlock2D(64)` read as `ResBlock2D(64, 64)` (the reference raises TypeError as
+    written, model.py:1354 vs 601).  Sequential indices: encoder 0 conv7x7, 1/3/5/7 blocks, 2/4/6 AvgPool2d(2); res_blocks
+    0..7; decoder 0/2/4 bilinear x2 (align_corners=True), 1/3/5 blocks, 6 conv7x7, 7 tanh."""
+    pre = (p + ".") if p else ""
+    x = _conv(x, sd, pre + "encoder.0", padding=3)
+    for i in (1, 3, 5, 7):
+        x = resblock2d(x, sd, f"{pre}encoder.{i}")
+        if i < 7:
+            x = F.avg_pool2d(x, 2, 2)
+    for i in range(8):
+        x = resblock2d(x, sd, f"{pre}res_blocks.{i}")
+    for i in (1, 3, 5):
+        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+        x = resblock2d(x, sd, f"{pre}decoder.{i}")
+    return torch.tanh(_conv(x, sd, pre + "decoder.6", padding=3))
+
+
+def ghr_forward(xs, xd, sd_gbase: SD, sd_genh: SD):
+    """GHR.forward, model.py:1446-1450, with the tuple returned by Gbase.forward reduced to its image (model.py:1180)."""
+    rgb, _ = gbase_forward(xs, xd, sd_gbase)
+    return genh(rgb, sd_genh, "")

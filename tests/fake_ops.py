@@ -70,6 +70,8 @@ def _act(v, code):
         return torch.tanh(F.relu(v))
     if code == ops.ACT_SIGMOID:
         return torch.sigmoid(v)
+    if code == ops.ACT_TANH:
+        return torch.tanh(v)
     return v
 
 
