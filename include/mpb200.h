@@ -143,6 +143,15 @@ typedef struct mp_conv_desc {
 enum { MP_PREC_SPLIT_BF16 = 0, MP_PREC_F16X2 = 1, MP_PREC_F16_Q8 = 2 };
 enum { MP_FMT_NATIVE = 0, MP_FMT_SPLIT_BF16 = 1, MP_FMT_F16 = 2, MP_FMT_F16_Q8 = 3 };
 
+/* ---------------------------------------------------------------- frame decode (row f-4) ------------------- */
+/* JPEG frames -> uint8 RGB HWC on the device through nvJPEG (a CUDA-toolkit library, dlopen'ed at first use):
+ * `Image.open(path).convert("RGB")` of inference.py:10-13 / the per-frame decode of EmoDataset.py:180-247 for JPEG
+ * sources.  jpeg_host[i] / nbytes[i] are HOST pointers to n bitstreams of identical size H x W; out_u8 [n, H, W, 3] is a
+ * DEVICE buffer in the layout mp_frames_u8_to_f32 reads.  Stream-ordered.  mp_jpeg_info parses the header only. */
+int mp_jpeg_info(const unsigned char* jpeg_host, size_t nbytes, int* width, int* height);
+int mp_decode_jpeg_frames(const unsigned char* const* jpeg_host, const size_t* nbytes, int n, unsigned char* out_u8,
+                          int H, int W, void* stream);
+
 /* Drops the library's host-side caches (encoded TMA descriptors keyed by pointer + geometry; they hold no device
  * memory and never dereference the pointer, so stale entries are harmless -- this only returns the host memory). */
 int mp_release_caches(void);

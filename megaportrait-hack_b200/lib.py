@@ -88,7 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc link failed:\n{r.stdout}\n{r.stderr}")
@@ -135,6 +135,8 @@ _SIGNATURES = {
     "mp_maxpool3x3s2_cl_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "mp_global_avgpool_cl_f16": (c_int, [_P, _P, c_int, c_int64, c_int, _P]),
     "mp_release_caches": (c_int, []),
+    "mp_jpeg_info": (c_int, [_P, c_size_t, POINTER(c_int), POINTER(c_int)]),
+    "mp_decode_jpeg_frames": (c_int, [_P, _P, c_int, _P, c_int, c_int, _P]),
     "mp_conv_tc": (c_int, [POINTER(ConvDesc), _P]),
     "mp_conv_simt": (c_int, [POINTER(ConvDesc), _P]),
     "mp_conv_tc_supported": (c_int, [POINTER(ConvDesc)]),

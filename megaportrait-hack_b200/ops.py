@@ -762,6 +762,27 @@ def gn_relu_conv3x3_head(a: Act, ab: torch.Tensor, weight_host: torch.Tensor, bi
     return out
 
 
+def decode_jpeg_frames(blobs: Sequence[bytes], device="cuda") -> torch.Tensor:
+    """JPEG bitstreams (host `bytes`, all the same size) -> uint8 RGB frames [N, H, W, 3] on `device` through nvJPEG
+    (row f-4: `Image.open(...).convert("RGB")` of inference.py:10-13 for JPEG sources; only the compressed bytes cross PCIe)."""
+    if not blobs:
+        raise RuntimeError("decode_jpeg_frames: no frames")
+    L = _lib.load()
+    bufs = [ctypes.create_string_buffer(bytes(b), len(b)) for b in blobs]
+    w, h = ctypes.c_int(), ctypes.c_int()
+    _lib.check(L.mp_jpeg_info(ctypes.cast(bufs[0], ctypes.c_void_p), len(blobs[0]), ctypes.byref(w), ctypes.byref(h)), "mp_jpeg_info")
+    n = len(blobs)
+    out = torch.empty((n, h.value, w.value, 3), dtype=torch.uint8, device=device)
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.cast(b, ctypes.c_void_p) for b in bufs])
+    sizes = (ctypes.c_size_t * n)(*[len(b) for b in blobs])
+    with torch.cuda.device(out.device):
+        _lib.check(L.mp_decode_jpeg_frames(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(sizes, ctypes.c_void_p), n, _p(out),
+                                           h.value, w.value, _stream()), "mp_decode_jpeg_frames")
+        torch.cuda.current_stream().synchronize()      # the host bitstream buffers are released when this function returns
+    _count(n)
+    return out
+
+
 @_profiled
 def frames_u8_to_f32(frames: torch.Tensor, mean: float = 0.5, std: float = 0.5) -> torch.Tensor:
     """uint8 HWC frames [N,H,W,3] on the device -> fp32 NCHW [N,3,H,W] = Normalize(mean, std)(ToTensor(frame))

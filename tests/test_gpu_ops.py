@@ -834,3 +834,47 @@ def test_frame_io_matches_reference_preprocessing(ops):
     assert diff.max().item() <= 1 and (diff > 0).float().mean().item() < 1e-3      # ties at integer boundaries only
     back = ops.frames_f32_to_u8(x.to(DEV), reverse_channels=False).cpu()          # round trip: truncation may lose one count
     assert (back.int() - u8.int()).abs().max().item() <= 1
+
+
+def test_jpeg_frames_decode_on_device(ops, tmp_path):
+    """Row f-4: JPEG bitstreams -> uint8 RGB HWC frames on the device through nvJPEG (`mp_decode_jpeg_frames`), against
+    OpenCV's libjpeg decode of the same bytes (decoders may differ by an LSB or two in the IDCT / colour conversion;
+    4:4:4 sampling keeps chroma up-sampling filters out of the comparison), then through `inference.inference_base`-style
+    plumbing: file -> device frame -> normalised fp32."""
+    import cv2
+    import numpy as np
+    from conftest import load_frames
+    from megaportrait_hack_b200 import inference
+    frames = [(f[0].permute(1, 2, 0) * 255).round().to(torch.uint8).numpy() for f in load_frames()]     # RGB 512 x 512
+    blobs = []
+    for fr in frames:
+        ok, enc = cv2.imencode(".jpg", cv2.cvtColor(fr, cv2.COLOR_RGB2BGR),
+                               [cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+        assert ok
+        blobs.append(enc.tobytes())
+    got = ops.decode_jpeg_frames(blobs, DEV)
+    assert got.shape == (2, 512, 512, 3) and got.dtype == torch.uint8 and got.is_cuda
+    for i, b in enumerate(blobs):
+        ref = cv2.cvtColor(cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+        d = np.abs(got[i].cpu().numpy().astype(np.int32) - ref.astype(np.int32))
+        print(f"frame {i}: nvJPEG vs libjpeg max diff {d.max()}, mean {d.mean():.4f}")
+        assert d.max() <= 4 and d.mean() < 1.0
+    # 4:2:0 (the common case): only the chroma up-sampling filters differ -> a PSNR bound
+    ok, enc = cv2.imencode(".jpg", cv2.cvtColor(frames[0], cv2.COLOR_RGB2BGR), [cv2.IMWRITE_JPEG_QUALITY, 90])
+    g420 = ops.decode_jpeg_frames([enc.tobytes()], DEV)[0].cpu().numpy().astype(np.float64)
+    r420 = cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB).astype(np.float64)
+    psnr = 10 * np.log10(255.0 ** 2 / max(((g420 - r420) ** 2).mean(), 1e-12))
+    print("4:2:0 PSNR nvJPEG vs libjpeg:", psnr)
+    assert psnr > 40.0
+    # file plumbing: a .jpg path goes through the device decoder, a .png path through PIL; same normalised tensor layout
+    pj, pp = str(tmp_path / "src.jpg"), str(tmp_path / "src.png")
+    open(pj, "wb").write(blobs[0])
+    cv2.imwrite(pp, cv2.cvtColor(frames[0], cv2.COLOR_RGB2BGR))
+    a = inference.load_image_device(pj, DEV)
+    b = inference.load_image_device(pp, DEV)
+    assert a.shape == b.shape == (1, 512, 512, 3) and a.is_cuda and b.is_cuda
+    assert (a.int() - b.int()).abs().float().mean().item() < 2.0      # JPEG q95 vs the lossless original
+    x = ops.frames_u8_to_f32(a)
+    assert x.shape == (1, 3, 512, 512) and x.min().item() >= -1.0 and x.max().item() <= 1.0
+    with pytest.raises(RuntimeError, match="not a decodable JPEG"):
+        ops.decode_jpeg_frames([b"not a jpeg at all"], DEV)
