@@ -220,6 +220,14 @@ int mp_gs_brick_tune(const int* cfg, int n);
  * re-normalisation and the trilinear border gather run in one kernel. */
 int mp_apply_warping_field(const float* v, const float* warp_field, float* out, int N, int C, int D, int H, int W,
                            int Df, int Hf, int Wf, void* stream);
+/* Backward of apply_warping_field (row f-2, first operator of the training step: train.py:188 back-propagates through
+ * model.py:1062): grad_v [N,C,D,H,W] and / or grad_warp_field [N,3,Df,Hf,Wf] (either may be NULL; both must be
+ * ZERO-INITIALISED by the caller, the kernel accumulates with fp32 atomics) from grad_out [N,C,D,H,W], following ATen's
+ * grid_sampler_3d_backward for (bilinear, border, align_corners=True) and the trilinear align_corners=True flow
+ * resample.  Accumulation order is not fixed: results are reproducible to fp32 rounding, not bit for bit. */
+int mp_apply_warping_field_backward(const float* grad_out, const float* v, const float* warp_field, float* grad_v,
+                                    float* grad_warp_field, int N, int C, int D, int H, int W, int Df, int Hf, int Wf,
+                                    void* stream);
 /* WarpGenerator tail (model.py:965-973): 64^3 field = affine_grid(theta[N,3,4], align_corners=False) +
  * trilinear(em 16^3 -> 64^3, align_corners=False).  em is CL [N,E,E,E,3]; out is NCDHW [N,3,G,G,G]. */
 int mp_warp_field(const float* em_cl, const float* theta, float* out, int N, int E, int G, void* stream);

@@ -394,3 +394,108 @@ extern "C" int mp_apply_warping_field_ws(const float* v, const float* warp_field
              "mp_apply_warping_field_ws: bad dims");
   return gather_ws_common(1, v, warp_field, out, workspace, workspace_bytes, N, C, D, H, W, D, H, W, Df, Hf, Wf, stream);
 }
+
+// ------------------------------------------------------------------------------------------------ backward (row f-2)
+// Gradients of apply_warping_field(v, warp_field) (model.py:1028-1065), i.e. of F.interpolate(flow, trilinear,
+// align_corners=True) -> identity grid + flow -> the reference's re-normalisation -> F.grid_sample(bilinear, border,
+// align_corners=True), following ATen's grid_sampler_3d_backward (GridSampler.h: clip_coordinates_set_grad zeroes the
+// coordinate gradient AT and beyond the border, out-of-range corners contribute nothing):
+//   grad_v[n,c,tap]  += grad_out[n,c,s] * w_tap                                   (scatter, fp32 atomics)
+//   d out / d ix      = sum_taps v[tap] * d w_tap / d ix  (and iy, iz); the chain pix = ((g+1)/2)(size-1),
+//                       g = 2 (lin + flow) / (size-1) - 1 has d pix / d flow = 1, times the clip mask
+//   grad_flow[n,k,:] += (d out / d pix_k) spread over the 8 flow voxels of the align_corners=True resample
+// One thread = one output voxel x GS_CCHUNK channels; both outputs must be zero-initialised by the caller.
+__device__ __forceinline__ float clip_grad_mask(float p, int size) {
+  // p = un-normalised coordinate BEFORE clipping: gradient 1 strictly inside (0, size-1), else 0
+  return (p <= 0.f || p >= (float)(size - 1)) ? 0.f : 1.f;
+}
+
+__global__ void k_apply_warping_field_bwd(const float* __restrict__ go, const float* __restrict__ v,
+                                          const float* __restrict__ wf, float* __restrict__ gv, float* __restrict__ gwf,
+                                          int C, int D, int H, int W, int Df, int Hf, int Wf) {
+  const int64_t S = (int64_t)D * H * W;
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int n = blockIdx.z;
+  int w = (int)(s % W), h = (int)((s / W) % H), d = (int)(s / ((int64_t)W * H));
+  int d0, d1, h0, h1, w0, w1;
+  float ld, lh, lw;
+  src_ac_true(d, Df, D, d0, d1, ld);
+  src_ac_true(h, Hf, H, h0, h1, lh);
+  src_ac_true(w, Wf, W, w0, w1, lw);
+  const int64_t fs = (int64_t)Df * Hf * Wf;
+  const float* f = wf + (int64_t)n * 3 * fs;
+  const float fx = resample_flow(f, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+  const float fy = resample_flow(f + fs, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+  const float fz = resample_flow(f + 2 * fs, Df, Hf, Wf, d0, d1, ld, h0, h1, lh, w0, w1, lw);
+  const float gx = 2.0f * (linspace_m1_1(w, W) + fx) / (float)(W - 1) - 1.0f;
+  const float gy = 2.0f * (linspace_m1_1(h, H) + fy) / (float)(H - 1) - 1.0f;
+  const float gz = 2.0f * (linspace_m1_1(d, D) + fz) / (float)(D - 1) - 1.0f;
+  const float px = ((gx + 1.f) / 2.f) * (float)(W - 1), py = ((gy + 1.f) / 2.f) * (float)(H - 1),
+              pz = ((gz + 1.f) / 2.f) * (float)(D - 1);
+  const float ix = fminf((float)(W - 1), fmaxf(px, 0.f)), iy = fminf((float)(H - 1), fmaxf(py, 0.f)),
+              iz = fminf((float)(D - 1), fmaxf(pz, 0.f));
+  const float flx = floorf(ix), fly = floorf(iy), flz = floorf(iz);
+  const int x0 = (int)flx, y0 = (int)fly, z0 = (int)flz;
+  const float tx = ix - flx, ty = iy - fly, tz = iz - flz;
+  const int c0 = blockIdx.y * GS_CCHUNK, c1 = min(C, c0 + GS_CCHUNK);
+  const float* vn = v + (int64_t)n * C * S;
+  const float* gon = go + (int64_t)n * C * S + s;
+  float* gvn = gv ? gv + (int64_t)n * C * S : nullptr;
+  float gix = 0.f, giy = 0.f, giz = 0.f;
+  for (int c = c0; c < c1; ++c) {
+    const float g = __ldg(gon + (int64_t)c * S);
+    const float* vc = vn + (int64_t)c * S;
+    float* gvc = gvn ? gvn + (int64_t)c * S : nullptr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+      const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
+      if (x >= W || y >= H || z >= D) continue;                 // within_bounds_3d (cells are never negative after the clip)
+      const float wx = dx ? tx : 1.f - tx, wy = dy ? ty : 1.f - ty, wz = dz ? tz : 1.f - tz;
+      const int64_t off = ((int64_t)z * H + y) * W + x;
+      if (gvc) atomicAdd(gvc + off, g * (wx * wy * wz));
+      if (gwf) {
+        const float val = __ldg(vc + off) * g;
+        gix += val * (dx ? 1.f : -1.f) * wy * wz;
+        giy += val * (dy ? 1.f : -1.f) * wx * wz;
+        giz += val * (dz ? 1.f : -1.f) * wx * wy;
+      }
+    }
+  }
+  if (!gwf) return;
+  gix *= clip_grad_mask(px, W);
+  giy *= clip_grad_mask(py, H);
+  giz *= clip_grad_mask(pz, D);
+  if (gix == 0.f && giy == 0.f && giz == 0.f) return;
+  float* gf = gwf + (int64_t)n * 3 * fs;
+  const float gk[3] = {gix, giy, giz};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (gk[k] == 0.f) continue;
+    float* p = gf + k * fs;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float wgt = (a ? ld : 1.f - ld) * (b ? lh : 1.f - lh) * (e ? lw : 1.f - lw);
+          if (wgt != 0.f) atomicAdd(p + ((int64_t)(a ? d1 : d0) * Hf + (b ? h1 : h0)) * Wf + (e ? w1 : w0), gk[k] * wgt);
+        }
+  }
+}
+
+extern "C" int mp_apply_warping_field_backward(const float* grad_out, const float* v, const float* warp_field, float* grad_v,
+                                               float* grad_warp_field, int N, int C, int D, int H, int W, int Df, int Hf,
+                                               int Wf, void* stream) {
+  MP_REQUIRE(grad_out && v && warp_field && (grad_v || grad_warp_field), "mp_apply_warping_field_backward: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && C > 0 && D > 1 && H > 1 && W > 1 && Df > 0 && Hf > 0 && Wf > 0,
+             "mp_apply_warping_field_backward: bad dims");
+  const int64_t S = (int64_t)D * H * W;
+  dim3 g((unsigned)((S + 127) / 128), (C + GS_CCHUNK - 1) / GS_CCHUNK, N);
+  k_apply_warping_field_bwd<<<g, 128, 0, mp_stream(stream)>>>(grad_out, v, warp_field, grad_v, grad_warp_field, C, D, H, W, Df, Hf,
+                                                            Wf);
+  MP_LAUNCH_CHECK("mp_apply_warping_field_backward");
+  return 0;
+}

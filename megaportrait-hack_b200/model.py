@@ -689,8 +689,13 @@ class WarpGeneratorC2D(_WarpGenerator):
 
 
 def apply_warping_field(v, warp_field):
-    """model.py:1028-1065."""
-    _require_inference(nn.Identity(), v, warp_field)
+    """model.py:1028-1065.  Differentiable (row f-2, first operator): with autograd recording on and an input that requires
+    grad it goes through `ops.WarpFunction` (CUDA backward for both v and warp_field)."""
+    for t in (v, warp_field):
+        if torch.is_tensor(t) and not t.is_cuda:
+            raise RuntimeError(f"apply_warping_field: input is on {t.device}; the B200 path has no CPU fallback")
+    if torch.is_grad_enabled() and (v.requires_grad or warp_field.requires_grad):
+        return ops.WarpFunction.apply(v, warp_field)
     return ops.apply_warping_field_ncdhw(_as_f32_cuda(v), _as_f32_cuda(warp_field))
 
 

@@ -693,6 +693,40 @@ def apply_warping_field_ncdhw(v: torch.Tensor, warp_field: torch.Tensor, direct:
     return out
 
 
+def apply_warping_field_backward(grad_out: torch.Tensor, v: torch.Tensor, warp_field: torch.Tensor, need_v: bool = True,
+                                 need_wf: bool = True):
+    """Gradients of `apply_warping_field_ncdhw` w.r.t. v and warp_field (row f-2; ATen grid_sampler_3d_backward semantics)."""
+    for t, nm in ((grad_out, "grad_out"), (v, "v"), (warp_field, "warp_field")):
+        _chk_cuda(t, torch.float32, "apply_warping_field_backward " + nm)
+    N, C, D, H, W = v.shape
+    _, _, Df, Hf, Wf = warp_field.shape
+    gv = torch.zeros_like(v) if need_v else None
+    gwf = torch.zeros_like(warp_field) if need_wf else None
+    L = _lib.load()
+    _lib.check(L.mp_apply_warping_field_backward(_p(grad_out), _p(v), _p(warp_field), _p(gv), _p(gwf), N, C, D, H, W, Df, Hf, Wf,
+                                                 _stream()), "mp_apply_warping_field_backward")
+    _count()
+    return gv, gwf
+
+
+class WarpFunction(torch.autograd.Function):
+    """`apply_warping_field(v, warp_field)` with a CUDA backward (row f-2): forward = the brick-staged kernel, backward =
+    `mp_apply_warping_field_backward`."""
+
+    @staticmethod
+    def forward(ctx, v, warp_field):
+        v, warp_field = v.detach().float().contiguous(), warp_field.detach().float().contiguous()
+        ctx.save_for_backward(v, warp_field)
+        return apply_warping_field_ncdhw(v, warp_field)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        v, warp_field = ctx.saved_tensors
+        gv, gwf = apply_warping_field_backward(grad_out.float().contiguous(), v, warp_field, ctx.needs_input_grad[0],
+                                               ctx.needs_input_grad[1])
+        return gv, gwf
+
+
 def warp_field(em_cl: torch.Tensor, theta: torch.Tensor, G: int = 64) -> torch.Tensor:
     """em_cl [N,E,E,E,3] fp32, theta [N,3,4] -> [N,3,G,G,G] (model.py:965-973)."""
     _chk_cuda(em_cl, torch.float32, "warp_field em")

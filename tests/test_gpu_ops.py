@@ -878,3 +878,45 @@ def test_jpeg_frames_decode_on_device(ops, tmp_path):
     assert x.shape == (1, 3, 512, 512) and x.min().item() >= -1.0 and x.max().item() <= 1.0
     with pytest.raises(RuntimeError, match="not a decodable JPEG"):
         ops.decode_jpeg_frames([b"not a jpeg at all"], DEV)
+
+
+@pytest.mark.parametrize("regime", ["interior", "border", "degenerate"])
+def test_apply_warping_field_backward(ops, regime):
+    """Row f-2, first operator: gradients of apply_warping_field w.r.t. the volume and the warp field against autograd of
+    the CPU oracle (F.interpolate + F.grid_sample) in fp32 -- the reference's own precision: the coordinate gradient is
+    discontinuous at the border (ATen's clip mask), so a float64 reference flips the mask of the few samples that sit
+    within rounding of the border.  `interior`: a few cells of displacement around the
+    identity; `border`: displacements that push many samples onto / beyond the border (clip mask, skipped corners);
+    `degenerate`: the reference's own regime (flow in [0, 1): everything samples the first cells)."""
+    import gbase_oracle as O
+    from megaportrait_hack_b200 import model
+    N, C, D, H, W = 2, 10, 16, 64, 64
+    g = torch.Generator().manual_seed(141)
+    v = torch.randn(N, C, D, H, W, generator=g)
+    zz, yy, xx = torch.meshgrid(torch.linspace(0, 15, 64), torch.linspace(0, 63, 64), torch.linspace(0, 63, 64), indexing="ij")
+    lin = torch.stack((torch.linspace(-1, 1, 64)[None, None, :].expand(64, 64, 64),
+                       torch.linspace(-1, 1, 64)[None, :, None].expand(64, 64, 64),
+                       torch.linspace(-1, 1, 64)[:, None, None].expand(64, 64, 64)))
+    ramp = (torch.stack((xx, yy, zz)) - lin)[None]
+    noise = torch.rand(N, 3, 64, 64, 64, generator=g) - 0.5
+    if regime == "interior":
+        wf = ramp + noise * torch.tensor([3.0, 3.0, 0.8]).view(1, 3, 1, 1, 1)
+    elif regime == "border":
+        wf = ramp * 1.08 - 2.0 + noise * 4.0
+    else:
+        wf = torch.rand(N, 3, 64, 64, 64, generator=g)
+    go = torch.randn(N, C, D, H, W, generator=g)
+    vd, wd = v.clone().requires_grad_(True), wf.clone().requires_grad_(True)
+    O.apply_warping_field(vd, wd).backward(go)
+    vc, wc = v.to(DEV).requires_grad_(True), wf.to(DEV).requires_grad_(True)
+    out = model.apply_warping_field(vc, wc)
+    assert out.requires_grad
+    out.backward(go.to(DEV))
+    gv_err = (vc.grad.cpu() - vd.grad).abs().max().item() / vd.grad.abs().max().item()
+    gw_err = (wc.grad.cpu() - wd.grad).abs().max().item() / max(wd.grad.abs().max().item(), 1e-12)
+    print(f"{regime}: grad_v rel err {gv_err:.2e}, grad_warp_field rel err {gw_err:.2e}")
+    assert gv_err <= 1e-4 and gw_err <= 1e-4
+    # only one gradient requested
+    v2 = v.to(DEV).requires_grad_(True)
+    model.apply_warping_field(v2, wf.to(DEV)).backward(go.to(DEV))
+    assert (v2.grad - vc.grad).abs().max().item() <= 1e-4 * vc.grad.abs().max().item()
