@@ -541,6 +541,20 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     return out, stats
 
 
+def pack_conv_dgrad(weight: torch.Tensor, device=None) -> PackedConv:
+    """Weights of the DATA gradient of a stride-1 "same" convolution (row f-2): dX = conv(dY, W') with W'[ci, co, k] =
+    W[co, ci, flip(k)] -- the transposed convolution is again an implicit GEMM of the same shape family, so it runs on
+    the same tcgen05 kernel as the forward pass (three-pass split-bf16: fp32-grade gradients)."""
+    w = weight.detach()
+    dims = tuple(range(2, w.dim()))
+    return pack_conv(w.transpose(0, 1).flip(dims).contiguous(), None, device or weight.device)
+
+
+def conv_input_grad(grad_out: Act, pw_dgrad: PackedConv, f32: bool = True, split: bool = False) -> Act:
+    """dL/dX of `conv(x, W)` (stride 1, padding k // 2) from dL/dY: `conv(grad_out, pack_conv_dgrad(W))`."""
+    return conv(grad_out, pw_dgrad, f32=f32, split=split)[0]
+
+
 @_profiled
 def maxpool3x3s2(a: Act) -> Act:
     """nn.MaxPool2d(3, 2, 1) on a split 2-D activation."""

@@ -920,3 +920,26 @@ def test_apply_warping_field_backward(ops, regime):
     v2 = v.to(DEV).requires_grad_(True)
     model.apply_warping_field(v2, wf.to(DEV)).backward(go.to(DEV))
     assert (v2.grad - vc.grad).abs().max().item() <= 1e-4 * vc.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 96, 96, 4, 16, 16, 3), (2, 512, 256, 1, 32, 32, 3), (1, 64, 128, 1, 64, 64, 1)],
+                         ids=["3d_96", "2d_512_256", "1x1"])
+def test_conv_input_gradient_on_tensor_cores(ops, shape):
+    """Row f-2: the data gradient of a stride-1 same-padded convolution is the forward kernel on flipped / transposed
+    weights (ops.pack_conv_dgrad); checked against autograd of F.conv2d / F.conv3d."""
+    N, Cin, Cout, D, H, W, k = shape
+    x = rnd(N, Cin, D, H, W, seed=151).requires_grad_(True)
+    wt = (rnd(Cout, Cin, *((k, k, k) if D > 1 else (k, k)), seed=152) / math.sqrt(Cin * k ** (3 if D > 1 else 2)))
+    go = rnd(N, Cout, D, H, W, seed=153)
+    if D > 1:
+        F.conv3d(x, wt, None, padding=k // 2).backward(go)
+    else:
+        F.conv2d(x.squeeze(2), wt, None, padding=k // 2).backward(go.squeeze(2))
+    ref = x.grad if D > 1 else x.grad
+    ga = ops.from_nchw(go.to(DEV))
+    dx = ops.conv_input_grad(ga, ops.pack_conv_dgrad(wt, DEV), f32=True)
+    got = cl_to_ncdhw(dx.f32.cpu())
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    print("dgrad rel err", err)
+    assert err <= 1e-4
