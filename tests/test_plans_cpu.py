@@ -87,19 +87,32 @@ def test_operand_packing_accuracy():
     wk = w.permute(0, 2, 3, 1).reshape(64, -1)
     p0 = ops.pack_conv(w, None)
     assert ((p0.w_hi.float() + p0.w_lo.float()) - wk).abs().max() <= wk.abs().max() * 2.0 ** -16
+    # fp16 planes hold w * sw (sw = 1 / acc_scale, the power of two that puts the largest weight into [1, 2))
     p1 = ops.pack_conv(w, None, prec=ops.PREC_F16X2)
-    assert ((p1.w_hi.float() + p1.w_lo.float() / ops.F16_LO_SCALE) - wk).abs().max() <= wk.abs().max() * 2.0 ** -20
+    assert 1.0 <= (wk / p1.acc_scale).abs().max() < 2.0
+    assert ((p1.w_hi.float() + p1.w_lo.float() / ops.F16_LO_SCALE) * p1.acc_scale - wk).abs().max() <= wk.abs().max() * 2.0 ** -20
     p2 = ops.pack_conv(w, None, prec=ops.PREC_F16_Q8)
     hi = p2.w_hi.view(torch.float16).float()
     q = p2.w_lo.reshape(64, -1, 2, 64).view(torch.float8_e4m3fn).float()
     wl8, w8 = q[:, :, 0].reshape(64, -1), q[:, :, 1].reshape(64, -1)
     assert p2.w_hi.data_ptr() + p2.w_hi.numel() == p2.w_lo.data_ptr()          # one allocation: single-TMA [hi | lo] loads
-    assert ((hi + wl8 * p2.corr_scale) - wk).abs().max() <= wk.abs().max() * 2.0 ** -15      # fp16 + e4m3 low part
-    sw = 1.0 / (ops.F16_LO_SCALE * p2.corr_scale)
-    assert (w8 / sw - wk).abs().max() <= wk.abs().max() * 2.0 ** -4 and 1.0 <= (wk * sw).abs().max() < 2.0
+    assert p2.corr_scale == 1.0 / ops.F16_LO_SCALE and 1.0 <= (wk / p2.acc_scale).abs().max() < 2.0
+    assert ((hi + wl8 * p2.corr_scale) * p2.acc_scale - wk).abs().max() <= wk.abs().max() * 2.0 ** -15   # fp16 + e4m3 low part
+    assert (w8 * p2.acc_scale - wk).abs().max() <= wk.abs().max() * 2.0 ** -4
+    # tiny weights keep all their bits (no fp16 subnormals): the same relative accuracy at 2^-12 of the magnitude
+    p3 = ops.pack_conv(w * 2.0 ** -12, None, prec=ops.PREC_F16X2)
+    assert ((p3.w_hi.float() + p3.w_lo.float() / ops.F16_LO_SCALE) * p3.acc_scale - wk * 2.0 ** -12).abs().max() <= \
+        wk.abs().max() * 2.0 ** -32
     # activation planes: fp16 plane + [e4m3(x) | e4m3((x - fp16 x) * 2048)] per 64-channel group
     x = torch.randn(2, 1, 3, 5, 128, generator=g) * 3
     qx = ops.q8_planes(x).reshape(2, 1, 3, 5, 2, 2, 64).view(torch.float8_e4m3fn).float()
     x8, xl8 = qx[..., 0, :].reshape(x.shape), qx[..., 1, :].reshape(x.shape)
     assert (x8 - x).abs().max() <= x.abs().max() * 2.0 ** -4
     assert ((x.half().float() + xl8 / 2048) - x).abs().max() <= x.abs().max() * 2.0 ** -15
+    # per-tensor power-of-two scale of the byte plane: large activations no longer saturate e4m3 (448)
+    xb = x * 300.0
+    sc = ops.q8_scale_for(xb.abs().max().item())
+    qs = ops.q8_planes(xb, sc).reshape(2, 1, 3, 5, 2, 2, 64).view(torch.float8_e4m3fn).float()
+    assert (qs[..., 0, :].reshape(x.shape) / sc - xb).abs().max() <= xb.abs().max() * 2.0 ** -4
+    q1 = ops.q8_planes(xb, 1.0).reshape(2, 1, 3, 5, 2, 2, 64).view(torch.float8_e4m3fn).float()
+    assert (q1[..., 0, :].reshape(x.shape) - xb).abs().max() > xb.abs().max() * 0.25      # unscaled: clipped at 448
