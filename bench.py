@@ -165,11 +165,18 @@ def grid_sample_leg(dev, pk, batches=(1, 32), reps=7):
                 del grid
             del v, out
     head = next(c for c in cells if c["batch"] == 32 and c["grid"] == "spread")
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_grid_sample_brick|32x96x16x64x64 spread"]
+        traffic = {"dram_bytes_per_launch": t["dram_bytes"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"],
+                   "ratio": t["dram_bytes"] / t["algorithmic_bytes"], "source": t["source"]}
+    except Exception:
+        pass
     return {"op": "mp_grid_sample3d_brick (TMA-staged bricks; NCDHW in/out, no workspace copy) / mp_grid_sample3d_ws for "
                   "the adversarial grid", "bound": "hbm", "peak": pk["hbm_gbs"], "unit": "GB/s",
             "algorithmic_bytes_per_sample": GS_ALG_BYTES, "l2": "flushed before every timed launch", "timing": f"median of {reps}",
             "batch": head["batch"], "grid": head["grid"], "ms": head["ms"], "achieved": head["achieved"], "frac": head["frac"],
-            "cells": cells}
+            "traffic": traffic, "cells": cells}
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
