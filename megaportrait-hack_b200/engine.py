@@ -73,6 +73,11 @@ class ShardedGbase:
     def step(self, xs: torch.Tensor, xd_local: torch.Tensor):
         src = self.G.encode_source(xs) if self.rank == self.src_rank else None
         src = self.broadcast_source(src, xd_local.device)
+        if xd_local.shape[0] == 0:          # more ranks than driver frames: this rank took part in the broadcast only
+            dev = xd_local.device
+            return (torch.empty((0, 3, 512, 512), dtype=torch.float32, device=dev),
+                    {"prediction_0.5": torch.empty((0, 3, 256, 256), dtype=torch.float32, device=dev),
+                     "prediction_0.25": torch.empty((0, 3, 128, 128), dtype=torch.float32, device=dev)})
         return self.G.drive(src, xd_local)
 
 

@@ -844,6 +844,32 @@ class Gbase(nn.Module):
         return self.drive(src, xd)
 
 
+ADAPTIVE_KEYS = tuple(f"warp_generator_{g}.adaptive_matrix_{m}" for g in ("s2c", "c2d") for m in ("gamma", "beta"))
+
+
+def load_reference_state_dict(gbase: "Gbase", state_dict, adaptive_matrices=None):
+    """`Gbase.load_state_dict` for checkpoints written by the reference.  On CUDA builds the reference's
+    `nn.Parameter(...).to(device)` (model.py:934-935, 985-986) leaves `adaptive_matrix_gamma/beta` OUT of `state_dict()`, so
+    such a checkpoint lacks exactly these 4 keys (`ADAPTIVE_KEYS`); every other key must be present.  Pass the matrices in
+    `adaptive_matrices` ({key: tensor}) when the training run kept them; otherwise they stay at this module's init and a
+    warning says so (the output then depends on this process's random state -- seed it or supply the matrices)."""
+    import warnings
+    sd = dict(state_dict)
+    if adaptive_matrices:
+        sd.update({k: v for k, v in adaptive_matrices.items() if k in ADAPTIVE_KEYS})
+    res = gbase.load_state_dict(sd, strict=False)
+    missing = [k for k in res.missing_keys if not k.startswith("image_pyramid.")]
+    bad = [k for k in missing if k not in ADAPTIVE_KEYS]
+    if bad or res.unexpected_keys:
+        raise RuntimeError(f"load_reference_state_dict: missing {bad[:5]}{'...' if len(bad) > 5 else ''}, "
+                           f"unexpected {list(res.unexpected_keys)[:5]}")
+    if missing:
+        warnings.warn("checkpoint has no adaptive_matrix_gamma/beta (written by a CUDA build of the reference, model.py:934-935): "
+                      f"{missing} keep this module's random init -- pass `adaptive_matrices=` or seed the construction")
+    invalidate_plans(gbase)
+    return res
+
+
 # ----------------------------------------------------------------------------------------------------- Genh / GHR
 class Genh(nn.Module, _Packed):
     """model.py:1346-1391: 7x7 stem, 4 ResBlock2D with AvgPool2d between them, 8 ResBlock2D, 3 x

@@ -22,7 +22,7 @@ from megaportrait_hack_b200.model import (  # noqa: F401
     COMPRESS_DIM, FEATURE_SIZE, FEATURE_SIZE_AVG_POOL, AdaptiveGroupNorm, AntiAliasInterpolation2d, Conv2d_WS,
     Conv3D_WS, CustomResNet50, Eapp, Emtn, FlowField, G2d, G3d, Gbase, Genh, GHR, ImagePyramide, ResBlock2D, ResBlock3D,
     ResBlock3D_Adaptive, ResBlock_Custom, SixDRepNet_Detector, WarpGeneratorC2D, WarpGeneratorS2C,
-    apply_warping_field, compute_rotation_matrix, compute_rt_warp, device, invalidate_plans)
+    apply_warping_field, compute_rotation_matrix, compute_rt_warp, device, invalidate_plans, load_reference_state_dict)
 
 _OUT_OF_SCOPE = ("PerceptualLoss", "IdentitySimilarityLoss", "PairwiseTransferLoss", "Discriminator",
                  "Student", "crop_and_warp_face", "get_foreground_mask", "remove_background_and_convert_to_rgb",

@@ -120,3 +120,41 @@ def test_out_of_scope_names_are_delegated_to_the_reference(tmp_path):
     env2 = dict(os.environ, MEGAPORTRAIT_REFERENCE=str(tmp_path / "missing"))
     r2 = subprocess.run([sys.executable, "-c", code2], cwd=ROOT, env=env2, capture_output=True, text=True, timeout=300)
     assert r2.returncode == 0 and ("IMPORT_ERROR_OK" in r2.stdout or "HAS_REF" in r2.stdout), r2.stdout + r2.stderr[-2000:]
+
+
+def test_reference_checkpoint_loader_tolerates_the_cuda_build_quirk():
+    """a checkpoint written by a CUDA build of the reference lacks the 4 `adaptive_matrix_*` keys
+    (model.py:934-935); `load_reference_state_dict` accepts exactly that, warns, and rejects anything else."""
+    import warnings
+    import model
+    G = model.Gbase()
+    sd = {k: v.clone() for k, v in G.state_dict().items()}
+    cuda_style = {k: v for k, v in sd.items() if "adaptive_matrix_" not in k}
+    assert len(sd) - len(cuda_style) == 4
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model.load_reference_state_dict(G, cuda_style)
+    assert any("adaptive_matrix" in str(x.message) for x in w)
+    mats = {k: torch.full_like(sd[k], 0.25) for k in sd if "adaptive_matrix_" in k}
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model.load_reference_state_dict(G, cuda_style, adaptive_matrices=mats)
+    assert not w and float(G.warp_generator_s2c.adaptive_matrix_gamma[0, 0]) == 0.25
+    broken = dict(cuda_style)
+    broken.pop("G3d.final_conv.weight")
+    with pytest.raises(RuntimeError, match="missing"):
+        model.load_reference_state_dict(G, broken)
+
+
+def test_sharded_step_with_more_ranks_than_frames_returns_empty_outputs():
+    from megaportrait_hack_b200 import engine
+
+    class _G:
+        def encode_source(self, xs):
+            return {"vc2d": None, "es": None}
+
+        def drive(self, src, xd):
+            raise AssertionError("drive must not run on an empty shard")
+
+    out, pyr = engine.ShardedGbase(_G()).step(torch.zeros(1, 3, 512, 512), torch.zeros(0, 3, 512, 512))
+    assert out.shape == (0, 3, 512, 512) and pyr["prediction_0.25"].shape == (0, 3, 128, 128)
