@@ -897,6 +897,241 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ kernel v4 (CTA pair)
+// MP_PREC_F16_Q8 convolutions on `cta_group::2`: a cluster of two CTAs (one SM pair) computes a 256-position x 128-channel
+// tile with M = 256 MMAs.  Each CTA stages ITS 128 positions of A (fp16 plane + FP8 byte plane) and HALF of the weight
+// tile (64 of the 128 output channels), the leader CTA's two issuing warps (fp16 main product, FP8 cross terms) drive the
+// tensor cores of both SMs, and each CTA's TMEM ends up with its own 128 rows of both accumulators.  Per SM and K step the
+// tensor core now fetches 4 KB of A + 2 KB of B instead of 4 + 4 KB -- the single-CTA kernel sits exactly on the 128 B/clk
+// shared-memory limit there (ncu: tensor pipe 70 %) -- and the weight tile crosses L2 -> SM once per pair instead of once
+// per CTA.
+//   barriers (same offsets in both CTAs): full[s]   leader only; the leader's producer expects the bytes of BOTH CTAs, the
+//                                                   peer's TMA loads signal it through the cluster address (.cta_group::2)
+//                                         empty[s]  per CTA; tcgen05.commit multicasts the two issuers' arrivals to both
+//                                         tfull[b]  per CTA (multicast commit): accumulator b is complete
+//                                         tempty[b] leader only: 8 epilogue warps of each CTA arrive (the peer's remotely)
+//   tiles: static walk, item = cluster id + k * clusters, item -> (pair of position tiles, channel tile), channel fastest.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+template <bool F8>
+__device__ __forceinline__ void umma_pair_e(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if (F8)
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of every MMA this thread issued so far -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair_e(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t.reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(bar)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS3, 1)
+k_conv_q8_pair(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* epi = reinterpret_cast<float*>(gen_base + p.epi_off);
+  long long* row_off = reinterpret_cast<long long*>(gen_base + p.epi_off + TILE_M * EPI_PITCH * 4);
+  const uint32_t bars = smem_base + p.epi_off + p.epi_bytes;   // full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t tmem_slot = bars + (2 * p.STAGES + 4) * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));   // unused (no GroupNorm statistics here)
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  auto full_bar = [&](int s) { return bars + s * 8; };
+  auto empty_bar = [&](int s) { return bars + (p.STAGES + s) * 8; };
+  auto tfull_bar = [&](int b) { return bars + (2 * p.STAGES + b) * 8; };
+  auto tempty_bar = [&](int b) { return bars + (2 * p.STAGES + 2 + b) * 8; };
+  const int taps = p.KD * p.KH * p.KW;
+  const int num_kb = taps * p.num_cchunks;
+  const int items = (p.total_tiles / p.tiles_n / 2) * p.tiles_n;     // (pairs of position tiles) x channel tiles
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 2);       // two issuing warps, multicast commits
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 2);
+      mbar_init(tempty_bar(b), 16);     // 8 epilogue warps of each CTA
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                    // both CTAs' barriers are initialised before anything signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+
+  // item -> my position tile (pair index * 2 + rank) and the channel tile
+  auto item_coords = [&](int item, int& n, int& d0, int& h0, int& w0, int& n0) {
+    n0 = (item % p.tiles_n) * p.BN;
+    int t = (item / p.tiles_n) * 2 + (int)rank;
+    w0 = (t % p.tiles_w) * p.BW; t /= p.tiles_w;
+    h0 = (t % p.tiles_h) * p.BH; t /= p.tiles_h;
+    d0 = (t % p.tiles_d) * p.BD;
+    n = t / p.tiles_d;
+  };
+  const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      const int pd = p.KD / 2, ph = p.KH / 2, pw = p.KW / 2;
+      uint32_t s = 0, ph_bit = 1;
+      const uint32_t tx_both = 2u * (2u * p.a_bytes + 2u * p.b_bytes);      // A (2 planes) + B half (2 planes), both CTAs
+      for (int item = first; item < items; item += step) {
+        int n, d0, h0, w0, n0;
+        item_coords(item, n, d0, h0, w0, n0);
+        int kw = -1, kh = 0, kd = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          if (++kw == p.KW) { kw = 0; if (++kh == p.KH) { kh = 0; ++kd; } }
+          for (int cc = 0; cc < p.num_cchunks; ++cc) {
+            mbar_wait(empty_bar(s), ph_bit);
+            const uint32_t sa = smem_base + s * p.stage_bytes;
+            const uint32_t fb = mapa_shared(full_bar(s), 0);                 // the LEADER's barrier, cluster address
+            if (leader) mbar_expect_tx(full_bar(s), tx_both);
+            const int c0 = cc * p.CCHUNK;
+            tma_load_5d_2sm(sa, &map_a_hi, fb, c0, w0 + kw - pw, h0 + kh - ph, d0 + kd - pd, n);
+            tma_load_5d_2sm(sa + p.a_bytes, &map_a_lo, fb, c0, w0 + kw - pw, h0 + kh - ph, d0 + kd - pd, n);
+            tma_load_3d_2sm(sa + 2 * p.a_bytes, &map_b, fb, tap * p.Cin + c0, n0 + (int)rank * (p.BN / 2), 0);
+            if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 10) {
+    // ===================================================================== MMA issuers (leader CTA only)
+    if (leader) {
+      const bool q8_issuer = warp == 10;
+      const uint32_t dhi = desc_hi_word(p.sbo, p.layout_type);
+      uint32_t it = 0, s = 0, ph_bit = 0;
+      for (int item = first; item < items; item += step, ++it) {
+        const uint32_t b = it & 1;
+        mbar_wait(tempty_bar(b), ((it >> 1) & 1) ^ 1);     // both CTAs' epilogues have drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + b * (uint32_t)p.acc_w;
+        for (int i = 0; i < num_kb; ++i) {
+          mbar_wait(full_bar(s), ph_bit);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + s * p.stage_bytes;
+          const uint32_t a_hi = sa, a_lo = sa + p.a_bytes, b_hi = sa + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
+          if (q8_issuer) {
+            const uint32_t aq = desc_lo_word(a_lo), bq = desc_lo_word(b_lo);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_pair_e<true>(d_tmem + (uint32_t)p.BN, aq + 2 * k, bq + 2 * k, dhi, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+          } else {
+            const uint32_t ah = desc_lo_word(a_hi), bh = desc_lo_word(b_hi);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_pair_e<false>(d_tmem, ah + 2 * k, bh + 2 * k, dhi, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair_e(empty_bar(s));
+          if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
+        }
+        umma_commit_pair_e(tfull_bar(b));
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9 of both CTAs)
+    const int q = warp & 3, half = (warp - 2) >> 2, r = q * 32 + lane, et = threadIdx.x - 64;
+    const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0), tempty_leader1 = mapa_shared(tempty_bar(1), 0);
+    uint32_t it = 0;
+    for (int item = first; item < items; item += step, ++it) {
+      int n, d0, h0, w0, n0;
+      item_coords(item, n, d0, h0, w0, n0);
+      const uint32_t b = it & 1;
+      const int ww = r % p.BW, hh = (r / p.BW) % p.BH, dd = r / (p.BW * p.BH);
+      const int64_t pos = (((int64_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
+      const int64_t obase = pos * p.out_C + p.out_c_off;
+      mbar_wait(tfull_bar(b), (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      epilogue_drain(p, epi, row_off, s_stats, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.acc_w), n0, obase,
+                     half, r, et, lane, true);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(b ? tempty_leader1 : tempty_leader0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();                    // the peer may still be reading my shared memory / signalling my barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel v3 (slab)
 // 3x3(x3) convolutions with few output channels are bound by the L2 -> shared-memory feed of the A operand when
 // every filter tap re-fetches its own shifted 128-position box.  Here the output tile is an (MT*BH) x BW patch
@@ -1785,13 +2020,13 @@ int encode_act2_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, cons
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(second source) failed (%d)", (int)r);
 }
 
-int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const Plan& pl) {
+int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const Plan& pl, int box_rows = 0) {
   const cuuint64_t ktot = (cuuint64_t)d->KD * d->KH * d->KW * d->Cin + (cuuint64_t)d->Cin2;
   if (pl.p.b_merged) {     // both planes in one box: (K chunk, BN rows, 2 planes) -> [Bh tile | Bl tile] in shared memory
     const CUtensorMapDataType dt3 = pl.p.prec != MP_PREC_SPLIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     cuuint64_t dims3[3] = {ktot, (cuuint64_t)d->Cout_pad, 2};
     cuuint64_t strides3[2] = {ktot * 2, ktot * 2 * (cuuint64_t)d->Cout_pad};
-    cuuint32_t box3[3] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)pl.p.BN, 2};
+    cuuint32_t box3[3] = {(cuuint32_t)pl.p.CCHUNK, (cuuint32_t)(box_rows ? box_rows : pl.p.BN), 2};
     cuuint32_t estr3[3] = {1, 1, 1};
     CUresult r3 = encode_cached(m, dt3, 3, const_cast<void*>(ptr), dims3, strides3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1806,6 +2041,46 @@ int encode_w_map(CUtensorMap* m, const void* ptr, const mp_conv_desc* d, const P
                              CU_TENSOR_MAP_INTERLEAVE_NONE, pl.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+}
+
+int launch_pair(const mp_conv_desc* d, Plan pl, void* stream) {
+  TcParams& p = pl.p;
+  p.b_bytes = (uint32_t)(p.BN / 2) * p.CCHUNK * 2u;            // each CTA stages half of the weight tile
+  p.stage_bytes = 2u * p.a_bytes + 2u * p.b_bytes;
+  const uint32_t fixed = 1024 + 1024 + 2 * 256 * sizeof(double) + EPI_BYTES + 2048;
+  int stages = (int)((SMEM_LIMIT - fixed) / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  MP_REQUIRE(stages >= 3, "mp_conv_tc: pair kernel does not fit shared memory");
+  p.STAGES = stages;
+  p.epi_tma = 0;
+  p.epi_bytes = EPI_BYTES;
+  p.epi_off = (uint32_t)stages * p.stage_bytes;
+  p.tmem_cols = 512;                                           // two accumulator pairs of 2 x 128 columns
+  p.acc_w = 2 * p.BN;
+  p.dualb = 1;
+  p.sched = nullptr;
+  const uint32_t idesc_fmt = (1u << 4);                        // D = f32, A / B = fp16 (kind::f16) resp. e4m3 (kind::f8f6f4)
+  p.idesc = idesc_fmt | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);     // M = 256 across the pair
+  const uint32_t smem_bytes = fixed + (uint32_t)stages * p.stage_bytes;
+  CUtensorMap ma_hi, ma_lo, mb;
+  if (int e = encode_act_map(&ma_hi, d->in_hi, d, pl)) return e;
+  if (int e = encode_act_map(&ma_lo, d->in_lo, d, pl)) return e;
+  if (int e = encode_w_map(&mb, d->w_hi, d, pl, p.BN / 2)) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  static bool attr_done[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    cudaError_t ae = cudaFuncSetAttribute(k_conv_q8_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    MP_REQUIRE(ae == cudaSuccess, "mp_conv_tc: cannot opt in to %u B shared memory: %s", SMEM_LIMIT, cudaGetErrorString(ae));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int items = (pl.tiles_m / 2) * pl.tiles_n;
+  int clusters = sms / 2;
+  if (clusters > items) clusters = items;
+  k_conv_q8_pair<<<2 * clusters, NUM_THREADS3, smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb, p);
+  MP_LAUNCH_CHECK("mp_conv_tc (pair)");
+  return 0;
 }
 
 // One counter slot for a launch on `stream` (NULL = use the static walk).  Rules that keep concurrently running kernels
@@ -1871,6 +2146,18 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
     const size_t plane = ((size_t)d->KD * d->KH * d->KW * d->Cin + d->Cin2) * d->Cout_pad * 2;
     pl.p.b_merged = (!no_merge && !pl.v1 &&
                      reinterpret_cast<const char*>(d->w_lo) == reinterpret_cast<const char*>(d->w_hi) + plane) ? 1 : 0;
+  }
+  // ---- CTA-pair kernel (cta_group::2) for the fp16 + FP8 convolutions whose tiles pair up (MPB200_TC_PAIR=0 disables it)
+  {
+    const char* pe = getenv("MPB200_TC_PAIR");          // read per launch: tests flip it inside one process
+    const int allow_pair = (pe && !atoi(pe)) ? 0 : 1;
+    const TcParams& q = pl.p;
+    const int ntaps = d->KD * d->KH * d->KW;
+    const bool all_taps = q.tap_mask == (ntaps == 64 ? ~0ull : ((1ull << ntaps) - 1ull));
+    if (allow_pair && d->prec == MP_PREC_F16_Q8 && !pl.slab && !pl.v1 && q.BN == 128 && q.CCHUNK == 64 && q.b_merged &&
+        d->Cin2 == 0 && q.stride == 1 && q.BNb == 1 && pl.tiles_m % 2 == 0 && q.in_c_off == 0 && !d->stats && !q.b_resident &&
+        all_taps && (d->in_C == 0 || d->in_C == d->Cin))
+      return launch_pair(d, pl, stream);
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (int e = encode_act_map(&ma_hi, d->in_hi, d, pl)) return e;

@@ -943,3 +943,39 @@ def test_conv_input_gradient_on_tensor_cores(ops, shape):
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     print("dgrad rel err", err)
     assert err <= 1e-4
+
+
+def test_conv_f16_q8_cta_pair_kernel(ops):
+    """`k_conv_q8_pair` (cta_group::2, M = 256 across an SM pair; taken when the fp16 + FP8 convolution has 128-channel tiles
+    and an even number of position tiles) against the single-CTA kernel (MPB200_TC_PAIR=0) bit for bit -- same MMAs, same
+    K order, same epilogue -- and against fp32."""
+    import os
+    N, Cin, Cout, H, W, k = 4, 512, 512, 64, 64, 3
+    x = rnd(N, Cin, 1, H, W, seed=161) * 1.3
+    r = rnd(N, Cout, 1, H, W, seed=162)
+    w = rnd(Cout, Cin, k, k, seed=163) / math.sqrt(Cin * k * k)
+    b = rnd(Cout, seed=164) * 0.1
+    xcl, rcl = x.permute(0, 2, 3, 4, 1).contiguous(), r.permute(0, 2, 3, 4, 1).contiguous()
+    sx, sr = ops.q8_scale_for(x.abs().max().item()), ops.q8_scale_for(r.abs().max().item())
+    a = ops.Act(tuple(xcl.shape), h16=_f16(xcl).to(DEV), q8=ops.q8_planes(xcl, sx).to(DEV), q8_scale=sx)
+    res = ops.Act(tuple(rcl.shape), h16=_f16(rcl).to(DEV), q8=ops.q8_planes(rcl, sr).to(DEV), q8_scale=sr)
+    pw = ops.pack_conv(w, b, DEV, prec=ops.PREC_F16_Q8)
+    outs = {}
+    saved = os.environ.get("MPB200_TC_PAIR")
+    try:
+        for mode in ("1", "0"):
+            os.environ["MPB200_TC_PAIR"] = mode
+            o, _ = ops.conv(a, pw, res=res, act=ops.ACT_RELU, f32=True, hq=True, out_q8_scale=4.0)
+            o2, _ = ops.conv(a, pw, res=res, act=ops.ACT_RELU, f32=False, split=True)     # last block of the chain: split planes
+            torch.cuda.synchronize()
+            outs[mode] = (o.f32.cpu(), o.h16.cpu(), o.q8.cpu(), (o2.hi.float() + o2.lo.float()).cpu())
+    finally:
+        if saved is None:
+            os.environ.pop("MPB200_TC_PAIR", None)
+        else:
+            os.environ["MPB200_TC_PAIR"] = saved
+    for i in range(4):
+        assert torch.equal(outs["1"][i], outs["0"][i]), i
+    full = F.relu(F.conv2d(x.squeeze(2), w, b, padding=1) + r.squeeze(2))
+    got = outs["1"][0].squeeze(1).permute(0, 3, 1, 2)
+    assert (got - full).abs().max().item() / full.abs().max().item() < 1e-4
