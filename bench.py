@@ -551,7 +551,8 @@ def run_b200(args):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        t = tj.get("k_conv_tc2|32x1x64x64 512->512 k133 s1 (MP_PREC_F16_Q8)") or tj.get("k_conv_tc2|32x1x64x64 512->512 k133 s1")
+        t = tj.get("k_conv_q8_pair|32x1x64x64 512->512 k133 s1 (MP_PREC_F16_Q8, cta_group::2)") or \
+            tj.get("k_conv_tc2|32x1x64x64 512->512 k133 s1 (MP_PREC_F16_Q8)") or tj.get("k_conv_tc2|32x1x64x64 512->512 k133 s1")
         if t:
             traffic = {"dram_bytes_per_launch": t["dram_bytes"], "algorithmic_bytes_per_launch": t["algorithmic_bytes"],
                        "launch": "G2d 512->512 3x3 @64x64 x32 (16 of the step's conv launches)", "source": t["source"]}
@@ -566,8 +567,8 @@ def run_b200(args):
         raw_all = sum(c["flops"] * ps for _, c, ps in fam)
         n_all = sum(c["n"] for _, c, _ in fam)
         ach = fl_all / (ms_all * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_conv_tc2 / k_conv_tc3 (tcgen05 implicit-GEMM conv; split-bf16 x3, fp16 x2 and "
-                                             "fp16 + e4m3 cross-term operand modes)",
+        roof = {"bound": "tensor", "kernel": "k_conv_tc2 / k_conv_tc3 / k_conv_q8_pair (tcgen05 implicit-GEMM conv; split-bf16 x3, "
+                                             "fp16 x2 and fp16 + e4m3 cross-term operand modes, the last one on cta_group::2)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                 "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                 "mma_passes": raw_all / fl_all, "raw_tensor_frac": raw_all / (ms_all * 1e-3) / 1e12 / pk["tf_sustained"],
@@ -586,7 +587,7 @@ def run_b200(args):
     if "conv_tc_q8" in agg:    # fp16 main product + FP8 cross terms (G2d identity res-blocks)
         c = agg["conv_tc_q8"]
         ach = c["flops"] / (c["ms"] * 1e-3) / 1e12
-        extra["conv_tc_f16_q8"] = {"kernel": "k_conv_tc2, MP_PREC_F16_Q8 (G2d res-blocks)", "bound": "tensor", "achieved": ach,
+        extra["conv_tc_f16_q8"] = {"kernel": "k_conv_q8_pair (cta_group::2), MP_PREC_F16_Q8 (G2d res-blocks)", "bound": "tensor", "achieved": ach,
                                    "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
                                    "mma_passes": 2, "raw_tensor_frac": 2 * ach / pk["tf_sustained"], "launches": c["n"],
                                    "ms": c["ms"], "share_of_step": c["ms"] / step_ms,
