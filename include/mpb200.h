@@ -57,6 +57,11 @@ int mp_avgpool2_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, 
  * up_d = 1 keeps D (2-D bilinear).  Source: in_f32 if non-NULL else split.  Either output may be NULL. */
 int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out_f32, void* out_hi,
                             void* out_lo, int N, int D, int H, int W, int C, int up_d, void* stream);
+/* The same bilinear x2 (2-D, align_corners=True) from split planes to the F16_Q8 plane pair (fp16 plane + FP8 byte plane
+ * written with the per-tensor power-of-two q8_scale): input of the fp16 + FP8 convolutions of G2d's up-blocks
+ * (model.py:733-743).  C % 64 == 0. */
+int mp_upsample2x_bilinear_hq(const void* in_hi, const void* in_lo, void* out_h16, void* out_q8, int N, int H, int W, int C,
+                              float q8_scale, void* stream);
 /* nn.Upsample(scale_factor=(sd,sh,sw)) nearest on CL fp32 (model.py:427-433). */
 int mp_upsample_nearest_cl(const float* in, float* out_f32, void* out_hi, void* out_lo, int N, int D, int H, int W,
                            int C, int sd, int sh, int sw, void* stream);

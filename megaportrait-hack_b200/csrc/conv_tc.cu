@@ -987,7 +987,8 @@ __device__ __forceinline__ void umma_commit_pair_e(uint32_t bar) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS3, 1)
 k_conv_q8_pair(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_a2_hi,
+               const __grid_constant__ CUtensorMap map_a2_lo, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1006,7 +1007,7 @@ k_conv_q8_pair(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   auto tfull_bar = [&](int b) { return bars + (2 * p.STAGES + b) * 8; };
   auto tempty_bar = [&](int b) { return bars + (2 * p.STAGES + 2 + b) * 8; };
   const int taps = p.KD * p.KH * p.KW;
-  const int num_kb = taps * p.num_cchunks;
+  const int num_kb = taps * p.num_cchunks + p.num_cchunks2;      // + the K chunks of a fused 1x1 shortcut
   const int items = (p.total_tiles / p.tiles_n / 2) * p.tiles_n;     // (pairs of position tiles) x channel tiles
 
   if (threadIdx.x == 0) {
@@ -1068,6 +1069,17 @@ k_conv_q8_pair(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_3d_2sm(sa + 2 * p.a_bytes, &map_b, fb, tap * p.Cin + c0, n0 + (int)rank * (p.BN / 2), 0);
             if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
           }
+        }
+        for (int cc = 0; cc < p.num_cchunks2; ++cc) {        // fused 1x1 shortcut: centre tap of the second source
+          mbar_wait(empty_bar(s), ph_bit);
+          const uint32_t sa = smem_base + s * p.stage_bytes;
+          const uint32_t fb = mapa_shared(full_bar(s), 0);
+          if (leader) mbar_expect_tx(full_bar(s), tx_both);
+          const int c0 = cc * p.CCHUNK;
+          tma_load_5d_2sm(sa, &map_a2_hi, fb, c0 + p.in2_c_off, w0, h0, d0, n);
+          tma_load_5d_2sm(sa + p.a_bytes, &map_a2_lo, fb, c0 + p.in2_c_off, w0, h0, d0, n);
+          tma_load_3d_2sm(sa + 2 * p.a_bytes, &map_b, fb, p.k2_off + c0, n0 + (int)rank * (p.BN / 2), 0);
+          if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
         }
       }
     }
@@ -2066,6 +2078,12 @@ int launch_pair(const mp_conv_desc* d, Plan pl, void* stream) {
   if (int e = encode_act_map(&ma_hi, d->in_hi, d, pl)) return e;
   if (int e = encode_act_map(&ma_lo, d->in_lo, d, pl)) return e;
   if (int e = encode_w_map(&mb, d->w_hi, d, pl, p.BN / 2)) return e;
+  CUtensorMap ma2_hi = ma_hi, ma2_lo = ma_lo;
+  if (d->Cin2 > 0) {
+    MP_REQUIRE((((uintptr_t)d->in2_hi | (uintptr_t)d->in2_lo) & 15) == 0, "mp_conv_tc: second source must be 16-byte aligned");
+    if (int e = encode_act2_map(&ma2_hi, d->in2_hi, d, pl)) return e;
+    if (int e = encode_act2_map(&ma2_lo, d->in2_lo, d, pl)) return e;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   static bool attr_done[64] = {false};
@@ -2078,7 +2096,7 @@ int launch_pair(const mp_conv_desc* d, Plan pl, void* stream) {
   const int items = (pl.tiles_m / 2) * pl.tiles_n;
   int clusters = sms / 2;
   if (clusters > items) clusters = items;
-  k_conv_q8_pair<<<2 * clusters, NUM_THREADS3, smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb, p);
+  k_conv_q8_pair<<<2 * clusters, NUM_THREADS3, smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb, ma2_hi, ma2_lo, p);
   MP_LAUNCH_CHECK("mp_conv_tc (pair)");
   return 0;
 }
@@ -2155,7 +2173,7 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
     const int ntaps = d->KD * d->KH * d->KW;
     const bool all_taps = q.tap_mask == (ntaps == 64 ? ~0ull : ((1ull << ntaps) - 1ull));
     if (allow_pair && d->prec == MP_PREC_F16_Q8 && !pl.slab && !pl.v1 && q.BN == 128 && q.CCHUNK == 64 && q.b_merged &&
-        d->Cin2 == 0 && q.stride == 1 && q.BNb == 1 && pl.tiles_m % 2 == 0 && q.in_c_off == 0 && !d->stats && !q.b_resident &&
+        (d->Cin2 == 0 || q.stride2 == 1) && q.stride == 1 && q.BNb == 1 && pl.tiles_m % 2 == 0 && q.in_c_off == 0 && !d->stats && !q.b_resident &&
         all_taps && (d->in_C == 0 || d->in_C == d->Cin))
       return launch_pair(d, pl, stream);
   }

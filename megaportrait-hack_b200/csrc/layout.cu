@@ -279,9 +279,14 @@ k_upsample2x_bilinear_split8(const bf16* __restrict__ in_hi, const bf16* __restr
 // (in-1)/(out-1) < 1/2, so the four outputs draw their taps from a 3 x 3 input patch: 18 loads instead of 32, and the
 // bf16 pair -> fp32 joins (the bulk of the instruction stream: the one-output-per-thread kernel is issue-bound, ncu
 // issue-active 81 %) are done once per patch element.  Tap order and weights are exactly those of the kernel above.
+// HQ = true: the outputs are the F16_Q8 plane pair instead (fp16 plane `out_hi`, FP8 byte plane `out_lo` written with the
+// per-tensor power-of-two `q8_scale`), feeding the fp16 + FP8 cross-term convolutions of the G2d up-blocks.
+template <bool HQ>
 __global__ void __launch_bounds__(256)
-k_upsample2x_bilinear_split8_2x2(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
-                                 bf16* __restrict__ out_lo, int H, int W, int C) {
+k_upsample2x_bilinear_split8_2x2(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, void* __restrict__ out_hi_v,
+                                 void* __restrict__ out_lo_v, int H, int W, int C, float q8_scale) {
+  bf16* out_hi = reinterpret_cast<bf16*>(out_hi_v);
+  bf16* out_lo = reinterpret_cast<bf16*>(out_lo_v);
   // grid: x = chunks of (input column j, c8) pairs, y = input row i (output rows 2i, 2i+1), z = sample
   const int C8 = C >> 3;
   const int Ho = H * 2, Wo = W * 2;
@@ -321,6 +326,7 @@ k_upsample2x_bilinear_split8_2x2(const bf16* __restrict__ in_hi, const bf16* __r
     // taps (h0,w0), (h0,w1), (h1,w0), (h1,w1) in this order, weights (1-lh)(1-lw), (1-lh)lw, lh(1-lw), lh*lw
     const float w00 = (1.f - lh) * (1.f - lw), w01 = (1.f - lh) * lw, w10 = lh * (1.f - lw), w11 = lh * lw;
     bf16x8v oh, ol;
+    float accs[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float v00 = shift ? top[1][k] : top[0][k], v01 = shift ? top[2][k] : top[1][k];
@@ -329,9 +335,21 @@ k_upsample2x_bilinear_split8_2x2(const bf16* __restrict__ in_hi, const bf16* __r
       acc += w01 * v01;
       acc += w10 * v10;
       acc += w11 * v11;
-      mp_split2(acc, oh.v[k], ol.v[k]);
+      accs[k] = acc;
+      if (!HQ) mp_split2(acc, oh.v[k], ol.v[k]);
     }
-    const int64_t o = ((((int64_t)n * Ho + ho) * Wo + wo) * C8 + c8) * 8;
+    const int64_t pos = ((int64_t)n * Ho + ho) * Wo + wo;
+    const int64_t o = (pos * C8 + c8) * 8;
+    if (HQ) {
+      f16x8 h;
+      uint2 a8, al8;
+      mp_hq_pack8(accs, h, a8, al8, q8_scale);
+      *reinterpret_cast<f16x8*>(reinterpret_cast<f16*>(out_hi_v) + o) = h;
+      uint8_t* q = reinterpret_cast<uint8_t*>(out_lo_v) + 2 * pos * C + mp_q8_off(c8 * 8);
+      *reinterpret_cast<uint2*>(q) = a8;
+      *reinterpret_cast<uint2*>(q + 64) = al8;
+      return;
+    }
     *reinterpret_cast<bf16x8v*>(out_hi + o) = oh;
     *reinterpret_cast<bf16x8v*>(out_lo + o) = ol;
   };
@@ -354,8 +372,8 @@ extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, c
                                                                        (bf16*)out_hi, (bf16*)out_lo, H, W, C);
     } else {
       dim3 g4((unsigned)((W * (C / 8) + 255) / 256), (unsigned)H, (unsigned)N);
-      k_upsample2x_bilinear_split8_2x2<<<g4, 256, 0, mp_stream(stream)>>>((const bf16*)in_hi, (const bf16*)in_lo,
-                                                                           (bf16*)out_hi, (bf16*)out_lo, H, W, C);
+      k_upsample2x_bilinear_split8_2x2<false><<<g4, 256, 0, mp_stream(stream)>>>((const bf16*)in_hi, (const bf16*)in_lo,
+                                                                                  out_hi, out_lo, H, W, C, 1.f);
     }
     MP_LAUNCH_CHECK("mp_upsample2x_linear_cl");
     return 0;
@@ -370,6 +388,19 @@ extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, c
                                                                       out_f32, (bf16*)out_hi, (bf16*)out_lo, N, D, H, W,
                                                                       C, up_d);
   MP_LAUNCH_CHECK("mp_upsample2x_linear_cl");
+  return 0;
+}
+
+// nn.Upsample(x2, bilinear, align_corners=True) from split-bf16 planes to the F16_Q8 plane pair (G2d up-blocks)
+extern "C" int mp_upsample2x_bilinear_hq(const void* in_hi, const void* in_lo, void* out_h16, void* out_q8, int N, int H, int W,
+                                         int C, float q8_scale, void* stream) {
+  MP_REQUIRE(in_hi && in_lo && out_h16 && out_q8, "mp_upsample2x_bilinear_hq: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && H > 0 && H * 2 <= 65535 && W > 0 && C > 0 && C % 64 == 0 && q8_scale > 0.f,
+             "mp_upsample2x_bilinear_hq: bad dims (channels in multiples of 64)");
+  dim3 g4((unsigned)((W * (C / 8) + 255) / 256), (unsigned)H, (unsigned)N);
+  k_upsample2x_bilinear_split8_2x2<true><<<g4, 256, 0, mp_stream(stream)>>>((const bf16*)in_hi, (const bf16*)in_lo, out_h16, out_q8,
+                                                                               H, W, C, q8_scale);
+  MP_LAUNCH_CHECK("mp_upsample2x_bilinear_hq");
   return 0;
 }
 

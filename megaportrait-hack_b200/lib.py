@@ -125,6 +125,7 @@ _SIGNATURES = {
     "mp_split": (c_int, [_P, _P, _P, c_int64, _P]),
     "mp_avgpool2_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_upsample2x_linear_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_upsample2x_bilinear_hq": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     "mp_upsample_nearest_cl": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_gn_stats": (c_int, [_P, _P, c_int, c_int64, c_int, c_int, _P]),
     "mp_gn_finalize": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_float, _P]),

@@ -27,6 +27,8 @@ from .ops import ACT_NONE, ACT_RELU, ACT_RELU_TANH, ACT_SIGMOID, ACT_TANH, Act
 
 # G2d's identity res-blocks on the fp16 + FP8 cross-term convolution (MPB200_G2D_PREC=split selects three-pass split-bf16)
 _Q8_ENABLED = os.environ.get("MPB200_G2D_PREC", "q8") != "split"
+# ... and its first two up-blocks (MPB200_G2D_UP_PREC=split keeps them on three-pass split-bf16)
+_Q8_UP = os.environ.get("MPB200_G2D_UP_PREC", "q8") != "split"
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")   # model.py:51 (kept for callers that read it)
 
@@ -408,9 +410,16 @@ class ResBlock2D(nn.Module, _Packed):
                              self._bn(self.shortcut[1]), self.shortcut[1].eps)
         # identity-shortcut blocks inside G2d run the fp16 + FP8 cross-term convolution (`G2d` sets `_mp_q8`): two
         # pass-units instead of three at the same end-to-end accuracy (tests/precision_study.py)
-        prec = ops.PREC_F16_Q8 if (sc is None and getattr(self, "_mp_q8", False) and _Q8_ENABLED) else ops.PREC_SPLIT_BF16
+        q8 = getattr(self, "_mp_q8", False) and _Q8_ENABLED
+        if sc is not None and q8:
+            # up-blocks (round 2): the same format with the fused shortcut; channel counts must be 64-multiples on both sources
+            q8 = self.conv1.in_channels % 64 == 0 and self.conv1.out_channels % 128 == 0
+        prec = ops.PREC_F16_Q8 if q8 else ops.PREC_SPLIT_BF16
         c1, c2 = self._pack_pair(prec, sc)
-        return {"c1": c1, "c2": c2, "fused_sc": sc is not None, "q8": prec == ops.PREC_F16_Q8}
+        P = {"c1": c1, "c2": c2, "fused_sc": sc is not None, "q8": q8}
+        if q8 and sc is not None:       # kept beside the FP8 plans: the fall-back of G2d's range check and stand-alone calls
+            P["c1_split"], P["c2_split"] = self._pack_pair(ops.PREC_SPLIT_BF16, sc)
+        return P
 
     def _pack_pair(self, prec, sc=None):
         dev = self.conv1.weight.device
@@ -424,6 +433,9 @@ class ResBlock2D(nn.Module, _Packed):
         per-tensor scales of the FP8 byte planes this block writes (its inner activation, its output)."""
         P = self._plan()
         if P["q8"] and x.q8 is not None:
+            if P["fused_sc"]:    # up-block: x (the upsampled tensor) and t share one byte-plane scale (one cross accumulator)
+                t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, hq=True, out_q8_scale=x.q8_scale)
+                return ops.conv(t, P["c2"], src2=x, act=ACT_RELU, f32=f32, split=split)
             t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, hq=True, out_q8_scale=q8_scales[0])
             return ops.conv(t, P["c2"], res=x, act=ACT_RELU, f32=f32, split=split and not hq_out, hq=hq_out,
                             out_q8_scale=q8_scales[1])
@@ -431,6 +443,8 @@ class ResBlock2D(nn.Module, _Packed):
             if "c1_split" not in P:
                 P["c1_split"], P["c2_split"] = self._pack_pair(ops.PREC_SPLIT_BF16)
             t, _ = ops.conv(x, P["c1_split"], act=ACT_RELU, f32=False, split=True)
+            if P["fused_sc"]:
+                return ops.conv(t, P["c2_split"], src2=x, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
             return ops.conv(t, P["c2_split"], res=x, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
         t, _ = ops.conv(x, P["c1"], act=ACT_RELU, f32=False, split=True)
         if P["fused_sc"]:
@@ -462,6 +476,9 @@ class G2d(nn.Module, _Packed):
                                        ResBlock2D(128, 64))
         self.final_conv = nn.Sequential(nn.GroupNorm(num_groups=32, num_channels=64), nn.ReLU(inplace=True),
                                         nn.Conv2d(64, 3, kernel_size=3, padding=1), nn.Sigmoid())
+        if _Q8_UP:                # up-blocks 512->256 @128^2 and 256->128 @256^2 on the FP8 cross-term format as well
+            self.upsample1[1]._mp_q8 = True
+            self.upsample2[1]._mp_q8 = True
 
     def _sig_extra(self):
         return None
@@ -503,20 +520,40 @@ class G2d(nn.Module, _Packed):
             h = h2
         return h
 
+    def _up_q8(self, i: int) -> bool:
+        blk = (self.upsample1, self.upsample2, self.upsample3)[i][1]
+        return bool(blk._plan()["q8"] and blk._plan()["fused_sc"])
+
     def _q8_calibrate(self, x: Act, P) -> None:
-        """One pass of the res-block chain with unit scales to measure every F16_Q8 tensor's largest magnitude, then
-        per-tensor power-of-two scales for the FP8 byte planes (ops.q8_scale_for); tensors near the fp16 range switch
-        the chain to the split-bf16 plans.  Runs once per plan, outside CUDA-graph capture (one host sync)."""
+        """One pass of the res-block chain (and of the up-blocks that use the format) with unit scales to measure every
+        F16_Q8 tensor's largest magnitude, then per-tensor power-of-two scales for the FP8 byte planes
+        (ops.q8_scale_for); tensors near the fp16 range switch the stage to the split-bf16 plans.  Runs once per plan,
+        outside CUDA-graph capture (one host sync)."""
         ones = [1.0] * (1 + 2 * len(self.res_blocks))
         h, _ = ops.conv(x, P["in"], f32=False, split=False, hq=True)
         seen = [h]
-        self._res_chain(h, ones, collect=seen)
-        amax = torch.stack([t.h16.float().abs().amax() for t in seen]).cpu().tolist()
-        ok = all(a == a and a < self.Q8_AMAX_LIMIT for a in amax)       # NaN / inf / near-overflow -> fall back
+        h = self._res_chain(h, ones, collect=seen)
+        up_seen = []
+        for i, up in enumerate((self.upsample1, self.upsample2)):
+            if not self._up_q8(i):
+                break
+            Pb = up[1]._plan()
+            u = ops.upsample2x_bilinear_hq(h, 1.0)
+            t, _ = ops.conv(u, Pb["c1"], act=ACT_RELU, f32=False, hq=True)
+            h, _ = ops.conv(t, Pb["c2"], src2=u, act=ACT_RELU, f32=False, split=True)
+            up_seen += [u, t]
+        amax = torch.stack([t.h16.float().abs().amax() for t in seen + up_seen]).cpu().tolist()
+        a_chain, a_up = amax[:len(seen)], amax[len(seen):]
+        ok = all(a == a and a < self.Q8_AMAX_LIMIT for a in a_chain)       # NaN / inf / near-overflow -> fall back
         P["q8_amax"] = amax
         # (the last block writes split-bf16 planes: its output has no byte plane, the trailing 1.0 is never used)
-        P["q8_scales"] = [ops.q8_scale_for(a) for a in amax] + [1.0] if ok else None
+        P["q8_scales"] = [ops.q8_scale_for(a) for a in a_chain] + [1.0] if ok else None
         P["q8_ok"] = ok
+        # up-blocks: the upsampled tensor and the block's inner activation share ONE scale (fused shortcut: one accumulator)
+        P["q8_up"] = []
+        for j in range(0, len(a_up), 2):
+            good = ok and all(a == a and a < self.Q8_AMAX_LIMIT for a in a_up[j:j + 2])
+            P["q8_up"].append(min(ops.q8_scale_for(a_up[j]), ops.q8_scale_for(a_up[j + 1])) if good else None)
 
     def _forward_cl(self, x: Act) -> torch.Tensor:
         """x: split channels-last [N,1,64,64,96] -> RGB NCHW fp32 [N,3,512,512]."""
@@ -536,9 +573,14 @@ class G2d(nn.Module, _Packed):
             for blk in self.res_blocks:
                 h, _ = blk._forward_cl(h)
         st = None
+        up_scales = P.get("q8_up", []) if q8 else []
         for i, up in enumerate((self.upsample1, self.upsample2, self.upsample3)):
-            u = ops.upsample2x_linear(h, 1, f32=False, split=True)
             last = i == 2
+            s_up = up_scales[i] if i < len(up_scales) else None
+            if s_up is not None and self._up_q8(i):
+                u = ops.upsample2x_bilinear_hq(h, s_up)
+            else:
+                u = ops.upsample2x_linear(h, 1, f32=False, split=True)
             h, st = up[1]._forward_cl(u, f32=last, split=not last, stats_groups=32 if last else 0)
         ab = ops.gn_finalize(st, h.shape, 32, *P["gn"])
         return ops.gn_relu_conv3x3_head(h, ab, P["head_w"], P["head_b"], ACT_SIGMOID)

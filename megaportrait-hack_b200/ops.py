@@ -211,6 +211,21 @@ def upsample2x_linear(a: Act, up_d: int, f32: bool = False, split: bool = True) 
 
 
 @_profiled
+def upsample2x_bilinear_hq(a: Act, q8_scale: float = 1.0) -> Act:
+    """nn.Upsample(x2, bilinear, align_corners=True) from split planes to the F16_Q8 plane pair (2-D, C % 64 == 0)."""
+    N, D, H, W, C = a.shape
+    if D != 1 or a.hi is None:
+        raise RuntimeError("upsample2x_bilinear_hq: needs a 2-D split-bf16 activation")
+    out = _alloc((N, 1, H * 2, W * 2, C), a.device, False, False, True, True)
+    out.q8_scale = float(q8_scale)
+    L = _lib.load()
+    _lib.check(L.mp_upsample2x_bilinear_hq(_p(a.hi), _p(a.lo), _p(out.h16), _p(out.q8), N, H, W, C, float(q8_scale), _stream()),
+               "mp_upsample2x_bilinear_hq")
+    _count()
+    return out
+
+
+@_profiled
 def upsample_nearest(a: Act, scale: Sequence[int], f32: bool = False, split: bool = True) -> Act:
     N, D, H, W, C = a.shape
     sd, sh, sw = scale
@@ -397,7 +412,7 @@ def pack_stem3x3_f16(weight: torch.Tensor, bias: Optional[torch.Tensor], device=
 
 
 def _conv_q8(a: Act, pw: PackedConv, res: Optional[Act], act: int, f32: bool, split: bool, stats_groups: int,
-             hq: bool, out_q8_scale: float = 1.0) -> Tuple[Act, Optional[torch.Tensor]]:
+             hq: bool, out_q8_scale: float = 1.0, src2: Optional[Act] = None) -> Tuple[Act, Optional[torch.Tensor]]:
     """Convolutions around the F16_Q8 operand format (fp16 plane + FP8 byte plane): `pw.prec == PREC_F16_Q8` consumes it
     (fp16 main product + FP8 cross terms), `hq=True` produces it -- from either kind of convolution, so the format change
     rides on an epilogue.  Stride 1, no channel windows; the residual may be fp32, split or F16_Q8."""
@@ -406,8 +421,15 @@ def _conv_q8(a: Act, pw: PackedConv, res: Optional[Act], act: int, f32: bool, sp
         raise RuntimeError("conv: a PREC_F16_Q8 convolution needs an activation with fp16 + FP8 planes")
     if not q8_in and a.hi is None:
         ensure_split(a)
-    if pw.Cin2 or pw.Cin != a.C or (hq and split):
+    if pw.Cin != a.C or (hq and split) or (pw.Cin2 and not q8_in):
         raise RuntimeError("conv: unsupported F16_Q8 configuration")
+    if pw.Cin2:
+        # fused 1x1 shortcut over a second F16_Q8 source on the same grid; both byte planes share one cross-term scale, so the
+        # two sources must have been written with the same per-tensor scale
+        if src2 is None or src2.q8 is None or src2.shape[:4] != a.shape[:4] or src2.C != pw.Cin2:
+            raise RuntimeError("conv: the fused F16_Q8 shortcut needs a second F16_Q8 source on the same grid")
+        if src2.q8_scale != a.q8_scale:
+            raise RuntimeError("conv: the two sources of a fused F16_Q8 shortcut must share the byte-plane scale")
     N, D, H, W, C = a.shape
     out = _alloc((N, D, H, W, pw.Cout), a.device, f32, split, hq, hq)
     out.q8_scale = float(out_q8_scale) if hq else 1.0
@@ -436,8 +458,11 @@ def _conv_q8(a: Act, pw: PackedConv, res: Optional[Act], act: int, f32: bool, sp
     d.KD, d.KH, d.KW = pw.k
     d.Cout_pad, d.gn_groups, d.act = pw.Cout_pad, stats_groups, act
     d.stride, d.in_C, d.out_C = 1, C, pw.Cout
+    if pw.Cin2:
+        d.Cin2, d.in2_C, d.in2_c_off, d.stride2 = pw.Cin2, src2.C, 0, 1
+        d.in2_hi, d.in2_lo = _p(src2.h16), _p(src2.q8)
     L = _lib.load()
-    flops = 2 * N * D * H * W * pw.Cout * pw.Cin * pw.k[0] * pw.k[1] * pw.k[2]
+    flops = 2 * N * D * H * W * pw.Cout * (pw.Cin * pw.k[0] * pw.k[1] * pw.k[2] + pw.Cin2)
     with _Prof(("conv_tc_q8" if q8_in else "conv_tc") + f"|{N}x{D}x{H}x{W} {pw.Cin}->{pw.Cout} k{pw.k[0]}{pw.k[1]}{pw.k[2]} s1",
                flops):
         _lib.check(L.mp_conv_tc(ctypes.byref(d), _stream()), "mp_conv_tc")
@@ -470,7 +495,7 @@ def conv(a: Act, pw: PackedConv, res: Optional[Act] = None, act: int = ACT_NONE,
     `stride` (1|2) applies to H and W.  `in_c_off` selects the window [in_c_off, in_c_off + pw.Cin) of a's channels;
     `out` / `out_c_off` write into the channel window of an existing activation (grouped convolutions)."""
     if pw.prec == PREC_F16_Q8 or hq:
-        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale)
+        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale, src2)
     half = pw.prec == PREC_F16X2
     if half:
         if a.h16 is None:

@@ -101,6 +101,15 @@ def avgpool2(a, pool_d, f32=True, split=False):
     return _mk(_to_cl(y), f32, split)
 
 
+def upsample2x_bilinear_hq(a, q8_scale=1.0):
+    x = _to_ncdhw(_val(a))
+    y = _to_cl(F.interpolate(x.squeeze(2), scale_factor=2, mode="bilinear", align_corners=True).unsqueeze(2)).contiguous()
+    out = _mk(y, False, False, True)
+    out.q8 = ops.q8_planes(y, q8_scale)
+    out.q8_scale = float(q8_scale)
+    return out
+
+
 def upsample2x_linear(a, up_d, f32=False, split=True):
     x = _to_ncdhw(_val(a))
     if up_d == 1:
@@ -157,17 +166,24 @@ def affine_act(a, ab, res=None, act=ops.ACT_NONE, f32=False, split=True):
     return _mk(_act(v, act), f32, split)
 
 
-def _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale=1.0):
+def _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale=1.0, src2=None):
     """fp16 main product + FP8 cross terms (PREC_F16_Q8) and / or F16_Q8 output planes, as the kernel computes them."""
     kd, kh, kw = pw.k
     pad = (kd // 2, kh // 2, kw // 2)
-    shape_w = lambda m: m[: pw.Cout].reshape(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3).contiguous()
+    km = kd * kh * kw * pw.Cin                       # K of the main operand; a fused 1x1 shortcut appends Cin2 columns
+    shape_w = lambda m: m[: pw.Cout, :km].reshape(pw.Cout, kd, kh, kw, pw.Cin).permute(0, 4, 1, 2, 3).contiguous()
+    shape_s = lambda m: m[: pw.Cout, km:].reshape(pw.Cout, pw.Cin2, 1, 1, 1).contiguous()
     if pw.prec == ops.PREC_F16_Q8:
         wh = pw.w_hi.view(torch.float16).float()
         wl8, w8 = _q8_decode(pw.w_lo)
         a8, al8 = _q8_decode(a.q8)
         y = F.conv3d(_to_ncdhw(a.h16.float()), shape_w(wh), None, padding=pad)
         corr = F.conv3d(_to_ncdhw(a8), shape_w(wl8), None, padding=pad) + F.conv3d(_to_ncdhw(al8), shape_w(w8), None, padding=pad)
+        if pw.Cin2:
+            assert src2 is not None and src2.q8_scale == a.q8_scale
+            s8, sl8 = _q8_decode(src2.q8)
+            y = y + F.conv3d(_to_ncdhw(src2.h16.float()), shape_s(wh))
+            corr = corr + F.conv3d(_to_ncdhw(s8), shape_s(wl8)) + F.conv3d(_to_ncdhw(sl8), shape_s(w8))
         y = (y + corr * (pw.corr_scale / a.q8_scale)) * pw.acc_scale
         if pw.bias is not None:
             y = y + pw.bias.view(1, -1, 1, 1, 1)
@@ -189,7 +205,7 @@ def _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale=1.0):
 def conv(a, pw, res=None, act=ops.ACT_NONE, f32=True, split=False, stats_groups=0, mode=None, stride=1, in_c_off=0,
          out=None, out_c_off=0, h16=False, src2=None, stride2=1, in2_c_off=0, hq=False, out_q8_scale=1.0):
     if pw.prec == ops.PREC_F16_Q8 or hq:
-        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale)
+        return _conv_q8(a, pw, res, act, f32, split, stats_groups, hq, out_q8_scale, src2)
     half = pw.prec == ops.PREC_F16X2
     kd, kh, kw = pw.k
     if half:     # two-pass fp16: one fp16 activation plane, fp16 hi + scaled fp16 lo weights
@@ -320,7 +336,7 @@ def blur_subsample(x, kernel2d, step):
     return y[:, :, ::step, ::step].contiguous()
 
 
-_NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample_nearest", "new_stats",
+_NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
           "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3", "from_nchw_pad16",
           "im2col3x3_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]

@@ -979,3 +979,60 @@ def test_conv_f16_q8_cta_pair_kernel(ops):
     full = F.relu(F.conv2d(x.squeeze(2), w, b, padding=1) + r.squeeze(2))
     got = outs["1"][0].squeeze(1).permute(0, 3, 1, 2)
     assert (got - full).abs().max().item() / full.abs().max().item() < 1e-4
+
+
+def test_upsample_bilinear_f16_q8_output(ops):
+    """`mp_upsample2x_bilinear_hq`: bilinear x2 (align_corners=True) from split planes straight into the F16_Q8 plane pair
+    (fp16 plane + FP8 byte plane with a per-tensor scale) = host packer applied to the split-output kernel's result."""
+    x = rnd(2, 128, 1, 12, 20, seed=171) * 3
+    a = ops.from_nchw(x.to(DEV))
+    ref = ops.upsample2x_linear(a, 1, f32=False, split=True)
+    val = (ref.hi.float() + ref.lo.float()).cpu()
+    want = F.interpolate(x.squeeze(2), scale_factor=2, mode="bilinear", align_corners=True)
+    for scale in (1.0, 8.0):
+        got = ops.upsample2x_bilinear_hq(a, scale)
+        assert got.q8_scale == scale and got.shape == ref.shape
+        full = got.h16.float().cpu() + _q8_decode(got.q8.cpu())[1] / (2048.0 * scale)
+        assert (full.squeeze(1).permute(0, 3, 1, 2) - want).abs().max().item() <= 4e-5 * want.abs().max().item()
+        # fp16 plane = RNE of the fp32 interpolation result; compare through the split-output kernel (same arithmetic, then
+        # rounded to 16 mantissa bits): differences are at most one fp16 ulp at rounding ties
+        assert (got.h16.float().cpu() - val).abs().max().item() <= 2.0 ** -10 * val.abs().max().item()
+        x8 = _q8_decode(got.q8.cpu())[0] / scale
+        assert (x8 - val).abs().max().item() <= val.abs().max().item() * 2.0 ** -4
+
+
+@pytest.mark.parametrize("pair", ["1", "0"], ids=["cta_pair", "single_cta"])
+def test_conv_f16_q8_fused_shortcut(ops, pair):
+    """G2d up-block tail on the FP8 cross-term format: relu(conv3x3(t) + conv1x1(x) + b) with the shortcut fused into the
+    accumulator as extra K chunks from a second F16_Q8 source (both sources share the byte-plane scale), on the CTA-pair
+    kernel and on the single-CTA kernel; against fp32."""
+    import os
+    N, C1, C2, Cout, H, W = 4, 256, 512, 256, 64, 64
+    t = F.relu(rnd(N, C1, 1, H, W, seed=181)) * 1.5
+    x = rnd(N, C2, 1, H, W, seed=182) * 2.0
+    w = rnd(Cout, C1, 3, 3, seed=183) / math.sqrt(C1 * 9)
+    ws = rnd(Cout, C2, 1, 1, seed=184) / math.sqrt(C2)
+    b, bs = rnd(Cout, seed=185) * 0.1, rnd(Cout, seed=186) * 0.1
+    s = min(ops.q8_scale_for(t.abs().max().item()), ops.q8_scale_for(x.abs().max().item()))
+    mk = lambda v: ops.Act(tuple(v.permute(0, 2, 3, 4, 1).shape), h16=_f16(v.permute(0, 2, 3, 4, 1).contiguous()).to(DEV),
+                           q8=ops.q8_planes(v.permute(0, 2, 3, 4, 1).contiguous(), s).to(DEV), q8_scale=s)
+    pw = ops.pack_conv(w, b, DEV, prec=ops.PREC_F16_Q8, shortcut=(ws, bs))
+    saved = os.environ.get("MPB200_TC_PAIR")
+    os.environ["MPB200_TC_PAIR"] = pair
+    try:
+        out, _ = ops.conv(mk(t), pw, src2=mk(x), act=ops.ACT_RELU, f32=True, split=True)
+        torch.cuda.synchronize()
+    finally:
+        if saved is None:
+            os.environ.pop("MPB200_TC_PAIR", None)
+        else:
+            os.environ["MPB200_TC_PAIR"] = saved
+    ref = F.relu(F.conv2d(t.squeeze(2), w, b, padding=1) + F.conv2d(x.squeeze(2), ws, bs))
+    got = out.f32.cpu().squeeze(1).permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    print(f"q8 fused shortcut ({'pair' if pair == '1' else 'single'}): rel err {err:.2e}")
+    assert err < 1e-4
+    with pytest.raises(RuntimeError, match="share the byte-plane scale"):
+        a2 = mk(x)
+        a2.q8_scale = s * 2
+        ops.conv(mk(t), pw, src2=a2, act=ops.ACT_RELU, f32=True)
