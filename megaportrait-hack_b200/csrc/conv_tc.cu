@@ -18,7 +18,7 @@
 //
 // Kernels: k_conv_tc2 (general: persistent, BN up to 256, smem ring of 2-8 stages, optional resident weights),
 // k_conv_tc3 (slab: 3x3(x3) with Cout <= 128, one (MT*16+2) x 8 pixel slab serves the three vertical taps of MT
-// accumulators), k_conv_tc (first generation, kept for A/B runs).  Warp roles in the persistent kernels (352 threads):
+// accumulators), k_conv_q8_pair (cta_group::2 pairs for the fp16 + FP8 format).  Warp roles in the persistent kernels (352 threads):
 // warp 0 = TMA producer + tile scheduler (tile ids drawn from a global atomic counter, published to the other roles
 // through a shared-memory queue), warp 1 (+ warp 10 when a tile has two independently issued accumulators) = MMA issue,
 // whole warp converged with one elected lane issuing, warps 2..9 = epilogue (TMEM -> registers -> bias / residual /
@@ -40,7 +40,6 @@ int mp_conv_validate(const mp_conv_desc* d, const char* who);
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 192;    // v1 kernel
 constexpr int NUM_THREADS2 = 320;   // v2: producer + MMA + 8 epilogue warps
 constexpr int NUM_THREADS3 = 352;   // v3 (slab): + a second MMA-issuing warp (one accumulator each when MT = 2)
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
@@ -177,27 +176,8 @@ __device__ __forceinline__ void load_b(const TcParams& p, uint32_t dst, const CU
   }
 }
 
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo, uint32_t layout_type) {
-  // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;                       // LBO is ignored for swizzled K-major operands; canonical value 1
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Lean issue path: the upper descriptor word (SBO | version | layout) is constant per kernel, the lower word is
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1
+// [46,48) | layout [61,64).  The upper word (SBO | version | layout) is constant per kernel, the lower word is
 // (smem address >> 4) | LBO; stepping 16 bf16 along K inside the swizzle atom adds 2 to the lower word.
 __device__ __forceinline__ uint32_t desc_hi_word(uint32_t sbo, uint32_t layout_type) {
   return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
@@ -296,9 +276,6 @@ __device__ __forceinline__ void umma_chunk_dyn(int ksteps, uint32_t tmem_d, uint
   if (ksteps == 4) umma_chunk<4>(tmem_d, a_hi, a_lo, b_hi, b_lo, hi, idesc, acc_first);
   else if (ksteps == 2) umma_chunk<2>(tmem_d, a_hi, a_lo, b_hi, b_lo, hi, idesc, acc_first);
   else umma_chunk<1>(tmem_d, a_hi, a_lo, b_hi, b_lo, hi, idesc, acc_first);
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   uint32_t r[16];
@@ -1414,209 +1391,6 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   }
 }
 
-// ------------------------------------------------------------------------------------------------ kernel v1
-// First-generation kernel (one tile per CTA, epilogue not overlapped); kept for A/B runs (MPB200_TC_V1=1).
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + p.STAGES * p.stage_bytes;       // full[STAGES], empty[STAGES], tmem_full
-  const uint32_t tmem_slot = bars + (2 * p.STAGES + 1) * 8;
-  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
-  double* s_stats = reinterpret_cast<double*>(gen_base + (tmem_slot + 8 - smem_base));   // [BN][2]
-
-  // warp index through a shuffle: tells the compiler it is warp-uniform, so role code stays on the uniform datapath
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  auto full_bar = [&](int s) { return bars + s * 8; };
-  auto empty_bar = [&](int s) { return bars + (p.STAGES + s) * 8; };
-  const uint32_t tmem_full_bar = bars + 2 * p.STAGES * 8;
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int td = t % p.tiles_d;
-  const int n = t / p.tiles_d;
-  const int w0 = tw * p.BW, h0 = th * p.BH, d0 = td * p.BD;
-  const int n0 = blockIdx.y * p.BN;
-  const int taps = p.KD * p.KH * p.KW;
-  const int num_kb = taps * p.num_cchunks;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.BN; i += NUM_THREADS) s_stats[i] = 0.0;
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // uniform for the compiler
-
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      const int pd = p.KD / 2, ph = p.KH / 2, pw = p.KW / 2;
-      int kb = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
-        for (int cc = 0; cc < p.num_cchunks; ++cc, ++kb) {
-          const int s = kb % p.STAGES;
-          const uint32_t ph_bit = (kb / p.STAGES) & 1;
-          mbar_wait(empty_bar(s), ph_bit ^ 1);
-          const uint32_t sa = smem_base + s * p.stage_bytes;
-          mbar_expect_tx(full_bar(s), 2 * p.a_bytes + 2 * p.b_bytes);
-          const int c0 = cc * p.CCHUNK;
-          tma_load_5d(sa, &map_a_hi, full_bar(s), c0, w0 + kw - pw, h0 + kh - ph, d0 + kd - pd, n);
-          tma_load_5d(sa + p.a_bytes, &map_a_lo, full_bar(s), c0, w0 + kw - pw, h0 + kh - ph, d0 + kd - pd, n);
-          tma_load_2d(sa + 2 * p.a_bytes, &map_b_hi, full_bar(s), tap * p.Cin + c0, n0);
-          tma_load_2d(sa + 2 * p.a_bytes + p.b_bytes, &map_b_lo, full_bar(s), tap * p.Cin + c0, n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const int ksteps = p.CCHUNK / 16;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.STAGES;
-        const uint32_t ph_bit = (kb / p.STAGES) & 1;
-        mbar_wait(full_bar(s), ph_bit);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_base + s * p.stage_bytes;
-        const uint32_t a_hi = sa, a_lo = sa + p.a_bytes, b_hi = sa + 2 * p.a_bytes, b_lo = b_hi + p.b_bytes;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint32_t ko = k * 32;   // 16 bf16 along K inside the swizzle atom
-          const uint64_t dah = make_smem_desc(a_hi + ko, p.sbo, p.layout_type);
-          const uint64_t dal = make_smem_desc(a_lo + ko, p.sbo, p.layout_type);
-          const uint64_t dbh = make_smem_desc(b_hi + ko, p.sbo, p.layout_type);
-          const uint64_t dbl = make_smem_desc(b_lo + ko, p.sbo, p.layout_type);
-          umma_bf16(tmem_base, dal, dbh, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, dah, dbl, p.idesc, 1u);
-          umma_bf16(tmem_base, dah, dbh, p.idesc, 1u);
-        }
-        umma_commit(empty_bar(s));   // implicit tcgen05.fence::before_thread_sync
-      }
-      umma_commit(tmem_full_bar);
-    }
-  } else {
-    // ===================================================================== epilogue (warps 2..5)
-    const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;               // accumulator row == position inside the tile
-    const int ww = r % p.BW, hh = (r / p.BW) % p.BH, dd = r / (p.BW * p.BH);
-    const int64_t pos = (((int64_t)n * p.D + d0 + dd) * p.H + h0 + hh) * p.W + w0 + ww;
-    const int64_t obase = pos * p.Cout;
-    const int cpg = p.gn_groups > 0 ? p.Cout / p.gn_groups : 1;
-    const bool vec4 = (p.Cout % 4) == 0, vec8 = (p.Cout % 8) == 0;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      const int co0 = n0 + c0;
-      if (co0 >= p.Cout) break;                // padded output channels (warp-uniform)
-      const bool full16 = co0 + 16 <= p.Cout;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (p.bias && co0 + i < p.Cout) v[i] += __ldg(p.bias + co0 + i);
-      if (p.res_f32) {
-        if (full16 && vec4) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 rr = *reinterpret_cast<const float4*>(p.res_f32 + obase + co0 + i);
-            v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
-          }
-        } else {
-          for (int i = 0; i < 16; ++i)
-            if (co0 + i < p.Cout) v[i] += p.res_f32[obase + co0 + i];
-        }
-      } else if (p.res_hi) {
-        if (full16 && vec4) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 rr = mp_load_split4(p.res_hi, p.res_lo, obase + co0 + i);
-            v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
-          }
-        } else {
-          for (int i = 0; i < 16; ++i)
-            if (co0 + i < p.Cout) v[i] += mp_join(p.res_hi[obase + co0 + i], p.res_lo[obase + co0 + i]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = mp_apply_act(v[i], p.act);
-      if (p.out_f32) {
-        if (full16 && vec4) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(p.out_f32 + obase + co0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-          for (int i = 0; i < 16; ++i)
-            if (co0 + i < p.Cout) p.out_f32[obase + co0 + i] = v[i];
-        }
-      }
-      if (p.out_hi) {
-        if (full16 && vec8) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) mp_store_split4(p.out_hi, p.out_lo, obase + co0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-        } else {
-          for (int i = 0; i < 16; ++i)
-            if (co0 + i < p.Cout) mp_split2(v[i], p.out_hi[obase + co0 + i], p.out_lo[obase + co0 + i]);
-        }
-      }
-      if (p.stats) {
-        // per-column sums over the 32 rows of this warp, then one shared-memory add per column
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float sm = (co0 + i < p.Cout) ? v[i] : 0.f;
-          float sq = sm * sm;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            sm += __shfl_xor_sync(0xffffffffu, sm, o);
-            sq += __shfl_xor_sync(0xffffffffu, sq, o);
-          }
-          if (lane == 0) {
-            atomicAdd(&s_stats[2 * (c0 + i)], (double)sm);
-            atomicAdd(&s_stats[2 * (c0 + i) + 1], (double)sq);
-          }
-        }
-      }
-    }
-    if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-      const int et = threadIdx.x - 64;
-      for (int c = et; c < p.BN; c += 128) {
-        const int co = n0 + c;
-        if (co < p.Cout) {
-          double* st = p.stats + ((int64_t)n * p.gn_groups + co / cpg) * 2;
-          atomicAdd(st, s_stats[2 * c]);
-          atomicAdd(st + 1, s_stats[2 * c + 1]);
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1692,18 +1466,12 @@ struct Plan {
   int tiles_m, tiles_n;
   uint32_t smem_bytes;
   CUtensorMapSwizzle swz;
-  bool v1;
   bool slab;
   SlabExtra x;
 };
 
 bool allow_dual() {
   static int v = [] { const char* e = getenv("MPB200_TC_NO_DUALB"); return (e && atoi(e)) ? 0 : 1; }();
-  return v != 0;
-}
-
-bool use_v1() {
-  static int v = [] { const char* e = getenv("MPB200_TC_V1"); return (e && atoi(e)) ? 1 : 0; }();
   return v != 0;
 }
 
@@ -1737,7 +1505,6 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   if (d->prec != MP_PREC_SPLIT_BF16 && d->prec != MP_PREC_F16X2 && d->prec != MP_PREC_F16_Q8) return fail("unknown prec");
   const bool f16x2 = d->prec == MP_PREC_F16X2;
   const bool f16q8 = d->prec == MP_PREC_F16_Q8;
-  if (f16q8 && use_v1()) return fail("v1 kernel has no fp16 + fp8 mode");
   if (f16q8 && (d->Cin % 64 || d->Cin2 % 64)) return fail("fp16 + fp8 mode needs input channels in multiples of 64");
   {
     const int native = f16q8 ? MP_FMT_F16_Q8 : f16x2 ? MP_FMT_F16 : MP_FMT_SPLIT_BF16;
@@ -1749,7 +1516,6 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     if ((p.out_fmt == MP_FMT_F16_Q8 && d->out_hi) || (p.res_fmt == MP_FMT_F16_Q8 && d->res_hi))
       if (out_C % 64 || d->out_c_off % 64 || d->Cout % 64) return fail("the fp16 + fp8 plane format needs 64-channel groups");
   }
-  if (f16x2 && use_v1()) return fail("v1 kernel has no fp16 two-pass mode");
   p.prec = d->prec;
   p.a_planes = f16x2 ? 1u : 2u;
   p.lo_scale = f16x2 ? 1.0f / 2048.0f : f16q8 ? d->corr_scale : 1.0f;
@@ -1759,7 +1525,6 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   const uint32_t ap = p.a_planes;
   // fused 1x1 shortcut (second source appended to K)
   if (d->Cin2 < 0 || (d->Cin2 > 0 && (!d->in2_hi || (!f16x2 && !d->in2_lo)))) return fail("bad second source");
-  if (d->Cin2 > 0 && use_v1()) return fail("v1 kernel has no fused shortcut");
   if (d->Cin2 % 16 != 0) return fail("Cin2 % 16 != 0");
   p.stride2 = d->stride2 > 0 ? d->stride2 : 1;
   p.in2_c_off = d->in2_c_off;
@@ -1800,7 +1565,6 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     const int sbox = p.BW * p.BH * p.BD;
     if (TILE_M % sbox || p.tiles_w * p.tiles_h * p.tiles_d != 1) return fail("sample grid is not a power-of-two box");
     if (d->stats) return fail("fused GroupNorm statistics need >= 128 positions per sample");
-    if (use_v1()) return fail("v1 kernel has no batch-in-tile support");
     p.BNb = TILE_M / sbox;
   }
   pl.tiles_m = ((d->N + p.BNb - 1) / p.BNb) * p.tiles_d * p.tiles_h * p.tiles_w;
@@ -1824,13 +1588,10 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   if (!p.BN) return fail("no N tile");
   while ((int64_t)pl.tiles_m * (d->Cout_pad / p.BN) < 148 && p.BN % 32 == 0 && p.BN > 32) p.BN /= 2;
   pl.tiles_n = d->Cout_pad / p.BN;
-  pl.v1 = use_v1();
   pl.slab = false;
   // ---- slab (vertical-halo reuse) kernel for 3x3(x3) convolutions with <= 128 output channels
   static int allow_slab = [] { const char* e = getenv("MPB200_TC_NO_SLAB"); return (e && atoi(e)) ? 0 : 1; }();
-  if (pl.v1 && (p.stride != 1 || p.in_c_off || p.out_c_off || p.out_C != d->Cout || (d->in_C > 0 && d->in_C != d->Cin)))
-    return fail("v1 kernel has no stride / channel-window support");
-  if (!pl.v1 && allow_slab && !f16q8 && p.stride == 1 && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) &&
+  if (allow_slab && !f16q8 && p.stride == 1 && d->KH == 3 && d->KW == 3 && (d->KD == 1 || d->KD == 3) &&
       d->Cout_pad <= 128 && d->W % 8 == 0 && d->H % 16 == 0) {
     const int bn = d->Cout_pad;
     const bool tma_s = tma_epi_ok(d, bn);
@@ -1919,12 +1680,12 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
     p.S = (int64_t)d->D * Ho * Wo;
     return 0;
   }
-  const bool tma_g = !pl.v1 && tma_epi_ok(d, p.BN);
+  const bool tma_g = tma_epi_ok(d, p.BN);
   // two staging buffers where shared memory is plentiful (narrow tiles, tiny K); one otherwise
   const uint32_t nbuf_g = (p.BN <= 64 || (int64_t)d->KD * d->KH * d->KW * d->Cin <= 128) ? 2u : 1u;
   const uint32_t tma_bytes_g = tma_g ? nbuf_g * (uint32_t)(p.BN / 64) * 16384u + 1024u /*alignment*/ : 0u;
   const uint32_t fixed = 1024 /*align slack*/ + 1024 /*barriers, tmem slot*/ + 2 * 256 * sizeof(double) +
-                         (pl.v1 ? 0 : (tma_g ? 0u : EPI_BYTES) + 2048 /*s_part*/) + tma_bytes_g;
+                         (tma_g ? 0u : EPI_BYTES) + 2048 /*s_part*/ + tma_bytes_g;
   // weight-resident mode: one N tile and the whole [taps*Cin x BN] weight tile (hi+lo) fits beside >= 3 A stages;
   // try the widest channel chunk first, then narrower ones (smaller A stages).
   static int allow_res = [] { const char* e = getenv("MPB200_TC_NO_BRES"); return (e && atoi(e)) ? 0 : 1; }();
@@ -1933,7 +1694,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   const uint32_t bres_bytes = ktot * (uint32_t)p.BN * 4u;
   const int ntaps = d->KD * d->KH * d->KW;
   const bool all_taps = p.tap_mask == (ntaps == 64 ? ~0ull : ((1ull << ntaps) - 1ull));
-  if (!pl.v1 && allow_res && all_taps && pl.tiles_n == 1 && pl.tiles_m >= 4 * 148 && bres_bytes < SMEM_LIMIT) {
+  if (allow_res && all_taps && pl.tiles_n == 1 && pl.tiles_m >= 4 * 148 && bres_bytes < SMEM_LIMIT) {
     for (int cc = p.CCHUNK; cc >= 16; cc /= 2) {
       const uint32_t a_stage = ap * TILE_M * cc * 2u;
       if (fixed + bres_bytes + 3 * a_stage <= SMEM_LIMIT && bres_bytes < (1u << 20)) {
@@ -1962,13 +1723,13 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   p.tma_off = (p.bres_off + (p.b_resident ? bres_bytes : 0) + 1023u) & ~1023u;
   p.tma_buf_bytes = tma_g ? (uint32_t)(p.BN / 64) * 16384u : 0u;
   p.tma_nbuf = nbuf_g;
-  p.epi_bytes = (tma_g || pl.v1) ? 0u : EPI_BYTES;
+  p.epi_bytes = tma_g ? 0u : EPI_BYTES;
   p.epi_off = tma_g ? p.tma_off + p.tma_nbuf * p.tma_buf_bytes : p.bres_off + (p.b_resident ? bres_bytes : 0);
-  p.dualb = (!pl.v1 && (allow_dual() || f16x2 || f16q8) && 2 * 2 * p.BN <= 512) ? 1 : 0;
+  p.dualb = ((allow_dual() || f16x2 || f16q8) && 2 * 2 * p.BN <= 512) ? 1 : 0;
   if ((f16x2 || f16q8) && !p.dualb) return fail("fp16 modes need the two-half accumulator layout (BN <= 128)");
   if (f16q8 && p.CCHUNK != 64) return fail("fp16 + fp8 mode needs 64-channel K chunks");
   p.acc_w = p.dualb ? 2 * p.BN : p.BN;
-  p.tmem_cols = next_pow2(pl.v1 ? p.BN : 2 * p.acc_w);
+  p.tmem_cols = next_pow2(2 * p.acc_w);
   p.idesc2 = idesc_fmt | ((uint32_t)(2 * p.BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   p.tiles_n = pl.tiles_n;
   p.total_tiles = pl.tiles_m * pl.tiles_n;
@@ -2162,7 +1923,7 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
   {
     static int no_merge = [] { const char* e = getenv("MPB200_TC_NO_BMERGE"); return (e && atoi(e)) ? 1 : 0; }();
     const size_t plane = ((size_t)d->KD * d->KH * d->KW * d->Cin + d->Cin2) * d->Cout_pad * 2;
-    pl.p.b_merged = (!no_merge && !pl.v1 &&
+    pl.p.b_merged = (!no_merge &&
                      reinterpret_cast<const char*>(d->w_lo) == reinterpret_cast<const char*>(d->w_hi) + plane) ? 1 : 0;
   }
   // ---- CTA-pair kernel (cta_group::2) for the fp16 + FP8 convolutions whose tiles pair up (MPB200_TC_PAIR=0 disables it)
@@ -2172,7 +1933,7 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
     const TcParams& q = pl.p;
     const int ntaps = d->KD * d->KH * d->KW;
     const bool all_taps = q.tap_mask == (ntaps == 64 ? ~0ull : ((1ull << ntaps) - 1ull));
-    if (allow_pair && d->prec == MP_PREC_F16_Q8 && !pl.slab && !pl.v1 && q.BN == 128 && q.CCHUNK == 64 && q.b_merged &&
+    if (allow_pair && d->prec == MP_PREC_F16_Q8 && !pl.slab && q.BN == 128 && q.CCHUNK == 64 && q.b_merged &&
         (d->Cin2 == 0 || q.stride2 == 1) && q.stride == 1 && q.BNb == 1 && pl.tiles_m % 2 == 0 && q.in_c_off == 0 && !d->stats && !q.b_resident &&
         all_taps && (d->in_C == 0 || d->in_C == d->Cin))
       return launch_pair(d, pl, stream);
@@ -2199,9 +1960,7 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-      cudaError_t ae = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-      if (ae == cudaSuccess)
-        ae = cudaFuncSetAttribute(k_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+      cudaError_t ae = cudaFuncSetAttribute(k_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
       if (ae == cudaSuccess)
         ae = cudaFuncSetAttribute(k_conv_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
       MP_REQUIRE(ae == cudaSuccess, "mp_conv_tc: cannot opt in to %u B shared memory: %s", SMEM_LIMIT,
@@ -2214,20 +1973,14 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
     // dynamic tile scheduling (default; MPB200_TC_STATIC=1 restores the static walk)
     static int dyn = [] { const char* e = getenv("MPB200_TC_STATIC"); return (e && atoi(e)) ? 0 : 1; }();
     pl.p.sched = nullptr;
-    if (dyn && !pl.v1) pl.p.sched = sched_slot((dev >= 0 && dev < 64) ? dev : 0, mp_stream(stream));
-    if (pl.v1) {
-      dim3 grid((unsigned)pl.tiles_m, (unsigned)pl.tiles_n);
-      k_conv_tc<<<grid, NUM_THREADS, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, pl.p);
-    } else {
-      int sms = (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) ? g_num_sms[dev] : 148;
-      int grid = pl.p.total_tiles < sms ? pl.p.total_tiles : sms;
-      if (pl.slab)
-        k_conv_tc3<<<grid, NUM_THREADS3, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
-                                                                               pl.p, pl.x);
-      else
-        k_conv_tc2<<<grid, NUM_THREADS3, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo,
-                                                                               pl.p);
-    }
+    if (dyn) pl.p.sched = sched_slot((dev >= 0 && dev < 64) ? dev : 0, mp_stream(stream));
+    int sms = (dev >= 0 && dev < 64 && g_num_sms[dev] > 0) ? g_num_sms[dev] : 148;
+    int grid = pl.p.total_tiles < sms ? pl.p.total_tiles : sms;
+    if (pl.slab)
+      k_conv_tc3<<<grid, NUM_THREADS3, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo, pl.p,
+                                                                             pl.x);
+    else
+      k_conv_tc2<<<grid, NUM_THREADS3, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo, pl.p);
   }
   MP_LAUNCH_CHECK("mp_conv_tc");
   return 0;
