@@ -455,7 +455,8 @@ def run_b200(args):
     if world == 1 and not args.no_extra_configs:
         with torch.no_grad():
             def timed_fwd(xs_in, xd_in, reps):
-                G(xs_in, xd_in)
+                for _ in range(3):                 # first call eager, second captures the shape's graph, third replays
+                    G(xs_in, xd_in)
                 torch.cuda.synchronize()
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 f0.record()
@@ -467,20 +468,17 @@ def run_b200(args):
             msA = timed_fwd(xs_d.expand(B, -1, -1, -1).contiguous(), xd_d, 3)
             cfgA = {"value": B / (msA * 1e-3), "unit": UNIT, "ms_per_step": msA,
                     "what": f"Gbase.forward(xs.expand({B}), xd): reference semantics, source half recomputed for every pair "
-                            "(SURVEY.md 8d config 2 variant A), eager launches through the drop-in forward()"}
+                            "(SURVEY.md 8d config 2 variant A) through the drop-in forward() (which replays a shape-keyed CUDA graph "
+                            "from the second call on)"}
+            G.release_forward_graphs()             # the batch-32 graph owns ~10 GB of activations: drop it before the next legs
+            torch.cuda.empty_cache()
             ms1 = timed_fwd(xs_d, xd_d[:1].contiguous(), 5)
-            g1 = GraphedGbase(G, 1, dev)
-            g1.step(xs_d, xd_d[:1])
-            torch.cuda.synchronize()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(5):
-                g1.step(xs_d, xd_d[:1])
-            f1.record()
-            torch.cuda.synchronize()
-            cfg1 = {"latency_ms_eager_forward": ms1, "latency_ms_graph_replay": f0.elapsed_time(f1) / 5,
-                    "what": "BASELINE config 1 on B200: Gbase(xs, xd) with 1 source + 1 driver frame (device-resident inputs)"}
-            del g1
+            G.forward_graphs = False
+            ms1_eager = timed_fwd(xs_d, xd_d[:1].contiguous(), 5)
+            G.forward_graphs = True
+            cfg1 = {"latency_ms_forward": ms1, "latency_ms_forward_eager_launches": ms1_eager,
+                    "what": "BASELINE config 1 on B200: the drop-in Gbase.forward(xs, xd) with 1 source + 1 driver frame, device-resident "
+                            "inputs, outputs cloned out of the graph's static buffers; `eager_launches` = forward_graphs off"}
             # BASELINE config 4 (row f-3): the high-resolution stage.  Genh is fully convolutional (model.py:1349-1391):
             # timed on a batch of 8 frames at 1024 x 1024, and GHR = Genh(Gbase(xs, xd)) on 8 (src, drv) pairs at 512 x 512
             from megaportrait_hack_b200 import model as M, seeded as S
@@ -490,7 +488,8 @@ def run_b200(args):
             xg = torch.rand(8, 3, 1024, 1024, generator=torch.Generator().manual_seed(11)).to(dev) * 2 - 1
 
             def timed(fn, reps):
-                fn()
+                for _ in range(3):                 # (GHR goes through Gbase.forward: eager, capture, replay)
+                    fn()
                 torch.cuda.synchronize()
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 t0.record()

@@ -106,3 +106,53 @@ def test_two_rank_nccl_shards_match_single_gpu():
         assert res[name]["max_abs_vs_same_shard_on_one_gpu"] <= 1e-6, res
         assert res[name]["max_abs_vs_full_batch_on_one_gpu"] <= 1e-4, res     # other batch size: batch-invariance bound
         assert res[name]["swap_visible"] > 2e-4, res      # frames differ by ~5e-4 with the seeded weights
+
+
+def test_forward_replays_a_shape_keyed_graph_and_tracks_weight_changes(gbase):
+    """The drop-in `Gbase.forward` captures a CUDA graph per (batch size, device) on the second call and replays it afterwards:
+    same bits as the eager launches, cloned outputs (a later call must not overwrite what the caller holds), and a weight
+    update drops the graph (the packed plans it captured are stale)."""
+    from megaportrait_hack_b200 import model as M, ops
+    G, _sd = gbase
+    G.release_forward_graphs()
+    # G2d's FP8 byte-plane scales are calibrated on the first batch a plan sees; start from fresh plans so that `ref` and the
+    # call after the weight is restored (which rebuilds the plan) are calibrated on the same batch and can be compared bit for bit
+    # (two calibrations on different batches differ by ~3e-5 in RGB, see test_g2d_q8_calibration_*)
+    M.invalidate_plans(G)
+    xs, xd = synthetic_pair(2)
+    xs2 = xs.expand(2, -1, -1, -1).contiguous().cuda()
+    xd2 = xd.cuda()
+    with torch.no_grad():
+        G.forward_graphs = False
+        ref, pref = G(xs2, xd2)
+        G.forward_graphs = True
+        a, _ = G(xs2, xd2)                     # sighting 1: eager
+        assert "_mp_fwd_graphs" not in G.__dict__ or not G.__dict__["_mp_fwd_graphs"]
+        b, pb = G(xs2, xd2)                    # sighting 2: capture + replay
+        assert len(G.__dict__["_mp_fwd_graphs"]) == 1
+        l0 = ops.LAUNCHES
+        c, pc = G(xs2, xd2)                    # replay
+        assert ops.LAUNCHES - l0 > 300
+        xd_other = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(77)).cuda()
+        d, _ = G(xs2, xd_other)                # replay with other inputs must not touch what `c` holds
+        for t in (a, b, c):
+            assert torch.equal(t, ref)
+        assert torch.equal(pc["prediction_0.25"], pref["prediction_0.25"])
+        assert c.data_ptr() != d.data_ptr() and not torch.equal(c, d)
+        # weight update (in place: bumps the tensor version) -> the graph is dropped and the next calls see the new weights
+        w = G.G2d.final_conv[2].bias
+        old = w.detach().clone()
+        try:
+            w.add_(0.05)
+            e, _ = G(xs2, xd2)
+            assert not G.__dict__["_mp_fwd_graphs"]
+            assert (e - ref).abs().max().item() > 1e-3
+            G.forward_graphs = False
+            e_ref, _ = G(xs2, xd2)
+            G.forward_graphs = True
+            assert torch.equal(e, e_ref)
+        finally:
+            w.copy_(old)
+        f, _ = G(xs2, xd2)
+        assert torch.equal(f, ref)
+    G.release_forward_graphs()
