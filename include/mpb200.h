@@ -186,6 +186,13 @@ int mp_global_avgpool_cl(const float* in_f32, const void* in_hi, const void* in_
 int mp_im2col3x3_f16(const float* in, void* out_h, int N, int C, int H, int W, int stride, void* stream);
 /* nn.MaxPool2d(3, 2, 1) on an fp16 CL tensor [N,1,H,W,C] -> [N,1,H/2,W/2,C] (resnet.py:196). */
 int mp_maxpool3x3s2_cl_f16(const void* in_h, void* out_h, int N, int H, int W, int C, void* stream);
+/* The whole stem of a CIFAR-style ResNet-18 trunk in one kernel: nn.Conv2d(3, C, 3, 1, 1) + folded BatchNorm + ReLU +
+ * nn.MaxPool2d(3, 2, 1) (resnet.py:192-197, 271-273): NCHW fp32 frames [N,3,H,W] -> fp16 CL [N,1,H/2,W/2,C]; the
+ * full-resolution C-channel tensor exists only in shared memory.  w_hi / w_lo: the [C, 32] fp16 planes of an MP_PREC_F16X2
+ * weight pack over the patch channels (kh*3+kw)*3 + c (27 used), acc_scale as in mp_conv_desc.  C = 64 or 128 (two trunks
+ * reading the same frame); H, W multiples of 16. */
+int mp_stem3x3_relu_maxpool_f16(const float* x, const void* w_hi, const void* w_lo, const float* bias, float acc_scale,
+                                void* out_h, int N, int H, int W, int C, void* stream);
 /* nn.AdaptiveAvgPool2d(1) on an fp16 CL tensor [N,S,C] -> out [N,C] fp32 (fp32 accumulation). */
 int mp_global_avgpool_cl_f16(const void* in_h, float* out, int N, int64_t S, int C, void* stream);
 

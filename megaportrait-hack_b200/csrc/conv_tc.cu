@@ -1695,7 +1695,7 @@ int make_plan(const mp_conv_desc* d, Plan& pl, bool report) {
   const int ntaps = d->KD * d->KH * d->KW;
   const bool all_taps = p.tap_mask == (ntaps == 64 ? ~0ull : ((1ull << ntaps) - 1ull));
   if (allow_res && all_taps && pl.tiles_n == 1 && pl.tiles_m >= 4 * 148 && bres_bytes < SMEM_LIMIT) {
-    for (int cc = p.CCHUNK; cc >= 16; cc /= 2) {
+    for (int cc = p.CCHUNK; cc >= (f16q8 ? 64 : 16); cc /= 2) {       // (fp16 + fp8 mode: 64-channel chunks only)
       const uint32_t a_stage = ap * TILE_M * cc * 2u;
       if (fixed + bres_bytes + 3 * a_stage <= SMEM_LIMIT && bres_bytes < (1u << 20)) {
         p.b_resident = 1;

@@ -34,6 +34,8 @@ from .ops import ACT_NONE, ACT_RELU, PREC_F16X2, PREC_SPLIT_BF16, Act
 
 RGB_PAD = 16
 EMTN_PREC = PREC_SPLIT_BF16 if os.environ.get("MPB200_EMTN_PREC", "f16x2") == "split" else PREC_F16X2
+# fp16 plans: the CIFAR-ResNet stems (conv3x3 + BN + ReLU + max-pool) run as ONE kernel; 0 = im2col -> 1x1 conv -> max-pool (A/B)
+STEM_FUSED = os.environ.get("MPB200_STEM_FUSED", "1") != "0"
 
 
 def rgb16(x: torch.Tensor) -> Act:
@@ -120,11 +122,15 @@ class DualResNet18Plan:
             self.stem = ops.pack_conv(w, bias, wa.device, cin_pad=RGB_PAD)
 
     def pooled(self, x_in):
-        """x_in: the fp16 patch tensor of `ops.im2col3x3_f16(x, 1)` (fp16 plans) or the padded split frame `rgb16(x)`."""
+        """x_in: the NCHW fp32 frames (fp16 plans: stem + max-pool run as one kernel; with MPB200_STEM_FUSED=0 the fp16
+        patch tensor of `ops.im2col3x3_f16(x, 1)`) or the padded split frame `rgb16(x)`."""
         c, half = self.c, self.prec == PREC_F16X2
         fmt = dict(f32=False, h16=True) if half else dict(f32=False, split=True)    # format of every intermediate
-        h, _ = ops.conv(x_in, self.stem, act=ACT_RELU, **fmt)
-        h = ops.maxpool3x3s2_f16(h) if half else ops.maxpool3x3s2(h)
+        if half and STEM_FUSED:
+            h = ops.stem3x3_relu_maxpool_f16(x_in, self.stem)
+        else:
+            h, _ = ops.conv(x_in, self.stem, act=ACT_RELU, **fmt)
+            h = ops.maxpool3x3s2_f16(h) if half else ops.maxpool3x3s2(h)
         n_lock = 0
         while (n_lock < len(self.a.blocks) and self.a.blocks[n_lock][1] is None and self.b.blocks[n_lock][1] is None
                and self.a.blocks[n_lock][0][0][1] == 1):
@@ -216,7 +222,8 @@ def emtn_forward(emtn, x: torch.Tensor):
     dual_plan, rot_plan = emtn_plans(emtn)
     x = x.float().contiguous()
     if dual_plan.prec == PREC_F16X2:
-        in_rot, in_dual = ops.im2col3x3_f16(x, rot_plan.stem_stride), ops.im2col3x3_f16(x, 1)
+        in_rot = ops.im2col3x3_f16(x, rot_plan.stem_stride)
+        in_dual = x if STEM_FUSED else ops.im2col3x3_f16(x, 1)
     else:
         in_rot = in_dual = rgb16(x)
     rot = emtn.rotation_net.model

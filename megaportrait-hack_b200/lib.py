@@ -134,6 +134,7 @@ _SIGNATURES = {
     "mp_global_avgpool_cl": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_int, _P]),
     "mp_im2col3x3_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_maxpool3x3s2_cl_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "mp_stem3x3_relu_maxpool_f16": (c_int, [_P, _P, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, _P]),
     "mp_global_avgpool_cl_f16": (c_int, [_P, _P, c_int, c_int64, c_int, _P]),
     "mp_release_caches": (c_int, []),
     "mp_jpeg_info": (c_int, [_P, c_size_t, POINTER(c_int), POINTER(c_int)]),

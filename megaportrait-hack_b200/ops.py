@@ -632,6 +632,23 @@ def maxpool3x3s2_f16(a: Act) -> Act:
 
 
 @_profiled
+def stem3x3_relu_maxpool_f16(x: torch.Tensor, pw: PackedConv) -> Act:
+    """conv3x3(3 -> C) + folded BN + ReLU + MaxPool2d(3, 2, 1) in one kernel (resnet.py:192-197, 271-273): NCHW fp32 frames
+    [N,3,H,W] -> fp16 CL [N,1,H/2,W/2,C]; `pw` = `pack_stem3x3_f16(...)`."""
+    _chk_cuda(x, torch.float32, "stem3x3_relu_maxpool_f16")
+    N, C, H, W = x.shape
+    if C != 3 or pw.prec != PREC_F16X2 or pw.Cin != 32 or pw.Cout != pw.Cout_pad:
+        raise RuntimeError(f"stem3x3_relu_maxpool_f16: needs RGB frames and a pack_stem3x3_f16 weight pack, got {tuple(x.shape)}")
+    out = _alloc((N, 1, H // 2, W // 2, pw.Cout), x.device, False, False, True)
+    L = _lib.load()
+    _lib.check(L.mp_stem3x3_relu_maxpool_f16(_p(x), _p(pw.w_hi), _p(pw.w_lo), _p(pw.bias) if pw.bias is not None else None,
+                                             float(pw.acc_scale), _p(out.h16), N, H, W, pw.Cout, _stream()),
+               "mp_stem3x3_relu_maxpool_f16")
+    _count()
+    return out
+
+
+@_profiled
 def global_avgpool_f16(a: Act) -> torch.Tensor:
     """nn.AdaptiveAvgPool2d(1) + flatten on an fp16 activation: -> [N, C] fp32."""
     N, D, H, W, C = a.shape

@@ -263,6 +263,11 @@ def im2col3x3_f16(x, stride=1):
     return _mk(cols, False, False, True)
 
 
+def stem3x3_relu_maxpool_f16(x, pw):
+    h, _ = conv(im2col3x3_f16(x, 1), pw, act=ops.ACT_RELU, f32=False, h16=True)
+    return maxpool3x3s2_f16(h)
+
+
 def maxpool3x3s2_f16(a):
     y = F.max_pool2d(_to_ncdhw(a.h16.float()).squeeze(2), 3, 2, 1).unsqueeze(2)
     return _mk(_to_cl(y), False, False, True)
@@ -339,7 +344,7 @@ def blur_subsample(x, kernel2d, step):
 _NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
           "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3", "from_nchw_pad16",
-          "im2col3x3_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]
+          "im2col3x3_f16", "stem3x3_relu_maxpool_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]
 
 
 @contextlib.contextmanager

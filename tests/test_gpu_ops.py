@@ -585,6 +585,33 @@ def test_im2col_stem_matches_conv3x3(ops, stride, H, W):
         assert (got - ref).abs().max().item() / ref.abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("Co", [64, 128])
+@pytest.mark.parametrize("N,H,W", [(3, 32, 64), (2, 48, 80), (2, 512, 512)], ids=["small", "odd_tiles", "frame"])
+def test_fused_stem_relu_maxpool_matches_unfused_and_torch(ops, Co, N, H, W):
+    """conv3x3 + folded BN + ReLU + MaxPool2d(3, 2, 1) in one kernel (resnet.py:192-197, 271-273) against (a) the unfused
+    kernels it replaces (im2col -> 1x1 tensor-core convolution -> max-pool: same operand format, so only the fp32 summation
+    order differs) and (b) torch fp32 on the fp16-rounded frame; weights far from unit scale exercise acc_scale; the frame
+    borders exercise the pool's halo (-inf padding in PyTorch, 0 after ReLU here)."""
+    x = torch.rand(N, 3, H, W, generator=torch.Generator().manual_seed(71))
+    w = rnd(Co, 3, 3, 3, seed=72) / math.sqrt(27) * 2.0 ** -7
+    b = rnd(Co, seed=73) * 0.01
+    pw = ops.pack_stem3x3_f16(w, b, DEV)
+    got = ops.stem3x3_relu_maxpool_f16(x.to(DEV), pw)
+    assert got.shape == (N, 1, H // 2, W // 2, Co) and got.h16 is not None
+    g = got.h16.float().cpu().squeeze(1).permute(0, 3, 1, 2)
+    ref = F.max_pool2d(F.relu(F.conv2d(_f16(x).float(), w, b, padding=1)), 3, 2, 1)
+    scale = ref.abs().max().item()
+    assert (g - ref).abs().max().item() / scale < 6e-4          # the fp16 rounding of the output (2^-11) dominates
+    if W % 64 == 0:             # (the tensor-core convolution's position tiles)
+        h, _ = ops.conv(ops.im2col3x3_f16(x.to(DEV), 1), pw, act=ops.ACT_RELU, f32=False, h16=True, mode="tc")
+        u = ops.maxpool3x3s2_f16(h).h16.float().cpu().squeeze(1).permute(0, 3, 1, 2)
+        d = (g - u).abs()
+        # same products, another summation order: results differ only where the fp32 sums straddle an fp16 rounding boundary
+        assert d.max().item() / scale < 6e-4 and (d > 0).float().mean().item() < 0.02
+    with pytest.raises(RuntimeError, match="multiples of 16"):
+        ops.stem3x3_relu_maxpool_f16(x[:, :, :24, :40].contiguous().to(DEV), pw)
+
+
 def test_maxpool_and_global_avgpool_f16(ops):
     x = rnd(3, 64, 1, 36, 52, seed=51)
     a = _h16_act(ops, x)

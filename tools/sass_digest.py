@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """SASS digest of libmpb200.so: per kernel, the opcode histogram of the mnemonics that prove (or disprove) a
 Blackwell-native kernel -- UTC*MMA (tcgen05.mma), LDTM/STTM (tcgen05.ld/st), UTMALDG/UTMASTG/UBLKCP (TMA), SYNCS
-(mbarrier), LDS/STS, LDG/STG, HMMA (legacy mma.sync; must be absent) -- plus registers / code size from cuobjdump.
+(mbarrier), LDS/STS, LDG/STG, HMMA (legacy mma.sync: expected in k_stem3x3_relu_maxpool_f16 only -- the K = 27 RGB stem fused
+with its max-pool, csrc/stem_pool.cu -- and nowhere else) -- plus registers / code size from cuobjdump.
 
     python tools/sass_digest.py [out.txt]          (no GPU needed: cuobjdump reads the cubin inside the .so)
 """
