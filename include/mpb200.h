@@ -250,12 +250,6 @@ int mp_warp_field(const float* em_cl, const float* theta, float* out, int N, int
 int mp_warp_fused_cl(const float* v, const float* em_cl, const float* theta, float* out_f32, void* out_hi,
                      void* out_lo, int N, int Nv, int C, int D, int H, int W, int E, int G, int sum_d, void* stream);
 
-/* 3x3 convolution head with few output channels (G2d's 64->3 RGB conv + Sigmoid, model.py:750-751), second half:
- * y [N,H,W,Ct] CL fp32 holds the 9*Co per-tap partial products of a 1x1 convolution: channel index (kh*3+kw)*Co + co;
- * out [N,Co,H,W] NCHW fp32 = act(bias + sum over the 3x3 neighbourhood).  Co = 3. */
-int mp_tap_sum3x3_cl(const float* y, const float* bias, float* out, int N, int H, int W, int Co, int Ct, int act,
-                     void* stream);
-
 /* G2d output head fused into one pass (model.py:748-751): GroupNorm(32,64) -> ReLU -> Conv2d(64,3,3,pad 1) -> act.
  * x [N,H,W,Cin] CL fp32 (the last decoder block's output), ab [N][Cin][2] from mp_gn_finalize, weight_host [Cout][Cin][3][3]
  * and bias_host [Cout] (may be NULL) are HOST pointers (the weights travel as kernel parameters), out [N,Cout,H,W] NCHW

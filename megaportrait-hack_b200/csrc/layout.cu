@@ -555,50 +555,6 @@ extern "C" int mp_global_avgpool_cl(const float* in_f32, const void* in_hi, cons
   return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ tap-sum head
-// A 3x3 convolution with very few output channels (the 64->3 RGB head of G2d, model.py:750) as a 1x1 convolution
-// that produces all 9*Co per-tap partial products per pixel (one tensor-core GEMM with N = 9*Co) followed by this
-// shift-and-add: out[n,co,h,w] = act(bias[co] + sum_{kh,kw} y[n, h+kh-1, w+kw-1, (kh*3+kw)*Co + co]), zero outside.
-// y is CL fp32 [N,H,W,Ct]; out is NCHW fp32.  One thread per output pixel; HBM-bound (reads y once, 9x from L1/L2).
-template <int CO>
-__global__ void k_tap_sum3x3(const float* __restrict__ y, const float* __restrict__ bias, float* __restrict__ out, int H,
-                             int W, int Ct, int act) {
-  const int64_t HW = (int64_t)H * W;
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= HW) return;
-  const int n = blockIdx.y;
-  const int w = (int)(t % W), h = (int)(t / W);
-  float acc[CO];
-#pragma unroll
-  for (int c = 0; c < CO; ++c) acc[c] = bias ? __ldg(bias + c) : 0.f;
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int hh = h + kh - 1;
-    if (hh < 0 || hh >= H) continue;
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int ww = w + kw - 1;
-      if (ww < 0 || ww >= W) continue;
-      const float* p = y + (((int64_t)n * H + hh) * W + ww) * Ct + (kh * 3 + kw) * CO;
-#pragma unroll
-      for (int c = 0; c < CO; ++c) acc[c] += __ldg(p + c);
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < CO; ++c) out[((int64_t)n * CO + c) * HW + t] = mp_apply_act(acc[c], act);
-}
-
-extern "C" int mp_tap_sum3x3_cl(const float* y, const float* bias, float* out, int N, int H, int W, int Co, int Ct,
-                                int act, void* stream) {
-  MP_REQUIRE(y && out, "mp_tap_sum3x3_cl: null pointer");
-  MP_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && Ct >= 9 * Co, "mp_tap_sum3x3_cl: bad dims");
-  MP_REQUIRE(Co == 3, "mp_tap_sum3x3_cl: only Co = 3 is instantiated");
-  dim3 grid((unsigned)(((int64_t)H * W + 255) / 256), N);
-  k_tap_sum3x3<3><<<grid, 256, 0, mp_stream(stream)>>>(y, bias, out, H, W, Ct, act);
-  MP_LAUNCH_CHECK("mp_tap_sum3x3_cl");
-  return 0;
-}
-
 // ------------------------------------------------------------------------------------------------ RGB stem input
 // NCHW fp32 [N,C,S] (C <= 16, the RGB frames) -> split channels-last [N,S,16] with the channel axis zero-padded to 16:
 // the operand of the tensor-core stems (one thread per position, coalesced plane reads, two 32-byte row writes).

@@ -158,7 +158,6 @@ _SIGNATURES = {
     "mp_warp_field": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "mp_warp_fused_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_int, _P]),
-    "mp_tap_sum3x3_cl": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_gn_relu_conv3x3_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_frames_u8_to_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, _P]),
     "mp_frames_f32_to_u8": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_float, c_int, _P]),

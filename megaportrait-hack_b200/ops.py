@@ -814,24 +814,6 @@ def warp_fused(v: Act, em_cl: torch.Tensor, theta: torch.Tensor, sum_d: bool, G:
     return out
 
 
-def pack_tap_head(weight: torch.Tensor, device=None) -> PackedConv:
-    """3x3 conv weight (Co, Cin, 3, 3) -> 1x1 PackedConv with 9*Co outputs, row (kh*3+kw)*Co + co (see tap_sum3x3)."""
-    Co, Cin = weight.shape[0], weight.shape[1]
-    w = weight.detach().double().permute(2, 3, 0, 1).reshape(9 * Co, Cin, 1, 1)
-    return pack_conv(w, None, device or weight.device)
-
-
-@_profiled
-def tap_sum3x3(y: Act, bias: Optional[torch.Tensor], Co: int, act: int = ACT_NONE) -> torch.Tensor:
-    """Second half of the tap-sum conv head: y CL fp32 [N,1,H,W,Ct] -> NCHW fp32 [N,Co,H,W]."""
-    N, D, H, W, Ct = y.shape
-    out = torch.empty((N, Co, H, W), dtype=torch.float32, device=y.device)
-    L = _lib.load()
-    _lib.check(L.mp_tap_sum3x3_cl(_p(y.f32), _p(bias), _p(out), N, H, W, Co, Ct, act, _stream()), "mp_tap_sum3x3_cl")
-    _count()
-    return out
-
-
 @_profiled
 def gn_relu_conv3x3_head(a: Act, ab: torch.Tensor, weight_host: torch.Tensor, bias_host: Optional[torch.Tensor],
                          act: int = ACT_SIGMOID) -> torch.Tensor:

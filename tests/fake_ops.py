@@ -316,19 +316,6 @@ def warp_fused(v, em_cl, theta, sum_d, G=64, f32=True, split=False):
     return _mk(_to_cl(out), f32, split)
 
 
-def tap_sum3x3(y, bias, Co, act=ops.ACT_NONE):
-    v = y.f32[:, 0]                                    # [N,H,W,Ct]
-    N, H, W, Ct = v.shape
-    vp = F.pad(v, (0, 0, 1, 1, 1, 1))
-    out = torch.zeros(N, H, W, Co)
-    for kh in range(3):
-        for kw in range(3):
-            out += vp[:, kh:kh + H, kw:kw + W, (kh * 3 + kw) * Co:(kh * 3 + kw + 1) * Co]
-    if bias is not None:
-        out = out + bias
-    return _act(out, act).permute(0, 3, 1, 2).contiguous()
-
-
 def gn_relu_conv3x3_head(a, ab, weight_host, bias_host, act=ops.ACT_SIGMOID):
     v = F.relu(a.f32 * ab[:, None, None, None, :, 0] + ab[:, None, None, None, :, 1])
     return _act(F.conv2d(_to_ncdhw(v).squeeze(2), weight_host, bias_host, padding=1), act)
@@ -343,7 +330,7 @@ def blur_subsample(x, kernel2d, step):
 
 _NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
-          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "tap_sum3x3", "from_nchw_pad16",
+          "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "from_nchw_pad16",
           "im2col3x3_f16", "stem3x3_relu_maxpool_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]
 
 

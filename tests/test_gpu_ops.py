@@ -449,20 +449,6 @@ def test_maxpool_and_global_avgpool(ops):
     assert (gap - xs.mean(dim=(2, 3))).abs().max().item() < 1e-6
 
 
-def test_tap_sum_head_matches_conv3x3(ops):
-    """G2d's 64->3 3x3 conv + Sigmoid (model.py:750-751) as a 27-output 1x1 tensor-core GEMM + shift-and-add."""
-    N, Cin, Co, H, W = 2, 64, 3, 64, 128
-    x = rnd(N, Cin, H, W, seed=51)
-    w = rnd(Co, Cin, 3, 3, seed=52) / math.sqrt(Cin * 9)
-    b = rnd(Co, seed=53) * 0.1
-    ref = torch.sigmoid(F.conv2d(x, w, b, padding=1))
-    a = ops.from_nchw(x.to(DEV), f32=False, split=True)
-    y, _ = ops.conv(a, ops.pack_tap_head(w, DEV), f32=True)
-    got = ops.tap_sum3x3(y, b.to(DEV), Co, ops.ACT_SIGMOID).cpu()
-    assert got.shape == ref.shape
-    assert (got - ref).abs().max().item() < 2e-5
-
-
 def test_rgb_pad16_layout(ops):
     x = rnd(3, 3, 40, 24, seed=61)
     a = ops.from_nchw_pad16(x.to(DEV))
