@@ -566,15 +566,34 @@ def run_b200(args):
         raw_all = sum(c["flops"] * ps for _, c, ps in fam)
         n_all = sum(c["n"] for _, c, _ in fam)
         ach = fl_all / (ms_all * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_conv_tc2 / k_conv_tc3 / k_conv_q8_pair (tcgen05 implicit-GEMM conv; split-bf16 x3, "
-                                             "fp16 x2 and fp16 + e4m3 cross-term operand modes, the last one on cta_group::2)",
-                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
-                "mma_passes": raw_all / fl_all, "raw_tensor_frac": raw_all / (ms_all * 1e-3) / 1e12 / pk["tf_sustained"],
-                "launches": n_all, "avg_launch_ms": ms_all / n_all, "share_of_step": ms_all / step_ms,
-                "algorithmic_gflop_per_launch": fl_all / n_all / 1e9,
-                "modes": {k: {"launches": c["n"], "ms": c["ms"], "useful_tflops": c["flops"] / (c["ms"] * 1e-3) / 1e12,
-                              "pass_units": ps} for k, c, ps in fam}}
+        family = {"kernel": "k_conv_tc2 / k_conv_tc3 / k_conv_q8_pair (tcgen05 implicit-GEMM conv; split-bf16 x3, fp16 x2 and "
+                            "fp16 + e4m3 cross-term operand modes, the last one on cta_group::2)",
+                  "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                  "mma_passes": raw_all / fl_all, "raw_tensor_frac": raw_all / (ms_all * 1e-3) / 1e12 / pk["tf_sustained"],
+                  "launches": n_all, "avg_launch_ms": ms_all / n_all, "share_of_step": ms_all / step_ms,
+                  "algorithmic_gflop_per_launch": fl_all / n_all / 1e9,
+                  "modes": {k: {"launches": c["n"], "ms": c["ms"], "useful_tflops": c["flops"] / (c["ms"] * 1e-3) / 1e12,
+                                "pass_units": ps} for k, c, ps in fam}}
+        # `roofline` = the DOMINANT KERNEL of the step: k_conv_q8_pair (the fp16 + FP8 cross-term convolutions of G2d on CTA
+        # pairs: the largest single share of the step in the ncu launch list, profiles/round2_*_launches_bench.txt);
+        # ALGORITHMIC flops (2 * M * N * K of the convolution, once -- not the 2 pass-units the operand format costs) over the
+        # summed launch durations.  `family` = the same figure over every tensor-core convolution launch of the step.
+        dom = agg.get("conv_tc_q8")
+        if dom and dom["ms"] > 0:
+            ach_d = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "k_conv_q8_pair (tcgen05 cta_group::2 implicit-GEMM convolution, MP_PREC_F16_Q8: fp16 "
+                                                 "main product + e4m3 cross terms; G2d res-blocks and up-blocks 1-2)",
+                    "achieved": ach_d, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach_d / pk["tf_sustained"],
+                    "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
+                    "mma_passes": 2, "raw_tensor_frac": 2 * ach_d / pk["tf_sustained"],
+                    "launches": dom["n"], "avg_launch_ms": dom["ms"] / dom["n"], "share_of_step": dom["ms"] / step_ms,
+                    "algorithmic_gflop_per_launch": dom["flops"] / dom["n"] / 1e9,
+                    "note": "pass-units per product: one fp16 pass + two FP8 passes at twice the rate = 2; ncu: tensor pipe 87.9 % "
+                            "active (profiles/round2_q8_pair_full.txt)",
+                    "family": family}
+        else:                     # (A/B runs with the FP8 format switched off: report the family)
+            roof = dict(family, bound="tensor", traffic=traffic,
+                        peak_source=pk["src"] + " bf16 sustained (kernel timed inside a long step)")
     extra = {}
     if "conv_tc_h" in agg:     # two-pass fp16 convolutions of the motion-encoder trunks
         c = agg["conv_tc_h"]
