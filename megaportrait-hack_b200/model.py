@@ -32,6 +32,16 @@ _Q8_ENABLED = os.environ.get("MPB200_G2D_PREC", "q8") != "split"
 _FWD_GRAPHS = os.environ.get("MPB200_FORWARD_GRAPHS", "1") != "0"
 # ... and its first two up-blocks (MPB200_G2D_UP_PREC=split keeps them on three-pass split-bf16)
 _Q8_UP = os.environ.get("MPB200_G2D_UP_PREC", "q8") != "split"
+# source half at small batch: the three branches that only read the frame run on three streams (0 = one stream; A/B runs)
+_SOURCE_FORK = os.environ.get("MPB200_SOURCE_FORK", "1") != "0"
+_SIDE_STREAMS: Dict[object, Tuple["torch.cuda.Stream", "torch.cuda.Stream"]] = {}
+
+
+def _side_streams(device):
+    key = torch.device(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(key), torch.cuda.Stream(key))
+    return _SIDE_STREAMS[key]
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")   # model.py:51 (kept for callers that read it)
 
@@ -823,12 +833,31 @@ class Gbase(nn.Module):
             raise NotImplementedError("Gbase: train mode is not implemented on the B200 path (SURVEY.md 8f-2)")
         xs = _as_f32_cuda(xs)
         B = xs.shape[0]
-        with ops.stage("Eapp.volume", 866.5e9 * B):
+        if _SOURCE_FORK and B <= 4 and xs.is_cuda and ops.PROFILE is None:
+            # Small source batches are latency-bound (~400 launches of 8-64 CTAs each): the three branches that only read the
+            # frame -- appearance volume, ResNet-50 descriptor, motion encoder -- run on three streams and meet before the S2C
+            # warp generator.  (Under CUDA-graph capture the side streams become parallel branches of the graph.)
+            cur = torch.cuda.current_stream(xs.device)
+            s1, s2 = _side_streams(xs.device)
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s1):
+                es = self.appearanceEncoder._descriptor(xs)
+                es.record_stream(cur)
+            with torch.cuda.stream(s2):
+                Rs, ts, zs = self._emtn(xs)
+                for t in (Rs, ts, zs):
+                    t.record_stream(cur)
             vs = self.appearanceEncoder._volume_cl(xs)
-        with ops.stage("Eapp.descriptor", 34.4e9 * B):
-            es = self.appearanceEncoder._descriptor(xs)
-        with ops.stage("Emtn(source)", 235.6e9 * B):
-            Rs, ts, zs = self._emtn(xs)
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
+        else:
+            with ops.stage("Eapp.volume", 866.5e9 * B):
+                vs = self.appearanceEncoder._volume_cl(xs)
+            with ops.stage("Eapp.descriptor", 34.4e9 * B):
+                es = self.appearanceEncoder._descriptor(xs)
+            with ops.stage("Emtn(source)", 235.6e9 * B):
+                Rs, ts, zs = self._emtn(xs)
         with ops.stage("WarpGeneratorS2C", 0.5e9 * B):
             em, theta = self.warp_generator_s2c._em_theta(Rs, ts, zs, es)
         with ops.stage("warp(vs)+G3d", 163.1e9 * B):
