@@ -281,12 +281,67 @@ k_upsample2x_bilinear_split8(const bf16* __restrict__ in_hi, const bf16* __restr
 // issue-active 81 %) are done once per patch element.  Tap order and weights are exactly those of the kernel above.
 // HQ = true: the outputs are the F16_Q8 plane pair instead (fp16 plane `out_hi`, FP8 byte plane `out_lo` written with the
 // per-tensor power-of-two `q8_scale`), feeding the fp16 + FP8 cross-term convolutions of the G2d up-blocks.
+// Instruction diet (round 2; the kernel was issue-bound at 37 instructions per output value, ncu issue-active 68 %): (1) interior
+// threads (i >= 1 and j >= 1: the four outputs always read patch rows / columns (0,1) and (1,2)) take a path without a single
+// select; only the first row / column of a frame runs the generic select path; (2) bf16 pairs are joined and split two at a
+// time on 32-bit words (one shift / mask per value, one F2FP per pair).  Same taps, weights and summation order: bit-identical.
+__device__ __forceinline__ void split2_pair(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                     // .x = a (low half)
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  const float ah = __uint_as_float(hi2 << 16), bh = __uint_as_float(hi2 & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// One output pixel x 8 channels from the 3 x 3 patch.  R0 / C0 >= 0: compile-time first patch row / column (interior
+// threads); R0 < 0: the run-time flags sh / sw pick rows (0,1) or (1,2) and columns (0,1) or (1,2) (first row / column of a frame).
+template <bool HQ, int R0, int C0>
+__device__ __forceinline__ void upsample_emit(const float (&P)[3][3][8], float lh, float lw, int64_t pos, int c8, int C,
+                                              void* out_hi_v, void* out_lo_v, float q8_scale, bool sh = false, bool sw = false) {
+  // taps (h0,w0), (h0,w1), (h1,w0), (h1,w1) in this order, weights (1-lh)(1-lw), (1-lh)lw, lh(1-lw), lh*lw
+  const float w00 = (1.f - lh) * (1.f - lw), w01 = (1.f - lh) * lw, w10 = lh * (1.f - lw), w11 = lh * lw;
+  float accs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v00, v01, v10, v11;
+    if (R0 >= 0) {
+      constexpr int r = R0 < 0 ? 0 : R0, c = C0 < 0 ? 0 : C0;
+      v00 = P[r][c][k]; v01 = P[r][c + 1][k]; v10 = P[r + 1][c][k]; v11 = P[r + 1][c + 1][k];
+    } else {
+      const float t0 = sh ? P[1][0][k] : P[0][0][k], t1 = sh ? P[1][1][k] : P[0][1][k], t2 = sh ? P[1][2][k] : P[0][2][k];
+      const float b0 = sh ? P[2][0][k] : P[1][0][k], b1 = sh ? P[2][1][k] : P[1][1][k], b2 = sh ? P[2][2][k] : P[1][2][k];
+      v00 = sw ? t1 : t0; v01 = sw ? t2 : t1; v10 = sw ? b1 : b0; v11 = sw ? b2 : b1;
+    }
+    float acc = w00 * v00;
+    acc += w01 * v01;
+    acc += w10 * v10;
+    acc += w11 * v11;
+    accs[k] = acc;
+  }
+  const int64_t o = (pos * (C >> 3) + c8) * 8;
+  if (HQ) {
+    f16x8 h;
+    uint2 a8, al8;
+    mp_hq_pack8(accs, h, a8, al8, q8_scale);
+    *reinterpret_cast<f16x8*>(reinterpret_cast<f16*>(out_hi_v) + o) = h;
+    uint8_t* q = reinterpret_cast<uint8_t*>(out_lo_v) + 2 * pos * C + mp_q8_off(c8 * 8);
+    *reinterpret_cast<uint2*>(q) = a8;
+    *reinterpret_cast<uint2*>(q + 64) = al8;
+  } else {
+    uint4 oh, ol;
+    split2_pair(accs[0], accs[1], oh.x, ol.x);
+    split2_pair(accs[2], accs[3], oh.y, ol.y);
+    split2_pair(accs[4], accs[5], oh.z, ol.z);
+    split2_pair(accs[6], accs[7], oh.w, ol.w);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out_hi_v) + o) = oh;
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out_lo_v) + o) = ol;
+  }
+}
+
 template <bool HQ>
 __global__ void __launch_bounds__(256)
 k_upsample2x_bilinear_split8_2x2(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, void* __restrict__ out_hi_v,
                                  void* __restrict__ out_lo_v, int H, int W, int C, float q8_scale) {
-  bf16* out_hi = reinterpret_cast<bf16*>(out_hi_v);
-  bf16* out_lo = reinterpret_cast<bf16*>(out_lo_v);
   // grid: x = chunks of (input column j, c8) pairs, y = input row i (output rows 2i, 2i+1), z = sample
   const int C8 = C >> 3;
   const int Ho = H * 2, Wo = W * 2;
@@ -301,62 +356,34 @@ k_upsample2x_bilinear_split8_2x2(const bf16* __restrict__ in_hi, const bf16* __r
   lin_src(2 * j, W, Wo, w0a, w1a, lwa);
   lin_src(2 * j + 1, W, Wo, w0b, w1b, lwb);
   const bool dh = h0b != h0a, dw = w0b != w0a;
-  int rr[3] = {h0a, min(h0a + 1, H - 1), min(h0a + 2, H - 1)};
-  int cc[3] = {w0a, min(w0a + 1, W - 1), min(w0a + 2, W - 1)};
+  const int rr[3] = {h0a, min(h0a + 1, H - 1), min(h0a + 2, H - 1)};
+  const int cc[3] = {w0a, min(w0a + 1, W - 1), min(w0a + 2, W - 1)};
   float P[3][3][8];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
       const int64_t o = ((((int64_t)n * H + rr[a]) * W + cc[b]) * C8 + c8) * 8;
-      const bf16x8v h = *reinterpret_cast<const bf16x8v*>(in_hi + o), l = *reinterpret_cast<const bf16x8v*>(in_lo + o);
+      const uint4 h = *reinterpret_cast<const uint4*>(in_hi + o), l = *reinterpret_cast<const uint4*>(in_lo + o);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw4[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) P[a][b][k] = mp_join(h.v[k], l.v[k]);
+      for (int k = 0; k < 4; ++k) {     // hi + lo is exact (the planes are the split of one fp32 value)
+        P[a][b][2 * k] = __uint_as_float(hw[k] << 16) + __uint_as_float(lw4[k] << 16);
+        P[a][b][2 * k + 1] = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw4[k] & 0xffff0000u);
+      }
     }
-  // rows feeding output row 2i+1: (dh ? rows 1,2 : rows 0,1); same for columns
-  float Q[2][3][8];
-#pragma unroll
-  for (int b = 0; b < 3; ++b)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      Q[0][b][k] = dh ? P[1][b][k] : P[0][b][k];
-      Q[1][b][k] = dh ? P[2][b][k] : P[1][b][k];
-    }
-  auto emit = [&](int ho, int wo, const float (*top)[8], const float (*bot)[8], bool shift, float lh, float lw) {
-    // taps (h0,w0), (h0,w1), (h1,w0), (h1,w1) in this order, weights (1-lh)(1-lw), (1-lh)lw, lh(1-lw), lh*lw
-    const float w00 = (1.f - lh) * (1.f - lw), w01 = (1.f - lh) * lw, w10 = lh * (1.f - lw), w11 = lh * lw;
-    bf16x8v oh, ol;
-    float accs[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float v00 = shift ? top[1][k] : top[0][k], v01 = shift ? top[2][k] : top[1][k];
-      const float v10 = shift ? bot[1][k] : bot[0][k], v11 = shift ? bot[2][k] : bot[1][k];
-      float acc = w00 * v00;
-      acc += w01 * v01;
-      acc += w10 * v10;
-      acc += w11 * v11;
-      accs[k] = acc;
-      if (!HQ) mp_split2(acc, oh.v[k], ol.v[k]);
-    }
-    const int64_t pos = ((int64_t)n * Ho + ho) * Wo + wo;
-    const int64_t o = (pos * C8 + c8) * 8;
-    if (HQ) {
-      f16x8 h;
-      uint2 a8, al8;
-      mp_hq_pack8(accs, h, a8, al8, q8_scale);
-      *reinterpret_cast<f16x8*>(reinterpret_cast<f16*>(out_hi_v) + o) = h;
-      uint8_t* q = reinterpret_cast<uint8_t*>(out_lo_v) + 2 * pos * C + mp_q8_off(c8 * 8);
-      *reinterpret_cast<uint2*>(q) = a8;
-      *reinterpret_cast<uint2*>(q + 64) = al8;
-      return;
-    }
-    *reinterpret_cast<bf16x8v*>(out_hi + o) = oh;
-    *reinterpret_cast<bf16x8v*>(out_lo + o) = ol;
-  };
-  emit(2 * i, 2 * j, P[0], P[1], false, lha, lwa);
-  emit(2 * i, 2 * j + 1, P[0], P[1], dw, lha, lwb);
-  emit(2 * i + 1, 2 * j, Q[0], Q[1], false, lhb, lwa);
-  emit(2 * i + 1, 2 * j + 1, Q[0], Q[1], dw, lhb, lwb);
+  const int64_t pos00 = ((int64_t)n * Ho + 2 * i) * Wo + 2 * j, pos10 = pos00 + Wo;
+  if (dh && dw) {      // interior thread (i >= 1 and j >= 1): no selects
+    upsample_emit<HQ, 0, 0>(P, lha, lwa, pos00, c8, C, out_hi_v, out_lo_v, q8_scale);
+    upsample_emit<HQ, 0, 1>(P, lha, lwb, pos00 + 1, c8, C, out_hi_v, out_lo_v, q8_scale);
+    upsample_emit<HQ, 1, 0>(P, lhb, lwa, pos10, c8, C, out_hi_v, out_lo_v, q8_scale);
+    upsample_emit<HQ, 1, 1>(P, lhb, lwb, pos10 + 1, c8, C, out_hi_v, out_lo_v, q8_scale);
+  } else {
+    upsample_emit<HQ, -1, -1>(P, lha, lwa, pos00, c8, C, out_hi_v, out_lo_v, q8_scale, false, false);
+    upsample_emit<HQ, -1, -1>(P, lha, lwb, pos00 + 1, c8, C, out_hi_v, out_lo_v, q8_scale, false, dw);
+    upsample_emit<HQ, -1, -1>(P, lhb, lwa, pos10, c8, C, out_hi_v, out_lo_v, q8_scale, dh, false);
+    upsample_emit<HQ, -1, -1>(P, lhb, lwb, pos10 + 1, c8, C, out_hi_v, out_lo_v, q8_scale, dh, dw);
+  }
 }
 
 extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, const void* in_lo, float* out_f32,
