@@ -240,6 +240,20 @@ int mp_apply_warping_field(const float* v, const float* warp_field, float* out, 
 int mp_apply_warping_field_backward(const float* grad_out, const float* v, const float* warp_field, float* grad_v,
                                     float* grad_warp_field, int N, int C, int D, int H, int W, int Df, int Hf, int Wf,
                                     void* stream);
+/* Weight gradient of a stride-1 "same" convolution (row f-2; nn.Conv2d / nn.Conv3d / Conv2d_WS / Conv3D_WS of the path,
+ * model.py:61-86, 439-471, back-propagated by train.py:188): x [N,D,H,W,Cin] and dy [N,D,H,W,Cout] channels-last fp32,
+ * dw [Cout, KD*KH*KW, Cin] fp32 (the K order of the packed forward weights; overwritten).  One GEMM per filter tap with
+ * K = positions on the tensor cores, three bf16 passes (fp32-grade), split-K with fp32 RED: reproducible to fp32 rounding,
+ * not bit for bit.  Cin, Cout multiples of 4; odd kernel sizes (padding k / 2). */
+int mp_conv_wgrad(const float* x, const float* dy, float* dw, int N, int D, int H, int W, int Cin, int Cout, int KD, int KH,
+                  int KW, void* stream);
+/* dL/dbias = column sums of dy [P, C] -> db [C] (overwritten). */
+int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* stream);
+/* nn.GroupNorm backward (model.py:302-316, 439-471) on channels-last fp32 tensors [N, S, C]: dx (fp32), dgamma / dbeta [C]
+ * (double, overwritten) from dy, the forward input x, the forward's `stats` [N,G,2] (mp_gn_stats or a convolution epilogue)
+ * and gamma (NULL = 1).  workspace: N*G*2 doubles. */
+int mp_group_norm_backward(const float* x, const float* dy, const double* stats, const float* gamma, float* dx, double* dgamma,
+                           double* dbeta, double* workspace, int N, int64_t S, int C, int G, float eps, void* stream);
 /* WarpGenerator tail (model.py:965-973): 64^3 field = affine_grid(theta[N,3,4], align_corners=False) +
  * trilinear(em 16^3 -> 64^3, align_corners=False).  em is CL [N,E,E,E,3]; out is NCDHW [N,3,G,G,G]. */
 int mp_warp_field(const float* em_cl, const float* theta, float* out, int N, int E, int G, void* stream);

@@ -1,0 +1,283 @@
+// Row f-2 (training step), second slice: the gradients that the forward operators of the path still lacked.
+//
+//   mp_conv_wgrad              dL/dW of a stride-1 "same" convolution (nn.Conv2d / nn.Conv3d, model.py:61-86, 439-471):
+//                              dW[co][tap][ci] = sum_p dY[p][co] * X[p + off(tap)][ci]   (zero outside the volume)
+//   mp_bias_grad               dL/db = column sums of dY
+//   mp_group_norm_backward     nn.GroupNorm backward (dX, dgamma, dbeta) from the forward's (sum, sum of squares) statistics
+//
+// mp_conv_wgrad: a GEMM per filter tap with K = positions (the long axis), M = Cout, N = Cin.  Both operands arrive
+// channels-last, i.e. K-outer / M-(N-)contiguous -- "transposed" for the tensor core -- so the fragments are fetched with
+// ldmatrix.trans from [position][channel] tiles; the products run as three bf16 passes (hi*hi + hi*lo + lo*hi, the split of
+// each fp32 value made while it is staged) with fp32 accumulation: fp32-grade gradients, like the forward and the data
+// gradient (ops.conv_input_grad on the tcgen05 kernel).  CTA = 64 x 64 tile of one tap over a slice of the positions; the
+// slices are summed with fp32 RED into dW (split-K).  This slice uses the legacy mma.sync path: the operand it needs (MN-major
+// A and B from channels-last tensors with a per-tap position shift and border mask) has no TMA box, so the tiles are built by
+// the threads anyway; moving the inner product to tcgen05 (smem descriptors with the transpose bits) is the follow-up.
+#include "common.cuh"
+
+namespace mpb200 {
+
+constexpr int WG_TM = 64, WG_TN = 64, WG_TK = 32;       // Cout tile, Cin tile, positions per stage
+constexpr int WG_PITCH = WG_TM + 8;                     // bf16 per smem row (144 B: conflict-free ldmatrix)
+constexpr int WG_THREADS = 128;
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  hi.x = *reinterpret_cast<const uint32_t*>(&h0);
+  hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __uint_as_float(hi.x << 16), v.y - __uint_as_float(hi.x & 0xffff0000u));
+  const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __uint_as_float(hi.y << 16), v.w - __uint_as_float(hi.y & 0xffff0000u));
+  lo.x = *reinterpret_cast<const uint32_t*>(&l0);
+  lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+
+struct WgradParams {
+  const float* x;      // [N, D, H, W, Cin]
+  const float* dy;     // [N, D, H, W, Cout]
+  float* dw;           // [Cout, KD*KH*KW, Cin], zeroed by the caller
+  int N, D, H, W, Cin, Cout, KD, KH, KW;
+  int tiles_n;         // Cin tiles
+  int64_t P, chunk;    // positions, positions per K slice (multiple of WG_TK)
+};
+
+__global__ void __launch_bounds__(WG_THREADS)
+k_conv_wgrad(const WgradParams p) {
+  __shared__ __align__(16) bf16 sA[2][2][WG_TK][WG_PITCH];      // [stage][hi, lo][position][co]
+  __shared__ __align__(16) bf16 sB[2][2][WG_TK][WG_PITCH];      // [stage][hi, lo][position][ci]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int co0 = (blockIdx.x / p.tiles_n) * WG_TM, ci0 = (blockIdx.x % p.tiles_n) * WG_TN;
+  const int tap = blockIdx.y;
+  const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
+  const int dz = kd - p.KD / 2, dyo = kh - p.KH / 2, dx = kw - p.KW / 2;
+  const int64_t k_begin = (int64_t)blockIdx.z * p.chunk;
+  const int64_t k_end = min(k_begin + p.chunk, p.P);
+  if (k_begin >= k_end) return;
+
+  // a thread stages 4 float4 of A (dY) and 4 of B (X) per 32-position stage: item f = tid + 128 j -> row f / 16, column 4 (f % 16)
+  const int col4 = (tid & 15) * 4, row_base = tid >> 4;          // rows row_base + 8 j
+  float4 ra[4], rb[4];
+  auto fetch = [&](int64_t k0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t pos = k0 + row_base + 8 * j;
+      ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pos < k_end) {
+        if (co0 + col4 < p.Cout) ra[j] = __ldg(reinterpret_cast<const float4*>(p.dy + pos * p.Cout + co0 + col4));
+        // position -> (n, z, y, x); the tap reads x at (z + dz, y + dy, x + dx): zero outside the volume
+        int64_t t = pos;
+        const int xx = (int)(t % p.W); t /= p.W;
+        const int yy = (int)(t % p.H); t /= p.H;
+        const int zz = (int)(t % p.D);
+        const int zs = zz + dz, ys = yy + dyo, xs = xx + dx;
+        if (zs >= 0 && zs < p.D && ys >= 0 && ys < p.H && xs >= 0 && xs < p.W && ci0 + col4 < p.Cin) {
+          const int64_t q = pos + ((int64_t)dz * p.H + dyo) * p.W + dx;
+          rb[j] = __ldg(reinterpret_cast<const float4*>(p.x + q * p.Cin + ci0 + col4));
+        }
+      }
+    }
+  };
+  auto stage = [&](int s) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = row_base + 8 * j;
+      uint2 hi, lo;
+      split4(ra[j], hi, lo);
+      *reinterpret_cast<uint2*>(&sA[s][0][r][col4]) = hi;
+      *reinterpret_cast<uint2*>(&sA[s][1][r][col4]) = lo;
+      split4(rb[j], hi, lo);
+      *reinterpret_cast<uint2*>(&sB[s][0][r][col4]) = hi;
+      *reinterpret_cast<uint2*>(&sB[s][1][r][col4]) = lo;
+    }
+  };
+
+  // warp tile: 32 (co) x 32 (ci) = 2 x 4 m16n8 accumulators
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+  // ldmatrix.trans lane addresses (see the header): A^T tile [k][m], B tile [k][n]
+  const int a_row = (lane & 7) + ((lane >> 4) & 1) * 8, a_col = ((lane >> 3) & 1) * 8;
+  const int b_row = (lane & 7) + ((lane >> 3) & 1) * 8, b_col = ((lane >> 4) & 1) * 8;
+
+  fetch(k_begin);
+  int s = 0;
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += WG_TK, s ^= 1) {
+    stage(s);
+    __syncthreads();
+    if (k0 + WG_TK < k_end) fetch(k0 + WG_TK);          // next stage's global loads fly under this stage's MMAs
+#pragma unroll
+    for (int ks = 0; ks < WG_TK; ks += 16) {
+      uint32_t ah[2][4], al[2][4], bh[2][4], bl[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        ldsm_x4_t(ah[i], (uint32_t)__cvta_generic_to_shared(&sA[s][0][ks + a_row][wm + 16 * i + a_col]));
+        ldsm_x4_t(al[i], (uint32_t)__cvta_generic_to_shared(&sA[s][1][ks + a_row][wm + 16 * i + a_col]));
+        ldsm_x4_t(bh[i], (uint32_t)__cvta_generic_to_shared(&sB[s][0][ks + b_row][wn + 16 * i + b_col]));
+        ldsm_x4_t(bl[i], (uint32_t)__cvta_generic_to_shared(&sB[s][1][ks + b_row][wn + 16 * i + b_col]));
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t bh0 = bh[j >> 1][(j & 1) * 2], bh1 = bh[j >> 1][(j & 1) * 2 + 1];
+          const uint32_t bl0 = bl[j >> 1][(j & 1) * 2], bl1 = bl[j >> 1][(j & 1) * 2 + 1];
+          mma_bf16(acc[i][j], al[i], bh0, bh1);           // small terms first
+          mma_bf16(acc[i][j], ah[i], bl0, bl1);
+          mma_bf16(acc[i][j], ah[i], bh0, bh1);
+        }
+    }
+    // (two stages: the next iteration writes the other buffer; the barrier at its top orders this stage's reads before the
+    //  iteration after next overwrites it)
+  }
+  // split-K reduction: fp32 RED into dW[co][tap][ci]
+  const int g = lane >> 2, t = lane & 3;
+  const int T = p.KD * p.KH * p.KW;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int co = co0 + wm + 16 * i + g + (e >> 1) * 8, ci = ci0 + wn + 8 * j + 2 * t + (e & 1);
+        if (co < p.Cout && ci < p.Cin) atomicAdd(p.dw + ((int64_t)co * T + tap) * p.Cin + ci, acc[i][j][e]);
+      }
+}
+
+// column sums of dY [P, C] -> db [C] (fp32 RED; db zeroed by the caller)
+__global__ void k_bias_grad(const float* __restrict__ dy, float* __restrict__ db, int64_t P, int C, int64_t rows_per_block) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, P);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += dy[r * C + c];
+    atomicAdd(db + c, s);
+  }
+}
+
+// ---- GroupNorm backward.  y = (x - mean_g) * rstd_g * gamma_c + beta_c over the group's S * C/G elements of one sample.
+//   dgamma_c = sum_{n,s} dy * xhat      dbeta_c = sum_{n,s} dy
+//   dx = rstd * (dy*gamma - mean_g(dy*gamma) - xhat * mean_g(dy*gamma*xhat))
+// pass 1: per (sample, group) the two group sums (double), per channel dgamma / dbeta (double RED); pass 2: elementwise.
+__global__ void __launch_bounds__(256)
+k_gn_bwd_reduce(const float* __restrict__ x, const float* __restrict__ dy, const double* __restrict__ stats,
+                const float* __restrict__ gamma, double* __restrict__ gsum, double* __restrict__ dgamma,
+                double* __restrict__ dbeta, int64_t S, int C, int G, float eps, int64_t rows_per_block) {
+  // grid: x = row blocks of one sample, y = sample; thread = channel (C <= 1024)
+  const int n = blockIdx.y, c = threadIdx.x;
+  if (c >= C) return;
+  const int cpg = C / G, g = c / cpg;
+  const double cnt = (double)S * cpg;
+  const double mean = stats[((int64_t)n * G + g) * 2] / cnt;
+  const double var = fmax(stats[((int64_t)n * G + g) * 2 + 1] / cnt - mean * mean, 0.0);
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
+  const float gm = gamma ? gamma[c] : 1.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, S);
+  double s_dy = 0.0, s_dyx = 0.0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t o = ((int64_t)n * S + r) * C + c;
+    const float d = dy[o], xh = (x[o] - mu) * rstd;
+    s_dy += d;
+    s_dyx += (double)d * xh;
+  }
+  atomicAdd(dbeta + c, s_dy);
+  atomicAdd(dgamma + c, s_dyx);
+  atomicAdd(gsum + ((int64_t)n * G + g) * 2, s_dy * gm);
+  atomicAdd(gsum + ((int64_t)n * G + g) * 2 + 1, s_dyx * gm);
+}
+
+__global__ void __launch_bounds__(256)
+k_gn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, const double* __restrict__ stats,
+               const float* __restrict__ gamma, const double* __restrict__ gsum, float* __restrict__ dx, int64_t S, int C, int G,
+               float eps, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int64_t n = i / ((int64_t)S * C);
+  const int cpg = C / G, g = c / cpg;
+  const double cnt = (double)S * cpg;
+  const double mean = stats[(n * G + g) * 2] / cnt;
+  const double var = fmax(stats[(n * G + g) * 2 + 1] / cnt - mean * mean, 0.0);
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
+  const float m1 = (float)(gsum[(n * G + g) * 2] / cnt), m2 = (float)(gsum[(n * G + g) * 2 + 1] / cnt);
+  const float gm = gamma ? gamma[c] : 1.f;
+  const float xh = (x[i] - mu) * rstd;
+  dx[i] = rstd * (dy[i] * gm - m1 - xh * m2);
+}
+
+}  // namespace mpb200
+
+extern "C" int mp_conv_wgrad(const float* x, const float* dy, float* dw, int N, int D, int H, int W, int Cin, int Cout, int KD,
+                             int KH, int KW, void* stream) {
+  using namespace mpb200;
+  MP_REQUIRE(x && dy && dw, "mp_conv_wgrad: null pointer");
+  MP_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "mp_conv_wgrad: bad dims");
+  MP_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "mp_conv_wgrad: channel counts must be multiples of 4 (16-byte rows), got %d -> %d",
+             Cin, Cout);
+  MP_REQUIRE(KD % 2 == 1 && KH % 2 == 1 && KW % 2 == 1 && KD * KH * KW <= 65535, "mp_conv_wgrad: odd kernel sizes only");
+  WgradParams p;
+  p.x = x; p.dy = dy; p.dw = dw;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KH = KH; p.KW = KW;
+  p.tiles_n = (Cin + WG_TN - 1) / WG_TN;
+  p.P = (int64_t)N * D * H * W;
+  const int T = KD * KH * KW;
+  const int64_t tiles = (int64_t)((Cout + WG_TM - 1) / WG_TM) * p.tiles_n * T;
+  // split K so that the grid is ~8 CTAs per SM deep, slices of at least 8 stages
+  int64_t slices = (8 * 148 + tiles - 1) / tiles;
+  const int64_t max_slices = (p.P + 8 * WG_TK - 1) / (8 * WG_TK);
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  if (slices > 65535) slices = 65535;
+  p.chunk = ((p.P + slices - 1) / slices + WG_TK - 1) / WG_TK * WG_TK;
+  slices = (p.P + p.chunk - 1) / p.chunk;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * T * Cin, mp_stream(stream));
+  MP_REQUIRE(e == cudaSuccess, "mp_conv_wgrad: memset: %s", cudaGetErrorString(e));
+  dim3 grid((unsigned)(tiles / T), (unsigned)T, (unsigned)slices);
+  k_conv_wgrad<<<grid, WG_THREADS, 0, mp_stream(stream)>>>(p);
+  MP_LAUNCH_CHECK("mp_conv_wgrad");
+  return 0;
+}
+
+extern "C" int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* stream) {
+  MP_REQUIRE(dy && db && P > 0 && C > 0, "mp_bias_grad: bad arguments");
+  cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)C, mp_stream(stream));
+  MP_REQUIRE(e == cudaSuccess, "mp_bias_grad: memset: %s", cudaGetErrorString(e));
+  const int64_t rows = 256;
+  const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
+  mpb200::k_bias_grad<<<(unsigned)((P + rows - 1) / rows), threads, 0, mp_stream(stream)>>>(dy, db, P, C, rows);
+  MP_LAUNCH_CHECK("mp_bias_grad");
+  return 0;
+}
+
+extern "C" int mp_group_norm_backward(const float* x, const float* dy, const double* stats, const float* gamma, float* dx,
+                                      double* dgamma, double* dbeta, double* workspace, int N, int64_t S, int C, int G, float eps,
+                                      void* stream) {
+  MP_REQUIRE(x && dy && stats && dx && dgamma && dbeta && workspace, "mp_group_norm_backward: null pointer");
+  MP_REQUIRE(N > 0 && N <= 65535 && S > 0 && C > 0 && C <= 1024 && G > 0 && C % G == 0, "mp_group_norm_backward: bad dims");
+  cudaStream_t st = mp_stream(stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(double) * (size_t)N * G * 2, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dgamma, 0, sizeof(double) * (size_t)C, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(double) * (size_t)C, st);
+  MP_REQUIRE(e == cudaSuccess, "mp_group_norm_backward: memset: %s", cudaGetErrorString(e));
+  const int64_t rows = 128;
+  const int threads = ((C + 31) / 32) * 32;
+  dim3 grid((unsigned)((S + rows - 1) / rows), (unsigned)N);
+  mpb200::k_gn_bwd_reduce<<<grid, threads, 0, st>>>(x, dy, stats, gamma, workspace, dgamma, dbeta, S, C, G, eps, rows);
+  MP_LAUNCH_CHECK("mp_group_norm_backward (reduce)");
+  const int64_t total = (int64_t)N * S * C;
+  mpb200::k_gn_bwd_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, stats, gamma, workspace, dx, S, C, G, eps, total);
+  MP_LAUNCH_CHECK("mp_group_norm_backward (apply)");
+  return 0;
+}

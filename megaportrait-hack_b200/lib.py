@@ -154,6 +154,9 @@ _SIGNATURES = {
     "mp_apply_warping_field_brick": (c_int, [_P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                              c_int, c_int, _P]),
     "mp_gs_brick_tune": (c_int, [POINTER(c_int), c_int]),
+    "mp_conv_wgrad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_bias_grad": (c_int, [_P, _P, c_int64, c_int, _P]),
+    "mp_group_norm_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_float, _P]),
     "mp_apply_warping_field_backward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_warp_field": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "mp_warp_fused_cl": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

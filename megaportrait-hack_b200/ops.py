@@ -783,6 +783,106 @@ class WarpFunction(torch.autograd.Function):
         return gv, gwf
 
 
+def conv_weight_grad(x: Act, grad_out: Act, k: Tuple[int, int, int]) -> torch.Tensor:
+    """dL/dW of a stride-1 "same" convolution (row f-2): x, grad_out channels-last fp32 Acts -> (Cout, Cin, kd, kh, kw) fp32.
+    One tensor-core GEMM per filter tap with K = positions (three bf16 passes, fp32 accumulation)."""
+    N, D, H, W, Cin = x.shape
+    Cout = grad_out.shape[-1]
+    if x.f32 is None or grad_out.f32 is None or tuple(grad_out.shape[:4]) != (N, D, H, W):
+        raise RuntimeError(f"conv_weight_grad: fp32 channels-last tensors of one spatial size, got {x.shape} / {grad_out.shape}")
+    kd, kh, kw = k
+    dw = torch.empty((Cout, kd * kh * kw, Cin), dtype=torch.float32, device=x.device)
+    L = _lib.load()
+    _lib.check(L.mp_conv_wgrad(_p(x.f32), _p(grad_out.f32), _p(dw), N, D, H, W, Cin, Cout, kd, kh, kw, _stream()),
+               "mp_conv_wgrad")
+    _count(2)
+    return dw.view(Cout, kd, kh, kw, Cin).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def bias_grad(grad_out: Act) -> torch.Tensor:
+    C = grad_out.shape[-1]
+    db = torch.empty((C,), dtype=torch.float32, device=grad_out.device)
+    L = _lib.load()
+    _lib.check(L.mp_bias_grad(_p(grad_out.f32), _p(db), grad_out.f32.numel() // C, C, _stream()), "mp_bias_grad")
+    _count(2)
+    return db
+
+
+def group_norm_backward(x: Act, grad_out: Act, stats: torch.Tensor, G: int, gamma: Optional[torch.Tensor], eps: float = 1e-5):
+    """nn.GroupNorm backward on channels-last fp32 Acts: -> (dx Act, dgamma [C] fp32, dbeta [C] fp32)."""
+    N, D, H, W, C = x.shape
+    dx = _alloc(x.shape, x.device, True, False)
+    dg = torch.empty((C,), dtype=torch.float64, device=x.device)
+    db = torch.empty((C,), dtype=torch.float64, device=x.device)
+    ws = torch.empty((N, G, 2), dtype=torch.float64, device=x.device)
+    L = _lib.load()
+    _lib.check(L.mp_group_norm_backward(_p(x.f32), _p(grad_out.f32), _p(stats), _p(gamma), _p(dx.f32), _p(dg), _p(db), _p(ws),
+                                        N, D * H * W, C, G, eps, _stream()), "mp_group_norm_backward")
+    _count(5)
+    return dx, dg.float(), db.float()
+
+
+def _to_cl_act(t: torch.Tensor) -> Act:
+    """NCHW / NCDHW fp32 -> channels-last fp32 Act."""
+    return from_nchw(t.detach().float().contiguous(), f32=True, split=False)
+
+
+class ConvFunction(torch.autograd.Function):
+    """`F.conv2d` / `F.conv3d` (stride 1, padding k // 2) on libmpb200 with CUDA backward (row f-2): forward = the tcgen05
+    implicit GEMM, dX = the same kernel on flipped / transposed weights, dW = `mp_conv_wgrad`, db = `mp_bias_grad`.
+    Tensors cross the boundary in the reference layout (NCHW / NCDHW fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        nd = x.dim()
+        ctx.nd = nd
+        a = _to_cl_act(x)
+        ensure_split(a)
+        k = tuple(weight.shape[2:]) if nd == 5 else (1,) + tuple(weight.shape[2:])
+        ctx.k = k
+        ctx.save_for_backward(x.detach(), weight.detach())
+        ctx.has_bias = bias is not None
+        out, _ = conv(a, pack_conv(weight.detach(), None if bias is None else bias.detach(), x.device), f32=True)
+        return to_nchw(out, nd)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        g = _to_cl_act(grad_out)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            ensure_split(g)
+            gx = to_nchw(conv_input_grad(g, pack_conv_dgrad(weight, x.device)), ctx.nd)
+        if ctx.needs_input_grad[1]:
+            gw = conv_weight_grad(_to_cl_act(x), g, ctx.k)
+            if ctx.nd == 4:
+                gw = gw.squeeze(2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = bias_grad(g)
+        return gx, gw, gb
+
+
+class GroupNormFunction(torch.autograd.Function):
+    """`F.group_norm` on libmpb200 with CUDA backward (row f-2); NCHW / NCDHW fp32 in and out."""
+
+    @staticmethod
+    def forward(ctx, x, G, gamma, beta, eps):
+        a = _to_cl_act(x)
+        stats = gn_stats(a, G)
+        ab = gn_finalize(stats, a.shape, G, None if gamma is None else gamma.detach().float().contiguous(),
+                         None if beta is None else beta.detach().float().contiguous(), eps=eps)
+        ctx.save_for_backward(x.detach(), stats, None if gamma is None else gamma.detach().float().contiguous())
+        ctx.G, ctx.eps, ctx.nd = G, eps, x.dim()
+        return to_nchw(affine_act(a, ab, None, ACT_NONE, f32=True, split=False), x.dim())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, stats, gamma = ctx.saved_tensors
+        dx, dg, db = group_norm_backward(_to_cl_act(x), _to_cl_act(grad_out), stats, ctx.G, gamma, ctx.eps)
+        return (to_nchw(dx, ctx.nd), None, dg if ctx.needs_input_grad[2] else None,
+                db if ctx.needs_input_grad[3] else None, None)
+
+
 def warp_field(em_cl: torch.Tensor, theta: torch.Tensor, G: int = 64) -> torch.Tensor:
     """em_cl [N,E,E,E,3] fp32, theta [N,3,4] -> [N,3,G,G,G] (model.py:965-973)."""
     _chk_cuda(em_cl, torch.float32, "warp_field em")

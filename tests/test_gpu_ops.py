@@ -1049,3 +1049,82 @@ def test_conv_f16_q8_fused_shortcut(ops, pair):
         a2 = mk(x)
         a2.q8_scale = s * 2
         ops.conv(mk(t), pw, src2=a2, act=ops.ACT_RELU, f32=True)
+
+
+@pytest.mark.parametrize("case", [
+    dict(N=2, Ci=32, Co=48, sp=(4, 16, 16), k=(3, 3, 3)),          # Conv3d, ragged 64-tiles (48 / 32 channels)
+    dict(N=1, Ci=96, Co=96, sp=(16, 32, 32), k=(3, 3, 3)),         # the 96 -> 96 volume convolution of Eapp / G3d, smaller volume
+    dict(N=2, Ci=64, Co=128, sp=(24, 40), k=(3, 3)),               # Conv2d
+    dict(N=1, Ci=128, Co=64, sp=(16, 16), k=(1, 1)),               # 1x1
+], ids=["c3d_small", "c3d_96", "c2d", "c2d_1x1"])
+def test_conv_function_gradients_match_autograd(ops, case):
+    """Row f-2: `ops.ConvFunction` (forward on the tcgen05 kernel; dX on the same kernel with flipped weights; dW = mp_conv_wgrad:
+    one tensor-core GEMM per tap with K = positions; db = mp_bias_grad) against torch autograd in float64."""
+    N, Ci, Co, sp, k = case["N"], case["Ci"], case["Co"], case["sp"], case["k"]
+    nd = len(sp)
+    x = rnd(N, Ci, *sp, seed=151)
+    w = rnd(Co, Ci, *k, seed=152) / math.sqrt(Ci * math.prod(k))
+    b = rnd(Co, seed=153) * 0.1
+    go = rnd(N, Co, *sp, seed=154)
+    conv = F.conv3d if nd == 3 else F.conv2d
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = conv(xd, wd, bd, padding=tuple(kk // 2 for kk in k))
+    ref.backward(go.double())
+    xc, wc, bc = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    out = ops.ConvFunction.apply(xc, wc, bc)
+    out.backward(go.to(DEV))
+    assert relerr(out.detach().cpu(), ref.detach().float()) < 3e-5       # three-pass split-bf16 forward (2^-16 products)
+    for name, got, want in (("dx", xc.grad, xd.grad), ("dw", wc.grad, wd.grad), ("db", bc.grad, bd.grad)):
+        assert got.shape == want.shape, name
+        e = relerr(got.cpu(), want.float())
+        print(name, e)
+        assert e < 2e-5, (name, e)
+
+
+def test_group_norm_function_gradients_match_autograd(ops):
+    """Row f-2: `ops.GroupNormFunction` (forward: stats + affine; backward: mp_group_norm_backward) against torch autograd."""
+    N, C, sp, G = 2, 64, (4, 12, 20), 32
+    x = rnd(N, C, *sp, seed=161) * 1.7 + 0.4
+    gamma, beta = rnd(C, seed=162) * 0.3 + 1.0, rnd(C, seed=163) * 0.2
+    go = rnd(N, C, *sp, seed=164)
+    xd, gd, bd = (t.double().requires_grad_(True) for t in (x, gamma, beta))
+    ref = F.group_norm(xd, G, gd, bd, 1e-5)
+    ref.backward(go.double())
+    xc, gc, bc = (t.to(DEV).requires_grad_(True) for t in (x, gamma, beta))
+    out = ops.GroupNormFunction.apply(xc, G, gc, bc, 1e-5)
+    out.backward(go.to(DEV))
+    assert relerr(out.detach().cpu(), ref.detach().float()) < 1e-5
+    for name, got, want in (("dx", xc.grad, xd.grad), ("dgamma", gc.grad, gd.grad), ("dbeta", bc.grad, bd.grad)):
+        e = relerr(got.cpu(), want.float())
+        print(name, e)
+        assert e < 1e-5, (name, e)
+
+
+def test_conv_gn_relu_block_trains_through_libmpb200(ops):
+    """Row f-2: conv3d -> GroupNorm -> ReLU -> conv3d (+ input skip) -- the shape of the path's residual blocks (model.py:439-471)
+    -- differentiated end to end through the libmpb200 Functions: every parameter gradient and the input gradient against
+    torch autograd in float64."""
+    N, C, sp = 1, 32, (4, 16, 16)
+    x = rnd(N, C, *sp, seed=171)
+    w1, w2 = rnd(C, C, 3, 3, 3, seed=172) / math.sqrt(27 * C), rnd(C, C, 3, 3, 3, seed=173) / math.sqrt(27 * C)
+    b1, b2 = rnd(C, seed=174) * 0.1, rnd(C, seed=175) * 0.1
+    gamma, beta = rnd(C, seed=176) * 0.3 + 1.0, rnd(C, seed=177) * 0.2
+    go = rnd(N, C, *sp, seed=178)
+    leaves = (x, w1, b1, gamma, beta, w2, b2)
+
+    def block(conv, gn, t):
+        xx, ww1, bb1, gg, be, ww2, bb2 = t
+        h = torch.relu(gn(conv(xx, ww1, bb1), gg, be))
+        return conv(h, ww2, bb2) + xx
+
+    td = [t.double().requires_grad_(True) for t in leaves]
+    ref = block(lambda a, w, b: F.conv3d(a, w, b, padding=1), lambda a, g, b: F.group_norm(a, 8, g, b, 1e-5), td)
+    ref.backward(go.double())
+    tc = [t.to(DEV).requires_grad_(True) for t in leaves]
+    out = block(lambda a, w, b: ops.ConvFunction.apply(a, w, b), lambda a, g, b: ops.GroupNormFunction.apply(a, 8, g, b, 1e-5), tc)
+    out.backward(go.to(DEV))
+    assert relerr(out.detach().cpu(), ref.detach().float()) < 1e-5
+    for name, got, want in zip(("dx", "dw1", "db1", "dgamma", "dbeta", "dw2", "db2"), tc, td):
+        e = relerr(got.grad.cpu(), want.grad.float())
+        print(name, e)
+        assert e < 3e-5, (name, e)
