@@ -175,27 +175,29 @@ __global__ void __launch_bounds__(256)
 k_gn_bwd_reduce(const float* __restrict__ x, const float* __restrict__ dy, const double* __restrict__ stats,
                 const float* __restrict__ gamma, double* __restrict__ gsum, double* __restrict__ dgamma,
                 double* __restrict__ dbeta, int64_t S, int C, int G, float eps, int64_t rows_per_block) {
-  // grid: x = row blocks of one sample, y = sample; thread = channel (C <= 1024)
-  const int n = blockIdx.y, c = threadIdx.x;
-  if (c >= C) return;
-  const int cpg = C / G, g = c / cpg;
+  // grid: x = row blocks of one sample, y = sample; a thread walks the channels c = tid, tid + 256, ...
+  const int n = blockIdx.y;
+  const int cpg = C / G;
   const double cnt = (double)S * cpg;
-  const double mean = stats[((int64_t)n * G + g) * 2] / cnt;
-  const double var = fmax(stats[((int64_t)n * G + g) * 2 + 1] / cnt - mean * mean, 0.0);
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
-  const float gm = gamma ? gamma[c] : 1.f;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, S);
-  double s_dy = 0.0, s_dyx = 0.0;
-  for (int64_t r = r0; r < r1; ++r) {
-    const int64_t o = ((int64_t)n * S + r) * C + c;
-    const float d = dy[o], xh = (x[o] - mu) * rstd;
-    s_dy += d;
-    s_dyx += (double)d * xh;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double mean = stats[((int64_t)n * G + g) * 2] / cnt;
+    const double var = fmax(stats[((int64_t)n * G + g) * 2 + 1] / cnt - mean * mean, 0.0);
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
+    const float gm = gamma ? gamma[c] : 1.f;
+    double s_dy = 0.0, s_dyx = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+      const int64_t o = ((int64_t)n * S + r) * C + c;
+      const float d = dy[o], xh = (x[o] - mu) * rstd;
+      s_dy += d;
+      s_dyx += (double)d * xh;
+    }
+    atomicAdd(dbeta + c, s_dy);
+    atomicAdd(dgamma + c, s_dyx);
+    atomicAdd(gsum + ((int64_t)n * G + g) * 2, s_dy * gm);
+    atomicAdd(gsum + ((int64_t)n * G + g) * 2 + 1, s_dyx * gm);
   }
-  atomicAdd(dbeta + c, s_dy);
-  atomicAdd(dgamma + c, s_dyx);
-  atomicAdd(gsum + ((int64_t)n * G + g) * 2, s_dy * gm);
-  atomicAdd(gsum + ((int64_t)n * G + g) * 2 + 1, s_dyx * gm);
 }
 
 __global__ void __launch_bounds__(256)
@@ -265,14 +267,14 @@ extern "C" int mp_group_norm_backward(const float* x, const float* dy, const dou
                                       double* dgamma, double* dbeta, double* workspace, int N, int64_t S, int C, int G, float eps,
                                       void* stream) {
   MP_REQUIRE(x && dy && stats && dx && dgamma && dbeta && workspace, "mp_group_norm_backward: null pointer");
-  MP_REQUIRE(N > 0 && N <= 65535 && S > 0 && C > 0 && C <= 1024 && G > 0 && C % G == 0, "mp_group_norm_backward: bad dims");
+  MP_REQUIRE(N > 0 && N <= 65535 && S > 0 && C > 0 && G > 0 && C % G == 0, "mp_group_norm_backward: bad dims");
   cudaStream_t st = mp_stream(stream);
   cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(double) * (size_t)N * G * 2, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(dgamma, 0, sizeof(double) * (size_t)C, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(double) * (size_t)C, st);
   MP_REQUIRE(e == cudaSuccess, "mp_group_norm_backward: memset: %s", cudaGetErrorString(e));
   const int64_t rows = 128;
-  const int threads = ((C + 31) / 32) * 32;
+  const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
   dim3 grid((unsigned)((S + rows - 1) / rows), (unsigned)N);
   mpb200::k_gn_bwd_reduce<<<grid, threads, 0, st>>>(x, dy, stats, gamma, workspace, dgamma, dbeta, S, C, G, eps, rows);
   MP_LAUNCH_CHECK("mp_group_norm_backward (reduce)");

@@ -57,6 +57,13 @@ def _require_inference(mod: nn.Module, *tensors) -> None:
                                   "call under torch.no_grad()")
 
 
+def _wants_grad(mod: nn.Module, *tensors) -> bool:
+    """Autograd is recording and an input or a parameter of `mod` asks for a gradient: modules that have a differentiable
+    libmpb200 path (row f-2: ResBlock3D, G3d) take it; the others raise."""
+    return torch.is_grad_enabled() and (any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+                                        or any(p.requires_grad for p in mod.parameters()))
+
+
 def _require_no_grad(mod: nn.Module, *tensors) -> None:
     """Entry points that run under `torch.no_grad()` internally: called with autograd recording on and anything that
     asks for a gradient (an input, or any parameter of `mod`), they would hand back detached outputs and the caller's
@@ -337,7 +344,21 @@ class ResBlock3D(nn.Module, _Packed):
         h, st = ops.conv(h, P["c2"], f32=True, stats_groups=32)
         return ops.group_norm_act(h, 32, st, *P["g2"], res=idt, act=ACT_RELU, f32=f32, split=split)
 
+    def _forward_autograd(self, x):
+        """Differentiable form (row f-2): the same operators as autograd Functions whose forward AND backward run on libmpb200
+        (ops.ConvFunction: tcgen05 forward / data gradient, tensor-core weight gradient; ops.GroupNormFunction)."""
+        if self.upsample:
+            raise NotImplementedError("ResBlock3D(upsample=True) is never used by the reference hot path")
+        conv, gn = ops.ConvFunction.apply, ops.GroupNormFunction.apply
+        idt = conv(x, self.shortcut.weight, self.shortcut.bias) if isinstance(self.shortcut, nn.Conv3d) else x
+        h = torch.relu(gn(conv(x, self.conv1.weight, self.conv1.bias), 32, self.gn1.weight, self.gn1.bias, self.gn1.eps))
+        h = gn(conv(h, self.conv2.weight, self.conv2.bias), 32, self.gn2.weight, self.gn2.bias, self.gn2.eps)
+        return torch.relu(h + idt)
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            _require_inference(self, x.detach())         # (device check only)
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
         return ops.to_nchw(self._forward_cl(a, f32=True, split=False), 5)
@@ -379,7 +400,19 @@ class G3d(nn.Module):
         out, _ = ops.conv(x, self._final_pack(), f32=True)
         return out
 
+    def _forward_autograd(self, x):
+        """Differentiable form (row f-2): residual blocks and the final convolution through the libmpb200 Functions; the 2x
+        average pools and trilinear upsamples between them (1 % of the FLOPs) through ATen's autograd."""
+        for i, m in enumerate(self.downsampling):
+            x = m._forward_autograd(x) if i % 2 == 0 else F.avg_pool3d(x, 2, 2)
+        for i, m in enumerate(self.upsampling):
+            x = m._forward_autograd(x) if i % 2 == 0 else F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+        return ops.ConvFunction.apply(x, self.final_conv.weight, self.final_conv.bias)
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
         return ops.to_nchw(self._forward_cl(a), 5)

@@ -1,5 +1,7 @@
+#!/usr/bin/env python
+"""In-graph time of every stage of the source half (one CUDA graph per stage, replayed): developer tool, run on a B200 via gpurun."""
 import os, sys, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(sys.path[0], "tests"))
 import __graft_entry__ as entry
 entry.build()
 from conftest import synthetic_pair

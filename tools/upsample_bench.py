@@ -1,5 +1,8 @@
+#!/usr/bin/env python
+"""Bilinear x2 upsample kernels (split-bf16 and fp16 + FP8 outputs) at the three G2d shapes, batch 32: ms and TB/s."""
 import sys, torch
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from megaportrait_hack_b200 import lib, ops
 lib.build()
 def timed(fn, reps=10):
