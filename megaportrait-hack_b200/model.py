@@ -128,7 +128,15 @@ def _as_f32_cuda(x: torch.Tensor) -> torch.Tensor:
 class Conv2d_WS(nn.Conv2d):
     """model.py:54-69: weight-standardised conv."""
 
+    def _forward_autograd(self, x):
+        """Differentiable form (row f-2): the standardisation is a float64 torch expression on the weight (autograd carries its
+        Jacobian), the convolution and its three gradients run on libmpb200 (ops.ConvFunction)."""
+        return ops.ConvFunction.apply(x, ops.standardize_weight(self.weight).float(), self.bias)
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         pw = ops.pack_conv(ops.standardize_weight(self.weight), self.bias, x.device)
         a = ops.from_nchw(_as_f32_cuda(x))
@@ -139,7 +147,13 @@ class Conv2d_WS(nn.Conv2d):
 class Conv3D_WS(nn.Conv3d):
     """model.py:71-86."""
 
+    def _forward_autograd(self, x):
+        return ops.ConvFunction.apply(x, ops.standardize_weight(self.weight).float(), self.bias)
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         pw = ops.pack_conv(ops.standardize_weight(self.weight), self.bias, x.device)
         a = ops.from_nchw(_as_f32_cuda(x))
@@ -180,7 +194,18 @@ class ResBlock_Custom(nn.Module, _Packed):
         out, _ = ops.conv(h, P["conv"], res=out2, f32=True)
         return out
 
+    def _forward_autograd(self, x):
+        """Differentiable form (row f-2): ops.ConvFunction / ops.GroupNormFunction (CUDA forward and backward)."""
+        conv, gn = ops.ConvFunction.apply, ops.GroupNormFunction.apply
+        out2 = conv(x, self.conv_res.weight, self.conv_res.bias)
+        h = torch.relu(gn(x, 32, None, None, 1e-5))
+        h = torch.relu(gn(self.conv_ws._forward_autograd(h), 32, None, None, 1e-5))
+        return conv(h, self.conv.weight, self.conv.bias) + out2
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
         out = self._forward_cl(a, None)
@@ -206,7 +231,15 @@ class AdaptiveGroupNorm(nn.Module):
         return (_f32c(self.group_norm.weight), _f32c(self.group_norm.bias), _f32c(self.weight).view(-1),
                 _f32c(self.bias).view(-1))
 
+    def _forward_autograd(self, x):
+        """Differentiable form (row f-2): GroupNorm forward / backward on libmpb200, the second affine as a torch expression."""
+        gn = self.group_norm
+        return ops.GroupNormFunction.apply(x, self.num_groups, gn.weight, gn.bias, gn.eps) * self.weight + self.bias
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=False)
         g, b, g2, b2 = self._affine()
@@ -251,7 +284,20 @@ class ResBlock3D_Adaptive(nn.Module, _Packed):
         res = x if P["rc"] is None else ops.conv(x, P["rc"], f32=True)[0]
         return ops.group_norm_act(h, G, st, *P["n2"], res=res, act=ACT_RELU, f32=f32, split=split)
 
+    def _forward_autograd(self, x):
+        """Differentiable form (row f-2)."""
+        if self.upsample:
+            raise NotImplementedError("ResBlock3D_Adaptive(upsample=True) is never used by the reference hot path")
+        conv = ops.ConvFunction.apply
+        h = torch.relu(self.norm1._forward_autograd(conv(x, self.conv1.weight, self.conv1.bias)))
+        h = self.norm2._forward_autograd(conv(h, self.conv2.weight, self.conv2.bias))
+        res = conv(x, self.residual_conv.weight, self.residual_conv.bias) if isinstance(self.residual_conv, nn.Conv3d) else x
+        return torch.relu(h + res)
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
         return ops.to_nchw(self._forward_cl(a, f32=True, split=False), 5)

@@ -245,3 +245,81 @@ def test_g3d_trains_through_libmpb200():
     with torch.no_grad():
         y = G.eval()(x.cuda())
     assert not y.requires_grad and ((y.cpu() - ref_u.float()).abs().max() / ref_u.abs().max()).item() < 1e-4
+
+
+def _masked_grad_parity(mod, oracle_fn, sd, prefix, x, go):
+    """Gradients of `mod(x)` (libmpb200 Functions) vs float64 autograd of `oracle_fn(x, sd)` evaluated with the GPU run's ReLU masks
+    (see test_g3d_trains_through_libmpb200).  Returns (forward error, worst parameter-gradient error, input-gradient error)."""
+    import unittest.mock as mock
+    import gbase_oracle as O
+    masks = []
+    real_relu = torch.relu
+
+    def recording_relu(z):
+        y = real_relu(z)
+        masks.append((y > 0).cpu())
+        return y
+
+    xc = x.cuda().requires_grad_(True)
+    with mock.patch.object(torch, "relu", recording_relu):
+        out = mod(xc)
+    assert out.requires_grad
+    out.backward(go.cuda())
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xd = x.double().clone().requires_grad_(True)
+    it = iter(masks)
+    with mock.patch.object(O.F, "relu", lambda z, inplace=False: z * next(it).to(z.dtype)):
+        ref = oracle_fn(xd, sdd)
+    ref.backward(go.double())
+    fwd = ((out.detach().cpu() - ref.detach().float()).abs().max() / ref.abs().max()).item()
+    worst = 0.0
+    n = 0
+    for name, p in mod.named_parameters():
+        want = sdd[prefix + name].grad
+        assert p.grad is not None and want is not None, name
+        worst = max(worst, ((p.grad.cpu().double() - want).abs().max() / want.abs().max().clamp_min(1e-20)).item())
+        n += 1
+    ex = ((xc.grad.cpu().double() - xd.grad).abs().max() / xd.grad.abs().max()).item()
+    return fwd, worst, ex, n
+
+
+@pytest.mark.parametrize("which", ["conv2d_ws", "resblock_custom", "adaptive_group_norm", "resblock3d_adaptive", "resblock3d"])
+def test_path_modules_are_differentiable_through_libmpb200(which):
+    """Row f-2: the building blocks of Eapp / the warp generators / G3d (`Conv2d_WS`, `ResBlock_Custom`, `AdaptiveGroupNorm`,
+    `ResBlock3D_Adaptive`, `ResBlock3D`: model.py:54-130, 304-408, 500-528) called with autograd recording on: forward AND backward
+    on libmpb200, every parameter gradient and the input gradient against float64 autograd of the CPU oracle."""
+    import gbase_oracle as O
+    from megaportrait_hack_b200 import lib, model, seeded
+    lib.build()
+    g = torch.Generator().manual_seed(31)
+    if which == "conv2d_ws":
+        mod, x = model.Conv2d_WS(64, 128, 3, padding=1), torch.randn(2, 64, 24, 40, generator=g)
+        fn = lambda xx, sdd: O.conv2d_ws(xx, sdd, "m")
+    elif which == "resblock_custom":
+        mod, x = model.ResBlock_Custom(2, 64, 128), torch.randn(1, 64, 32, 48, generator=g)
+        fn = lambda xx, sdd: O.resblock_custom2d(xx, sdd, "m")
+    elif which == "adaptive_group_norm":
+        mod, x = model.AdaptiveGroupNorm(96), torch.randn(2, 96, 4, 8, 12, generator=g) * 1.4 + 0.2
+        fn = lambda xx, sdd: O.adaptive_group_norm(xx, sdd, "m")
+    elif which == "resblock3d_adaptive":
+        mod, x = model.ResBlock3D_Adaptive(128, 64), torch.randn(1, 128, 8, 8, 8, generator=g)
+        fn = lambda xx, sdd: O.resblock3d_adaptive(xx, sdd, "m")
+    else:
+        mod, x = model.ResBlock3D(96, 192), torch.randn(1, 96, 4, 16, 16, generator=g)
+        fn = lambda xx, sdd: O.resblock3d(xx, sdd, "m")
+    with torch.no_grad():
+        for name, p in mod.named_parameters():       # away from the (1, 0) defaults of the affine parameters
+            if p.dim() >= 4 and p.shape[0] != 1:
+                p.copy_(seeded.seeded_tensor("t." + name, p.shape, seeded.CONV_W, 5))
+            elif "bias" in name:
+                p.copy_(seeded.seeded_tensor("t." + name, p.shape, seeded.NORM_B, 5))
+            else:
+                p.copy_(seeded.seeded_tensor("t." + name, p.shape, seeded.NORM_W, 5))
+    sd = {"m." + k: v.detach().clone() for k, v in mod.state_dict().items()}
+    mod = mod.cuda().train()
+    with torch.no_grad():
+        shape = mod(x.cuda()).shape
+    go = torch.randn(shape, generator=g)
+    fwd, worst, ex, n = _masked_grad_parity(mod, fn, sd, "m.", x, go)
+    print(f"{which}: forward {fwd:.2e}; {n} parameter gradients, worst {worst:.2e}; input gradient {ex:.2e}")
+    assert fwd < 5e-5 and worst < 1e-4 and ex < 1e-4
