@@ -64,26 +64,35 @@ k_conv_wgrad(const WgradParams p) {
 
   // a thread stages 4 float4 of A (dY) and 4 of B (X) per 32-position stage: item f = tid + 128 j -> row f / 16, column 4 (f % 16)
   const int col4 = (tid & 15) * 4, row_base = tid >> 4;          // rows row_base + 8 j
+  // position -> (z, y, x) inside its sample with 32-bit arithmetic: `vbase` = (first position of the stage) mod D*H*W is carried
+  // from stage to stage, a row adds its offset (< 32) and wraps once (volumes of fewer than 32 positions take the 64-bit path)
+  const uint32_t HW = (uint32_t)p.H * p.W, DHW = (uint32_t)p.D * HW;
+  const bool small = DHW < (uint32_t)WG_TK;
+  uint32_t vbase = (uint32_t)(k_begin % DHW);
   float4 ra[4], rb[4];
   auto fetch = [&](int64_t k0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int64_t pos = k0 + row_base + 8 * j;
+      const int r = row_base + 8 * j;
+      const int64_t pos = k0 + r;
       ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pos < k_end) {
         if (co0 + col4 < p.Cout) ra[j] = __ldg(reinterpret_cast<const float4*>(p.dy + pos * p.Cout + co0 + col4));
-        // position -> (n, z, y, x); the tap reads x at (z + dz, y + dy, x + dx): zero outside the volume
-        int64_t t = pos;
-        const int xx = (int)(t % p.W); t /= p.W;
-        const int yy = (int)(t % p.H); t /= p.H;
-        const int zz = (int)(t % p.D);
-        const int zs = zz + dz, ys = yy + dyo, xs = xx + dx;
+        // the tap reads x at (z + dz, y + dy, x + dx): zero outside the volume
+        uint32_t q = small ? (uint32_t)(pos % DHW) : vbase + (uint32_t)r;
+        if (!small && q >= DHW) q -= DHW;
+        const uint32_t zz = q / HW, rem = q - zz * HW, yy = rem / (uint32_t)p.W, xx = rem - yy * (uint32_t)p.W;
+        const int zs = (int)zz + dz, ys = (int)yy + dyo, xs = (int)xx + dx;
         if (zs >= 0 && zs < p.D && ys >= 0 && ys < p.H && xs >= 0 && xs < p.W && ci0 + col4 < p.Cin) {
-          const int64_t q = pos + ((int64_t)dz * p.H + dyo) * p.W + dx;
-          rb[j] = __ldg(reinterpret_cast<const float4*>(p.x + q * p.Cin + ci0 + col4));
+          const int64_t src = pos + ((int64_t)dz * p.H + dyo) * p.W + dx;
+          rb[j] = __ldg(reinterpret_cast<const float4*>(p.x + src * p.Cin + ci0 + col4));
         }
       }
+    }
+    if (!small) {                        // advance to the next stage
+      vbase += WG_TK;
+      if (vbase >= DHW) vbase -= DHW;
     }
   };
   auto stage = [&](int s) {

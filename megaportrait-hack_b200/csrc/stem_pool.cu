@@ -231,11 +231,13 @@ template <int C>
 static int launch_stem(const float* x, const void* w_hi, const void* w_lo, const float* bias, float acc_scale, void* out,
                        int N, int H, int W, void* stream) {
   const size_t smem = (size_t)(3 * SP_IT * SP_IPITCH + 4 + SP_MT * 16 * SP_PPITCH + SP_MT * 16 * (C + 8)) * sizeof(__half);
-  static bool attr_done = false;        // (one attribute per instantiation; idempotent, so a race only repeats the call)
-  if (!attr_done) {
+  static bool attr_done[64] = {false};  // per device (the attribute is per device; idempotent, so a race only repeats the call)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_stem3x3_relu_maxpool_f16<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return mp_set_error("mp_stem3x3_relu_maxpool_f16: %s", cudaGetErrorString(e));
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const int tiles_x = W / (2 * SP_PT);
   const int per_cta = tiles_x % 4 == 0 ? 4 : tiles_x % 2 == 0 ? 2 : 1;     // consecutive tiles of one CTA (input prefetch)
