@@ -451,7 +451,7 @@ def run_b200(args):
             del xbig
         strong = strong_ms
     # ---- BASELINE config 2 variant (A) and config 1 through the drop-in `Gbase.forward` (eager launches, rank 0, N = 1)
-    cfgA = cfg1 = cfg4 = None
+    cfgA = cfg1 = cfg4 = cfg5 = None
     if world == 1 and not args.no_extra_configs:
         with torch.no_grad():
             def timed_fwd(xs_in, xd_in, reps):
@@ -512,6 +512,44 @@ def run_b200(args):
                     "what": "BASELINE config 4: Genh (model.py:1349-1391, ResBlock2D(64) read as ResBlock2D(64, 64)) on 8 frames "
                             "of 1024 x 1024, and GHR.forward = Genh(Gbase(xs, xd)[0]) on 8 pairs; eager launches, seeded weights"}
             del genh, ghr, xg
+            # BASELINE config 5, generator half (row f-2): one `train_base` iteration of Gbase alone -- train-mode forward
+            # (batch-statistics BatchNorm), an L1 loss against the driver frame in place of the out-of-scope perceptual /
+            # adversarial losses, backward through every operator of the path on libmpb200, AdamW step (train.py:135, 194, 318).
+            # Runs on a deep copy so the headline model keeps its eval-mode weights.
+            import copy
+            cfg5 = None
+            if not args.no_train_leg:
+                Gt = copy.deepcopy(G).train()
+                opt = torch.optim.AdamW(Gt.parameters(), lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2)
+                xs1, xd1 = xs_d[:1].contiguous(), xd_d[:1].contiguous()
+
+                def train_iter():
+                    with torch.enable_grad():            # (this block of legs runs under torch.no_grad())
+                        opt.zero_grad(set_to_none=True)
+                        pred, _ = Gt(xs1, xd1)
+                        loss = (pred - xd1).abs().mean()
+                        loss.backward()
+                    opt.step()
+                    return loss.detach()
+                n0 = ops.LAUNCHES
+                train_iter()
+                launches_train = ops.LAUNCHES - n0
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(2):
+                    loss = train_iter()
+                t1.record()
+                torch.cuda.synchronize()
+                ms_t = t0.elapsed_time(t1) / 2
+                # 2041 GF forward per pair; backward = data + weight gradient of every convolution ~ 2x the forward
+                cfg5 = {"generator_fwd_bwd_adamw_batch1": {"ms": ms_t, "pairs_per_s": 1e3 / ms_t, "loss": float(loss),
+                                                           "libmpb200_launches": launches_train,
+                                                           "useful_tflops": 3 * 2041e9 / (ms_t * 1e-3) / 1e12},
+                        "what": "BASELINE config 5, generator half at batch 1 on one GPU: Gbase.train() forward + backward + AdamW "
+                                "with an L1 loss (losses / discriminator are out of scope); fp32-grade three-pass convolutions in "
+                                "all three directions, eager launches, NCHW <-> channels-last conversion around every operator"}
+                del Gt, opt
 
     t = torch.tensor([ms, ms_e2e, strong if strong is not None else 0.0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
@@ -669,6 +707,7 @@ def run_b200(args):
         "config2A": cfgA,
         "config1": cfg1,
         "config4": cfg4,
+        "config5": cfg5,
         "stages_eager_step": stages,
         "cpu_baseline": cpu,
         "useful_tflops_whole_step": (B * FLOPS_PER_DRIVER + FLOPS_SOURCE) * world / (step_ms * 1e-3) / 1e12,
@@ -687,6 +726,7 @@ def main():
     ap.add_argument("--drivers-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config 2(A) / config 1 legs")
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the config 5 leg (Gbase forward + backward + AdamW)")
     ap.add_argument("--strong-drivers", type=int, default=256, help="global driver frames of the strong-scaling leg (0 = off)")
     ap.add_argument("--strong-steps", type=int, default=3)
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")

@@ -45,8 +45,16 @@ class CustomResNet50(nn.Module):
         self.conv_reduce = nn.Conv2d(1024, 512, kernel_size=1)
         self.backend = "mpb200"
 
+    def _forward_autograd(self, x):
+        """Differentiable / train-mode form: every convolution and BatchNorm on the libmpb200 autograd Functions."""
+        x = resnet_trunk_autograd(self.conv1, self.bn1, self.maxpool, (self.layer1, self.layer2, self.layer3), x)
+        from . import ops
+        return ops.conv_train(self.adaptive_avg_pool(x), self.conv_reduce.weight, self.conv_reduce.bias)
+
     def forward(self, x):
         if getattr(self, "backend", "mpb200") == "mpb200":
+            if x.is_cuda and (self.training or _wants_grad(self, x)):
+                return self._forward_autograd(x.float().contiguous())
             _require_mpb200(self, x)
             from . import emtn_cuda
             return emtn_cuda.resnet50_descriptor(self, x)
@@ -193,6 +201,37 @@ def _versions(mod: nn.Module):
     return (tuple((t.data_ptr(), t._version) for t in ts), str(ts[0].device) if ts else "")
 
 
+def _wants_grad(mod: nn.Module, x: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in mod.parameters()))
+
+
+def resnet_block_autograd(blk: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """torchvision `BasicBlock` / `Bottleneck` (v1.5: stride on conv2) forward on the differentiable libmpb200 operators
+    (ops.conv_train: tcgen05 forward / data gradient + tensor-core weight gradient; ops.batch_norm_train: batch statistics)."""
+    from . import ops
+    conv, bn = ops.conv_train, ops.batch_norm_train
+    idt = x
+    if blk.downsample is not None:
+        dc, dbn = blk.downsample[0], blk.downsample[1]
+        idt = bn(conv(x, dc.weight, dc.bias, stride=dc.stride[0]), dbn)
+    out = torch.relu(bn(conv(x, blk.conv1.weight, blk.conv1.bias, stride=blk.conv1.stride[0]), blk.bn1))
+    out = bn(conv(out, blk.conv2.weight, blk.conv2.bias, stride=blk.conv2.stride[0]), blk.bn2)
+    if hasattr(blk, "conv3"):
+        out = bn(conv(torch.relu(out), blk.conv3.weight, blk.conv3.bias), blk.bn3)
+    return torch.relu(out + idt)
+
+
+def resnet_trunk_autograd(conv1, bn1, maxpool, layers, x: torch.Tensor) -> torch.Tensor:
+    """Stem conv + BatchNorm + ReLU, the max-pool (ATen autograd), residual stages -- the differentiable form of `ResNetTrunkPlan`."""
+    from . import ops
+    x = torch.relu(ops.batch_norm_train(ops.conv_train(x, conv1.weight, conv1.bias, stride=conv1.stride[0]), bn1))
+    x = F.max_pool2d(x, maxpool.kernel_size, maxpool.stride, maxpool.padding)
+    for layer in layers:
+        for blk in layer:
+            x = resnet_block_autograd(blk, x)
+    return x
+
+
 def _require_mpb200(mod: nn.Module, x: torch.Tensor) -> None:
     """The libmpb200 backend serves CUDA tensors in inference mode only; everything else raises (no silent fallback)."""
     if not x.is_cuda:
@@ -236,8 +275,26 @@ class Emtn(nn.Module):
             self.__dict__["_mp_plans"] = c
         return c[1]
 
+    def _forward_autograd(self, x):
+        """Differentiable / train-mode form (train.py:289-293 calls it on generated frames).  The two CIFAR
+        ResNet-18 trunks run on the libmpb200 autograd Functions (train-mode BatchNorm = batch statistics).  6DRepNet is not a
+        registered sub-module in the reference: `Gbase.train()` never reaches it and no optimizer holds its weights, so the Euler
+        angles come from the inference kernels without a graph (the reference's graph through them only reaches the detector's own,
+        never-updated weights and the input frame)."""
+        from . import emtn_cuda
+        with torch.no_grad():
+            rotations = emtn_cuda.rotation_forward(self, x.detach())
+        hp, ex = self.head_pose_net, self.expression_net
+        f = resnet_trunk_autograd(hp.conv1, hp.bn1, hp.maxpool, (hp.layer1, hp.layer2, hp.layer3, hp.layer4), x)
+        translation = hp.fc(torch.flatten(F.adaptive_avg_pool2d(f, 1), 1))[:, 3:]
+        g = resnet_trunk_autograd(ex[0], ex[1], ex[3], (ex[4], ex[5], ex[6], ex[7]), x)
+        g = F.adaptive_avg_pool2d(F.adaptive_avg_pool2d(g, 1), FEATURE_SIZE)      # model.py:880-881
+        return rotations, translation, self.fc(torch.flatten(g, start_dim=1))
+
     def forward(self, x):
         if getattr(self, "backend", "mpb200") == "mpb200":
+            if x.is_cuda and (self.training or _wants_grad(self, x)):
+                return self._forward_autograd(x.float().contiguous())
             _require_mpb200(self, x)
             from . import emtn_cuda          # libmpb200 tcgen05 kernels (SURVEY.md row f-1)
             with torch.no_grad():

@@ -238,6 +238,24 @@ def emtn_forward(emtn, x: torch.Tensor):
     return rotations, translation, expression
 
 
+def rotation_forward(emtn, x: torch.Tensor) -> torch.Tensor:
+    """Only the 6DRepNet branch of `emtn_forward` (Euler degrees [B,3]) -- the differentiable / train-mode `Emtn` takes the angles
+    from here and trains the two ResNet-18 trunks through the autograd Functions (emtn.py `_forward_autograd`)."""
+    from .emtn import ortho6d_to_euler_deg
+    rot = emtn.rotation_net.model
+    sig = _versions(rot) + (EMTN_PREC,)
+    c = emtn.__dict__.get("_mp_cuda_rot_plan")
+    if c is None or c[0] != sig:
+        with torch.no_grad():
+            c = (sig, RepVGGPlan(rot, prec=EMTN_PREC))
+        emtn.__dict__["_mp_cuda_rot_plan"] = c
+    plan = c[1]
+    x = x.float().contiguous()
+    x_in = ops.im2col3x3_f16(x, plan.stem_stride) if plan.prec == PREC_F16X2 else rgb16(x)
+    x6 = F.linear(plan.pooled(x_in), rot.linear_reg.weight, rot.linear_reg.bias)
+    return ortho6d_to_euler_deg(x6[:, :6])
+
+
 def resnet50_descriptor(r50, x: torch.Tensor) -> torch.Tensor:
     """CustomResNet50.forward (model.py:156-173) on libmpb200 kernels -> (B, 512, 2, 2) NCHW."""
     sig = _versions(r50)

@@ -87,7 +87,8 @@ def _sig(mod: nn.Module):
 def invalidate_plans(root: nn.Module) -> None:
     """Drop every cached kernel-format weight plan under `root` (they are rebuilt on the next forward)."""
     for m in root.modules():
-        for k in ("_mp_plan", "_mp_final", "_mp_plans", "_mp_cuda_plans", "_mp_cuda_plan", "_mp_fwd_graphs", "_mp_fwd_seen"):
+        for k in ("_mp_plan", "_mp_final", "_mp_plans", "_mp_cuda_plans", "_mp_cuda_plan", "_mp_cuda_rot_plan", "_mp_fwd_graphs",
+                  "_mp_fwd_seen"):
             m.__dict__.pop(k, None)
         det = getattr(m, "rotation_net", None)
         if det is not None and hasattr(det, "model"):
@@ -348,7 +349,23 @@ class FlowField(nn.Module, _Packed):
         out = ops.group_norm_act(h, 1, st, *P["gn"], act=ACT_RELU_TANH, f32=True, split=False)
         return out.f32
 
+    def _forward_autograd(self, zs):
+        """Differentiable form (row f-2): zs [B,512,1,1] -> (B,3,16,16,16); nearest upsamples through ATen's autograd."""
+        x = ops.conv_train(zs, self.conv1x1.weight, self.conv1x1.bias)
+        x = x.view(-1, 512, 4, *x.shape[2:])
+        for blk, sf in ((self.resblock1, (2, 2, 2)), (self.resblock2, (2, 2, 2)), (self.resblock3, (1, 2, 2)),
+                        (self.resblock4, (1, 2, 2))):
+            x = F.interpolate(blk._forward_autograd(x), scale_factor=sf, mode="nearest")
+        x = ops.conv_train(x, self.conv3x3x3.weight, self.conv3x3x3.bias)
+        x = ops.GroupNormFunction.apply(x, 1, self.gn.weight, self.gn.bias, self.gn.eps)
+        return torch.tanh(torch.relu(x))
+
     def forward(self, zs, adaptive_gamma, adaptive_beta):
+        if _wants_grad(self, zs):
+            _require_inference(self, zs.detach())
+            x = self._forward_autograd(zs.float().reshape(zs.shape[0], 512, 1, 1))
+            assert x.shape[1] == 3, f"Expected 3 channels after conv3x3x3, got {x.shape[1]}"
+            return x
         _require_inference(self, zs)
         em = self._forward_cl(_as_f32_cuda(zs).reshape(zs.shape[0], 512))
         x = em.permute(0, 4, 1, 2, 3).contiguous()
@@ -543,7 +560,22 @@ class ResBlock2D(nn.Module, _Packed):
             return ops.conv(t, P["c2"], src2=x, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
         return ops.conv(t, P["c2"], res=x, act=ACT_RELU, f32=f32, split=split, stats_groups=stats_groups)
 
+    def _forward_autograd(self, x):
+        """Differentiable / train-mode form (row f-2): convolutions and BatchNorm (batch statistics in train mode, running
+        statistics updated like ATen does) through the libmpb200 Functions of ops.py."""
+        if self.downsample:
+            raise NotImplementedError("ResBlock2D(downsample=True) is never used by the reference hot path")
+        conv, bn = ops.conv_train, ops.batch_norm_train
+        out = torch.relu(bn(conv(x, self.conv1.weight, self.conv1.bias), self.bn1))
+        out = bn(conv(out, self.conv2.weight, self.conv2.bias), self.bn2)
+        if isinstance(self.shortcut, nn.Sequential):
+            x = bn(conv(x, self.shortcut[0].weight, self.shortcut[0].bias), self.shortcut[1])
+        return torch.relu(out + x)
+
     def forward(self, x):
+        if self.training or _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=False, split=True)
         out, _ = self._forward_cl(a, f32=True, split=False)
@@ -677,7 +709,26 @@ class G2d(nn.Module, _Packed):
         ab = ops.gn_finalize(st, h.shape, 32, *P["gn"])
         return ops.gn_relu_conv3x3_head(h, ab, P["head_w"], P["head_b"], ACT_SIGMOID)
 
+    def _forward_autograd(self, x):
+        """Differentiable / train-mode form (row f-2).  `reshape` and `conv1x1` have no non-linearity between them (model.py:756-757):
+        their product is formed as a torch expression on the two weights (autograd carries the gradient to both) and ONE 96 -> 512
+        convolution runs; the bilinear x2 upsamples go through ATen's autograd."""
+        conv = ops.conv_train
+        w2 = self.conv1x1.weight.view(512, 1536)
+        w = (w2 @ self.reshape.weight.view(1536, 96)).view(512, 96, 1, 1)
+        x = conv(x, w, w2 @ self.reshape.bias + self.conv1x1.bias)
+        for blk in self.res_blocks:
+            x = blk._forward_autograd(x)
+        for up in (self.upsample1, self.upsample2, self.upsample3):
+            x = up[1]._forward_autograd(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True))
+        gn = self.final_conv[0]
+        x = torch.relu(ops.GroupNormFunction.apply(x, gn.num_groups, gn.weight, gn.bias, gn.eps))
+        return torch.sigmoid(conv(x, self.final_conv[2].weight, self.final_conv[2].bias))
+
     def forward(self, x):
+        if self.training or _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=False, split=True)
         return self._forward_cl(a)
@@ -737,7 +788,24 @@ class Eapp(nn.Module, _Packed):
             es = self.custom_resnet50(x)
         return self.fc(torch.flatten(es, start_dim=1))
 
+    def _forward_autograd(self, x):
+        """Differentiable / train-mode form (row f-2) -> (vs, es); 2x2 average pools through ATen's autograd."""
+        conv, gn = ops.conv_train, ops.GroupNormFunction.apply
+        out = conv(x, self.conv.weight, self.conv.bias)
+        for blk in (self.resblock_128, self.resblock_256, self.resblock_512):
+            out = F.avg_pool2d(blk._forward_autograd(out), 2, 2)
+        out = conv(torch.relu(gn(out, 32, None, None, 1e-5)), self.conv_1.weight, self.conv_1.bias)
+        vs = out.view(out.size(0), 96, 16, *out.shape[2:])
+        for blk in (self.resblock3D_96, self.resblock3D_96_2, self.resblock3D_96_1, self.resblock3D_96_1_2,
+                    self.resblock3D_96_2, self.resblock3D_96_2_2):
+            vs = blk._forward_autograd(vs)
+        es = self.custom_resnet50._forward_autograd(x)
+        return vs, self.fc(torch.flatten(es, start_dim=1))
+
     def forward(self, x):
+        if self.training or _wants_grad(self, x):
+            _require_inference(self, x.detach())
+            return self._forward_autograd(x.float().contiguous())
         _require_inference(self, x)
         x = _as_f32_cuda(x)
         vs = ops.to_nchw(self._volume_cl(x), 5)
@@ -800,7 +868,22 @@ class _WarpGenerator(nn.Module):
         em = self.flowfield._forward_cl(s)
         return em, _affine_3x4(R, t, self._invert)
 
+    def _forward_autograd(self, R, t, z, e):
+        """Differentiable form (row f-2): the flow-field tower through libmpb200; the 3-channel rigid grid (`F.affine_grid`) and the
+        trilinear 16^3 -> 64^3 resize of the flow (model.py:965-973) through ATen's autograd."""
+        assert R.shape == (z.shape[0], 3), f"Expected R shape (batch_size, 3), got {R.shape}"
+        assert t.shape == (z.shape[0], 3), f"Expected t shape (batch_size, 3), got {t.shape}"
+        assert z.shape == e.shape, f"Expected z and es to have the same shape, got {z.shape} and {e.shape}"
+        s = torch.matmul((z + e).float(), self.adaptive_matrix_gamma.float())
+        em = self.flowfield._forward_autograd(s[:, :, None, None])
+        theta = _affine_3x4(R, t, self._invert)
+        w_rt = F.affine_grid(theta, (z.shape[0], 1, 64, 64, 64), align_corners=False).permute(0, 4, 1, 2, 3)
+        return w_rt + F.interpolate(em, size=(64, 64, 64), mode="trilinear", align_corners=False)
+
     def _forward(self, R, t, z, e):
+        if _wants_grad(self, R, t, z, e):
+            _require_inference(self, *(v.detach() for v in (R, t, z, e)))
+            return self._forward_autograd(R, t, z, e)
         _require_inference(self, R, t, z, e)
         em, theta = self._em_theta(R, t, z, e)
         return ops.warp_field(em, theta, 64)
@@ -856,6 +939,10 @@ class AntiAliasInterpolation2d(nn.Module):
     def forward(self, input):
         if self.scale == 1.0:
             return input
+        if torch.is_grad_enabled() and input.requires_grad:
+            # differentiable form (row f-2): a 3-channel depthwise blur + nearest sub-sampling (0.3 GFLOP) through ATen's autograd
+            out = F.conv2d(F.pad(input, (self.ka, self.kb, self.ka, self.kb)), weight=self.weight, groups=self.groups)
+            return F.interpolate(out, scale_factor=(self.scale, self.scale))
         _require_inference(self, input)
         step = int(round(1.0 / self.scale))
         return ops.blur_subsample(_as_f32_cuda(input), self.weight[0, 0].contiguous(), step)
@@ -998,12 +1085,34 @@ class Gbase(nn.Module):
         graph is keyed on the weights' signature (`_sig`): any parameter update, `.to()`, `load_state_dict` or
         `invalidate_plans` drops it.  `self.forward_graphs = False` (or MPB200_FORWARD_GRAPHS=0) launches eagerly."""
         assert xs.shape[0] == xd.shape[0], f"Expected zs and es to have the same shape (Bs == Bd), got {xs.shape[0]} and {xd.shape[0]}"
-        _require_no_grad(self, xs, xd)
+        if self.training or _wants_grad(self, xs, xd):
+            _require_inference(self, xs.detach(), xd.detach())
+            return self._forward_autograd(xs.float().contiguous(), xd.float().contiguous())
         if (_FWD_GRAPHS and getattr(self, "forward_graphs", True) and not self.training and xs.is_cuda and xd.is_cuda
                 and xs.device == xd.device and tuple(xs.shape[1:]) == (3, 512, 512) and tuple(xd.shape[1:]) == (3, 512, 512)
                 and not _capturing(xs)):
             return self._forward_graphed(xs, xd)
         return self._forward_eager(xs, xd)
+
+    def _forward_autograd(self, xs, xd):
+        """Differentiable / train-mode `forward` (row f-2; train.py:194, 283): the reference's statement order (model.py:1141-1178)
+        on the autograd Functions of ops.py -- every convolution (forward, data and weight gradient), GroupNorm, train-mode
+        BatchNorm and both `apply_warping_field` calls run on libmpb200; pools, resizes and the rigid 3-channel grid go
+        through ATen's autograd."""
+        assert tuple(xs.shape[1:]) == (3, 512, 512) and tuple(xd.shape[1:]) == (3, 512, 512), \
+            f"Expected input shape (_, 3, 512, 512), got {tuple(xs.shape)}"
+        vs, es = self.appearanceEncoder._forward_autograd(xs)
+        Rs, ts, zs = self.motionEncoder._forward_autograd(xs)
+        Rd, td, zd = self.motionEncoder._forward_autograd(xd)
+        w_s2c = self.warp_generator_s2c._forward_autograd(Rs, ts, zs, es)
+        vc = ops.WarpFunction.apply(vs, w_s2c)
+        assert vc.shape[1:] == (96, 16, 64, 64), f"Expected vc shape (_, 96, 16, 64, 64), got {vc.shape}"
+        vc2d = self.G3d._forward_autograd(vc)
+        w_c2d = self.warp_generator_c2d._forward_autograd(Rd, td, zd, es)
+        vc2d_warped = ops.WarpFunction.apply(vc2d, w_c2d)
+        assert vc2d_warped.shape[1:] == (96, 16, 64, 64), f"Expected vc2d_warped shape (_, 96, 16, 64, 64), got {vc2d_warped.shape}"
+        xhat_base = self.G2d._forward_autograd(torch.sum(vc2d_warped, dim=2))
+        return xhat_base, self.image_pyramid(xhat_base)
 
     def _forward_eager(self, xs, xd):
         src = self.encode_source(xs)

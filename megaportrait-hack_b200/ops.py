@@ -883,6 +883,128 @@ class GroupNormFunction(torch.autograd.Function):
                 db if ctx.needs_input_grad[3] else None, None)
 
 
+class ConvS2Function(torch.autograd.Function):
+    """`F.conv2d(x, w, b, stride=2, padding=k // 2)` (odd k, even H and W) with CUDA forward and backward (row f-2).  Forward = the
+    tcgen05 kernel's native stride-2 walk (TMA element strides).  A stride-2 "same" convolution is the stride-1 one sampled at the
+    even positions, so its gradients are the stride-1 gradients of dY spread onto the even positions of a zero tensor: dX and dW
+    reuse `conv_input_grad` / `conv_weight_grad` unchanged (4x the minimal work on the few stride-2 layers of the encoders)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        if x.dim() != 4 or x.shape[2] % 2 or x.shape[3] % 2:
+            raise RuntimeError(f"ConvS2Function: NCHW input with even H and W expected, got {tuple(x.shape)}")
+        a = _to_cl_act(x)
+        ensure_split(a)
+        ctx.k = (1,) + tuple(weight.shape[2:])
+        ctx.save_for_backward(x.detach(), weight.detach())
+        ctx.has_bias = bias is not None
+        out, _ = conv(a, pack_conv(weight.detach(), None if bias is None else bias.detach(), x.device), f32=True, stride=2)
+        return to_nchw(out, 4)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        N, _, H, W = x.shape
+        up = torch.zeros((N, grad_out.shape[1], H, W), dtype=torch.float32, device=grad_out.device)
+        up[:, :, ::2, ::2] = grad_out
+        g = _to_cl_act(up)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            ensure_split(g)
+            gx = to_nchw(conv_input_grad(g, pack_conv_dgrad(weight, x.device)), 4)
+        if ctx.needs_input_grad[1]:
+            gw = conv_weight_grad(_to_cl_act(x), g, ctx.k).squeeze(2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = bias_grad(g)
+        return gx, gw, gb
+
+
+def _pad_channels(t: torch.Tensor, dim: int, mult: int) -> torch.Tensor:
+    c = t.shape[dim]
+    extra = (-c) % mult
+    if not extra:
+        return t
+    shape = list(t.shape)
+    shape[dim] = extra
+    return torch.cat((t, t.new_zeros(shape)), dim)
+
+
+def conv_train(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1) -> torch.Tensor:
+    """Differentiable `F.conv2d / F.conv3d(x, weight, bias, stride, padding=k // 2)` on libmpb200 (row f-2) for every convolution of
+    the path: channel counts that are not multiples of 16 (RGB stems, the 3-channel heads) are zero-padded around the Function by
+    torch expressions (autograd slices the gradients back), 1x1 stride-2 shortcuts sub-sample their input first, other stride-2
+    convolutions (2-D only) go through `ConvS2Function`."""
+    cin, cout = weight.shape[1], weight.shape[0]
+    if x.shape[1] != cin:
+        raise RuntimeError(f"conv_train: input has {x.shape[1]} channels, weight expects {cin} (grouped convolutions are not on "
+                           "the trained path)")
+    if stride not in (1, 2):
+        raise RuntimeError(f"conv_train: stride {stride} is not supported")
+    x = x.float()
+    if stride == 2 and all(k == 1 for k in weight.shape[2:]):
+        x = x[:, :, ::2, ::2] if x.dim() == 4 else x[:, :, ::2, ::2, ::2]
+        stride = 1
+    x = _pad_channels(x.contiguous(), 1, 16)
+    w = _pad_channels(_pad_channels(weight.float(), 1, 16), 0, 16)
+    b = None if bias is None else _pad_channels(bias.float(), 0, 16)
+    y = (ConvS2Function if stride == 2 else ConvFunction).apply(x.contiguous(), w, b)
+    return y if cout == y.shape[1] else y[:, :cout]
+
+
+class BatchNormFunction(torch.autograd.Function):
+    """Train-mode `F.batch_norm` (batch statistics) with CUDA forward and backward (row f-2).  On the channels-last tensor a
+    BatchNorm over (N, H, W) is a GroupNorm with ONE sample of N*H*W rows and one group per channel, so forward and backward are
+    the GroupNorm entry points called with N = 1, G = C (`mp_gn_stats`, `mp_gn_finalize`, `mp_affine_act_cl`,
+    `mp_group_norm_backward`: double-precision sums).  Returns (y, batch mean, biased batch variance); the caller folds the last two
+    into the running statistics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        a = _to_cl_act(x)
+        N, D, H, W, C = a.shape
+        a1 = Act((1, 1, N * D * H, W, C), f32=a.f32.view(1, 1, N * D * H, W, C))
+        stats = gn_stats(a1, C)
+        g = None if gamma is None else gamma.detach().float().contiguous()
+        ab = gn_finalize(stats, a1.shape, C, g, None if beta is None else beta.detach().float().contiguous(), eps=eps)
+        ctx.save_for_backward(x.detach(), stats, g)
+        ctx.eps, ctx.nd = eps, x.dim()
+        y = affine_act(a1, ab, None, ACT_NONE, f32=True, split=False)
+        cnt = float(N * D * H * W)
+        mean = stats[0, :, 0] / cnt
+        var = (stats[0, :, 1] / cnt - mean * mean).clamp_min(0.0)
+        ctx.mark_non_differentiable(mean, var)
+        return to_nchw(Act(a.shape, f32=y.f32.view(a.shape)), x.dim()), mean, var
+
+    @staticmethod
+    def backward(ctx, grad_out, _gm, _gv):
+        x, stats, gamma = ctx.saved_tensors
+        a, g = _to_cl_act(x), _to_cl_act(grad_out)
+        N, D, H, W, C = a.shape
+        one = (1, 1, N * D * H, W, C)
+        dx, dg, db = group_norm_backward(Act(one, f32=a.f32.view(one)), Act(one, f32=g.f32.view(one)), stats, C, gamma, ctx.eps)
+        return (to_nchw(Act(a.shape, f32=dx.f32.view(a.shape)), ctx.nd), dg if ctx.needs_input_grad[1] else None,
+                db if ctx.needs_input_grad[2] else None, None)
+
+
+def batch_norm_train(x: torch.Tensor, bn) -> torch.Tensor:
+    """`nn.BatchNorm2d.forward` for the differentiable path (row f-2).  Train mode: batch statistics through `BatchNormFunction`
+    and the running statistics updated like ATen does (momentum, unbiased variance, `num_batches_tracked`); eval mode: the
+    running-statistics affine map as a torch expression (elementwise)."""
+    if bn.training or bn.running_mean is None:
+        y, mean, var = BatchNormFunction.apply(x.float().contiguous(), bn.weight, bn.bias, bn.eps)
+        if bn.training and bn.track_running_stats and bn.running_mean is not None:
+            with torch.no_grad():
+                n = x.numel() // x.shape[1]
+                bn.num_batches_tracked += 1
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1 - m).add_(mean.to(bn.running_mean.dtype), alpha=m)
+                bn.running_var.mul_(1 - m).add_((var * (n / max(n - 1, 1))).to(bn.running_var.dtype), alpha=m)
+        return y
+    shape = (1, -1) + (1,) * (x.dim() - 2)
+    scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    return x * scale.view(shape) + (bn.bias - bn.running_mean * scale).view(shape)
+
+
 def warp_field(em_cl: torch.Tensor, theta: torch.Tensor, G: int = 64) -> torch.Tensor:
     """em_cl [N,E,E,E,3] fp32, theta [N,3,4] -> [N,3,G,G,G] (model.py:965-973)."""
     _chk_cuda(em_cl, torch.float32, "warp_field em")

@@ -15,7 +15,7 @@ imports `/root/reference/model.py` through `oracle/ref_shim.py`, fills it with t
 `tests/test_oracle_golden.py` checks this restatement against them (the reference itself ships no tests,
 golden vectors or checkpoints: SURVEY.md section 4 / 8c).
 
-Each function cites the reference lines it follows.  Eval-mode semantics only (BatchNorm uses running stats).
+Each function cites the reference lines it follows.  Eval-mode semantics (BatchNorm uses running stats) unless `BN_TRAINING` is set.
 """
 from __future__ import annotations
 
@@ -37,8 +37,14 @@ def _conv(x, sd: SD, p: str, stride=1, padding=0, groups=1):
     return fn(x, w, b, stride=stride, padding=padding, groups=groups)
 
 
+BN_TRAINING = False     # True: nn.BatchNorm2d as in `.train()` (batch statistics) -- the gradient tests of SURVEY.md row f-2
+
+
 def _bn(x, sd: SD, p: str):
-    """nn.BatchNorm2d in eval mode, eps 1e-5 (model.py:605-616 and the resnets)."""
+    """nn.BatchNorm2d, eps 1e-5 (model.py:605-616 and the resnets): running statistics (eval mode, the default) or, under
+    `BN_TRAINING`, the batch statistics `Gbase.train()` uses (train.py:133)."""
+    if BN_TRAINING:
+        return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], training=True, eps=1e-5)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
                         training=False, eps=1e-5)
 
@@ -183,9 +189,11 @@ def sixdrepnet_euler(x, sd: SD, p: str = ROTNET_PREFIX[:-1]) -> torch.Tensor:
     return ortho6d_to_euler_deg(x[:, :6])
 
 
-def emtn(x, sd: SD, p: str = "motionEncoder"):
-    """Emtn.forward, model.py:888-907: (Euler degrees from 6DRepNet, translation = head_pose[:,3:], z)."""
-    rot = sixdrepnet_euler(x, sd)
+def emtn(x, sd: SD, p: str = "motionEncoder", rot=None):
+    """Emtn.forward, model.py:888-907: (Euler degrees from 6DRepNet, translation = head_pose[:,3:], z).  `rot` (gradient tests):
+    angles to use instead of running 6DRepNet."""
+    if rot is None:
+        rot = sixdrepnet_euler(x, sd)
     hp = _resnet18_trunk(x, sd, p + ".head_pose_net", ("conv1", "bn1", ("layer1", "layer2", "layer3", "layer4")))
     hp = F.linear(torch.flatten(hp, 1), sd[p + ".head_pose_net.fc.weight"], sd[p + ".head_pose_net.fc.bias"])
     t = hp[:, 3:]
@@ -363,6 +371,26 @@ def gbase_forward(xs, xd, sd: SD, stages: bool = False):
     if stages:
         return drv["rgb"], drv["pyramids"], {**src, **drv}
     return drv["rgb"], drv["pyramids"]
+
+
+def gbase_forward_train(xs, xd, sd: SD, rotations=None):
+    """`Gbase.forward` in the reference's statement order (model.py:1141-1178) WITH autograd recording and, under `BN_TRAINING`,
+    train-mode BatchNorm -- the checker of the differentiable path (train.py:194).  -> (rgb, pyramids, stages).
+    `rotations` = (Rs, Rd) replaces 6DRepNet's output (its weights are outside `Gbase.parameters()` and never trained)."""
+    st = {}
+    st["vs"], st["es"] = eapp(xs, sd)
+    rs, rd = rotations if rotations is not None else (None, None)
+    st["Rs"], st["ts"], st["zs"] = emtn(xs, sd, rot=rs)
+    st["Rd"], st["td"], st["zd"] = emtn(xd, sd, rot=rd)
+    st["w_s2c"], _ = warp_generator(st["Rs"], st["ts"], st["zs"], st["es"], sd, "warp_generator_s2c", invert=True)
+    st["vc"] = apply_warping_field(st["vs"], st["w_s2c"])
+    st["vc2d"] = g3d(st["vc"], sd)
+    st["w_c2d"], _ = warp_generator(st["Rd"], st["td"], st["zd"], st["es"], sd, "warp_generator_c2d", invert=False)
+    st["warped"] = apply_warping_field(st["vc2d"], st["w_c2d"])
+    st["projected"] = torch.sum(st["warped"], dim=2)
+    st["rgb"] = g2d(st["projected"], sd)
+    st["pyramids"] = image_pyramid(st["rgb"])
+    return st["rgb"], st["pyramids"], st
 
 
 @torch.no_grad()

@@ -65,9 +65,9 @@ def _to_cl(x):
 
 def _act(v, code):
     if code == ops.ACT_RELU:
-        return F.relu(v)
+        return v.clamp_min(0)
     if code == ops.ACT_RELU_TANH:
-        return torch.tanh(F.relu(v))
+        return torch.tanh(v.clamp_min(0))
     if code == ops.ACT_SIGMOID:
         return torch.sigmoid(v)
     if code == ops.ACT_TANH:
@@ -317,7 +317,7 @@ def warp_fused(v, em_cl, theta, sum_d, G=64, f32=True, split=False):
 
 
 def gn_relu_conv3x3_head(a, ab, weight_host, bias_host, act=ops.ACT_SIGMOID):
-    v = F.relu(a.f32 * ab[:, None, None, None, :, 0] + ab[:, None, None, None, :, 1])
+    v = (a.f32 * ab[:, None, None, None, :, 0] + ab[:, None, None, None, :, 1]).clamp_min(0)
     return _act(F.conv2d(_to_ncdhw(v).squeeze(2), weight_host, bias_host, padding=1), act)
 
 
@@ -328,7 +328,46 @@ def blur_subsample(x, kernel2d, step):
     return y[:, :, ::step, ::step].contiguous()
 
 
-_NAMES = ["from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
+def conv_weight_grad(x, grad_out, k):
+    kd, kh, kw = k
+    Cin, Cout = x.shape[-1], grad_out.shape[-1]
+    gw = torch.nn.grad.conv3d_weight(_to_ncdhw(x.f32).double(), (Cout, Cin, kd, kh, kw), _to_ncdhw(grad_out.f32).double(),
+                                     padding=(kd // 2, kh // 2, kw // 2))
+    return gw.float()
+
+
+def bias_grad(grad_out):
+    return grad_out.f32.double().sum(dim=(0, 1, 2, 3)).float()
+
+
+def group_norm_backward(x, grad_out, stats, G, gamma, eps=1e-5):
+    N, D, H, W, C = x.shape
+    cpg = C // G
+    cnt = D * H * W * cpg
+    mean = stats[..., 0] / cnt
+    rstd = 1.0 / torch.sqrt((stats[..., 1] / cnt - mean * mean).clamp_min(0) + eps)
+    xv = x.f32.double().reshape(N, -1, G, cpg)
+    dy = grad_out.f32.double().reshape(N, -1, G, cpg)
+    xh = (xv - mean[:, None, :, None]) * rstd[:, None, :, None]
+    gm = torch.ones(C, dtype=torch.float64) if gamma is None else gamma.double()
+    dg = (dy * xh).sum(dim=(0, 1)).reshape(C)
+    db = dy.sum(dim=(0, 1)).reshape(C)
+    dyg = dy * gm.view(1, 1, G, cpg)
+    m1 = dyg.mean(dim=(1, 3), keepdim=True)
+    m2 = (dyg * xh).mean(dim=(1, 3), keepdim=True)
+    dx = rstd[:, None, :, None] * (dyg - m1 - xh * m2)
+    return _mk(dx.reshape(x.shape).float(), True, False), dg.float(), db.float()
+
+
+def apply_warping_field_backward(grad_out, v, wf, need_v=True, need_wf=True):
+    import gbase_oracle as O
+    with torch.enable_grad():
+        vv, ww = v.detach().clone().requires_grad_(True), wf.detach().clone().requires_grad_(True)
+        O.apply_warping_field(vv, ww).backward(grad_out)
+    return (vv.grad if need_v else None), (ww.grad if need_wf else None)
+
+
+_NAMES = ["conv_weight_grad", "bias_grad", "group_norm_backward", "apply_warping_field_backward", "from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
           "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "from_nchw_pad16",
           "im2col3x3_f16", "stem3x3_relu_maxpool_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]

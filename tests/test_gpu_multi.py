@@ -69,17 +69,20 @@ def test_reference_semantics_forward_32_pairs(gbase):
     assert (pa["prediction_0.5"] - pb["prediction_0.5"]).abs().max().item() <= 1e-4
 
 
-def test_forward_refuses_to_return_detached_outputs(gbase):
-    """with autograd recording on and trainable parameters, `Gbase.forward` must raise instead of
-    silently handing train.py detached tensors."""
+def test_forward_with_autograd_recording_returns_attached_outputs(gbase):
+    """`Gbase.forward` called with autograd recording on and trainable parameters must never hand train.py
+    detached tensors.  Round 2 (row f-2): it takes the differentiable libmpb200 path instead of raising -- the outputs carry a
+    graph and (eval mode: running statistics) agree with the inference kernels."""
     G, _sd = gbase
     xs, xd = synthetic_pair(1)
-    with pytest.raises(NotImplementedError, match="inference-only"):
-        G(xs.cuda(), xd.cuda())
-    with pytest.raises(NotImplementedError):
-        G.motionEncoder(xd.cuda())
+    rgb, pyr = G(xs.cuda(), xd.cuda())
+    assert rgb.requires_grad and pyr["prediction_0.5"].requires_grad
+    _, _, z = G.motionEncoder(xd.cuda())
+    assert z.requires_grad
     with torch.no_grad():
-        G(xs.cuda(), xd.cuda())
+        ref, _ = G(xs.cuda(), xd.cuda())
+    assert not ref.requires_grad
+    assert (rgb.detach() - ref).abs().max().item() <= 2e-4
 
 
 @pytest.mark.timeout(900)
