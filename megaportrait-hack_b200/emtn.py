@@ -54,7 +54,7 @@ class CustomResNet50(nn.Module):
     def forward(self, x):
         if getattr(self, "backend", "mpb200") == "mpb200":
             if x.is_cuda and (self.training or _wants_grad(self, x)):
-                return self._forward_autograd(x.float().contiguous())
+                return self._forward_autograd(x.float()).contiguous()
             _require_mpb200(self, x)
             from . import emtn_cuda
             return emtn_cuda.resnet50_descriptor(self, x)
@@ -294,7 +294,7 @@ class Emtn(nn.Module):
     def forward(self, x):
         if getattr(self, "backend", "mpb200") == "mpb200":
             if x.is_cuda and (self.training or _wants_grad(self, x)):
-                return self._forward_autograd(x.float().contiguous())
+                return tuple(t.contiguous() for t in self._forward_autograd(x.float()))
             _require_mpb200(self, x)
             from . import emtn_cuda          # libmpb200 tcgen05 kernels
             with torch.no_grad():

@@ -64,6 +64,16 @@ def _wants_grad(mod: nn.Module, *tensors) -> bool:
                                         or any(p.requires_grad for p in mod.parameters()))
 
 
+def _public(y):
+    """Outputs of the differentiable path are channels-last in memory (ops._cl_view); a module's public `forward()` hands its
+    callers the reference's contiguous NCHW / NCDHW layout (`.view()` on it keeps working)."""
+    if torch.is_tensor(y):
+        return y.contiguous()
+    if isinstance(y, dict):
+        return {k: _public(v) for k, v in y.items()}
+    return tuple(_public(v) for v in y)
+
+
 def _require_no_grad(mod: nn.Module, *tensors) -> None:
     """Entry points that run under `torch.no_grad()` internally: called with autograd recording on and anything that
     asks for a gradient (an input, or any parameter of `mod`), they would hand back detached outputs and the caller's
@@ -137,7 +147,7 @@ class Conv2d_WS(nn.Conv2d):
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         pw = ops.pack_conv(ops.standardize_weight(self.weight), self.bias, x.device)
         a = ops.from_nchw(_as_f32_cuda(x))
@@ -154,7 +164,7 @@ class Conv3D_WS(nn.Conv3d):
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         pw = ops.pack_conv(ops.standardize_weight(self.weight), self.bias, x.device)
         a = ops.from_nchw(_as_f32_cuda(x))
@@ -206,7 +216,7 @@ class ResBlock_Custom(nn.Module, _Packed):
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
         out = self._forward_cl(a, None)
@@ -240,7 +250,7 @@ class AdaptiveGroupNorm(nn.Module):
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=False)
         g, b, g2, b2 = self._affine()
@@ -298,7 +308,7 @@ class ResBlock3D_Adaptive(nn.Module, _Packed):
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
         return ops.to_nchw(self._forward_cl(a, f32=True, split=False), 5)
@@ -363,7 +373,7 @@ class FlowField(nn.Module, _Packed):
     def forward(self, zs, adaptive_gamma, adaptive_beta):
         if _wants_grad(self, zs):
             _require_inference(self, zs.detach())
-            x = self._forward_autograd(zs.float().reshape(zs.shape[0], 512, 1, 1))
+            x = _public(self._forward_autograd(zs.float().reshape(zs.shape[0], 512, 1, 1)))
             assert x.shape[1] == 3, f"Expected 3 channels after conv3x3x3, got {x.shape[1]}"
             return x
         _require_inference(self, zs)
@@ -421,7 +431,7 @@ class ResBlock3D(nn.Module, _Packed):
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())         # (device check only)
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
         return ops.to_nchw(self._forward_cl(a, f32=True, split=False), 5)
@@ -475,7 +485,7 @@ class G3d(nn.Module):
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
         return ops.to_nchw(self._forward_cl(a), 5)
@@ -575,7 +585,7 @@ class ResBlock2D(nn.Module, _Packed):
     def forward(self, x):
         if self.training or _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=False, split=True)
         out, _ = self._forward_cl(a, f32=True, split=False)
@@ -728,7 +738,7 @@ class G2d(nn.Module, _Packed):
     def forward(self, x):
         if self.training or _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=False, split=True)
         return self._forward_cl(a)
@@ -805,7 +815,7 @@ class Eapp(nn.Module, _Packed):
     def forward(self, x):
         if self.training or _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return self._forward_autograd(x.float().contiguous())
+            return _public(self._forward_autograd(x.float()))
         _require_inference(self, x)
         x = _as_f32_cuda(x)
         vs = ops.to_nchw(self._volume_cl(x), 5)
@@ -883,7 +893,7 @@ class _WarpGenerator(nn.Module):
     def _forward(self, R, t, z, e):
         if _wants_grad(self, R, t, z, e):
             _require_inference(self, *(v.detach() for v in (R, t, z, e)))
-            return self._forward_autograd(R, t, z, e)
+            return _public(self._forward_autograd(R, t, z, e))
         _require_inference(self, R, t, z, e)
         em, theta = self._em_theta(R, t, z, e)
         return ops.warp_field(em, theta, 64)
@@ -1087,7 +1097,7 @@ class Gbase(nn.Module):
         assert xs.shape[0] == xd.shape[0], f"Expected zs and es to have the same shape (Bs == Bd), got {xs.shape[0]} and {xd.shape[0]}"
         if self.training or _wants_grad(self, xs, xd):
             _require_inference(self, xs.detach(), xd.detach())
-            return self._forward_autograd(xs.float().contiguous(), xd.float().contiguous())
+            return _public(self._forward_autograd(xs.float(), xd.float()))
         if (_FWD_GRAPHS and getattr(self, "forward_graphs", True) and not self.training and xs.is_cuda and xd.is_cuda
                 and xs.device == xd.device and tuple(xs.shape[1:]) == (3, 512, 512) and tuple(xd.shape[1:]) == (3, 512, 512)
                 and not _capturing(xs)):

@@ -823,14 +823,36 @@ def group_norm_backward(x: Act, grad_out: Act, stats: torch.Tensor, G: int, gamm
 
 
 def _to_cl_act(t: torch.Tensor) -> Act:
-    """NCHW / NCDHW fp32 -> channels-last fp32 Act."""
-    return from_nchw(t.detach().float().contiguous(), f32=True, split=False)
+    """Logical NCHW / NCDHW fp32 tensor -> channels-last fp32 Act.  The autograd Functions hand each other logical-NCHW tensors
+    whose MEMORY is already channels-last (`_cl_view`): those are wrapped without a copy; a contiguous NCHW tensor (the reference
+    layout, at the boundary) goes through the transposing kernel; anything else through one strided ATen copy."""
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() == 4:
+        v = t.permute(0, 2, 3, 1).unsqueeze(1)
+    else:
+        v = t.permute(0, 2, 3, 4, 1)
+    if not v.is_contiguous():
+        if t.is_contiguous():
+            return from_nchw(t, f32=True, split=False)
+        v = v.contiguous()
+    return Act(tuple(v.shape), f32=v)
+
+
+def _cl_view(a: Act, ndim: int) -> torch.Tensor:
+    """Channels-last fp32 Act -> logical NCHW / NCDHW tensor that is a VIEW of the same memory (torch.channels_last /
+    channels_last_3d strides): no transposition between consecutive operators of the differentiable path."""
+    N, D, H, W, C = a.shape
+    v = a.f32.view(N, D, H, W, C)
+    return v.permute(0, 4, 1, 2, 3) if ndim == 5 else v.view(N, H, W, C).permute(0, 3, 1, 2)
 
 
 class ConvFunction(torch.autograd.Function):
     """`F.conv2d` / `F.conv3d` (stride 1, padding k // 2) on libmpb200 with CUDA backward (row f-2): forward = the tcgen05
     implicit GEMM, dX = the same kernel on flipped / transposed weights, dW = `mp_conv_wgrad`, db = `mp_bias_grad`.
-    Tensors cross the boundary in the reference layout (NCHW / NCDHW fp32)."""
+    Tensors are logical NCHW / NCDHW fp32; outputs (and gradients) are channels-last in memory (`_cl_view`), so a chain of these
+    Functions never transposes; the reference layout is restored by `.contiguous()` at the modules' public `forward()`."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -843,7 +865,7 @@ class ConvFunction(torch.autograd.Function):
         ctx.save_for_backward(x.detach(), weight.detach())
         ctx.has_bias = bias is not None
         out, _ = conv(a, pack_conv(weight.detach(), None if bias is None else bias.detach(), x.device), f32=True)
-        return to_nchw(out, nd)
+        return _cl_view(out, nd)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -852,7 +874,7 @@ class ConvFunction(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             ensure_split(g)
-            gx = to_nchw(conv_input_grad(g, pack_conv_dgrad(weight, x.device)), ctx.nd)
+            gx = _cl_view(conv_input_grad(g, pack_conv_dgrad(weight, x.device)), ctx.nd)
         if ctx.needs_input_grad[1]:
             gw = conv_weight_grad(_to_cl_act(x), g, ctx.k)
             if ctx.nd == 4:
@@ -873,13 +895,13 @@ class GroupNormFunction(torch.autograd.Function):
                          None if beta is None else beta.detach().float().contiguous(), eps=eps)
         ctx.save_for_backward(x.detach(), stats, None if gamma is None else gamma.detach().float().contiguous())
         ctx.G, ctx.eps, ctx.nd = G, eps, x.dim()
-        return to_nchw(affine_act(a, ab, None, ACT_NONE, f32=True, split=False), x.dim())
+        return _cl_view(affine_act(a, ab, None, ACT_NONE, f32=True, split=False), x.dim())
 
     @staticmethod
     def backward(ctx, grad_out):
         x, stats, gamma = ctx.saved_tensors
         dx, dg, db = group_norm_backward(_to_cl_act(x), _to_cl_act(grad_out), stats, ctx.G, gamma, ctx.eps)
-        return (to_nchw(dx, ctx.nd), None, dg if ctx.needs_input_grad[2] else None,
+        return (_cl_view(dx, ctx.nd), None, dg if ctx.needs_input_grad[2] else None,
                 db if ctx.needs_input_grad[3] else None, None)
 
 
@@ -899,19 +921,19 @@ class ConvS2Function(torch.autograd.Function):
         ctx.save_for_backward(x.detach(), weight.detach())
         ctx.has_bias = bias is not None
         out, _ = conv(a, pack_conv(weight.detach(), None if bias is None else bias.detach(), x.device), f32=True, stride=2)
-        return to_nchw(out, 4)
+        return _cl_view(out, 4)
 
     @staticmethod
     def backward(ctx, grad_out):
         x, weight = ctx.saved_tensors
         N, _, H, W = x.shape
-        up = torch.zeros((N, grad_out.shape[1], H, W), dtype=torch.float32, device=grad_out.device)
+        up = torch.zeros((N, H, W, grad_out.shape[1]), dtype=torch.float32, device=grad_out.device).permute(0, 3, 1, 2)
         up[:, :, ::2, ::2] = grad_out
         g = _to_cl_act(up)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             ensure_split(g)
-            gx = to_nchw(conv_input_grad(g, pack_conv_dgrad(weight, x.device)), 4)
+            gx = _cl_view(conv_input_grad(g, pack_conv_dgrad(weight, x.device)), 4)
         if ctx.needs_input_grad[1]:
             gw = conv_weight_grad(_to_cl_act(x), g, ctx.k).squeeze(2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -944,10 +966,10 @@ def conv_train(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     if stride == 2 and all(k == 1 for k in weight.shape[2:]):
         x = x[:, :, ::2, ::2] if x.dim() == 4 else x[:, :, ::2, ::2, ::2]
         stride = 1
-    x = _pad_channels(x.contiguous(), 1, 16)
+    x = _pad_channels(x, 1, 16)
     w = _pad_channels(_pad_channels(weight.float(), 1, 16), 0, 16)
     b = None if bias is None else _pad_channels(bias.float(), 0, 16)
-    y = (ConvS2Function if stride == 2 else ConvFunction).apply(x.contiguous(), w, b)
+    y = (ConvS2Function if stride == 2 else ConvFunction).apply(x, w, b)
     return y if cout == y.shape[1] else y[:, :cout]
 
 
@@ -973,7 +995,7 @@ class BatchNormFunction(torch.autograd.Function):
         mean = stats[0, :, 0] / cnt
         var = (stats[0, :, 1] / cnt - mean * mean).clamp_min(0.0)
         ctx.mark_non_differentiable(mean, var)
-        return to_nchw(Act(a.shape, f32=y.f32.view(a.shape)), x.dim()), mean, var
+        return _cl_view(Act(a.shape, f32=y.f32.view(a.shape)), x.dim()), mean, var
 
     @staticmethod
     def backward(ctx, grad_out, _gm, _gv):
@@ -982,7 +1004,7 @@ class BatchNormFunction(torch.autograd.Function):
         N, D, H, W, C = a.shape
         one = (1, 1, N * D * H, W, C)
         dx, dg, db = group_norm_backward(Act(one, f32=a.f32.view(one)), Act(one, f32=g.f32.view(one)), stats, C, gamma, ctx.eps)
-        return (to_nchw(Act(a.shape, f32=dx.f32.view(a.shape)), ctx.nd), dg if ctx.needs_input_grad[1] else None,
+        return (_cl_view(Act(a.shape, f32=dx.f32.view(a.shape)), ctx.nd), dg if ctx.needs_input_grad[1] else None,
                 db if ctx.needs_input_grad[2] else None, None)
 
 
@@ -991,7 +1013,7 @@ def batch_norm_train(x: torch.Tensor, bn) -> torch.Tensor:
     and the running statistics updated like ATen does (momentum, unbiased variance, `num_batches_tracked`); eval mode: the
     running-statistics affine map as a torch expression (elementwise)."""
     if bn.training or bn.running_mean is None:
-        y, mean, var = BatchNormFunction.apply(x.float().contiguous(), bn.weight, bn.bias, bn.eps)
+        y, mean, var = BatchNormFunction.apply(x.float(), bn.weight, bn.bias, bn.eps)
         if bn.training and bn.track_running_stats and bn.running_mean is not None:
             with torch.no_grad():
                 n = x.numel() // x.shape[1]
