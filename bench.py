@@ -515,11 +515,11 @@ def run_b200(args):
             # BASELINE config 5, generator half (row f-2): one `train_base` iteration of Gbase alone -- train-mode forward
             # (batch-statistics BatchNorm), an L1 loss against the driver frame in place of the out-of-scope perceptual /
             # adversarial losses, backward through every operator of the path on libmpb200, AdamW step (train.py:135, 194, 318).
-            # Runs on a deep copy so the headline model keeps its eval-mode weights.
-            import copy
+            # Runs on a second model instance so the headline model keeps its eval-mode weights.
             cfg5 = None
             if not args.no_train_leg:
-                Gt = copy.deepcopy(G).train()
+                import __graft_entry__ as entry
+                Gt = entry.load_seeded_gbase(dev)[0].train()       # a second instance: the headline model keeps its eval-mode state
                 opt = torch.optim.AdamW(Gt.parameters(), lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2)
                 xs1, xd1 = xs_d[:1].contiguous(), xd_d[:1].contiguous()
 

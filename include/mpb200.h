@@ -247,6 +247,14 @@ int mp_apply_warping_field_backward(const float* grad_out, const float* v, const
  * not bit for bit.  Cin, Cout multiples of 4; odd kernel sizes (padding k / 2). */
 int mp_conv_wgrad(const float* x, const float* dy, float* dw, int N, int D, int H, int W, int Cin, int Cout, int KD, int KH,
                   int KW, void* stream);
+/* The same weight gradient on tcgen05 (round 2, second session): x and dy as split-bf16 plane pairs (hi, lo; channels-last, the
+ * operand format of mp_conv_tc).  K = positions: both operands are read as they lie in HBM ("MN-major" UMMA descriptors over TMA
+ * boxes of 64 channels x 32 / 64 positions), tap shift = TMA box origin, zero border and channel padding = TMA out-of-bounds
+ * fill, one TMEM accumulator per tap of a 3-tap group, split-K with 16-byte fp32 RED.  Cin, Cout multiples of 8.
+ * mp_conv_wgrad_tc_supported() tells whether a shape can take this path (else mp_conv_wgrad). */
+int mp_conv_wgrad_tc_supported(int Cin, int Cout, int KD, int KH, int KW);
+int mp_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw, int N, int D, int H,
+                     int W, int Cin, int Cout, int KD, int KH, int KW, void* stream);
 /* dL/dbias = column sums of dy [P, C] -> db [C] (overwritten). */
 int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* stream);
 /* nn.GroupNorm backward (model.py:302-316, 439-471) on channels-last fp32 tensors [N, S, C]: dx (fp32), dgamma / dbeta [C]

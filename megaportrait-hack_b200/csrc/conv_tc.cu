@@ -1391,6 +1391,184 @@ k_conv_tc3(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ weight gradient (tcgen05)
+// dW[co][tap][ci] = sum_p dY[p][co] * X[p + shift(tap)][ci]: one GEMM per filter tap whose K axis is the POSITION axis.  Both
+// operands are channels-last tensors, i.e. [K = position][MN = channel] with the channel contiguous: "MN-major" in UMMA terms.
+// A TMA box of (64 channels, bw, bh, bd, bn positions) with SWIZZLE_128B lands in shared memory as [positions][128 B] rows --
+// exactly the canonical MN-major SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) (16-byte units): 8-row groups 1 024 B apart
+// (SBO), 64-channel sub-tiles LBO = positions * 128 B apart.  So the tensor cores read dY and X as they lie in HBM: no transpose,
+// no im2col; the tap shift is the box origin of the X load and the zero border is TMA's out-of-bounds fill (which also pads
+// channel counts up to the 128 x BN tile and ragged boxes at the volume edge).  Three bf16 passes (hi*hi + hi*lo + lo*hi) with fp32
+// accumulation in TMEM, one accumulator per tap of the CTA's tap group (the un-shifted operand is staged once per group),
+// split-K over position boxes with a vectorised fp32 RED epilogue.
+struct WgParams {
+  float* dw;
+  int Cout, Cin, T, KD, KH, KW;
+  int swap;                       // 0: M = output channels (dY), N = input channels (X);  1: M = input channels, N = output channels
+  int BN, TG;                     // N tile (64 | 128); taps per CTA
+  int tiles_m, tiles_n, tap_groups;
+  int bw, bh, bd, bn, kblk;       // position box (K block)
+  int nbw, nbh, nbd;              // boxes per dimension (the sample axis takes the rest)
+  int total_boxes, boxes_per_slice;
+  int STAGES;
+  int s_sub, x_sub;               // 64-channel sub-tiles of the shared (dY) / shifted (X) operand per stage
+  uint32_t sub_bytes, stage_bytes;
+  uint32_t idesc, tmem_cols;
+};
+constexpr int WG_TC_THREADS = 192;        // warp 0: TMA producer, warp 1: TMEM + MMA issue, warps 2-5: epilogue
+
+__global__ void __launch_bounds__(WG_TC_THREADS, 1)
+k_wgrad_tc(const __grid_constant__ CUtensorMap map_s_hi, const __grid_constant__ CUtensorMap map_s_lo,
+           const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + (uint32_t)p.STAGES * p.stage_bytes;      // full[S], empty[S], done
+  const uint32_t done_bar = bars + 2 * p.STAGES * 8;
+  const uint32_t tmem_slot = done_bar + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  // tile: (m tile, n tile, tap group); slice of the K (position box) axis
+  int tile = blockIdx.x;
+  const int tg = tile % p.tap_groups; tile /= p.tap_groups;
+  const int n0 = (tile % p.tiles_n) * p.BN;
+  const int m0 = (tile / p.tiles_n) * 128;
+  const int tap0 = tg * p.TG;
+  const int ntap = min(p.TG, p.T - tap0);
+  const int box0 = blockIdx.y * p.boxes_per_slice;
+  const int nbox = min(p.boxes_per_slice, p.total_boxes - box0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.STAGES; ++s) {
+      mbar_init(bars + s * 8, 1);
+      mbar_init(bars + (p.STAGES + s) * 8, 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_s_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_s_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x_lo)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+
+  // shared operand S = dY (channel origin: m0 or n0), shifted operand X (the other origin)
+  const int s_c0 = p.swap ? n0 : m0, x_c0 = p.swap ? m0 : n0;
+  const uint32_t s_plane = (uint32_t)p.s_sub * p.sub_bytes, x_plane = (uint32_t)p.x_sub * p.sub_bytes;
+  const uint32_t x_off = 2u * s_plane;                 // stage layout: [S hi][S lo] then per tap [X hi][X lo]
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0 && nbox > 0) {
+      const uint32_t tx = 2u * s_plane + (uint32_t)ntap * 2u * x_plane;
+      uint32_t s = 0, ph_bit = 1;
+      for (int b = box0; b < box0 + nbox; ++b) {
+        int t = b;
+        const int w0 = (t % p.nbw) * p.bw; t /= p.nbw;
+        const int h0 = (t % p.nbh) * p.bh; t /= p.nbh;
+        const int d0 = (t % p.nbd) * p.bd;
+        const int ns = (t / p.nbd) * p.bn;
+        mbar_wait(bars + (p.STAGES + s) * 8, ph_bit);
+        const uint32_t sa = smem_base + s * p.stage_bytes, fb = bars + s * 8;
+        mbar_expect_tx(fb, tx);
+        for (int j = 0; j < p.s_sub; ++j) {
+          tma_load_5d(sa + j * p.sub_bytes, &map_s_hi, fb, s_c0 + 64 * j, w0, h0, d0, ns);
+          tma_load_5d(sa + s_plane + j * p.sub_bytes, &map_s_lo, fb, s_c0 + 64 * j, w0, h0, d0, ns);
+        }
+        for (int i = 0; i < ntap; ++i) {
+          const int tap = tap0 + i;
+          const int kw = tap % p.KW, kh = (tap / p.KW) % p.KH, kd = tap / (p.KW * p.KH);
+          const int ws = w0 + kw - p.KW / 2, hs = h0 + kh - p.KH / 2, ds = d0 + kd - p.KD / 2;
+          const uint32_t xb = sa + x_off + (uint32_t)i * 2u * x_plane;
+          for (int j = 0; j < p.x_sub; ++j) {
+            tma_load_5d(xb + j * p.sub_bytes, &map_x_hi, fb, x_c0 + 64 * j, ws, hs, ds, ns);
+            tma_load_5d(xb + x_plane + j * p.sub_bytes, &map_x_lo, fb, x_c0 + 64 * j, ws, hs, ds, ns);
+          }
+        }
+        if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (whole warp converged, one elected lane)
+    if (nbox > 0) {
+      // MN-major SWIZZLE_128B descriptors: SBO = 1 024 B between 8-position groups, LBO = one 64-channel sub-tile
+      const uint32_t dhi = desc_hi_word(1024u, 2u);
+      const uint32_t lbo = ((p.sub_bytes >> 4) & 0x3FFFu) << 16;
+      auto dlo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | lbo; };
+      const int ksteps = p.kblk / 16;
+      uint32_t s = 0, ph_bit = 0;
+      for (int b = 0; b < nbox; ++b) {
+        mbar_wait(bars + s * 8, ph_bit);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + s * p.stage_bytes;
+        const uint32_t s_hi = dlo(sa), s_lo = dlo(sa + s_plane);
+        for (int i = 0; i < ntap; ++i) {
+          const uint32_t xb = sa + x_off + (uint32_t)i * 2u * x_plane;
+          const uint32_t x_hi = dlo(xb), x_lo = dlo(xb + x_plane);
+          const uint32_t a_hi = p.swap ? x_hi : s_hi, a_lo = p.swap ? x_lo : s_lo;
+          const uint32_t b_hi = p.swap ? s_hi : x_hi, b_lo = p.swap ? s_lo : x_lo;
+          const uint32_t acc = tmem_base + (uint32_t)(i * p.BN);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t ko = (uint32_t)k * 128u;          // 16 positions x 128 B, in 16-byte units
+            umma_lean_e(acc, a_lo + ko, b_hi + ko, dhi, p.idesc, (b > 0 || k > 0) ? 1u : 0u);
+            umma_lean_e(acc, a_hi + ko, b_lo + ko, dhi, p.idesc, 1u);
+            umma_lean_e(acc, a_hi + ko, b_hi + ko, dhi, p.idesc, 1u);
+          }
+        }
+        umma_commit_e(bars + (p.STAGES + s) * 8);            // frees the stage once its MMAs have read it
+        if (++s == (uint32_t)p.STAGES) { s = 0; ph_bit ^= 1u; }
+      }
+      umma_commit_e(done_bar);
+    }
+  } else if (nbox > 0) {
+    // ===================================================================== epilogue: TMEM -> fp32 RED into dW[co][tap][ci]
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(done_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int CM = p.swap ? p.Cin : p.Cout, CN = p.swap ? p.Cout : p.Cin;
+    for (int i = 0; i < ntap; ++i) {
+      const int tap = tap0 + i;
+      for (int c = 0; c < p.BN; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * p.BN + c), v);
+        if (m >= CM) continue;
+        if (!p.swap) {          // thread = one output channel, 32 consecutive input channels: 16-byte vector REDs
+          float* row = p.dw + ((int64_t)m * p.T + tap) * p.Cin;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int ci = n0 + c + j;
+            if (ci + 3 < CN) atomicAdd(reinterpret_cast<float4*>(row + ci), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            else
+              for (int e = 0; e < 4; ++e)
+                if (ci + e < CN) atomicAdd(row + ci + e, v[j + e]);
+          }
+        } else {                // thread = one input channel: lanes of a warp are consecutive addresses for every column
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = n0 + c + j;
+            if (co < CN) atomicAdd(p.dw + ((int64_t)co * p.T + tap) * p.Cin + m, v[j]);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1983,5 +2161,107 @@ extern "C" int mp_conv_tc(const mp_conv_desc* d, void* stream) {
       k_conv_tc2<<<grid, NUM_THREADS3, pl.smem_bytes, mp_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, mo, ma2_hi, ma2_lo, pl.p);
   }
   MP_LAUNCH_CHECK("mp_conv_tc");
+  return 0;
+}
+
+// ---- weight gradient on tcgen05 (row f-2): see k_wgrad_tc
+namespace {
+int wg_pow2_at_least(int v, int cap) {
+  int r = 1;
+  while (r < v && r < cap) r <<= 1;
+  return r;
+}
+int encode_wg_map(CUtensorMap* m, const void* ptr, int C, int N, int D, int H, int W, const WgParams& p) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H, (cuuint64_t)C * 2 * W * H * D};
+  cuuint32_t box[5] = {64u, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, (cuuint32_t)p.bn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_cached(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : mp_set_error("mp_conv_wgrad_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+}
+}  // namespace
+
+extern "C" int mp_conv_wgrad_tc_supported(int Cin, int Cout, int KD, int KH, int KW) {
+  return (Cin > 0 && Cout > 0 && Cin % 8 == 0 && Cout % 8 == 0 && KD % 2 == 1 && KH % 2 == 1 && KW % 2 == 1 &&
+          KD * KH * KW <= 4096 && get_encoder() != nullptr) ? 1 : 0;
+}
+
+extern "C" int mp_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw, int N, int D,
+                                int H, int W, int Cin, int Cout, int KD, int KH, int KW, void* stream) {
+  MP_REQUIRE(x_hi && x_lo && dy_hi && dy_lo && dw, "mp_conv_wgrad_tc: null pointer");
+  MP_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "mp_conv_wgrad_tc: bad dims");
+  MP_REQUIRE(mp_conv_wgrad_tc_supported(Cin, Cout, KD, KH, KW) == 1,
+             "mp_conv_wgrad_tc: needs channel counts in multiples of 8 and odd kernel sizes, got %d -> %d, %dx%dx%d", Cin, Cout, KD,
+             KH, KW);
+  MP_REQUIRE((((uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)dy_hi | (uintptr_t)dy_lo | (uintptr_t)dw) & 15) == 0,
+             "mp_conv_wgrad_tc: operands must be 16-byte aligned");
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.dw = dw; p.Cout = Cout; p.Cin = Cin; p.KD = KD; p.KH = KH; p.KW = KW; p.T = KD * KH * KW;
+  // M side in 128-channel tiles, N side in 64 / 128: put the roles so that the zero padding of the tile is smallest
+  auto n_tile = [](int c) { return c > 64 ? 128 : 64; };
+  auto padded = [&](int cm, int cn) { return (int64_t)((cm + 127) / 128 * 128) * ((cn + n_tile(cn) - 1) / n_tile(cn) * n_tile(cn)); };
+  p.swap = padded(Cin, Cout) < padded(Cout, Cin) ? 1 : 0;
+  const int CM = p.swap ? Cin : Cout, CN = p.swap ? Cout : Cin;
+  p.BN = n_tile(CN);
+  p.tiles_m = (CM + 127) / 128;
+  p.tiles_n = (CN + p.BN - 1) / p.BN;
+  p.TG = p.T >= 3 ? 3 : 1;
+  p.tap_groups = (p.T + p.TG - 1) / p.TG;
+  p.kblk = p.TG == 1 ? 64 : 32;
+  // position box of kblk positions: W first, then H, D, and the sample axis takes what is left
+  int rem = p.kblk;
+  p.bw = wg_pow2_at_least(W, rem < 8 ? rem : 8); rem /= p.bw;
+  p.bh = wg_pow2_at_least(H, rem); rem /= p.bh;
+  p.bd = wg_pow2_at_least(D, rem); rem /= p.bd;
+  p.bn = rem;
+  p.nbw = (W + p.bw - 1) / p.bw; p.nbh = (H + p.bh - 1) / p.bh; p.nbd = (D + p.bd - 1) / p.bd;
+  const int64_t boxes = (int64_t)p.nbw * p.nbh * p.nbd * ((N + p.bn - 1) / p.bn);
+  MP_REQUIRE(boxes < 0x7fffffff, "mp_conv_wgrad_tc: too many position boxes");
+  p.total_boxes = (int)boxes;
+  p.s_sub = p.swap ? p.BN / 64 : 2;
+  p.x_sub = p.swap ? 2 : p.BN / 64;
+  p.sub_bytes = (uint32_t)p.kblk * 128u;
+  p.stage_bytes = 2u * p.sub_bytes * (uint32_t)(p.s_sub + p.TG * p.x_sub);
+  p.STAGES = (int)((SMEM_LIMIT - 2048u) / p.stage_bytes);
+  if (p.STAGES > 6) p.STAGES = 6;
+  MP_REQUIRE(p.STAGES >= 2, "mp_conv_wgrad_tc: stage of %u B does not fit twice", p.stage_bytes);
+  p.tmem_cols = next_pow2((uint32_t)(p.TG * p.BN) < 32u ? 32u : (uint32_t)(p.TG * p.BN));
+  // kind::f16, D = f32, A / B = bf16, both operands MN-major (bits 15 / 16), N = BN, M = 128
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n * p.tap_groups;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // split K so that the grid is about two waves of one CTA per SM; every slice keeps at least 4 boxes
+  int64_t slices = (2 * (int64_t)sms + tiles - 1) / tiles;
+  if (slices > (p.total_boxes + 3) / 4) slices = (p.total_boxes + 3) / 4;
+  if (slices < 1) slices = 1;
+  if (slices > 65535) slices = 65535;
+  p.boxes_per_slice = (int)((p.total_boxes + slices - 1) / slices);
+  slices = (p.total_boxes + p.boxes_per_slice - 1) / p.boxes_per_slice;
+  MP_REQUIRE(tiles < 0x7fffffff, "mp_conv_wgrad_tc: too many tiles");
+  CUtensorMap ms_hi, ms_lo, mx_hi, mx_lo;
+  if (int e = encode_wg_map(&ms_hi, dy_hi, Cout, N, D, H, W, p)) return e;
+  if (int e = encode_wg_map(&ms_lo, dy_lo, Cout, N, D, H, W, p)) return e;
+  if (int e = encode_wg_map(&mx_hi, x_hi, Cin, N, D, H, W, p)) return e;
+  if (int e = encode_wg_map(&mx_lo, x_lo, Cin, N, D, H, W, p)) return e;
+  {
+    static bool attr_done[64] = {false};
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      cudaError_t ae = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+      MP_REQUIRE(ae == cudaSuccess, "mp_conv_wgrad_tc: cannot opt in to %u B shared memory: %s", SMEM_LIMIT, cudaGetErrorString(ae));
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+  }
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * p.T * Cin, mp_stream(stream));
+  MP_REQUIRE(e == cudaSuccess, "mp_conv_wgrad_tc: memset: %s", cudaGetErrorString(e));
+  const uint32_t smem_bytes = (uint32_t)p.STAGES * p.stage_bytes + 2048u;
+  dim3 grid((unsigned)tiles, (unsigned)slices);
+  k_wgrad_tc<<<grid, WG_TC_THREADS, smem_bytes, mp_stream(stream)>>>(ms_hi, ms_lo, mx_hi, mx_lo, p);
+  MP_LAUNCH_CHECK("mp_conv_wgrad_tc");
   return 0;
 }

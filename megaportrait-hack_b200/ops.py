@@ -783,6 +783,10 @@ class WarpFunction(torch.autograd.Function):
         return gv, gwf
 
 
+# weight gradient on the tcgen05 kernel (MPB200_WGRAD=mma selects the first-generation mma.sync kernel; A/B runs and tests)
+WGRAD_TC = os.environ.get("MPB200_WGRAD", "tc") != "mma"
+
+
 def conv_weight_grad(x: Act, grad_out: Act, k: Tuple[int, int, int]) -> torch.Tensor:
     """dL/dW of a stride-1 "same" convolution (row f-2): x, grad_out channels-last fp32 Acts -> (Cout, Cin, kd, kh, kw) fp32.
     One tensor-core GEMM per filter tap with K = positions (three bf16 passes, fp32 accumulation)."""
@@ -793,8 +797,17 @@ def conv_weight_grad(x: Act, grad_out: Act, k: Tuple[int, int, int]) -> torch.Te
     kd, kh, kw = k
     dw = torch.empty((Cout, kd * kh * kw, Cin), dtype=torch.float32, device=x.device)
     L = _lib.load()
-    _lib.check(L.mp_conv_wgrad(_p(x.f32), _p(grad_out.f32), _p(dw), N, D, H, W, Cin, Cout, kd, kh, kw, _stream()),
-               "mp_conv_wgrad")
+    if WGRAD_TC and L.mp_conv_wgrad_tc_supported(Cin, Cout, kd, kh, kw) == 1:
+        # tcgen05 path: both operands as split-bf16 planes, read position-major straight from the channels-last tensors
+        ensure_split(x)
+        ensure_split(grad_out)
+        flops = 2 * N * D * H * W * Cout * Cin * kd * kh * kw
+        with _Prof(f"wgrad_tc|{N}x{D}x{H}x{W} {Cin}->{Cout} k{kd}{kh}{kw}", flops):
+            _lib.check(L.mp_conv_wgrad_tc(_p(x.hi), _p(x.lo), _p(grad_out.hi), _p(grad_out.lo), _p(dw), N, D, H, W, Cin, Cout,
+                                          kd, kh, kw, _stream()), "mp_conv_wgrad_tc")
+    else:
+        _lib.check(L.mp_conv_wgrad(_p(x.f32), _p(grad_out.f32), _p(dw), N, D, H, W, Cin, Cout, kd, kh, kw, _stream()),
+                   "mp_conv_wgrad")
     _count(2)
     return dw.view(Cout, kd, kh, kw, Cin).permute(0, 4, 1, 2, 3).contiguous()
 

@@ -1081,6 +1081,38 @@ def test_conv_function_gradients_match_autograd(ops, case):
         assert e < 2e-5, (name, e)
 
 
+@pytest.mark.parametrize("mode", ["tc", "mma"])
+@pytest.mark.parametrize("case", [
+    dict(N=1, Ci=96, Co=96, sp=(8, 32, 32), k=(3, 3, 3)),          # the volume convolution: 9 tap groups of 3, tile padding 96 -> 128
+    dict(N=2, Ci=16, Co=64, sp=(1, 40, 24), k=(1, 7, 7)),          # padded RGB stem: 49 taps, 16-channel operand, ragged boxes
+    dict(N=2, Ci=64, Co=16, sp=(1, 24, 20), k=(1, 3, 3)),          # 16 output channels: operand roles swapped
+    dict(N=3, Ci=512, Co=256, sp=(4, 1, 1), k=(3, 3, 3)),          # flow-field tower: 4 positions per sample, boxes span samples
+    dict(N=2, Ci=256, Co=192, sp=(1, 16, 16), k=(1, 1, 1)),        # 1x1: one tap, 64-position K blocks, ragged 192 = 128 + 64
+    dict(N=1, Ci=128, Co=128, sp=(1, 64, 64), k=(1, 3, 3)),
+], ids=["c3d_96", "stem7x7", "swap16", "flow_4x1x1", "c1x1_192", "c2d_128"])
+def test_conv_weight_grad_kernels(ops, case, mode):
+    """Row f-2: dW of a stride-1 "same" convolution from channels-last x and dy -- the tcgen05 kernel (`mp_conv_wgrad_tc`:
+    position-major UMMA operands straight from TMA boxes, tap groups in TMEM, split-K RED) and the first-generation `mma.sync`
+    kernel (`mp_conv_wgrad`) against float64 ATen: <= 2e-5 of abs-max (three bf16 passes, fp32 accumulation)."""
+    N, Ci, Co, sp, k = case["N"], case["Ci"], case["Co"], case["sp"], case["k"]
+    x = rnd(N, Ci, *sp, seed=171)
+    go = rnd(N, Co, *sp, seed=172)
+    want = torch.nn.grad.conv3d_weight(x.double(), (Co, Ci) + tuple(k), go.double(), padding=tuple(kk // 2 for kk in k))
+    saved = ops.WGRAD_TC
+    ops.WGRAD_TC = mode == "tc"
+    try:
+        n0 = ops.LAUNCHES
+        got = ops.conv_weight_grad(ops._to_cl_act(x.to(DEV)), ops._to_cl_act(go.to(DEV)), tuple(k))
+        torch.cuda.synchronize()
+        assert ops.LAUNCHES > n0
+    finally:
+        ops.WGRAD_TC = saved
+    assert got.shape == want.shape
+    e = relerr(got.cpu(), want.float())
+    print(mode, case, e)
+    assert e < 2e-5, e
+
+
 def test_group_norm_function_gradients_match_autograd(ops):
     """Row f-2: `ops.GroupNormFunction` (forward: stats + affine; backward: mp_group_norm_backward) against torch autograd."""
     N, C, sp, G = 2, 64, (4, 12, 20), 32
