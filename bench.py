@@ -542,13 +542,48 @@ def run_b200(args):
                 t1.record()
                 torch.cuda.synchronize()
                 ms_t = t0.elapsed_time(t1) / 2
+                # the same iteration replayed as ONE CUDA graph (whole-network capture: forward, backward and a capturable AdamW):
+                # at batch 1 the eager iteration is bound by the host enqueueing ~7 000 launches
+                ms_graph, graph_note_t = None, None
+                try:
+                    opt = torch.optim.AdamW(Gt.parameters(), lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True)
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            train_iter()
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    gt = torch.cuda.CUDAGraph()
+                    opt.zero_grad(set_to_none=True)
+                    with torch.cuda.graph(gt):
+                        with torch.enable_grad():
+                            pred, _ = Gt(xs1, xd1)
+                            loss_g = (pred - xd1).abs().mean()
+                            loss_g.backward()
+                        opt.step()
+                    gt.replay()
+                    torch.cuda.synchronize()
+                    t0.record()
+                    for _ in range(3):
+                        gt.replay()
+                    t1.record()
+                    torch.cuda.synchronize()
+                    ms_graph = t0.elapsed_time(t1) / 3
+                    graph_note_t = f"loss after replay {float(loss_g):.6f}"
+                    del gt
+                except Exception as e:  # noqa: BLE001  (the eager number above stands on its own)
+                    graph_note_t = f"capture failed: {type(e).__name__}: {str(e)[:200]}"
+                    torch.cuda.synchronize()
                 # 2041 GF forward per pair; backward = data + weight gradient of every convolution ~ 2x the forward
                 cfg5 = {"generator_fwd_bwd_adamw_batch1": {"ms": ms_t, "pairs_per_s": 1e3 / ms_t, "loss": float(loss),
+                                                           "ms_cuda_graph": ms_graph, "cuda_graph": graph_note_t,
                                                            "libmpb200_launches": launches_train,
                                                            "useful_tflops": 3 * 2041e9 / (ms_t * 1e-3) / 1e12},
                         "what": "BASELINE config 5, generator half at batch 1 on one GPU: Gbase.train() forward + backward + AdamW "
                                 "with an L1 loss (losses / discriminator are out of scope); fp32-grade three-pass convolutions in "
-                                "all three directions, eager launches, NCHW <-> channels-last conversion around every operator"}
+                                "all three directions (weight gradient on tcgen05), operators exchange channels-last views; `ms` = eager "
+                                "launches, `ms_cuda_graph` = the whole iteration replayed as one CUDA graph"}
                 del Gt, opt
 
     t = torch.tensor([ms, ms_e2e, strong if strong is not None else 0.0], dtype=torch.float64, device=dev)

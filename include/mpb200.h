@@ -255,6 +255,10 @@ int mp_conv_wgrad(const float* x, const float* dy, float* dw, int N, int D, int 
 int mp_conv_wgrad_tc_supported(int Cin, int Cout, int KD, int KH, int KW);
 int mp_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw, int N, int D, int H,
                      int W, int Cin, int Cout, int KD, int KH, int KW, void* stream);
+/* OIDHW fp32 weights [Cout, Cin, T] -> the split-bf16 K-major operand planes [rows_pad][K] of mp_conv_tc in one launch:
+ * dgrad = 0: the forward operand (rows = Cout, K = tap * Cin + ci); dgrad = 1: the operand of the data gradient (rows = Cin,
+ * K = tap * Cout + co, taps reversed).  Rows >= the real row count are zero.  Bit-identical to ops.pack_conv on fp32 weights. */
+int mp_pack_conv_weights(const float* w, void* out_hi, void* out_lo, int Cout, int Cin, int T, int rows_pad, int dgrad, void* stream);
 /* dL/dbias = column sums of dy [P, C] -> db [C] (overwritten). */
 int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* stream);
 /* nn.GroupNorm backward (model.py:302-316, 439-471) on channels-last fp32 tensors [N, S, C]: dx (fp32), dgamma / dbeta [C]

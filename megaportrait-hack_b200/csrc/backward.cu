@@ -12,7 +12,12 @@
 // gradient (ops.conv_input_grad on the tcgen05 kernel).  CTA = 64 x 64 tile of one tap over a slice of the positions; the
 // slices are summed with fp32 RED into dW (split-K).  This slice uses the legacy mma.sync path: the operand it needs (MN-major
 // A and B from channels-last tensors with a per-tap position shift and border mask) has no TMA box, so the tiles are built by
-// the threads anyway; moving the inner product to tcgen05 (smem descriptors with the transpose bits) is the follow-up.
+// the threads anyway.  (Superseded on supported shapes by mp_conv_wgrad_tc in conv_tc.cu: the same GEMM on tcgen05 with
+// MN-major UMMA descriptors over TMA boxes; this kernel stays as the fallback and as its cross-check.)
+//
+//   mp_pack_conv_weights       OIDHW fp32 weights -> the split-bf16 K-major operand planes of mp_conv_tc in ONE launch, for the
+//                              forward convolution or (transposed + tap-flipped) for its data gradient: the training step repacks
+//                              every weight twice per iteration, which as ATen expressions cost ~10 launches each
 #include "common.cuh"
 
 namespace mpb200 {
@@ -229,6 +234,45 @@ k_gn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, const 
 }
 
 }  // namespace mpb200
+
+namespace mpb200 {
+// out planes [rows_pad][K] bf16 (hi, lo).  dgrad = 0: rows = Cout, K index = tap * Cin + ci, value w[co][ci][tap].
+// dgrad = 1: rows = Cin, K index = tap' * Cout + co, value w[co][ci][T - 1 - tap'] (all spatial axes flipped).
+__global__ void k_pack_conv_weights(const float* __restrict__ w, bf16* __restrict__ hi, bf16* __restrict__ lo, int Cout, int Cin,
+                                    int T, int rows, int rows_pad, int dgrad) {
+  const int64_t K = (int64_t)T * (dgrad ? Cout : Cin);
+  const int64_t total = (int64_t)rows_pad * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / K);
+    const int64_t kk = i - (int64_t)r * K;
+    float v = 0.f;
+    if (r < rows) {
+      if (!dgrad) {
+        const int tap = (int)(kk / Cin), ci = (int)(kk % Cin);
+        v = w[((int64_t)r * Cin + ci) * T + tap];
+      } else {
+        const int tap = (int)(kk / Cout), co = (int)(kk % Cout);
+        v = w[((int64_t)co * Cin + r) * T + (T - 1 - tap)];
+      }
+    }
+    mp_split2(v, hi[i], lo[i]);
+  }
+}
+}  // namespace mpb200
+
+extern "C" int mp_pack_conv_weights(const float* w, void* out_hi, void* out_lo, int Cout, int Cin, int T, int rows_pad, int dgrad,
+                                    void* stream) {
+  MP_REQUIRE(w && out_hi && out_lo && Cout > 0 && Cin > 0 && T > 0, "mp_pack_conv_weights: bad arguments");
+  const int rows = dgrad ? Cin : Cout;
+  MP_REQUIRE(rows_pad >= rows, "mp_pack_conv_weights: rows_pad %d < %d rows", rows_pad, rows);
+  const int64_t total = (int64_t)rows_pad * T * (dgrad ? Cout : Cin);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mpb200::k_pack_conv_weights<<<(unsigned)blocks, 256, 0, mp_stream(stream)>>>(w, (bf16*)out_hi, (bf16*)out_lo, Cout, Cin, T, rows,
+                                                                              rows_pad, dgrad);
+  MP_LAUNCH_CHECK("mp_pack_conv_weights");
+  return 0;
+}
 
 extern "C" int mp_conv_wgrad(const float* x, const float* dy, float* dw, int N, int D, int H, int W, int Cin, int Cout, int KD,
                              int KH, int KW, void* stream) {

@@ -99,3 +99,21 @@ def test_gbase_trains_through_libmpb200(seeded_sd):
     with torch.no_grad():
         rgb, _ = G(xs.cuda(), xd.cuda())
     assert torch.isfinite(rgb).all() and rgb.shape == (1, 3, 512, 512)
+
+
+def test_pack_conv_weights_kernel_matches_host_packing():
+    """`ops.pack_conv_train` (one `mp_pack_conv_weights` launch) == `ops.pack_conv` / `ops.pack_conv_dgrad` (ATen expressions), bit
+    for bit, for 2-D, 3-D, 1x1 and 7x7 weights and row counts that need padding to 16."""
+    from megaportrait_hack_b200 import lib, ops
+    lib.build()
+    g = torch.Generator().manual_seed(5)
+    for shape in ((96, 96, 3, 3, 3), (48, 32, 3, 3), (16, 16, 7, 7), (512, 2048, 1, 1), (24, 64, 1, 3, 3)):
+        w = torch.randn(shape, generator=g).cuda()
+        b = torch.randn(shape[0], generator=g).cuda()
+        for dgrad in (False, True):
+            ref = ops.pack_conv_dgrad(w) if dgrad else ops.pack_conv(w, b)
+            got = ops.pack_conv_train(w, b, dgrad=dgrad)
+            assert (got.Cin, got.Cout, got.Cout_pad, got.k) == (ref.Cin, ref.Cout, ref.Cout_pad, ref.k), (shape, dgrad)
+            assert torch.equal(got.w_hi, ref.w_hi) and torch.equal(got.w_lo, ref.w_lo), (shape, dgrad)
+            assert (got.bias is None) == (ref.bias is None) and (got.bias is None or torch.equal(got.bias, ref.bias))
+            assert got.w_lo.data_ptr() == got.w_hi.data_ptr() + got.w_hi.numel() * 2      # one allocation: merged TMA load
