@@ -263,7 +263,7 @@ int mp_pack_conv_weights(const float* w, void* out_hi, void* out_lo, int Cout, i
 int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* stream);
 /* nn.GroupNorm backward (model.py:302-316, 439-471) on channels-last fp32 tensors [N, S, C]: dx (fp32), dgamma / dbeta [C]
  * (double, overwritten) from dy, the forward input x, the forward's `stats` [N,G,2] (mp_gn_stats or a convolution epilogue)
- * and gamma (NULL = 1).  workspace: N*G*2 doubles. */
+ * and gamma (NULL = 1).  workspace: N*(2*G + 2*C) doubles (group sums + the per-channel coefficient table). */
 int mp_group_norm_backward(const float* x, const float* dy, const double* stats, const float* gamma, float* dx, double* dgamma,
                            double* dbeta, double* workspace, int N, int64_t S, int C, int G, float eps, void* stream);
 /* WarpGenerator tail (model.py:965-973): 64^3 field = affine_grid(theta[N,3,4], align_corners=False) +

@@ -171,66 +171,150 @@ k_conv_wgrad(const WgradParams p) {
       }
 }
 
-// column sums of dY [P, C] -> db [C] (fp32 RED; db zeroed by the caller)
-__global__ void k_bias_grad(const float* __restrict__ dy, float* __restrict__ db, int64_t P, int C, int64_t rows_per_block) {
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, P);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) s += dy[r * C + c];
-    atomicAdd(db + c, s);
+// column sums of dY [P, C] -> db [C] (fp32 RED; db zeroed by the caller).  Block = R rows x CV channel-vectors (16-byte loads);
+// a thread owns VEC fixed channels and walks rows; the R row-lanes meet in shared memory before one RED per channel and block.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_bias_grad(const float* __restrict__ dy, float* __restrict__ db, int64_t P, int C, int Cc, int64_t rows_per_block) {
+  // grid.y walks chunks of Cc <= 1024 channels (c0 = blockIdx.y * Cc) of the C-wide rows
+  __shared__ float sh[1024];
+  const int c0 = blockIdx.y * Cc;
+  const int cw = min(Cc, C - c0);
+  const int CV = Cc / VEC, R = blockDim.x / CV;
+  const int r = threadIdx.x / CV, cv = threadIdx.x % CV;
+  for (int i = threadIdx.x; i < Cc; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  if (r < R && cv * VEC < cw) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, P);
+    float s[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) s[k] = 0.f;
+    for (int64_t row = r0 + r; row < r1; row += R) {
+      if (VEC == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(dy + row * C + c0 + cv * 4);
+        s[0] += v.x; s[1 % VEC] += v.y; s[2 % VEC] += v.z; s[3 % VEC] += v.w;
+      } else {
+        s[0] += dy[row * C + c0 + cv];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) atomicAdd(&sh[cv * VEC + k], s[k]);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) atomicAdd(db + c0 + i, sh[i]);
 }
 
 // ---- GroupNorm backward.  y = (x - mean_g) * rstd_g * gamma_c + beta_c over the group's S * C/G elements of one sample.
 //   dgamma_c = sum_{n,s} dy * xhat      dbeta_c = sum_{n,s} dy
 //   dx = rstd * (dy*gamma - mean_g(dy*gamma) - xhat * mean_g(dy*gamma*xhat))
 // pass 1: per (sample, group) the two group sums (double), per channel dgamma / dbeta (double RED); pass 2: elementwise.
+// grid (row blocks, N); block = R rows x CV channel-vectors.  A thread owns VEC fixed channels (their group statistics live in
+// registers) and walks rows with 16-byte loads; fp32 partial sums over <= 16 rows, promoted to double where the R row-lanes meet
+// in shared memory; then one double RED per channel (dgamma, dbeta) and per group (the two group sums) and block.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 k_gn_bwd_reduce(const float* __restrict__ x, const float* __restrict__ dy, const double* __restrict__ stats,
                 const float* __restrict__ gamma, double* __restrict__ gsum, double* __restrict__ dgamma,
                 double* __restrict__ dbeta, int64_t S, int C, int G, float eps, int64_t rows_per_block) {
-  // grid: x = row blocks of one sample, y = sample; a thread walks the channels c = tid, tid + 256, ...
+  extern __shared__ double shd[];          // [C][2] per-channel sums, then [G][2] group sums
   const int n = blockIdx.y;
   const int cpg = C / G;
   const double cnt = (double)S * cpg;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, S);
+  const int CV = C / VEC, R = blockDim.x / CV;
+  const int r = threadIdx.x / CV, cv = threadIdx.x % CV;
+  for (int i = threadIdx.x; i < 2 * C + 2 * G; i += blockDim.x) shd[i] = 0.0;
+  __syncthreads();
+  if (r < R) {
+    float mu[VEC], rstd[VEC], s_dy[VEC], s_dyx[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int g = (cv * VEC + k) / cpg;
+      const double mean = stats[((int64_t)n * G + g) * 2] / cnt;
+      const double var = fmax(stats[((int64_t)n * G + g) * 2 + 1] / cnt - mean * mean, 0.0);
+      rstd[k] = (float)(1.0 / sqrt(var + (double)eps));
+      mu[k] = (float)mean;
+      s_dy[k] = s_dyx[k] = 0.f;
+    }
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, S);
+#pragma unroll 4
+    for (int64_t row = r0 + r; row < r1; row += R) {
+      const int64_t o = ((int64_t)n * S + row) * C + cv * VEC;
+      if (VEC == 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + o), dv = *reinterpret_cast<const float4*>(dy + o);
+        s_dy[0] += dv.x; s_dyx[0] += dv.x * ((xv.x - mu[0]) * rstd[0]);
+        s_dy[1 % VEC] += dv.y; s_dyx[1 % VEC] += dv.y * ((xv.y - mu[1 % VEC]) * rstd[1 % VEC]);
+        s_dy[2 % VEC] += dv.z; s_dyx[2 % VEC] += dv.z * ((xv.z - mu[2 % VEC]) * rstd[2 % VEC]);
+        s_dy[3 % VEC] += dv.w; s_dyx[3 % VEC] += dv.w * ((xv.w - mu[3 % VEC]) * rstd[3 % VEC]);
+      } else {
+        const float d = dy[o];
+        s_dy[0] += d; s_dyx[0] += d * ((x[o] - mu[0]) * rstd[0]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      atomicAdd(&shd[2 * (cv * VEC + k)], (double)s_dy[k]);
+      atomicAdd(&shd[2 * (cv * VEC + k) + 1], (double)s_dyx[k]);
+    }
+  }
+  __syncthreads();
+  double* shg = shd + 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double a = shd[2 * c], b = shd[2 * c + 1], gm = gamma ? (double)gamma[c] : 1.0;
+    atomicAdd(dbeta + c, a);
+    atomicAdd(dgamma + c, b);
+    atomicAdd(&shg[2 * (c / cpg)], a * gm);
+    atomicAdd(&shg[2 * (c / cpg) + 1], b * gm);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(gsum + (int64_t)n * G * 2 + i, shg[i]);
+}
+
+// dx = rstd * (dy * gamma - m1 - xhat * m2) is affine in (dy, x) per (sample, channel): dx = a * dy + b * x + c with
+//   a = rstd * gamma,  b = -rstd^2 * m2,  c = rstd * (mu * rstd * m2 - m1).
+// The double-precision part runs once per (sample, channel) here; the elementwise pass below is three FMAs on 16-byte vectors.
+__global__ void k_gn_bwd_coef(const double* __restrict__ stats, const float* __restrict__ gamma, const double* __restrict__ gsum,
+                              float* __restrict__ coef, int64_t S, int C, int G, float eps) {
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  const double cnt = (double)S * cpg;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     const double mean = stats[((int64_t)n * G + g) * 2] / cnt;
     const double var = fmax(stats[((int64_t)n * G + g) * 2 + 1] / cnt - mean * mean, 0.0);
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
-    const float gm = gamma ? gamma[c] : 1.f;
-    double s_dy = 0.0, s_dyx = 0.0;
-    for (int64_t r = r0; r < r1; ++r) {
-      const int64_t o = ((int64_t)n * S + r) * C + c;
-      const float d = dy[o], xh = (x[o] - mu) * rstd;
-      s_dy += d;
-      s_dyx += (double)d * xh;
-    }
-    atomicAdd(dbeta + c, s_dy);
-    atomicAdd(dgamma + c, s_dyx);
-    atomicAdd(gsum + ((int64_t)n * G + g) * 2, s_dy * gm);
-    atomicAdd(gsum + ((int64_t)n * G + g) * 2 + 1, s_dyx * gm);
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const double m1 = gsum[((int64_t)n * G + g) * 2] / cnt, m2 = gsum[((int64_t)n * G + g) * 2 + 1] / cnt;
+    const double gm = gamma ? (double)gamma[c] : 1.0;
+    float* o = coef + ((int64_t)n * 3) * C + c;
+    o[0] = (float)(rstd * gm);
+    o[C] = (float)(-rstd * rstd * m2);
+    o[2 * C] = (float)(rstd * (mean * rstd * m2 - m1));
   }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256)
-k_gn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, const double* __restrict__ stats,
-               const float* __restrict__ gamma, const double* __restrict__ gsum, float* __restrict__ dx, int64_t S, int C, int G,
-               float eps, int64_t total) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % C);
-  const int64_t n = i / ((int64_t)S * C);
-  const int cpg = C / G, g = c / cpg;
-  const double cnt = (double)S * cpg;
-  const double mean = stats[(n * G + g) * 2] / cnt;
-  const double var = fmax(stats[(n * G + g) * 2 + 1] / cnt - mean * mean, 0.0);
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
-  const float m1 = (float)(gsum[(n * G + g) * 2] / cnt), m2 = (float)(gsum[(n * G + g) * 2 + 1] / cnt);
-  const float gm = gamma ? gamma[c] : 1.f;
-  const float xh = (x[i] - mu) * rstd;
-  dx[i] = rstd * (dy[i] * gm - m1 - xh * m2);
+k_gn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ coef, float* __restrict__ dx,
+               int64_t S, int C, int64_t total_vec) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_vec) return;
+  const int CV = C / VEC;
+  const int cv = (int)(t % CV);
+  const int64_t n = (t / CV) / S;
+  const float* k = coef + n * 3 * C + cv * VEC;
+  const int64_t o = t * VEC;
+  if (VEC == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(k), b = *reinterpret_cast<const float4*>(k + C),
+                 c = *reinterpret_cast<const float4*>(k + 2 * C);
+    const float4 xv = *reinterpret_cast<const float4*>(x + o), dv = *reinterpret_cast<const float4*>(dy + o);
+    float4 r;
+    r.x = fmaf(a.x, dv.x, fmaf(b.x, xv.x, c.x));
+    r.y = fmaf(a.y, dv.y, fmaf(b.y, xv.y, c.y));
+    r.z = fmaf(a.z, dv.z, fmaf(b.z, xv.z, c.z));
+    r.w = fmaf(a.w, dv.w, fmaf(b.w, xv.w, c.w));
+    *reinterpret_cast<float4*>(dx + o) = r;
+  } else {
+    dx[o] = fmaf(k[0], dy[o], fmaf(k[C], x[o], k[2 * C]));
+  }
 }
 
 }  // namespace mpb200
@@ -309,9 +393,17 @@ extern "C" int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* 
   MP_REQUIRE(dy && db && P > 0 && C > 0, "mp_bias_grad: bad arguments");
   cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)C, mp_stream(stream));
   MP_REQUIRE(e == cudaSuccess, "mp_bias_grad: memset: %s", cudaGetErrorString(e));
-  const int64_t rows = 256;
-  const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
-  mpb200::k_bias_grad<<<(unsigned)((P + rows - 1) / rows), threads, 0, mp_stream(stream)>>>(dy, db, P, C, rows);
+  const int vec = (C % 4 == 0) ? 4 : 1;
+  const int Cc = C <= 1024 ? C : 1024;                  // channels per block column (C % 4 == 0 keeps chunks 16-byte aligned)
+  const int CV = Cc / vec;
+  int R = 256 / CV;
+  if (R < 1) R = 1;
+  const int threads = R * CV;
+  const int64_t rows = (int64_t)R * 64;
+  dim3 grid((unsigned)((P + rows - 1) / rows), (unsigned)((C + Cc - 1) / Cc));
+  MP_REQUIRE(grid.y <= 65535 && (vec == 4 || C <= 256), "mp_bias_grad: unsupported channel count %d", C);
+  if (vec == 4) mpb200::k_bias_grad<4><<<grid, threads, 0, mp_stream(stream)>>>(dy, db, P, C, Cc, rows);
+  else mpb200::k_bias_grad<1><<<grid, threads, 0, mp_stream(stream)>>>(dy, db, P, C, Cc, rows);
   MP_LAUNCH_CHECK("mp_bias_grad");
   return 0;
 }
@@ -326,13 +418,29 @@ extern "C" int mp_group_norm_backward(const float* x, const float* dy, const dou
   if (e == cudaSuccess) e = cudaMemsetAsync(dgamma, 0, sizeof(double) * (size_t)C, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, sizeof(double) * (size_t)C, st);
   MP_REQUIRE(e == cudaSuccess, "mp_group_norm_backward: memset: %s", cudaGetErrorString(e));
-  const int64_t rows = 128;
-  const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
+  MP_REQUIRE(C <= 1024 && (C % 4 == 0 || C <= 256), "mp_group_norm_backward: unsupported channel count %d", C);
+  const int vec = (C % 4 == 0) ? 4 : 1, CV = C / vec;
+  int R = 256 / CV;
+  if (R < 1) R = 1;
+  const int threads = R * CV;
+  // 16 rows per thread: enough blocks (>= 8 per SM on the large tensors) to hide the latency of a streaming read
+  const int64_t rows = (int64_t)R * 16;
   dim3 grid((unsigned)((S + rows - 1) / rows), (unsigned)N);
-  mpb200::k_gn_bwd_reduce<<<grid, threads, 0, st>>>(x, dy, stats, gamma, workspace, dgamma, dbeta, S, C, G, eps, rows);
+  const size_t shb = sizeof(double) * (size_t)(2 * C + 2 * G);
+  if (vec == 4)
+    mpb200::k_gn_bwd_reduce<4><<<grid, threads, shb, st>>>(x, dy, stats, gamma, workspace, dgamma, dbeta, S, C, G, eps, rows);
+  else
+    mpb200::k_gn_bwd_reduce<1><<<grid, threads, shb, st>>>(x, dy, stats, gamma, workspace, dgamma, dbeta, S, C, G, eps, rows);
   MP_LAUNCH_CHECK("mp_group_norm_backward (reduce)");
   const int64_t total = (int64_t)N * S * C;
-  mpb200::k_gn_bwd_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, stats, gamma, workspace, dx, S, C, G, eps, total);
+  float* coef = reinterpret_cast<float*>(workspace + (size_t)N * G * 2);          // [N][3][C] floats after the group sums
+  mpb200::k_gn_bwd_coef<<<N, 256, 0, st>>>(stats, gamma, workspace, coef, S, C, G, eps);
+  MP_LAUNCH_CHECK("mp_group_norm_backward (coefficients)");
+  const int64_t total_vec = total / vec;
+  if (vec == 4)
+    mpb200::k_gn_bwd_apply<4><<<(unsigned)((total_vec + 255) / 256), 256, 0, st>>>(x, dy, coef, dx, S, C, total_vec);
+  else
+    mpb200::k_gn_bwd_apply<1><<<(unsigned)((total_vec + 255) / 256), 256, 0, st>>>(x, dy, coef, dx, S, C, total_vec);
   MP_LAUNCH_CHECK("mp_group_norm_backward (apply)");
   return 0;
 }

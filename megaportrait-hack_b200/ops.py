@@ -849,7 +849,7 @@ def group_norm_backward(x: Act, grad_out: Act, stats: torch.Tensor, G: int, gamm
     dx = _alloc(x.shape, x.device, True, False)
     dg = torch.empty((C,), dtype=torch.float64, device=x.device)
     db = torch.empty((C,), dtype=torch.float64, device=x.device)
-    ws = torch.empty((N, G, 2), dtype=torch.float64, device=x.device)
+    ws = torch.empty((N * (2 * G + 2 * C),), dtype=torch.float64, device=x.device)     # group sums + coefficient table
     L = _lib.load()
     _lib.check(L.mp_group_norm_backward(_p(x.f32), _p(grad_out.f32), _p(stats), _p(gamma), _p(dx.f32), _p(dg), _p(db), _p(ws),
                                         N, D * H * W, C, G, eps, _stream()), "mp_group_norm_backward")
