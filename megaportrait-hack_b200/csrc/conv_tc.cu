@@ -1405,7 +1405,7 @@ struct WgParams {
   float* dw;
   int Cout, Cin, T, KD, KH, KW;
   int swap;                       // 0: M = output channels (dY), N = input channels (X);  1: M = input channels, N = output channels
-  int BN, TG;                     // N tile (64 | 128); taps per CTA
+  int BN, TG;                     // N tile (multiple of 16, <= 128); taps per CTA
   int tiles_m, tiles_n, tap_groups;
   int bw, bh, bd, bn, kblk;       // position box (K block)
   int nbw, nbh, nbd;              // boxes per dimension (the sample axis takes the rest)
@@ -2201,16 +2201,27 @@ extern "C" int mp_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* 
   memset(&p, 0, sizeof(p));
   p.dw = dw; p.Cout = Cout; p.Cin = Cin; p.KD = KD; p.KH = KH; p.KW = KW; p.T = KD * KH * KW;
   // M side in 128-channel tiles, N side in 64 / 128: put the roles so that the zero padding of the tile is smallest
-  auto n_tile = [](int c) { return c > 64 ? 128 : 64; };
+  // (N tile: 128 channels, or the whole N side rounded up to the MMA's multiple of 16 when it is narrower)
+  auto n_tile = [](int c) { return c >= 128 ? 128 : (c + 15) / 16 * 16; };
   auto padded = [&](int cm, int cn) { return (int64_t)((cm + 127) / 128 * 128) * ((cn + n_tile(cn) - 1) / n_tile(cn) * n_tile(cn)); };
   p.swap = padded(Cin, Cout) < padded(Cout, Cin) ? 1 : 0;
   const int CM = p.swap ? Cin : Cout, CN = p.swap ? Cout : Cin;
   p.BN = n_tile(CN);
   p.tiles_m = (CM + 127) / 128;
   p.tiles_n = (CN + p.BN - 1) / p.BN;
-  p.TG = p.T >= 3 ? 3 : 1;
+  // One tap per CTA with 64-position K blocks and a four-wave split-K measured best (tools/wgrad_tc_bench.py: 512 -> 512 3x3 at
+  // 289 useful TFLOP/s against 201 with three taps sharing the dY tile over 32-position blocks)
+  p.TG = 1;
+  int waves = 4;
+  {   // tuning overrides (tools/wgrad_tc_bench.py): MPB200_WG_TG = taps per CTA (1..3), MPB200_WG_WAVES = split-K target in waves
+    const char* e = getenv("MPB200_WG_TG");
+    if (e && atoi(e) >= 1 && atoi(e) <= 3 && atoi(e) <= p.T) p.TG = atoi(e);
+    e = getenv("MPB200_WG_WAVES");
+    if (e && atoi(e) >= 1 && atoi(e) <= 16) waves = atoi(e);
+  }
   p.tap_groups = (p.T + p.TG - 1) / p.TG;
   p.kblk = p.TG == 1 ? 64 : 32;
+  if (p.TG == 2) p.kblk = 32;
   // position box of kblk positions: W first, then H, D, and the sample axis takes what is left
   int rem = p.kblk;
   p.bw = wg_pow2_at_least(W, rem < 8 ? rem : 8); rem /= p.bw;
@@ -2221,8 +2232,8 @@ extern "C" int mp_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* 
   const int64_t boxes = (int64_t)p.nbw * p.nbh * p.nbd * ((N + p.bn - 1) / p.bn);
   MP_REQUIRE(boxes < 0x7fffffff, "mp_conv_wgrad_tc: too many position boxes");
   p.total_boxes = (int)boxes;
-  p.s_sub = p.swap ? p.BN / 64 : 2;
-  p.x_sub = p.swap ? 2 : p.BN / 64;
+  p.s_sub = p.swap ? (p.BN + 63) / 64 : 2;
+  p.x_sub = p.swap ? 2 : (p.BN + 63) / 64;
   p.sub_bytes = (uint32_t)p.kblk * 128u;
   p.stage_bytes = 2u * p.sub_bytes * (uint32_t)(p.s_sub + p.TG * p.x_sub);
   p.STAGES = (int)((SMEM_LIMIT - 2048u) / p.stage_bytes);
@@ -2237,7 +2248,7 @@ extern "C" int mp_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* 
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // split K so that the grid is about two waves of one CTA per SM; every slice keeps at least 4 boxes
-  int64_t slices = (2 * (int64_t)sms + tiles - 1) / tiles;
+  int64_t slices = (waves * (int64_t)sms + tiles - 1) / tiles;
   if (slices > (p.total_boxes + 3) / 4) slices = (p.total_boxes + 3) / 4;
   if (slices < 1) slices = 1;
   if (slices > 65535) slices = 65535;
