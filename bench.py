@@ -579,7 +579,7 @@ def run_b200(args):
                 cfg5 = {"generator_fwd_bwd_adamw_batch1": {"ms": ms_t, "pairs_per_s": 1e3 / ms_t, "loss": float(loss),
                                                            "ms_cuda_graph": ms_graph, "cuda_graph": graph_note_t,
                                                            "libmpb200_launches": launches_train,
-                                                           "useful_tflops": 3 * 2041e9 / (ms_t * 1e-3) / 1e12},
+                                                           "useful_tflops": 3 * 2041e9 / ((ms_graph or ms_t) * 1e-3) / 1e12},
                         "what": "BASELINE config 5, generator half at batch 1 on one GPU: Gbase.train() forward + backward + AdamW "
                                 "with an L1 loss (losses / discriminator are out of scope); fp32-grade three-pass convolutions in "
                                 "all three directions (weight gradient on tcgen05), operators exchange channels-last views; `ms` = eager "
