@@ -586,6 +586,37 @@ def run_b200(args):
                                 "launches, `ms_cuda_graph` = the whole iteration replayed as one CUDA graph"}
                 del Gt, opt
 
+    # ---- BASELINE config 5 across the GPUs (row f-2): data-parallel training of the generator, one (source, driver) pair per rank,
+    # ONE NCCL all-reduce of the flat gradient buffer per iteration (engine.DataParallelTrainer); weak scaling, max over ranks
+    cfg5_dp = None
+    if world > 1 and not args.no_train_leg and not args.no_extra_configs:
+        from megaportrait_hack_b200 import engine as E
+        Gt = entry.load_seeded_gbase(dev)[0]
+        trainer = E.DataParallelTrainer(
+            Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2))
+        xs1, xd1 = xs_d[:1].contiguous(), xd_d[:1].contiguous()          # every rank owns different driver frames
+        for _ in range(2):
+            loss = trainer.step(xs1, xd1)
+        sync_all()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(3):
+            loss = trainer.step(xs1, xd1)
+        d1.record()
+        sync_all()
+        tms = torch.tensor([d0.elapsed_time(d1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        # the replicas must still hold identical weights: compare a float64 checksum of all parameters across ranks
+        chk = torch.stack([p.detach().double().sum() for p in trainer.bucket.params]).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        cfg5_dp = {"ms_per_iteration": float(tms.item()), "pairs_per_s": world * 1e3 / float(tms.item()), "scaling": "weak",
+                   "pairs_per_gpu": 1, "all_reduce_bytes": int(trainer.bucket.flat.numel() * 4), "loss_rank0": float(loss),
+                   "replica_checksum_spread": float((hi - lo).abs().item()),
+                   "what": "BASELINE config 5, generator half, data-parallel: per rank Gbase.train() forward + backward on its own "
+                           "pair, one NCCL all-reduce of the flat fp32 gradient buffer, AdamW on every rank; eager launches"}
+        del Gt, trainer
     t = torch.tensor([ms, ms_e2e, strong if strong is not None else 0.0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -743,6 +774,7 @@ def run_b200(args):
         "config1": cfg1,
         "config4": cfg4,
         "config5": cfg5,
+        "config5_data_parallel": cfg5_dp,
         "stages_eager_step": stages,
         "cpu_baseline": cpu,
         "useful_tflops_whole_step": (B * FLOPS_PER_DRIVER + FLOPS_SOURCE) * world / (step_ms * 1e-3) / 1e12,

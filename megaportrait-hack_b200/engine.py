@@ -174,3 +174,71 @@ class GraphedGbase:
             if sink is not None:
                 sink(i, out)
         return out
+
+
+# ----------------------------------------------------------------------------------------------------- training (row f-2)
+class GradBucket:
+    """All gradients of a module as views into ONE flat fp32 buffer, so data-parallel training needs a single NCCL all-reduce per
+    iteration and no gather / scatter copies (BASELINE config 5: `train_base` on 8 GPUs, data-parallel; the reference itself is
+    single-process, train.py:129-356).
+
+    `attach()` points every `param.grad` at its slice of the buffer (autograd accumulates into an existing `.grad` in place, so the
+    backward pass fills the buffer); `zero()` clears it with one memset; `all_reduce_mean()` averages it over the process group.
+    Use `optimizer.zero_grad(set_to_none=False)` or just `bucket.zero()`: setting grads to None would detach the views."""
+
+    def __init__(self, module: torch.nn.Module, group=None):
+        import torch.distributed as dist
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise RuntimeError("GradBucket: the module has no trainable parameters")
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        # 16-byte aligned slices: vectorised optimizer kernels and NCCL's 16-byte chunks stay aligned
+        self.offsets, total = [], 0
+        for n in sizes:
+            self.offsets.append(total)
+            total += (n + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.attach()
+
+    def attach(self) -> None:
+        for p, off in zip(self.params, self.offsets):
+            if p.dtype != torch.float32 or p.device != self.flat.device:
+                raise RuntimeError("GradBucket: fp32 parameters on one device expected")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce_mean(self) -> None:
+        """ONE collective for all gradients (sum over ranks, then 1 / world).  No-op in a single process."""
+        if self.dist is None or self.world == 1:
+            return
+        self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.flat.mul_(1.0 / self.world)
+
+
+class DataParallelTrainer:
+    """One process per GPU: every rank runs `Gbase.train()` forward + backward on its own (source, driver) pairs, the gradients
+    meet in ONE all-reduce (`GradBucket`), every rank applies the same optimizer step (weights stay bit-identical across ranks as
+    long as they start equal).  BatchNorm statistics stay per-rank, as `DistributedDataParallel` does by default.
+    `loss_fn(pred, pyramids, xs, xd) -> scalar` stands in for the reference's out-of-scope losses."""
+
+    def __init__(self, gbase, optimizer_factory, loss_fn=None, group=None):
+        self.G = gbase.train()
+        self.bucket = GradBucket(gbase, group)
+        self.opt = optimizer_factory(self.bucket.params)
+        self.loss_fn = loss_fn or (lambda pred, pyr, xs, xd: (pred - xd).abs().mean())
+
+    def step(self, xs: torch.Tensor, xd: torch.Tensor) -> torch.Tensor:
+        self.bucket.zero()
+        with torch.enable_grad():
+            pred, pyr = self.G(xs, xd)
+            loss = self.loss_fn(pred, pyr, xs, xd)
+            loss.backward()
+        self.bucket.all_reduce_mean()
+        self.opt.step()
+        return loss.detach()

@@ -1,0 +1,50 @@
+"""Host logic of the data-parallel training step (engine.GradBucket / DataParallelTrainer wiring): world_size 2 over gloo on CPU
+with a stand-in module (the collective and the bucket views are device-agnostic; the CUDA path is tests/test_gpu_train.py)."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from megaportrait_hack_b200 import engine
+    torch.manual_seed(0)                                   # same initial weights on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    bucket = engine.GradBucket(net)
+    opt = torch.optim.SGD(bucket.params, lr=0.1)
+    g = torch.Generator().manual_seed(100 + rank)          # different data per rank
+    x = torch.randn(4, 6, generator=g)
+    for _ in range(2):
+        bucket.zero()
+        net(x).pow(2).mean().backward()
+        local = bucket.flat.clone()
+        bucket.all_reduce_mean()
+        opt.step()
+    for p, off in zip(bucket.params, bucket.offsets):      # grads are still views of the flat buffer after the steps
+        assert p.grad.data_ptr() == bucket.flat[off:].data_ptr()
+    torch.save((rank, local, bucket.flat.clone(), [p.detach().clone() for p in net.parameters()]),
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_all_reduce_world2(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2)]
+    (_, l0, f0, w0), (_, l1, f1, w1) = res
+    assert not torch.equal(l0, l1)                                   # ranks saw different data
+    assert torch.allclose(f0, (l0 + l1) / 2, atol=1e-7) and torch.equal(f0, f1)      # one averaged gradient everywhere
+    for a, b in zip(w0, w1):
+        assert torch.equal(a, b)                                     # weights stay identical across ranks
