@@ -3,7 +3,9 @@
 Same class names, constructor arguments, `forward()` signatures, attribute names and `state_dict()` keys as the
 reference (model.py:54-1180), so `train.py` / `inference.py` / `PairwiseTransferLoss` call them unchanged; the
 arithmetic runs in the sm_100a kernels of libmpb200 (include/mpb200.h).  There is NO CPU path and NO ATen fallback
-for the hot-path operators: CPU tensors, train-mode BatchNorm and autograd raise.
+for the hot-path operators: CPU tensors raise.  Under `torch.no_grad()` in eval mode the modules run the fused inference
+kernels; in `.train()` mode or with autograd recording they run the differentiable libmpb200 path (`_forward_autograd`,
+SURVEY.md row f-2: every convolution in all three directions, GroupNorm, train-mode BatchNorm and both warps on the GPU kernels).
 
 Two calling levels:
   * module level -- every class takes / returns the reference's NCHW / NCDHW fp32 tensors;
@@ -852,6 +854,11 @@ def _affine_3x4(rotation, translation, invert: bool) -> torch.Tensor:
 
 def compute_rt_warp(rotation, translation, invert=False, grid_size=64):
     """model.py:777-809 -> (B, 3, G, G, G)."""
+    if torch.is_grad_enabled() and (rotation.requires_grad or translation.requires_grad):
+        # differentiable form (row f-2): the 3-channel rigid grid through ATen's autograd, as inside the warp generators
+        theta = _affine_3x4(rotation, translation, invert)
+        grid = F.affine_grid(theta, (rotation.shape[0], 1, grid_size, grid_size, grid_size), align_corners=False)
+        return grid.permute(0, 4, 1, 2, 3).contiguous()
     _require_inference(nn.Identity(), rotation, translation)
     theta = _affine_3x4(rotation, translation, invert)
     em0 = torch.zeros((rotation.shape[0], 1, 1, 1, 3), device=rotation.device, dtype=torch.float32)
