@@ -575,11 +575,43 @@ def run_b200(args):
                 except Exception as e:  # noqa: BLE001  (the eager number above stands on its own)
                     graph_note_t = f"capture failed: {type(e).__name__}: {str(e)[:200]}"
                     torch.cuda.synchronize()
+                # the same iteration at batch 4 (4 different (source, driver) pairs): the launches carry 4x the work, so the
+                # iteration is no longer bound by launch latency / the host
+                ms_b4 = None
+                try:
+                    nb = 4
+                    xs4 = torch.cat([xs_d[:1], xd_d[4:7]], 0).contiguous()       # four distinct source frames
+                    xd4 = xd_d[:nb].contiguous()
+                    opt = torch.optim.AdamW(Gt.parameters(), lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2)
+
+                    def train_iter4():
+                        with torch.enable_grad():
+                            opt.zero_grad(set_to_none=True)
+                            pred, _ = Gt(xs4, xd4)
+                            l4 = (pred - xd4).abs().mean()
+                            l4.backward()
+                        opt.step()
+                        return l4.detach()
+                    train_iter4()
+                    torch.cuda.synchronize()
+                    t0.record()
+                    for _ in range(2):
+                        train_iter4()
+                    t1.record()
+                    torch.cuda.synchronize()
+                    ms_b4 = t0.elapsed_time(t1) / 2
+                except Exception as e:  # noqa: BLE001
+                    graph_note_t = (graph_note_t or "") + f"; batch-4 leg failed: {type(e).__name__}: {str(e)[:160]}"
+                    torch.cuda.synchronize()
                 # 2041 GF forward per pair; backward = data + weight gradient of every convolution ~ 2x the forward
                 cfg5 = {"generator_fwd_bwd_adamw_batch1": {"ms": ms_t, "pairs_per_s": 1e3 / ms_t, "loss": float(loss),
                                                            "ms_cuda_graph": ms_graph, "cuda_graph": graph_note_t,
                                                            "libmpb200_launches": launches_train,
-                                                           "useful_tflops": 3 * 2041e9 / ((ms_graph or ms_t) * 1e-3) / 1e12},
+                                                           "useful_tflops": 3 * 2041e9 / ((ms_graph or ms_t) * 1e-3) / 1e12,
+                                                           "batch4_ms": ms_b4,
+                                                           "batch4_pairs_per_s": None if not ms_b4 else 4e3 / ms_b4,
+                                                           "batch4_useful_tflops": None if not ms_b4 else
+                                                           4 * 3 * 2041e9 / (ms_b4 * 1e-3) / 1e12},
                         "what": "BASELINE config 5, generator half at batch 1 on one GPU: Gbase.train() forward + backward + AdamW "
                                 "with an L1 loss (losses / discriminator are out of scope); fp32-grade three-pass convolutions in "
                                 "all three directions (weight gradient on tcgen05), operators exchange channels-last views; `ms` = eager "

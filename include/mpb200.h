@@ -259,6 +259,10 @@ int mp_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, cons
  * dgrad = 0: the forward operand (rows = Cout, K = tap * Cin + ci); dgrad = 1: the operand of the data gradient (rows = Cin,
  * K = tap * Cout + co, taps reversed).  Rows >= the real row count are zero.  Bit-identical to ops.pack_conv on fp32 weights. */
 int mp_pack_conv_weights(const float* w, void* out_hi, void* out_lo, int Cout, int Cin, int T, int rows_pad, int dgrad, void* stream);
+/* Backward of mp_upsample2x_linear_cl (nn.Upsample(x2, bilinear / trilinear, align_corners=True), model.py:585-589, 733-743,
+ * back-propagated by train.py:318): grad_out [N, D*up_d, 2H, 2W, C] -> grad_in [N, D, H, W, C], channels-last fp32; the adjoint
+ * evaluated as a gather with the forward's own index rule (deterministic, no atomics). */
+int mp_upsample2x_linear_backward_cl(const float* grad_out, float* grad_in, int N, int D, int H, int W, int C, int up_d, void* stream);
 /* dL/dbias = column sums of dy [P, C] -> db [C] (overwritten). */
 int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* stream);
 /* nn.GroupNorm backward (model.py:302-316, 439-471) on channels-last fp32 tensors [N, S, C]: dx (fp32), dgamma / dbeta [C]

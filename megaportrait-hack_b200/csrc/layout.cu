@@ -418,6 +418,70 @@ extern "C" int mp_upsample2x_linear_cl(const float* in_f32, const void* in_hi, c
   return 0;
 }
 
+// ---- backward of the x2 linear upsample (row f-2): the adjoint as a GATHER, so the result is deterministic.  Input voxel i of an
+// axis is read by the outputs o with i0(o) == i (weight 1 - l) or i1(o) == i (weight l) under the forward's own `lin_src`; for a
+// x2 resize that is at most 5 outputs per axis.  One thread = one input position x 4 channels.
+__device__ __forceinline__ int lin_bwd_taps(int i, int in_size, int out_size, int (&oo)[8], float (&ww)[8]) {
+  int lo = 0, hi = out_size - 1;
+  if (in_size > 1 && out_size > 1 && in_size != out_size) {
+    const float inv = (float)(out_size - 1) / (float)(in_size - 1);
+    lo = max((int)floorf((float)(i - 1) * inv) - 1, 0);
+    hi = min((int)ceilf((float)(i + 1) * inv) + 1, out_size - 1);
+  } else if (in_size == out_size) {
+    lo = hi = i;
+  }
+  int n = 0;
+  for (int o = lo; o <= hi && n < 8; ++o) {
+    int i0, i1;
+    float l;
+    lin_src(o, in_size, out_size, i0, i1, l);
+    const float w = (i0 == i ? 1.f - l : 0.f) + (i1 == i ? l : 0.f);
+    if (w != 0.f) { oo[n] = o; ww[n] = w; ++n; }
+  }
+  return n;
+}
+
+__global__ void k_upsample2x_linear_bwd_cl(const float* __restrict__ gout, float* __restrict__ gin, int N, int D, int H, int W,
+                                           int C, int ud) {
+  const int C4 = C >> 2;
+  const int Do = D * ud, Ho = H * 2, Wo = W * 2;
+  const int64_t total = (int64_t)N * D * H * W * C4;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c4 = (int)(t % C4);
+  int64_t p = t / C4;
+  const int w = (int)(p % W); p /= W;
+  const int h = (int)(p % H); p /= H;
+  const int d = (int)(p % D);
+  const int n = (int)(p / D);
+  int od[8], oh[8], ow[8];
+  float wd[8], wh[8], ww[8];
+  const int nd = lin_bwd_taps(d, D, Do, od, wd), nh = lin_bwd_taps(h, H, Ho, oh, wh), nw = lin_bwd_taps(w, W, Wo, ow, ww);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int a = 0; a < nd; ++a)
+    for (int b = 0; b < nh; ++b) {
+      const float wab = wd[a] * wh[b];
+      const int64_t row = (((int64_t)n * Do + od[a]) * Ho + oh[b]) * Wo;
+      for (int c = 0; c < nw; ++c) {
+        const float4 g = *reinterpret_cast<const float4*>(gout + (row + ow[c]) * C + c4 * 4);
+        const float wgt = wab * ww[c];
+        acc.x += wgt * g.x; acc.y += wgt * g.y; acc.z += wgt * g.z; acc.w += wgt * g.w;
+      }
+    }
+  *reinterpret_cast<float4*>(gin + t * 4) = acc;
+}
+
+extern "C" int mp_upsample2x_linear_backward_cl(const float* grad_out, float* grad_in, int N, int D, int H, int W, int C, int up_d,
+                                                void* stream) {
+  MP_REQUIRE(grad_out && grad_in, "mp_upsample2x_linear_backward_cl: null pointer");
+  MP_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && (up_d == 1 || up_d == 2),
+             "mp_upsample2x_linear_backward_cl: bad dims");
+  const int64_t total = (int64_t)N * D * H * W * (C / 4);
+  k_upsample2x_linear_bwd_cl<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(grad_out, grad_in, N, D, H, W, C, up_d);
+  MP_LAUNCH_CHECK("mp_upsample2x_linear_backward_cl");
+  return 0;
+}
+
 // nn.Upsample(x2, bilinear, align_corners=True) from split-bf16 planes to the F16_Q8 plane pair (G2d up-blocks)
 extern "C" int mp_upsample2x_bilinear_hq(const void* in_hi, const void* in_lo, void* out_h16, void* out_q8, int N, int H, int W,
                                          int C, float q8_scale, void* stream) {

@@ -155,6 +155,7 @@ _SIGNATURES = {
                                              c_int, c_int, _P]),
     "mp_gs_brick_tune": (c_int, [POINTER(c_int), c_int]),
     "mp_conv_wgrad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_upsample2x_linear_backward_cl": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_pack_conv_weights": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_conv_wgrad_tc_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "mp_conv_wgrad_tc": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -362,12 +362,12 @@ class FlowField(nn.Module, _Packed):
         return out.f32
 
     def _forward_autograd(self, zs):
-        """Differentiable form (row f-2): zs [B,512,1,1] -> (B,3,16,16,16); nearest upsamples through ATen's autograd."""
+        """Differentiable form (row f-2): zs [B,512,1,1] -> (B,3,16,16,16)."""
         x = ops.conv_train(zs, self.conv1x1.weight, self.conv1x1.bias)
         x = x.view(-1, 512, 4, *x.shape[2:])
         for blk, sf in ((self.resblock1, (2, 2, 2)), (self.resblock2, (2, 2, 2)), (self.resblock3, (1, 2, 2)),
                         (self.resblock4, (1, 2, 2))):
-            x = F.interpolate(blk._forward_autograd(x), scale_factor=sf, mode="nearest")
+            x = ops.UpsampleNearestFunction.apply(blk._forward_autograd(x), sf[0])
         x = ops.conv_train(x, self.conv3x3x3.weight, self.conv3x3x3.bias)
         x = ops.GroupNormFunction.apply(x, 1, self.gn.weight, self.gn.bias, self.gn.eps)
         return torch.tanh(torch.relu(x))
@@ -476,12 +476,12 @@ class G3d(nn.Module):
         return out
 
     def _forward_autograd(self, x):
-        """Differentiable form (row f-2): residual blocks and the final convolution through the libmpb200 Functions; the 2x
-        average pools and trilinear upsamples between them (1 % of the FLOPs) through ATen's autograd."""
+        """Differentiable form (row f-2): residual blocks, the final convolution, the 2x average pools and the trilinear upsamples
+        between them through the libmpb200 Functions of ops.py (CUDA forward and backward)."""
         for i, m in enumerate(self.downsampling):
-            x = m._forward_autograd(x) if i % 2 == 0 else F.avg_pool3d(x, 2, 2)
+            x = m._forward_autograd(x) if i % 2 == 0 else ops.AvgPool2Function.apply(x, 2)
         for i, m in enumerate(self.upsampling):
-            x = m._forward_autograd(x) if i % 2 == 0 else F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+            x = m._forward_autograd(x) if i % 2 == 0 else ops.UpsampleLinear2xFunction.apply(x)
         return ops.ConvFunction.apply(x, self.final_conv.weight, self.final_conv.bias)
 
     def forward(self, x):
@@ -724,7 +724,7 @@ class G2d(nn.Module, _Packed):
     def _forward_autograd(self, x):
         """Differentiable / train-mode form (row f-2).  `reshape` and `conv1x1` have no non-linearity between them (model.py:756-757):
         their product is formed as a torch expression on the two weights (autograd carries the gradient to both) and ONE 96 -> 512
-        convolution runs; the bilinear x2 upsamples go through ATen's autograd."""
+        convolution runs; the bilinear x2 upsamples are `ops.UpsampleLinear2xFunction` (CUDA forward and backward)."""
         conv = ops.conv_train
         w2 = self.conv1x1.weight.view(512, 1536)
         w = (w2 @ self.reshape.weight.view(1536, 96)).view(512, 96, 1, 1)
@@ -732,7 +732,7 @@ class G2d(nn.Module, _Packed):
         for blk in self.res_blocks:
             x = blk._forward_autograd(x)
         for up in (self.upsample1, self.upsample2, self.upsample3):
-            x = up[1]._forward_autograd(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True))
+            x = up[1]._forward_autograd(ops.UpsampleLinear2xFunction.apply(x))
         gn = self.final_conv[0]
         x = torch.relu(ops.GroupNormFunction.apply(x, gn.num_groups, gn.weight, gn.bias, gn.eps))
         return torch.sigmoid(conv(x, self.final_conv[2].weight, self.final_conv[2].bias))
@@ -801,11 +801,11 @@ class Eapp(nn.Module, _Packed):
         return self.fc(torch.flatten(es, start_dim=1))
 
     def _forward_autograd(self, x):
-        """Differentiable / train-mode form (row f-2) -> (vs, es); 2x2 average pools through ATen's autograd."""
+        """Differentiable / train-mode form (row f-2) -> (vs, es)."""
         conv, gn = ops.conv_train, ops.GroupNormFunction.apply
         out = conv(x, self.conv.weight, self.conv.bias)
         for blk in (self.resblock_128, self.resblock_256, self.resblock_512):
-            out = F.avg_pool2d(blk._forward_autograd(out), 2, 2)
+            out = ops.AvgPool2Function.apply(blk._forward_autograd(out), 1)
         out = conv(torch.relu(gn(out, 32, None, None, 1e-5)), self.conv_1.weight, self.conv_1.bias)
         vs = out.view(out.size(0), 96, 16, *out.shape[2:])
         for blk in (self.resblock3D_96, self.resblock3D_96_2, self.resblock3D_96_1, self.resblock3D_96_1_2,

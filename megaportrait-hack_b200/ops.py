@@ -976,6 +976,62 @@ class ConvS2Function(torch.autograd.Function):
         return gx, gw, gb
 
 
+def upsample2x_linear_backward(grad_out: Act, up_d: int) -> Act:
+    """Adjoint of `upsample2x_linear` on channels-last fp32 Acts (row f-2)."""
+    N, Do, Ho, Wo, C = grad_out.shape
+    out = _alloc((N, Do // up_d, Ho // 2, Wo // 2, C), grad_out.device, True, False)
+    L = _lib.load()
+    _lib.check(L.mp_upsample2x_linear_backward_cl(_p(grad_out.f32), _p(out.f32), N, Do // up_d, Ho // 2, Wo // 2, C, up_d,
+                                                  _stream()), "mp_upsample2x_linear_backward_cl")
+    _count()
+    return out
+
+
+class AvgPool2Function(torch.autograd.Function):
+    """`F.avg_pool2d(x, 2)` (pool_d = 1) / `F.avg_pool3d(x, 2)` (pool_d = 2) on libmpb200 (row f-2): forward `mp_avgpool2_cl`,
+    backward = the nearest upsample of the scaled gradient (`mp_upsample_nearest_cl`)."""
+
+    @staticmethod
+    def forward(ctx, x, pool_d):
+        ctx.pool_d, ctx.nd = pool_d, x.dim()
+        return _cl_view(avgpool2(_to_cl_act(x), pool_d, f32=True, split=False), x.dim())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = _to_cl_act(grad_out * (1.0 / (4 * ctx.pool_d)))
+        return _cl_view(upsample_nearest(g, (ctx.pool_d, 2, 2), f32=True, split=False), ctx.nd), None
+
+
+class UpsampleNearestFunction(torch.autograd.Function):
+    """`F.interpolate(x, scale_factor=(sd, 2, 2), mode="nearest")`, sd in {1, 2} (FlowField, model.py:427-433) on libmpb200:
+    forward `mp_upsample_nearest_cl`, backward = the 2 x 2 (x sd) sum pool (`mp_avgpool2_cl` times the window size)."""
+
+    @staticmethod
+    def forward(ctx, x, sd):
+        ctx.sd, ctx.nd = sd, x.dim()
+        return _cl_view(upsample_nearest(_to_cl_act(x), (sd, 2, 2), f32=True, split=False), x.dim())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = avgpool2(_to_cl_act(grad_out), ctx.sd, f32=True, split=False)
+        return _cl_view(g, ctx.nd) * float(4 * ctx.sd), None
+
+
+class UpsampleLinear2xFunction(torch.autograd.Function):
+    """`nn.Upsample(scale_factor=2, mode="bilinear" | "trilinear", align_corners=True)` (G2d / G3d, model.py:585-589, 733-743) on
+    libmpb200: forward `mp_upsample2x_linear_cl`, backward `mp_upsample2x_linear_backward_cl` (deterministic gather)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.nd = x.dim()
+        ctx.up_d = 2 if x.dim() == 5 else 1
+        return _cl_view(upsample2x_linear(_to_cl_act(x), ctx.up_d, f32=True, split=False), x.dim())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return _cl_view(upsample2x_linear_backward(_to_cl_act(grad_out), ctx.up_d), ctx.nd)
+
+
 def _pad_channels(t: torch.Tensor, dim: int, mult: int) -> torch.Tensor:
     c = t.shape[dim]
     extra = (-c) % mult

@@ -367,7 +367,20 @@ def apply_warping_field_backward(grad_out, v, wf, need_v=True, need_wf=True):
     return (vv.grad if need_v else None), (ww.grad if need_wf else None)
 
 
-_NAMES = ["conv_weight_grad", "bias_grad", "group_norm_backward", "apply_warping_field_backward", "from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
+def upsample2x_linear_backward(grad_out, up_d):
+    g = _to_ncdhw(grad_out.f32)
+    N, C, Do, Ho, Wo = g.shape
+    with torch.enable_grad():
+        x = torch.zeros((N, C, Do // up_d, Ho // 2, Wo // 2), requires_grad=True)
+        if up_d == 2:
+            y = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+        else:
+            y = F.interpolate(x.squeeze(2), scale_factor=2, mode="bilinear", align_corners=True).unsqueeze(2)
+        y.backward(g)
+    return _mk(_to_cl(x.grad), True, False)
+
+
+_NAMES = ["upsample2x_linear_backward", "conv_weight_grad", "bias_grad", "group_norm_backward", "apply_warping_field_backward", "from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
           "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "from_nchw_pad16",
           "im2col3x3_f16", "stem3x3_relu_maxpool_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]

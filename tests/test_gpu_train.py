@@ -117,3 +117,36 @@ def test_pack_conv_weights_kernel_matches_host_packing():
             assert torch.equal(got.w_hi, ref.w_hi) and torch.equal(got.w_lo, ref.w_lo), (shape, dgrad)
             assert (got.bias is None) == (ref.bias is None) and (got.bias is None or torch.equal(got.bias, ref.bias))
             assert got.w_lo.data_ptr() == got.w_hi.data_ptr() + got.w_hi.numel() * 2      # one allocation: merged TMA load
+
+
+def test_pool_and_resize_functions_vs_aten_autograd():
+    """Row f-2: the pools / resizes between the blocks on libmpb200 -- `AvgPool2Function` (2-D and 3-D), `UpsampleNearestFunction`
+    ((2,2,2) and (1,2,2)), `UpsampleLinear2xFunction` (bilinear and trilinear, align_corners=True; backward = the deterministic
+    gather kernel) -- forward and input gradient against ATen on the same device: <= 1e-6 of abs-max."""
+    from megaportrait_hack_b200 import lib, ops
+    lib.build()
+    g = torch.Generator().manual_seed(9)
+    cases = [
+        ("avg2d", (2, 64, 24, 40), lambda x: ops.AvgPool2Function.apply(x, 1), lambda x: F.avg_pool2d(x, 2, 2)),
+        ("avg3d", (1, 96, 8, 16, 12), lambda x: ops.AvgPool2Function.apply(x, 2), lambda x: F.avg_pool3d(x, 2, 2)),
+        ("near222", (2, 32, 4, 2, 2), lambda x: ops.UpsampleNearestFunction.apply(x, 2),
+         lambda x: F.interpolate(x, scale_factor=(2, 2, 2), mode="nearest")),
+        ("near122", (2, 32, 16, 4, 4), lambda x: ops.UpsampleNearestFunction.apply(x, 1),
+         lambda x: F.interpolate(x, scale_factor=(1, 2, 2), mode="nearest")),
+        ("bilinear", (2, 64, 17, 24), lambda x: ops.UpsampleLinear2xFunction.apply(x),
+         lambda x: F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)),
+        ("bilinear_1px", (1, 16, 1, 5), lambda x: ops.UpsampleLinear2xFunction.apply(x),
+         lambda x: F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)),
+        ("trilinear", (1, 96, 4, 16, 16), lambda x: ops.UpsampleLinear2xFunction.apply(x),
+         lambda x: F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)),
+    ]
+    for name, shape, ours, ref in cases:
+        x = torch.randn(shape, generator=g).cuda()
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya, yb = ours(xa), ref(xb)
+        assert ya.shape == yb.shape, name
+        go = torch.randn(yb.shape, generator=g).cuda()
+        ya.backward(go)
+        yb.backward(go)
+        assert rel(ya.detach(), yb.detach()) < 1e-6, (name, rel(ya.detach(), yb.detach()))
+        assert rel(xa.grad, xb.grad) < 1e-6, (name, rel(xa.grad, xb.grad))
