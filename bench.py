@@ -625,9 +625,10 @@ def run_b200(args):
         from megaportrait_hack_b200 import engine as E
         Gt = entry.load_seeded_gbase(dev)[0]
         trainer = E.DataParallelTrainer(
-            Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2))
+            Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True),
+            graph=not args.no_graphs, warmup=2)       # the iteration incl. the NCCL all-reduce is replayed as one CUDA graph
         xs1, xd1 = xs_d[:1].contiguous(), xd_d[:1].contiguous()          # every rank owns different driver frames
-        for _ in range(2):
+        for _ in range(4):                                               # 2 eager + capture + 1 replay
             loss = trainer.step(xs1, xd1)
         sync_all()
         d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
