@@ -648,7 +648,8 @@ def run_b200(args):
                    "pairs_per_gpu": 1, "all_reduce_bytes": int(trainer.bucket.flat.numel() * 4), "loss_rank0": float(loss),
                    "replica_checksum_spread": float((hi - lo).abs().item()),
                    "what": "BASELINE config 5, generator half, data-parallel: per rank Gbase.train() forward + backward on its own "
-                           "pair, one NCCL all-reduce of the flat fp32 gradient buffer, AdamW on every rank; eager launches"}
+                           "pair, one NCCL all-reduce of the flat fp32 gradient buffer, AdamW on every rank; the whole iteration incl. the "
+                           "collective replayed as one CUDA graph (--no-graphs: eager launches)"}
         del Gt, trainer
     t = torch.tensor([ms, ms_e2e, strong if strong is not None else 0.0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
