@@ -285,10 +285,11 @@ class ResBlock3D_Adaptive(nn.Module, _Packed):
             P["rc"] = ops.pack_conv(self.residual_conv.weight, self.residual_conv.bias, dev)
         return P
 
-    def _forward_cl(self, x: Act, f32: bool = True, split: bool = True) -> Act:
+    def _forward_cl(self, x: Act, f32: bool = True, split: bool = True, _module_call: bool = False) -> Act:
         """x: split (+ f32 when the residual is the identity and full precision is wanted)."""
-        if self.upsample:
-            raise NotImplementedError("ResBlock3D_Adaptive(upsample=True) is never used by the reference hot path")
+        if self.upsample and not _module_call:
+            raise NotImplementedError("ResBlock3D_Adaptive(upsample=True) inside a fused pipeline: the reference has no such call "
+                                      "site (the stand-alone module forward() supports it)")
         P = self._plan()
         G = self.norm1.num_groups
         h, st = ops.conv(x, P["c1"], f32=True, stats_groups=G)
@@ -297,10 +298,14 @@ class ResBlock3D_Adaptive(nn.Module, _Packed):
         res = x if P["rc"] is None else ops.conv(x, P["rc"], f32=True)[0]
         return ops.group_norm_act(h, G, st, *P["n2"], res=res, act=ACT_RELU, f32=f32, split=split)
 
+    def _tail(self, y):
+        """`upsample=True` (model.py:405-406; no call site in the reference): the trailing trilinear resize, through ATen."""
+        if self.upsample:
+            y = F.interpolate(y, scale_factor=self.scale_factors, mode="trilinear", align_corners=False)
+        return y
+
     def _forward_autograd(self, x):
         """Differentiable form (row f-2)."""
-        if self.upsample:
-            raise NotImplementedError("ResBlock3D_Adaptive(upsample=True) is never used by the reference hot path")
         conv = ops.ConvFunction.apply
         h = torch.relu(self.norm1._forward_autograd(conv(x, self.conv1.weight, self.conv1.bias)))
         h = self.norm2._forward_autograd(conv(h, self.conv2.weight, self.conv2.bias))
@@ -310,10 +315,10 @@ class ResBlock3D_Adaptive(nn.Module, _Packed):
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())
-            return _public(self._forward_autograd(x.float()))
+            return self._tail(_public(self._forward_autograd(x.float())))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
-        return ops.to_nchw(self._forward_cl(a, f32=True, split=False), 5)
+        return self._tail(ops.to_nchw(self._forward_cl(a, f32=True, split=False, _module_call=True), 5))
 
 
 class FlowField(nn.Module, _Packed):
@@ -409,9 +414,10 @@ class ResBlock3D(nn.Module, _Packed):
             P["sc"] = ops.pack_conv(self.shortcut.weight, self.shortcut.bias, dev)
         return P
 
-    def _forward_cl(self, x: Act, f32: bool = True, split: bool = False) -> Act:
-        if self.upsample:
-            raise NotImplementedError("ResBlock3D(upsample=True) is never used by the reference hot path")
+    def _forward_cl(self, x: Act, f32: bool = True, split: bool = False, _module_call: bool = False) -> Act:
+        if self.upsample and not _module_call:
+            raise NotImplementedError("ResBlock3D(upsample=True) inside a fused pipeline: the reference has no such call site "
+                                      "(the stand-alone module forward() supports it)")
         P = self._plan()
         idt = x if P["sc"] is None else ops.conv(x, P["sc"], f32=True)[0]
         h, st = ops.conv(x, P["c1"], f32=True, stats_groups=32)
@@ -422,21 +428,25 @@ class ResBlock3D(nn.Module, _Packed):
     def _forward_autograd(self, x):
         """Differentiable form (row f-2): the same operators as autograd Functions whose forward AND backward run on libmpb200
         (ops.ConvFunction: tcgen05 forward / data gradient, tensor-core weight gradient; ops.GroupNormFunction)."""
-        if self.upsample:
-            raise NotImplementedError("ResBlock3D(upsample=True) is never used by the reference hot path")
         conv, gn = ops.ConvFunction.apply, ops.GroupNormFunction.apply
         idt = conv(x, self.shortcut.weight, self.shortcut.bias) if isinstance(self.shortcut, nn.Conv3d) else x
         h = torch.relu(gn(conv(x, self.conv1.weight, self.conv1.bias), 32, self.gn1.weight, self.gn1.bias, self.gn1.eps))
         h = gn(conv(h, self.conv2.weight, self.conv2.bias), 32, self.gn2.weight, self.gn2.bias, self.gn2.eps)
         return torch.relu(h + idt)
 
+    def _tail(self, y):
+        """`upsample=True` (model.py:525-526; no call site in the reference): the trailing trilinear resize, through ATen."""
+        if self.upsample:
+            y = F.interpolate(y, scale_factor=self.scale_factors, mode="trilinear", align_corners=False)
+        return y
+
     def forward(self, x):
         if _wants_grad(self, x):
             _require_inference(self, x.detach())         # (device check only)
-            return _public(self._forward_autograd(x.float()))
+            return self._tail(_public(self._forward_autograd(x.float())))
         _require_inference(self, x)
         a = ops.from_nchw(_as_f32_cuda(x), f32=True, split=True)
-        return ops.to_nchw(self._forward_cl(a, f32=True, split=False), 5)
+        return self._tail(ops.to_nchw(self._forward_cl(a, f32=True, split=False, _module_call=True), 5))
 
 
 class G3d(nn.Module):
@@ -522,7 +532,8 @@ class ResBlock2D(nn.Module, _Packed):
             raise NotImplementedError("ResBlock2D: train-mode BatchNorm (batch statistics) is not implemented "
                                       "(SURVEY.md 8f-2); call .eval()")
         if self.downsample:
-            raise NotImplementedError("ResBlock2D(downsample=True) is never used by the reference hot path")
+            raise NotImplementedError("ResBlock2D(downsample=True): no call site in the reference, and its own forward fails there "
+                                      "(model.py:632-637 adds a stride-2 identity to a full-resolution tensor)")
         sc = None
         if isinstance(self.shortcut, nn.Sequential):
             # Conv2d(1x1) + BatchNorm shortcut: folded, then fused into conv2's accumulator as extra K columns, so the
@@ -576,7 +587,8 @@ class ResBlock2D(nn.Module, _Packed):
         """Differentiable / train-mode form (row f-2): convolutions and BatchNorm (batch statistics in train mode, running
         statistics updated like ATen does) through the libmpb200 Functions of ops.py."""
         if self.downsample:
-            raise NotImplementedError("ResBlock2D(downsample=True) is never used by the reference hot path")
+            raise NotImplementedError("ResBlock2D(downsample=True): no call site in the reference, and its own forward fails there "
+                                      "(model.py:632-637 adds a stride-2 identity to a full-resolution tensor)")
         conv, bn = ops.conv_train, ops.batch_norm_train
         out = torch.relu(bn(conv(x, self.conv1.weight, self.conv1.bias), self.bn1))
         out = bn(conv(out, self.conv2.weight, self.conv2.bias), self.bn2)

@@ -103,6 +103,23 @@ def test_resblock3d_forward(gb):
     assert got.shape == (1, 192, 4, 16, 16) and rel(got, ref) <= TOL
 
 
+def test_resblock3d_upsample_branch(gb):
+    """`upsample=True` of ResBlock3D / ResBlock3D_Adaptive (model.py:405-406, 525-526; no call site in the reference, VERDICT
+    round 1 "missing" #8): the block followed by F.interpolate(scale_factors, trilinear, align_corners=False)."""
+    import gbase_oracle as O
+    from megaportrait_hack_b200 import model
+    G, sd = gb
+    x = rnd(1, 96, 4, 16, 16, seed=21)
+    for cls, src, prefix, fn in ((model.ResBlock3D, G.G3d.downsampling[0], "G3d.downsampling.0", O.resblock3d),
+                                 (model.ResBlock3D_Adaptive, G.appearanceEncoder.resblock3D_96, "appearanceEncoder.resblock3D_96",
+                                  O.resblock3d_adaptive)):
+        blk = cls(96, 96, upsample=True, scale_factors=(1, 2, 2)).cuda().eval()
+        blk.load_state_dict(src.state_dict())
+        got = run(blk, x)
+        ref = F.interpolate(fn(x, sd, prefix), scale_factor=(1, 2, 2), mode="trilinear", align_corners=False)
+        assert got.shape == (1, 96, 4, 32, 32) and rel(got, ref) <= TOL
+
+
 def test_resblock2d_forward(gb):
     """ResBlock2D.forward (model.py:621-640): an identity block of G2d's chain (called on its own it takes split-bf16
     planes, not the chain's F16_Q8 planes) and an up-block with the Conv1x1 + BatchNorm shortcut."""
