@@ -76,18 +76,6 @@ def _public(y):
     return tuple(_public(v) for v in y)
 
 
-def _require_no_grad(mod: nn.Module, *tensors) -> None:
-    """Entry points that run under `torch.no_grad()` internally: called with autograd recording on and anything that
-    asks for a gradient (an input, or any parameter of `mod`), they would hand back detached outputs and the caller's
-    `.backward()` would silently train nothing (train.py:194, PairwiseTransferLoss model.py:2192-2214).  Raise instead."""
-    if not torch.is_grad_enabled():
-        return
-    if any(torch.is_tensor(t) and t.requires_grad for t in tensors) or any(p.requires_grad for p in mod.parameters()):
-        raise NotImplementedError(
-            f"{type(mod).__name__}: this B200 path is inference-only (backward = SURVEY.md 8f-2). Call it under "
-            "torch.no_grad() / torch.inference_mode(), or freeze the module with .requires_grad_(False)")
-
-
 def _sig(mod: nn.Module):
     """Change-detector for cached packed weights: per-tensor (data_ptr, version) of every parameter and buffer, the
     device and the train flag.  In-place writes through `param.data` / `.data.copy_()` do NOT bump `_version`: after
