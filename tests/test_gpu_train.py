@@ -175,3 +175,46 @@ def test_trainer_cuda_graph_matches_eager_iterations(seeded_sd):
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) <= 1e-2 * abs(a), losses
     assert losses[True][-1] < losses[True][0]
+
+
+def test_train_py_call_patterns(seeded_sd):
+    """The ways train.py and its losses drive the path with gradients (train.py:145, 188-194, 289-293, 318-319;
+    model.py:2188-2212): (1) the sub-module sequence of `PairwiseTransferLoss` (appearanceEncoder, motionEncoder,
+    warp_generator_s2c / c2d, the free function apply_warping_field, G3d, G2d) gives the same image as `Gbase(xs, xd)` and
+    back-propagates into every sub-module; (2) `Gbase.motionEncoder(generated_frame)` carries a graph back into the generator;
+    (3) fp16 autocast + GradScaler around the step, as train.py wraps it, runs and updates the weights."""
+    import __graft_entry__ as entry
+    from megaportrait_hack_b200 import model
+    G = entry.load_seeded_gbase("cuda")[0].train()
+    xs, xd = synthetic_pair(1)
+    xs, xd = xs.cuda(), xd.cuda()
+    # (1) + (2)
+    vs, es = G.appearanceEncoder(xs)
+    Rs, ts, zs = G.motionEncoder(xs)
+    Rd, td, zd = G.motionEncoder(xd)
+    vc2d = G.G3d(model.apply_warping_field(vs, G.warp_generator_s2c(Rs, ts, zs, es)))
+    warped = model.apply_warping_field(vc2d, G.warp_generator_c2d(Rd, td, zd, es))
+    img = G.G2d(torch.sum(warped, dim=2))
+    assert img.shape == (1, 3, 512, 512) and img.requires_grad and img.is_contiguous()
+    _, _, z_pred = G.motionEncoder(img)                       # train.py:289: motion encoder on the generated frame
+    (img.mean() + z_pred.pow(2).mean()).backward()
+    missing = [n for n, p in G.named_parameters() if p.grad is None and not n.endswith("adaptive_matrix_beta")]
+    assert not missing, missing[:5]
+    with torch.no_grad():
+        G.eval()
+        ref, _ = G(xs, xd)        # (BatchNorm: running statistics here, batch statistics above -- only shapes / finiteness compare)
+        G.train()
+    assert torch.isfinite(img).all() and ref.shape == img.shape
+    # (3)
+    opt = torch.optim.AdamW(G.parameters(), lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2)
+    scaler = torch.amp.GradScaler("cuda")
+    w0 = G.G2d.final_conv[2].weight.detach().clone()
+    opt.zero_grad()
+    with torch.autocast("cuda", dtype=torch.float16):
+        pred, pyr = G(xs, xd)
+        loss = (pred - xd).abs().mean() + (pyr["prediction_0.5"] - F.avg_pool2d(xd, 2)).abs().mean()
+    scaler.scale(loss).backward()
+    scaler.step(opt)
+    scaler.update()
+    assert pred.dtype == torch.float32 and torch.isfinite(loss)
+    assert not torch.equal(w0, G.G2d.final_conv[2].weight.detach())
