@@ -582,23 +582,21 @@ def run_b200(args):
                     nb = 4
                     xs4 = torch.cat([xs_d[:1], xd_d[4:7]], 0).contiguous()       # four distinct source frames
                     xd4 = xd_d[:nb].contiguous()
-                    opt = torch.optim.AdamW(Gt.parameters(), lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2)
-
-                    def train_iter4():
-                        with torch.enable_grad():
-                            opt.zero_grad(set_to_none=True)
-                            pred, _ = Gt(xs4, xd4)
-                            l4 = (pred - xd4).abs().mean()
-                            l4.backward()
-                        opt.step()
-                        return l4.detach()
-                    train_iter4()
+                    # through engine.DataParallelTrainer (one process: no collective), the iteration replayed as one CUDA graph
+                    # so that the number does not depend on the box's host speed
+                    from megaportrait_hack_b200 import engine as E
+                    tr4 = E.DataParallelTrainer(
+                        Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True),
+                        graph=not args.no_graphs, warmup=1)
+                    for _ in range(3):                      # eager, capture, first replay
+                        tr4.step(xs4, xd4)
                     torch.cuda.synchronize()
                     t0.record()
                     for _ in range(2):
-                        train_iter4()
+                        tr4.step(xs4, xd4)
                     t1.record()
                     torch.cuda.synchronize()
+                    del tr4
                     ms_b4 = t0.elapsed_time(t1) / 2
                 except Exception as e:  # noqa: BLE001
                     graph_note_t = (graph_note_t or "") + f"; batch-4 leg failed: {type(e).__name__}: {str(e)[:160]}"

@@ -209,22 +209,21 @@ def resnet_block_autograd(blk: nn.Module, x: torch.Tensor) -> torch.Tensor:
     """torchvision `BasicBlock` / `Bottleneck` (v1.5: stride on conv2) forward on the differentiable libmpb200 operators
     (ops.conv_train: tcgen05 forward / data gradient + tensor-core weight gradient; ops.batch_norm_train: batch statistics)."""
     from . import ops
-    conv, bn = ops.conv_train, ops.batch_norm_train
+    cb = ops.conv_bn_train                # (train mode: the batch statistics come out of the convolution's epilogue)
     idt = x
     if blk.downsample is not None:
-        dc, dbn = blk.downsample[0], blk.downsample[1]
-        idt = bn(conv(x, dc.weight, dc.bias, stride=dc.stride[0]), dbn)
-    out = torch.relu(bn(conv(x, blk.conv1.weight, blk.conv1.bias, stride=blk.conv1.stride[0]), blk.bn1))
-    out = bn(conv(out, blk.conv2.weight, blk.conv2.bias, stride=blk.conv2.stride[0]), blk.bn2)
+        idt = cb(x, blk.downsample[0], blk.downsample[1])
+    out = torch.relu(cb(x, blk.conv1, blk.bn1))
+    out = cb(out, blk.conv2, blk.bn2)
     if hasattr(blk, "conv3"):
-        out = bn(conv(torch.relu(out), blk.conv3.weight, blk.conv3.bias), blk.bn3)
+        out = cb(torch.relu(out), blk.conv3, blk.bn3)
     return torch.relu(out + idt)
 
 
 def resnet_trunk_autograd(conv1, bn1, maxpool, layers, x: torch.Tensor) -> torch.Tensor:
     """Stem conv + BatchNorm + ReLU, the max-pool (ATen autograd), residual stages -- the differentiable form of `ResNetTrunkPlan`."""
     from . import ops
-    x = torch.relu(ops.batch_norm_train(ops.conv_train(x, conv1.weight, conv1.bias, stride=conv1.stride[0]), bn1))
+    x = torch.relu(ops.conv_bn_train(x, conv1, bn1))
     x = F.max_pool2d(x, maxpool.kernel_size, maxpool.stride, maxpool.padding)
     for layer in layers:
         for blk in layer:

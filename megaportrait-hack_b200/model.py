@@ -129,10 +129,11 @@ def _as_f32_cuda(x: torch.Tensor) -> torch.Tensor:
 class Conv2d_WS(nn.Conv2d):
     """model.py:54-69: weight-standardised conv."""
 
-    def _forward_autograd(self, x):
+    def _forward_autograd(self, x, stats_groups: int = 0):
         """Differentiable form (row f-2): the standardisation is a float64 torch expression on the weight (autograd carries its
-        Jacobian), the convolution and its three gradients run on libmpb200 (ops.ConvFunction)."""
-        return ops.ConvFunction.apply(x, ops.standardize_weight(self.weight).float(), self.bias)
+        Jacobian), the convolution and its three gradients run on libmpb200 (ops.ConvFunction).  `stats_groups`: also return
+        the GroupNorm statistics of the output from the convolution's epilogue -> (y, stats)."""
+        return ops.conv_train(x, ops.standardize_weight(self.weight).float(), self.bias, stats_groups=stats_groups)
 
     def forward(self, x):
         if _wants_grad(self, x):
@@ -200,7 +201,8 @@ class ResBlock_Custom(nn.Module, _Packed):
         conv, gn = ops.ConvFunction.apply, ops.GroupNormFunction.apply
         out2 = conv(x, self.conv_res.weight, self.conv_res.bias)
         h = torch.relu(gn(x, 32, None, None, 1e-5))
-        h = torch.relu(gn(self.conv_ws._forward_autograd(h), 32, None, None, 1e-5))
+        t, st = self.conv_ws._forward_autograd(h, stats_groups=32)       # GroupNorm statistics from the convolution's epilogue
+        h = torch.relu(gn(t, 32, None, None, 1e-5, st))
         return conv(h, self.conv.weight, self.conv.bias) + out2
 
     def forward(self, x):
@@ -232,10 +234,10 @@ class AdaptiveGroupNorm(nn.Module):
         return (_f32c(self.group_norm.weight), _f32c(self.group_norm.bias), _f32c(self.weight).view(-1),
                 _f32c(self.bias).view(-1))
 
-    def _forward_autograd(self, x):
+    def _forward_autograd(self, x, stats=None):
         """Differentiable form (row f-2): GroupNorm forward / backward on libmpb200, the second affine as a torch expression."""
         gn = self.group_norm
-        return ops.GroupNormFunction.apply(x, self.num_groups, gn.weight, gn.bias, gn.eps) * self.weight + self.bias
+        return ops.GroupNormFunction.apply(x, self.num_groups, gn.weight, gn.bias, gn.eps, stats) * self.weight + self.bias
 
     def forward(self, x):
         if _wants_grad(self, x):
@@ -294,9 +296,11 @@ class ResBlock3D_Adaptive(nn.Module, _Packed):
 
     def _forward_autograd(self, x):
         """Differentiable form (row f-2)."""
-        conv = ops.ConvFunction.apply
-        h = torch.relu(self.norm1._forward_autograd(conv(x, self.conv1.weight, self.conv1.bias)))
-        h = self.norm2._forward_autograd(conv(h, self.conv2.weight, self.conv2.bias))
+        conv = ops.conv_train
+        t, st = conv(x, self.conv1.weight, self.conv1.bias, stats_groups=self.norm1.num_groups)
+        h = torch.relu(self.norm1._forward_autograd(t, st))
+        t, st = conv(h, self.conv2.weight, self.conv2.bias, stats_groups=self.norm2.num_groups)
+        h = self.norm2._forward_autograd(t, st)
         res = conv(x, self.residual_conv.weight, self.residual_conv.bias) if isinstance(self.residual_conv, nn.Conv3d) else x
         return torch.relu(h + res)
 
@@ -416,10 +420,12 @@ class ResBlock3D(nn.Module, _Packed):
     def _forward_autograd(self, x):
         """Differentiable form (row f-2): the same operators as autograd Functions whose forward AND backward run on libmpb200
         (ops.ConvFunction: tcgen05 forward / data gradient, tensor-core weight gradient; ops.GroupNormFunction)."""
-        conv, gn = ops.ConvFunction.apply, ops.GroupNormFunction.apply
+        conv, gn = ops.conv_train, ops.GroupNormFunction.apply
         idt = conv(x, self.shortcut.weight, self.shortcut.bias) if isinstance(self.shortcut, nn.Conv3d) else x
-        h = torch.relu(gn(conv(x, self.conv1.weight, self.conv1.bias), 32, self.gn1.weight, self.gn1.bias, self.gn1.eps))
-        h = gn(conv(h, self.conv2.weight, self.conv2.bias), 32, self.gn2.weight, self.gn2.bias, self.gn2.eps)
+        t, st = conv(x, self.conv1.weight, self.conv1.bias, stats_groups=32)      # statistics from the convolution's epilogue
+        h = torch.relu(gn(t, 32, self.gn1.weight, self.gn1.bias, self.gn1.eps, st))
+        t, st = conv(h, self.conv2.weight, self.conv2.bias, stats_groups=32)
+        h = gn(t, 32, self.gn2.weight, self.gn2.bias, self.gn2.eps, st)
         return torch.relu(h + idt)
 
     def _tail(self, y):
@@ -577,11 +583,11 @@ class ResBlock2D(nn.Module, _Packed):
         if self.downsample:
             raise NotImplementedError("ResBlock2D(downsample=True): no call site in the reference, and its own forward fails there "
                                       "(model.py:632-637 adds a stride-2 identity to a full-resolution tensor)")
-        conv, bn = ops.conv_train, ops.batch_norm_train
-        out = torch.relu(bn(conv(x, self.conv1.weight, self.conv1.bias), self.bn1))
-        out = bn(conv(out, self.conv2.weight, self.conv2.bias), self.bn2)
+        cb = ops.conv_bn_train            # (train mode: the batch statistics come out of the convolution's epilogue)
+        out = torch.relu(cb(x, self.conv1, self.bn1))
+        out = cb(out, self.conv2, self.bn2)
         if isinstance(self.shortcut, nn.Sequential):
-            x = bn(conv(x, self.shortcut[0].weight, self.shortcut[0].bias), self.shortcut[1])
+            x = cb(x, self.shortcut[0], self.shortcut[1])
         return torch.relu(out + x)
 
     def forward(self, x):

@@ -919,13 +919,38 @@ class ConvFunction(torch.autograd.Function):
         return gx, gw, gb
 
 
+class ConvStatsFunction(torch.autograd.Function):
+    """`ConvFunction` whose forward also returns the per-(sample, group) sum / sum of squares of its output, accumulated by the
+    convolution's epilogue (`mp_conv_desc.stats`) -- the normalisation that follows (`GroupNormFunction` / `BatchNormFunction` with
+    `stats=`) then needs no statistics pass over the tensor.  `groups` = GroupNorm groups, or the channel count for BatchNorm."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups, stride):
+        nd = x.dim()
+        ctx.nd, ctx.stride = nd, stride
+        a = _to_cl_act(x)
+        ensure_split(a)
+        ctx.k = tuple(weight.shape[2:]) if nd == 5 else (1,) + tuple(weight.shape[2:])
+        ctx.save_for_backward(x.detach(), weight.detach())
+        ctx.has_bias = bias is not None
+        out, stats = conv(a, pack_conv_train(weight, bias), f32=True, stats_groups=groups, stride=stride)
+        ctx.mark_non_differentiable(stats)
+        return _cl_view(out, nd), stats
+
+    @staticmethod
+    def backward(ctx, grad_out, _gstats):
+        fn = ConvS2Function if ctx.stride == 2 else ConvFunction
+        return fn.backward(ctx, grad_out) + (None, None)
+
+
 class GroupNormFunction(torch.autograd.Function):
     """`F.group_norm` on libmpb200 with CUDA backward (row f-2); NCHW / NCDHW fp32 in and out."""
 
     @staticmethod
-    def forward(ctx, x, G, gamma, beta, eps):
+    def forward(ctx, x, G, gamma, beta, eps, stats=None):
         a = _to_cl_act(x)
-        stats = gn_stats(a, G)
+        if stats is None:
+            stats = gn_stats(a, G)
         ab = gn_finalize(stats, a.shape, G, None if gamma is None else gamma.detach().float().contiguous(),
                          None if beta is None else beta.detach().float().contiguous(), eps=eps)
         ctx.save_for_backward(x.detach(), stats, None if gamma is None else gamma.detach().float().contiguous())
@@ -937,7 +962,7 @@ class GroupNormFunction(torch.autograd.Function):
         x, stats, gamma = ctx.saved_tensors
         dx, dg, db = group_norm_backward(_to_cl_act(x), _to_cl_act(grad_out), stats, ctx.G, gamma, ctx.eps)
         return (_cl_view(dx, ctx.nd), None, dg if ctx.needs_input_grad[2] else None,
-                db if ctx.needs_input_grad[3] else None, None)
+                db if ctx.needs_input_grad[3] else None, None, None)
 
 
 class ConvS2Function(torch.autograd.Function):
@@ -1042,7 +1067,8 @@ def _pad_channels(t: torch.Tensor, dim: int, mult: int) -> torch.Tensor:
     return torch.cat((t, t.new_zeros(shape)), dim)
 
 
-def conv_train(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1) -> torch.Tensor:
+def conv_train(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, stride: int = 1,
+               stats_groups: int = 0):
     """Differentiable `F.conv2d / F.conv3d(x, weight, bias, stride, padding=k // 2)` on libmpb200 (row f-2) for every convolution of
     the path: channel counts that are not multiples of 16 (RGB stems, the 3-channel heads) are zero-padded around the Function by
     torch expressions (autograd slices the gradients back), 1x1 stride-2 shortcuts sub-sample their input first, other stride-2
@@ -1060,8 +1086,26 @@ def conv_train(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     x = _pad_channels(x, 1, 16)
     w = _pad_channels(_pad_channels(weight.float(), 1, 16), 0, 16)
     b = None if bias is None else _pad_channels(bias.float(), 0, 16)
+    if stats_groups:
+        # statistics of the output from the convolution's epilogue: -> (y, stats [N, groups, 2] float64).  Only when the groups
+        # survive the channel padding (no padding, or one group per channel: padded channels are exactly zero)
+        if w.shape[0] == cout or stats_groups == cout:
+            y, stats = ConvStatsFunction.apply(x, w, b, stats_groups if w.shape[0] == cout else w.shape[0], stride)
+            return (y, stats) if cout == y.shape[1] else (y[:, :cout], stats[:, :cout])
+        y = (ConvS2Function if stride == 2 else ConvFunction).apply(x, w, b)
+        return y[:, :cout], None
     y = (ConvS2Function if stride == 2 else ConvFunction).apply(x, w, b)
     return y if cout == y.shape[1] else y[:, :cout]
+
+
+def conv_bn_train(x: torch.Tensor, conv_mod, bn, stride: Optional[int] = None) -> torch.Tensor:
+    """`bn(conv(x))` of the differentiable path: in train mode the BatchNorm's batch statistics come out of the convolution's
+    epilogue (one group per channel, summed over the samples), so the normalisation costs one read + one write of the tensor."""
+    st = conv_mod.stride[0] if stride is None else stride
+    if bn.training and not (st == 2 and all(k == 1 for k in conv_mod.weight.shape[2:])):
+        y, stats = conv_train(x, conv_mod.weight, conv_mod.bias, stride=st, stats_groups=conv_mod.weight.shape[0])
+        return batch_norm_train(y, bn, None if stats is None else stats.sum(dim=0, keepdim=True))
+    return batch_norm_train(conv_train(x, conv_mod.weight, conv_mod.bias, stride=st), bn)
 
 
 class BatchNormFunction(torch.autograd.Function):
@@ -1072,11 +1116,12 @@ class BatchNormFunction(torch.autograd.Function):
     into the running statistics."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps):
+    def forward(ctx, x, gamma, beta, eps, stats=None):
         a = _to_cl_act(x)
         N, D, H, W, C = a.shape
         a1 = Act((1, 1, N * D * H, W, C), f32=a.f32.view(1, 1, N * D * H, W, C))
-        stats = gn_stats(a1, C)
+        if stats is None:
+            stats = gn_stats(a1, C)
         g = None if gamma is None else gamma.detach().float().contiguous()
         ab = gn_finalize(stats, a1.shape, C, g, None if beta is None else beta.detach().float().contiguous(), eps=eps)
         ctx.save_for_backward(x.detach(), stats, g)
@@ -1096,15 +1141,15 @@ class BatchNormFunction(torch.autograd.Function):
         one = (1, 1, N * D * H, W, C)
         dx, dg, db = group_norm_backward(Act(one, f32=a.f32.view(one)), Act(one, f32=g.f32.view(one)), stats, C, gamma, ctx.eps)
         return (_cl_view(Act(a.shape, f32=dx.f32.view(a.shape)), ctx.nd), dg if ctx.needs_input_grad[1] else None,
-                db if ctx.needs_input_grad[2] else None, None)
+                db if ctx.needs_input_grad[2] else None, None, None)
 
 
-def batch_norm_train(x: torch.Tensor, bn) -> torch.Tensor:
+def batch_norm_train(x: torch.Tensor, bn, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`nn.BatchNorm2d.forward` for the differentiable path (row f-2).  Train mode: batch statistics through `BatchNormFunction`
     and the running statistics updated like ATen does (momentum, unbiased variance, `num_batches_tracked`); eval mode: the
     running-statistics affine map as a torch expression (elementwise)."""
     if bn.training or bn.running_mean is None:
-        y, mean, var = BatchNormFunction.apply(x.float(), bn.weight, bn.bias, bn.eps)
+        y, mean, var = BatchNormFunction.apply(x.float(), bn.weight, bn.bias, bn.eps, stats)
         if bn.training and bn.track_running_stats and bn.running_mean is not None:
             with torch.no_grad():
                 n = x.numel() // x.shape[1]
