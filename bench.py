@@ -624,7 +624,8 @@ def run_b200(args):
         Gt = entry.load_seeded_gbase(dev)[0]
         trainer = E.DataParallelTrainer(
             Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True),
-            graph=not args.no_graphs, warmup=2)       # the iteration incl. the NCCL all-reduce is replayed as one CUDA graph
+            graph=not args.no_graphs, warmup=2,       # the iteration incl. the NCCL all-reduce is replayed as one CUDA graph
+            n_buckets=args.train_buckets)             # > 1: bucket all-reduces overlap the rest of the backward pass
         xs1, xd1 = xs_d[:1].contiguous(), xd_d[:1].contiguous()          # every rank owns different driver frames
         for _ in range(4):                                               # 2 eager + capture + 1 replay
             loss = trainer.step(xs1, xd1)
@@ -644,6 +645,7 @@ def run_b200(args):
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         cfg5_dp = {"ms_per_iteration": float(tms.item()), "pairs_per_s": world * 1e3 / float(tms.item()), "scaling": "weak",
                    "pairs_per_gpu": 1, "all_reduce_bytes": int(trainer.bucket.flat.numel() * 4), "loss_rank0": float(loss),
+                   "all_reduce_buckets": len(trainer.bucket.ranges),
                    "replica_checksum_spread": float((hi - lo).abs().item()),
                    "what": "BASELINE config 5, generator half, data-parallel: per rank Gbase.train() forward + backward on its own "
                            "pair, one NCCL all-reduce of the flat fp32 gradient buffer, AdamW on every rank; the whole iteration incl. the "
@@ -825,6 +827,8 @@ def main():
     ap.add_argument("--drivers-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config 2(A) / config 1 legs")
+    ap.add_argument("--train-buckets", type=int, default=4,
+                    help="gradient all-reduce buckets of the data-parallel training leg (1 = one collective after the backward pass)")
     ap.add_argument("--no-train-leg", action="store_true", help="skip the config 5 leg (Gbase forward + backward + AdamW)")
     ap.add_argument("--strong-drivers", type=int, default=256, help="global driver frames of the strong-scaling leg (0 = off)")
     ap.add_argument("--strong-steps", type=int, default=3)

@@ -178,15 +178,20 @@ class GraphedGbase:
 
 # ----------------------------------------------------------------------------------------------------- training (row f-2)
 class GradBucket:
-    """All gradients of a module as views into ONE flat fp32 buffer, so data-parallel training needs a single NCCL all-reduce per
-    iteration and no gather / scatter copies (BASELINE config 5: `train_base` on 8 GPUs, data-parallel; the reference itself is
-    single-process, train.py:129-356).
+    """All gradients of a module as views into ONE flat fp32 buffer, so data-parallel training needs no gather / scatter copies
+    (BASELINE config 5: `train_base` on 8 GPUs, data-parallel; the reference itself is single-process, train.py:129-356).
 
     `attach()` points every `param.grad` at its slice of the buffer (autograd accumulates into an existing `.grad` in place, so the
     backward pass fills the buffer); `zero()` clears it with one memset; `all_reduce_mean()` averages it over the process group.
-    Use `optimizer.zero_grad(set_to_none=False)` or just `bucket.zero()`: setting grads to None would detach the views."""
+    Use `optimizer.zero_grad(set_to_none=False)` or just `bucket.zero()`: setting grads to None would detach the views.
 
-    def __init__(self, module: torch.nn.Module, group=None):
+    `n_buckets` > 1 overlaps the collective with the backward pass: the buffer is cut into contiguous ranges of about equal size
+    (parameters in registration order, which the backward pass walks roughly in reverse), and the moment the last gradient of a
+    range has been accumulated (`register_post_accumulate_grad_hook`) its all-reduce is enqueued on a communication stream that
+    runs beside the rest of the backward pass; `all_reduce_mean()` then only reduces what is left, joins the stream and scales.
+    Under CUDA-graph capture the communication stream becomes a parallel branch of the graph."""
+
+    def __init__(self, module: torch.nn.Module, group=None, n_buckets: int = 1):
         import torch.distributed as dist
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
@@ -202,6 +207,24 @@ class GradBucket:
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = group
         self.world = self.dist.get_world_size(group) if self.dist else 1
+        # contiguous ranges of ~equal size: (lo, hi, number of parameters inside)
+        n_buckets = max(1, min(int(n_buckets), len(self.params)))
+        self.ranges, self._bucket_of = [], {}
+        target, lo, count = total / n_buckets, 0, 0
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            end = self.offsets[i + 1] if i + 1 < len(self.params) else total
+            self._bucket_of[id(p)] = len(self.ranges)
+            count += 1
+            if (end >= target * (len(self.ranges) + 1) and len(self.ranges) < n_buckets - 1) or i + 1 == len(self.params):
+                self.ranges.append((lo, end, count))
+                lo, count = end, 0
+        self._pending = [c for _, _, c in self.ranges]
+        self._launched = [False] * len(self.ranges)
+        self._comm = torch.cuda.Stream(dev) if (dev.type == "cuda" and len(self.ranges) > 1) else None
+        self._hooks = []
+        if len(self.ranges) > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self.attach()
 
     def attach(self) -> None:
@@ -212,12 +235,38 @@ class GradBucket:
 
     def zero(self) -> None:
         self.flat.zero_()
+        self._pending = [c for _, _, c in self.ranges]
+        self._launched = [False] * len(self.ranges)
 
-    def all_reduce_mean(self) -> None:
-        """ONE collective for all gradients (sum over ranks, then 1 / world).  No-op in a single process."""
+    def _on_grad(self, p) -> None:
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._launch(b)
+
+    def _launch(self, b: int) -> None:
+        if self._launched[b]:
+            return
+        self._launched[b] = True
         if self.dist is None or self.world == 1:
             return
-        self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
+        lo, hi, _ = self.ranges[b]
+        if self._comm is None:
+            self.dist.all_reduce(self.flat[lo:hi], op=self.dist.ReduceOp.SUM, group=self.group)
+            return
+        self._comm.wait_stream(torch.cuda.current_stream(self.flat.device))      # the range's gradients are complete here
+        with torch.cuda.stream(self._comm):
+            self.dist.all_reduce(self.flat[lo:hi], op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def all_reduce_mean(self) -> None:
+        """Sum over ranks, then 1 / world: ONE collective (n_buckets = 1), or whatever the backward pass has not already sent
+        (ranges holding a parameter that received no gradient, e.g. the unused `adaptive_matrix_beta`).  No-op in one process."""
+        if self.dist is None or self.world == 1:
+            return
+        for b in range(len(self.ranges)):
+            self._launch(b)
+        if self._comm is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._comm)
         self.flat.mul_(1.0 / self.world)
 
 
@@ -232,9 +281,10 @@ class DataParallelTrainer:
     ~7 000 launches: 160-250 ms eager vs 77 ms replayed on one B200).  The optimizer must be capturable
     (`torch.optim.AdamW(..., capturable=True)`), `loss_fn` must not synchronise, inputs are copied into static buffers."""
 
-    def __init__(self, gbase, optimizer_factory, loss_fn=None, group=None, graph: bool = False, warmup: int = 2):
+    def __init__(self, gbase, optimizer_factory, loss_fn=None, group=None, graph: bool = False, warmup: int = 2,
+                 n_buckets: int = 1):
         self.G = gbase.train()
-        self.bucket = GradBucket(gbase, group)
+        self.bucket = GradBucket(gbase, group, n_buckets)        # n_buckets > 1: all-reduce overlapped with the backward pass
         self.opt = optimizer_factory(self.bucket.params)
         self.loss_fn = loss_fn or (lambda pred, pyr, xs, xd: (pred - xd).abs().mean())
         self.graph, self.warmup = bool(graph), int(warmup)

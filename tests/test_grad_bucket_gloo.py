@@ -11,21 +11,29 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, n_buckets):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from megaportrait_hack_b200 import engine
     torch.manual_seed(0)                                   # same initial weights on every rank
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
-    bucket = engine.GradBucket(net)
+    bucket = engine.GradBucket(net, n_buckets=n_buckets)
+    assert len(bucket.ranges) == n_buckets and bucket.ranges[0][0] == 0 and bucket.ranges[-1][1] == bucket.flat.numel()
+    assert sum(c for _, _, c in bucket.ranges) == len(bucket.params)
     opt = torch.optim.SGD(bucket.params, lr=0.1)
     g = torch.Generator().manual_seed(100 + rank)          # different data per rank
     x = torch.randn(4, 6, generator=g)
     for _ in range(2):
         bucket.zero()
+        # this rank's own gradient, computed without touching .grad (with n_buckets > 1 the hooks reduce during backward)
+        own = torch.autograd.grad(net(x).pow(2).mean(), bucket.params)
+        local = torch.zeros_like(bucket.flat)
+        for gp, p, off in zip(own, bucket.params, bucket.offsets):
+            local[off:off + p.numel()] = gp.reshape(-1)
         net(x).pow(2).mean().backward()
-        local = bucket.flat.clone()
+        if n_buckets > 1:                                  # every range was sent by its last gradient's hook
+            assert all(bucket._launched)
         bucket.all_reduce_mean()
         opt.step()
     for p, off in zip(bucket.params, bucket.offsets):      # grads are still views of the flat buffer after the steps
@@ -36,12 +44,16 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_grad_bucket_all_reduce_world2(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("n_buckets", [1, 3])
+def test_grad_bucket_all_reduce_world2(tmp_path, n_buckets):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), n_buckets), nprocs=2, join=True)
     res = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2)]
     (_, l0, f0, w0), (_, l1, f1, w1) = res
     assert not torch.equal(l0, l1)                                   # ranks saw different data
