@@ -546,7 +546,7 @@ def run_b200(args):
                 # at batch 1 the eager iteration is bound by the host enqueueing ~7 000 launches
                 ms_graph, graph_note_t = None, None
                 try:
-                    opt = torch.optim.AdamW(Gt.parameters(), lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True)
+                    opt = torch.optim.AdamW(Gt.parameters(), lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True, fused=True)
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(side):
@@ -586,7 +586,7 @@ def run_b200(args):
                     # so that the number does not depend on the box's host speed
                     from megaportrait_hack_b200 import engine as E
                     tr4 = E.DataParallelTrainer(
-                        Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True),
+                        Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True, fused=True),
                         graph=not args.no_graphs, warmup=1)
                     for _ in range(3):                      # eager, capture, first replay
                         tr4.step(xs4, xd4)
@@ -613,7 +613,8 @@ def run_b200(args):
                         "what": "BASELINE config 5, generator half at batch 1 on one GPU: Gbase.train() forward + backward + AdamW "
                                 "with an L1 loss (losses / discriminator are out of scope); fp32-grade three-pass convolutions in "
                                 "all three directions (weight gradient on tcgen05), operators exchange channels-last views; `ms` = eager "
-                                "launches, `ms_cuda_graph` = the whole iteration replayed as one CUDA graph"}
+                                "launches with the reference's default AdamW, `ms_cuda_graph` / `batch4_ms` = the whole iteration "
+                                "replayed as one CUDA graph with AdamW(capturable, fused)"}
                 del Gt, opt
 
     # ---- BASELINE config 5 across the GPUs (row f-2): data-parallel training of the generator, one (source, driver) pair per rank,
@@ -623,7 +624,7 @@ def run_b200(args):
         from megaportrait_hack_b200 import engine as E
         Gt = entry.load_seeded_gbase(dev)[0]
         trainer = E.DataParallelTrainer(
-            Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True),
+            Gt, lambda ps: torch.optim.AdamW(ps, lr=1e-5, betas=(0.5, 0.999), weight_decay=1e-2, capturable=True, fused=True),
             graph=not args.no_graphs, warmup=2,       # the iteration incl. the NCCL all-reduce is replayed as one CUDA graph
             n_buckets=args.train_buckets)             # > 1: bucket all-reduces overlap the rest of the backward pass
         xs1, xd1 = xs_d[:1].contiguous(), xd_d[:1].contiguous()          # every rank owns different driver frames

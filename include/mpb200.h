@@ -263,6 +263,11 @@ int mp_pack_conv_weights(const float* w, void* out_hi, void* out_lo, int Cout, i
  * back-propagated by train.py:318): grad_out [N, D*up_d, 2H, 2W, C] -> grad_in [N, D, H, W, C], channels-last fp32; the adjoint
  * evaluated as a gather with the forward's own index rule (deterministic, no atomics). */
 int mp_upsample2x_linear_backward_cl(const float* grad_out, float* grad_in, int N, int D, int H, int W, int C, int up_d, void* stream);
+/* Patches of an RGB frame for the weight gradient of a stem convolution (Eapp 7x7, model.py:211; the 3x3 / 7x7 stems of the
+ * ResNets, resnet.py:192, torchvision): x NCHW fp32 [N, C <= 4, H, W] -> split-bf16 rows [N, H/stride, W/stride, Kpad], element
+ * (kh*KW + kw)*C + c.  dW is then one mp_conv_wgrad_tc call with a 1x1 filter over Kpad "input channels". */
+int mp_im2col_rgb_split(const float* x, void* out_hi, void* out_lo, int N, int C, int H, int W, int KH, int KW, int stride, int Kpad,
+                        void* stream);
 /* dL/dbias = column sums of dy [P, C] -> db [C] (overwritten). */
 int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* stream);
 /* nn.GroupNorm backward (model.py:302-316, 439-471) on channels-last fp32 tensors [N, S, C]: dx (fp32), dgamma / dbeta [C]

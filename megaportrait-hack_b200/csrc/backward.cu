@@ -344,6 +344,58 @@ __global__ void k_pack_conv_weights(const float* __restrict__ w, bf16* __restric
 }
 }  // namespace mpb200
 
+namespace mpb200 {
+// RGB patches for the weight gradient of a stem convolution (row f-2): x NCHW fp32 [N, C <= 4, H, W] -> split-bf16 rows
+// [N, Ho, Wo, Kpad], element (kh * KW + kw) * C + c = x[n, c, ho * stride + kh - KH/2, wo * stride + kw - KW/2] (zero outside the
+// image and for the padding up to Kpad).  dW of the stem is then ONE K = positions GEMM with Kpad "input channels"
+// (mp_conv_wgrad_tc with a 1x1 filter) instead of KH*KW tap GEMMs over 16 zero-padded channels.  One thread = 8 patch elements.
+struct __align__(16) bf16x8 {
+  bf16 v[8];
+};
+__global__ void __launch_bounds__(256)
+k_im2col_rgb_split(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, int C, int H, int W, int KH, int KW,
+                   int stride, int Kpad, int64_t total_chunks) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_chunks) return;
+  const int Ho = H / stride, Wo = W / stride, chunks = Kpad >> 3;
+  const int j = (int)(t % chunks);
+  int64_t p = t / chunks;
+  const int wo = (int)(p % Wo); p /= Wo;
+  const int ho = (int)(p % Ho);
+  const int n = (int)(p / Ho);
+  const int Kreal = KH * KW * C;
+  const float* base = x + (int64_t)n * C * H * W;
+  bf16x8 h, l;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = j * 8 + e;
+    float v = 0.f;
+    if (k < Kreal) {
+      const int tap = k / C, c = k - tap * C;
+      const int kh = tap / KW, kw = tap - kh * KW;
+      const int y = ho * stride + kh - KH / 2, xx = wo * stride + kw - KW / 2;
+      if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(base + ((int64_t)c * H + y) * W + xx);
+    }
+    mp_split2(v, h.v[e], l.v[e]);
+  }
+  *reinterpret_cast<bf16x8*>(hi + t * 8) = h;
+  *reinterpret_cast<bf16x8*>(lo + t * 8) = l;
+}
+}  // namespace mpb200
+
+extern "C" int mp_im2col_rgb_split(const float* x, void* out_hi, void* out_lo, int N, int C, int H, int W, int KH, int KW, int stride,
+                                   int Kpad, void* stream) {
+  MP_REQUIRE(x && out_hi && out_lo, "mp_im2col_rgb_split: null pointer");
+  MP_REQUIRE(N > 0 && C > 0 && C <= 4 && H > 0 && W > 0 && KH % 2 == 1 && KW % 2 == 1 && (stride == 1 || stride == 2) &&
+             H % stride == 0 && W % stride == 0 && Kpad % 8 == 0 && Kpad >= KH * KW * C,
+             "mp_im2col_rgb_split: bad arguments");
+  const int64_t total = (int64_t)N * (H / stride) * (W / stride) * (Kpad / 8);
+  mpb200::k_im2col_rgb_split<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(x, (bf16*)out_hi, (bf16*)out_lo, C, H, W,
+                                                                                             KH, KW, stride, Kpad, total);
+  MP_LAUNCH_CHECK("mp_im2col_rgb_split");
+  return 0;
+}
+
 extern "C" int mp_pack_conv_weights(const float* w, void* out_hi, void* out_lo, int Cout, int Cin, int T, int rows_pad, int dgrad,
                                     void* stream) {
   MP_REQUIRE(w && out_hi && out_lo && Cout > 0 && Cin > 0 && T > 0, "mp_pack_conv_weights: bad arguments");

@@ -279,7 +279,7 @@ class DataParallelTrainer:
     `graph=True`: after `warmup` eager iterations the whole iteration -- forward, backward, the all-reduce and the optimizer step --
     is captured into ONE CUDA graph per input shape and replayed (at batch 1 the eager iteration is bound by the host enqueueing
     ~7 000 launches: 160-250 ms eager vs 77 ms replayed on one B200).  The optimizer must be capturable
-    (`torch.optim.AdamW(..., capturable=True)`), `loss_fn` must not synchronise, inputs are copied into static buffers."""
+    (`torch.optim.AdamW(..., capturable=True, fused=True)`: the fused variant also saves ~15 ms per iteration over the foreach one), `loss_fn` must not synchronise, inputs are copied into static buffers."""
 
     def __init__(self, gbase, optimizer_factory, loss_fn=None, group=None, graph: bool = False, warmup: int = 2,
                  n_buckets: int = 1):

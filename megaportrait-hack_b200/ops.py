@@ -814,8 +814,8 @@ def conv_weight_grad(x: Act, grad_out: Act, k: Tuple[int, int, int]) -> torch.Te
     One tensor-core GEMM per filter tap with K = positions (three bf16 passes, fp32 accumulation)."""
     N, D, H, W, Cin = x.shape
     Cout = grad_out.shape[-1]
-    if x.f32 is None or grad_out.f32 is None or tuple(grad_out.shape[:4]) != (N, D, H, W):
-        raise RuntimeError(f"conv_weight_grad: fp32 channels-last tensors of one spatial size, got {x.shape} / {grad_out.shape}")
+    if tuple(grad_out.shape[:4]) != (N, D, H, W) or (x.f32 is None and x.hi is None) or (grad_out.f32 is None and grad_out.hi is None):
+        raise RuntimeError(f"conv_weight_grad: channels-last tensors of one spatial size, got {x.shape} / {grad_out.shape}")
     kd, kh, kw = k
     dw = torch.empty((Cout, kd * kh * kw, Cin), dtype=torch.float32, device=x.device)
     L = _lib.load()
@@ -828,6 +828,9 @@ def conv_weight_grad(x: Act, grad_out: Act, k: Tuple[int, int, int]) -> torch.Te
             _lib.check(L.mp_conv_wgrad_tc(_p(x.hi), _p(x.lo), _p(grad_out.hi), _p(grad_out.lo), _p(dw), N, D, H, W, Cin, Cout,
                                           kd, kh, kw, _stream()), "mp_conv_wgrad_tc")
     else:
+        for t in (x, grad_out):                  # the mma.sync kernel reads fp32: rebuild it from the planes if need be
+            if t.f32 is None:
+                t.f32 = t.hi.float() + t.lo.float()
         _lib.check(L.mp_conv_wgrad(_p(x.f32), _p(grad_out.f32), _p(dw), N, D, H, W, Cin, Cout, kd, kh, kw, _stream()),
                    "mp_conv_wgrad")
     _count(2)
@@ -1057,6 +1060,66 @@ class UpsampleLinear2xFunction(torch.autograd.Function):
         return _cl_view(upsample2x_linear_backward(_to_cl_act(grad_out), ctx.up_d), ctx.nd)
 
 
+def im2col_rgb_split(x: torch.Tensor, kh: int, kw: int, stride: int) -> Act:
+    """NCHW fp32 [N, C <= 4, H, W] -> split-bf16 patch rows [N, 1, H/stride, W/stride, Kpad] (Kpad = kh*kw*C rounded up to 16)."""
+    _chk_cuda(x, torch.float32, "im2col_rgb_split")
+    N, C, H, W = x.shape
+    kpad = (kh * kw * C + 15) // 16 * 16
+    out = _alloc((N, 1, H // stride, W // stride, kpad), x.device, False, True)
+    L = _lib.load()
+    _lib.check(L.mp_im2col_rgb_split(_p(x), _p(out.hi), _p(out.lo), N, C, H, W, kh, kw, stride, kpad, _stream()),
+               "mp_im2col_rgb_split")
+    _count()
+    return out
+
+
+class RgbStemConvFunction(torch.autograd.Function):
+    """The RGB stem convolutions (Eapp 7x7, model.py:211; the stems of the three ResNets): `F.conv2d(x, w, b, stride, padding=k//2)`
+    with x [N, 3, H, W].  Forward: the tcgen05 kernel with the three channels zero-padded to 16 (as in inference).  Weight gradient:
+    instead of kh*kw tap GEMMs over 16 mostly-zero channels, the frame is unfolded into patch rows (`mp_im2col_rgb_split`,
+    kh*kw*3 -> Kpad columns) and dW is ONE K = positions GEMM on tcgen05 (`mp_conv_wgrad_tc`, 1x1 filter, Cin = Kpad) at the OUTPUT
+    resolution -- 7x7 @512^2: 1.36 ms -> ~0.2 ms; a stride-2 stem needs no zero-spread gradient.  The data gradient (only asked for
+    when the frame itself requires grad: `Gbase.motionEncoder(generated_frame)`, train.py:289) takes the generic path.
+    `groups` > 0 also returns the epilogue's normalisation statistics."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, groups):
+        x = x.detach().float().contiguous()
+        cout, cin, kh, kw = weight.shape
+        a = from_nchw_pad16(x)
+        wpad = _pad_channels(weight.detach().float(), 1, 16)
+        ctx.save_for_backward(x, weight.detach())
+        ctx.stride, ctx.has_bias = stride, bias is not None
+        out, stats = conv(a, pack_conv_train(wpad, bias), f32=True, stride=stride, stats_groups=groups)
+        if stats is None:
+            stats = torch.empty(0, dtype=torch.float64, device=x.device)
+        ctx.mark_non_differentiable(stats)
+        return _cl_view(out, 4), stats
+
+    @staticmethod
+    def backward(ctx, grad_out, _gstats):
+        x, weight = ctx.saved_tensors
+        cout, cin, kh, kw = weight.shape
+        g = _to_cl_act(grad_out)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[1]:
+            cols = im2col_rgb_split(x, kh, kw, ctx.stride)
+            dw = conv_weight_grad(cols, g, (1, 1, 1))                                   # [Cout, Kpad, 1, 1, 1]
+            gw = dw.reshape(cout, -1)[:, :kh * kw * cin].reshape(cout, kh, kw, cin).permute(0, 3, 1, 2).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = bias_grad(g)
+        if ctx.needs_input_grad[0]:
+            N, _, H, W = x.shape
+            if ctx.stride == 2:
+                up = torch.zeros((N, H, W, cout), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+                up[:, :, ::2, ::2] = grad_out
+                g = _to_cl_act(up)
+            ensure_split(g)
+            wpad = _pad_channels(weight.float(), 1, 16)
+            gx = _cl_view(conv_input_grad(g, pack_conv_train(wpad, None, dgrad=True)), 4)[:, :cin]
+        return gx, gw, gb, None, None
+
+
 def _pad_channels(t: torch.Tensor, dim: int, mult: int) -> torch.Tensor:
     c = t.shape[dim]
     extra = (-c) % mult
@@ -1080,6 +1143,10 @@ def conv_train(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     if stride not in (1, 2):
         raise RuntimeError(f"conv_train: stride {stride} is not supported")
     x = x.float()
+    if x.dim() == 4 and cin <= 4 and cout % 16 == 0 and WGRAD_TC and all(k % 2 == 1 for k in weight.shape[2:]) \
+            and x.shape[2] % stride == 0 and x.shape[3] % stride == 0:
+        y, stats = RgbStemConvFunction.apply(x, weight, bias, stride, stats_groups)      # RGB stem: im2col weight gradient
+        return (y, stats) if stats_groups else y
     if stride == 2 and all(k == 1 for k in weight.shape[2:]):
         x = x[:, :, ::2, ::2] if x.dim() == 4 else x[:, :, ::2, ::2, ::2]
         stride = 1

@@ -331,9 +331,19 @@ def blur_subsample(x, kernel2d, step):
 def conv_weight_grad(x, grad_out, k):
     kd, kh, kw = k
     Cin, Cout = x.shape[-1], grad_out.shape[-1]
-    gw = torch.nn.grad.conv3d_weight(_to_ncdhw(x.f32).double(), (Cout, Cin, kd, kh, kw), _to_ncdhw(grad_out.f32).double(),
+    gw = torch.nn.grad.conv3d_weight(_to_ncdhw(_val(x)).double(), (Cout, Cin, kd, kh, kw), _to_ncdhw(_val(grad_out)).double(),
                                      padding=(kd // 2, kh // 2, kw // 2))
     return gw.float()
+
+
+def im2col_rgb_split(x, kh, kw, stride):
+    N, C, H, W = x.shape
+    kpad = (kh * kw * C + 15) // 16 * 16
+    cols = F.unfold(x, (kh, kw), padding=(kh // 2, kw // 2), stride=stride)          # [N, C*kh*kw, L], channel-major
+    Ho, Wo = H // stride, W // stride
+    cols = cols.view(N, C, kh * kw, Ho, Wo).permute(0, 3, 4, 2, 1).reshape(N, 1, Ho, Wo, kh * kw * C)
+    cols = F.pad(cols, (0, kpad - kh * kw * C))
+    return _mk(cols.contiguous(), False, True)
 
 
 def bias_grad(grad_out):
@@ -380,7 +390,7 @@ def upsample2x_linear_backward(grad_out, up_d):
     return _mk(_to_cl(x.grad), True, False)
 
 
-_NAMES = ["upsample2x_linear_backward", "conv_weight_grad", "bias_grad", "group_norm_backward", "apply_warping_field_backward", "from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
+_NAMES = ["im2col_rgb_split", "upsample2x_linear_backward", "conv_weight_grad", "bias_grad", "group_norm_backward", "apply_warping_field_backward", "from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
           "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "from_nchw_pad16",
           "im2col3x3_f16", "stem3x3_relu_maxpool_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]
