@@ -27,7 +27,6 @@ def test_train_operators_vs_aten_autograd():
         x = torch.randn(xs, generator=g)
         w = torch.randn(ws, generator=g) * (1.0 / (ws[1] * ws[2] * ws[3]) ** 0.5)
         b = torch.randn(ws[0], generator=g)
-        go = torch.randn(1)  # placeholder
         xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
         y = ops.conv_train(xc, wc, bc, stride=stride)
         xd_, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
