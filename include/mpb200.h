@@ -268,6 +268,11 @@ int mp_upsample2x_linear_backward_cl(const float* grad_out, float* grad_in, int 
  * (kh*KW + kw)*C + c.  dW is then one mp_conv_wgrad_tc call with a 1x1 filter over Kpad "input channels". */
 int mp_im2col_rgb_split(const float* x, void* out_hi, void* out_lo, int N, int C, int H, int W, int KH, int KW, int stride, int Kpad,
                         void* stream);
+/* nn.MaxPool2d(3, stride 2, padding 1) of the ResNet stems for the training path (resnet.py:195, torchvision resnet50; row f-2),
+ * channels-last fp32: forward writes the maxima and, per element, the window position (kh*3+kw) of the first maximum in ATen's
+ * scan order (idx: one byte per output element); backward gathers grad_out through those positions (deterministic). */
+int mp_maxpool3x3s2_forward_idx(const float* in, float* out, void* idx, int N, int H, int W, int C, void* stream);
+int mp_maxpool3x3s2_backward(const float* grad_out, const void* idx, float* grad_in, int N, int H, int W, int C, void* stream);
 /* dL/dbias = column sums of dy [P, C] -> db [C] (overwritten). */
 int mp_bias_grad(const float* dy, float* db, int64_t P, int C, void* stream);
 /* nn.GroupNorm backward (model.py:302-316, 439-471) on channels-last fp32 tensors [N, S, C]: dx (fp32), dgamma / dbeta [C]

@@ -396,6 +396,100 @@ extern "C" int mp_im2col_rgb_split(const float* x, void* out_hi, void* out_lo, i
   return 0;
 }
 
+namespace mpb200 {
+// ---- nn.MaxPool2d(3, stride 2, padding 1) for the training path (row f-2; the stems of the three ResNets), channels-last fp32.
+// Forward: the maximum and the window position (kh * 3 + kw, 0..8) of the FIRST maximum in ATen's scan order (kh outer, kw inner,
+// strict >; a NaN wins, as in ATen).  Backward: a gather -- an input pixel lies in at most 2 x 2 windows; it receives a window's
+// gradient iff the stored position is its own (deterministic, no atomics).  One thread = one pixel x 4 channels.
+__global__ void __launch_bounds__(256)
+k_maxpool3x3s2_fwd_idx(const float* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ idx, int H, int W, int C,
+                       int64_t total) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int C4 = C >> 2, Ho = H >> 1, Wo = W >> 1;
+  const int c4 = (int)(t % C4);
+  int64_t p = t / C4;
+  const int wo = (int)(p % Wo); p /= Wo;
+  const int ho = (int)(p % Ho);
+  const int64_t n = p / Ho;
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int at[4] = {-1, -1, -1, -1};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int y = ho * 2 + a - 1;
+    if (y < 0 || y >= H) continue;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int x = wo * 2 + b - 1;
+      if (x < 0 || x >= W) continue;
+      const float4 v = *reinterpret_cast<const float4*>(in + ((n * H + y) * W + x) * C + c4 * 4);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (at[k] < 0 || e[k] > m[k] || e[k] != e[k]) { m[k] = e[k]; at[k] = a * 3 + b; }
+    }
+  }
+  *reinterpret_cast<float4*>(out + t * 4) = make_float4(m[0], m[1], m[2], m[3]);
+  *reinterpret_cast<uchar4*>(idx + t * 4) = make_uchar4((unsigned char)at[0], (unsigned char)at[1], (unsigned char)at[2],
+                                                        (unsigned char)at[3]);
+}
+
+__global__ void __launch_bounds__(256)
+k_maxpool3x3s2_bwd(const float* __restrict__ gout, const uint8_t* __restrict__ idx, float* __restrict__ gin, int H, int W, int C,
+                   int64_t total) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int C4 = C >> 2, Ho = H >> 1, Wo = W >> 1;
+  const int c4 = (int)(t % C4);
+  int64_t p = t / C4;
+  const int x = (int)(p % W); p /= W;
+  const int y = (int)(p % H);
+  const int64_t n = p / H;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int ho0 = y >> 1, ho1 = (y + 1) >> 1, wo0 = x >> 1, wo1 = (x + 1) >> 1;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int ho = a ? ho1 : ho0;
+    if ((a && ho1 == ho0) || ho >= Ho) continue;
+    const int kh = y - (2 * ho - 1);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int wo = b ? wo1 : wo0;
+      if ((b && wo1 == wo0) || wo >= Wo) continue;
+      const int me = kh * 3 + (x - (2 * wo - 1));
+      const int64_t o = ((n * Ho + ho) * Wo + wo) * C + c4 * 4;
+      const uchar4 at = *reinterpret_cast<const uchar4*>(idx + o);
+      const float4 g = *reinterpret_cast<const float4*>(gout + o);
+      if (at.x == me) acc[0] += g.x;
+      if (at.y == me) acc[1] += g.y;
+      if (at.z == me) acc[2] += g.z;
+      if (at.w == me) acc[3] += g.w;
+    }
+  }
+  *reinterpret_cast<float4*>(gin + t * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+}  // namespace mpb200
+
+extern "C" int mp_maxpool3x3s2_forward_idx(const float* in, float* out, void* idx, int N, int H, int W, int C, void* stream) {
+  MP_REQUIRE(in && out && idx, "mp_maxpool3x3s2_forward_idx: null pointer");
+  MP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "mp_maxpool3x3s2_forward_idx: bad dims");
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 4);
+  mpb200::k_maxpool3x3s2_fwd_idx<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(in, out, (uint8_t*)idx, H, W, C, total);
+  MP_LAUNCH_CHECK("mp_maxpool3x3s2_forward_idx");
+  return 0;
+}
+
+extern "C" int mp_maxpool3x3s2_backward(const float* grad_out, const void* idx, float* grad_in, int N, int H, int W, int C,
+                                        void* stream) {
+  MP_REQUIRE(grad_out && idx && grad_in, "mp_maxpool3x3s2_backward: null pointer");
+  MP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "mp_maxpool3x3s2_backward: bad dims");
+  const int64_t total = (int64_t)N * H * W * (C / 4);
+  mpb200::k_maxpool3x3s2_bwd<<<(unsigned)((total + 255) / 256), 256, 0, mp_stream(stream)>>>(grad_out, (const uint8_t*)idx, grad_in, H,
+                                                                                             W, C, total);
+  MP_LAUNCH_CHECK("mp_maxpool3x3s2_backward");
+  return 0;
+}
+
 extern "C" int mp_pack_conv_weights(const float* w, void* out_hi, void* out_lo, int Cout, int Cin, int T, int rows_pad, int dgrad,
                                     void* stream) {
   MP_REQUIRE(w && out_hi && out_lo && Cout > 0 && Cin > 0 && T > 0, "mp_pack_conv_weights: bad arguments");

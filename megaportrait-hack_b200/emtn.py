@@ -221,10 +221,15 @@ def resnet_block_autograd(blk: nn.Module, x: torch.Tensor) -> torch.Tensor:
 
 
 def resnet_trunk_autograd(conv1, bn1, maxpool, layers, x: torch.Tensor) -> torch.Tensor:
-    """Stem conv + BatchNorm + ReLU, the max-pool (ATen autograd), residual stages -- the differentiable form of `ResNetTrunkPlan`."""
+    """Stem conv + BatchNorm + ReLU, the max-pool, residual stages -- the differentiable form of `ResNetTrunkPlan`."""
     from . import ops
     x = torch.relu(ops.conv_bn_train(x, conv1, bn1))
-    x = F.max_pool2d(x, maxpool.kernel_size, maxpool.stride, maxpool.padding)
+    as_int = lambda v: v if isinstance(v, int) else (v[0] if len(set(v)) == 1 else -1)
+    if (as_int(maxpool.kernel_size), as_int(maxpool.stride), as_int(maxpool.padding)) == (3, 2, 1) and x.shape[1] % 4 == 0 \
+            and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and not getattr(maxpool, "ceil_mode", False):
+        x = ops.MaxPool3x3s2Function.apply(x)              # CUDA forward + backward (one byte of arg-max per output element)
+    else:
+        x = F.max_pool2d(x, maxpool.kernel_size, maxpool.stride, maxpool.padding)
     for layer in layers:
         for blk in layer:
             x = resnet_block_autograd(blk, x)

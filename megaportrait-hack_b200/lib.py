@@ -156,6 +156,8 @@ _SIGNATURES = {
     "mp_gs_brick_tune": (c_int, [POINTER(c_int), c_int]),
     "mp_conv_wgrad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_upsample2x_linear_backward_cl": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "mp_maxpool3x3s2_forward_idx": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "mp_maxpool3x3s2_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "mp_im2col_rgb_split": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_pack_conv_weights": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "mp_conv_wgrad_tc_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),

@@ -1120,6 +1120,44 @@ class RgbStemConvFunction(torch.autograd.Function):
         return gx, gw, gb, None, None
 
 
+def maxpool3x3s2_forward_idx(a: Act):
+    """nn.MaxPool2d(3, 2, 1) on a channels-last fp32 Act -> (Act, uint8 window positions of the maxima)."""
+    N, D, H, W, C = a.shape
+    out = _alloc((N, 1, H // 2, W // 2, C), a.device, True, False)
+    idx = torch.empty((N, 1, H // 2, W // 2, C), dtype=torch.uint8, device=a.device)
+    L = _lib.load()
+    _lib.check(L.mp_maxpool3x3s2_forward_idx(_p(a.f32), _p(out.f32), _p(idx), N, H, W, C, _stream()), "mp_maxpool3x3s2_forward_idx")
+    _count()
+    return out, idx
+
+
+def maxpool3x3s2_backward(grad_out: Act, idx: torch.Tensor) -> Act:
+    N, _, Ho, Wo, C = grad_out.shape
+    out = _alloc((N, 1, Ho * 2, Wo * 2, C), grad_out.device, True, False)
+    L = _lib.load()
+    _lib.check(L.mp_maxpool3x3s2_backward(_p(grad_out.f32), _p(idx), _p(out.f32), N, Ho * 2, Wo * 2, C, _stream()),
+               "mp_maxpool3x3s2_backward")
+    _count()
+    return out
+
+
+class MaxPool3x3s2Function(torch.autograd.Function):
+    """`nn.MaxPool2d(kernel_size=3, stride=2, padding=1)` (the ResNet stems) on libmpb200 with CUDA backward (row f-2): the forward
+    stores one byte per output element (which of the 9 window positions held the first maximum, ATen's rule), the backward is a
+    deterministic gather through them."""
+
+    @staticmethod
+    def forward(ctx, x):
+        out, idx = maxpool3x3s2_forward_idx(_to_cl_act(x))
+        ctx.save_for_backward(idx)
+        return _cl_view(out, 4)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        return _cl_view(maxpool3x3s2_backward(_to_cl_act(grad_out), idx), 4)
+
+
 def _pad_channels(t: torch.Tensor, dim: int, mult: int) -> torch.Tensor:
     c = t.shape[dim]
     extra = (-c) % mult

@@ -346,6 +346,20 @@ def im2col_rgb_split(x, kh, kw, stride):
     return _mk(cols.contiguous(), False, True)
 
 
+def maxpool3x3s2_forward_idx(a):
+    x = _to_ncdhw(a.f32).squeeze(2)
+    y, flat = F.max_pool2d(x, 3, 2, 1, return_indices=True)
+    return _mk(_to_cl(y.unsqueeze(2)), True, False), flat        # (test emulation: ATen's flat indices stand in for the bytes)
+
+
+def maxpool3x3s2_backward(grad_out, flat):
+    g = _to_ncdhw(grad_out.f32).squeeze(2)
+    shape = (g.shape[0], g.shape[1], g.shape[2] * 2, g.shape[3] * 2)
+    gin = torch.zeros(shape).reshape(shape[0], shape[1], -1).scatter_add(2, flat.reshape(shape[0], shape[1], -1),
+                                                                           g.reshape(shape[0], shape[1], -1)).reshape(shape)
+    return _mk(_to_cl(gin.unsqueeze(2)), True, False)
+
+
 def bias_grad(grad_out):
     return grad_out.f32.double().sum(dim=(0, 1, 2, 3)).float()
 
@@ -390,7 +404,7 @@ def upsample2x_linear_backward(grad_out, up_d):
     return _mk(_to_cl(x.grad), True, False)
 
 
-_NAMES = ["im2col_rgb_split", "upsample2x_linear_backward", "conv_weight_grad", "bias_grad", "group_norm_backward", "apply_warping_field_backward", "from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
+_NAMES = ["maxpool3x3s2_forward_idx", "maxpool3x3s2_backward", "im2col_rgb_split", "upsample2x_linear_backward", "conv_weight_grad", "bias_grad", "group_norm_backward", "apply_warping_field_backward", "from_nchw", "to_nchw", "ensure_split", "avgpool2", "upsample2x_linear", "upsample2x_bilinear_hq", "upsample_nearest", "new_stats",
           "gn_stats", "gn_finalize", "affine_act", "conv", "grid_sample3d", "apply_warping_field_ncdhw", "warp_field",
           "warp_fused", "blur_subsample", "maxpool3x3s2", "global_avgpool", "_alloc", "from_nchw_pad16",
           "im2col3x3_f16", "stem3x3_relu_maxpool_f16", "maxpool3x3s2_f16", "global_avgpool_f16", "gn_relu_conv3x3_head"]

@@ -120,8 +120,8 @@ def test_pack_conv_weights_kernel_matches_host_packing():
 
 def test_pool_and_resize_functions_vs_aten_autograd():
     """Row f-2: the pools / resizes between the blocks on libmpb200 -- `AvgPool2Function` (2-D and 3-D), `UpsampleNearestFunction`
-    ((2,2,2) and (1,2,2)), `UpsampleLinear2xFunction` (bilinear and trilinear, align_corners=True; backward = the deterministic
-    gather kernel) -- forward and input gradient against ATen on the same device: <= 1e-6 of abs-max."""
+    ((2,2,2) and (1,2,2)), `MaxPool3x3s2Function` (one byte of arg-max per output), `UpsampleLinear2xFunction` (bilinear and
+    trilinear, align_corners=True; backward = the deterministic gather kernel) -- forward and input gradient against ATen on the same device: <= 1e-6 of abs-max."""
     from megaportrait_hack_b200 import lib, ops
     lib.build()
     g = torch.Generator().manual_seed(9)
@@ -132,6 +132,7 @@ def test_pool_and_resize_functions_vs_aten_autograd():
          lambda x: F.interpolate(x, scale_factor=(2, 2, 2), mode="nearest")),
         ("near122", (2, 32, 16, 4, 4), lambda x: ops.UpsampleNearestFunction.apply(x, 1),
          lambda x: F.interpolate(x, scale_factor=(1, 2, 2), mode="nearest")),
+        ("maxpool", (2, 64, 34, 46), lambda x: ops.MaxPool3x3s2Function.apply(x), lambda x: F.max_pool2d(x, 3, 2, 1)),
         ("bilinear", (2, 64, 17, 24), lambda x: ops.UpsampleLinear2xFunction.apply(x),
          lambda x: F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)),
         ("bilinear_1px", (1, 16, 1, 5), lambda x: ops.UpsampleLinear2xFunction.apply(x),
