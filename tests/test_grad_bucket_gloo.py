@@ -60,3 +60,46 @@ def test_grad_bucket_all_reduce_world2(tmp_path, n_buckets):
     assert torch.allclose(f0, (l0 + l1) / 2, atol=1e-7) and torch.equal(f0, f1)      # one averaged gradient everywhere
     for a, b in zip(w0, w1):
         assert torch.equal(a, b)                                     # weights stay identical across ranks
+
+
+class _ToyG(torch.nn.Module):
+    """Stand-in with Gbase's calling convention: forward(xs, xd) -> (image, pyramids)."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Conv2d(3, 4, 3, padding=1)
+        self.b = torch.nn.Conv2d(4, 3, 3, padding=1)
+
+    def forward(self, xs, xd):
+        y = torch.sigmoid(self.b(torch.relu(self.a(xs + xd))))
+        return y, {"prediction_0.5": torch.nn.functional.avg_pool2d(y, 2)}
+
+
+def _trainer_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from megaportrait_hack_b200 import engine
+    torch.manual_seed(0)
+    net = _ToyG()
+    tr = engine.DataParallelTrainer(net, lambda ps: torch.optim.AdamW(ps, lr=1e-2), n_buckets=2,
+                                    loss_fn=lambda pred, pyr, xs, xd: (pred - xd).abs().mean() + pyr["prediction_0.5"].mean())
+    g = torch.Generator().manual_seed(10 + rank)
+    xs, xd = torch.rand(2, 3, 8, 8, generator=g), torch.rand(2, 3, 8, 8, generator=g)
+    losses = [float(tr.step(xs, xd)) for _ in range(4)]
+    torch.save((losses, [p.detach().clone() for p in net.parameters()]), os.path.join(out_dir, f"t{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_trainer_world2(tmp_path):
+    """engine.DataParallelTrainer (eager): two ranks with different data keep bit-identical weights and their losses fall."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_trainer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    (l0, w0), (l1, w1) = [torch.load(os.path.join(tmp_path, f"t{r}.pt")) for r in range(2)]
+    assert l0 != l1 and l0[-1] < l0[0] and l1[-1] < l1[0]
+    for a, b in zip(w0, w1):
+        assert torch.equal(a, b)
