@@ -186,7 +186,9 @@ def test_train_operators_on_emulated_kernels():
     from megaportrait_hack_b200 import ops
     g = torch.Generator().manual_seed(3)
     cases = [((2, 3, 16, 16), (8, 3, 7, 7), 1), ((2, 3, 16, 16), (8, 3, 7, 7), 2), ((1, 32, 12, 12), (3, 32, 3, 3), 1),
-             ((2, 16, 8, 8), (32, 16, 1, 1), 2), ((2, 16, 8, 8), (32, 16, 3, 3), 2), ((1, 16, 4, 6, 6), (16, 16, 3, 3, 3), 1)]
+             ((2, 16, 8, 8), (32, 16, 1, 1), 2), ((2, 16, 8, 8), (32, 16, 3, 3), 2), ((1, 16, 4, 6, 6), (16, 16, 3, 3, 3), 1),
+             # 64 output channels on an RGB frame: the im2col route of the stem weight gradient (ops.RgbStemConvFunction)
+             ((2, 3, 16, 16), (64, 3, 3, 3), 1), ((2, 3, 16, 16), (64, 3, 7, 7), 2)]
     with fake_ops.installed():
         for xs, ws, stride in cases:
             x = torch.randn(xs, generator=g, requires_grad=True)
